@@ -1,0 +1,97 @@
+"""ctypes binding of libader_b200.so (the C ABI declared in include/ader_b200.h).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc, and if that
+fails the import raises.  Every entry point returns an int status; non-zero raises
+``AderError`` carrying ``ader_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+ABI_VERSION = 1
+
+
+class AderError(RuntimeError):
+    pass
+
+
+class AderModel(C.Structure):
+    _fields_ = [("v_tab", C.c_int32), ("d", C.c_int32), ("maxlen", C.c_int32),
+                ("num_blocks", C.c_int32), ("num_heads", C.c_int32)]
+
+
+class AderLossArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("n_train", C.c_int32), ("n_ex", C.c_int32), ("V", C.c_int32),
+                ("V_prev", C.c_int32), ("mode", C.c_int32), ("lambda_", C.c_float),
+                ("pos", C.c_void_p), ("ex_pos", C.c_void_p), ("teacher", C.c_void_p),
+                ("teacher_row", C.c_void_p), ("teacher_ld", C.c_int64)]
+
+
+class AderAdamArgs(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("V", C.c_int32), ("ewc_lambda", C.c_float), ("fisher", C.c_void_p),
+                ("theta_star", C.c_void_p)]
+
+
+_P = C.c_void_p
+_MP = C.POINTER(AderModel)
+
+# name -> (restype, argtypes); mirrors include/ader_b200.h one to one (tests/test_abi.py checks
+# that every symbol declared in the header is exported and listed here).
+SIGNATURES = {
+    "ader_abi_version": (C.c_int32, []),
+    "ader_last_error": (C.c_char_p, []),
+    "ader_param_count": (C.c_int64, [_MP]),
+    "ader_param_offset": (C.c_int64, [_MP, C.c_int32]),
+    "ader_dense_count": (C.c_int64, [_MP]),
+    "ader_encoder_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
+    "ader_encoder_bwd_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
+    "ader_encoder_ws_slot": (C.c_int64, [_MP, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "ader_encoder_fwd": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_float, C.c_uint64, _P]),
+    "ader_encoder_bwd": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, C.c_uint64, _P]),
+    "ader_loss_ws_bytes": (C.c_size_t, [_MP, C.POINTER(AderLossArgs)]),
+    "ader_loss_fwd_bwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P]),
+    "ader_logits": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "ader_adam_step": (C.c_int32, [_MP, _P, _P, _P, _P, _P, C.POINTER(AderAdamArgs), _P]),
+    "ader_eval_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
+    "ader_eval_rank_topk": (C.c_int32, [_MP, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "ader_herding_ws_bytes": (C.c_size_t, [_MP, C.c_int32]),
+    "ader_herding_segmented": (C.c_int32, [_MP, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "ader_fisher_accumulate": (C.c_int32, [_MP, _P, _P, C.c_int32, _P]),
+    "ader_fisher_finalize": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P]),
+    "ader_gather_rows_i32": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the shared library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or (os.environ.get("ADER_B200_REBUILD") == "1"):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ader_abi_version() != ABI_VERSION:
+        raise AderError("libader_b200.so ABI %d != binding ABI %d" % (lib.ader_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ader_last_error().decode("utf-8", "replace")
+        raise AderError("%s failed (%d): %s" % (what or "libader_b200 call", rc, msg))

@@ -1,0 +1,99 @@
+// Shared host/device helpers for libader_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+#include "../../include/ader_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libader_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace ader {
+
+int fail(int code, const char* fmt, ...);
+
+#define ADER_CHECK_ARG(cond, ...) do { if (!(cond)) return ::ader::fail(-1, __VA_ARGS__); } while (0)
+#define ADER_CHECK_LAUNCH(name) do { cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return ::ader::fail(-3, "%s: %s", name, cudaGetErrorString(e__)); } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- flat parameter layout (EWC.py:90) ----------------------------------------
+struct Layout {
+  int v_tab, d, L, nb, nh;
+  long long off_table, off_pos, off_blocks, block_size, off_lnf, total;
+  // offsets inside one block
+  long long ln1b, ln1g, wq, bq, wk, bk, wv, bv, ln2b, ln2g, w1, b1, w2, b2;
+  __host__ __device__ long long block(int b) const { return off_blocks + (long long)b * block_size; }
+  long long dense_count() const { return total - off_pos; }
+};
+
+static inline Layout make_layout(const AderModel* m) {
+  Layout l;
+  l.v_tab = m->v_tab; l.d = m->d; l.L = m->maxlen; l.nb = m->num_blocks; l.nh = m->num_heads;
+  long long d = m->d, dd = d * d;
+  l.off_table = 0;
+  l.off_pos = (long long)m->v_tab * d;
+  l.off_blocks = l.off_pos + (long long)m->maxlen * d;
+  l.ln1b = 0; l.ln1g = d; l.wq = 2 * d; l.bq = 2 * d + dd; l.wk = 3 * d + dd; l.bk = 3 * d + 2 * dd;
+  l.wv = 4 * d + 2 * dd; l.bv = 4 * d + 3 * dd; l.ln2b = 5 * d + 3 * dd; l.ln2g = 6 * d + 3 * dd;
+  l.w1 = 7 * d + 3 * dd; l.b1 = 7 * d + 4 * dd; l.w2 = 8 * d + 4 * dd; l.b2 = 8 * d + 5 * dd;
+  l.block_size = 9 * d + 5 * dd;
+  l.off_lnf = l.off_blocks + (long long)m->num_blocks * l.block_size;
+  l.total = l.off_lnf + 2 * d;
+  return l;
+}
+
+static inline int check_model(const AderModel* m) {
+  if (!m) return fail(-1, "model is NULL");
+  if (m->d <= 0 || m->d > 256 || m->d % 2) return fail(-1, "hidden_units must be even and <= 256 (got %d)", m->d);
+  if (m->maxlen <= 0 || m->maxlen > 64) return fail(-1, "maxlen must be in 1..64 (got %d)", m->maxlen);
+  if (m->num_heads <= 0 || m->d % m->num_heads) return fail(-1, "num_heads must divide hidden_units");
+  if (m->num_blocks <= 0 || m->num_blocks > 8) return fail(-1, "num_blocks must be in 1..8");
+  if (m->v_tab < 2) return fail(-1, "v_tab must be >= 2");
+  return 0;
+}
+
+// ---- generic fp32 GEMM (sgemm.cu) ----------------------------------------------------------
+// C(m,n) = epilogue( sum_k A(m,k) * B(k,n) ), element (i,j) of X at X[i*rs + j*cs].
+struct GemmArgs {
+  const float* A; long long a_rs, a_cs;
+  const float* B; long long b_rs, b_cs;
+  float* C; long long c_rs, c_cs;
+  int M, N, K;
+  const int* dM;          // optional device override of M (token count)
+  const int* dK;          // optional device override of K
+  const float* bias;      // [N] added per column (or NULL)
+  const float* resid;     // [M,N] row-major (ld = resid_ld) added (or NULL)
+  long long resid_ld;
+  const float* relu_mask; // [M,N] row-major (ld = mask_ld): out *= (mask > 0)  (or NULL)
+  long long mask_ld;
+  int relu;               // out = max(out, 0)
+  int accumulate;         // C += out instead of C = out
+  float alpha;
+  int splits;             // split-K: grid.z; split z writes C + z*split_stride, k-range chunked
+  long long split_stride;
+  float* colsum;          // optional [N] (+ z*split_stride): column sums of B over this split's k-range
+  // dropout applied to the epilogue output (after relu), tf.layers.dropout semantics
+  float drop_p; uint64_t drop_seed; uint32_t drop_site;
+};
+void gemm_defaults(GemmArgs& g);
+int launch_gemm(const GemmArgs& g, cudaStream_t st);
+
+// ---- counter-based dropout mask (shared by fwd and bwd) -----------------------------------
+__host__ __device__ inline uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+// returns the multiplier (0 or 1/(1-p)) for element `idx` of dropout site `site`.
+__host__ __device__ inline float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)site << 40) + idx);
+  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+  return u < p ? 0.0f : 1.0f / (1.0f - p);
+}
+
+}  // namespace ader

@@ -1,0 +1,815 @@
+// SASRec encoder over PACKED real tokens (modules.py:23-271, ADER.py:25-85), forward and
+// backward, exact fp32.  Packing is exact w.r.t. the reference's dense-over-padding graph
+// (SURVEY A.1 / A.10): padded keys get exactly zero attention weight for real queries and
+// padded rows never reach `rep`, so only the T = sum(len) real tokens are computed.
+//
+// Layout in HBM: every activation is a [T, d] fp32 matrix in row order of (session row, position);
+// row r owns tokens row_off[r] .. row_off[r+1).  T lives on the device (row_off[M]) so the whole
+// step is stream-ordered with no host synchronisation; grids are sized for the capacity Tcap and
+// surplus CTAs exit at once.
+#include "common.cuh"
+
+namespace ader {
+
+constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
+constexpr int SPLITS = 16;        // split-K partials for weight / LN / bias gradients
+
+struct EncWs {
+  int *row_len, *row_off, *tok_row, *tok_id, *flags;
+  float* slot[8][NSLOT];           // [block][slot]
+  float *mean1[8], *rstd1[8], *mean2[8], *rstd2[8], *probs[8];
+  float* xfinal; float *meanf, *rstdf;
+  size_t bytes;
+};
+
+static EncWs carve_enc(const AderModel* m, int M, int Tcap, char* base) {
+  EncWs w; size_t o = 0;
+  auto take = [&](size_t n) { char* p = base ? base + o : nullptr; o += align_up(n); return p; };
+  const size_t d = m->d;
+  w.row_len = (int*)take(sizeof(int) * M);
+  w.row_off = (int*)take(sizeof(int) * (M + 1));
+  w.tok_row = (int*)take(sizeof(int) * Tcap);
+  w.tok_id  = (int*)take(sizeof(int) * Tcap);
+  w.flags   = (int*)take(sizeof(int) * 4);
+  for (int b = 0; b < m->num_blocks; ++b) {
+    for (int s = 0; s < NSLOT; ++s) w.slot[b][s] = (float*)take(sizeof(float) * Tcap * d);
+    w.mean1[b] = (float*)take(sizeof(float) * Tcap); w.rstd1[b] = (float*)take(sizeof(float) * Tcap);
+    w.mean2[b] = (float*)take(sizeof(float) * Tcap); w.rstd2[b] = (float*)take(sizeof(float) * Tcap);
+    w.probs[b] = (float*)take(sizeof(float) * (size_t)m->num_heads * Tcap * m->maxlen);
+  }
+  w.xfinal = (float*)take(sizeof(float) * Tcap * d);
+  w.meanf = (float*)take(sizeof(float) * M); w.rstdf = (float*)take(sizeof(float) * M);
+  w.bytes = o;
+  return w;
+}
+
+struct BwdWs {
+  float* g[11];          // gX, gXin, gO, gH, gZ, gY, gQ, gK, gV, gQ1, spare
+  float* partial;        // [SPLITS][dense_count]
+  int *keys[2], *vals[2], *hist;
+  size_t bytes;
+};
+static int sort_tiles(int Tcap) { return cdiv(Tcap, 2048); }
+static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
+  BwdWs w; size_t o = 0;
+  auto take = [&](size_t n) { char* p = base ? base + o : nullptr; o += align_up(n); return p; };
+  Layout l = make_layout(m);
+  for (int i = 0; i < 11; ++i) w.g[i] = (float*)take(sizeof(float) * (size_t)Tcap * m->d);
+  w.partial = (float*)take(sizeof(float) * (size_t)SPLITS * l.dense_count());
+  for (int i = 0; i < 2; ++i) { w.keys[i] = (int*)take(sizeof(int) * Tcap); w.vals[i] = (int*)take(sizeof(int) * Tcap); }
+  w.hist = (int*)take(sizeof(int) * 256 * (size_t)sort_tiles(Tcap));
+  w.bytes = o;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------
+__global__ void k_row_len(const int* __restrict__ ids, int M, int L, int* __restrict__ row_len) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  int c = 0;
+  for (int j = lane; j < L; j += 32) c += (ids[(long long)r * L + j] != 0);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) row_len[r] = c;
+}
+
+// single CTA exclusive scan; row_off[M] = T (clamped to Tcap, overflow flagged)
+__global__ void __launch_bounds__(1024) k_scan_rows(const int* __restrict__ row_len, int M, int Tcap,
+                                                    int* __restrict__ row_off, int* __restrict__ flags) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < M; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = (i < M) ? row_len[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int s = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      warp_sum[lane] = s;
+    }
+    __syncthreads();
+    int excl = carry + (wid ? warp_sum[wid - 1] : 0) + x - v;
+    if (i < M) row_off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int T = carry;
+    if (T > Tcap) { flags[0] = T; T = Tcap; }   // overflow: host checks flags[0] lazily
+    row_off[M] = T;
+  }
+}
+
+__global__ void k_fill_tok(const int* __restrict__ ids, const int* __restrict__ row_len,
+                           const int* __restrict__ row_off, int M, int L, int Tcap,
+                           int* __restrict__ tok_row, int* __restrict__ tok_id) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  int n = row_len[r], off = row_off[r];
+  for (int i = lane; i < n; i += 32) {
+    if (off + i < Tcap) {
+      tok_row[off + i] = r;
+      tok_id[off + i] = ids[(long long)r * L + (L - n + i)];   // real tokens are the suffix (util.py:161-169)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding: x = (E0[id]*sqrt(d) + P[pos]) * dropout     (modules.py:124-130, ADER.py:41-60)
+// ------------------------------------------------------------------------------------------
+__global__ void k_embed(const float* __restrict__ table, const float* __restrict__ pos_table,
+                        const int* __restrict__ tok_row, const int* __restrict__ tok_id,
+                        const int* __restrict__ row_len, const int* __restrict__ row_off,
+                        const int* __restrict__ dT, int d, int L, float sqrt_d,
+                        float drop_p, uint64_t seed, float* __restrict__ x) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int T = *dT;
+  if (e >= (long long)T * d) return;
+  int t = (int)(e / d), c = (int)(e % d);
+  int r = tok_row[t];
+  int p = L - row_len[r] + (t - row_off[r]);
+  int id = tok_id[t];
+  float v = table[(long long)id * d + c] * sqrt_d + pos_table[p * d + c];
+  if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)e, drop_p);
+  x[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (modules.py:44-48): population variance, eps inside the sqrt.  Warp per token.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_MAXE = 8;  // d <= 256
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void ln_row_fwd(const float* __restrict__ x, float* __restrict__ out,
+                                           const float* __restrict__ beta, const float* __restrict__ gamma,
+                                           int d, int lane, float& mean_o, float& rstd_o) {
+  float v[LN_MAXE]; float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) { int c = lane + 32 * i; v[i] = (c < d) ? x[c] : 0.f; s += v[i]; }
+  float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) { int c = lane + 32 * i; if (c < d) { float t = v[i] - mean; q += t * t; } }
+  float var = warp_sum(q) / (float)d;
+  float rstd = 1.0f / sqrtf(var + 1e-8f);
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) { int c = lane + 32 * i; if (c < d) out[c] = gamma[c] * ((v[i] - mean) * rstd) + beta[c]; }
+  mean_o = mean; rstd_o = rstd;
+}
+
+__global__ void k_ln_fwd(const float* __restrict__ x, float* __restrict__ out, float* __restrict__ mean,
+                         float* __restrict__ rstd, const float* __restrict__ beta,
+                         const float* __restrict__ gamma, const int* __restrict__ dT, int d) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= *dT) return;
+  float mu, rs;
+  ln_row_fwd(x + (long long)t * d, out + (long long)t * d, beta, gamma, d, lane, mu, rs);
+  if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+}
+
+// final LN on the last token of every row only (ADER.py:82-85): rep[r] = LN(x[last(r)])
+__global__ void k_ln_last_fwd(const float* __restrict__ x, const int* __restrict__ row_len,
+                              const int* __restrict__ row_off, int M, float* __restrict__ rep,
+                              float* __restrict__ mean, float* __restrict__ rstd,
+                              const float* __restrict__ beta, const float* __restrict__ gamma, int d) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  int n = row_len[r];
+  if (n == 0) {   // empty row (no usable session): defined as zeros, carries no gradient
+    for (int c = lane; c < d; c += 32) rep[(long long)r * d + c] = 0.f;
+    if (lane == 0) { mean[r] = 0.f; rstd[r] = 0.f; }
+    return;
+  }
+  int t = row_off[r] + n - 1;
+  float mu, rs;
+  ln_row_fwd(x + (long long)t * d, rep + (long long)r * d, beta, gamma, d, lane, mu, rs);
+  if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+}
+
+// dx (+)= LN backward.  g = dout*gamma; dx = rstd*(g - mean(g) - xhat*mean(g*xhat))
+__device__ __forceinline__ void ln_row_bwd(const float* __restrict__ dout, const float* __restrict__ x,
+                                           float mean, float rstd, const float* __restrict__ gamma,
+                                           float* __restrict__ dx, int d, int lane, bool accumulate) {
+  float g[LN_MAXE], xh[LN_MAXE]; float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) {
+    int c = lane + 32 * i;
+    if (c < d) { xh[i] = (x[c] - mean) * rstd; g[i] = dout[c] * gamma[c]; s1 += g[i]; s2 += g[i] * xh[i]; }
+    else { xh[i] = 0.f; g[i] = 0.f; }
+  }
+  s1 = warp_sum(s1) / (float)d; s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+  for (int i = 0; i < LN_MAXE; ++i) {
+    int c = lane + 32 * i;
+    if (c < d) { float v = rstd * (g[i] - s1 - xh[i] * s2); dx[c] = accumulate ? dx[c] + v : v; }
+  }
+}
+
+__global__ void k_ln_bwd(const float* __restrict__ dout, const float* __restrict__ x,
+                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, float* __restrict__ dx,
+                         const int* __restrict__ dT, int d, int accumulate) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= *dT) return;
+  long long o = (long long)t * d;
+  ln_row_bwd(dout + o, x + o, mean[t], rstd[t], gamma, dx + o, d, lane, accumulate != 0);
+}
+
+// gX[t] = LNf backward of d_rep[row] when t is the last token of its row, else 0.
+__global__ void k_lnf_bwd(const float* __restrict__ d_rep, const float* __restrict__ x,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ gamma, const int* __restrict__ tok_row,
+                          const int* __restrict__ row_off, float* __restrict__ gx,
+                          const int* __restrict__ dT, int d) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= *dT) return;
+  int r = tok_row[t];
+  long long o = (long long)t * d;
+  if (t != row_off[r + 1] - 1) { for (int c = lane; c < d; c += 32) gx[o + c] = 0.f; return; }
+  ln_row_bwd(d_rep + (long long)r * d, x + o, mean[r], rstd[r], gamma, gx + o, d, lane, false);
+}
+
+// partial LN parameter gradients: dbeta[c] = sum_t dout[t,c]; dgamma[c] = sum_t dout[t,c]*xhat[t,c]
+// split s sums tokens [s*chunk, (s+1)*chunk) sequentially -> deterministic.
+// rows != nullptr: "last token" mode (dout indexed by row, x by last token of the row, count = M).
+__global__ void k_ln_param_grad(const float* __restrict__ dout, const float* __restrict__ x,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const int* __restrict__ dT, int count_host,
+                                const int* __restrict__ row_len, const int* __restrict__ row_off,
+                                int d, float* __restrict__ pbeta, float* __restrict__ pgamma,
+                                long long split_stride) {
+  const int c = threadIdx.x;
+  const int s = blockIdx.x;
+  const int count = row_off ? count_host : *dT;
+  const int chunk = (count + gridDim.x - 1) / gridDim.x;
+  const int lo = s * chunk, hi = min(count, lo + chunk);
+  if (c >= d) return;
+  float sb = 0.f, sg = 0.f;
+  for (int i = lo; i < hi; ++i) {
+    long long xo, go; float mu, rs;
+    if (row_off) {
+      if (row_len[i] == 0) continue;
+      xo = (long long)(row_off[i + 1] - 1) * d; go = (long long)i * d; mu = mean[i]; rs = rstd[i];
+    } else { xo = go = (long long)i * d; mu = mean[i]; rs = rstd[i]; }
+    float g = dout[go + c];
+    sb += g; sg += g * ((x[xo + c] - mu) * rs);
+  }
+  pbeta[(long long)s * split_stride + c] = sb;
+  pgamma[(long long)s * split_stride + c] = sg;
+}
+
+// ------------------------------------------------------------------------------------------
+// causal self-attention per session row (modules.py:177-223).  CTA per row, 4 warps.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K,
+                                                  const float* __restrict__ V, const float* __restrict__ Q1,
+                                                  const int* __restrict__ row_len, const int* __restrict__ row_off,
+                                                  int d, int nh, int L, int Tcap, float drop_p, uint64_t seed,
+                                                  uint32_t site, float* __restrict__ probs, float* __restrict__ Y) {
+  extern __shared__ float sm[];
+  const int r = blockIdx.x;
+  const int n = row_len[r];
+  if (n == 0) return;
+  const int off = row_off[r];
+  const int ld = d + 1;
+  float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* ps = Vs + L * ld;  // ps [4][64]
+  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
+    int i = idx / d, c = idx % d; long long g = (long long)(off + i) * d + c;
+    Qs[i * ld + c] = Q[g]; Ks[i * ld + c] = K[g]; Vs[i * ld + c] = V[g];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int dh = d / nh;
+  const float denom = sqrtf((float)dh);
+  float* pw = ps + warp * 64;
+  for (int h = 0; h < nh; ++h) {
+    const int hc = h * dh;
+    for (int i = warp; i < n; i += 4) {
+      float s[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int j = lane + 32 * u;
+        float acc = -INFINITY;
+        if (j <= i) {
+          acc = 0.f;
+          for (int k = 0; k < dh; ++k) acc = fmaf(Qs[i * ld + hc + k], Ks[j * ld + hc + k], acc);
+          acc = acc / denom;
+        }
+        s[u] = acc;
+      }
+      float mx = warp_max(fmaxf(s[0], s[1]));
+      float e0 = (lane <= i) ? expf(s[0] - mx) : 0.f;
+      float e1 = (lane + 32 <= i) ? expf(s[1] - mx) : 0.f;
+      float sum = warp_sum(e0 + e1);
+      float p[2] = {e0 / sum, e1 / sum};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int j = lane + 32 * u;
+        if (j < L) {
+          long long po = ((long long)h * Tcap + off + i) * L + j;
+          probs[po] = p[u];
+          float pd = p[u];
+          if (drop_p > 0.f) pd *= drop_scale(seed, site, (uint64_t)po, drop_p);
+          pw[j] = pd;
+        }
+      }
+      __syncwarp();
+      for (int c = lane; c < dh; c += 32) {
+        float acc = 0.f;
+        for (int j = 0; j <= i; ++j) acc = fmaf(pw[j], Vs[j * ld + hc + c], acc);
+        long long g = (long long)(off + i) * d + hc + c;
+        Y[g] = acc + Q1[g];                       // residual on the NORMALISED queries (modules.py:223)
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K,
+                                                  const float* __restrict__ V, const float* __restrict__ probs,
+                                                  const float* __restrict__ gY, const int* __restrict__ row_len,
+                                                  const int* __restrict__ row_off, int d, int nh, int L, int Tcap,
+                                                  float drop_p, uint64_t seed, uint32_t site,
+                                                  float* __restrict__ gQ, float* __restrict__ gK,
+                                                  float* __restrict__ gV) {
+  extern __shared__ float sm[];
+  const int r = blockIdx.x;
+  const int n = row_len[r];
+  if (n == 0) return;
+  const int off = row_off[r];
+  const int ld = d + 1, lp = L + 1;
+  float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* Gs = Vs + L * ld;
+  float* dSs = Gs + L * ld; float* Pds = dSs + L * lp;
+  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
+    int i = idx / d, c = idx % d; long long g = (long long)(off + i) * d + c;
+    Qs[i * ld + c] = Q[g]; Ks[i * ld + c] = K[g]; Vs[i * ld + c] = V[g]; Gs[i * ld + c] = gY[g];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int dh = d / nh;
+  const float denom = sqrtf((float)dh);
+  for (int h = 0; h < nh; ++h) {
+    const int hc = h * dh;
+    for (int i = warp; i < n; i += 4) {
+      float P[2], dP[2], scl[2];
+      float rowdot = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int j = lane + 32 * u;
+        P[u] = 0.f; dP[u] = 0.f; scl[u] = 1.f;
+        if (j <= i) {
+          long long po = ((long long)h * Tcap + off + i) * L + j;
+          P[u] = probs[po];
+          if (drop_p > 0.f) scl[u] = drop_scale(seed, site, (uint64_t)po, drop_p);
+          float acc = 0.f;
+          for (int k = 0; k < dh; ++k) acc = fmaf(Gs[i * ld + hc + k], Vs[j * ld + hc + k], acc);
+          dP[u] = acc * scl[u];
+          rowdot += dP[u] * P[u];
+        }
+      }
+      rowdot = warp_sum(rowdot);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int j = lane + 32 * u;
+        if (j < L) {
+          dSs[i * lp + j] = (j <= i) ? P[u] * (dP[u] - rowdot) / denom : 0.f;
+          Pds[i * lp + j] = (j <= i) ? P[u] * scl[u] : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += 4) {
+      for (int c = lane; c < dh; c += 32) {
+        float aq = 0.f;
+        for (int j = 0; j <= i; ++j) aq = fmaf(dSs[i * lp + j], Ks[j * ld + hc + c], aq);
+        gQ[(long long)(off + i) * d + hc + c] = aq;
+        float ak = 0.f, av = 0.f;   // here "i" plays the role of the key index j
+        for (int q = i; q < n; ++q) {
+          ak = fmaf(dSs[q * lp + i], Qs[q * ld + hc + c], ak);
+          av = fmaf(Pds[q * lp + i], Gs[q * ld + hc + c], av);
+        }
+        gK[(long long)(off + i) * d + hc + c] = ak;
+        gV[(long long)(off + i) * d + hc + c] = av;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small elementwise helpers
+// ------------------------------------------------------------------------------------------
+// out[e] = in[e] * dropmask(site, e)   (gradient of an output-dropout site)
+__global__ void k_apply_drop(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ dT,
+                             int d, float p, uint64_t seed, uint32_t site) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)(*dT) * d) return;
+  out[e] = in[e] * drop_scale(seed, site, (uint64_t)e, p);
+}
+
+// grad_dense[i] = sum_s partial[s][i] for i in [lo, hi)
+__global__ void k_reduce_partials(const float* __restrict__ partial, long long stride, int splits,
+                                  long long lo, long long hi, float* __restrict__ out) {
+  long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(long long)k * stride + i];
+  out[i] = s;
+}
+
+// position-table gradient: dP[p,c] = sum over rows having position p of dx0[token(r,p), c]
+__global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__ row_len,
+                           const int* __restrict__ row_off, int M, int L, int d,
+                           float drop_p, uint64_t seed, float* __restrict__ gpos) {
+  const int p = blockIdx.x, c = threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int r = 0; r < M; ++r) {
+    int n = row_len[r];
+    if (n >= L - p) {
+      long long e = (long long)(row_off[r] + p - (L - n)) * d + c;
+      float v = gx[e];
+      if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)e, drop_p);
+      s += v;
+    }
+  }
+  gpos[p * d + c] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding-gradient scatter (subsystem 3): stable LSD radix sort of (item id, token) + warp
+// segmented reduction.  No float atomics; every table row is summed in token order by one warp.
+// ------------------------------------------------------------------------------------------
+constexpr int SORT_TILE = 2048;
+
+__global__ void __launch_bounds__(256) k_sort_hist(const int* __restrict__ keys, const int* __restrict__ dT,
+                                                   int shift, int ntiles, int* __restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int T = *dT;
+  const int base = blockIdx.x * SORT_TILE;
+  for (int r = 0; r < SORT_TILE / 256; ++r) {
+    int i = base + r * 256 + threadIdx.x;
+    if (i < T) atomicAdd(&h[(keys[i] >> shift) & 255], 1);     // integer atomics: order-independent result
+  }
+  __syncthreads();
+  hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of hist (digit-major) in place; single CTA
+__global__ void __launch_bounds__(1024) k_sort_scan(int* __restrict__ hist, int n) {
+  __shared__ int warp_sum_s[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = (i < n) ? hist[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sum_s[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int s = warp_sum_s[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      warp_sum_s[lane] = s;
+    }
+    __syncthreads();
+    int excl = carry + (wid ? warp_sum_s[wid - 1] : 0) + x - v;
+    if (i < n) hist[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ keys_in, const int* __restrict__ vals_in,
+                                                      const int* __restrict__ dT, int shift, int ntiles,
+                                                      const int* __restrict__ hist, int first_pass,
+                                                      int* __restrict__ keys_out, int* __restrict__ vals_out) {
+  __shared__ int running[256];
+  __shared__ int cnt[8][256];
+  const int T = *dT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  running[tid] = hist[tid * ntiles + blockIdx.x];
+  const int base = blockIdx.x * SORT_TILE;
+  for (int r = 0; r < SORT_TILE / 256; ++r) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) cnt[w][tid] = 0;
+    __syncthreads();
+    int i = base + r * 256 + tid;
+    bool valid = i < T;
+    int key = valid ? keys_in[i] : 0;
+    int val = valid ? (first_pass ? i : vals_in[i]) : 0;
+    int digit = valid ? ((key >> shift) & 255) : 256 + lane;      // invalid lanes match nobody
+    unsigned mask = __match_any_sync(0xffffffffu, digit);
+    int rank_in_warp = __popc(mask & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0) cnt[warp][digit] = __popc(mask);
+    __syncthreads();
+    if (valid) {
+      int pre = 0;
+      for (int w = 0; w < warp; ++w) pre += cnt[w][digit];
+      int dst = running[digit] + pre + rank_in_warp;
+      keys_out[dst] = key; vals_out[dst] = val;
+    }
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += cnt[w][tid];
+    running[tid] += tot;
+    __syncthreads();
+  }
+}
+
+// warp per CH sorted positions; the warp owning a segment head sums the whole segment.
+__global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys, const int* __restrict__ vals,
+                                                    const int* __restrict__ dT, const float* __restrict__ gx,
+                                                    int d, float scale, float drop_p, uint64_t seed,
+                                                    float* __restrict__ gtable) {
+  constexpr int CH = 4;
+  const int T = *dT;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int p0 = w * CH;
+  if (p0 >= T) return;
+  for (int p = p0; p < min(T, p0 + CH); ++p) {
+    int key = keys[p];
+    if (p > 0 && keys[p - 1] == key) continue;        // not a head
+    float acc[LN_MAXE];
+#pragma unroll
+    for (int i = 0; i < LN_MAXE; ++i) acc[i] = 0.f;
+    for (int q = p; q < T && keys[q] == key; ++q) {
+      long long o = (long long)vals[q] * d;
+#pragma unroll
+      for (int i = 0; i < LN_MAXE; ++i) {
+        int c = lane + 32 * i;
+        if (c < d) {
+          float v = gx[o + c];
+          if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)(o + c), drop_p);
+          acc[i] += v;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAXE; ++i) {
+      int c = lane + 32 * i;
+      if (c < d) gtable[(long long)key * d + c] += scale * acc[i];
+    }
+  }
+}
+
+static int key_bits(int v_tab) { int b = 1; while ((1LL << b) < v_tab) ++b; return b; }
+
+// ------------------------------------------------------------------------------------------
+// group entry points
+// ------------------------------------------------------------------------------------------
+static int run_dense(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
+                     int Tcap, const int* dT, int d, bool transW, int relu, const float* resid,
+                     const float* relu_mask, int accumulate, float alpha,
+                     float drop_p, uint64_t seed, uint32_t site) {
+  GemmArgs g; gemm_defaults(g);
+  g.A = A; g.a_rs = d; g.a_cs = 1;
+  g.B = W; if (!transW) { g.b_rs = d; g.b_cs = 1; } else { g.b_rs = 1; g.b_cs = d; }
+  g.C = C; g.c_rs = d; g.c_cs = 1;
+  g.M = Tcap; g.N = d; g.K = d; g.dM = dT;
+  g.bias = bias; g.resid = resid; g.resid_ld = d; g.relu_mask = relu_mask; g.mask_ld = d;
+  g.relu = relu; g.accumulate = accumulate; g.alpha = alpha;
+  g.drop_p = drop_p; g.drop_seed = seed; g.drop_site = site;
+  return launch_gemm(g, st);
+}
+
+// dW partial[s] = act^T . grad over token split s, db partial[s] = colsum(grad)
+static int run_wgrad(cudaStream_t st, const float* act, const float* grad, float* pW, float* pb,
+                     long long split_stride, int Tcap, const int* dT, int d) {
+  GemmArgs g; gemm_defaults(g);
+  g.A = act; g.a_rs = 1; g.a_cs = d;       // A(m=c_in, k=t) = act[t*d + c_in]
+  g.B = grad; g.b_rs = d; g.b_cs = 1;      // B(k=t, n=c_out)
+  g.C = pW; g.c_rs = d; g.c_cs = 1;
+  g.M = d; g.N = d; g.K = Tcap; g.dK = dT;
+  g.splits = SPLITS; g.split_stride = split_stride; g.colsum = pb;
+  return launch_gemm(g, st);
+}
+
+}  // namespace ader
+
+using namespace ader;
+
+extern "C" size_t ader_encoder_ws_bytes(const AderModel* m, int32_t M, int32_t Tcap) {
+  if (check_model(m) || M <= 0 || Tcap <= 0) return 0;
+  return carve_enc(m, M, Tcap, nullptr).bytes;
+}
+extern "C" size_t ader_encoder_bwd_ws_bytes(const AderModel* m, int32_t M, int32_t Tcap) {
+  if (check_model(m) || M <= 0 || Tcap <= 0) return 0;
+  return carve_bwd(m, M, Tcap, nullptr).bytes;
+}
+extern "C" int64_t ader_encoder_ws_slot(const AderModel* m, int32_t M, int32_t Tcap, int32_t slot, int32_t block) {
+  if (check_model(m) || M <= 0 || Tcap <= 0 || block < 0 || block >= m->num_blocks) return -1;
+  EncWs w = carve_enc(m, M, Tcap, (char*)0x1000);   // fake base to turn pointers into offsets
+  const char* base = (const char*)0x1000;
+  auto off = [&](const void* p) { return (int64_t)((const char*)p - base); };
+  switch (slot) {
+    case -1: return off(w.row_len);
+    case -2: return off(w.row_off);
+    case -3: return off(w.tok_row);
+    case -4: return off(w.flags);
+    case 8: return off(w.xfinal);
+    case 9: return off(w.probs[block]);
+    default:
+      if (slot >= 0 && slot < NSLOT) return off(w.slot[block][slot]);
+  }
+  return -1;
+}
+
+extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                                    int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
+                                    void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && ids && ws && rep, "encoder_fwd: NULL pointer");
+  ADER_CHECK_ARG(M > 0 && Tcap > 0 && (long long)Tcap <= (long long)M * m->maxlen, "encoder_fwd: bad M/Tcap (%d, %d)", M, Tcap);
+  ADER_CHECK_ARG(dropout_rate >= 0.f && dropout_rate < 1.f, "encoder_fwd: dropout_rate out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(m);
+  const int d = m->d, L = m->maxlen;
+  EncWs w = carve_enc(m, M, Tcap, (char*)ws);
+  const int* dT = w.row_off + M;
+
+  cudaMemsetAsync(w.flags, 0, sizeof(int) * 4, st);
+  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
+  k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
+  k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
+  k_embed<<<cdiv((long long)Tcap * d, 256), 256, 0, st>>>(theta + l.off_table, theta + l.off_pos, w.tok_row, w.tok_id,
+                                                           w.row_len, w.row_off, dT, d, L, sqrtf((float)d),
+                                                           dropout_rate, seed, w.slot[0][0]);
+  ADER_CHECK_LAUNCH("encoder_fwd/pack+embed");
+
+  const size_t attn_smem = sizeof(float) * (3 * (size_t)L * (d + 1) + 4 * 64);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  ADER_CHECK_ARG(attn_smem <= 200 * 1024, "encoder_fwd: attention tile does not fit shared memory");
+  const int ln_grid = cdiv((long long)Tcap * 32, 256);
+
+  for (int b = 0; b < m->num_blocks; ++b) {
+    const float* P = theta + l.block(b);
+    float* X = w.slot[b][0]; float* Q1 = w.slot[b][1]; float* Qp = w.slot[b][2]; float* Kp = w.slot[b][3];
+    float* Vp = w.slot[b][4]; float* Y = w.slot[b][5]; float* Z = w.slot[b][6]; float* H = w.slot[b][7];
+    float* Xn = (b + 1 < m->num_blocks) ? w.slot[b + 1][0] : w.xfinal;
+    k_ln_fwd<<<ln_grid, 256, 0, st>>>(X, Q1, w.mean1[b], w.rstd1[b], P + l.ln1b, P + l.ln1g, dT, d);
+    if (int e = run_dense(st, Q1, P + l.wq, P + l.bq, Qp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    if (int e = run_dense(st, X, P + l.wk, P + l.bk, Kp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    if (int e = run_dense(st, X, P + l.wv, P + l.bv, Vp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    k_attn_fwd<<<M, 128, attn_smem, st>>>(Qp, Kp, Vp, Q1, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
+                                          dropout_rate, seed, 1u + 3u * b, w.probs[b], Y);
+    k_ln_fwd<<<ln_grid, 256, 0, st>>>(Y, Z, w.mean2[b], w.rstd2[b], P + l.ln2b, P + l.ln2g, dT, d);
+    if (int e = run_dense(st, Z, P + l.w1, P + l.b1, H, Tcap, dT, d, false, 1, nullptr, nullptr, 0, 1.f,
+                          dropout_rate, seed, 2u + 3u * b)) return e;
+    if (int e = run_dense(st, H, P + l.w2, P + l.b2, Xn, Tcap, dT, d, false, 0, Z, nullptr, 0, 1.f,
+                          dropout_rate, seed, 3u + 3u * b)) return e;
+    ADER_CHECK_LAUNCH("encoder_fwd/block");
+  }
+  k_ln_last_fwd<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.xfinal, w.row_len, w.row_off, M, rep, w.meanf, w.rstdf,
+                                                               theta + l.off_lnf, theta + l.off_lnf + d, d);
+  ADER_CHECK_LAUNCH("encoder_fwd/final_ln");
+  return 0;
+}
+
+extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                                    int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
+                                    float dropout_rate, uint64_t seed, void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && ids && ws && bwd_ws && d_rep && grad, "encoder_bwd: NULL pointer");
+  ADER_CHECK_ARG(M > 0 && Tcap > 0, "encoder_bwd: bad M/Tcap");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(m);
+  const int d = m->d, L = m->maxlen;
+  const float p = dropout_rate;
+  EncWs w = carve_enc(m, M, Tcap, (char*)ws);
+  BwdWs g = carve_bwd(m, M, Tcap, (char*)bwd_ws);
+  const int* dT = w.row_off + M;
+  const long long PS = l.dense_count();                 // split stride of the partial workspace
+  auto part = [&](long long param_off) { return g.partial + (param_off - l.off_pos); };
+  float *gX = g.g[0], *gXin = g.g[1], *gO = g.g[2], *gH = g.g[3], *gZ = g.g[4], *gY = g.g[5],
+        *gQ = g.g[6], *gK = g.g[7], *gV = g.g[8], *gQ1 = g.g[9];
+  const int ln_grid = cdiv((long long)Tcap * 32, 256);
+  const int el_grid = cdiv((long long)Tcap * d, 256);
+  const int ln_threads = ((d + 31) / 32) * 32;
+
+  const size_t attn_smem = sizeof(float) * (4 * (size_t)L * (d + 1) + 2 * (size_t)L * (L + 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  ADER_CHECK_ARG(attn_smem <= 220 * 1024, "encoder_bwd: attention tile does not fit shared memory");
+
+  // final LayerNorm (ADER.py:82): only the last token of each row carries gradient
+  k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, gX, dT, d);
+  k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+                                                 part(l.off_lnf), part(l.off_lnf + d), PS);
+  ADER_CHECK_LAUNCH("encoder_bwd/final_ln");
+
+  for (int b = m->num_blocks - 1; b >= 0; --b) {
+    const long long bo = l.block(b);
+    const float* P = theta + bo;
+    const float* X = w.slot[b][0]; const float* Q1 = w.slot[b][1]; const float* Qp = w.slot[b][2];
+    const float* Kp = w.slot[b][3]; const float* Vp = w.slot[b][4]; const float* Y = w.slot[b][5];
+    const float* Z = w.slot[b][6]; const float* H = w.slot[b][7];
+    const float* gOut = gX;
+    if (p > 0.f) {   // x_out = drop(h.W2 + b2) + z  (modules.py:259-266)
+      k_apply_drop<<<el_grid, 256, 0, st>>>(gX, gO, dT, d, p, seed, 3u + 3u * b);
+      gOut = gO;
+    }
+    if (int e = run_wgrad(st, H, gOut, part(bo + l.w2), part(bo + l.b2), PS, Tcap, dT, d)) return e;
+    // gH = (gOut . W2^T) * [h > 0] * 1/(1-p)   (h is stored post-dropout)
+    if (int e = run_dense(st, gOut, P + l.w2, nullptr, gH, Tcap, dT, d, true, 0, nullptr, H, 0,
+                          p > 0.f ? 1.f / (1.f - p) : 1.f, 0.f, 0, 0)) return e;
+    if (int e = run_wgrad(st, Z, gH, part(bo + l.w1), part(bo + l.b1), PS, Tcap, dT, d)) return e;
+    // gZ = gH . W1^T + gX   (residual z -> x_out)
+    if (int e = run_dense(st, gH, P + l.w1, nullptr, gZ, Tcap, dT, d, true, 0, gX, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    k_ln_bwd<<<ln_grid, 256, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], P + l.ln2g, gY, dT, d, 0);
+    k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
+                                                   part(bo + l.ln2b), part(bo + l.ln2g), PS);
+    k_attn_bwd<<<M, 128, attn_smem, st>>>(Qp, Kp, Vp, w.probs[b], gY, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
+                                          p, seed, 1u + 3u * b, gQ, gK, gV);
+    ADER_CHECK_LAUNCH("encoder_bwd/attn");
+    if (int e = run_wgrad(st, Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d)) return e;
+    if (int e = run_wgrad(st, X, gK, part(bo + l.wk), part(bo + l.bk), PS, Tcap, dT, d)) return e;
+    if (int e = run_wgrad(st, X, gV, part(bo + l.wv), part(bo + l.bv), PS, Tcap, dT, d)) return e;
+    // gQ1 = gQ . Wq^T + gY   (y = attn + q)
+    if (int e = run_dense(st, gQ, P + l.wq, nullptr, gQ1, Tcap, dT, d, true, 0, gY, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    if (int e = run_dense(st, gK, P + l.wk, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
+    if (int e = run_dense(st, gV, P + l.wv, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 1, 1.f, 0.f, 0, 0)) return e;
+    k_ln_bwd<<<ln_grid, 256, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], P + l.ln1g, gXin, dT, d, 1);
+    k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], dT, 0, nullptr, nullptr, d,
+                                                   part(bo + l.ln1b), part(bo + l.ln1g), PS);
+    ADER_CHECK_LAUNCH("encoder_bwd/block");
+    float* t = gX; gX = gXin; gXin = t;
+  }
+
+  // dense parameter gradients: reduce the split partials in fixed order
+  {
+    const long long lo = (long long)L * d, hi = PS;
+    k_reduce_partials<<<cdiv(hi - lo, 256), 256, 0, st>>>(g.partial, PS, SPLITS, lo, hi, grad + l.off_pos);
+  }
+  // position table (ADER.py:41-52) and item-table scatter (modules.py:127-130)
+  k_pos_grad<<<L, ln_threads, 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
+  {
+    const int ntiles = sort_tiles(Tcap);
+    const int bits = key_bits(m->v_tab);
+    int cur = 0;
+    const int* kin = w.tok_id; const int* vin = nullptr;
+    int pass = 0;
+    for (int shift = 0; shift < bits; shift += 8, ++pass) {
+      k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
+      k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
+      k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
+      kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
+    }
+    k_seg_reduce<<<cdiv((long long)cdiv(Tcap, 4) * 32, 256), 256, 0, st>>>(kin, vin, dT, gX, d, sqrtf((float)d), p, seed,
+                                                                           grad + l.off_table);
+  }
+  ADER_CHECK_LAUNCH("encoder_bwd/embedding");
+  return 0;
+}
+
+extern "C" int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
+                                        int32_t* out, void* stream);
+__global__ void k_gather_rows(const int* __restrict__ src, const int* __restrict__ idx, int n, int width, int* __restrict__ out) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n * width) return;
+  int i = (int)(e / width), c = (int)(e % width);
+  out[e] = src[(long long)idx[i] * width + c];
+}
+extern "C" int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
+                                        int32_t* out, void* stream) {
+  ADER_CHECK_ARG(src && idx && out && n >= 0 && width > 0, "gather_rows: bad argument");
+  if (n == 0) return 0;
+  k_gather_rows<<<cdiv((long long)n * width, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, width, out);
+  ADER_CHECK_LAUNCH("gather_rows");
+  return 0;
+}

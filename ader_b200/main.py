@@ -1,0 +1,277 @@
+"""Continual-learning driver with the reference's CLI (main.py:68-336): same flags and defaults
+(incl. the ``type=bool`` parsing quirk), same period / epoch / early-stop / exemplar
+protocol, same Training_logs.txt lines -- re-hosted on the GPU-resident fast paths.
+
+    python -m ader_b200.main --dataset=DIGINETICA            # ADER defaults
+    python -m ader_b200.main --dataset=YOOCHOOSE --lambda_=1.0 --batch_size=512 --test_batch=64
+
+Extra flags (not in the reference): --data_root, --max_periods, --results_root.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import random
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from .data import DataLoader, Evaluator, ExemplarGenerator, ExemplarSet, Sampler
+from .model import Ader, Ewc
+
+ITEM_NUM = {"DIGINETICA": 43136, "YOOCHOOSE": 25958}     # main.py:133-138
+
+
+def get_periods(data_dir: str):                            # main.py:36-51
+    n = len([f for f in os.listdir(data_dir) if f.startswith("period_") and f.endswith(".txt")])
+    return list(range(1, n))
+
+
+def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (types as in the reference)
+    p = argparse.ArgumentParser()
+    p.add_argument("--dataset", default="DIGINETICA", type=str)
+    p.add_argument("--save_dir", default="ADER", type=str)
+    p.add_argument("--exemplar_size", default=30000, type=int)
+    p.add_argument("--lambda_", default=0.8, type=float)
+    p.add_argument("--finetune", default=False, type=bool)
+    p.add_argument("--dropout", default=False, type=bool)
+    p.add_argument("--ewc", default=False, type=bool)
+    p.add_argument("--joint", default=False, type=bool)
+    p.add_argument("--ewc_sample_num", default=1000, type=int)
+    p.add_argument("--selection", default="herding", type=str)
+    p.add_argument("--disable_distillation", default=False, type=bool)
+    p.add_argument("--equal_exemplar", default=False, type=bool)
+    p.add_argument("--fix_lambda", default=False, type=bool)
+    p.add_argument("--num_epochs", default=100, type=int)
+    p.add_argument("--batch_size", default=256, type=int)
+    p.add_argument("--test_batch", default=64, type=int)
+    p.add_argument("--device_num", default=0, type=int)
+    p.add_argument("--lr", default=0.0005, type=float)
+    p.add_argument("--num_blocks", default=2, type=int)
+    p.add_argument("--num_heads", default=1, type=int)
+    p.add_argument("--stop", default=5, type=int)
+    p.add_argument("--random_seed", default=0, type=int)
+    p.add_argument("--hidden_units", default=150, type=int)
+    p.add_argument("--maxlen", default=50, type=int)
+    p.add_argument("--dropout_rate", default=0.3, type=float)
+    p.add_argument("--l2_emb", default=0.0, type=float)
+    # additions
+    p.add_argument("--data_root", default=None, type=str)
+    p.add_argument("--results_root", default="results", type=str)
+    p.add_argument("--max_periods", default=0, type=int)
+    p.add_argument("--item_num", default=0, type=int)
+    return p
+
+
+class PeriodTrainer:
+    """One period's epoch loop on GPU-resident rows (main.py:217-256)."""
+
+    def __init__(self, model: Ader, train_sampler: Sampler, exemplar_sampler, args, max_item: int):
+        self.model, self.args, self.max_item = model, args, max_item
+        self.ts, self.es = train_sampler, exemplar_sampler
+        dev = model.device
+        self.t_ids, self.t_lab = train_sampler.device_rows(dev)
+        self.t_nin = train_sampler.packed()[2]
+        if exemplar_sampler is not None:
+            self.e_ids, self.e_lab = exemplar_sampler.device_rows(dev)
+            self.e_nin = exemplar_sampler.packed()[2]
+        self.rows_seen = 0
+
+    def step(self):
+        m, dev, L = self.model, self.model.device, self.model.hp.maxlen
+        ti = self.ts.next_indices()
+        ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        n_tok = int(self.t_nin[ti].sum())
+        if self.es is None:
+            ids = torch.empty((len(ti), L), dtype=torch.int32, device=dev)
+            ops.gather_rows_i32(self.t_ids, ti_d, ids)
+            pos = self.t_lab[ti_d.long()]
+            loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
+            self.rows_seen += len(ti)
+            return loss
+        ei = self.es.next_indices()
+        ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        n_tok += int(self.e_nin[ei].sum())
+        ids = torch.empty((len(ti) + len(ei), L), dtype=torch.int32, device=dev)
+        ops.gather_rows_i32(self.t_ids, ti_d, ids[:len(ti)])
+        if len(ei):
+            ops.gather_rows_i32(self.e_ids, ei_d, ids[len(ti):])
+        pos = self.t_lab[ti_d.long()]
+        if m.disable_distillation:
+            loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
+                                exemplar_pos=self.e_lab[ei_d.long()], n_tokens=n_tok)
+        else:
+            if getattr(self.es, "teacher", None) is not None:
+                rows = torch.as_tensor(np.asarray([self.es.logits[i] for i in ei], dtype=np.int32)).to(dev)
+                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
+                                    exemplar_logits=self.es.teacher, teacher_rows=rows, n_tokens=n_tok)
+            else:
+                lg = np.asarray([self.es.logits[i] for i in ei], dtype=np.float32)
+                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
+                                    exemplar_logits=lg, n_tokens=n_tok)
+        self.rows_seen += len(ti) + len(ei)
+        return loss
+
+
+def run(args) -> dict:
+    res_dir = os.path.join(args.results_root, args.dataset + "-" + args.save_dir)
+    os.makedirs(res_dir, exist_ok=True)
+    logs = open(os.path.join(res_dir, "Training_logs.txt"), mode="w")
+    logs.write("\n".join([str(k) + "," + str(v) for k, v in sorted(vars(args).items(), key=lambda x: x[0])]))
+
+    torch.cuda.set_device(args.device_num)
+    np.random.seed(args.random_seed)                           # main.py:123-125
+    random.seed(args.random_seed)
+
+    dataloader = DataLoader(args.dataset, args.data_root)
+    item_num = args.item_num or ITEM_NUM.get(os.path.basename(args.dataset.rstrip("/")))
+    if not item_num:
+        raise ValueError("Invalid dataset name")
+    args.dropout_rate = 0 if (args.ewc or args.finetune) else args.dropout_rate      # main.py:141
+    model = Ader(item_num, args) if not args.ewc else Ewc(item_num, args)
+
+    periods = get_periods(dataloader.path)
+    if args.max_periods:
+        periods = periods[:args.max_periods]
+    print("Continue Learning: number of periods is %d." % len(periods))
+    logs.write("Continue Learning: number of periods is %d.\n" % len(periods))
+    best_epoch, item_num_prev = 0, 0
+    t_start = time.time()
+    metrics = {"MRR_20": [], "Recall_20": [], "MRR_10": [], "Recall_10": []}
+    stats = []
+    fast_exemplar = None
+    ckpt = {}                                                  # (period, epoch) -> state (tf.train.Saver max_to_keep=1)
+    stop_counter = 0                                           # reference leaves it uninitialised
+    no_replay = args.finetune or args.dropout or args.joint
+
+    for period in periods:
+        print("Period %d:" % period)
+        logs.write("Period %d:\n" % period)
+        best_performance, performance = 0, 0
+        train_sess, info = dataloader.train_loader(period - 1)
+        logs.write(info + "\n")
+        if args.joint and period > 1:
+            for p in range(1, period):
+                pre, info = dataloader.train_loader(p - 1)
+                logs.write(info + "\n")
+                train_sess.extend(pre)
+        train_sampler = Sampler(train_sess, args.maxlen, args.batch_size)
+        valid_subseq, train_subseq = train_sampler.split_data(valid_portion=0.1, return_train=True)
+        batch_num = train_sampler.batch_num()
+        test_sess, info = dataloader.evaluate_loader(period)
+        logs.write(info + "\n")
+        max_item = dataloader.max_item()
+
+        exemplar_sampler = None
+        exemplar_subseq = []
+        if period > 1 and not no_replay:                       # main.py:181-191
+            exemplar_size = len(fast_exemplar)
+            exemplar_subseq = list(fast_exemplar.sessions)
+            exemplar_batch = int(exemplar_size / batch_num)
+            exemplar_sampler = Sampler([], args.maxlen, exemplar_batch)
+            exemplar_sampler.add_exemplar(fast_exemplar)
+            if args.ewc or args.fix_lambda:                    # main.py:194-203
+                lambda_ = args.lambda_
+            else:
+                lambda_ = args.lambda_ * math.sqrt((item_num_prev / max_item) * (exemplar_size / train_sampler.data_size()))
+            model.update_loss(lambda_=lambda_)
+        else:
+            model.set_vanilla_loss()
+
+        if period > 1 and not args.joint:                      # main.py:210-213
+            model.load_state_dict(ckpt[(period - 1, best_epoch)])
+        else:
+            model.reinitialize()
+
+        use_ex = exemplar_sampler is not None and not args.ewc
+        trainer = PeriodTrainer(model, train_sampler, exemplar_sampler if use_ex else None, args, max_item)
+        best_epoch = 1
+        train_time = 0.0
+        for epoch in range(1, args.num_epochs + 1):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(batch_num):
+                trainer.step()
+            torch.cuda.synchronize()
+            train_time += time.time() - t0
+            if period > 1 and args.ewc:                        # main.py:258-262 (no effect on train_op, S13)
+                model.variables_prev = model.snapshot_variables()
+                rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
+                model.compute_fisher(None, rnd, 50, max_item)
+            valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None)
+            info = valid_evaluator.evaluate(epoch)
+            logs.write(info + "\n")
+            performance = valid_evaluator.results()[1]
+            if best_performance >= performance:                # main.py:272-280
+                stop_counter += 1
+                if stop_counter >= args.stop:
+                    break
+            else:
+                stop_counter = 0
+                best_epoch = epoch
+                best_performance = performance
+                ckpt = {(period, epoch): model.state_dict()}
+        model.load_state_dict(ckpt[(period, best_epoch)])      # main.py:283
+        test_evaluator = Evaluator(test_sess, False, args.maxlen, args.test_batch, max_item, "test", model, None)
+        info = test_evaluator.evaluate(best_epoch)
+        logs.write(info + "\n")
+        r = test_evaluator.results()
+        metrics["MRR_20"].append(r[0]); metrics["Recall_20"].append(r[1])
+        metrics["MRR_10"].append(r[2]); metrics["Recall_10"].append(r[3])
+        sps = trainer.rows_seen / max(train_time, 1e-9)
+        stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps})
+        info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s)" % (period, sps, trainer.rows_seen, train_time)
+        print(info)
+        logs.write(info + "\n")
+
+        if not no_replay:                                      # main.py:294-313
+            cand = train_subseq
+            cand.extend(valid_subseq)
+            cand.extend(exemplar_subseq)
+            gen = ExemplarGenerator(cand, args.exemplar_size, args.equal_exemplar, args.batch_size, args.maxlen,
+                                    args.dropout_rate, max_item)
+            if args.selection == "herding":
+                saved = gen.herding_selection(None, model)
+            elif args.selection == "loss":
+                saved = gen.loss_selection(None, model)
+            elif args.selection == "random":
+                saved = gen.randomly_selection(None, model)
+            else:
+                print("Invalid exemplar selection method")
+                saved = 0
+            info = "Total saved exemplar: %d" % saved
+            print(info)
+            logs.write(info + "\n")
+            fast_exemplar = gen.exemplars
+            del gen
+        item_num_prev = max_item
+        if args.ewc:                                           # main.py:319-323
+            exemplar_subseq = list(fast_exemplar.sessions)
+            model.variables_prev = model.snapshot_variables()
+            rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
+            model.compute_fisher(None, rnd, 50, max_item)
+        logs.flush()
+
+    avg = {k: float(np.array(v).mean()) for k, v in metrics.items()}
+    info = "Average: (MRR@20: %.4f, RECALL@20: %.4f, MRR@10: %.4f, RECALL@10: %.4f)" % (
+        avg["MRR_20"], avg["Recall_20"], avg["MRR_10"], avg["Recall_10"])
+    print(info)
+    logs.write(info + "\n")
+    minutes = (time.time() - t_start) / 60.0
+    print("Total time: %.2f minutes." % minutes)
+    logs.write("Total time: %.2f minutes\nDone." % minutes)
+    logs.close()
+    print("Done.")
+    return {"average": avg, "per_period": metrics, "throughput": stats, "minutes": minutes}
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    return run(args)
+
+
+if __name__ == "__main__":
+    main()

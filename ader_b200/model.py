@@ -1,0 +1,315 @@
+"""`Ader` / `Ewc` model objects: the reference's TF1 feed/fetch surface re-hosted on the C ABI.
+
+Reference seam: ``Ader(item_num, args)`` (ADER.py:13-103), ``set_vanilla_loss``
+(ADER.py:105), ``update_loss(lambda_)`` (ADER.py:108), ``predict(sess, seq, item_idx)``
+(ADER.py:140), fetches ``rep`` / ``logits`` / ``loss`` / ``train_op``; ``Ewc`` adds
+``compute_fisher`` and ``variables_prev`` (EWC.py:115-164).  ``sess`` arguments are accepted and
+ignored.  Exemplar rows are the LAST rows of ``input_seq`` and ``pos`` covers the train rows only
+(main.py:229, ADER.py:113-124).
+
+All state is device resident: one flat fp32 parameter vector + Adam slots + gradient buffer
+(params.py), so a "checkpoint" (tf.train.Saver, main.py:209-213,280,283) is a clone of four tensors.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .params import Hyper, ParamLayout
+
+
+def _to_ids(seq, maxlen: int, device) -> torch.Tensor:
+    """Accept the reference's tuple-of-arrays batches, ndarrays or device tensors -> int32 [M, L] on device."""
+    if isinstance(seq, torch.Tensor):
+        t = seq.to(device=device, dtype=torch.int32, non_blocking=True)
+    else:
+        a = np.ascontiguousarray(np.asarray(seq, dtype=np.int32))
+        t = torch.from_numpy(a).pin_memory().to(device, non_blocking=True) if a.size else torch.zeros((0, maxlen), dtype=torch.int32, device=device)
+    if t.dim() == 1:
+        t = t.view(1, -1)
+    if t.shape[1] != maxlen:
+        raise ValueError("input_seq must have maxlen=%d columns, got %s" % (maxlen, tuple(t.shape)))
+    return t.contiguous()
+
+
+def _to_i32(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32, non_blocking=True).contiguous().view(-1)
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.int32)).reshape(-1)
+    return torch.from_numpy(a).pin_memory().to(device, non_blocking=True)
+
+
+class Ader:
+    """SASRec + CE / distillation model (ADER.py:13-150) on libader_b200."""
+
+    VANILLA, KD, ER = 0, 1, 2
+
+    def __init__(self, item_num: int, args, device: Optional[torch.device] = None, init_seed: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ader_b200 needs a CUDA device (B200 / sm_100a); there is no CPU path")
+        ops._lib.load()
+        self.args = args
+        self.hp = Hyper(item_num=item_num, hidden_units=args.hidden_units, maxlen=args.maxlen,
+                        num_blocks=args.num_blocks, num_heads=args.num_heads)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.layout = ParamLayout(self.hp)
+        self.ms = ops.model_struct(self.hp)
+        seed = getattr(args, "random_seed", 0) if init_seed is None else init_seed
+        self.seed = int(getattr(args, "random_seed", 0))
+        self.theta = torch.from_numpy(self.layout.init_flat(seed)).to(self.device)
+        self.adam_m = torch.zeros_like(self.theta)
+        self.adam_v = torch.zeros_like(self.theta)
+        self.grad = torch.zeros_like(self.theta)
+        self.adam_state = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.disable_distillation = bool(getattr(args, "disable_distillation", False))
+        self.mode = self.VANILLA
+        self.lambda_ = 0.0
+        self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
+        self._enc_ws = ops.Workspace(self.device)
+        self._bwd_ws = ops.Workspace(self.device)
+        self._loss_ws = ops.Workspace(self.device)
+        self._eval_ws = ops.Workspace(self.device)
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.last_row_loss: Optional[torch.Tensor] = None
+
+    # ---- reference surface ----------------------------------------------------------------
+    @property
+    def variables(self):
+        """The 32 trainable tensors in creation order (EWC.py:90) as views of ``theta``."""
+        return self.layout.views(self.theta)
+
+    def set_vanilla_loss(self):                       # ADER.py:105-106
+        self.mode = self.VANILLA
+        self.lambda_ = 0.0
+
+    def update_loss(self, lambda_: float):            # ADER.py:108-138
+        self.mode = self.ER if self.disable_distillation else self.KD
+        self.lambda_ = float(lambda_)
+
+    # ---- encoder ----------------------------------------------------------------------------
+    def _tcap(self, ids: torch.Tensor, n_tokens: Optional[int]) -> int:
+        M = ids.shape[0]
+        cap = M * self.hp.maxlen if n_tokens is None else max(int(n_tokens), 1)
+        return min(max(cap, 1), M * self.hp.maxlen)
+
+    def encode(self, ids: torch.Tensor, n_tokens: Optional[int] = None, dropout_rate: float = 0.0,
+               seed: int = 0, out: Optional[torch.Tensor] = None):
+        """ids int32 [M, L] (device) -> rep fp32 [M, d]; returns (rep, Tcap).  The activation
+        workspace stays valid until the next encode() (needed by backward)."""
+        M = ids.shape[0]
+        tcap = self._tcap(ids, n_tokens)
+        ws = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, M, tcap))
+        rep = out if out is not None else torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
+        ops.encoder_fwd(self.ms, self.theta, ids, tcap, ws, rep, dropout_rate, seed)
+        return rep, tcap
+
+    def rep(self, seq, n_tokens: Optional[int] = None) -> torch.Tensor:
+        """fetch ``model.rep`` in eval mode (util.py:452)."""
+        ids = _to_ids(seq, self.hp.maxlen, self.device)
+        return self.encode(ids, n_tokens)[0]
+
+    def logits(self, rep: torch.Tensor, max_item: int) -> torch.Tensor:
+        """fetch ``model.logits`` (ADER.py:91): [M, max_item] fp32."""
+        out = torch.empty((rep.shape[0], max_item), dtype=torch.float32, device=self.device)
+        ops.logits(self.ms, self.theta, rep, max_item, out)
+        return out
+
+    def rep_logits(self, seq, max_item: int):
+        """fetch [model.rep, model.logits] (util.py:452-455)."""
+        r = self.rep(seq)
+        return r, self.logits(r, max_item)
+
+    # ---- training step ------------------------------------------------------------------------
+    def loss_and_grad(self, seq, pos, max_item: int, exemplar_logits=None, exemplar_pos=None,
+                      teacher_rows=None, dropout_rate: float = 0.0, n_tokens: Optional[int] = None,
+                      mode: Optional[int] = None, lambda_: Optional[float] = None) -> torch.Tensor:
+        """Forward + backward of the current loss; fills ``self.grad`` (flat).  Returns the device
+        scalar loss.  ``exemplar_logits`` is either a host array / list [M_e, V_prev] (reference feed,
+        ADER.py:20) or a device tensor [E, V_prev] indexed by ``teacher_rows`` [M_e]."""
+        mode = self.mode if mode is None else mode
+        lam = self.lambda_ if lambda_ is None else lambda_
+        ids = _to_ids(seq, self.hp.maxlen, self.device)
+        pos_t = _to_i32(pos, self.device)
+        M, n_train = ids.shape[0], pos_t.numel()
+        n_ex = M - n_train
+        teacher = trow = ex_pos_t = None
+        v_prev = 0
+        if n_ex > 0:
+            if mode == self.KD:
+                if exemplar_logits is None:
+                    raise ValueError("KD loss needs exemplar_logits")
+                if isinstance(exemplar_logits, torch.Tensor):
+                    teacher = exemplar_logits
+                else:
+                    a = np.ascontiguousarray(np.asarray(exemplar_logits, dtype=np.float32))
+                    teacher = torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True)
+                if teacher.dim() != 2 or teacher.stride(1) != 1 or teacher.dtype != torch.float32:
+                    raise ValueError("exemplar_logits must be a 2-D fp32 row-major matrix")
+                v_prev = teacher.shape[1]
+                if teacher_rows is not None:
+                    trow = _to_i32(teacher_rows, self.device)
+                    if trow.numel() != n_ex:
+                        raise ValueError("teacher_rows must have one entry per exemplar row")
+                elif teacher.shape[0] != n_ex:
+                    raise ValueError("exemplar_logits rows (%d) != exemplar rows (%d)" % (teacher.shape[0], n_ex))
+            elif mode == self.ER:
+                if exemplar_pos is None:
+                    raise ValueError("one-hot exemplar loss needs exemplar_pos")
+                ex_pos_t = _to_i32(exemplar_pos, self.device)
+            else:
+                raise ValueError("exemplar rows were fed but the loss is vanilla (call update_loss first)")
+        seed = (self.seed << 32) + self.global_step
+        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed)
+        a = ops.make_loss_args(M, n_train, n_ex, max_item, v_prev, mode if n_ex > 0 else self.VANILLA, lam,
+                               pos_t, ex_pos_t, teacher, trow)
+        ws = self._loss_ws.get(ops.loss_ws_bytes(self.ms, a))
+        row_loss = torch.empty(M, dtype=torch.float32, device=self.device)
+        d_rep = torch.empty_like(rep)
+        ops.loss_fwd_bwd(self.ms, self.theta, rep, a, ws, self._loss, row_loss, d_rep, self.grad)
+        bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
+        ops.encoder_bwd(self.ms, self.theta, ids, tcap, self._enc_ws.buf, bws, d_rep, self.grad, dropout_rate, seed)
+        self.last_row_loss = row_loss
+        self._keep = (ids, pos_t, teacher, trow, ex_pos_t, rep, d_rep)   # keep alive until the stream is done
+        return self._loss
+
+    def apply_gradients(self, max_item: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None):
+        """tf.train.AdamOptimizer.apply_gradients (ADER.py:96,106,138)."""
+        ops.adam_step(self.ms, self.theta, self.adam_m, self.adam_v, self.grad, self.adam_state, max_item, lr,
+                      ewc_lambda, fisher, theta_star)
+        self.global_step += 1
+
+    def train_step(self, seq, pos, max_item: int, lr: Optional[float] = None, dropout_rate: Optional[float] = None,
+                   exemplar_logits=None, exemplar_pos=None, teacher_rows=None, n_tokens: Optional[int] = None):
+        """sess.run(model.train_op, feed) (main.py:233-256).  Returns the device scalar loss."""
+        lr = self.args.lr if lr is None else lr
+        p = self.args.dropout_rate if dropout_rate is None else dropout_rate
+        loss = self.loss_and_grad(seq, pos, max_item, exemplar_logits, exemplar_pos, teacher_rows, p, n_tokens)
+        self.apply_gradients(max_item, lr)
+        return loss
+
+    # ---- evaluation ---------------------------------------------------------------------------
+    def rank_topk(self, seq, gt, max_item: int, k: int = 20, n_tokens: Optional[int] = None):
+        """Rank of the ground-truth item among items 1..max_item (== pred_last[row, gt-1],
+        ADER.py:103 + util.py:325; ties -> lower index first) and the top-k item ids."""
+        ids = _to_ids(seq, self.hp.maxlen, self.device)
+        gt_t = _to_i32(gt, self.device)
+        rep, _ = self.encode(ids, n_tokens)
+        M = ids.shape[0]
+        ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
+        rank = torch.empty(M, dtype=torch.int32, device=self.device)
+        items = torch.empty((M, max(k, 1)), dtype=torch.int32, device=self.device)
+        scores = torch.empty((M, max(k, 1)), dtype=torch.float32, device=self.device)
+        ops.eval_rank_topk(self.ms, self.theta, rep, gt_t, max_item, k, ws, rank, items, scores)
+        return rank, items, scores
+
+    def predict(self, sess, seq, item_idx):
+        """Reference signature (ADER.py:140-150): full rank matrix ``argsort(argsort(-logits))`` over
+        ``item_idx``.  Kept for drop-in use; the evaluator uses ``rank_topk`` and never builds it."""
+        ids = _to_ids(seq, self.hp.maxlen, self.device)
+        rep, _ = self.encode(ids)
+        items = np.asarray(item_idx, dtype=np.int64)
+        vmax = int(items.max())
+        lg = self.logits(rep, vmax)
+        if not (len(items) == vmax and items[0] == 1 and items[-1] == vmax):
+            lg = lg[:, torch.from_numpy(items - 1).to(self.device)]
+        order = torch.argsort(lg, dim=1, descending=True, stable=True)
+        ranks = torch.empty_like(order)
+        ar = torch.arange(order.shape[1], device=self.device).expand_as(order)
+        ranks.scatter_(1, order, ar)
+        return ranks.cpu().numpy()
+
+    # ---- checkpoint (tf.train.Saver analogue, main.py:209-213,280,283) ---------------------------
+    def state_dict(self):
+        return {"theta": self.theta.clone(), "adam_m": self.adam_m.clone(), "adam_v": self.adam_v.clone(),
+                "adam_state": self.adam_state.clone(), "global_step": self.global_step}
+
+    def load_state_dict(self, sd):
+        self.theta.copy_(sd["theta"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"])
+        self.adam_state.copy_(sd["adam_state"]); self.global_step = int(sd["global_step"])
+
+    def reinitialize(self, seed: Optional[int] = None):
+        """sess.run(tf.global_variables_initializer()) (main.py:213)."""
+        s = self.seed if seed is None else seed
+        self.theta.copy_(torch.from_numpy(self.layout.init_flat(s)))
+        self.adam_m.zero_(); self.adam_v.zero_(); self.adam_state.zero_(); self.global_step = 0
+
+    def save(self, path: str):
+        torch.save({k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in self.state_dict().items()}, path)
+
+    def restore(self, path: str):
+        sd = torch.load(path, map_location=self.device)
+        self.load_state_dict(sd)
+
+
+class Ewc(Ader):
+    """EWC baseline (EWC.py:14-177): same network, CE + (lambda/2) sum F (theta - theta*)^2."""
+
+    def __init__(self, item_num: int, args, device=None, init_seed=None):
+        super().__init__(item_num, args, device, init_seed)
+        self.fisher: Optional[torch.Tensor] = None          # F_accum, flat fp32
+        self.theta_star: Optional[torch.Tensor] = None      # variables_prev, flat fp32
+        self._fisher_acc: Optional[torch.Tensor] = None
+        self.ewc_lambda = 0.0
+        self._graph_fisher = None
+        self._graph_star = None
+
+    @property
+    def variables_prev(self):
+        return None if self.theta_star is None else self.layout.views(self.theta_star)
+
+    @variables_prev.setter
+    def variables_prev(self, value):
+        """main.py:260,321 assign ``sess.run(model.variables)``; accept that list or a flat tensor."""
+        if isinstance(value, torch.Tensor):
+            self.theta_star = value.detach().clone()
+        else:
+            self.theta_star = torch.cat([torch.as_tensor(v, device=self.device).reshape(-1) for v in value]).float()
+
+    def snapshot_variables(self):
+        """sess.run(model.variables) as one flat device tensor."""
+        return self.theta.clone()
+
+    def set_vanilla_loss(self):
+        super().set_vanilla_loss()
+        self.ewc_lambda = 0.0
+
+    def update_loss(self, lambda_: float):
+        """EWC.py:115-124.  TF bakes F_accum / variables_prev into the graph as CONSTANTS at this
+        call, so later reassignments do not affect the running train_op: freeze copies."""
+        self.mode = self.VANILLA
+        self.ewc_lambda = float(lambda_)
+        self._graph_fisher = self.fisher.clone()
+        self._graph_star = self.theta_star.clone()
+
+    def apply_gradients(self, max_item: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None):
+        if self.ewc_lambda != 0.0:
+            super().apply_gradients(max_item, lr, self.ewc_lambda, self._graph_fisher, self._graph_star)
+        else:
+            super().apply_gradients(max_item, lr)
+
+    def compute_fisher(self, sess, data: Sequence[Sequence[int]], batch_size: int, max_item: int):
+        """EWC.py:126-164: per-sample (batch of one) squared gradients of the vanilla CE in eval mode,
+        accumulated in float64, divided by len(data).  Consumes the Python RNG like the reference
+        (Sampler shuffle at construction and at wrap)."""
+        from .data import Sampler
+        sampler = Sampler(data, self.hp.maxlen, batch_size, is_subseq=True)
+        if self._fisher_acc is None:
+            self._fisher_acc = torch.zeros(self.layout.total, dtype=torch.float64, device=self.device)
+        acc = self._fisher_acc
+        acc.zero_()
+        for _ in range(sampler.batch_num()):
+            seq, pos = sampler.sampler_arrays()
+            for i in range(seq.shape[0]):
+                self.loss_and_grad(seq[i:i + 1], pos[i:i + 1], max_item, mode=self.VANILLA, lambda_=0.0,
+                                   n_tokens=int((seq[i] != 0).sum()))
+                ops.fisher_accumulate(self.ms, self.grad, acc, max_item)
+        if self.fisher is None:
+            self.fisher = torch.empty(self.layout.total, dtype=torch.float32, device=self.device)
+        ops.fisher_finalize(self.ms, acc, self.fisher, max_item, len(data))
+
+    @property
+    def F_accum(self):
+        return None if self.fisher is None else self.layout.views(self.fisher)

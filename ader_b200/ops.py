@@ -1,0 +1,207 @@
+"""Device ops of the ADER hot path: thin shims from torch tensors to the C ABI.
+
+Each function below passes raw device pointers + the current CUDA stream to one entry point of
+``libader_b200.so`` (include/ader_b200.h).  They are also registered as ``torch.ops.ader_b200.*``
+custom ops (see ``register_torch_ops``) so the kernels are reachable from the dispatcher; the host
+loop calls the shims directly to keep per-step overhead out of the way.  torch is used for device
+memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AderAdamArgs, AderLossArgs, AderModel, check
+from .params import Hyper
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.AderError("ader_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def model_struct(hp: Hyper) -> AderModel:
+    return AderModel(hp.v_tab, hp.hidden_units, hp.maxlen, hp.num_blocks, hp.num_heads)
+
+
+class Workspace:
+    """Grow-only caller-owned device scratch (the C ABI never allocates)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+def encoder_ws_bytes(ms: AderModel, M: int, Tcap: int) -> int:
+    n = _lib.load().ader_encoder_ws_bytes(C.byref(ms), M, Tcap)
+    if n == 0:
+        raise _lib.AderError("encoder_ws_bytes: bad model / sizes")
+    return n
+
+
+def encoder_bwd_ws_bytes(ms: AderModel, M: int, Tcap: int) -> int:
+    n = _lib.load().ader_encoder_bwd_ws_bytes(C.byref(ms), M, Tcap)
+    if n == 0:
+        raise _lib.AderError("encoder_bwd_ws_bytes: bad model / sizes")
+    return n
+
+
+def encoder_ws_slot(ms: AderModel, M: int, Tcap: int, slot: int, block: int = 0) -> int:
+    return _lib.load().ader_encoder_ws_slot(C.byref(ms), M, Tcap, slot, block)
+
+
+def encoder_fwd(ms: AderModel, theta, ids, Tcap: int, ws, rep, dropout_rate: float = 0.0, seed: int = 0):
+    """ids [M, maxlen] int32 -> rep [M, d] (ADER.py:25-85)."""
+    _require_cuda(theta, ids, ws, rep)
+    check(_lib.load().ader_encoder_fwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
+                                       float(dropout_rate), C.c_uint64(seed), _stream()), "encoder_fwd")
+
+
+def encoder_bwd(ms: AderModel, theta, ids, Tcap: int, ws, bwd_ws, d_rep, grad, dropout_rate: float = 0.0, seed: int = 0):
+    _require_cuda(theta, ids, ws, bwd_ws, d_rep, grad)
+    check(_lib.load().ader_encoder_bwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
+                                       _ptr(d_rep), _ptr(grad), float(dropout_rate), C.c_uint64(seed), _stream()),
+          "encoder_bwd")
+
+
+def make_loss_args(M, n_train, n_ex, V, V_prev=0, mode=0, lambda_=0.0, pos=None, ex_pos=None,
+                   teacher=None, teacher_row=None) -> AderLossArgs:
+    a = AderLossArgs()
+    a.M, a.n_train, a.n_ex, a.V, a.V_prev, a.mode, a.lambda_ = M, n_train, n_ex, V, V_prev, mode, lambda_
+    a.pos = pos.data_ptr() if pos is not None else None
+    a.ex_pos = ex_pos.data_ptr() if ex_pos is not None else None
+    a.teacher = teacher.data_ptr() if teacher is not None else None
+    a.teacher_row = teacher_row.data_ptr() if teacher_row is not None else None
+    a.teacher_ld = teacher.stride(0) if teacher is not None else 0
+    return a
+
+
+def loss_ws_bytes(ms: AderModel, a: AderLossArgs) -> int:
+    n = _lib.load().ader_loss_ws_bytes(C.byref(ms), C.byref(a))
+    if n == 0:
+        raise _lib.AderError("loss_ws_bytes: bad model / sizes")
+    return n
+
+
+def loss_fwd_bwd(ms: AderModel, theta, rep, a: AderLossArgs, ws, loss, row_loss, d_rep, grad):
+    _require_cuda(theta, rep, ws, loss, row_loss, d_rep, grad)
+    check(_lib.load().ader_loss_fwd_bwd(C.byref(ms), _ptr(theta), _ptr(rep), C.byref(a), _ptr(ws), _ptr(loss),
+                                        _ptr(row_loss), _ptr(d_rep), _ptr(grad), _stream()), "loss_fwd_bwd")
+
+
+def logits(ms: AderModel, theta, rep, V: int, out):
+    """out [M, >=V] fp32 = rep . E[1..V]^T (ADER.py:90-91)."""
+    _require_cuda(theta, rep, out)
+    check(_lib.load().ader_logits(C.byref(ms), _ptr(theta), _ptr(rep), rep.shape[0], V, _ptr(out), out.stride(0),
+                                  _stream()), "logits")
+
+
+def adam_step(ms: AderModel, theta, m, v, grad, state, V: int, lr: float, ewc_lambda: float = 0.0,
+              fisher=None, theta_star=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    _require_cuda(theta, m, v, grad, state, fisher, theta_star)
+    a = AderAdamArgs(lr, beta1, beta2, eps, V, ewc_lambda,
+                     fisher.data_ptr() if fisher is not None else None,
+                     theta_star.data_ptr() if theta_star is not None else None)
+    check(_lib.load().ader_adam_step(C.byref(ms), _ptr(theta), _ptr(m), _ptr(v), _ptr(grad), _ptr(state), C.byref(a),
+                                     _stream()), "adam_step")
+
+
+def eval_ws_bytes(ms: AderModel, M: int, V: int) -> int:
+    n = _lib.load().ader_eval_ws_bytes(C.byref(ms), M, V)
+    if n == 0:
+        raise _lib.AderError("eval_ws_bytes: bad model / sizes")
+    return n
+
+
+def eval_rank_topk(ms: AderModel, theta, rep, gt, V: int, k: int, ws, rank, topk_item, topk_score):
+    _require_cuda(theta, rep, gt, ws, rank, topk_item, topk_score)
+    check(_lib.load().ader_eval_rank_topk(C.byref(ms), _ptr(theta), _ptr(rep), _ptr(gt), rep.shape[0], V, k, _ptr(ws),
+                                          _ptr(rank), _ptr(topk_item), _ptr(topk_score), _stream()), "eval_rank_topk")
+
+
+def herding_ws_bytes(ms: AderModel, N: int) -> int:
+    n = _lib.load().ader_herding_ws_bytes(C.byref(ms), N)
+    if n == 0:
+        raise _lib.AderError("herding_ws_bytes: bad model / sizes")
+    return n
+
+
+def herding_segmented(ms: AderModel, rep, cand, seg_off, quota, max_steps, ws, picks, n_picked):
+    _require_cuda(rep, cand, seg_off, quota, max_steps, ws, picks, n_picked)
+    check(_lib.load().ader_herding_segmented(C.byref(ms), _ptr(rep), rep.shape[0], _ptr(cand), _ptr(seg_off),
+                                             seg_off.numel() - 1, _ptr(quota), _ptr(max_steps), _ptr(ws), _ptr(picks),
+                                             _ptr(n_picked), _stream()), "herding_segmented")
+
+
+def fisher_accumulate(ms: AderModel, grad, acc, V: int):
+    _require_cuda(grad, acc)
+    check(_lib.load().ader_fisher_accumulate(C.byref(ms), _ptr(grad), _ptr(acc), V, _stream()), "fisher_accumulate")
+
+
+def fisher_finalize(ms: AderModel, acc, fisher, V: int, n_data: int):
+    _require_cuda(acc, fisher)
+    check(_lib.load().ader_fisher_finalize(C.byref(ms), _ptr(acc), _ptr(fisher), V, n_data, _stream()), "fisher_finalize")
+
+
+def gather_rows_i32(src, idx, out):
+    _require_cuda(src, idx, out)
+    check(_lib.load().ader_gather_rows_i32(_ptr(src), _ptr(idx), idx.numel(), src.shape[1], _ptr(out), _stream()),
+          "gather_rows_i32")
+
+
+# ---- torch.ops registration -------------------------------------------------------------------
+_registered = False
+
+
+def register_torch_ops() -> None:
+    """Expose the kernel groups as ``torch.ops.ader_b200.*`` (CUDA implementations only)."""
+    global _registered
+    if _registered:
+        return
+    lib = torch.library.Library("ader_b200", "DEF")
+    lib.define("encoder_fwd(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor(a!) ws, Tensor(b!) rep, "
+               "float dropout_rate, int seed) -> ()")
+    lib.define("logits(int[] model, Tensor theta, Tensor rep, int V, Tensor(a!) out) -> ()")
+    lib.define("eval_rank_topk(int[] model, Tensor theta, Tensor rep, Tensor gt, int V, int k, Tensor(a!) ws, "
+               "Tensor(b!) rank, Tensor(c!) topk_item, Tensor(d!) topk_score) -> ()")
+    lib.define("adam_step(int[] model, Tensor(a!) theta, Tensor(b!) m, Tensor(c!) v, Tensor grad, Tensor(d!) state, "
+               "int V, float lr) -> ()")
+
+    def _ms(model):
+        return AderModel(*[int(x) for x in model])
+
+    def _enc(model, theta, ids, Tcap, ws, rep, dropout_rate, seed):
+        encoder_fwd(_ms(model), theta, ids, Tcap, ws, rep, dropout_rate, seed)
+
+    def _logits(model, theta, rep, V, out):
+        logits(_ms(model), theta, rep, V, out)
+
+    def _eval(model, theta, rep, gt, V, k, ws, rank, topk_item, topk_score):
+        eval_rank_topk(_ms(model), theta, rep, gt, V, k, ws, rank, topk_item, topk_score)
+
+    def _adam(model, theta, m, v, grad, state, V, lr):
+        adam_step(_ms(model), theta, m, v, grad, state, V, lr)
+
+    lib.impl("encoder_fwd", _enc, "CUDA")
+    lib.impl("logits", _logits, "CUDA")
+    lib.impl("eval_rank_topk", _eval, "CUDA")
+    lib.impl("adam_step", _adam, "CUDA")
+    register_torch_ops._lib = lib      # keep alive
+    _registered = True

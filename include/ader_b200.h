@@ -1,0 +1,148 @@
+/* ader_b200.h -- C ABI of the B200-native ADER hot path (libader_b200.so).
+ *
+ * The reference (doublemul/ADER) has no FFI layer: its seam is the TF1 feed/fetch contract of
+ * the `Ader` / `Ewc` model objects (ADER.py:16-23, ADER.py:85-150, EWC.py:115-177).  Each entry
+ * point below replaces the device work behind one group of those fetches; the Python host
+ * (`ader_b200/model.py`) keeps the reference's method surface on top of them.
+ *
+ * Conventions:
+ *   - plain C, POD structs, raw DEVICE pointers + sizes, `void* stream` is a cudaStream_t;
+ *   - the caller owns every buffer (incl. workspaces; sizes from the *_bytes queries);
+ *   - functions never allocate, never synchronise, are stream-ordered and re-entrant;
+ *   - return 0 on success, <0 on error (-1 bad argument, -2 bad alignment/size, -3 launch error);
+ *     `ader_last_error()` returns a thread-local message;
+ *   - no C++ exception crosses the boundary.  There is no CPU fallback.
+ *
+ * Data layout.  All trainable state lives in ONE flat fp32 vector `theta` (and twins m, v, grad,
+ * fisher, theta_star) in the creation order of EWC.py:90 / SURVEY A.2:
+ *   [ item_table (v_tab x d) | pos_table (maxlen x d) | block 0 | ... | block NB-1 | lnf.beta | lnf.gamma ]
+ *   block = [ln1.beta, ln1.gamma, wq (d x d, in-major), bq, wk, bk, wv, bv, ln2.beta, ln2.gamma, w1, b1, w2, b2]
+ * Sessions are packed: only real (non-zero) tokens are stored, T = sum of row lengths.
+ */
+#ifndef ADER_B200_H
+#define ADER_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADER_ABI_VERSION 1
+
+typedef struct AderModel {
+  int32_t v_tab;       /* rows of the item table = item_num + 1   (ADER.py:29-38)           */
+  int32_t d;           /* hidden_units                            (main.py:103)             */
+  int32_t maxlen;      /* L                                       (main.py:104)             */
+  int32_t num_blocks;  /* (main.py:99)                                                       */
+  int32_t num_heads;   /* (main.py:100), must divide d                                      */
+} AderModel;
+
+/* ---- introspection ------------------------------------------------------------------- */
+int32_t     ader_abi_version(void);
+const char* ader_last_error(void);
+/* number of fp32 elements in theta; offset (in elements) of tensor `idx` (0..2+14*NB+1). */
+int64_t     ader_param_count(const AderModel* m);
+int64_t     ader_param_offset(const AderModel* m, int32_t idx);
+int64_t     ader_dense_count(const AderModel* m);      /* everything after the item table */
+
+/* ---- encoder: modules.py:23-271 + ADER.py:25-85 (subsystem 1) ------------------------- */
+/* Activation workspace (saved for backward) for M rows and a capacity of Tcap real tokens
+ * (Tcap <= M * maxlen; the exact token count is computed on the device, overflow is flagged
+ * in the workspace's flags slot and clamped). */
+size_t  ader_encoder_ws_bytes(const AderModel* m, int32_t M, int32_t Tcap);
+/* Backward scratch + split-K partial-gradient workspace. */
+size_t  ader_encoder_bwd_ws_bytes(const AderModel* m, int32_t M, int32_t Tcap);
+/* byte offset of a named activation slot inside the encoder workspace (tests / debugging).
+ * slot: 0 x_in(block), 1 q=LN1(x), 2 Q, 3 K, 4 V, 5 y=attn+q, 6 z=LN2(y), 7 h=relu(.), 8 x_out(last block),
+ *       9 probs(block) ; -1 row_len, -2 row_off, -3 tok_row, -4 flags (flags[0] != 0: token overflow) */
+int64_t ader_encoder_ws_slot(const AderModel* m, int32_t M, int32_t Tcap, int32_t slot, int32_t block);
+
+/* ids [M, maxlen] int32 left-zero-padded (util.py:151-171) -> rep [M, d] fp32 (ADER.py:85).
+ * dropout_rate > 0 applies tf.layers.dropout at the 1+3*NB reference sites (ADER.py:55,
+ * modules.py:214,257,262) with a counter-based generator keyed by (seed, step). */
+int32_t ader_encoder_fwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                         int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed, void* stream);
+/* d_rep [M, d] -> grad (flat, same layout as theta): writes the pos_table and all block / lnf
+ * gradients, and ADDS the input-lookup scatter (ADER.py:29-38, sqrt(d)-scaled) into the item
+ * table rows of `grad` (which must already hold the output-projection gradient, or zeros).
+ * The scatter is a stable radix sort by item id + segmented reduction: no float atomics. */
+int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                         int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
+                         float dropout_rate, uint64_t seed, void* stream);
+
+/* ---- logits + CE + distillation: ADER.py:88-93, ADER.py:108-138 (subsystem 2) ---------- */
+typedef struct AderLossArgs {
+  int32_t M;               /* rows of rep = n_train + n_ex (exemplar rows LAST, main.py:229)   */
+  int32_t n_train;         /* rows with one-hot labels `pos`                                   */
+  int32_t n_ex;            /* exemplar rows                                                    */
+  int32_t V;               /* max_item: logits columns are items 1..V (ADER.py:90-92)          */
+  int32_t V_prev;          /* teacher width (columns 1..V_prev), 0 when mode != KD             */
+  int32_t mode;            /* 0 vanilla (ADER.py:93), 1 KD (ADER.py:133-137), 2 ER one-hot (ADER.py:126-131) */
+  float   lambda_;         /* main.py:196-200                                                  */
+  const int32_t* pos;      /* [n_train] labels 1..V                                            */
+  const int32_t* ex_pos;   /* [n_ex] labels (mode 2)                                           */
+  const float*   teacher;  /* [*, V_prev] fp32 stored exemplar logits (mode 1)                 */
+  const int32_t* teacher_row; /* [n_ex] row of `teacher` per exemplar row, or NULL = identity  */
+  int64_t teacher_ld;      /* row stride of `teacher` in elements (>= V_prev)                  */
+} AderLossArgs;
+
+size_t  ader_loss_ws_bytes(const AderModel* m, const AderLossArgs* a);
+/* rep [M,d] -> loss[0] (scalar), row_loss [M], d_rep [M,d]; writes the dense output-projection
+ * gradient into grad rows 1..V of the item table (rows 0 and >V untouched). */
+int32_t ader_loss_fwd_bwd(const AderModel* m, const float* theta, const float* rep,
+                          const AderLossArgs* a, void* ws, float* loss, float* row_loss,
+                          float* d_rep, float* grad, void* stream);
+/* logits [M, V] fp32 = rep . E[1..V]^T  (fetch `logits`, util.py:452,482,514). ld = row stride. */
+int32_t ader_logits(const AderModel* m, const float* theta, const float* rep, int32_t M, int32_t V,
+                    float* logits, int64_t ld, void* stream);
+
+/* ---- optimiser: tf.train.AdamOptimizer (ADER.py:96) + EWC penalty (EWC.py:115-124) ------ */
+typedef struct AderAdamArgs {
+  float lr, beta1, beta2, eps;
+  int32_t V;               /* table rows 1..V are updated (rows > V have m = v = g = 0 forever) */
+  float ewc_lambda;        /* 0 = off; else grad += lambda * F * (theta - theta_star)          */
+  const float* fisher;     /* flat, same layout as theta (or NULL)                              */
+  const float* theta_star; /* flat (or NULL)                                                    */
+} AderAdamArgs;
+/* state: device int32[2]; state[0] = step t, incremented by this call (the update uses the value
+ * after the increment); state[1] is scratch (bits of the bias-corrected step size). */
+int32_t ader_adam_step(const AderModel* m, float* theta, float* adam_m, float* adam_v,
+                       const float* grad, int32_t* state, const AderAdamArgs* a, void* stream);
+
+/* ---- evaluation: ADER.py:99-103, util.py:309-339 (subsystem 5) -------------------------- */
+size_t  ader_eval_ws_bytes(const AderModel* m, int32_t M, int32_t V);
+/* rep [M,d], gt [M] (1..V) -> rank [M] (0-based rank of gt, ties -> lower index first),
+ * topk_item [M,k] (1-based ids, best first), topk_score [M,k]; k <= 32. */
+int32_t ader_eval_rank_topk(const AderModel* m, const float* theta, const float* rep, const int32_t* gt,
+                            int32_t M, int32_t V, int32_t k, void* ws, int32_t* rank,
+                            int32_t* topk_item, float* topk_score, void* stream);
+
+/* ---- exemplar selection: util.py:401-461 (subsystem 4) ---------------------------------- */
+/* Segmented herding.  rep [N,d]; segment s owns candidate rows cand[seg_off[s] .. seg_off[s+1])
+ * (indices into rep, in the reference's sess_by_item order); quota[s] = min(m, n_s);
+ * max_steps[s] = ceil(1.1*m) evaluated in float64 on the host (util.py:425).
+ * Output picks[seg_off[s] + k] = k-th selected LOCAL candidate index, n_picked[s]. */
+size_t  ader_herding_ws_bytes(const AderModel* m, int32_t N);
+int32_t ader_herding_segmented(const AderModel* m, const float* rep, int32_t N, const int32_t* cand,
+                               const int32_t* seg_off, int32_t n_seg, const int32_t* quota,
+                               const int32_t* max_steps, void* ws, int32_t* picks, int32_t* n_picked,
+                               void* stream);
+
+/* ---- EWC Fisher diagonal: EWC.py:126-164 ------------------------------------------------ */
+/* acc (fp64, flat) += square_fp32(grad) over table rows 1..V and all dense params. */
+int32_t ader_fisher_accumulate(const AderModel* m, const float* grad, double* acc, int32_t V, void* stream);
+/* fisher (fp32, flat) = acc / n_data over the same range; zero elsewhere. */
+int32_t ader_fisher_finalize(const AderModel* m, const double* acc, float* fisher, int32_t V,
+                             int32_t n_data, void* stream);
+
+/* ---- helpers ---------------------------------------------------------------------------- */
+/* out[i, :] = src[idx[i], :] for int32 rows (batch assembly from the GPU-resident row matrix). */
+int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
+                             int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADER_B200_H */
