@@ -67,6 +67,7 @@ class Ader:
         self.disable_distillation = bool(getattr(args, "disable_distillation", False))
         self.mode = self.VANILLA
         self.lambda_ = 0.0
+        self.grad_sync = None
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
         self._enc_ws = ops.Workspace(self.device)
         self._bwd_ws = ops.Workspace(self.device)
@@ -125,7 +126,7 @@ class Ader:
     # ---- training step ------------------------------------------------------------------------
     def loss_and_grad(self, seq, pos, max_item: int, exemplar_logits=None, exemplar_pos=None,
                       teacher_rows=None, dropout_rate: float = 0.0, n_tokens: Optional[int] = None,
-                      mode: Optional[int] = None, lambda_: Optional[float] = None) -> torch.Tensor:
+                      mode: Optional[int] = None, lambda_: Optional[float] = None, _events=None) -> torch.Tensor:
         """Forward + backward of the current loss; fills ``self.grad`` (flat).  Returns the device
         scalar loss.  ``exemplar_logits`` is either a host array / list [M_e, V_prev] (reference feed,
         ADER.py:20) or a device tensor [E, V_prev] indexed by ``teacher_rows`` [M_e]."""
@@ -163,14 +164,22 @@ class Ader:
                 raise ValueError("exemplar rows were fed but the loss is vanilla (call update_loss first)")
         seed = (self.seed << 32) + self.global_step
         rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed)
+        if _events:
+            _events[0].record()
         a = ops.make_loss_args(M, n_train, n_ex, max_item, v_prev, mode if n_ex > 0 else self.VANILLA, lam,
                                pos_t, ex_pos_t, teacher, trow)
         ws = self._loss_ws.get(ops.loss_ws_bytes(self.ms, a))
         row_loss = torch.empty(M, dtype=torch.float32, device=self.device)
         d_rep = torch.empty_like(rep)
         ops.loss_fwd_bwd(self.ms, self.theta, rep, a, ws, self._loss, row_loss, d_rep, self.grad)
+        if _events:
+            _events[1].record()
         bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
         ops.encoder_bwd(self.ms, self.theta, ids, tcap, self._enc_ws.buf, bws, d_rep, self.grad, dropout_rate, seed)
+        if _events:
+            _events[2].record()
+        if self.grad_sync is not None:      # data parallel: NCCL all-reduce of the flat gradient
+            self.grad_sync()
         self.last_row_loss = row_loss
         self._keep = (ids, pos_t, teacher, trow, ex_pos_t, rep, d_rep)   # keep alive until the stream is done
         return self._loss

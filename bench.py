@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- train sessions/sec of the ADER hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: encoder forward, full-vocabulary logits +
+CE + adaptive distillation, backward (incl. embedding scatter) and the TF1-Adam update, on the
+shape of BASELINE.json configs[1] (YOOCHOOSE ADER, --batch_size=512): 512 train rows + 138
+exemplar rows per step, V = 18 661 items, V_prev = 17 421, table 25 959 rows (period 4 of the
+shipped split), synthetic sessions with the YOOCHOOSE length histogram.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (under torchrun): data parallel, one rank per GPU, per-rank batch fixed (weak scaling), one
+NCCL all-reduce (avg) of the flat gradient per step.  `--impl reference` times the reference's own
+CPU implementation of the same step (its torch-CPU restatement under oracle/, TensorFlow is not
+installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ---- workload: YOOCHOOSE ADER, period-4 shape (measured with the reference loaders) ----
+WL = dict(name="yoochoose_ader_train_step(period4 shape)", item_num=25958, B=512, M_e=138, V=18661, V_prev=17421,
+          lam=1.0, lr=5e-4, pool_rows=110699, exemplars=30000)
+# P(input length = k), k = 0..50, of YOOCHOOSE period-5 training rows (reference Sampler, seed 0)
+LEN_HIST = [0.0001, 0.3048, 0.1778, 0.1171, 0.0812, 0.0597, 0.0449, 0.0352, 0.0279, 0.0221, 0.018, 0.0148, 0.0124,
+            0.0102, 0.0086, 0.0072, 0.0063, 0.0053, 0.0046, 0.0041, 0.0036, 0.0031, 0.0028, 0.0024, 0.0022, 0.0018,
+            0.0017, 0.0016, 0.0014, 0.0012, 0.0011, 0.001, 0.0009, 0.0008, 0.0008, 0.0007, 0.0007, 0.0006, 0.0005,
+            0.0005, 0.0005, 0.0005, 0.0004, 0.0004, 0.0003, 0.0003, 0.0003, 0.0003, 0.0003, 0.0003, 0.0047]
+
+
+def make_args():
+    return type("Args", (), dict(hidden_units=150, maxlen=50, num_blocks=2, num_heads=1, random_seed=0, lr=WL["lr"],
+                                 dropout_rate=0.0, disable_distillation=False))()
+
+
+def synth_rows(rng, n, vmax, L=50):
+    p = np.array(LEN_HIST[1:], np.float64)
+    p /= p.sum()
+    lens = rng.choice(np.arange(1, L + 1), size=n, p=p)
+    ids = np.zeros((n, L), np.int32)
+    # item popularity ~ Zipf-like over 1..vmax (hot rows exercise the scatter)
+    u = rng.random_sample((n, L))
+    items = np.minimum(vmax, np.floor(vmax ** u).astype(np.int64)).astype(np.int32)
+    items = np.maximum(items, 1)
+    mask = np.arange(L)[None, :] >= (L - lens)[:, None]
+    ids[mask] = items[mask]
+    label = np.maximum(1, np.minimum(vmax, np.floor(vmax ** rng.random_sample(n)).astype(np.int64))).astype(np.int32)
+    return ids, label, lens.astype(np.int32)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = []
+        for ts, line in self.samples:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                rows.append((ts, float(f[0]), float(f[1]), f[3:7]))
+            except ValueError:
+                continue
+        inwin = [r for r in rows if any(a - 0.05 <= r[0] <= b + 0.05 for a, b in windows)] or rows
+        if not inwin:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in inwin for i in range(4) if r[3][i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median([r[1] for r in inwin])), "sm_max_mhz": inwin[0][2], "reasons": reasons,
+                "samples": len(inwin)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's algorithm on the host cores (oracle restatement)
+# --------------------------------------------------------------------------------------------------
+def cpu_step_fn():
+    import torch
+    from oracle import sasrec as S
+    hp = S.Hyper(WL["item_num"])
+    params = S.init_params(hp, 0)
+    rng = np.random.RandomState(1)
+    M = WL["B"] + WL["M_e"]
+    ids, label, _ = synth_rows(rng, M, WL["V"])
+    ids_t = torch.tensor(ids).long()
+    pos = torch.tensor(label[:WL["B"]])
+    teacher = torch.tensor(rng.standard_normal((WL["M_e"], WL["V_prev"])).astype(np.float32))
+    opt = S.AdamTF1(params)
+    state = {"params": params}
+
+    def step():
+        fn = lambda ps: S.loss_ader(ps, ids_t, pos, WL["V"], hp, WL["lam"], exemplar_logits=teacher)
+        loss, grads = S.grads_of(fn, state["params"])
+        state["params"] = opt.step(state["params"], grads, WL["lr"])
+        return loss
+
+    return step, M, torch.get_num_threads()
+
+
+def run_cpu(steps: int, warmup: int):
+    step, M, cores = cpu_step_fn()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return M * steps / dt, dt / steps * 1e3, cores, M
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded: as many of the K requested steps as fit in ~150 s of CPU time (one step is seconds)
+    step, M, cores = cpu_step_fn()
+    t0 = time.perf_counter(); step(); t1 = time.perf_counter() - t0
+    steps = int(max(1, min(args.steps, 150.0 / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val, ms = M * steps / dt, dt / steps * 1e3
+    sample = ("%d full steps (of %d requested; bounded to ~150 s) of %d rows, dense over 50 slots, [M,V] logits "
+              "materialised, torch-CPU fp32 restatement of the reference graph" % (steps, args.steps, M))
+    line = {"impl": "reference", "metric": "train sessions/sec", "value": val, "unit": "sessions/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1),
+            "cpu_baseline": {"value": val, "unit": "sessions/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": WL["name"], "batch_size": WL["B"], "exemplar_rows": WL["M_e"], "max_item": WL["V"],
+            "prev_max_item": WL["V_prev"], "table_rows": WL["item_num"] + 1, "lambda": WL["lam"], "maxlen": 50,
+            "hidden_units": 150, "num_blocks": 2, "global_batch": (WL["B"] + WL["M_e"]) * n,
+            "parallelism": "dp%d" % n if n > 1 else "single",
+            "l2": "per-step working set (theta+m+v+grad of %d rows, logits workspace) exceeds the 126 MB L2; "
+                  "inputs change every step" % (WL["V"] + 1)}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from ader_b200 import ops
+    from ader_b200.model import Ader
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    B, Me, V, Vp = WL["B"], WL["M_e"], WL["V"], WL["V_prev"]
+    M = B + Me
+
+    model = Ader(WL["item_num"], make_args(), device=dev, init_seed=0)
+    model.update_loss(WL["lam"])
+    if world > 1:
+        def sync_grad():
+            dist.all_reduce(model.grad, op=dist.ReduceOp.AVG)
+        model.grad_sync = sync_grad
+    rng = np.random.RandomState(100 + rank)
+    pool = 32768
+    t_ids, t_lab, t_len = synth_rows(rng, pool, V)
+    e_ids, e_lab, e_len = synth_rows(rng, WL["exemplars"], Vp)
+    d_t_ids, d_t_lab = torch.from_numpy(t_ids).to(dev), torch.from_numpy(t_lab).to(dev)
+    d_e_ids = torch.from_numpy(e_ids).to(dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(5 + rank)
+    teacher = torch.randn((WL["exemplars"], Vp), device=dev, generator=gen) * 2.0     # stored exemplar logits, HBM resident
+
+    nsteps = W + K
+    ti_all = [rng.randint(0, pool, B).astype(np.int32) for _ in range(nsteps)]
+    ei_all = [rng.randint(0, WL["exemplars"], Me).astype(np.int32) for _ in range(nsteps)]
+    ntok = [int(t_len[a].sum() + e_len[b].sum()) for a, b in zip(ti_all, ei_all)]
+    d_ti = [torch.from_numpy(a).to(dev) for a in ti_all]
+    d_ei = [torch.from_numpy(a).to(dev) for a in ei_all]
+    ids_buf = torch.empty((M, 50), dtype=torch.int32, device=dev)
+
+    def resident_step(i):
+        ops.gather_rows_i32(d_t_ids, d_ti[i], ids_buf[:B])
+        ops.gather_rows_i32(d_e_ids, d_ei[i], ids_buf[B:])
+        pos = d_t_lab[d_ti[i].long()]
+        return model.train_step(ids_buf, pos, V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=d_ei[i],
+                                n_tokens=ntok[i])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    windows = []
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------
+    for i in range(W):
+        resident_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for i in range(W, W + K):
+        resident_step(i)
+    e1.record()
+    barrier()
+    windows.append((w0, time.time()))
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = M * K * world / (ms_total / 1e3)
+
+    # ---- e2e: public API with HOST buffers, H2D of the step inputs + D2H of the loss every step ---
+    h_ids = [np.concatenate([t_ids[a], e_ids[b]]) for a, b in zip(ti_all, ei_all)]
+    h_pos = [t_lab[a] for a in ti_all]
+    for i in range(min(W, 3)):
+        float(model.train_step(h_ids[i], h_pos[i], V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=ei_all[i],
+                               n_tokens=ntok[i]).item())
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for i in range(W, W + K):
+        loss = model.train_step(h_ids[i], h_pos[i], V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=ei_all[i],
+                                n_tokens=ntok[i])
+        last_loss = float(loss.item())
+    e1.record()
+    barrier()
+    windows.append((w0, time.time()))
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = M * K * world / (ms_e2e / 1e3)
+    h2d = M * 50 * 4 + B * 4 + Me * 4
+    clock_info = clocks.stop(windows) if clocks else None
+
+    # ---- per-phase device times (CUDA events on the launching stream), averaged over the timed inputs
+    phases = {}
+    reps = min(K, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(reps)]
+    for r in range(reps):
+        i = W + r
+        ops.gather_rows_i32(d_t_ids, d_ti[i], ids_buf[:B])
+        ops.gather_rows_i32(d_e_ids, d_ei[i], ids_buf[B:])
+        pos = d_t_lab[d_ti[i].long()]
+        evs[r][0].record()
+        model.loss_and_grad(ids_buf, pos, V, exemplar_logits=teacher, teacher_rows=d_ei[i], n_tokens=ntok[i],
+                                    _events=evs[r][1:4])
+        model.apply_gradients(V, WL["lr"])
+        evs[r][4].record()
+    torch.cuda.synchronize()
+    for name, a, b in (("encoder_fwd", 0, 1), ("logits_ce_kd_fwd_bwd", 1, 2), ("encoder_bwd_scatter", 2, 3), ("adam", 3, 4)):
+        phases[name] = float(np.mean([evs[r][a].elapsed_time(evs[r][b]) for r in range(reps)]))
+
+    # ---- kernel launch count (CUPTI via torch.profiler, outside the timed regions) ----------------
+    launches_per_step = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            resident_step(W)
+            torch.cuda.synchronize()
+        names = [e.key for e in prof.key_averages() for _ in range(e.count) if e.device_type.name == "CUDA"]
+        mine = [n for n in names if "ader" in n or n.startswith("k_")]
+        launches_per_step = len(mine)
+    except Exception:
+        pass
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
+        flops = 6.0 * M * 150 * V                      # fwd + bwd of the output projection, d counted as 150
+        dom_ms = phases["logits_ce_kd_fwd_bwd"]
+        achieved = flops / (dom_ms * 1e-3) / 1e12
+        cpu_val, cpu_ms, cores, _ = run_cpu(2, 1)
+        line = {"metric": "train sessions/sec", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / K, "last_loss": last_loss},
+                "gpu_launches": (launches_per_step or 0) * K,
+                "gpu_launches_per_step": launches_per_step,
+                "clocks": clock_info,
+                "phases_ms": phases,
+                "roofline": {"kernel": "logits+CE+KD fwd+bwd group (ader_loss_fwd_bwd)", "bound": "tensor",
+                             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                             "traffic": None, "peak_source": peak_src,
+                             "algorithmic_flops_per_launch": flops},
+                "cpu_baseline": {"value": cpu_val, "unit": "sessions/s", "cores": cores, "kind": "port",
+                                 "sample": "2 full steps of %d rows after 1 warm-up, torch-CPU fp32 restatement" % M}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ader_b200")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -168,6 +168,11 @@ def test_adam_matches_tf1_adam():
         m.train_step(ids, pos, 250, lr=5e-4, dropout_rate=0.0)
     got = _views(m, m.theta)
     for i, (name, _) in enumerate(S.param_shapes(hp)):
+        if name.endswith(".bk"):
+            # d(loss)/d(bk) is identically zero (a key bias shifts every score of a softmax row by the
+            # same amount), so both sides feed rounding noise to Adam, which normalises it to +-lr.
+            assert float((got[i] - params[i]).abs().max()) <= 3 * 5e-4 * 1.01
+            continue
         # the first Adam steps move every touched weight by ~lr regardless of |g|: compare absolutely
         _close(got[i], cur[i], 0, 2e-5, "theta %s after 3 steps" % name)
     assert int(m.adam_state[0].item()) == 3
@@ -322,6 +327,8 @@ def test_fisher_and_ewc_step():
     m.train_step(b_ids, b_pos, 100, lr=5e-4, dropout_rate=0.0)
     got = _views(m, m.theta)
     for i, (name, _) in enumerate(S.param_shapes(hp)):
+        if name.endswith(".bk"):          # zero gradient by construction: Adam normalises rounding noise
+            continue
         _close(got[i], new[i], 0, 2e-5, "ewc step %s" % name)
 
 
