@@ -13,6 +13,7 @@ namespace ader {
 
 constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
 constexpr int SPLITS = 16;        // split-K partials for weight / LN / bias gradients
+constexpr int PG_LANES = 4;       // token lanes per column in the LN / position gradient reductions
 
 struct EncWs {
   int *row_len, *row_off, *tok_row, *tok_id, *flags;
@@ -258,29 +259,56 @@ __global__ void k_ln_param_grad(const float* __restrict__ dout, const float* __r
                                 const int* __restrict__ row_len, const int* __restrict__ row_off,
                                 int d, float* __restrict__ pbeta, float* __restrict__ pgamma,
                                 long long split_stride) {
-  const int c = threadIdx.x;
+  // blockDim = (ceil32(d), PG_LANES): thread (c, k) sums tokens lo+k, lo+k+PG_LANES, ... ; the
+  // PG_LANES partial sums are then added in lane order -> deterministic.
+  __shared__ float sb_s[PG_LANES][256], sg_s[PG_LANES][256];
+  const int c = threadIdx.x, k = threadIdx.y;
   const int s = blockIdx.x;
   const int count = row_off ? count_host : *dT;
   const int chunk = (count + gridDim.x - 1) / gridDim.x;
   const int lo = s * chunk, hi = min(count, lo + chunk);
-  if (c >= d) return;
   float sb = 0.f, sg = 0.f;
-  for (int i = lo; i < hi; ++i) {
-    long long xo, go; float mu, rs;
-    if (row_off) {
-      if (row_len[i] == 0) continue;
-      xo = (long long)(row_off[i + 1] - 1) * d; go = (long long)i * d; mu = mean[i]; rs = rstd[i];
-    } else { xo = go = (long long)i * d; mu = mean[i]; rs = rstd[i]; }
-    float g = dout[go + c];
-    sb += g; sg += g * ((x[xo + c] - mu) * rs);
+  if (c < d) {
+    for (int i = lo + k; i < hi; i += PG_LANES) {
+      long long xo, go; float mu, rs;
+      if (row_off) {
+        if (row_len[i] == 0) continue;
+        xo = (long long)(row_off[i + 1] - 1) * d; go = (long long)i * d; mu = mean[i]; rs = rstd[i];
+      } else { xo = go = (long long)i * d; mu = mean[i]; rs = rstd[i]; }
+      float g = dout[go + c];
+      sb += g; sg += g * ((x[xo + c] - mu) * rs);
+    }
   }
-  pbeta[(long long)s * split_stride + c] = sb;
-  pgamma[(long long)s * split_stride + c] = sg;
+  sb_s[k][c] = sb; sg_s[k][c] = sg;
+  __syncthreads();
+  if (k == 0 && c < d) {
+    float tb = 0.f, tg = 0.f;
+#pragma unroll
+    for (int q = 0; q < PG_LANES; ++q) { tb += sb_s[q][c]; tg += sg_s[q][c]; }
+    pbeta[(long long)s * split_stride + c] = tb;
+    pgamma[(long long)s * split_stride + c] = tg;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // causal self-attention per session row (modules.py:177-223).  CTA per row, 4 warps.
 // ------------------------------------------------------------------------------------------
+// copy n contiguous rows of d floats (d even) into padded shared rows; 4 float2 loads in flight
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, float* __restrict__ dst, int n, int d, int ld) {
+  const int n2 = (n * d) >> 1;
+  const float2* s2 = reinterpret_cast<const float2*>(src);
+  for (int base = threadIdx.x; base < n2; base += 4 * blockDim.x) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { int idx = base + u * blockDim.x; if (idx < n2) v[u] = s2[idx]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int idx = base + u * blockDim.x;
+      if (idx < n2) { int e = idx * 2; int i = e / d, c = e - i * d; dst[i * ld + c] = v[u].x; dst[i * ld + c + 1] = v[u].y; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K,
                                                   const float* __restrict__ V, const float* __restrict__ Q1,
                                                   const int* __restrict__ row_len, const int* __restrict__ row_off,
@@ -293,10 +321,9 @@ __global__ void __launch_bounds__(128) k_attn_fwd(const float* __restrict__ Q, c
   const int off = row_off[r];
   const int ld = d + 1;
   float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* ps = Vs + L * ld;  // ps [4][64]
-  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
-    int i = idx / d, c = idx % d; long long g = (long long)(off + i) * d + c;
-    Qs[i * ld + c] = Q[g]; Ks[i * ld + c] = K[g]; Vs[i * ld + c] = V[g];
-  }
+  stage_rows(Q + (long long)off * d, Qs, n, d, ld);
+  stage_rows(K + (long long)off * d, Ks, n, d, ld);
+  stage_rows(V + (long long)off * d, Vs, n, d, ld);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = d / nh;
@@ -360,10 +387,10 @@ __global__ void __launch_bounds__(128) k_attn_bwd(const float* __restrict__ Q, c
   const int ld = d + 1, lp = L + 1;
   float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* Gs = Vs + L * ld;
   float* dSs = Gs + L * ld; float* Pds = dSs + L * lp;
-  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
-    int i = idx / d, c = idx % d; long long g = (long long)(off + i) * d + c;
-    Qs[i * ld + c] = Q[g]; Ks[i * ld + c] = K[g]; Vs[i * ld + c] = V[g]; Gs[i * ld + c] = gY[g];
-  }
+  stage_rows(Q + (long long)off * d, Qs, n, d, ld);
+  stage_rows(K + (long long)off * d, Ks, n, d, ld);
+  stage_rows(V + (long long)off * d, Vs, n, d, ld);
+  stage_rows(gY + (long long)off * d, Gs, n, d, ld);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = d / nh;
@@ -441,19 +468,29 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, long long s
 __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__ row_len,
                            const int* __restrict__ row_off, int M, int L, int d,
                            float drop_p, uint64_t seed, float* __restrict__ gpos) {
-  const int p = blockIdx.x, c = threadIdx.x;
-  if (c >= d) return;
+  // blockDim = (ceil32(d), 4): thread (c, k) sums rows k, k+4, ...; lanes reduced in fixed order.
+  __shared__ float part[PG_LANES][256];
+  const int p = blockIdx.x, c = threadIdx.x, k = threadIdx.y;
   float s = 0.f;
-  for (int r = 0; r < M; ++r) {
-    int n = row_len[r];
-    if (n >= L - p) {
-      long long e = (long long)(row_off[r] + p - (L - n)) * d + c;
-      float v = gx[e];
-      if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)e, drop_p);
-      s += v;
+  if (c < d) {
+    for (int r = k; r < M; r += PG_LANES) {
+      int n = row_len[r];
+      if (n >= L - p) {
+        long long e = (long long)(row_off[r] + p - (L - n)) * d + c;
+        float v = gx[e];
+        if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)e, drop_p);
+        s += v;
+      }
     }
   }
-  gpos[p * d + c] = s;
+  part[k][c] = s;
+  __syncthreads();
+  if (k == 0 && c < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < PG_LANES; ++q) t += part[q][c];
+    gpos[p * d + c] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -561,17 +598,34 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys
     float acc[LN_MAXE];
 #pragma unroll
     for (int i = 0; i < LN_MAXE; ++i) acc[i] = 0.f;
-    for (int q = p; q < T && keys[q] == key; ++q) {
-      long long o = (long long)vals[q] * d;
+    int qe = p + 1;                                    // segment end: lanes probe 32 positions at a time
+    for (;;) {
+      int q = qe + lane;
+      unsigned diff = __ballot_sync(0xffffffffu, q >= T || keys[q] != key);
+      if (diff) { qe += __ffs(diff) - 1; break; }
+      qe += 32;
+    }
+    for (int q = p; q < qe; q += 4) {                  // 4 rows in flight, added in token order
+      float v[4][LN_MAXE];
 #pragma unroll
-      for (int i = 0; i < LN_MAXE; ++i) {
-        int c = lane + 32 * i;
-        if (c < d) {
-          float v = gx[o + c];
-          if (drop_p > 0.f) v *= drop_scale(seed, 0u, (uint64_t)(o + c), drop_p);
-          acc[i] += v;
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = q + u < qe;
+        long long o = ok ? (long long)vals[q + u] * d : 0;
+#pragma unroll
+        for (int i = 0; i < LN_MAXE; ++i) {
+          int c = lane + 32 * i;
+          float x = 0.f;
+          if (ok && c < d) {
+            x = gx[o + c];
+            if (drop_p > 0.f) x *= drop_scale(seed, 0u, (uint64_t)(o + c), drop_p);
+          }
+          v[u][i] = x;
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < LN_MAXE; ++i) acc[i] += v[u][i];
     }
 #pragma unroll
     for (int i = 0; i < LN_MAXE; ++i) {
@@ -729,7 +783,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
 
   // final LayerNorm (ADER.py:82): only the last token of each row carries gradient
   k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, gX, dT, d);
-  k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
   ADER_CHECK_LAUNCH("encoder_bwd/final_ln");
 
@@ -752,7 +806,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     // gZ = gH . W1^T + gX   (residual z -> x_out)
     if (int e = run_dense(st, gH, P + l.w1, nullptr, gZ, Tcap, dT, d, true, 0, gX, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     k_ln_bwd<<<ln_grid, 256, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], P + l.ln2g, gY, dT, d, 0);
-    k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
+    k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
                                                    part(bo + l.ln2b), part(bo + l.ln2g), PS);
     k_attn_bwd<<<M, 128, attn_smem, st>>>(Qp, Kp, Vp, w.probs[b], gY, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
                                           p, seed, 1u + 3u * b, gQ, gK, gV);
@@ -765,7 +819,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     if (int e = run_dense(st, gK, P + l.wk, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     if (int e = run_dense(st, gV, P + l.wv, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 1, 1.f, 0.f, 0, 0)) return e;
     k_ln_bwd<<<ln_grid, 256, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], P + l.ln1g, gXin, dT, d, 1);
-    k_ln_param_grad<<<SPLITS, ln_threads, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], dT, 0, nullptr, nullptr, d,
+    k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], dT, 0, nullptr, nullptr, d,
                                                    part(bo + l.ln1b), part(bo + l.ln1g), PS);
     ADER_CHECK_LAUNCH("encoder_bwd/block");
     float* t = gX; gX = gXin; gXin = t;
@@ -777,7 +831,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     k_reduce_partials<<<cdiv(hi - lo, 256), 256, 0, st>>>(g.partial, PS, SPLITS, lo, hi, grad + l.off_pos);
   }
   // position table (ADER.py:41-52) and item-table scatter (modules.py:127-130)
-  k_pos_grad<<<L, ln_threads, 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
+  k_pos_grad<<<L, dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
   {
     const int ntiles = sort_tiles(Tcap);
     const int bits = key_bits(m->v_tab);

@@ -1,0 +1,553 @@
+// Fused output projection + online-softmax CE + ADER distillation on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM), ADER.py:88-93 / 108-138.  The [M, V] logits never touch HBM.
+//
+// Operand format in HBM ("T128"): the bf16 shadow of the item table and of `rep` are stored as
+// tiles of 128 rows x 160 k (d = 150 zero-padded to 160), each tile pre-arranged as the UMMA
+// no-swizzle canonical layout: 8x8 core matrices (8 rows x 16 B, 128 B contiguous), core (rg, kc)
+// at byte (kc*16 + rg)*128.  One tile = 40 960 contiguous bytes = ONE cp.async.bulk into shared
+// memory, no tensor map, no swizzle.  The same tile serves as
+//   - K-major operand (K = feature): SBO = 128 B (row groups), LBO = 2048 B (k groups), and
+//   - MN-major B operand (N = feature, K = row): SBO = 2048 B, LBO = 128 B
+// so forward (S = rep.E^T) and both backward products (dRep = dS.E, dE = dS^T.rep) read the same bytes.
+//
+// Kernel roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane) +
+// TMEM allocator, warps 2..5 = epilogue (one TMEM lane = one logits row per thread).
+//   MODE_FWD : per (row-tile, vocab-chunk) CTA: S tiles -> online (max, sumexp), label logit, KD dot
+//   MODE_DREP: same loop; dS (bf16) is staged in shared memory and a second MMA accumulates
+//              dRep[128, 160] in TMEM across the CTA's vocab tiles
+//   MODE_DE  : per vocab-tile CTA, loops over row tiles; second MMA accumulates dE[128, 160]
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+namespace ader {
+namespace tc {
+
+constexpr int TILE = 128;
+constexpr int KP = 160;                       // padded feature dim
+constexpr int TILE_BYTES = TILE * KP * 2;     // 40960
+constexpr int DS_BYTES = TILE * TILE * 2;     // 32768
+constexpr int KSTEPS1 = KP / 16;              // 10 MMAs per S tile
+constexpr int KSTEPS2 = TILE / 16;            // 8 MMAs per gradient tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum { MODE_FWD = 0, MODE_DREP = 1, MODE_DE = 2 };
+
+struct TcArgs {
+  const uint8_t* rep_tiles;     // [n_mtiles][TILE_BYTES]
+  const uint8_t* e_tiles;       // [n_vtiles][TILE_BYTES]
+  int M, V, n_mtiles, n_vtiles, n_chunks;
+  // loss description
+  int n_train, n_ex, V_prev, mode;
+  float coef_train, coef_ex;    // 1/n_train, lambda/n_ex
+  const int* pos; const int* ex_pos;
+  const float* teacher; const int* teacher_row; long long teacher_ld;
+  const float* lse;             // [M]   (backward)
+  const float* lse_t;           // [n_ex] teacher log-sum-exp
+  float* stats;                 // FWD: [n_chunks][M][4] = (max, sumexp, label logit, kd dot)
+  float* drep_part;             // DREP: [n_chunks][n_mtiles*128][160]
+  float* grad_table;            // DE: grad + d (row of item 1), row stride d
+  int d;
+  int variant;                  // debug: bit0 swaps LBO/SBO of K-major descriptors, bit1 of MN-major ones
+  int* err;                     // device error flag (barrier timeout)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && spin > (1u << 24)) {            // a broken pipeline must not hang the GPU
+      if (err) atomicExch(err, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// per-row description of the loss (shared by all modes)
+struct RowInfo {
+  int kind;           // 0 none (row >= M), 1 one-hot CE over V, 2 KD over V_prev
+  int vlim;           // softmax width
+  int label;          // 0-based column of the one-hot label (kind 1), else -1
+  float coef;         // dS scale
+  float lse2;         // lse * log2(e)  (backward)
+  float lset2;        // teacher lse * log2(e)
+  const float* trow;  // teacher row (kind 2)
+};
+__device__ __forceinline__ RowInfo row_info(const TcArgs& a, int gm, bool bwd) {
+  RowInfo r; r.kind = 0; r.vlim = 0; r.label = -1; r.coef = 0.f; r.lse2 = 0.f; r.lset2 = 0.f; r.trow = nullptr;
+  if (gm >= a.M) return r;
+  if (gm < a.n_train) { r.kind = 1; r.vlim = a.V; r.label = a.pos[gm] - 1; r.coef = a.coef_train; }
+  else if (a.mode == 2) { r.kind = 1; r.vlim = a.V; r.label = a.ex_pos[gm - a.n_train] - 1; r.coef = a.coef_ex; }
+  else {
+    const int e = gm - a.n_train;
+    r.kind = 2; r.vlim = a.V_prev; r.coef = a.coef_ex;
+    const long long tr = a.teacher_row ? a.teacher_row[e] : e;
+    r.trow = a.teacher + tr * a.teacher_ld;
+    r.lset2 = a.lse_t[e] * LOG2E;
+  }
+  if (bwd) r.lse2 = a.lse[gm] * LOG2E;
+  return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve: [X stationary tile][Y stage 0][Y stage 1][dS 0][dS 1][barriers]
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + TILE_BYTES;
+  uint8_t* sD = smem + 3 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + (MODE == MODE_FWD ? 0 : 2 * DS_BYTES));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // barrier ids
+  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 3, B_TFULL = 5, B_TEMPTY = 7, B_DSFULL = 9, B_DSEMPTY = 11, B_ACC = 13;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work assignment -------------------------------------------------------------------
+  int x_tile, y_lo, y_hi;      // stationary tile index, streamed tile range
+  int chunk = 0;
+  if (MODE == MODE_DE) { x_tile = blockIdx.x; y_lo = 0; y_hi = a.n_mtiles; }
+  else {
+    x_tile = blockIdx.x % a.n_mtiles; chunk = blockIdx.x / a.n_mtiles;
+    const int per = (a.n_vtiles + a.n_chunks - 1) / a.n_chunks;
+    y_lo = chunk * per; y_hi = min(a.n_vtiles, y_lo + per);
+  }
+  const int n_it = max(0, y_hi - y_lo);
+  const uint8_t* gX = (MODE == MODE_DE ? a.e_tiles : a.rep_tiles) + (size_t)x_tile * TILE_BYTES;
+  const uint8_t* gY = (MODE == MODE_DE ? a.rep_tiles : a.e_tiles);
+
+  // ---- setup ---------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(B_XFULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1);
+      mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), 128);
+      mbar_init(BAR(B_DSFULL + s), 128); mbar_init(BAR(B_DSEMPTY + s), 1);
+    }
+    mbar_init(BAR(B_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = (MODE == MODE_FWD) ? 256u : 512u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t ACC_COL = 256;
+
+  if (warp == 0) {
+    // ===== producer: one elected lane issues bulk copies ========================================
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(BAR(B_XFULL), TILE_BYTES);
+      bulk_g2s(smem_u32(sX), gX, TILE_BYTES, BAR(B_XFULL));
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(BAR(B_YEMPTY + s), ph ^ 1, a.err);
+        mbar_expect_tx(BAR(B_YFULL + s), TILE_BYTES);
+        bulk_g2s(smem_u32(sY + s * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, TILE_BYTES, BAR(B_YFULL + s));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ===============================================================================
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t IDESC1 = make_idesc(128, 128, 0, 0);
+      constexpr uint32_t IDESC2 = (MODE == MODE_DE) ? make_idesc(128, KP, 1, 1) : make_idesc(128, KP, 0, 1);
+      const uint32_t xa = smem_u32(sX);
+      const bool swk = a.variant & 1, swm = a.variant & 2;
+      auto kdesc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) { return swk ? make_desc(addr, sbo, lbo) : make_desc(addr, lbo, sbo); };
+      auto mdesc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) { return swm ? make_desc(addr, sbo, lbo) : make_desc(addr, lbo, sbo); };
+      auto issue_s = [&](int it) {          // S[buf] = rep_tile . e_tile^T
+        const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(BAR(B_YFULL + s), ph, a.err);
+        mbar_wait(BAR(B_TEMPTY + s), ph ^ 1, a.err);
+        tc_fence_after();
+        const uint32_t ya = smem_u32(sY + s * TILE_BYTES);
+        const uint32_t A = (MODE == MODE_DE) ? ya : xa;     // rows of S = logits rows (rep)
+        const uint32_t B = (MODE == MODE_DE) ? xa : ya;
+#pragma unroll
+        for (int k = 0; k < KSTEPS1; ++k)
+          umma_bf16(tmem + s * 128, kdesc(A + k * 4096, 2048, 128), kdesc(B + k * 4096, 2048, 128), IDESC1, k > 0);
+        if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + s));
+        umma_commit(BAR(B_TFULL + s));
+      };
+      mbar_wait(BAR(B_XFULL), 0, a.err);
+      issue_s(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_s(it + 1);
+        if (MODE != MODE_FWD) {
+          const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(BAR(B_DSFULL + s), ph, a.err);
+          tc_fence_after();
+          const uint32_t da = smem_u32(sD + s * DS_BYTES);
+          const uint32_t ya = smem_u32(sY + s * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KSTEPS2; ++k) {
+            // dS tile: core (vg, mg) at (vg*16 + mg)*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=2048,
+            // k-step = 2 v-groups = 4096 B.  DE: A MN-major (M=v, K=m): SBO=2048, LBO=128, k-step = 256 B.
+            const uint64_t ad = (MODE == MODE_DE) ? mdesc(da + k * 256, 128, 2048) : kdesc(da + k * 4096, 2048, 128);
+            // streamed T128 tile as MN-major B (N = feature, K = tile row): SBO=2048, LBO=128, k-step = 256 B
+            const uint64_t bd = mdesc(ya + k * 256, 128, 2048);
+            umma_bf16(tmem + ACC_COL, ad, bd, IDESC2, (it > 0 || k > 0));
+          }
+          umma_commit(BAR(B_YEMPTY + s));
+          umma_commit(BAR(B_DSEMPTY + s));
+        }
+      }
+      if (MODE != MODE_FWD) umma_commit(BAR(B_ACC));
+    }
+  } else {
+    // ===== epilogue: TMEM lane = logits row ===========================================================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;             // row inside the 128-row tile
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    RowInfo ri;
+    float mx = -INFINITY, sum = 0.f, lab = 0.f, dot = 0.f;
+    if (MODE != MODE_DE) ri = row_info(a, x_tile * TILE + row, MODE != MODE_FWD);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+      int v0;
+      if (MODE == MODE_DE) { ri = row_info(a, (y_lo + it) * TILE + row, true); v0 = x_tile * TILE; }
+      else v0 = (y_lo + it) * TILE;
+      mbar_wait(BAR(B_TFULL + s), ph, a.err);
+      tc_fence_after();
+      if (MODE != MODE_FWD) mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+      uint8_t* ds = sD + s * DS_BYTES;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t r[32];
+        tmem_ld32(tmem + tlane + s * 128 + c4 * 32, r);
+        const int vb = v0 + c4 * 32;
+        if (MODE == MODE_FWD) {
+          if (ri.kind != 0 && vb < ri.vlim) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(r[i]));
+            const float nm = fmaxf(mx, cm);
+            sum *= ex2((mx - nm) * LOG2E);
+            mx = nm;
+            const float nm2 = nm * LOG2E;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int v = vb + i;
+              if (v < ri.vlim) {
+                const float sv = __uint_as_float(r[i]);
+                sum += ex2(fmaf(sv, LOG2E, -nm2));
+                if (v == ri.label) lab = sv;
+                if (ri.kind == 2) dot = fmaf(ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)), sv, dot);
+              }
+            }
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float g2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int v = vb + i + u;
+              float g = 0.f;
+              if (ri.kind != 0 && v < ri.vlim) {
+                const float p = ex2(fmaf(__uint_as_float(r[i + u]), LOG2E, -ri.lse2));
+                if (ri.kind == 1) g = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
+                else g = ri.coef * (p - ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)));
+              }
+              g2[u] = g;
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {      // 8 columns = one 16-byte core-matrix row
+            const int vg = c4 * 4 + gq;
+            uint4 val = make_uint4(pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2], pk[gq * 4 + 3]);
+            *reinterpret_cast<uint4*>(ds + (vg * 16 + (row >> 3)) * 128 + (row & 7) * 16) = val;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + s));
+      if (MODE != MODE_FWD) {
+        fence_async_smem();                    // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(BAR(B_DSFULL + s));
+      }
+    }
+    if (MODE == MODE_FWD) {
+      const int gm = x_tile * TILE + row;
+      if (gm < a.M) {
+        float4 o = make_float4(mx, sum, lab, dot);
+        *reinterpret_cast<float4*>(a.stats + ((size_t)chunk * a.M + gm) * 4) = o;
+      }
+    } else if (n_it > 0) {
+      mbar_wait(BAR(B_ACC), 0, a.err);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c4 = 0; c4 < KP / 32; ++c4) {
+        uint32_t r[32];
+        tmem_ld32(tmem + tlane + ACC_COL + c4 * 32, r);
+        if (MODE == MODE_DREP) {
+          float* o = a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP + c4 * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                            __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        } else {
+          const int v = x_tile * TILE + row;
+          if (v < a.V) {
+            float* o = a.grad_table + (size_t)v * a.d + c4 * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c4 * 32 + i < a.d) o[i] = __uint_as_float(r[i]);
+          }
+        }
+      }
+      tc_fence_before();
+    } else if (MODE == MODE_DREP) {           // empty chunk: its partial must still be defined
+      float* o = a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP;
+      for (int i = 0; i < KP; ++i) o[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- operand packing: fp32 rows -> bf16 T128 tiles --------------------------------------------
+// one thread per (row, 8-wide k group); rows >= n_rows and k >= d are zero.
+__global__ void k_pack_tiles(const float* __restrict__ src, long long ld, int n_rows, int d, int n_tiles,
+                             uint8_t* __restrict__ tiles) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_tiles * TILE * (KP / 8);
+  if (idx >= total) return;
+  const int kc = (int)(idx % (KP / 8));
+  const long long rr = idx / (KP / 8);
+  const int tile = (int)(rr / TILE), r = (int)(rr % TILE);
+  const long long grow = (long long)tile * TILE + r;
+  uint32_t pk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v0 = 0.f, v1 = 0.f;
+    const int k = kc * 8 + i * 2;
+    if (grow < n_rows) {
+      if (k < d) v0 = src[grow * ld + k];
+      if (k + 1 < d) v1 = src[grow * ld + k + 1];
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(tiles + (size_t)tile * TILE_BYTES + (kc * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
+      make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// teacher log-sum-exp per exemplar row (CTA per row)
+__global__ void __launch_bounds__(256) k_teacher_lse(const float* __restrict__ teacher, const int* __restrict__ teacher_row,
+                                                     long long ld, int Vp, float* __restrict__ lse_t) {
+  __shared__ float sh[8];
+  const int e = blockIdx.x;
+  const float* t = teacher + (long long)(teacher_row ? teacher_row[e] : e) * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < Vp; j += 256) mx = fmaxf(mx, t[j]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sh[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < Vp; j += 256) s += expf(t[j] - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < 8; ++w) tot += sh[w]; lse_t[e] = mx + logf(tot); }
+}
+
+// merge the per-chunk online-softmax partials: lse[M], row_loss[M]
+__global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chunks, int n_train, int mode,
+                              float* __restrict__ lse, float* __restrict__ row_loss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float mx = -INFINITY;
+  for (int c = 0; c < n_chunks; ++c) mx = fmaxf(mx, stats[((size_t)c * M + i) * 4]);
+  float sum = 0.f, lab = 0.f, dot = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const float4 s = *reinterpret_cast<const float4*>(stats + ((size_t)c * M + i) * 4);
+    if (s.x > -INFINITY) sum += s.y * expf(s.x - mx);
+    lab += s.z; dot += s.w;
+  }
+  const float l = mx + logf(sum);
+  lse[i] = l;
+  const bool kd = (i >= n_train) && mode == 1;
+  row_loss[i] = kd ? l - dot : l - lab;
+}
+
+// d_rep[M, d] = sum over chunks of the padded partials
+__global__ void k_reduce_drep(const float* __restrict__ part, int n_chunks, int rows_pad, int M, int d,
+                              float* __restrict__ d_rep) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * d) return;
+  const int i = (int)(idx / d), c = (int)(idx % d);
+  float s = 0.f;
+  for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows_pad + i) * KP + c];
+  d_rep[idx] = s;
+}
+
+}  // namespace tc
+}  // namespace ader
+
+using namespace ader;
+using namespace ader::tc;
+
+// loss_reduce lives in loss.cu
+namespace ader { int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st); }
+
+struct TcWs {
+  uint8_t *rep_tiles, *e_tiles;
+  float *stats, *lse, *lse_t, *drep_part;
+  int* err;
+  size_t bytes;
+};
+static int tc_chunks(int n_mtiles, int n_vtiles) {
+  int c = 148 / n_mtiles; if (c < 1) c = 1; if (c > n_vtiles) c = n_vtiles; return c;
+}
+static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, char* base) {
+  TcWs w; size_t o = 0;
+  auto take = [&](size_t n) { char* p = base ? base + o : nullptr; o += align_up(n); return p; };
+  const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
+  w.rep_tiles = (uint8_t*)take((size_t)nm * TILE_BYTES);
+  w.e_tiles = (uint8_t*)take((size_t)nv * TILE_BYTES);
+  w.stats = (float*)take(sizeof(float) * 4 * (size_t)nc * M);
+  w.lse = (float*)take(sizeof(float) * M);
+  w.lse_t = (float*)take(sizeof(float) * (n_ex > 0 ? n_ex : 1));
+  w.drep_part = (float*)take(sizeof(float) * (size_t)nc * nm * TILE * KP);
+  w.err = (int*)take(sizeof(int) * 4);
+  w.bytes = o;
+  return w;
+}
+
+extern "C" size_t ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a) {
+  if (check_model(m) || !a || a->M <= 0 || a->V <= 0) return 0;
+  return carve_tc(m, a->M, a->V, a->n_ex, nullptr).bytes;
+}
+
+extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
+                                        const AderLossArgs* a, void* ws, float* loss, float* row_loss,
+                                        float* d_rep, float* grad, void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && rep && a && ws && loss && row_loss, "loss_fwd_bwd_tc: NULL pointer");
+  ADER_CHECK_ARG(m->d <= KP && m->d % 2 == 0, "loss_fwd_bwd_tc: hidden_units must be <= %d", KP);
+  ADER_CHECK_ARG(a->M == a->n_train + a->n_ex && a->M > 0, "loss_fwd_bwd_tc: M != n_train + n_ex");
+  ADER_CHECK_ARG(a->V >= 1 && a->V < m->v_tab, "loss_fwd_bwd_tc: max_item outside the table");
+  ADER_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "loss_fwd_bwd_tc: bad mode");
+  ADER_CHECK_ARG(a->n_train == 0 || a->pos, "loss_fwd_bwd_tc: pos is NULL");
+  if (a->n_ex > 0) {
+    ADER_CHECK_ARG(a->mode != 0, "loss_fwd_bwd_tc: exemplar rows given in vanilla mode");
+    if (a->mode == 1) ADER_CHECK_ARG(a->teacher && a->V_prev >= 1 && a->V_prev <= a->V && a->teacher_ld >= a->V_prev, "loss_fwd_bwd_tc: bad teacher");
+    if (a->mode == 2) ADER_CHECK_ARG(a->ex_pos, "loss_fwd_bwd_tc: exemplar_pos is NULL");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = m->d, M = a->M, V = a->V;
+  TcWs w = carve_tc(m, M, V, a->n_ex, (char*)ws);
+  const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
+
+  static bool attr_set = false;
+  const int smem_fwd = 3 * TILE_BYTES + 256, smem_bwd = 3 * TILE_BYTES + 2 * DS_BYTES + 256;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
+    cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+    cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+    attr_set = true;
+  }
+  cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
+  k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
+  k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + d, d, V, d, nv, w.e_tiles);
+  const bool kd = a->n_ex > 0 && a->mode == 1;
+  if (kd) k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
+  ADER_CHECK_LAUNCH("tc pack");
+
+  TcArgs t;
+  t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = V; t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
+  t.n_train = a->n_train; t.n_ex = a->n_ex; t.V_prev = a->V_prev; t.mode = a->n_ex > 0 ? a->mode : 0;
+  t.coef_train = a->n_train > 0 ? 1.0f / (float)a->n_train : 0.f;
+  t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)a->n_ex : 0.f;
+  t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
+  t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
+  t.d = d; t.err = w.err;
+  { const char* v = getenv("ADER_TC_VARIANT"); t.variant = v ? atoi(v) : 0; }
+
+  k_tc_logits<MODE_FWD><<<nm * nc, 192, smem_fwd, st>>>(t);
+  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc, a->n_train, t.mode, w.lse, row_loss);
+  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st)) return e;
+  ADER_CHECK_LAUNCH("tc fwd");
+  if (d_rep) {
+    k_tc_logits<MODE_DREP><<<nm * nc, 192, smem_bwd, st>>>(t);
+    k_reduce_drep<<<cdiv((long long)M * d, 256), 256, 0, st>>>(w.drep_part, nc, nm * TILE, M, d, d_rep);
+    ADER_CHECK_LAUNCH("tc d_rep");
+  }
+  if (grad) {
+    k_tc_logits<MODE_DE><<<nv, 192, smem_bwd, st>>>(t);
+    ADER_CHECK_LAUNCH("tc d_table");
+  }
+  return 0;
+}

@@ -96,6 +96,12 @@ __global__ void k_reduce_splits(const float* __restrict__ partial, long long str
   out[i] = s;
 }
 
+int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st) {
+  k_loss_reduce<<<1, 256, 0, st>>>(row_loss, n_train, n_ex, lambda_, loss);
+  ADER_CHECK_LAUNCH("loss_reduce");
+  return 0;
+}
+
 static long long logits_ld(int V) { return ((long long)V + 3) / 4 * 4; }
 
 static int run_logits(const AderModel* m, const float* theta, const float* rep, int M, int V, float* out,

@@ -45,28 +45,39 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   const bool a_kfast = (g.a_cs == 1);   // k contiguous in A
   const bool b_nfast = (g.b_cs == 1);   // n contiguous in B
 
-  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+  // register-staged double buffering: the global loads of tile k+1 are in flight while tile k is
+  // multiplied out of shared memory.
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int idx = tid + i * 256;
       int mm, kk;
       if (a_kfast) { kk = idx & (BK - 1); mm = idx >> 4; } else { mm = idx & (BM - 1); kk = idx >> 6; }
       int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < M && gk < k_hi) v = g.A[(long long)gm * g.a_rs + (long long)gk * g.a_cs];
-      As[kk][mm] = v;
+      ra[i] = (gm < M && gk < k_hi) ? g.A[(long long)gm * g.a_rs + (long long)gk * g.a_cs] : 0.f;
+      int nn;
+      if (b_nfast) { nn = idx & (BN - 1); kk = idx >> 6; } else { kk = idx & (BK - 1); nn = idx >> 4; }
+      int gn = n0 + nn; gk = k0 + kk;
+      rb[i] = (gn < N && gk < k_hi) ? g.B[(long long)gk * g.b_rs + (long long)gn * g.b_cs] : 0.f;
     }
+  };
+  auto store_tile = [&]() {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int idx = tid + i * 256;
-      int nn, kk;
+      int mm, kk, nn;
+      if (a_kfast) { kk = idx & (BK - 1); mm = idx >> 4; } else { mm = idx & (BM - 1); kk = idx >> 6; }
+      As[kk][mm] = ra[i];
       if (b_nfast) { nn = idx & (BN - 1); kk = idx >> 6; } else { kk = idx & (BK - 1); nn = idx >> 4; }
-      int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < N && gk < k_hi) v = g.B[(long long)gk * g.b_rs + (long long)gn * g.b_cs];
-      Bs[kk][nn] = v;
+      Bs[kk][nn] = rb[i];
     }
-    __syncthreads();
+  };
+  if (k_lo < k_hi) { load_tile(k_lo); store_tile(); }
+  __syncthreads();
+  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+    const bool has_next = k0 + BK < k_hi;
+    if (has_next) load_tile(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -82,6 +93,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
         for (int j = 0; j < 4; ++j) bsum[j] += bv[j];
       }
     }
+    __syncthreads();
+    if (has_next) store_tile();
     __syncthreads();
   }
 

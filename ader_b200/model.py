@@ -68,6 +68,7 @@ class Ader:
         self.mode = self.VANILLA
         self.lambda_ = 0.0
         self.grad_sync = None
+        self.loss_impl = getattr(args, "loss_impl", "exact")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
         self._enc_ws = ops.Workspace(self.device)
         self._bwd_ws = ops.Workspace(self.device)
@@ -168,10 +169,14 @@ class Ader:
             _events[0].record()
         a = ops.make_loss_args(M, n_train, n_ex, max_item, v_prev, mode if n_ex > 0 else self.VANILLA, lam,
                                pos_t, ex_pos_t, teacher, trow)
-        ws = self._loss_ws.get(ops.loss_ws_bytes(self.ms, a))
         row_loss = torch.empty(M, dtype=torch.float32, device=self.device)
         d_rep = torch.empty_like(rep)
-        ops.loss_fwd_bwd(self.ms, self.theta, rep, a, ws, self._loss, row_loss, d_rep, self.grad)
+        if self.loss_impl == "tc":       # tcgen05 fused kernels (bf16 operands)
+            ws = self._loss_ws.get(ops.loss_tc_ws_bytes(self.ms, a))
+            ops.loss_fwd_bwd_tc(self.ms, self.theta, rep, a, ws, self._loss, row_loss, d_rep, self.grad)
+        else:                            # exact fp32 path
+            ws = self._loss_ws.get(ops.loss_ws_bytes(self.ms, a))
+            ops.loss_fwd_bwd(self.ms, self.theta, rep, a, ws, self._loss, row_loss, d_rep, self.grad)
         if _events:
             _events[1].record()
         bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))

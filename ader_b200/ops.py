@@ -106,6 +106,20 @@ def loss_fwd_bwd(ms: AderModel, theta, rep, a: AderLossArgs, ws, loss, row_loss,
                                         _ptr(row_loss), _ptr(d_rep), _ptr(grad), _stream()), "loss_fwd_bwd")
 
 
+def loss_tc_ws_bytes(ms: AderModel, a: AderLossArgs) -> int:
+    n = _lib.load().ader_loss_tc_ws_bytes(C.byref(ms), C.byref(a))
+    if n == 0:
+        raise _lib.AderError("loss_tc_ws_bytes: bad model / sizes")
+    return n
+
+
+def loss_fwd_bwd_tc(ms: AderModel, theta, rep, a: AderLossArgs, ws, loss, row_loss, d_rep, grad):
+    """tcgen05 fused logits + CE + KD forward/backward (bf16 operands, fp32 accumulation)."""
+    _require_cuda(theta, rep, ws, loss, row_loss, d_rep, grad)
+    check(_lib.load().ader_loss_fwd_bwd_tc(C.byref(ms), _ptr(theta), _ptr(rep), C.byref(a), _ptr(ws), _ptr(loss),
+                                           _ptr(row_loss), _ptr(d_rep), _ptr(grad), _stream()), "loss_fwd_bwd_tc")
+
+
 def logits(ms: AderModel, theta, rep, V: int, out):
     """out [M, >=V] fp32 = rep . E[1..V]^T (ADER.py:90-91)."""
     _require_cuda(theta, rep, out)

@@ -94,6 +94,13 @@ size_t  ader_loss_ws_bytes(const AderModel* m, const AderLossArgs* a);
 int32_t ader_loss_fwd_bwd(const AderModel* m, const float* theta, const float* rep,
                           const AderLossArgs* a, void* ws, float* loss, float* row_loss,
                           float* d_rep, float* grad, void* stream);
+/* Same contract on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM): fused
+ * logits + online-softmax CE + distillation, [M, V] logits never materialised in HBM.  Results
+ * agree with ader_loss_fwd_bwd to bf16 operand rounding (tests state the tolerance). */
+size_t  ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a);
+int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
+                             const AderLossArgs* a, void* ws, float* loss, float* row_loss,
+                             float* d_rep, float* grad, void* stream);
 /* logits [M, V] fp32 = rep . E[1..V]^T  (fetch `logits`, util.py:452,482,514). ld = row stride. */
 int32_t ader_logits(const AderModel* m, const float* theta, const float* rep, int32_t M, int32_t V,
                     float* logits, int64_t ld, void* stream);
