@@ -48,7 +48,6 @@ struct TcArgs {
   float* drep_part;             // DREP: [n_chunks][n_mtiles*128][160]
   float* grad_table;            // DE: grad + d (row of item 1), row stride d
   int d;
-  int variant;                  // debug: bit0 swaps LBO/SBO of K-major descriptors, bit1 of MN-major ones
   int* err;                     // device error flag (barrier timeout)
 };
 
@@ -213,9 +212,6 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
       constexpr uint32_t IDESC1 = make_idesc(128, 128, 0, 0);
       constexpr uint32_t IDESC2 = (MODE == MODE_DE) ? make_idesc(128, KP, 1, 1) : make_idesc(128, KP, 0, 1);
       const uint32_t xa = smem_u32(sX);
-      const bool swk = a.variant & 1, swm = a.variant & 2;
-      auto kdesc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) { return swk ? make_desc(addr, sbo, lbo) : make_desc(addr, lbo, sbo); };
-      auto mdesc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) { return swm ? make_desc(addr, sbo, lbo) : make_desc(addr, lbo, sbo); };
       auto issue_s = [&](int it) {          // S[buf] = rep_tile . e_tile^T
         const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
         mbar_wait(BAR(B_YFULL + s), ph, a.err);
@@ -226,7 +222,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
         const uint32_t B = (MODE == MODE_DE) ? xa : ya;
 #pragma unroll
         for (int k = 0; k < KSTEPS1; ++k)
-          umma_bf16(tmem + s * 128, kdesc(A + k * 4096, 2048, 128), kdesc(B + k * 4096, 2048, 128), IDESC1, k > 0);
+          umma_bf16(tmem + s * 128, make_desc(A + k * 4096, 2048, 128), make_desc(B + k * 4096, 2048, 128), IDESC1, k > 0);
         if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + s));
         umma_commit(BAR(B_TFULL + s));
       };
@@ -244,9 +240,9 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
           for (int k = 0; k < KSTEPS2; ++k) {
             // dS tile: core (vg, mg) at (vg*16 + mg)*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=2048,
             // k-step = 2 v-groups = 4096 B.  DE: A MN-major (M=v, K=m): SBO=2048, LBO=128, k-step = 256 B.
-            const uint64_t ad = (MODE == MODE_DE) ? mdesc(da + k * 256, 128, 2048) : kdesc(da + k * 4096, 2048, 128);
+            const uint64_t ad = (MODE == MODE_DE) ? make_desc(da + k * 256, 128, 2048) : make_desc(da + k * 4096, 2048, 128);
             // streamed T128 tile as MN-major B (N = feature, K = tile row): SBO=2048, LBO=128, k-step = 256 B
-            const uint64_t bd = mdesc(ya + k * 256, 128, 2048);
+            const uint64_t bd = make_desc(ya + k * 256, 128, 2048);
             umma_bf16(tmem + ACC_COL, ad, bd, IDESC2, (it > 0 || k > 0));
           }
           umma_commit(BAR(B_YEMPTY + s));
@@ -534,7 +530,6 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
-  { const char* v = getenv("ADER_TC_VARIANT"); t.variant = v ? atoi(v) : 0; }
 
   k_tc_logits<MODE_FWD><<<nm * nc, 192, smem_fwd, st>>>(t);
   k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc, a->n_train, t.mode, w.lse, row_loss);

@@ -68,7 +68,7 @@ class Ader:
         self.mode = self.VANILLA
         self.lambda_ = 0.0
         self.grad_sync = None
-        self.loss_impl = getattr(args, "loss_impl", "exact")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
+        self.loss_impl = getattr(args, "loss_impl", "tc")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
         self._enc_ws = ops.Workspace(self.device)
         self._bwd_ws = ops.Workspace(self.device)

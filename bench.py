@@ -320,7 +320,7 @@ def gpu_arm(args):
         cpu_val, cpu_ms, cores, _ = run_cpu(2, 1)
         line = {"metric": "train sessions/sec", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (logits+CE+KD on tcgen05), f32 elsewhere", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K, "last_loss": last_loss},
                 "gpu_launches": (launches_per_step or 0) * K,

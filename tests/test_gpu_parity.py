@@ -19,7 +19,7 @@ from oracle import sasrec as S
 
 def _args(**kw):
     base = dict(hidden_units=150, maxlen=50, num_blocks=2, num_heads=1, random_seed=0, lr=5e-4,
-                dropout_rate=0.0, disable_distillation=False)
+                dropout_rate=0.0, disable_distillation=False, loss_impl="exact")
     base.update(kw)
     return type("Args", (), base)()
 
@@ -293,6 +293,7 @@ def test_fisher_and_ewc_step():
     from ader_b200.model import Ewc
     args = _args()
     m = Ewc(120, args, init_seed=0)
+    assert m.loss_impl == "exact"
     hp = S.Hyper(120)
     params = S.randomize_params(S.init_params(hp, 0), 2, 0.05)
     m.theta.copy_(torch.cat([p.reshape(-1) for p in params]))
@@ -390,3 +391,71 @@ def test_full_size_properties():
     r2, _, _ = m.rank_topk(ids, items[:, 0].contiguous(), V, 20)
     assert int(r2.abs().max().item()) == 0
     assert bool((scores[:, :-1] >= scores[:, 1:]).all())
+
+
+# ---- tcgen05 fused logits + CE + KD path (bf16 operands, fp32 accumulation in TMEM) --------------
+# Tolerance: operands are rounded to bf16 (2^-9 relative), accumulation is fp32.  Against the fp32
+# oracle: loss within 1e-3 relative, gradients within 1e-2 * max|g| per tensor.
+@pytest.mark.parametrize("mode", ["vanilla", "kd", "er"])
+@pytest.mark.parametrize("shape", [(24, 16, 450, 400, 500), (333, 256, 3001, 2500, 4000)])
+def test_tc_loss_path_matches_oracle(mode, shape):
+    M, Bt, V, Vp, item_num = shape
+    m, hp, params = _model(item_num, loss_impl="tc", disable_distillation=(mode == "er"))
+    assert m.loss_impl == "tc"
+    rng = np.random.RandomState(21)
+    lens = np.minimum(50, rng.geometric(0.25, M))
+    kw, okw = {}, {}
+    if mode == "vanilla":
+        M = Bt
+    ids = _ids(rng, M, 50, V, lens[:M])
+    pos = rng.randint(1, V + 1, Bt).astype(np.int32)
+    pos[0], pos[-1] = 1, V                                  # first / last column
+    if mode == "kd":
+        teacher = (rng.randn(M - Bt, Vp) * 2).astype(np.float32)
+        kw["exemplar_logits"] = teacher; okw["exemplar_logits"] = torch.tensor(teacher)
+        m.update_loss(0.9)
+    elif mode == "er":
+        ex_pos = rng.randint(1, V + 1, M - Bt).astype(np.int32)
+        kw["exemplar_pos"] = ex_pos; okw["exemplar_pos"] = torch.tensor(ex_pos)
+        m.update_loss(0.9)
+    loss = float(m.loss_and_grad(ids, pos, V, **kw).item())
+    if mode == "vanilla":
+        fn = lambda ps: S.loss_vanilla(ps, torch.tensor(ids).long(), torch.tensor(pos), V, hp)
+    else:
+        fn = lambda ps: S.loss_ader(ps, torch.tensor(ids).long(), torch.tensor(pos), V, hp, 0.9, **okw)
+    ref, grads = S.grads_of(fn, params)
+    assert loss == pytest.approx(ref, rel=1e-3)
+    got = _views(m, m.grad)
+    for i, (name, _) in enumerate(S.param_shapes(hp)):
+        g, w = got[i], grads[i]
+        if i == 0:
+            g, w = g[1:V + 1], w[1:V + 1]
+        _close(g, w, 1e-2, 1e-7, "tc %s grad of %s" % (mode, name))
+    # run-to-run determinism of the fused path
+    g0 = m.grad.clone()
+    m.loss_and_grad(ids, pos, V, **kw)
+    assert torch.equal(g0, m.grad)
+
+
+def test_tc_full_size_step_tracks_exact_path():
+    """DIGINETICA period-10 shape (M=385, V=40135): the tcgen05 path against the exact fp32 CUDA path."""
+    rng = np.random.RandomState(22)
+    M, Bt, V, Vp = 385, 256, 40135, 38501
+    lens = np.minimum(50, rng.geometric(0.22, M))
+    ids = _ids(rng, M, 50, V, lens)
+    pos = rng.randint(1, V + 1, Bt).astype(np.int32)
+    out = {}
+    for impl in ("exact", "tc"):
+        m, hp, _ = _model(43136, scale=0.02, loss_impl=impl)
+        teacher = torch.randn(M - Bt, Vp, device=m.device, generator=torch.Generator(device=m.device).manual_seed(3))
+        m.update_loss(0.6)
+        loss = float(m.loss_and_grad(ids, pos, V, exemplar_logits=teacher, n_tokens=int(lens.sum())).item())
+        out[impl] = (loss, m.grad.clone(), m.layout)
+    (le, ge, lay), (lt, gt, _) = out["exact"], out["tc"]
+    assert lt == pytest.approx(le, rel=1e-3)
+    for i, (name, shape, off) in enumerate(lay.entries):
+        n = int(np.prod(shape))
+        a, b = gt[off:off + n], ge[off:off + n]
+        if i == 0:
+            a, b = a[150:(V + 1) * 150], b[150:(V + 1) * 150]
+        _close(a.cpu(), b.cpu(), 1e-2, 1e-8, "full-size tc grad of %s" % name)
