@@ -10,8 +10,9 @@
 //   - MN-major B operand (N = feature, K = row): SBO = 2048 B, LBO = 128 B
 // so forward (S = rep.E^T) and both backward products (dRep = dS.E, dE = dS^T.rep) read the same bytes.
 //
-// Kernel roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane) +
-// TMEM allocator, warps 2..5 = epilogue (one TMEM lane = one logits row per thread).
+// Kernel roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane) +
+// TMEM allocator, warps 2..9 = epilogue: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4, so
+// two threads share one logits row (64 of the 128 tile columns each).
 //   MODE_FWD : per (row-tile, vocab-chunk) CTA: S tiles -> online (max, sumexp), label logit, KD dot
 //   MODE_DREP: same loop; dS (bf16) is staged in shared memory and a second MMA accumulates
 //              dRep[128, 160] in TMEM across the CTA's vocab tiles
@@ -44,7 +45,7 @@ struct TcArgs {
   const float* teacher; const int* teacher_row; long long teacher_ld;
   const float* lse;             // [M]   (backward)
   const float* lse_t;           // [n_ex] teacher log-sum-exp
-  float* stats;                 // FWD: [n_chunks][M][4] = (max, sumexp, label logit, kd dot)
+  float* stats;                 // FWD: [n_chunks*2][M][4] = (max, sumexp, label logit, kd dot) per column half
   float* drep_part;             // DREP: [n_chunks][n_mtiles*128][160]
   float* grad_table;            // DE: grad + d (row of item 1), row stride d
   int d;
@@ -76,6 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one T128 tile as LOAD_SPLIT independent bulk copies (a single 40 KB bulk copy keeps only a few
+// 128 B requests in flight: measured ~50 us per tile from HBM; many smaller ones overlap)
+constexpr int LOAD_SPLIT = 20;
+__device__ __forceinline__ void load_tile(uint32_t dst, const uint8_t* src, uint32_t bar) {
+  mbar_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+  for (int i = 0; i < LOAD_SPLIT; ++i)
+    bulk_g2s(dst + i * (TILE_BYTES / LOAD_SPLIT), src + i * (TILE_BYTES / LOAD_SPLIT), TILE_BYTES / LOAD_SPLIT, bar);
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -143,8 +153,10 @@ __device__ __forceinline__ RowInfo row_info(const TcArgs& a, int gm, bool bwd) {
   return r;
 }
 
+constexpr int NTHREADS = 320, NEPI = 256;
+
 template <int MODE>
-__global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   // carve: [X stationary tile][Y stage 0][Y stage 1][dS 0][dS 1][barriers]
   uint8_t* sX = smem;
@@ -177,8 +189,8 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
     mbar_init(BAR(B_XFULL), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1);
-      mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), 128);
-      mbar_init(BAR(B_DSFULL + s), 128); mbar_init(BAR(B_DSEMPTY + s), 1);
+      mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), NEPI);
+      mbar_init(BAR(B_DSFULL + s), NEPI); mbar_init(BAR(B_DSEMPTY + s), 1);
     }
     mbar_init(BAR(B_ACC), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,13 +209,11 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
   if (warp == 0) {
     // ===== producer: one elected lane issues bulk copies ========================================
     if (lane == 0 && n_it > 0) {
-      mbar_expect_tx(BAR(B_XFULL), TILE_BYTES);
-      bulk_g2s(smem_u32(sX), gX, TILE_BYTES, BAR(B_XFULL));
+      load_tile(smem_u32(sX), gX, BAR(B_XFULL));
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
         mbar_wait(BAR(B_YEMPTY + s), ph ^ 1, a.err);
-        mbar_expect_tx(BAR(B_YFULL + s), TILE_BYTES);
-        bulk_g2s(smem_u32(sY + s * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, TILE_BYTES, BAR(B_YFULL + s));
+        load_tile(smem_u32(sY + s * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, BAR(B_YFULL + s));
       }
     }
   } else if (warp == 1) {
@@ -254,6 +264,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
   } else {
     // ===== epilogue: TMEM lane = logits row ===========================================================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which 64 of the tile's 128 columns this thread owns
     const int row = q * 32 + lane;             // row inside the 128-row tile
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     RowInfo ri;
@@ -269,10 +280,15 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
       if (MODE != MODE_FWD) mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
       uint8_t* ds = sD + s * DS_BYTES;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = half * 2; c4 < half * 2 + 2; ++c4) {
         uint32_t r[32];
-        tmem_ld32(tmem + tlane + s * 128 + c4 * 32, r);
         const int vb = v0 + c4 * 32;
+        float tv[32];                           // teacher logits of this chunk: 32 independent loads in flight
+        if (ri.kind == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tv[i] = (vb + i < ri.vlim) ? ri.trow[vb + i] : 0.f;
+        }
+        tmem_ld32(tmem + tlane + s * 128 + c4 * 32, r);
         if (MODE == MODE_FWD) {
           if (ri.kind != 0 && vb < ri.vlim) {
             float cm = -INFINITY;
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
                 const float sv = __uint_as_float(r[i]);
                 sum += ex2(fmaf(sv, LOG2E, -nm2));
                 if (v == ri.label) lab = sv;
-                if (ri.kind == 2) dot = fmaf(ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)), sv, dot);
+                if (ri.kind == 2) dot = fmaf(ex2(fmaf(tv[i], LOG2E, -ri.lset2)), sv, dot);
               }
             }
           }
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
               if (ri.kind != 0 && v < ri.vlim) {
                 const float p = ex2(fmaf(__uint_as_float(r[i + u]), LOG2E, -ri.lse2));
                 if (ri.kind == 1) g = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
-                else g = ri.coef * (p - ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)));
+                else g = ri.coef * (p - ex2(fmaf(tv[i + u], LOG2E, -ri.lset2)));
               }
               g2[u] = g;
             }
@@ -331,13 +347,13 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
       const int gm = x_tile * TILE + row;
       if (gm < a.M) {
         float4 o = make_float4(mx, sum, lab, dot);
-        *reinterpret_cast<float4*>(a.stats + ((size_t)chunk * a.M + gm) * 4) = o;
+        *reinterpret_cast<float4*>(a.stats + ((size_t)(chunk * 2 + half) * a.M + gm) * 4) = o;
       }
     } else if (n_it > 0) {
       mbar_wait(BAR(B_ACC), 0, a.err);
       tc_fence_after();
 #pragma unroll 1
-      for (int c4 = 0; c4 < KP / 32; ++c4) {
+      for (int c4 = half; c4 < KP / 32; c4 += 2) {
         uint32_t r[32];
         tmem_ld32(tmem + tlane + ACC_COL + c4 * 32, r);
         if (MODE == MODE_DREP) {
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_logits(TcArgs a) {
       tc_fence_before();
     } else if (MODE == MODE_DREP) {           // empty chunk: its partial must still be defined
       float* o = a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP;
-      for (int i = 0; i < KP; ++i) o[i] = 0.f;
+      for (int i = half * (KP / 2); i < (half + 1) * (KP / 2); ++i) o[i] = 0.f;
     }
   }
   __syncthreads();
@@ -473,7 +489,7 @@ static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, char* base) {
   const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
   w.rep_tiles = (uint8_t*)take((size_t)nm * TILE_BYTES);
   w.e_tiles = (uint8_t*)take((size_t)nv * TILE_BYTES);
-  w.stats = (float*)take(sizeof(float) * 4 * (size_t)nc * M);
+  w.stats = (float*)take(sizeof(float) * 4 * (size_t)nc * 2 * M);
   w.lse = (float*)take(sizeof(float) * M);
   w.lse_t = (float*)take(sizeof(float) * (n_ex > 0 ? n_ex : 1));
   w.drep_part = (float*)take(sizeof(float) * (size_t)nc * nm * TILE * KP);
@@ -531,17 +547,17 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
 
-  k_tc_logits<MODE_FWD><<<nm * nc, 192, smem_fwd, st>>>(t);
-  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc, a->n_train, t.mode, w.lse, row_loss);
+  k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
+  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss);
   if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
-    k_tc_logits<MODE_DREP><<<nm * nc, 192, smem_bwd, st>>>(t);
+    k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
     k_reduce_drep<<<cdiv((long long)M * d, 256), 256, 0, st>>>(w.drep_part, nc, nm * TILE, M, d, d_rep);
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {
-    k_tc_logits<MODE_DE><<<nv, 192, smem_bwd, st>>>(t);
+    k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
     ADER_CHECK_LAUNCH("tc d_table");
   }
   return 0;

@@ -79,8 +79,15 @@ class PeriodTrainer:
             self.e_ids, self.e_lab = exemplar_sampler.device_rows(dev)
             self.e_nin = exemplar_sampler.packed()[2]
         self.rows_seen = 0
+        self.trace = None
 
     def step(self):
+        loss = self._step()
+        if self.trace is not None:
+            self.trace.append(float(loss.item()))
+        return loss
+
+    def _step(self):
         m, dev, L = self.model, self.model.device, self.model.hp.maxlen
         ti = self.ts.next_indices()
         ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
@@ -145,6 +152,7 @@ def run(args) -> dict:
     fast_exemplar = None
     ckpt = {}                                                  # (period, epoch) -> state (tf.train.Saver max_to_keep=1)
     stop_counter = 0                                           # reference leaves it uninitialised
+    trace = {"periods": []} if getattr(args, "trace", False) else None
     no_replay = args.finetune or args.dropout or args.joint
 
     for period in periods:
@@ -188,6 +196,10 @@ def run(args) -> dict:
 
         use_ex = exemplar_sampler is not None and not args.ewc
         trainer = PeriodTrainer(model, train_sampler, exemplar_sampler if use_ex else None, args, max_item)
+        rec = {"losses": [], "valid": [], "best_epoch": None, "test": None, "exemplars": None}
+        if trace is not None:
+            trainer.trace = rec["losses"]
+            trace["periods"].append(rec)
         best_epoch = 1
         train_time = 0.0
         for epoch in range(1, args.num_epochs + 1):
@@ -205,6 +217,7 @@ def run(args) -> dict:
             info = valid_evaluator.evaluate(epoch)
             logs.write(info + "\n")
             performance = valid_evaluator.results()[1]
+            rec["valid"].append(valid_evaluator.results())
             if best_performance >= performance:                # main.py:272-280
                 stop_counter += 1
                 if stop_counter >= args.stop:
@@ -219,6 +232,7 @@ def run(args) -> dict:
         info = test_evaluator.evaluate(best_epoch)
         logs.write(info + "\n")
         r = test_evaluator.results()
+        rec["best_epoch"], rec["test"], rec["test_ranks"] = best_epoch, r, list(test_evaluator.ranks)
         metrics["MRR_20"].append(r[0]); metrics["Recall_20"].append(r[1])
         metrics["MRR_10"].append(r[2]); metrics["Recall_10"].append(r[3])
         sps = trainer.rows_seen / max(train_time, 1e-9)
@@ -246,6 +260,7 @@ def run(args) -> dict:
             print(info)
             logs.write(info + "\n")
             fast_exemplar = gen.exemplars
+            rec["exemplars"] = list(fast_exemplar.sessions)
             del gen
         item_num_prev = max_item
         if args.ewc:                                           # main.py:319-323
@@ -265,7 +280,7 @@ def run(args) -> dict:
     logs.write("Total time: %.2f minutes\nDone." % minutes)
     logs.close()
     print("Done.")
-    return {"average": avg, "per_period": metrics, "throughput": stats, "minutes": minutes}
+    return {"average": avg, "per_period": metrics, "throughput": stats, "minutes": minutes, "trace": trace, "model": model}
 
 
 def main(argv=None):

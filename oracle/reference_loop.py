@@ -1,0 +1,126 @@
+"""Restatement of the reference's continual-learning driver (main.py:158-323) on top of the
+oracle pieces -- TEST INFRASTRUCTURE ONLY.  Dense over all maxlen slots, one forward per eval
+batch / per item, Python lists of logits: slow and literal, like the reference.  Covers the ADER
+path (herding / loss / random selection, KD or one-hot exemplar loss) and the no-replay baselines.
+"""
+from __future__ import annotations
+
+import copy
+import math
+import random
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import protocol as P
+from . import sasrec as S
+
+
+def _evaluate(params, hp, data, is_subseq, maxlen, batch, max_item):
+    """util.py:309-339."""
+    s = P.RefSampler(data, maxlen, batch, is_subseq=is_subseq)
+    ranks = []
+    for _ in range(s.batch_num()):
+        seq, pos = s.sampler()
+        with torch.no_grad():
+            lg = S.logits_of(S.forward_rep(params, torch.tensor(np.array(seq)).long(), hp), params[0], max_item).numpy()
+        ranks.extend(S.rank_of_gt(lg, np.array(pos)).tolist())
+    return ranks, S.metrics_from_ranks(ranks)
+
+
+def run(data_dir: str, item_num: int, args, n_periods: int) -> dict:
+    """args: namespace with the main.py flag names used below."""
+    hp = S.Hyper(item_num, args.hidden_units, args.maxlen, args.num_blocks, args.num_heads)
+    np.random.seed(args.random_seed)
+    random.seed(args.random_seed)
+    files = P.PeriodFiles(data_dir)
+    params = S.init_params(hp, args.random_seed)
+    opt = S.AdamTF1(params)
+    no_replay = args.finetune or args.dropout or args.joint
+    trace = {"periods": []}
+    exemplars = []                # flattened [[session, logits_row], ...] (main.py:54-65)
+    item_prev = 0
+    best_state = None
+    stop_counter = 0
+    for period in range(1, n_periods + 1):
+        rec = {"losses": [], "valid": [], "best_epoch": None, "test": None, "exemplars": None}
+        train_sess, _ = files.train(period - 1)
+        ts = P.RefSampler(train_sess, args.maxlen, args.batch_size)
+        valid_rows, train_rows = ts.split_data(0.1)
+        batch_num = ts.batch_num()
+        test_sess, _, _ = files.evaluate(period)
+        max_item = files.max_item()
+        lam = 0.0
+        es = None
+        ex_sessions = []
+        if period > 1 and not no_replay:
+            ex_sessions = [e[0] for e in exemplars]
+            es = P.RefSampler([], args.maxlen, P.exemplar_rows_per_step(len(exemplars), batch_num))
+            es.add_exemplar(exemplars)
+            lam = args.lambda_ if args.fix_lambda else P.adaptive_lambda(args.lambda_, item_prev, max_item, len(exemplars), ts.data_size())
+        if period > 1:
+            params, opt = copy.deepcopy(best_state)          # saver.restore (main.py:211)
+        best_perf, best_epoch = 0, 1
+        for epoch in range(1, args.num_epochs + 1):
+            for _ in range(batch_num):
+                seq, pos = ts.sampler()
+                ids = torch.tensor(np.array(seq)).long()
+                pos_t = torch.tensor(np.array(pos))
+                if es is not None:
+                    ex_seq, ex_pos, ex_logits = es.exemplar_sampler()
+                    ids = torch.cat([ids, torch.tensor(np.array(ex_seq)).long()])
+                    if args.disable_distillation:
+                        fn = lambda ps: S.loss_ader(ps, ids, pos_t, max_item, hp, lam, exemplar_pos=torch.tensor(np.array(ex_pos)))
+                    else:
+                        tl = torch.tensor(np.array(ex_logits, dtype=np.float32))
+                        fn = lambda ps: S.loss_ader(ps, ids, pos_t, max_item, hp, lam, exemplar_logits=tl)
+                else:
+                    fn = lambda ps: S.loss_vanilla(ps, ids, pos_t, max_item, hp)
+                loss, grads = S.grads_of(fn, params)
+                params = opt.step(params, grads, args.lr)
+                rec["losses"].append(loss)
+            _, res = _evaluate(params, hp, valid_rows, True, args.maxlen, args.test_batch, max_item)
+            rec["valid"].append(res)
+            perf = res[1]
+            if best_perf >= perf:                            # main.py:272-280
+                stop_counter += 1
+                if stop_counter >= args.stop:
+                    break
+            else:
+                stop_counter = 0
+                best_epoch, best_perf = epoch, perf
+                best_state = copy.deepcopy((params, opt))
+        params, opt = copy.deepcopy(best_state)              # main.py:283
+        rec["best_epoch"] = best_epoch
+        ranks, res = _evaluate(params, hp, test_sess, False, args.maxlen, args.test_batch, max_item)
+        rec["test"] = res
+        rec["test_ranks"] = ranks
+        if not no_replay:                                    # main.py:294-313
+            cand = list(train_rows) + list(valid_rows) + list(ex_sessions)
+            by_item, count = P.group_by_label(cand, args.maxlen, args.batch_size, max_item)
+            quota = P.exemplar_quota(count, args.exemplar_size, args.equal_exemplar)
+            new = defaultdict(list)
+            for item, seqs in by_item.items():
+                seqs = np.array(seqs)
+                m = quota[item - 1]
+                if args.selection == "loss" and m < 0.5:
+                    continue
+                if args.selection == "random" and m <= 0:
+                    continue
+                with torch.no_grad():
+                    rep = S.forward_rep(params, torch.tensor(seqs[:, :-1]).long(), hp)
+                    lg = S.logits_of(rep, params[0], max_item).numpy()
+                if args.selection == "herding":
+                    picks = P.herding_picks(rep.numpy(), int(min(m, len(seqs))))
+                elif args.selection == "loss":
+                    picks = P.loss_picks(len(seqs), int(m))
+                else:
+                    picks = P.random_picks(len(seqs), m).tolist()
+                new[item] = [[P.stored_session(seqs[i]), lg[i].tolist()] for i in picks]
+            exemplars = P.flatten_exemplars(new)
+            rec["exemplars"] = [e[0] for e in exemplars]
+        item_prev = max_item
+        trace["periods"].append(rec)
+    trace["params"] = params
+    return trace

@@ -459,3 +459,58 @@ def test_tc_full_size_step_tracks_exact_path():
         if i == 0:
             a, b = a[150:(V + 1) * 150], b[150:(V + 1) * 150]
         _close(a.cpu(), b.cpu(), 1e-2, 1e-8, "full-size tc grad of %s" % name)
+
+
+# ---- end to end: the product driver (ader_b200/main.py) vs the oracle driver on the tiny split ----
+def _e2e_args(tmp, **kw):
+    from ader_b200.main import build_parser
+    a = build_parser().parse_args([])
+    a.dataset = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_data")
+    a.results_root = str(tmp)
+    a.item_num = 400
+    a.batch_size, a.test_batch, a.exemplar_size, a.num_epochs, a.stop = 64, 16, 150, 3, 5
+    a.dropout_rate = 0.0
+    a.loss_impl = "exact"
+    a.trace = True
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("selection,disable_kd", [("herding", False), ("random", True)])
+def test_end_to_end_three_periods_match_oracle_driver(tmp_path, selection, disable_kd):
+    from ader_b200.main import run
+    from oracle import reference_loop
+    a = _e2e_args(tmp_path, selection=selection, disable_distillation=disable_kd)
+    got = run(a)
+    want = reference_loop.run(a.dataset, a.item_num, a, n_periods=3)
+    assert len(got["trace"]["periods"]) == 3
+    for p, (g, w) in enumerate(zip(got["trace"]["periods"], want["periods"])):
+        assert len(g["losses"]) == len(w["losses"]), "period %d step count" % (p + 1)
+        np.testing.assert_allclose(g["losses"], w["losses"], rtol=2e-3, err_msg="period %d losses" % (p + 1))
+        np.testing.assert_allclose(g["losses"][:20], w["losses"][:20], rtol=2e-4)
+        assert g["best_epoch"] == w["best_epoch"]
+        # Recall/MRR: identical up to rank flips at near-ties (<= 1% of rows)
+        gr, wr = np.array(g["test_ranks"]), np.array(w["test_ranks"])
+        assert len(gr) == len(wr)
+        assert np.mean(gr != wr) <= 0.01, "period %d: %.3f of test ranks differ" % (p + 1, np.mean(gr != wr))
+        np.testing.assert_allclose(g["test"], w["test"], atol=5e-3)
+        for ge, we in zip(g["valid"], w["valid"]):
+            np.testing.assert_allclose(ge, we, atol=2e-2)
+        # exemplar sets: same sessions in the same order (herding picks are exact away from near-ties)
+        same = sum(1 for x, y in zip(g["exemplars"], w["exemplars"]) if x == y)
+        assert len(g["exemplars"]) == len(w["exemplars"])
+        assert same >= 0.97 * len(w["exemplars"]), "period %d exemplars: %d of %d identical" % (p + 1, same, len(w["exemplars"]))
+    log = open(os.path.join(str(tmp_path), os.path.basename(a.dataset) + "-ADER", "Training_logs.txt")).read()
+    assert "Period 3:" in log and "Total saved exemplar:" in log and "Average: (MRR@20:" in log
+
+
+def test_end_to_end_tc_path_reaches_same_metrics(tmp_path):
+    """Same driver with the tcgen05 loss path: losses within 1e-2, Recall@20 within 0.02 of the exact path."""
+    from ader_b200.main import run
+    a = _e2e_args(tmp_path / "exact")
+    b = _e2e_args(tmp_path / "tc", loss_impl="tc")
+    ra, rb = run(a), run(b)
+    for pa, pb in zip(ra["trace"]["periods"], rb["trace"]["periods"]):
+        np.testing.assert_allclose(pb["losses"][:30], pa["losses"][:30], rtol=1e-2)
+        assert abs(pa["test"][1] - pb["test"][1]) <= 0.03
