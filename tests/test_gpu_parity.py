@@ -467,7 +467,7 @@ def _e2e_args(tmp, **kw):
     a = build_parser().parse_args([])
     a.dataset = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_data")
     a.results_root = str(tmp)
-    a.item_num = 400
+    a.item_num = 700
     a.batch_size, a.test_batch, a.exemplar_size, a.num_epochs, a.stop = 64, 16, 150, 3, 5
     a.dropout_rate = 0.0
     a.loss_impl = "exact"
@@ -483,7 +483,8 @@ def test_end_to_end_three_periods_match_oracle_driver(tmp_path, selection, disab
     from oracle import reference_loop
     a = _e2e_args(tmp_path, selection=selection, disable_distillation=disable_kd)
     got = run(a)
-    want = reference_loop.run(a.dataset, a.item_num, a, n_periods=3)
+    with S.literal_masks(False):          # fresh init: see oracle/sasrec.py LITERAL_MASKS
+        want = reference_loop.run(a.dataset, a.item_num, a, n_periods=3)
     assert len(got["trace"]["periods"]) == 3
     for p, (g, w) in enumerate(zip(got["trace"]["periods"], want["periods"])):
         assert len(g["losses"]) == len(w["losses"]), "period %d step count" % (p + 1)

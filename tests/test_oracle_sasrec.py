@@ -136,3 +136,26 @@ def test_fisher_counts_skipped_rows():
     _, g2 = S.grads_of(lambda ps: S.loss_vanilla(ps, ids[2:3], pos[2:3], 15, hp), params)
     want = (g0[4].double() ** 2 + g1[4].double() ** 2 + g2[4].double() ** 2) / 5
     assert np.allclose(F[4], want.numpy(), rtol=1e-12)
+
+
+def test_literal_query_mask_quirk_only_bites_at_fresh_init():
+    """modules.py:208-211: query mask = sign|sum_d LN(x)|.  With LN beta=0, gamma=1 the sum is zero up to
+    rounding, so some REAL rows hit an exact fp32 zero and lose their attention output; any beta != 0
+    removes the effect.  The id-derived mask is what the CUDA path (and the packed form) computes."""
+    hp = S.Hyper(item_num=300)
+    rng = np.random.RandomState(0)
+    ids = _ids(rng, 64, hp.maxlen, 250)
+    fresh = S.init_params(hp, 0)
+    with S.literal_masks(True):
+        a = S.forward_rep(fresh, ids, hp)
+    with S.literal_masks(False):
+        b = S.forward_rep(fresh, ids, hp)
+    c = S.forward_rep_packed(fresh, ids, hp)
+    assert float((b - c).abs().max()) < 5e-5                       # id masks == packed form
+    assert float((a - b).abs().max()) > 1e-2                       # the literal masks zero some real rows
+    trained = S.randomize_params(fresh, 1, 0.05)                   # beta != 0: the quirk disappears
+    with S.literal_masks(True):
+        a2 = S.forward_rep(trained, ids, hp)
+    with S.literal_masks(False):
+        b2 = S.forward_rep(trained, ids, hp)
+    assert torch.equal(a2, b2)
