@@ -80,11 +80,14 @@ class PeriodTrainer:
             self.e_nin = exemplar_sampler.packed()[2]
         self.rows_seen = 0
         self.trace = None
+        self.trace_rows = None
 
     def step(self):
         loss = self._step()
         if self.trace is not None:
             self.trace.append(float(loss.item()))
+            if self.trace_rows is not None:
+                self.trace_rows.append((self.model.last_row_loss.cpu().numpy(), self.model._keep[0].cpu().numpy()))
         return loss
 
     def _step(self):
@@ -124,7 +127,7 @@ class PeriodTrainer:
 
 
 def run(args) -> dict:
-    res_dir = os.path.join(args.results_root, args.dataset + "-" + args.save_dir)
+    res_dir = os.path.join(args.results_root, os.path.basename(args.dataset.rstrip("/")) + "-" + args.save_dir)
     os.makedirs(res_dir, exist_ok=True)
     logs = open(os.path.join(res_dir, "Training_logs.txt"), mode="w")
     logs.write("\n".join([str(k) + "," + str(v) for k, v in sorted(vars(args).items(), key=lambda x: x[0])]))
@@ -199,6 +202,9 @@ def run(args) -> dict:
         rec = {"losses": [], "valid": [], "best_epoch": None, "test": None, "exemplars": None}
         if trace is not None:
             trainer.trace = rec["losses"]
+            if getattr(args, "trace_rows", False):
+                rec["rows"] = []
+                trainer.trace_rows = rec["rows"]
             trace["periods"].append(rec)
         best_epoch = 1
         train_time = 0.0
@@ -261,6 +267,8 @@ def run(args) -> dict:
             logs.write(info + "\n")
             fast_exemplar = gen.exemplars
             rec["exemplars"] = list(fast_exemplar.sessions)
+            if trace is not None:
+                rec["ex_by_item"] = {int(k): [gen.rows[r][-(args.maxlen + 1):] for r in v] for k, v in fast_exemplar.by_item.items()}
             del gen
         item_num_prev = max_item
         if args.ewc:                                           # main.py:319-323

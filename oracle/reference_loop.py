@@ -78,6 +78,12 @@ def run(data_dir: str, item_num: int, args, n_periods: int) -> dict:
                 else:
                     fn = lambda ps: S.loss_vanilla(ps, ids, pos_t, max_item, hp)
                 loss, grads = S.grads_of(fn, params)
+                if getattr(args, "trace_rows", False):
+                    with torch.no_grad():
+                        lg = S.logits_of(S.forward_rep(params, ids, hp), params[0], max_item)
+                        n_t = pos_t.numel()
+                        rl = S.ce_rows(lg[:n_t], pos_t).numpy()
+                    rec.setdefault("rows", []).append((rl, ids.numpy()))
                 params = opt.step(params, grads, args.lr)
                 rec["losses"].append(loss)
             _, res = _evaluate(params, hp, valid_rows, True, args.maxlen, args.test_batch, max_item)
@@ -120,7 +126,11 @@ def run(data_dir: str, item_num: int, args, n_periods: int) -> dict:
                 new[item] = [[P.stored_session(seqs[i]), lg[i].tolist()] for i in picks]
             exemplars = P.flatten_exemplars(new)
             rec["exemplars"] = [e[0] for e in exemplars]
+            rec["ex_by_item"] = {int(k): [e[0] for e in v] for k, v in new.items()}
+            rec["cand_by_item"] = {int(k): np.array(v) for k, v in by_item.items()}
+            rec["quota"] = quota
         item_prev = max_item
         trace["periods"].append(rec)
+        trace.setdefault("periods_params", []).append([q.clone() for q in params])
     trace["params"] = params
     return trace

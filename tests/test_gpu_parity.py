@@ -477,8 +477,12 @@ def _e2e_args(tmp, **kw):
     return a
 
 
-@pytest.mark.parametrize("selection,disable_kd", [("herding", False), ("random", True)])
+@pytest.mark.parametrize("selection,disable_kd", [("random", False), ("loss", True)])
 def test_end_to_end_three_periods_match_oracle_driver(tmp_path, selection, disable_kd):
+    """Whole protocol (3 periods: training with Adam state carried over, early stop / best epoch, test,
+    exemplar selection + stored logits, adaptive lambda, KD or one-hot replay) against the oracle driver.
+    random / loss selection do not depend on floating-point near-ties, so everything must agree:
+    step losses to 1e-5, identical best epochs and exemplar sets, >= 99 % identical test ranks."""
     from ader_b200.main import run
     from oracle import reference_loop
     a = _e2e_args(tmp_path, selection=selection, disable_distillation=disable_kd)
@@ -488,29 +492,63 @@ def test_end_to_end_three_periods_match_oracle_driver(tmp_path, selection, disab
     assert len(got["trace"]["periods"]) == 3
     for p, (g, w) in enumerate(zip(got["trace"]["periods"], want["periods"])):
         assert len(g["losses"]) == len(w["losses"]), "period %d step count" % (p + 1)
-        np.testing.assert_allclose(g["losses"], w["losses"], rtol=2e-3, err_msg="period %d losses" % (p + 1))
-        np.testing.assert_allclose(g["losses"][:20], w["losses"][:20], rtol=2e-4)
+        np.testing.assert_allclose(g["losses"], w["losses"], rtol=1e-5, err_msg="period %d losses" % (p + 1))
         assert g["best_epoch"] == w["best_epoch"]
-        # Recall/MRR: identical up to rank flips at near-ties (<= 1% of rows)
         gr, wr = np.array(g["test_ranks"]), np.array(w["test_ranks"])
         assert len(gr) == len(wr)
         assert np.mean(gr != wr) <= 0.01, "period %d: %.3f of test ranks differ" % (p + 1, np.mean(gr != wr))
         np.testing.assert_allclose(g["test"], w["test"], atol=5e-3)
         for ge, we in zip(g["valid"], w["valid"]):
-            np.testing.assert_allclose(ge, we, atol=2e-2)
-        # exemplar sets: same sessions in the same order (herding picks are exact away from near-ties)
-        same = sum(1 for x, y in zip(g["exemplars"], w["exemplars"]) if x == y)
-        assert len(g["exemplars"]) == len(w["exemplars"])
-        assert same >= 0.97 * len(w["exemplars"]), "period %d exemplars: %d of %d identical" % (p + 1, same, len(w["exemplars"]))
+            np.testing.assert_allclose(ge, we, atol=1e-2)
+        assert g["exemplars"] == w["exemplars"], "period %d exemplar sets differ" % (p + 1)
     log = open(os.path.join(str(tmp_path), os.path.basename(a.dataset) + "-ADER", "Training_logs.txt")).read()
     assert "Period 3:" in log and "Total saved exemplar:" in log and "Average: (MRR@20:" in log
+
+
+def test_end_to_end_herding_periods(tmp_path):
+    """Default ADER (herding + KD).  Period 1 must agree step by step; its herding picks may differ from
+    the oracle's only where the arg-max of w.D is a near-tie (gap < 1e-4 in an fp64 replay; the tiny split
+    is full of duplicated prefixes, i.e. exact ties, and the CPU and GPU reps differ by ~1e-6).  Later
+    periods train on slightly different exemplar sets, so they are compared on losses (2 %) and metrics."""
+    from ader_b200.main import run
+    from oracle import reference_loop
+    a = _e2e_args(tmp_path, selection="herding")
+    got = run(a)
+    with S.literal_masks(False):
+        want = reference_loop.run(a.dataset, a.item_num, a, n_periods=3)
+    g, w = got["trace"]["periods"][0], want["periods"][0]
+    np.testing.assert_allclose(g["losses"], w["losses"], rtol=1e-5)
+    assert g["best_epoch"] == w["best_epoch"] and len(g["exemplars"]) == len(w["exemplars"])
+    n_diff = 0
+    for item, want_sessions in w["ex_by_item"].items():
+        got_sessions = g["ex_by_item"].get(item, [])
+        if got_sessions == want_sessions:
+            continue
+        n_diff += 1
+        cand = w["cand_by_item"][item]
+        k = next(i for i, (x, y) in enumerate(zip(got_sessions + [None], want_sessions + [None])) if x != y)
+        hp = S.Hyper(a.item_num)
+        rep = S.forward_rep(want["periods_params"][0], torch.tensor(cand[:, :-1]).long(), hp).numpy()
+        m = int(min(w["quota"][item - 1], len(cand)))
+        want_idx = P.herding_picks(rep, m)
+        gap = _herding_gap(rep, m, want_idx, k)
+        assert gap < 1e-4, "item %d: picks diverge at pick %d with arg-max gap %.3e" % (item, k, gap)
+    assert n_diff <= 0.1 * len(w["ex_by_item"])
+    for p in (1, 2):
+        g, w = got["trace"]["periods"][p], want["periods"][p]
+        assert len(g["losses"]) == len(w["losses"])
+        # a step draws only ~9 exemplar rows here, so one different exemplar moves a step loss by a few %
+        np.testing.assert_allclose(g["losses"], w["losses"], rtol=6e-2)
+        assert np.mean(g["losses"]) == pytest.approx(np.mean(w["losses"]), rel=1e-2)
+        np.testing.assert_allclose(g["test"], w["test"], atol=5e-2)
+        assert len(g["exemplars"]) == len(w["exemplars"])
 
 
 def test_end_to_end_tc_path_reaches_same_metrics(tmp_path):
     """Same driver with the tcgen05 loss path: losses within 1e-2, Recall@20 within 0.02 of the exact path."""
     from ader_b200.main import run
-    a = _e2e_args(tmp_path / "exact")
-    b = _e2e_args(tmp_path / "tc", loss_impl="tc")
+    a = _e2e_args(tmp_path / "exact", selection="random")
+    b = _e2e_args(tmp_path / "tc", loss_impl="tc", selection="random")
     ra, rb = run(a), run(b)
     for pa, pb in zip(ra["trace"]["periods"], rb["trace"]["periods"]):
         np.testing.assert_allclose(pb["losses"][:30], pa["losses"][:30], rtol=1e-2)
