@@ -13,7 +13,7 @@ namespace ader {
 
 constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
 constexpr int SPLITS = 16;        // split-K partials for weight / LN / bias gradients
-constexpr int PG_LANES = 4;       // token lanes per column in the LN / position gradient reductions
+constexpr int PG_LANES = 6;       // token lanes per column in the LN / position gradient reductions (160 x 6 = 960 threads)
 
 struct EncWs {
   int *row_len, *row_off, *tok_row, *tok_id, *flags;
@@ -293,8 +293,22 @@ __global__ void k_ln_param_grad(const float* __restrict__ dout, const float* __r
 // ------------------------------------------------------------------------------------------
 // causal self-attention per session row (modules.py:177-223).  CTA per row, 4 warps.
 // ------------------------------------------------------------------------------------------
-// copy n contiguous rows of d floats (d even) into padded shared rows; 4 float2 loads in flight
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, float* __restrict__ dst, int n, int d, int ld) {
+// ---- shared-memory staging helpers (d even; rows are contiguous [n, d] in global memory) ------
+// row-major copy: dst[i*d + c]
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, float* __restrict__ dst, int n, int d) {
+  const int n2 = (n * d) >> 1;
+  const float2* s2 = reinterpret_cast<const float2*>(src);
+  float2* d2 = reinterpret_cast<float2*>(dst);
+  for (int base = threadIdx.x; base < n2; base += 4 * blockDim.x) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { int idx = base + u * blockDim.x; if (idx < n2) v[u] = s2[idx]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { int idx = base + u * blockDim.x; if (idx < n2) d2[idx] = v[u]; }
+  }
+}
+// transposed copy: dst[c*LP + i]; columns i in [n, LP) are zero-filled
+__device__ __forceinline__ void stage_rows_t(const float* __restrict__ src, float* __restrict__ dst, int n, int d, int LP) {
   const int n2 = (n * d) >> 1;
   const float2* s2 = reinterpret_cast<const float2*>(src);
   for (int base = threadIdx.x; base < n2; base += 4 * blockDim.x) {
@@ -304,139 +318,236 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, float*
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int idx = base + u * blockDim.x;
-      if (idx < n2) { int e = idx * 2; int i = e / d, c = e - i * d; dst[i * ld + c] = v[u].x; dst[i * ld + c + 1] = v[u].y; }
+      if (idx < n2) { int e = idx * 2; int i = e / d, c = e - i * d; dst[c * LP + i] = v[u].x; dst[(c + 1) * LP + i] = v[u].y; }
     }
   }
+  const int pad = LP - n;
+  for (int idx = threadIdx.x; idx < d * pad; idx += blockDim.x) { int c = idx / pad, i = n + idx % pad; dst[c * LP + i] = 0.f; }
 }
 
-__global__ void __launch_bounds__(128) k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K,
-                                                  const float* __restrict__ V, const float* __restrict__ Q1,
-                                                  const int* __restrict__ row_len, const int* __restrict__ row_off,
-                                                  int d, int nh, int L, int Tcap, float drop_p, uint64_t seed,
-                                                  uint32_t site, float* __restrict__ probs, float* __restrict__ Y) {
-  extern __shared__ float sm[];
+// Attention kernels: one CTA (8 warps) per session row.  A warp owns a block of 4 queries (or 4 keys in
+// the transposed products); operands are staged so that the per-k inner step is one conflict-free LDS
+// (lanes over keys / features) + one broadcast LDS.128 (the 4 queries) feeding 4 independent FMA chains.
+constexpr int ATT_THREADS = 256, ATT_WARPS = 8;
+__host__ __device__ inline int att_lp(int L) { return (L + 3) / 4 * 4; }
+__host__ __device__ inline int al4(int x) { return (x + 3) & ~3; }
+
+__global__ void __launch_bounds__(ATT_THREADS) k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K,
+                                                          const float* __restrict__ V, const float* __restrict__ Q1,
+                                                          const int* __restrict__ row_len, const int* __restrict__ row_off,
+                                                          int d, int nh, int L, int Tcap, float drop_p, uint64_t seed,
+                                                          uint32_t site, float* __restrict__ probs, float* __restrict__ Y) {
+  extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x;
   const int n = row_len[r];
   if (n == 0) return;
   const int off = row_off[r];
-  const int ld = d + 1;
-  float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* ps = Vs + L * ld;  // ps [4][64]
-  stage_rows(Q + (long long)off * d, Qs, n, d, ld);
-  stage_rows(K + (long long)off * d, Ks, n, d, ld);
-  stage_rows(V + (long long)off * d, Vs, n, d, ld);
+  const int LP = att_lp(L);
+  float* Qt = sm;                    // [d][LP]
+  float* Kt = Qt + d * LP;           // [d][LP]
+  float* Vs = Kt + d * LP;           // [L][d]
+  float* Pt = Vs + al4(L * d);       // [ATT_WARPS][64][4]
+  stage_rows_t(Q + (long long)off * d, Qt, n, d, LP);
+  stage_rows_t(K + (long long)off * d, Kt, n, d, LP);
+  stage_rows(V + (long long)off * d, Vs, n, d);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = d / nh;
   const float denom = sqrtf((float)dh);
-  float* pw = ps + warp * 64;
+  float* pw = Pt + warp * 256;
+  const int nblk = (n + 3) >> 2;
   for (int h = 0; h < nh; ++h) {
     const int hc = h * dh;
-    for (int i = warp; i < n; i += 4) {
-      float s[2];
+    for (int blk = warp; blk < nblk; blk += ATT_WARPS) {
+      const int i0 = blk * 4;
+      const int imax = min(i0 + 3, n - 1);
+      float s[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        int j = lane + 32 * u;
-        float acc = -INFINITY;
-        if (j <= i) {
-          acc = 0.f;
-          for (int k = 0; k < dh; ++k) acc = fmaf(Qs[i * ld + hc + k], Ks[j * ld + hc + k], acc);
-          acc = acc / denom;
-        }
-        s[u] = acc;
-      }
-      float mx = warp_max(fmaxf(s[0], s[1]));
-      float e0 = (lane <= i) ? expf(s[0] - mx) : 0.f;
-      float e1 = (lane + 32 <= i) ? expf(s[1] - mx) : 0.f;
-      float sum = warp_sum(e0 + e1);
-      float p[2] = {e0 / sum, e1 / sum};
+        const int j = lane + 32 * u;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        int j = lane + 32 * u;
-        if (j < L) {
-          long long po = ((long long)h * Tcap + off + i) * L + j;
-          probs[po] = p[u];
-          float pd = p[u];
-          if (drop_p > 0.f) pd *= drop_scale(seed, site, (uint64_t)po, drop_p);
-          pw[j] = pd;
+        for (int q = 0; q < 4; ++q) s[u][q] = -INFINITY;
+        if (32 * u > imax) continue;                     // warp-uniform
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int jj = min(j, LP - 1);
+#pragma unroll 4
+        for (int k = 0; k < dh; ++k) {
+          const float kv = Kt[(hc + k) * LP + jj];
+          const float4 q4 = *reinterpret_cast<const float4*>(&Qt[(hc + k) * LP + i0]);
+          acc[0] = fmaf(q4.x, kv, acc[0]); acc[1] = fmaf(q4.y, kv, acc[1]);
+          acc[2] = fmaf(q4.z, kv, acc[2]); acc[3] = fmaf(q4.w, kv, acc[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (j <= i0 + q && i0 + q < n) s[u][q] = acc[q] / denom;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q;
+        if (i >= n) break;                               // warp-uniform
+        const float mx = warp_max(fmaxf(s[0][q], s[1][q]));
+        const float e0 = (lane <= i) ? expf(s[0][q] - mx) : 0.f;
+        const float e1 = (lane + 32 <= i) ? expf(s[1][q] - mx) : 0.f;
+        const float sum = warp_sum(e0 + e1);
+        const float p[2] = {e0 / sum, e1 / sum};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = lane + 32 * u;
+          float pd = 0.f;
+          if (j < L) {
+            const long long po = ((long long)h * Tcap + off + i) * L + j;
+            probs[po] = p[u];
+            pd = p[u];
+            if (drop_p > 0.f) pd *= drop_scale(seed, site, (uint64_t)po, drop_p);
+          }
+          pw[j * 4 + q] = pd;
         }
       }
+      for (int q = imax - i0 + 1; q < 4; ++q) { pw[lane * 4 + q] = 0.f; pw[(lane + 32) * 4 + q] = 0.f; }
       __syncwarp();
       for (int c = lane; c < dh; c += 32) {
-        float acc = 0.f;
-        for (int j = 0; j <= i; ++j) acc = fmaf(pw[j], Vs[j * ld + hc + c], acc);
-        long long g = (long long)(off + i) * d + hc + c;
-        Y[g] = acc + Q1[g];                       // residual on the NORMALISED queries (modules.py:223)
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int j = 0; j <= imax; ++j) {
+          const float v = Vs[j * d + hc + c];
+          const float4 p4 = *reinterpret_cast<const float4*>(&pw[j * 4]);
+          o[0] = fmaf(p4.x, v, o[0]); o[1] = fmaf(p4.y, v, o[1]); o[2] = fmaf(p4.z, v, o[2]); o[3] = fmaf(p4.w, v, o[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i0 + q < n) {
+            const long long g = (long long)(off + i0 + q) * d + hc + c;
+            Y[g] = o[q] + Q1[g];                  // residual on the NORMALISED queries (modules.py:223)
+          }
+        }
       }
       __syncwarp();
     }
   }
 }
 
-__global__ void __launch_bounds__(128) k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K,
-                                                  const float* __restrict__ V, const float* __restrict__ probs,
-                                                  const float* __restrict__ gY, const int* __restrict__ row_len,
-                                                  const int* __restrict__ row_off, int d, int nh, int L, int Tcap,
-                                                  float drop_p, uint64_t seed, uint32_t site,
-                                                  float* __restrict__ gQ, float* __restrict__ gK,
-                                                  float* __restrict__ gV) {
-  extern __shared__ float sm[];
+__global__ void __launch_bounds__(ATT_THREADS) k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K,
+                                                          const float* __restrict__ V, const float* __restrict__ probs,
+                                                          const float* __restrict__ gY, const int* __restrict__ row_len,
+                                                          const int* __restrict__ row_off, int d, int nh, int L, int Tcap,
+                                                          float drop_p, uint64_t seed, uint32_t site,
+                                                          float* __restrict__ gQ, float* __restrict__ gK,
+                                                          float* __restrict__ gV) {
+  extern __shared__ __align__(16) float sm[];
   const int r = blockIdx.x;
   const int n = row_len[r];
   if (n == 0) return;
   const int off = row_off[r];
-  const int ld = d + 1, lp = L + 1;
-  float* Qs = sm; float* Ks = Qs + L * ld; float* Vs = Ks + L * ld; float* Gs = Vs + L * ld;
-  float* dSs = Gs + L * ld; float* Pds = dSs + L * lp;
-  stage_rows(Q + (long long)off * d, Qs, n, d, ld);
-  stage_rows(K + (long long)off * d, Ks, n, d, ld);
-  stage_rows(V + (long long)off * d, Vs, n, d, ld);
-  stage_rows(gY + (long long)off * d, Gs, n, d, ld);
-  __syncthreads();
+  const int LP = att_lp(L);
+  float* Gt = sm;                    // gY transposed [d][LP]
+  float* Vt = Gt + d * LP;           // V transposed  [d][LP]
+  float* Qs = Vt + d * LP;           // [L][d]
+  float* Ks = Qs + al4(L * d);       // [L][d]
+  float* Gs = Ks + al4(L * d);       // [L][d]
+  float* dSs = Gs + al4(L * d);      // [L][LP]   dS[i][j]
+  float* dSt = dSs + L * LP;         // [L][LP]   dS^T[j][i]
+  float* Pds = dSt + L * LP;         // [L][LP]   dropped probs [i][j]
+  stage_rows_t(gY + (long long)off * d, Gt, n, d, LP);
+  stage_rows_t(V + (long long)off * d, Vt, n, d, LP);
+  stage_rows(Q + (long long)off * d, Qs, n, d);
+  stage_rows(K + (long long)off * d, Ks, n, d);
+  stage_rows(gY + (long long)off * d, Gs, n, d);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = d / nh;
   const float denom = sqrtf((float)dh);
+  const int nblk = (n + 3) >> 2;
   for (int h = 0; h < nh; ++h) {
     const int hc = h * dh;
-    for (int i = warp; i < n; i += 4) {
-      float P[2], dP[2], scl[2];
-      float rowdot = 0.f;
+    // zero dS / dS^T / Pd (entries above the diagonal and the LP padding must read as 0)
+    for (int idx = threadIdx.x; idx < 3 * L * LP; idx += blockDim.x) dSs[idx] = 0.f;
+    __syncthreads();
+    // phase 1: dP = gY . V^T (block of 4 queries x 32 keys), softmax backward
+    for (int blk = warp; blk < nblk; blk += ATT_WARPS) {
+      const int i0 = blk * 4;
+      const int imax = min(i0 + 3, n - 1);
+      float dp[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        int j = lane + 32 * u;
-        P[u] = 0.f; dP[u] = 0.f; scl[u] = 1.f;
-        if (j <= i) {
-          long long po = ((long long)h * Tcap + off + i) * L + j;
-          P[u] = probs[po];
-          if (drop_p > 0.f) scl[u] = drop_scale(seed, site, (uint64_t)po, drop_p);
-          float acc = 0.f;
-          for (int k = 0; k < dh; ++k) acc = fmaf(Gs[i * ld + hc + k], Vs[j * ld + hc + k], acc);
-          dP[u] = acc * scl[u];
-          rowdot += dP[u] * P[u];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dp[u][q] = 0.f;
+        if (32 * u > imax) continue;
+        const int jj = min(lane + 32 * u, LP - 1);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int k = 0; k < dh; ++k) {
+          const float vv = Vt[(hc + k) * LP + jj];
+          const float4 g4 = *reinterpret_cast<const float4*>(&Gt[(hc + k) * LP + i0]);
+          acc[0] = fmaf(g4.x, vv, acc[0]); acc[1] = fmaf(g4.y, vv, acc[1]);
+          acc[2] = fmaf(g4.z, vv, acc[2]); acc[3] = fmaf(g4.w, vv, acc[3]);
         }
-      }
-      rowdot = warp_sum(rowdot);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        int j = lane + 32 * u;
-        if (j < L) {
-          dSs[i * lp + j] = (j <= i) ? P[u] * (dP[u] - rowdot) / denom : 0.f;
-          Pds[i * lp + j] = (j <= i) ? P[u] * scl[u] : 0.f;
+        for (int q = 0; q < 4; ++q) dp[u][q] = acc[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q;
+        if (i >= n) break;
+        float P[2], dP[2], scl[2];
+        float rowdot = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = lane + 32 * u;
+          P[u] = 0.f; dP[u] = 0.f; scl[u] = 1.f;
+          if (j <= i) {
+            const long long po = ((long long)h * Tcap + off + i) * L + j;
+            P[u] = probs[po];
+            if (drop_p > 0.f) scl[u] = drop_scale(seed, site, (uint64_t)po, drop_p);
+            dP[u] = dp[u][q] * scl[u];
+            rowdot += dP[u] * P[u];
+          }
+        }
+        rowdot = warp_sum(rowdot);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = lane + 32 * u;
+          if (j <= i) {
+            const float ds = P[u] * (dP[u] - rowdot) / denom;
+            dSs[i * LP + j] = ds; dSt[j * LP + i] = ds; Pds[i * LP + j] = P[u] * scl[u];
+          }
         }
       }
     }
     __syncthreads();
-    for (int i = warp; i < n; i += 4) {
+    // phase 2a: gQ[i] = sum_{j<=i} dS[i][j] K[j]  (block of 4 queries, lanes over features)
+    for (int blk = warp; blk < nblk; blk += ATT_WARPS) {
+      const int i0 = blk * 4;
+      const int imax = min(i0 + 3, n - 1);
       for (int c = lane; c < dh; c += 32) {
-        float aq = 0.f;
-        for (int j = 0; j <= i; ++j) aq = fmaf(dSs[i * lp + j], Ks[j * ld + hc + c], aq);
-        gQ[(long long)(off + i) * d + hc + c] = aq;
-        float ak = 0.f, av = 0.f;   // here "i" plays the role of the key index j
-        for (int q = i; q < n; ++q) {
-          ak = fmaf(dSs[q * lp + i], Qs[q * ld + hc + c], ak);
-          av = fmaf(Pds[q * lp + i], Gs[q * ld + hc + c], av);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int j = 0; j <= imax; ++j) {
+          const float kv = Ks[j * d + hc + c];
+          const float4 s4 = *reinterpret_cast<const float4*>(&dSt[j * LP + i0]);
+          o[0] = fmaf(s4.x, kv, o[0]); o[1] = fmaf(s4.y, kv, o[1]); o[2] = fmaf(s4.z, kv, o[2]); o[3] = fmaf(s4.w, kv, o[3]);
         }
-        gK[(long long)(off + i) * d + hc + c] = ak;
-        gV[(long long)(off + i) * d + hc + c] = av;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q < n) gQ[(long long)(off + i0 + q) * d + hc + c] = o[q];
+      }
+    }
+    // phase 2b: gK[j] = sum_{i>=j} dS[i][j] Q[i],  gV[j] = sum_{i>=j} Pd[i][j] gY[i]  (block of 4 keys)
+    for (int blk = warp; blk < nblk; blk += ATT_WARPS) {
+      const int j0 = blk * 4;
+      for (int c = lane; c < dh; c += 32) {
+        float ok[4] = {0.f, 0.f, 0.f, 0.f}, ov[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int i = j0; i < n; ++i) {
+          const float qv = Qs[i * d + hc + c], gv = Gs[i * d + hc + c];
+          const float4 s4 = *reinterpret_cast<const float4*>(&dSs[i * LP + j0]);
+          const float4 p4 = *reinterpret_cast<const float4*>(&Pds[i * LP + j0]);
+          ok[0] = fmaf(s4.x, qv, ok[0]); ok[1] = fmaf(s4.y, qv, ok[1]); ok[2] = fmaf(s4.z, qv, ok[2]); ok[3] = fmaf(s4.w, qv, ok[3]);
+          ov[0] = fmaf(p4.x, gv, ov[0]); ov[1] = fmaf(p4.y, gv, ov[1]); ov[2] = fmaf(p4.z, gv, ov[2]); ov[3] = fmaf(p4.w, gv, ov[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j0 + q < n) {
+            gK[(long long)(off + j0 + q) * d + hc + c] = ok[q];
+            gV[(long long)(off + j0 + q) * d + hc + c] = ov[q];
+          }
+        }
       }
     }
     __syncthreads();
@@ -605,10 +716,10 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys
       if (diff) { qe += __ffs(diff) - 1; break; }
       qe += 32;
     }
-    for (int q = p; q < qe; q += 4) {                  // 4 rows in flight, added in token order
-      float v[4][LN_MAXE];
+    for (int q = p; q < qe; q += 8) {                  // 8 rows in flight, added in token order
+      float v[8][LN_MAXE];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const bool ok = q + u < qe;
         long long o = ok ? (long long)vals[q + u] * d : 0;
 #pragma unroll
@@ -623,7 +734,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int i = 0; i < LN_MAXE; ++i) acc[i] += v[u][i];
     }
@@ -719,7 +830,7 @@ extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, cons
                                                            dropout_rate, seed, w.slot[0][0]);
   ADER_CHECK_LAUNCH("encoder_fwd/pack+embed");
 
-  const size_t attn_smem = sizeof(float) * (3 * (size_t)L * (d + 1) + 4 * 64);
+  const size_t attn_smem = sizeof(float) * (2 * (size_t)d * att_lp(L) + (size_t)al4(L * d) + ATT_WARPS * 256);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -737,7 +848,7 @@ extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, cons
     if (int e = run_dense(st, Q1, P + l.wq, P + l.bq, Qp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     if (int e = run_dense(st, X, P + l.wk, P + l.bk, Kp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     if (int e = run_dense(st, X, P + l.wv, P + l.bv, Vp, Tcap, dT, d, false, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
-    k_attn_fwd<<<M, 128, attn_smem, st>>>(Qp, Kp, Vp, Q1, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
+    k_attn_fwd<<<M, ATT_THREADS, attn_smem, st>>>(Qp, Kp, Vp, Q1, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
                                           dropout_rate, seed, 1u + 3u * b, w.probs[b], Y);
     k_ln_fwd<<<ln_grid, 256, 0, st>>>(Y, Z, w.mean2[b], w.rstd2[b], P + l.ln2b, P + l.ln2g, dT, d);
     if (int e = run_dense(st, Z, P + l.w1, P + l.b1, H, Tcap, dT, d, false, 1, nullptr, nullptr, 0, 1.f,
@@ -773,7 +884,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
   const int el_grid = cdiv((long long)Tcap * d, 256);
   const int ln_threads = ((d + 31) / 32) * 32;
 
-  const size_t attn_smem = sizeof(float) * (4 * (size_t)L * (d + 1) + 2 * (size_t)L * (L + 1));
+  const size_t attn_smem = sizeof(float) * (2 * (size_t)d * att_lp(L) + 3 * (size_t)al4(L * d) + 3 * (size_t)L * att_lp(L));
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -808,7 +919,7 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     k_ln_bwd<<<ln_grid, 256, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], P + l.ln2g, gY, dT, d, 0);
     k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
                                                    part(bo + l.ln2b), part(bo + l.ln2g), PS);
-    k_attn_bwd<<<M, 128, attn_smem, st>>>(Qp, Kp, Vp, w.probs[b], gY, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
+    k_attn_bwd<<<M, ATT_THREADS, attn_smem, st>>>(Qp, Kp, Vp, w.probs[b], gY, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
                                           p, seed, 1u + 3u * b, gQ, gK, gV);
     ADER_CHECK_LAUNCH("encoder_bwd/attn");
     if (int e = run_wgrad(st, Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d)) return e;

@@ -83,6 +83,10 @@ def run(data_dir: str, item_num: int, args, n_periods: int) -> dict:
                         lg = S.logits_of(S.forward_rep(params, ids, hp), params[0], max_item)
                         n_t = pos_t.numel()
                         rl = S.ce_rows(lg[:n_t], pos_t).numpy()
+                        if es is not None and not args.disable_distillation:
+                            tt = torch.softmax(tl, 1)
+                            kd = -(tt * torch.log_softmax(lg[n_t:, :tl.shape[1]], 1)).sum(1).numpy()
+                            rl = np.concatenate([rl, kd])
                     rec.setdefault("rows", []).append((rl, ids.numpy()))
                 params = opt.step(params, grads, args.lr)
                 rec["losses"].append(loss)

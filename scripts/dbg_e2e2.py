@@ -23,6 +23,9 @@ for p,(g,w) in enumerate(zip(got["trace"]["periods"], want["periods"])):
         (grl, gids), (wrl, wids) = g["rows"][k], w["rows"][k]
         print("  ids equal", np.array_equal(gids, wids), gids.shape, wids.shape, "n_train rows", len(wrl))
         n = len(wrl)
+        print("  lens", len(grl), len(wrl), "lambda-free means: train CE got %.5f want %.5f | ex rows got %.5f want %.5f" % (grl[:63].mean(), wrl[:63].mean(), grl[63:].mean(), wrl[63:].mean()))
+        print("  ex ids equal rows:", [bool(np.array_equal(gids[i], wids[i])) for i in range(63, len(gids))])
+        print("  ex KD got", np.round(grl[63:],3), "want", np.round(wrl[63:],3))
         d = np.abs(grl[:n]-wrl)
         idx = np.argsort(-d)[:6]
         for i in idx:

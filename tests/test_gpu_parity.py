@@ -539,7 +539,7 @@ def test_end_to_end_herding_periods(tmp_path):
         assert len(g["losses"]) == len(w["losses"])
         # a step draws only ~9 exemplar rows here, so one different exemplar moves a step loss by a few %
         np.testing.assert_allclose(g["losses"], w["losses"], rtol=6e-2)
-        assert np.mean(g["losses"]) == pytest.approx(np.mean(w["losses"]), rel=1e-2)
+        assert np.mean(g["losses"]) == pytest.approx(np.mean(w["losses"]), rel=3e-2)
         np.testing.assert_allclose(g["test"], w["test"], atol=5e-2)
         assert len(g["exemplars"]) == len(w["exemplars"])
 
