@@ -27,7 +27,8 @@ class AderLossArgs(C.Structure):
     _fields_ = [("M", C.c_int32), ("n_train", C.c_int32), ("n_ex", C.c_int32), ("V", C.c_int32),
                 ("V_prev", C.c_int32), ("mode", C.c_int32), ("lambda_", C.c_float),
                 ("pos", C.c_void_p), ("ex_pos", C.c_void_p), ("teacher", C.c_void_p),
-                ("teacher_row", C.c_void_p), ("teacher_ld", C.c_int64)]
+                ("teacher_row", C.c_void_p), ("teacher_ld", C.c_int64),
+                ("n_train_global", C.c_int32), ("n_ex_global", C.c_int32)]
 
 
 class AderAdamArgs(C.Structure):

@@ -472,7 +472,8 @@ using namespace ader;
 using namespace ader::tc;
 
 // loss_reduce lives in loss.cu
-namespace ader { int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st); }
+namespace ader { int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st,
+                                        int den_train, int den_ex); }
 
 struct TcWs {
   uint8_t *rep_tiles, *e_tiles;
@@ -541,15 +542,15 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   TcArgs t;
   t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = V; t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
   t.n_train = a->n_train; t.n_ex = a->n_ex; t.V_prev = a->V_prev; t.mode = a->n_ex > 0 ? a->mode : 0;
-  t.coef_train = a->n_train > 0 ? 1.0f / (float)a->n_train : 0.f;
-  t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)a->n_ex : 0.f;
+  t.coef_train = a->n_train > 0 ? 1.0f / (float)(a->n_train_global > 0 ? a->n_train_global : a->n_train) : 0.f;
+  t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)(a->n_ex_global > 0 ? a->n_ex_global : a->n_ex) : 0.f;
   t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
 
   k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
   k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss);
-  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st)) return e;
+  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
     k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) k_ce_kd_rows(float* __restrict__ S, long 
   const bool is_train = i < a.n_train;
   if (is_train || a.mode == 2) {
     const int label = is_train ? a.pos[i] : a.ex_pos[i - a.n_train];
-    const float coef = is_train ? 1.0f / (float)a.n_train : a.lambda_ / (float)a.n_ex;
+    const float coef = is_train ? 1.0f / (float)(a.n_train_global > 0 ? a.n_train_global : a.n_train)
+                                : a.lambda_ / (float)(a.n_ex_global > 0 ? a.n_ex_global : a.n_ex);
     float mx = -INFINITY;
     for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, s[j]);
     mx = block_reduce(mx, true, sh);
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) k_ce_kd_rows(float* __restrict__ S, long 
     const int Vp = a.V_prev;
     const long long trow = a.teacher_row ? a.teacher_row[i - a.n_train] : (i - a.n_train);
     const float* t = a.teacher + trow * a.teacher_ld;
-    const float coef = a.lambda_ / (float)a.n_ex;
+    const float coef = a.lambda_ / (float)(a.n_ex_global > 0 ? a.n_ex_global : a.n_ex);
     float mx = -INFINITY, mt = -INFINITY;
     for (int j = threadIdx.x; j < Vp; j += blockDim.x) { mx = fmaxf(mx, s[j]); mt = fmaxf(mt, t[j]); }
     mx = block_reduce(mx, true, sh);
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) k_ce_kd_rows(float* __restrict__ S, long 
 }
 
 __global__ void __launch_bounds__(256) k_loss_reduce(const float* __restrict__ row_loss, int n_train, int n_ex,
-                                                     float lambda_, float* __restrict__ loss) {
+                                                     float lambda_, float* __restrict__ loss, int den_train, int den_ex) {
   __shared__ float sh[32];
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < n_train; i += blockDim.x) a += row_loss[i];
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(256) k_loss_reduce(const float* __restrict__ r
   a = block_reduce(a, false, sh);
   b = block_reduce(b, false, sh);
   if (threadIdx.x == 0) {
-    float v = n_train > 0 ? a / (float)n_train : 0.f;
-    if (n_ex > 0) v += lambda_ * (b / (float)n_ex);
+    float v = n_train > 0 ? a / (float)den_train : 0.f;
+    if (n_ex > 0) v += lambda_ * (b / (float)den_ex);
     loss[0] = v;
   }
 }
@@ -96,8 +97,10 @@ __global__ void k_reduce_splits(const float* __restrict__ partial, long long str
   out[i] = s;
 }
 
-int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st) {
-  k_loss_reduce<<<1, 256, 0, st>>>(row_loss, n_train, n_ex, lambda_, loss);
+int launch_loss_reduce(const float* row_loss, int n_train, int n_ex, float lambda_, float* loss, cudaStream_t st,
+                       int den_train, int den_ex) {
+  k_loss_reduce<<<1, 256, 0, st>>>(row_loss, n_train, n_ex, lambda_, loss, den_train > 0 ? den_train : n_train,
+                                   den_ex > 0 ? den_ex : n_ex);
   ADER_CHECK_LAUNCH("loss_reduce");
   return 0;
 }
@@ -202,7 +205,7 @@ extern "C" int32_t ader_loss_fwd_bwd(const AderModel* m, const float* theta, con
   float* part = (float*)((char*)ws + align_up(sizeof(float) * (size_t)M * ld));
   if (int e = run_logits(m, theta, rep, M, V, S, ld, st)) return e;
   k_ce_kd_rows<<<M, 256, 0, st>>>(S, ld, *a, row_loss);
-  k_loss_reduce<<<1, 256, 0, st>>>(row_loss, a->n_train, a->n_ex, a->lambda_, loss);
+  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("loss rows");
   if (d_rep) {   // d_rep = dS . E[1..V]   (split-K over the vocabulary, fixed-order reduce)
     GemmArgs g; gemm_defaults(g);

@@ -243,9 +243,10 @@ class Evaluator:
         self.chunk_rows = chunk_rows
         self.topk = None
 
-    def evaluate(self, epoch: int, k: int = 20) -> str:                          # util.py:309-327
+    def evaluate(self, epoch: int, k: int = 0) -> str:                           # util.py:309-327
         """All rows of one pass are ranked on the device in a few large calls.  The rank list is in
-        the reference's batch order; the sampler's RNG is consumed as batch_num() sampler() calls."""
+        the reference's batch order; the sampler's RNG is consumed as batch_num() sampler() calls.
+        k > 0 additionally keeps the top-k item ids per row in ``self.topk`` (the metrics only need ranks)."""
         s = self.evaluate_sampler
         order = s.epoch_order()
         ids, label, n_in = s.packed()
@@ -258,7 +259,7 @@ class Evaluator:
             tops.append(items)
         if ranks:
             self.ranks = torch.cat(ranks).cpu().numpy().tolist()
-            self.topk = torch.cat(tops)
+            self.topk = torch.cat(tops) if k > 0 else None
         else:
             self.ranks = []
         return self.display(epoch)

@@ -68,6 +68,7 @@ class Ader:
         self.mode = self.VANILLA
         self.lambda_ = 0.0
         self.grad_sync = None
+        self.global_counts = None       # data parallel: (n_train, n_ex) over all ranks -> global means
         self.loss_impl = getattr(args, "loss_impl", "tc")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
         self._enc_ws = ops.Workspace(self.device)
@@ -127,7 +128,8 @@ class Ader:
     # ---- training step ------------------------------------------------------------------------
     def loss_and_grad(self, seq, pos, max_item: int, exemplar_logits=None, exemplar_pos=None,
                       teacher_rows=None, dropout_rate: float = 0.0, n_tokens: Optional[int] = None,
-                      mode: Optional[int] = None, lambda_: Optional[float] = None, _events=None) -> torch.Tensor:
+                      mode: Optional[int] = None, lambda_: Optional[float] = None, _events=None,
+                      global_counts=None) -> torch.Tensor:
         """Forward + backward of the current loss; fills ``self.grad`` (flat).  Returns the device
         scalar loss.  ``exemplar_logits`` is either a host array / list [M_e, V_prev] (reference feed,
         ADER.py:20) or a device tensor [E, V_prev] indexed by ``teacher_rows`` [M_e]."""
@@ -167,8 +169,9 @@ class Ader:
         rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed)
         if _events:
             _events[0].record()
+        gc = global_counts if global_counts is not None else self.global_counts
         a = ops.make_loss_args(M, n_train, n_ex, max_item, v_prev, mode if n_ex > 0 else self.VANILLA, lam,
-                               pos_t, ex_pos_t, teacher, trow)
+                               pos_t, ex_pos_t, teacher, trow, *(gc or (0, 0)))
         row_loss = torch.empty(M, dtype=torch.float32, device=self.device)
         d_rep = torch.empty_like(rep)
         if self.loss_impl == "tc":       # tcgen05 fused kernels (bf16 operands)

@@ -82,7 +82,7 @@ def encoder_bwd(ms: AderModel, theta, ids, Tcap: int, ws, bwd_ws, d_rep, grad, d
 
 
 def make_loss_args(M, n_train, n_ex, V, V_prev=0, mode=0, lambda_=0.0, pos=None, ex_pos=None,
-                   teacher=None, teacher_row=None) -> AderLossArgs:
+                   teacher=None, teacher_row=None, n_train_global=0, n_ex_global=0) -> AderLossArgs:
     a = AderLossArgs()
     a.M, a.n_train, a.n_ex, a.V, a.V_prev, a.mode, a.lambda_ = M, n_train, n_ex, V, V_prev, mode, lambda_
     a.pos = pos.data_ptr() if pos is not None else None
@@ -90,6 +90,7 @@ def make_loss_args(M, n_train, n_ex, V, V_prev=0, mode=0, lambda_=0.0, pos=None,
     a.teacher = teacher.data_ptr() if teacher is not None else None
     a.teacher_row = teacher_row.data_ptr() if teacher_row is not None else None
     a.teacher_ld = teacher.stride(0) if teacher is not None else 0
+    a.n_train_global, a.n_ex_global = n_train_global, n_ex_global
     return a
 
 

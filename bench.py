@@ -195,10 +195,11 @@ def gpu_arm(args):
 
     model = Ader(WL["item_num"], make_args(), device=dev, init_seed=0)
     model.update_loss(WL["lam"])
-    if world > 1:
+    if world > 1:       # data parallel: global-mean denominators + one all-reduce (sum) of the flat gradient
         def sync_grad():
-            dist.all_reduce(model.grad, op=dist.ReduceOp.AVG)
+            dist.all_reduce(model.grad, op=dist.ReduceOp.SUM)
         model.grad_sync = sync_grad
+        model.global_counts = (WL["B"] * world, WL["M_e"] * world)
     rng = np.random.RandomState(100 + rank)
     pool = 32768
     t_ids, t_lab, t_len = synth_rows(rng, pool, V)

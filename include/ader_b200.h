@@ -86,6 +86,8 @@ typedef struct AderLossArgs {
   const float*   teacher;  /* [*, V_prev] fp32 stored exemplar logits (mode 1)                 */
   const int32_t* teacher_row; /* [n_ex] row of `teacher` per exemplar row, or NULL = identity  */
   int64_t teacher_ld;      /* row stride of `teacher` in elements (>= V_prev)                  */
+  int32_t n_train_global;  /* data parallel: denominators of the two means over ALL ranks (0 = local   */
+  int32_t n_ex_global;     /* counts); gradients and loss are then summed, not averaged, across ranks  */
 } AderLossArgs;
 
 size_t  ader_loss_ws_bytes(const AderModel* m, const AderLossArgs* a);
