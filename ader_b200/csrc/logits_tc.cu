@@ -110,7 +110,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// wait for outstanding tcgen05.ld; the registers are passed as in/out operands so the compiler cannot
+// schedule their first use ahead of the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
 }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -177,8 +193,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   if (MODE == MODE_DE) { x_tile = blockIdx.x; y_lo = 0; y_hi = a.n_mtiles; }
   else {
     x_tile = blockIdx.x % a.n_mtiles; chunk = blockIdx.x / a.n_mtiles;
-    const int per = (a.n_vtiles + a.n_chunks - 1) / a.n_chunks;
-    y_lo = chunk * per; y_hi = min(a.n_vtiles, y_lo + per);
+    y_lo = (int)((long long)chunk * a.n_vtiles / a.n_chunks);           // balanced split of the vocabulary tiles
+    y_hi = (int)((long long)(chunk + 1) * a.n_vtiles / a.n_chunks);
   }
   const int n_it = max(0, y_hi - y_lo);
   const uint8_t* gX = (MODE == MODE_DE ? a.e_tiles : a.rep_tiles) + (size_t)x_tile * TILE_BYTES;
@@ -277,23 +293,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
       else v0 = (y_lo + it) * TILE;
       mbar_wait(BAR(B_TFULL + s), ph, a.err);
       tc_fence_after();
-      if (MODE != MODE_FWD) mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
-      uint8_t* ds = sD + s * DS_BYTES;
-#pragma unroll 1
-      for (int c4 = half * 2; c4 < half * 2 + 2; ++c4) {
-        uint32_t r[32];
-        const int vb = v0 + c4 * 32;
-        float tv[32];                           // teacher logits of this chunk: 32 independent loads in flight
-        if (ri.kind == 2) {
+      // this thread's 64 columns of the S tile -> registers, then hand the TMEM buffer back at once so the
+      // next S tile's MMAs overlap with the exponentials below
+      uint32_t r[2][32];
+      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2) * 32, r[0]);
+      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2 + 1) * 32, r[1]);
+      tmem_ld_wait(r[0]);
+      tmem_ld_wait(r[1]);
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + s));
+      const int vb0 = v0 + half * 64;
+      const bool full = (ri.kind != 0) && (vb0 + 64 <= ri.vlim);     // all 64 columns inside this row's softmax
+      if (MODE == MODE_FWD) {
+        if (full) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tv[i] = (vb + i < ri.vlim) ? ri.trow[vb + i] : 0.f;
-        }
-        tmem_ld32(tmem + tlane + s * 128 + c4 * 32, r);
-        if (MODE == MODE_FWD) {
-          if (ri.kind != 0 && vb < ri.vlim) {
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[c][i]));
+          const float nm = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          sum *= ex2((mx - nm) * LOG2E);
+          mx = nm;
+          const float nm2 = nm * LOG2E;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s4[i & 3] += ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -nm2));
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          if (ri.label >= vb0 && ri.label < vb0 + 64) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (vb0 + c * 32 + i == ri.label) lab = __uint_as_float(r[c][i]);
+          }
+          if (ri.kind == 2) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float tv[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) tv[i] = ri.trow[vb0 + c * 32 + i];
+              float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                d4[i & 3] = fmaf(ex2(fmaf(tv[i], LOG2E, -ri.lset2)), __uint_as_float(r[c][i]), d4[i & 3]);
+              dot += (d4[0] + d4[1]) + (d4[2] + d4[3]);
+            }
+          }
+        } else if (ri.kind != 0 && vb0 < ri.vlim) {               // boundary tile: per-element checks
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int vb = vb0 + c * 32;
+            if (vb >= ri.vlim) break;
             float cm = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(r[c][i]));
             const float nm = fmaxf(mx, cm);
             sum *= ex2((mx - nm) * LOG2E);
             mx = nm;
@@ -302,43 +356,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
             for (int i = 0; i < 32; ++i) {
               const int v = vb + i;
               if (v < ri.vlim) {
-                const float sv = __uint_as_float(r[i]);
+                const float sv = __uint_as_float(r[c][i]);
                 sum += ex2(fmaf(sv, LOG2E, -nm2));
                 if (v == ri.label) lab = sv;
-                if (ri.kind == 2) dot = fmaf(ex2(fmaf(tv[i], LOG2E, -ri.lset2)), sv, dot);
+                if (ri.kind == 2) dot = fmaf(ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)), sv, dot);
               }
             }
           }
-        } else {
-          uint32_t pk[16];
+        }
+      } else {
+        mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+        uint8_t* ds = sD + s * DS_BYTES;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float g2[2];
+        for (int c = 0; c < 2; ++c) {
+          const int vb = vb0 + c * 32;
+          float g[32];
+          if (full) {
+            if (ri.kind == 1) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int v = vb + i + u;
-              float g = 0.f;
-              if (ri.kind != 0 && v < ri.vlim) {
-                const float p = ex2(fmaf(__uint_as_float(r[i + u]), LOG2E, -ri.lse2));
-                if (ri.kind == 1) g = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
-                else g = ri.coef * (p - ex2(fmaf(tv[i + u], LOG2E, -ri.lset2)));
+              for (int i = 0; i < 32; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+              if (ri.label >= vb && ri.label < vb + 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
               }
-              g2[u] = g;
+            } else {
+              float tv[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) tv[i] = ri.trow[vb + i];
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                g[i] = ri.coef * (ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2)) - ex2(fmaf(tv[i], LOG2E, -ri.lset2)));
             }
-            __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int v = vb + i;
+              float gv = 0.f;
+              if (ri.kind != 0 && v < ri.vlim) {
+                const float p = ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+                if (ri.kind == 1) gv = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
+                else gv = ri.coef * (p - ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)));
+              }
+              g[i] = gv;
+            }
           }
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {      // 8 columns = one 16-byte core-matrix row
-            const int vg = c4 * 4 + gq;
-            uint4 val = make_uint4(pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2], pk[gq * 4 + 3]);
-            *reinterpret_cast<uint4*>(ds + (vg * 16 + (row >> 3)) * 128 + (row & 7) * 16) = val;
+            uint32_t pk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(g[gq * 8 + 2 * u], g[gq * 8 + 2 * u + 1]);
+              pk[u] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const int vg = (half * 2 + c) * 4 + gq;
+            *reinterpret_cast<uint4*>(ds + (vg * 16 + (row >> 3)) * 128 + (row & 7) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(BAR(B_TEMPTY + s));
-      if (MODE != MODE_FWD) {
         fence_async_smem();                    // generic-proxy writes -> visible to the MMA (async proxy)
         mbar_arrive(BAR(B_DSFULL + s));
       }
@@ -482,7 +555,16 @@ struct TcWs {
   size_t bytes;
 };
 static int tc_chunks(int n_mtiles, int n_vtiles) {
-  int c = 148 / n_mtiles; if (c < 1) c = 1; if (c > n_vtiles) c = n_vtiles; return c;
+  // vocabulary chunks per row tile: fill whole waves of 148 SMs (one CTA per SM), keep >= 4 tiles per CTA
+  int best = 1; double best_eff = 0.0;
+  const int cmax = n_vtiles / 4 > 1 ? (n_vtiles / 4 < 64 ? n_vtiles / 4 : 64) : 1;
+  for (int c = 1; c <= cmax; ++c) {
+    const long long ctas = (long long)n_mtiles * c;
+    const long long waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (148.0 * waves);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+  }
+  return best;
 }
 static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, char* base) {
   TcWs w; size_t o = 0;
