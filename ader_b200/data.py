@@ -364,6 +364,7 @@ class ExemplarGenerator:
             rows.append(sel)
         picked = np.concatenate(rows) if rows else np.zeros(0, np.int32)
         self.last_picks = (picks_h, n_h)
+        self.last_reps, self.last_quota = reps, quota
         return self._store(model, picked, reps, by_item)
 
     def loss_selection(self, sess, model) -> int:                                 # util.py:463-492

@@ -267,6 +267,9 @@ def run(args) -> dict:
             logs.write(info + "\n")
             fast_exemplar = gen.exemplars
             rec["exemplars"] = list(fast_exemplar.sessions)
+            if trace is not None and args.selection == "herding":
+                rec["herding"] = {"reps": gen.last_reps.cpu().numpy(), "cand": gen.cand, "seg_off": gen.seg_off,
+                                  "items": gen.items, "quota": gen.last_quota, "picks": gen.last_picks}
             if trace is not None:
                 rec["ex_by_item"] = {int(k): [gen.rows[r][-(args.maxlen + 1):] for r in v] for k, v in fast_exemplar.by_item.items()}
             del gen
