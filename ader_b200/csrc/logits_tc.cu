@@ -43,6 +43,7 @@ struct TcArgs {
   float coef_train, coef_ex;    // 1/n_train, lambda/n_ex
   const int* pos; const int* ex_pos;
   const float* teacher; const int* teacher_row; long long teacher_ld;
+  int teacher_vec4;             // teacher rows are 16-byte aligned (ld % 4 == 0): 128-bit loads
   const float* lse;             // [M]   (backward)
   const float* lse_t;           // [n_ex] teacher log-sum-exp
   float* stats;                 // FWD: [n_chunks*2][M][4] = (max, sumexp, label logit, kd dot) per column half
@@ -170,6 +171,21 @@ __device__ __forceinline__ RowInfo row_info(const TcArgs& a, int gm, bool bwd) {
 }
 
 constexpr int NTHREADS = 320, NEPI = 256;
+// streamed-tile ring depth: the backward kernels free a stage only after the SECOND MMA of a tile, so two
+// stages expose the L2 latency of every tile (ncu: epilogue warps 41 % stalled on the S-tile barrier)
+__host__ __device__ constexpr int n_stages(int mode) { return mode == 0 ? 4 : 3; }
+
+// 32 consecutive teacher logits of one row (start column is a multiple of 32)
+__device__ __forceinline__ void load_teacher32(const float* __restrict__ p, bool vec4, float (&tv)[32]) {
+  if (vec4) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const float4 x = __ldg(p4 + q); tv[4 * q] = x.x; tv[4 * q + 1] = x.y; tv[4 * q + 2] = x.z; tv[4 * q + 3] = x.w; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tv[i] = __ldg(p + i);
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
@@ -177,13 +193,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   // carve: [X stationary tile][Y stage 0][Y stage 1][dS 0][dS 1][barriers]
   uint8_t* sX = smem;
   uint8_t* sY = smem + TILE_BYTES;
-  uint8_t* sD = smem + 3 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES + (MODE == MODE_FWD ? 0 : 2 * DS_BYTES));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  constexpr int NST = n_stages(MODE);
+  uint8_t* sD = smem + (1 + NST) * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + NST) * TILE_BYTES + (MODE == MODE_FWD ? 0 : 2 * DS_BYTES));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   // barrier ids
-  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 3, B_TFULL = 5, B_TEMPTY = 7, B_DSFULL = 9, B_DSEMPTY = 11, B_ACC = 13;
+  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 5, B_TFULL = 9, B_TEMPTY = 11, B_DSFULL = 13, B_DSEMPTY = 15, B_ACC = 17;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -203,8 +220,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   // ---- setup ---------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     mbar_init(BAR(B_XFULL), 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1);
       mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), NEPI);
       mbar_init(BAR(B_DSFULL + s), NEPI); mbar_init(BAR(B_DSEMPTY + s), 1);
     }
@@ -227,9 +244,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
     if (lane == 0 && n_it > 0) {
       load_tile(smem_u32(sX), gX, BAR(B_XFULL));
       for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(B_YEMPTY + s), ph ^ 1, a.err);
-        load_tile(smem_u32(sY + s * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, BAR(B_YFULL + s));
+        const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
+        mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
+        load_tile(smem_u32(sY + ys * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, BAR(B_YFULL + ys));
       }
     }
   } else if (warp == 1) {
@@ -240,16 +257,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
       const uint32_t xa = smem_u32(sX);
       auto issue_s = [&](int it) {          // S[buf] = rep_tile . e_tile^T
         const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(B_YFULL + s), ph, a.err);
+        const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
+        mbar_wait(BAR(B_YFULL + ys), yph, a.err);
         mbar_wait(BAR(B_TEMPTY + s), ph ^ 1, a.err);
         tc_fence_after();
-        const uint32_t ya = smem_u32(sY + s * TILE_BYTES);
+        const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
         const uint32_t A = (MODE == MODE_DE) ? ya : xa;     // rows of S = logits rows (rep)
         const uint32_t B = (MODE == MODE_DE) ? xa : ya;
 #pragma unroll
         for (int k = 0; k < KSTEPS1; ++k)
           umma_bf16(tmem + s * 128, make_desc(A + k * 4096, 2048, 128), make_desc(B + k * 4096, 2048, 128), IDESC1, k > 0);
-        if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + s));
+        if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + ys));
         umma_commit(BAR(B_TFULL + s));
       };
       mbar_wait(BAR(B_XFULL), 0, a.err);
@@ -258,10 +276,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
         if (it + 1 < n_it) issue_s(it + 1);
         if (MODE != MODE_FWD) {
           const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+          const int ys = it % NST;
           mbar_wait(BAR(B_DSFULL + s), ph, a.err);
           tc_fence_after();
           const uint32_t da = smem_u32(sD + s * DS_BYTES);
-          const uint32_t ya = smem_u32(sY + s * TILE_BYTES);
+          const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < KSTEPS2; ++k) {
             // dS tile: core (vg, mg) at (vg*16 + mg)*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=2048,
@@ -271,7 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
             const uint64_t bd = make_desc(ya + k * 256, 128, 2048);
             umma_bf16(tmem + ACC_COL, ad, bd, IDESC2, (it > 0 || k > 0));
           }
-          umma_commit(BAR(B_YEMPTY + s));
+          umma_commit(BAR(B_YEMPTY + ys));
           umma_commit(BAR(B_DSEMPTY + s));
         }
       }
@@ -285,12 +304,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     RowInfo ri;
     float mx = -INFINITY, sum = 0.f, lab = 0.f, dot = 0.f;
+    RowInfo ri_next;
     if (MODE != MODE_DE) ri = row_info(a, x_tile * TILE + row, MODE != MODE_FWD);
+    else ri_next = row_info(a, y_lo * TILE + row, true);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
       int v0;
-      if (MODE == MODE_DE) { ri = row_info(a, (y_lo + it) * TILE + row, true); v0 = x_tile * TILE; }
-      else v0 = (y_lo + it) * TILE;
+      if (MODE == MODE_DE) {          // row description of the NEXT row tile is fetched one iteration ahead
+        ri = ri_next;
+        if (it + 1 < n_it) ri_next = row_info(a, (y_lo + it + 1) * TILE + row, true);
+        v0 = x_tile * TILE;
+      } else v0 = (y_lo + it) * TILE;
       mbar_wait(BAR(B_TFULL + s), ph, a.err);
       tc_fence_after();
       // this thread's 64 columns of the S tile -> registers, then hand the TMEM buffer back at once so the
@@ -331,8 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               float tv[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) tv[i] = ri.trow[vb0 + c * 32 + i];
+              load_teacher32(ri.trow + vb0 + c * 32, a.teacher_vec4 != 0, tv);
               float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -381,8 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
               }
             } else {
               float tv[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) tv[i] = ri.trow[vb + i];
+              load_teacher32(ri.trow + vb, a.teacher_vec4 != 0, tv);
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 g[i] = ri.coef * (ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2)) - ex2(fmaf(tv[i], LOG2E, -ri.lset2)));
@@ -607,7 +629,7 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
 
   static bool attr_set = false;
-  const int smem_fwd = 3 * TILE_BYTES + 256, smem_bwd = 3 * TILE_BYTES + 2 * DS_BYTES + 256;
+  const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256, smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
   if (!attr_set) {
     cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
     cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
@@ -627,6 +649,7 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.coef_train = a->n_train > 0 ? 1.0f / (float)(a->n_train_global > 0 ? a->n_train_global : a->n_train) : 0.f;
   t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)(a->n_ex_global > 0 ? a->n_ex_global : a->n_ex) : 0.f;
   t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
+  t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0)) ? 1 : 0;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
 

@@ -116,7 +116,8 @@ class Ader:
 
     def logits(self, rep: torch.Tensor, max_item: int) -> torch.Tensor:
         """fetch ``model.logits`` (ADER.py:91): [M, max_item] fp32."""
-        out = torch.empty((rep.shape[0], max_item), dtype=torch.float32, device=self.device)
+        ld = (max_item + 3) // 4 * 4      # 16-byte aligned rows (stored exemplar logits are read with 128-bit loads)
+        out = torch.empty((rep.shape[0], ld), dtype=torch.float32, device=self.device)[:, :max_item]
         ops.logits(self.ms, self.theta, rep, max_item, out)
         return out
 
@@ -148,8 +149,11 @@ class Ader:
                 if isinstance(exemplar_logits, torch.Tensor):
                     teacher = exemplar_logits
                 else:
-                    a = np.ascontiguousarray(np.asarray(exemplar_logits, dtype=np.float32))
-                    teacher = torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True)
+                    a = np.asarray(exemplar_logits, dtype=np.float32)
+                    ld = (a.shape[1] + 3) // 4 * 4
+                    buf = np.zeros((a.shape[0], ld), np.float32)
+                    buf[:, :a.shape[1]] = a
+                    teacher = torch.from_numpy(buf).pin_memory().to(self.device, non_blocking=True)[:, :a.shape[1]]
                 if teacher.dim() != 2 or teacher.stride(1) != 1 or teacher.dtype != torch.float32:
                     raise ValueError("exemplar_logits must be a 2-D fp32 row-major matrix")
                 v_prev = teacher.shape[1]

@@ -207,7 +207,8 @@ def gpu_arm(args):
     d_t_ids, d_t_lab = torch.from_numpy(t_ids).to(dev), torch.from_numpy(t_lab).to(dev)
     d_e_ids = torch.from_numpy(e_ids).to(dev)
     gen = torch.Generator(device=dev); gen.manual_seed(5 + rank)
-    teacher = torch.randn((WL["exemplars"], Vp), device=dev, generator=gen) * 2.0     # stored exemplar logits, HBM resident
+    ld_t = (Vp + 3) // 4 * 4     # rows 16-byte aligned, as ExemplarGenerator stores them
+    teacher = (torch.randn((WL["exemplars"], ld_t), device=dev, generator=gen) * 2.0)[:, :Vp]   # stored exemplar logits, HBM resident
 
     nsteps = W + K
     ti_all = [rng.randint(0, pool, B).astype(np.int32) for _ in range(nsteps)]

@@ -11,7 +11,7 @@ for (M, Bt, V, Vp, item_num) in shapes:
     m = Ader(item_num, args, init_seed=0)
     rep = torch.randn(M, 150, device="cuda")
     pos = torch.randint(1, V + 1, (Bt,), device="cuda", dtype=torch.int32)
-    teacher = torch.randn(max(M - Bt, 1), max(Vp, 1), device="cuda") if M > Bt else None
+    teacher = torch.randn(max(M - Bt, 1), (max(Vp, 1) + 3) // 4 * 4, device="cuda")[:, :max(Vp, 1)] if M > Bt else None
     a = ops.make_loss_args(M, Bt, M - Bt, V, Vp if M > Bt else 0, 1 if M > Bt else 0, 0.8, pos, None, teacher, None)
     loss = torch.zeros(1, device="cuda"); row_loss = torch.zeros(M, device="cuda"); d_rep = torch.zeros(M, 150, device="cuda")
     for impl in ("tc", "exact"):
