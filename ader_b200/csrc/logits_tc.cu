@@ -37,13 +37,14 @@ enum { MODE_FWD = 0, MODE_DREP = 1, MODE_DE = 2 };
 struct TcArgs {
   const uint8_t* rep_tiles;     // [n_mtiles][TILE_BYTES]
   const uint8_t* e_tiles;       // [n_vtiles][TILE_BYTES]
-  int M, V, n_mtiles, n_vtiles, n_chunks;
+  int M, V, V_total, n_mtiles, n_vtiles, n_chunks;   // V = columns of this shard, V_total = max_item
   // loss description
   int n_train, n_ex, V_prev, mode;
   float coef_train, coef_ex;    // 1/n_train, lambda/n_ex
   const int* pos; const int* ex_pos;
   const float* teacher; const int* teacher_row; long long teacher_ld;
   int teacher_vec4;             // teacher rows are 16-byte aligned (ld % 4 == 0): 128-bit loads
+  int v_off;                    // vocab-parallel: global column of local column 0 (multiple of 128); V is the LOCAL width
   const float* lse;             // [M]   (backward)
   const float* lse_t;           // [n_ex] teacher log-sum-exp
   float* stats;                 // FWD: [n_chunks*2][M][4] = (max, sumexp, label logit, kd dot) per column half
@@ -155,17 +156,21 @@ struct RowInfo {
   const float* trow;  // teacher row (kind 2)
 };
 __device__ __forceinline__ RowInfo row_info(const TcArgs& a, int gm, bool bwd) {
+  // all column indices inside the kernel are LOCAL to this vocabulary shard: labels, softmax widths and the
+  // teacher row pointer are shifted by v_off here (a label outside the shard simply never matches)
   RowInfo r; r.kind = 0; r.vlim = 0; r.label = -1; r.coef = 0.f; r.lse2 = 0.f; r.lset2 = 0.f; r.trow = nullptr;
   if (gm >= a.M) return r;
-  if (gm < a.n_train) { r.kind = 1; r.vlim = a.V; r.label = a.pos[gm] - 1; r.coef = a.coef_train; }
-  else if (a.mode == 2) { r.kind = 1; r.vlim = a.V; r.label = a.ex_pos[gm - a.n_train] - 1; r.coef = a.coef_ex; }
+  int vlim_g;
+  if (gm < a.n_train) { r.kind = 1; vlim_g = a.V_total; r.label = a.pos[gm] - 1 - a.v_off; r.coef = a.coef_train; }
+  else if (a.mode == 2) { r.kind = 1; vlim_g = a.V_total; r.label = a.ex_pos[gm - a.n_train] - 1 - a.v_off; r.coef = a.coef_ex; }
   else {
     const int e = gm - a.n_train;
-    r.kind = 2; r.vlim = a.V_prev; r.coef = a.coef_ex;
+    r.kind = 2; vlim_g = a.V_prev; r.coef = a.coef_ex;
     const long long tr = a.teacher_row ? a.teacher_row[e] : e;
-    r.trow = a.teacher + tr * a.teacher_ld;
+    r.trow = a.teacher + tr * a.teacher_ld + a.v_off;
     r.lset2 = a.lse_t[e] * LOG2E;
   }
+  r.vlim = max(0, min(a.V, vlim_g - a.v_off));
   if (bwd) r.lse2 = a.lse[gm] * LOG2E;
   return r;
 }
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(256) k_teacher_lse(const float* __restrict__ t
 
 // merge the per-chunk online-softmax partials: lse[M], row_loss[M]
 __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chunks, int n_train, int mode,
-                              float* __restrict__ lse, float* __restrict__ row_loss) {
+                              float* __restrict__ lse, float* __restrict__ row_loss, float* __restrict__ local_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   float mx = -INFINITY;
@@ -542,6 +547,10 @@ __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chun
     const float4 s = *reinterpret_cast<const float4*>(stats + ((size_t)c * M + i) * 4);
     if (s.x > -INFINITY) sum += s.y * expf(s.x - mx);
     lab += s.z; dot += s.w;
+  }
+  if (local_out) {      // vocab-parallel: hand the shard's (max, sumexp, label logit, kd dot) to the host-side all-reduce
+    *reinterpret_cast<float4*>(local_out + (size_t)i * 4) = make_float4(mx, sum, lab, dot);
+    return;
   }
   const float l = mx + logf(sum);
   lse[i] = l;
@@ -644,7 +653,7 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   ADER_CHECK_LAUNCH("tc pack");
 
   TcArgs t;
-  t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = V; t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
+  t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = V; t.V_total = V; t.v_off = 0; t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
   t.n_train = a->n_train; t.n_ex = a->n_ex; t.V_prev = a->V_prev; t.mode = a->n_ex > 0 ? a->mode : 0;
   t.coef_train = a->n_train > 0 ? 1.0f / (float)(a->n_train_global > 0 ? a->n_train_global : a->n_train) : 0.f;
   t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)(a->n_ex_global > 0 ? a->n_ex_global : a->n_ex) : 0.f;
@@ -654,7 +663,7 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.d = d; t.err = w.err;
 
   k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
-  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss);
+  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss, nullptr);
   if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
@@ -666,5 +675,88 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
     k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
     ADER_CHECK_LAUNCH("tc d_table");
   }
+  return 0;
+}
+
+
+// ---- vocab-parallel variant: this rank owns logits columns [v_lo, v_hi) ---------------------
+static int vp_setup(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, int v_lo, int v_hi,
+                    void* ws, cudaStream_t st, TcWs& w, TcArgs& t, bool pack) {
+  const int d = m->d, M = a->M, Vl = v_hi - v_lo;
+  w = carve_tc(m, M, Vl, a->n_ex, (char*)ws);
+  const int nm = cdiv(M, TILE), nv = cdiv(Vl, TILE), nc = tc_chunks(nm, nv);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256, smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
+    cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
+    cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+    cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+    attr_set = true;
+  }
+  if (pack) {
+    cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
+    k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
+    k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + (size_t)(1 + v_lo) * d, d, Vl, d, nv, w.e_tiles);
+    if (a->n_ex > 0 && a->mode == 1)
+      k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
+  }
+  t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = Vl; t.V_total = a->V; t.v_off = v_lo;
+  t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
+  t.n_train = a->n_train; t.n_ex = a->n_ex; t.V_prev = a->V_prev; t.mode = a->n_ex > 0 ? a->mode : 0;
+  t.coef_train = a->n_train > 0 ? 1.0f / (float)(a->n_train_global > 0 ? a->n_train_global : a->n_train) : 0.f;
+  t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)(a->n_ex_global > 0 ? a->n_ex_global : a->n_ex) : 0.f;
+  t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
+  t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0)) ? 1 : 0;
+  t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = nullptr;
+  t.d = d; t.err = w.err;
+  return 0;
+}
+
+static int vp_check(const AderModel* m, const AderLossArgs* a, int v_lo, int v_hi) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(a && a->M == a->n_train + a->n_ex && a->M > 0, "loss_tc_vp: bad row counts");
+  ADER_CHECK_ARG(a->V >= 1 && a->V < m->v_tab && a->mode >= 0 && a->mode <= 2, "loss_tc_vp: bad V / mode");
+  ADER_CHECK_ARG(v_lo >= 0 && v_lo < v_hi && v_hi <= a->V && v_lo % TILE == 0, "loss_tc_vp: shard [%d,%d) must be 128-aligned inside [0,%d)", v_lo, v_hi, a->V);
+  ADER_CHECK_ARG(m->d <= KP, "loss_tc_vp: hidden_units too large");
+  if (a->n_ex > 0 && a->mode == 1) ADER_CHECK_ARG(a->teacher && a->V_prev >= 1 && a->V_prev <= a->V, "loss_tc_vp: bad teacher");
+  return 0;
+}
+
+extern "C" size_t ader_loss_tc_vp_ws_bytes(const AderModel* m, const AderLossArgs* a, int32_t v_lo, int32_t v_hi) {
+  if (check_model(m) || !a || a->M <= 0 || v_hi <= v_lo) return 0;
+  return carve_tc(m, a->M, v_hi - v_lo, a->n_ex, nullptr).bytes;
+}
+
+extern "C" int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
+                                       int32_t v_lo, int32_t v_hi, void* ws, float* stats, void* stream) {
+  if (int e = vp_check(m, a, v_lo, v_hi)) return e;
+  ADER_CHECK_ARG(theta && rep && ws && stats, "loss_tc_vp_fwd: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TcWs w; TcArgs t;
+  vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, true);
+  const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256;
+  k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_fwd, st>>>(t);
+  k_merge_stats<<<cdiv(a->M, 128), 128, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats);
+  ADER_CHECK_LAUNCH("loss_tc_vp_fwd");
+  return 0;
+}
+
+extern "C" int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
+                                       int32_t v_lo, int32_t v_hi, void* ws, const float* lse, float* d_rep_partial,
+                                       float* grad, void* stream) {
+  if (int e = vp_check(m, a, v_lo, v_hi)) return e;
+  ADER_CHECK_ARG(theta && rep && ws && lse, "loss_tc_vp_bwd: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  TcWs w; TcArgs t;
+  vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, false);     // tiles were packed by the forward call
+  t.lse = lse;
+  t.grad_table = grad ? grad + (size_t)(1 + v_lo) * m->d : nullptr;
+  const int smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
+  if (d_rep_partial) {
+    k_tc_logits<MODE_DREP><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_bwd, st>>>(t);
+    k_reduce_drep<<<cdiv((long long)a->M * m->d, 256), 256, 0, st>>>(w.drep_part, t.n_chunks, t.n_mtiles * TILE, a->M, m->d, d_rep_partial);
+  }
+  if (grad) k_tc_logits<MODE_DE><<<t.n_vtiles, NTHREADS, smem_bwd, st>>>(t);
+  ADER_CHECK_LAUNCH("loss_tc_vp_bwd");
   return 0;
 }

@@ -121,6 +121,25 @@ def loss_fwd_bwd_tc(ms: AderModel, theta, rep, a: AderLossArgs, ws, loss, row_lo
                                            _ptr(row_loss), _ptr(d_rep), _ptr(grad), _stream()), "loss_fwd_bwd_tc")
 
 
+def loss_tc_vp_ws_bytes(ms: AderModel, a: AderLossArgs, v_lo: int, v_hi: int) -> int:
+    n = _lib.load().ader_loss_tc_vp_ws_bytes(C.byref(ms), C.byref(a), v_lo, v_hi)
+    if n == 0:
+        raise _lib.AderError("loss_tc_vp_ws_bytes: bad model / sizes")
+    return n
+
+
+def loss_tc_vp_fwd(ms: AderModel, theta, rep, a: AderLossArgs, v_lo: int, v_hi: int, ws, stats):
+    _require_cuda(theta, rep, ws, stats)
+    check(_lib.load().ader_loss_tc_vp_fwd(C.byref(ms), _ptr(theta), _ptr(rep), C.byref(a), v_lo, v_hi, _ptr(ws), _ptr(stats),
+                                          _stream()), "loss_tc_vp_fwd")
+
+
+def loss_tc_vp_bwd(ms: AderModel, theta, rep, a: AderLossArgs, v_lo: int, v_hi: int, ws, lse, d_rep_partial, grad):
+    _require_cuda(theta, rep, ws, lse, d_rep_partial, grad)
+    check(_lib.load().ader_loss_tc_vp_bwd(C.byref(ms), _ptr(theta), _ptr(rep), C.byref(a), v_lo, v_hi, _ptr(ws), _ptr(lse),
+                                          _ptr(d_rep_partial), _ptr(grad), _stream()), "loss_tc_vp_bwd")
+
+
 def logits(ms: AderModel, theta, rep, V: int, out):
     """out [M, >=V] fp32 = rep . E[1..V]^T (ADER.py:90-91)."""
     _require_cuda(theta, rep, out)

@@ -103,6 +103,17 @@ size_t  ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a);
 int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
                              const AderLossArgs* a, void* ws, float* loss, float* row_loss,
                              float* d_rep, float* grad, void* stream);
+/* Vocab-parallel form of the same kernels (one rank owns logits columns [v_lo, v_hi), v_lo % 128 == 0):
+ *   fwd  -> stats [M,4] = this shard's per-row (max, sum exp(s - max), label logit or 0, KD dot);
+ *           the caller all-reduces them (max; rescaled sum; sums) into lse [M];
+ *   bwd  -> d_rep_partial [M,d] (to be all-reduce-summed) and grad rows v_lo+1 .. v_hi of the item table.
+ * `a->V` stays the GLOBAL max_item.  The workspace must persist between the two calls. */
+size_t  ader_loss_tc_vp_ws_bytes(const AderModel* m, const AderLossArgs* a, int32_t v_lo, int32_t v_hi);
+int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
+                            int32_t v_lo, int32_t v_hi, void* ws, float* stats, void* stream);
+int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
+                            int32_t v_lo, int32_t v_hi, void* ws, const float* lse, float* d_rep_partial,
+                            float* grad, void* stream);
 /* logits [M, V] fp32 = rep . E[1..V]^T  (fetch `logits`, util.py:452,482,514). ld = row stride. */
 int32_t ader_logits(const AderModel* m, const float* theta, const float* rep, int32_t M, int32_t V,
                     float* logits, int64_t ld, void* stream);

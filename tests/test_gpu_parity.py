@@ -560,3 +560,50 @@ def test_end_to_end_tc_path_reaches_same_metrics(tmp_path):
         np.testing.assert_allclose(pb["losses"][:30], pa["losses"][:30], rtol=5e-2)   # trajectories drift (bf16)
         assert abs(pa["test"][1] - pb["test"][1]) <= 0.03
     np.testing.assert_allclose(rb["trace"]["periods"][0]["losses"][:10], ra["trace"]["periods"][0]["losses"][:10], rtol=2e-3)
+
+
+@pytest.mark.parametrize("mode,shards", [("vanilla", 2), ("kd", 3), ("er", 2)])
+def test_vocab_parallel_shards_match_single_kernel(mode, shards):
+    """Vocab-parallel kernels (column offset, per-shard stats, partial d_rep, own-row dE) emulated with
+    `shards` sequential shards on one GPU == the unsharded tcgen05 call (same bf16 products; only the fp32
+    summation order of the merge differs)."""
+    from ader_b200 import ops
+    from ader_b200.dist import VocabParallelLoss, vocab_shard
+    M, Bt, V, Vp, item_num = 300, 200, 3001, 2500, 4000
+    if mode == "vanilla":
+        M = Bt
+    m, hp, _ = _model(item_num, loss_impl="tc", disable_distillation=(mode == "er"))
+    dev = m.device
+    g = torch.Generator(device=dev).manual_seed(5)
+    rep = torch.randn(M, 150, device=dev, generator=g)
+    pos = torch.randint(1, V + 1, (Bt,), device=dev, dtype=torch.int32, generator=g)
+    pos[0], pos[1] = 1, V
+    teacher = ex_pos = None
+    md, lam = 0, 0.0
+    if mode == "kd":
+        teacher = (torch.randn(M - Bt, (Vp + 3) // 4 * 4, device=dev, generator=g) * 2)[:, :Vp]; md, lam = 1, 0.9
+    elif mode == "er":
+        ex_pos = torch.randint(1, V + 1, (M - Bt,), device=dev, dtype=torch.int32, generator=g); md, lam = 2, 0.9
+    a = ops.make_loss_args(M, Bt, M - Bt, V, Vp if md == 1 else 0, md, lam, pos, ex_pos, teacher, None)
+    ws = torch.empty(ops.loss_tc_ws_bytes(m.ms, a), dtype=torch.uint8, device=dev)
+    loss = torch.zeros(1, device=dev); row_loss = torch.zeros(M, device=dev); d_rep = torch.zeros(M, 150, device=dev)
+    grad = torch.zeros_like(m.theta)
+    ops.loss_fwd_bwd_tc(m.ms, m.theta, rep, a, ws, loss, row_loss, d_rep, grad)
+    # sharded
+    vp = [VocabParallelLoss(m, rank=r, world=shards) for r in range(shards)]
+    parts = []
+    for r in range(shards):
+        lo, hi = vocab_shard(V, r, shards)
+        parts.append((lo, hi) + vp[r].local_forward(rep, a, lo, hi))
+    lse, rl, ls = VocabParallelLoss.merge([p[3] for p in parts], Bt, M - Bt, lam, md == 1)
+    assert float(ls) == pytest.approx(float(loss), rel=1e-5)
+    _close(rl.cpu(), row_loss.cpu(), 1e-5, 1e-5, "row_loss")
+    grad2 = torch.zeros_like(m.theta)
+    d_sum = torch.zeros_like(d_rep)
+    for lo, hi, wsr, _ in parts:
+        d_part = torch.empty_like(d_rep)
+        ops.loss_tc_vp_bwd(m.ms, m.theta, rep, a, lo, hi, wsr, lse, d_part, grad2)
+        d_sum += d_part
+    _close(d_sum.cpu(), d_rep.cpu(), 1e-4, 1e-7, "d_rep")
+    _close(grad2[150:(V + 1) * 150].cpu(), grad[150:(V + 1) * 150].cpu(), 1e-4, 1e-8, "table grad")
+    assert float(grad2[(V + 1) * 150:].abs().max()) == 0.0
