@@ -83,6 +83,9 @@ struct GemmArgs {
 };
 void gemm_defaults(GemmArgs& g);
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
+constexpr int GEMM_GROUP_MAX = 5;
+struct GemmGroup { GemmArgs g[GEMM_GROUP_MAX]; int n, av, bv; };
+int launch_gemm_group(const GemmArgs* gs, int n, cudaStream_t st);
 
 // ---- counter-based dropout mask (shared by fwd and bwd) -----------------------------------
 __host__ __device__ inline uint32_t mix32(uint64_t x) {

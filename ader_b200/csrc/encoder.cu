@@ -20,6 +20,7 @@ struct EncWs {
   float* slot[8][NSLOT];           // [block][slot]
   float *mean1[8], *rstd1[8], *mean2[8], *rstd2[8], *probs[8];
   float* xfinal; float *meanf, *rstdf;
+  void* wshadow;                   // fused path: bf16 weight shadows, NB x 10 x [160][168]
   size_t bytes;
 };
 
@@ -40,6 +41,7 @@ static EncWs carve_enc(const AderModel* m, int M, int Tcap, char* base) {
   }
   w.xfinal = (float*)take(sizeof(float) * Tcap * d);
   w.meanf = (float*)take(sizeof(float) * M); w.rstdf = (float*)take(sizeof(float) * M);
+  w.wshadow = take((size_t)m->num_blocks * 10 * 160 * 168 * 2);
   w.bytes = o;
   return w;
 }
@@ -48,6 +50,7 @@ struct BwdWs {
   float* g[11];          // gX, gXin, gO, gH, gZ, gY, gQ, gK, gV, gQ1, spare
   float* partial;        // [SPLITS][dense_count]
   int *keys[2], *vals[2], *hist;
+  float* Dv;             // fused path: per-token softmax-backward row dots
   size_t bytes;
 };
 static int sort_tiles(int Tcap) { return cdiv(Tcap, 2048); }
@@ -59,6 +62,7 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
   w.partial = (float*)take(sizeof(float) * (size_t)SPLITS * l.dense_count());
   for (int i = 0; i < 2; ++i) { w.keys[i] = (int*)take(sizeof(int) * Tcap); w.vals[i] = (int*)take(sizeof(int) * Tcap); }
   w.hist = (int*)take(sizeof(int) * 256 * (size_t)sort_tiles(Tcap));
+  w.Dv = (float*)take(sizeof(float) * Tcap);
   w.bytes = o;
   return w;
 }
@@ -748,6 +752,10 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys
 
 static int key_bits(int v_tab) { int b = 1; while ((1LL << b) < v_tab) ++b; return b; }
 
+}  // namespace ader
+#include "encoder_fused.cuh"
+namespace ader {
+
 // ------------------------------------------------------------------------------------------
 // group entry points
 // ------------------------------------------------------------------------------------------
@@ -767,15 +775,51 @@ static int run_dense(cudaStream_t st, const float* A, const float* W, const floa
 }
 
 // dW partial[s] = act^T . grad over token split s, db partial[s] = colsum(grad)
-static int run_wgrad(cudaStream_t st, const float* act, const float* grad, float* pW, float* pb,
-                     long long split_stride, int Tcap, const int* dT, int d) {
+static GemmArgs wgrad_args(const float* act, const float* grad, float* pW, float* pb,
+                           long long split_stride, int Tcap, const int* dT, int d) {
   GemmArgs g; gemm_defaults(g);
   g.A = act; g.a_rs = 1; g.a_cs = d;       // A(m=c_in, k=t) = act[t*d + c_in]
   g.B = grad; g.b_rs = d; g.b_cs = 1;      // B(k=t, n=c_out)
   g.C = pW; g.c_rs = d; g.c_cs = 1;
   g.M = d; g.N = d; g.K = Tcap; g.dK = dT;
   g.splits = SPLITS; g.split_stride = split_stride; g.colsum = pb;
-  return launch_gemm(g, st);
+  return g;
+}
+static int run_wgrad(cudaStream_t st, const float* act, const float* grad, float* pW, float* pb,
+                     long long split_stride, int Tcap, const int* dT, int d) {
+  return launch_gemm(wgrad_args(act, grad, pW, pb, split_stride, Tcap, dT, d), st);
+}
+
+// Tail shared by both encoder paths: split-K partials -> dense gradients, position table, item-table scatter.
+static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
+                               int M, int Tcap, float p, uint64_t seed, float* grad, cudaStream_t st) {
+  const int d = m->d, L = m->maxlen;
+  const int* dT = w.row_off + M;
+  const long long PS = l.dense_count();
+  const int ln_threads = ((d + 31) / 32) * 32;
+  // dense parameter gradients: reduce the split partials in fixed order
+  {
+    const long long lo = (long long)L * d, hi = PS;
+    k_reduce_partials<<<cdiv(hi - lo, 256), 256, 0, st>>>(g.partial, PS, SPLITS, lo, hi, grad + l.off_pos);
+  }
+  // position table (ADER.py:41-52) and item-table scatter (modules.py:127-130)
+  k_pos_grad<<<L, dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
+  {
+    const int ntiles = sort_tiles(Tcap);
+    const int bits = key_bits(m->v_tab);
+    int cur = 0;
+    const int* kin = w.tok_id; const int* vin = nullptr;
+    int pass = 0;
+    for (int shift = 0; shift < bits; shift += 8, ++pass) {
+      k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
+      k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
+      k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
+      kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
+    }
+    k_seg_reduce<<<cdiv((long long)cdiv(Tcap, 4) * 32, 256), 256, 0, st>>>(kin, vin, dT, gX, d, sqrtf((float)d), p, seed,
+                                                                           grad + l.off_table);
+  }
+  return 0;
 }
 
 }  // namespace ader
@@ -936,29 +980,197 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     float* t = gX; gX = gXin; gXin = t;
   }
 
-  // dense parameter gradients: reduce the split partials in fixed order
-  {
-    const long long lo = (long long)L * d, hi = PS;
-    k_reduce_partials<<<cdiv(hi - lo, 256), 256, 0, st>>>(g.partial, PS, SPLITS, lo, hi, grad + l.off_pos);
-  }
-  // position table (ADER.py:41-52) and item-table scatter (modules.py:127-130)
-  k_pos_grad<<<L, dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
-  {
-    const int ntiles = sort_tiles(Tcap);
-    const int bits = key_bits(m->v_tab);
-    int cur = 0;
-    const int* kin = w.tok_id; const int* vin = nullptr;
-    int pass = 0;
-    for (int shift = 0; shift < bits; shift += 8, ++pass) {
-      k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
-      k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
-      k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
-      kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
-    }
-    k_seg_reduce<<<cdiv((long long)cdiv(Tcap, 4) * 32, 256), 256, 0, st>>>(kin, vin, dT, gX, d, sqrtf((float)d), p, seed,
-                                                                           grad + l.off_table);
-  }
+  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, p, seed, grad, st)) return e;
   ADER_CHECK_LAUNCH("encoder_bwd/embedding");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused tensor-core path (encoder_fused.cuh): same contract, same workspace slots
+// ------------------------------------------------------------------------------------------
+namespace ader {
+// LayerNorm parameter gradients of BOTH LayerNorms of a block in one launch (blockIdx.y = which).
+struct LnPgSet { const float *dout, *x, *mean, *rstd; float *pbeta, *pgamma; };
+__global__ void k_ln_param_grad2(LnPgSet s0, LnPgSet s1, const int* __restrict__ dT, int d, long long split_stride) {
+  __shared__ float sb_s[PG_LANES][256], sg_s[PG_LANES][256];
+  const LnPgSet s = blockIdx.y ? s1 : s0;
+  const int c = threadIdx.x, k = threadIdx.y;
+  const int count = *dT;
+  const int chunk = (count + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * chunk, hi = min(count, lo + chunk);
+  float sb = 0.f, sg = 0.f;
+  if (c < d) {
+    for (int i = lo + k; i < hi; i += PG_LANES) {
+      const float g = s.dout[(long long)i * d + c];
+      sb += g; sg += g * ((s.x[(long long)i * d + c] - s.mean[i]) * s.rstd[i]);
+    }
+  }
+  sb_s[k][c] = sb; sg_s[k][c] = sg;
+  __syncthreads();
+  if (k == 0 && c < d) {
+    float tb = 0.f, tg = 0.f;
+#pragma unroll
+    for (int q = 0; q < PG_LANES; ++q) { tb += sb_s[q][c]; tg += sg_s[q][c]; }
+    s.pbeta[(long long)blockIdx.x * split_stride + c] = tb;
+    s.pgamma[(long long)blockIdx.x * split_stride + c] = tg;
+  }
+}
+
+static int fused_check(const AderModel* m) {
+  if (m->d > fz::KP) return fail(-1, "fused encoder path needs hidden_units <= %d (got %d): use the exact path", fz::KP, m->d);
+  if (m->maxlen > 64) return fail(-1, "fused encoder path needs maxlen <= 64");
+  return 0;
+}
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+static void fused_attrs() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(fz::k_qkv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::QKV_FWD_SMEM);
+  cudaFuncSetAttribute(fz::k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_FWD_SMEM);
+  cudaFuncSetAttribute(fz::k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_BWD_SMEM);
+  cudaFuncSetAttribute(fz::k_qkv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::QKV_BWD_SMEM);
+  done = true;
+}
+static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
+  return (const fz::op_t*)w.wshadow + (size_t)((b * 5 + which) * 2 + orient) * (fz::KP * fz::LDS);
+}
+}  // namespace ader
+
+extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                                       int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
+                                       void* stream) {
+  if (int e = check_model(m)) return e;
+  if (int e = fused_check(m)) return e;
+  ADER_CHECK_ARG(theta && ids && ws && rep, "encoder_fwd_tc: NULL pointer");
+  ADER_CHECK_ARG(M > 0 && Tcap > 0 && (long long)Tcap <= (long long)M * m->maxlen, "encoder_fwd_tc: bad M/Tcap (%d, %d)", M, Tcap);
+  ADER_CHECK_ARG(dropout_rate >= 0.f && dropout_rate < 1.f, "encoder_fwd_tc: dropout_rate out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(m);
+  const int d = m->d, L = m->maxlen;
+  EncWs w = carve_enc(m, M, Tcap, (char*)ws);
+  const int* dT = w.row_off + M;
+  fused_attrs();
+
+  cudaMemsetAsync(w.flags, 0, sizeof(int) * 4, st);
+  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
+  k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
+  k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
+  fz::k_pack_weights<<<m->num_blocks * fz::W_PER_BLOCK, 256, 0, st>>>(theta, l, (fz::op_t*)w.wshadow);
+  ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
+
+  const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
+  const int warp_grid = cdiv((long long)Tcap * 32, 256);
+  for (int b = 0; b < m->num_blocks; ++b) {
+    const float* P = theta + l.block(b);
+    float* X = w.slot[b][0]; float* Q1 = w.slot[b][1]; float* Qp = w.slot[b][2]; float* Kp = w.slot[b][3];
+    float* Vp = w.slot[b][4]; float* Y = w.slot[b][5]; float* Z = w.slot[b][6]; float* H = w.slot[b][7];
+    float* Xn = (b + 1 < m->num_blocks) ? w.slot[b + 1][0] : w.xfinal;
+    fz::QkvFwdArgs qa;
+    qa.X = X; qa.Xw = X; qa.embed = (b == 0);
+    qa.table = theta + l.off_table; qa.pos_table = theta + l.off_pos;
+    qa.tok_row = w.tok_row; qa.tok_id = w.tok_id; qa.row_len = w.row_len; qa.row_off = w.row_off;
+    qa.sqrt_d = sqrtf((float)d); qa.drop_p = dropout_rate; qa.seed = seed;
+    qa.ln_b = P + l.ln1b; qa.ln_g = P + l.ln1g; qa.Q1 = Q1; qa.mean = w.mean1[b]; qa.rstd = w.rstd1[b];
+    qa.Wq = shadow_of(w, b, 0, 0); qa.Wk = shadow_of(w, b, 1, 0); qa.Wv = shadow_of(w, b, 2, 0);
+    qa.bq = P + l.bq; qa.bk = P + l.bk; qa.bv = P + l.bv;
+    qa.Q = Qp; qa.K = Kp; qa.V = Vp; qa.dT = dT; qa.d = d; qa.L = L;
+    fz::k_qkv_fwd<<<tile_grid, fz::NTHR, fz::QKV_FWD_SMEM, st>>>(qa);
+
+    fz::AttnFwdArgs aa;
+    aa.Q = Qp; aa.K = Kp; aa.V = Vp; aa.Q1 = Q1; aa.tok_row = w.tok_row; aa.row_off = w.row_off;
+    aa.probs = w.probs[b]; aa.Y = Y; aa.Z = Z; aa.mean2 = w.mean2[b]; aa.rstd2 = w.rstd2[b];
+    aa.ln_b = P + l.ln2b; aa.ln_g = P + l.ln2g; aa.dT = dT; aa.d = d; aa.nh = m->num_heads; aa.L = L; aa.Tcap = Tcap;
+    aa.drop_p = dropout_rate; aa.seed = seed; aa.site = 1u + 3u * b;
+    fz::k_attn_ln_fwd<<<warp_grid, 256, 0, st>>>(aa);
+
+    fz::FfnFwdArgs fa;
+    fa.Z = Z; fa.H = H; fa.Xn = Xn; fa.W1 = shadow_of(w, b, 3, 0); fa.W2 = shadow_of(w, b, 4, 0);
+    fa.b1 = P + l.b1; fa.b2 = P + l.b2; fa.dT = dT; fa.d = d;
+    fa.drop_p = dropout_rate; fa.seed = seed; fa.site1 = 2u + 3u * b; fa.site2 = 3u + 3u * b;
+    fz::k_ffn_fwd<<<tile_grid, fz::NTHR, fz::FFN_FWD_SMEM, st>>>(fa);
+    ADER_CHECK_LAUNCH("encoder_fwd_tc/block");
+  }
+  k_ln_last_fwd<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.xfinal, w.row_len, w.row_off, M, rep, w.meanf, w.rstdf,
+                                                               theta + l.off_lnf, theta + l.off_lnf + d, d);
+  ADER_CHECK_LAUNCH("encoder_fwd_tc/final_ln");
+  return 0;
+}
+
+extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                                       int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
+                                       float dropout_rate, uint64_t seed, void* stream) {
+  if (int e = check_model(m)) return e;
+  if (int e = fused_check(m)) return e;
+  ADER_CHECK_ARG(theta && ids && ws && bwd_ws && d_rep && grad, "encoder_bwd_tc: NULL pointer");
+  ADER_CHECK_ARG(M > 0 && Tcap > 0, "encoder_bwd_tc: bad M/Tcap");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(m);
+  const int d = m->d, L = m->maxlen;
+  const float p = dropout_rate;
+  EncWs w = carve_enc(m, M, Tcap, (char*)ws);
+  BwdWs g = carve_bwd(m, M, Tcap, (char*)bwd_ws);
+  const int* dT = w.row_off + M;
+  const long long PS = l.dense_count();
+  auto part = [&](long long param_off) { return g.partial + (param_off - l.off_pos); };
+  float *gX = g.g[0], *gXin = g.g[1], *gO = g.g[2], *gH = g.g[3], *gZ = g.g[4], *gY = g.g[5],
+        *gQ = g.g[6], *gK = g.g[7], *gV = g.g[8], *gQ1 = g.g[9];
+  const int ln_grid = cdiv((long long)Tcap * 32, 256);
+  const int ln_threads = ((d + 31) / 32) * 32;
+  const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
+  fused_attrs();
+
+  k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, gX, dT, d);
+  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+                                                 part(l.off_lnf), part(l.off_lnf + d), PS);
+  ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
+
+  for (int b = m->num_blocks - 1; b >= 0; --b) {
+    const long long bo = l.block(b);
+    const float* P = theta + bo;
+    const float* X = w.slot[b][0]; const float* Q1 = w.slot[b][1]; const float* Qp = w.slot[b][2];
+    const float* Kp = w.slot[b][3]; const float* Vp = w.slot[b][4]; const float* Y = w.slot[b][5];
+    const float* Z = w.slot[b][6]; const float* H = w.slot[b][7];
+    fz::FfnBwdArgs fa;
+    fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
+    fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
+    fa.gH = gH; fa.gZ = gZ; fa.gY = gY; fa.D = g.Dv; fa.dT = dT; fa.d = d;
+    fa.drop_p = p; fa.seed = seed; fa.site2 = 3u + 3u * b;
+    fz::k_ffn_bwd<<<tile_grid, fz::NTHR, fz::FFN_BWD_SMEM, st>>>(fa);
+
+    fz::AttnBwdArgs ab;
+    ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
+    ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
+    ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.site = 1u + 3u * b;
+    fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
+
+    fz::QkvBwdArgs qb;
+    qb.gQ = gQ; qb.gK = gK; qb.gV = gV; qb.gY = gY; qb.X = X; qb.mean1 = w.mean1[b]; qb.rstd1 = w.rstd1[b];
+    qb.ln_g = P + l.ln1g; qb.Wqb = shadow_of(w, b, 0, 1); qb.Wkb = shadow_of(w, b, 1, 1); qb.Wvb = shadow_of(w, b, 2, 1);
+    qb.gQ1 = gQ1; qb.gXin = gXin; qb.dT = dT; qb.d = d;
+    fz::k_qkv_bwd<<<tile_grid, fz::NTHR, fz::QKV_BWD_SMEM, st>>>(qb);
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
+
+    // weight + bias gradients of the block's five dense layers: one grouped split-K launch (fp32)
+    const float* gOut = (p > 0.f) ? gO : gX;
+    GemmArgs wg[5] = {
+        wgrad_args(H, gOut, part(bo + l.w2), part(bo + l.b2), PS, Tcap, dT, d),
+        wgrad_args(Z, gH, part(bo + l.w1), part(bo + l.b1), PS, Tcap, dT, d),
+        wgrad_args(Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d),
+        wgrad_args(X, gK, part(bo + l.wk), part(bo + l.bk), PS, Tcap, dT, d),
+        wgrad_args(X, gV, part(bo + l.wv), part(bo + l.bv), PS, Tcap, dT, d)};
+    if (int e = launch_gemm_group(wg, 5, st)) return e;
+    LnPgSet s2 = {gZ, Y, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
+    LnPgSet s1 = {gQ1, X, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
+    k_ln_param_grad2<<<dim3(SPLITS, 2), dim3(ln_threads, PG_LANES), 0, st>>>(s2, s1, dT, d, PS);
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
+    float* t = gX; gX = gXin; gXin = t;
+  }
+  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, p, seed, grad, st)) return e;
+  ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");
   return 0;
 }
 

@@ -1,0 +1,793 @@
+// Fused tensor-core encoder (subsystem 1 of the north star): the SASRec blocks of modules.py:23-271 /
+// ADER.py:25-85 over PACKED real tokens with 16-bit tensor-core operands and fp32 accumulation,
+// forward and backward.  Operand type: IEEE fp16 with a per-row power-of-two scale (exactly undone in
+// the epilogue) -- the same tensor-core rate and bytes as bf16 but 11 significand bits instead of 8, which
+// matters here because parity with the fp32 reference is the first gate (measured: gradient error vs the fp32
+// oracle 3-5 % rel-L2 with bf16 operands, see profiles/; the row scale removes fp16's range problem for
+// gradients).  Included by encoder.cu (same translation unit: it shares the packing, LayerNorm,
+// radix-sort and segmented-reduction kernels of the exact path).
+//
+// Why these shapes.  At the reference's batch sizes a step holds T ~ 2-6 k real tokens (8-10 % of
+// the dense [M,50] grid), so every dense layer is a [T,150] x [150,150] product: ~0.2 GFLOP, far
+// below what one launch costs.  The step is bound by launch count and by the dependent chain of small
+// kernels, not by the math pipe, so the design is
+//   * token tiles of 32 rows (T/32 ~ 110 CTAs spread over the 148 SMs; a 128-row tcgen05 tile
+//     would leave 80 % of the SMs idle at these T) on warp-level mma.sync.m16n8k16 (fp16 operands, fp32 accumulate),
+//   * the weight matrices as 16-bit shadows [n][k] (row stride 168 -> conflict-free 32-bit fragment
+//     loads), one 53 760-byte contiguous block each, staged into shared memory by cp.async.bulk + mbarrier
+//     (TMA bulk path) once per CTA, overlapped with the LayerNorm prologue,
+//   * whole sub-layers fused in one kernel: [embed] + LN1 + Q/K/V projections; attention + residual +
+//     LN2 (warp per query, straight from L1/L2: rows are 1-50 tokens); FFN1 + ReLU + FFN2 + residual;
+//     and in backward FFN dgrad + LN2 backward; attention backward (warp per token, flash-style
+//     D = gY.(Y - q) so no dS matrix is stored); Q/K/V dgrad + LN1 backward.
+//   * weight / bias / LN-parameter gradients stay fp32 (grouped split-K SIMT GEMM over the 5 matrices of a
+//     block in ONE launch, fixed reduction order -> deterministic).
+// Saved activations stay fp32 in HBM in the same workspace slots as the exact path, so the two paths can
+// be compared slot by slot (tests/test_gpu_parity.py).
+#pragma once
+#include <cuda_fp16.h>
+
+namespace ader {
+namespace fz {
+
+using op_t = __half;                    // 16-bit operand type of the tiles and weight shadows
+constexpr int KP = 160;                 // feature dim padded to a multiple of 16 (d <= 160 on this path)
+constexpr int LDS = 168;                // row stride (op_t elements) of shared-memory operand tiles and weight shadows
+constexpr int TM = 32;                  // token rows per tile
+constexpr int NTHR = 256;               // 8 warps: (m-tile = warp & 1) x (column group = warp >> 1)
+constexpr int NT = 5;                   // n8 tiles per warp (4 column groups x 5 x 8 = 160 columns)
+constexpr int WMAT_BYTES = KP * LDS * 2;        // 53 760
+constexpr int ATILE_BYTES = TM * LDS * 2;       // 10 752
+constexpr int FT_LD = 168;              // row stride (floats) of fp32 staging tiles (168 % 32 == 8: conflict-free float2 stores)
+constexpr int FTILE_BYTES = TM * FT_LD * 4;     // 21 504
+constexpr int NE = 5;                   // features per lane in the warp-per-token kernels (32 x 5 = 160)
+constexpr int W_PER_BLOCK = 10;         // 5 matrices x {forward [out][in], backward [in][out]} shadows
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && spin > (1u << 26)) __trap();   // a broken copy must not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one weight shadow as 8 bulk copies (several requests in flight), all completing on `bar`
+__device__ __forceinline__ void load_wmat(uint32_t dst, const op_t* src, uint32_t bar) {
+  constexpr int CH = WMAT_BYTES / 8;    // 6720, multiple of 16
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bulk_g2s(dst + i * CH, (const char*)src + i * CH, CH, bar);
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[j] (+)= A[16 x 160] . W[n0 + 8j .. +8][160]^T for the warp's m-tile / column group.
+//   A: first row of the m-tile in a [TM][LDS] op_t tile;  W: row n0 of a [KP][LDS] shadow ([n][k]).
+__device__ __forceinline__ void warp_gemm(const op_t* __restrict__ A, const op_t* __restrict__ W, float (&acc)[NT][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t* a_lo = reinterpret_cast<const uint32_t*>(A + g * LDS) + t;
+  const uint32_t* a_hi = reinterpret_cast<const uint32_t*>(A + (g + 8) * LDS) + t;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(W + g * LDS) + t;
+#pragma unroll
+  for (int ks = 0; ks < KP / 16; ++ks) {
+    const uint32_t a0 = a_lo[ks * 8], a1 = a_hi[ks * 8], a2 = a_lo[ks * 8 + 4], a3 = a_hi[ks * 8 + 4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t b0 = w[j * 8 * (LDS / 2) + ks * 8], b1 = w[j * 8 * (LDS / 2) + ks * 8 + 4];
+      mma_16816(acc[j], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+__device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+}
+// visit the warp's accumulator elements as (tile row, column pair): f(row, col, v0, v1), col even.
+template <typename F>
+__device__ __forceinline__ void for_acc(const float (&acc)[NT][4], int mt, int ng, int lane, F f) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int col = ng * (NT * 8) + j * 8 + 2 * t;
+    f(mt * 16 + g, col, acc[j][0], acc[j][1]);
+    f(mt * 16 + g + 8, col, acc[j][2], acc[j][3]);
+  }
+}
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ void st_op2(op_t* p, float a, float b) {
+  *reinterpret_cast<__half2*>(p) = __floats2half2_rn(clamp_h(a), clamp_h(b));
+}
+__device__ __forceinline__ op_t to_op(float v) { return __float2half_rn(clamp_h(v)); }
+// power-of-two scale s with max * s in [2^10, 2^11): 16x headroom for the chained product, exact to undo
+__device__ __forceinline__ float row_scale(float mx) {
+  if (!(mx > 0.f)) return 1.f;
+  int e; frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, min(max(11 - e, -100), 100));
+}
+// Warp-per-row staging of rows t0 + warp*4 .. +3 of a [T,d] fp32 matrix into a 16-bit operand tile with a
+// per-row power-of-two scale; inv_scale[r] receives 1/s_r.  Optional dropout site applied (and the dropped
+// values written back) first.  Optional second matrix G2 -> As2 shares the row scale (joint maximum).
+__device__ __forceinline__ void stage_rows_scaled(op_t* __restrict__ As, float* __restrict__ inv_scale,
+                                                  const float* __restrict__ G, int t0, int T, int d, int warp, int lane,
+                                                  float drop_p = 0.f, uint64_t seed = 0, uint32_t site = 0,
+                                                  float* __restrict__ dropped_out = nullptr,
+                                                  const float* __restrict__ G2 = nullptr, op_t* __restrict__ As2 = nullptr) {
+#pragma unroll
+  for (int rr = 0; rr < TM / 8; ++rr) {
+    const int r = warp * (TM / 8) + rr, tk = t0 + r;
+    float v[NE], v2[NE]; float mx = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      v[e] = 0.f; v2[e] = 0.f;
+      if (tk < T && c < d) {
+        const long long el = (long long)tk * d + c;
+        v[e] = G[el];
+        if (drop_p > 0.f) { v[e] *= drop_scale(seed, site, (uint64_t)el, drop_p); if (dropped_out) dropped_out[el] = v[e]; }
+        if (G2) v2[e] = G2[el];
+      }
+      mx = fmaxf(mx, fmaxf(fabsf(v[e]), fabsf(v2[e])));
+    }
+    const float sc = row_scale(warp_max(mx));
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      As[r * LDS + c] = to_op(v[e] * sc);
+      if (As2) As2[r * LDS + c] = to_op(v2[e] * sc);
+    }
+    if (lane == 0) inv_scale[r] = 1.f / sc;
+  }
+}
+// stage rows t0.. of a [T,d] fp32 matrix (optionally scaled by a dropout site) into a op_t tile, zero padded
+__device__ __forceinline__ void stage_tile16(op_t* __restrict__ As, const float* __restrict__ G, int t0, int T, int d,
+                                           float drop_p = 0.f, uint64_t seed = 0, uint32_t site = 0,
+                                           float* __restrict__ dropped_out = nullptr) {
+  for (int idx = threadIdx.x; idx < TM * (KP / 2); idx += NTHR) {
+    const int r = idx / (KP / 2), c = (idx % (KP / 2)) * 2;
+    const int tk = t0 + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (tk < T && c < d) {
+      const long long e = (long long)tk * d + c;
+      v = *reinterpret_cast<const float2*>(G + e);
+      if (drop_p > 0.f) {
+        v.x *= drop_scale(seed, site, (uint64_t)e, drop_p);
+        v.y *= drop_scale(seed, site, (uint64_t)e + 1, drop_p);
+        if (dropped_out) *reinterpret_cast<float2*>(dropped_out + e) = v;
+      }
+    }
+    st_op2(As + r * LDS + c, v.x, v.y);
+  }
+}
+
+// ---- weight shadows ------------------------------------------------------------------------------
+// shadow[(b*5 + w)*2 + 0][n][k] = W_w[k][n]   (forward:  out = in . W,   B(k = in,  n = out))
+// shadow[(b*5 + w)*2 + 1][n][k] = W_w[n][k]   (backward: gin = gout . W^T, B(k = out, n = in))
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ theta, Layout l, op_t* __restrict__ shadow) {
+  const int which = blockIdx.x;                 // (b*5 + w)*2 + orient
+  const int orient = which & 1, w = (which >> 1) % 5, b = (which >> 1) / 5;
+  const long long rel[5] = {l.wq, l.wk, l.wv, l.w1, l.w2};
+  const float* W = theta + l.block(b) + rel[w];
+  op_t* out = shadow + (size_t)which * (KP * LDS);
+  const int d = l.d;
+  for (int idx = threadIdx.x; idx < KP * (LDS / 2); idx += blockDim.x) {
+    const int n = idx / (LDS / 2), k = (idx % (LDS / 2)) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (n < d) {
+      if (orient == 0) { if (k < d) v0 = W[(long long)k * d + n]; if (k + 1 < d) v1 = W[(long long)(k + 1) * d + n]; }
+      else             { if (k < d) v0 = W[(long long)n * d + k]; if (k + 1 < d) v1 = W[(long long)n * d + k + 1]; }
+    }
+    st_op2(out + n * LDS + k, v0, v1);
+  }
+}
+
+// ---- forward: [embed] + LN1 + Q/K/V ---------------------------------------------------------------
+struct QkvFwdArgs {
+  const float* X;            // [T,d] block input (ignored when embed != 0: computed here and written to Xw)
+  float* Xw;
+  int embed;
+  const float *table, *pos_table; const int *tok_row, *tok_id, *row_len, *row_off;
+  float sqrt_d, drop_p; uint64_t seed;
+  const float *ln_b, *ln_g; float *Q1, *mean, *rstd;
+  const op_t *Wq, *Wk, *Wv; const float *bq, *bk, *bv;
+  float *Q, *K, *V;
+  const int* dT; int d, L;
+};
+constexpr size_t QKV_FWD_SMEM = 3 * WMAT_BYTES + 2 * ATILE_BYTES + TM * 4 + 16;
+
+__global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ QkvFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  op_t* Wsm = reinterpret_cast<op_t*>(smem);
+  op_t* A1 = reinterpret_cast<op_t*>(smem + 3 * WMAT_BYTES);      // LN1(x)
+  op_t* A2 = A1 + TM * LDS;                                      // x (row-scaled: the residual stream is unbounded)
+  float* rs = reinterpret_cast<float*>(smem + 3 * WMAT_BYTES + 2 * ATILE_BYTES);
+  const uint32_t bar = smem_u32(smem + 3 * WMAT_BYTES + 2 * ATILE_BYTES + TM * 4);
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, 3 * WMAT_BYTES);
+    load_wmat(smem_u32(Wsm), a.Wq, bar);
+    load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.Wk, bar);
+    load_wmat(smem_u32(Wsm) + 2 * WMAT_BYTES, a.Wv, bar);
+  }
+  __syncthreads();
+  const int mt = warp & 1, ng = warp >> 1;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * TM;
+    // prologue: warp w owns tile rows w*4 .. w*4+3
+#pragma unroll
+    for (int rr = 0; rr < TM / 8; ++rr) {
+      const int r = warp * (TM / 8) + rr, tk = t0 + r;
+      float x[NE];
+      if (tk < T) {
+        if (a.embed) {     // x = (E0[id]*sqrt(d) + P[pos]) * dropout   (modules.py:124-130, ADER.py:41-60)
+          const int row = a.tok_row[tk];
+          const int p = a.L - a.row_len[row] + (tk - a.row_off[row]);
+          const long long id = a.tok_id[tk];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int c = lane + 32 * e;
+            float v = 0.f;
+            if (c < d) {
+              v = a.table[id * d + c] * a.sqrt_d + a.pos_table[p * d + c];
+              if (a.drop_p > 0.f) v *= drop_scale(a.seed, 0u, (uint64_t)tk * d + c, a.drop_p);
+              a.Xw[(long long)tk * d + c] = v;
+            }
+            x[e] = v;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; x[e] = (c < d) ? a.X[(long long)tk * d + c] : 0.f; }
+        }
+        float s = 0.f, mx = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { s += x[e]; mx = fmaxf(mx, fabsf(x[e])); }
+        const float sc = row_scale(warp_max(mx));
+        const float mean = warp_sum(s) / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = x[e] - mean; q += u * u; } }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-8f);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int c = lane + 32 * e;
+          float y = 0.f;
+          if (c < d) { y = a.ln_g[c] * ((x[e] - mean) * rstd) + a.ln_b[c]; a.Q1[(long long)tk * d + c] = y; }
+          A1[r * LDS + c] = to_op(y);
+          A2[r * LDS + c] = to_op(x[e] * sc);
+        }
+        if (lane == 0) { a.mean[tk] = mean; a.rstd[tk] = rstd; rs[r] = 1.f / sc; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; A1[r * LDS + c] = to_op(0.f); A2[r * LDS + c] = to_op(0.f); }
+        if (lane == 0) rs[r] = 1.f;
+      }
+    }
+    __syncthreads();
+    if (first) { mbar_wait(bar, 0); first = false; }
+    float acc[NT][4];
+    zero_acc(acc);
+    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (t0 + r < T && c < d)
+        *reinterpret_cast<float2*>(a.Q + (long long)(t0 + r) * d + c) = make_float2(v0 + a.bq[c], v1 + a.bq[c + 1]);
+    });
+    zero_acc(acc);
+    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (t0 + r < T && c < d)
+        *reinterpret_cast<float2*>(a.K + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + a.bk[c], v1 * rs[r] + a.bk[c + 1]);
+    });
+    zero_acc(acc);
+    warp_gemm(A2 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (t0 + r < T && c < d)
+        *reinterpret_cast<float2*>(a.V + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + a.bv[c], v1 * rs[r] + a.bv[c + 1]);
+    });
+    __syncthreads();
+  }
+}
+
+// ---- forward: causal attention + residual + LN2, warp per query token (modules.py:177-223, 40-48) ---
+struct AttnFwdArgs {
+  const float *Q, *K, *V, *Q1;
+  const int *tok_row, *row_off;
+  float *probs, *Y, *Z, *mean2, *rstd2;
+  const float *ln_b, *ln_g;
+  const int* dT; int d, nh, L, Tcap;
+  float drop_p; uint64_t seed; uint32_t site;
+};
+
+__global__ void __launch_bounds__(256) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
+  const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tk >= *a.dT) return;
+  const int d = a.d, L = a.L;
+  const int row = a.tok_row[tk];
+  const int off = a.row_off[row];
+  const int i = tk - off;                       // query index inside its session; keys 0..i
+  const int dh = d / a.nh;
+  const float inv_denom = 1.0f / sqrtf((float)dh);
+  float q[NE], o[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; q[e] = (c < d) ? a.Q[(long long)tk * d + c] : 0.f; o[e] = 0.f; }
+  for (int h = 0; h < a.nh; ++h) {
+    const int c_lo = h * dh, c_hi = c_lo + dh;
+    float s0 = -INFINITY, s1 = -INFINITY;       // score of key `lane` / key `lane + 32`
+    for (int j0 = 0; j0 <= i; j0 += 4) {
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, i);
+        const float* kr = a.K + (long long)(off + j) * d;
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(q[e], kr[c], p); }
+        part[u] = p;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s = warp_sum(part[u]) * inv_denom;
+        const int j = j0 + u;
+        if (j <= i) { if (lane == (j & 31)) { if (j < 32) s0 = s; else s1 = s; } }
+      }
+    }
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float e0 = (lane <= i) ? expf(s0 - mx) : 0.f;
+    const float e1 = (lane + 32 <= i) ? expf(s1 - mx) : 0.f;
+    const float sum = warp_sum(e0 + e1);
+    float p0 = e0 / sum, p1 = e1 / sum;
+    const long long po = ((long long)h * a.Tcap + tk) * L;
+    if (lane < L) a.probs[po + lane] = p0;
+    if (lane + 32 < L) a.probs[po + lane + 32] = p1;
+    if (a.drop_p > 0.f) {
+      if (lane < L) p0 *= drop_scale(a.seed, a.site, (uint64_t)(po + lane), a.drop_p);
+      if (lane + 32 < L) p1 *= drop_scale(a.seed, a.site, (uint64_t)(po + lane + 32), a.drop_p);
+    }
+    for (int j0 = 0; j0 <= i; j0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
+        if (j <= i) {
+          const float* vr = a.V + (long long)(off + j) * d;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) o[e] = fmaf(pj, vr[c], o[e]); }
+        }
+      }
+    }
+  }
+  // y = attn + q1 (residual on the NORMALISED queries, modules.py:223), z = LN2(y)
+  float y[NE]; float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    y[e] = (c < d) ? o[e] + a.Q1[(long long)tk * d + c] : 0.f;
+    if (c < d) a.Y[(long long)tk * d + c] = y[e];
+    s += y[e];
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float qq = 0.f;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = y[e] - mean; qq += u * u; } }
+  const float rstd = 1.0f / sqrtf(warp_sum(qq) / (float)d + 1e-8f);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) a.Z[(long long)tk * d + c] = a.ln_g[c] * ((y[e] - mean) * rstd) + a.ln_b[c];
+  }
+  if (lane == 0) { a.mean2[tk] = mean; a.rstd2[tk] = rstd; }
+}
+
+// ---- forward: FFN1 + ReLU + FFN2 + residual (modules.py:252-271) -----------------------------------
+struct FfnFwdArgs {
+  const float* Z; float *H, *Xn;
+  const op_t *W1, *W2; const float *b1, *b2;
+  const int* dT; int d;
+  float drop_p; uint64_t seed; uint32_t site1, site2;
+};
+constexpr size_t FFN_FWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + 16;
+
+__global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ FfnFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  op_t* Wsm = reinterpret_cast<op_t*>(smem);
+  op_t* A1 = reinterpret_cast<op_t*>(smem + 2 * WMAT_BYTES);
+  op_t* A2 = A1 + TM * LDS;
+  const uint32_t bar = smem_u32(smem + 2 * WMAT_BYTES + 2 * ATILE_BYTES);
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, 2 * WMAT_BYTES);
+    load_wmat(smem_u32(Wsm), a.W1, bar);
+    load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.W2, bar);
+  }
+  // zero the padding columns of the hidden tile once (the epilogue only writes columns < d)
+  for (int idx = tid; idx < TM * LDS; idx += NTHR) A2[idx] = to_op(0.f);
+  __syncthreads();
+  const int mt = warp & 1, ng = warp >> 1;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * TM;
+    stage_tile16(A1, a.Z, t0, T, d);
+    __syncthreads();
+    if (first) { mbar_wait(bar, 0); first = false; }
+    float acc[NT][4];
+    zero_acc(acc);
+    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (c < d) {
+        float h0 = 0.f, h1 = 0.f;
+        if (t0 + r < T) {
+          const long long e = (long long)(t0 + r) * d + c;
+          h0 = fmaxf(v0 + a.b1[c], 0.f); h1 = fmaxf(v1 + a.b1[c + 1], 0.f);
+          if (a.drop_p > 0.f) { h0 *= drop_scale(a.seed, a.site1, (uint64_t)e, a.drop_p); h1 *= drop_scale(a.seed, a.site1, (uint64_t)e + 1, a.drop_p); }
+          *reinterpret_cast<float2*>(a.H + e) = make_float2(h0, h1);
+        }
+        st_op2(A2 + r * LDS + c, h0, h1);
+      }
+    });
+    __syncthreads();
+    zero_acc(acc);
+    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (t0 + r < T && c < d) {
+        const long long e = (long long)(t0 + r) * d + c;
+        float x0 = v0 + a.b2[c], x1 = v1 + a.b2[c + 1];
+        if (a.drop_p > 0.f) { x0 *= drop_scale(a.seed, a.site2, (uint64_t)e, a.drop_p); x1 *= drop_scale(a.seed, a.site2, (uint64_t)e + 1, a.drop_p); }
+        const float2 z = *reinterpret_cast<const float2*>(a.Z + e);
+        *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + z.x, x1 + z.y);
+      }
+    });
+    __syncthreads();
+  }
+}
+
+// ---- LayerNorm backward of one fp32 tile row held in shared memory ------------------------------------
+// dx = rstd*(g - mean(g) - xhat*mean(g*xhat)),  g = dout*gamma.  Returns dx in v[] (lane-strided columns).
+__device__ __forceinline__ void ln_bwd_row(const float* __restrict__ dout_row /*smem*/, const float* __restrict__ x_row,
+                                           float mean, float rstd, const float* __restrict__ gamma, int d, int lane,
+                                           float (&dx)[NE], float (&xv)[NE]) {
+  float g[NE], xh[NE]; float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) { xv[e] = x_row[c]; xh[e] = (xv[e] - mean) * rstd; g[e] = dout_row[c] * gamma[c]; s1 += g[e]; s2 += g[e] * xh[e]; }
+    else { xv[e] = 0.f; xh[e] = 0.f; g[e] = 0.f; }
+  }
+  s1 = warp_sum(s1) / (float)d; s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) dx[e] = rstd * (g[e] - s1 - xh[e] * s2);
+}
+
+// ---- backward: FFN dgrad + LN2 backward --------------------------------------------------------------
+struct FfnBwdArgs {
+  const float* gX;           // grad w.r.t. the block output
+  float* gO;                 // gX * dropout(site2) (written only when drop_p > 0; the wgrad of W2 reads it)
+  const float *H, *Y, *Q1, *mean2, *rstd2, *ln_g;
+  const op_t *W2b, *W1b;     // backward-orientation shadows
+  float *gH, *gZ, *gY, *D;
+  const int* dT; int d;
+  float drop_p; uint64_t seed; uint32_t site2;
+};
+constexpr size_t FFN_BWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES + TM * 4 + 16;
+
+__global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ FfnBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  op_t* Wsm = reinterpret_cast<op_t*>(smem);
+  op_t* A1 = reinterpret_cast<op_t*>(smem + 2 * WMAT_BYTES);
+  op_t* A2 = A1 + TM * LDS;
+  float* Ft = reinterpret_cast<float*>(smem + 2 * WMAT_BYTES + 2 * ATILE_BYTES);
+  float* rs = reinterpret_cast<float*>(smem + 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES);
+  const uint32_t bar = smem_u32(smem + 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES + TM * 4);
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, 2 * WMAT_BYTES);
+    load_wmat(smem_u32(Wsm), a.W2b, bar);
+    load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.W1b, bar);
+  }
+  for (int idx = tid; idx < TM * LDS; idx += NTHR) A2[idx] = to_op(0.f);
+  __syncthreads();
+  const int mt = warp & 1, ng = warp >> 1;
+  const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * TM;
+    stage_rows_scaled(A1, rs, a.gX, t0, T, d, warp, lane, a.drop_p, a.seed, a.site2, a.gO);   // x_out = drop(h.W2 + b2) + z
+    __syncthreads();
+    if (first) { mbar_wait(bar, 0); first = false; }
+    float acc[NT][4];
+    zero_acc(acc);
+    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
+    // gH = (gOut . W2^T) * [h > 0] / (1 - p)   (h is stored post-dropout)
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (c < d) {
+        float g0 = 0.f, g1 = 0.f;
+        if (t0 + r < T) {
+          const long long e = (long long)(t0 + r) * d + c;
+          const float2 h = *reinterpret_cast<const float2*>(a.H + e);
+          g0 = h.x > 0.f ? v0 * inv_keep : 0.f; g1 = h.y > 0.f ? v1 * inv_keep : 0.f;   // still carries the row scale
+          *reinterpret_cast<float2*>(a.gH + e) = make_float2(g0 * rs[r], g1 * rs[r]);
+        }
+        st_op2(A2 + r * LDS + c, g0, g1);
+      }
+    });
+    __syncthreads();
+    zero_acc(acc);
+    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    // gZ = gH . W1^T + gX   (residual z -> x_out)
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (c < d) {
+        float z0 = 0.f, z1 = 0.f;
+        if (t0 + r < T) {
+          const long long e = (long long)(t0 + r) * d + c;
+          const float2 gx = *reinterpret_cast<const float2*>(a.gX + e);
+          z0 = v0 * rs[r] + gx.x; z1 = v1 * rs[r] + gx.y;
+          *reinterpret_cast<float2*>(a.gZ + e) = make_float2(z0, z1);
+        }
+        *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(z0, z1);
+      }
+    });
+    __syncthreads();
+    // gY = LN2 backward;  D = gY . (Y - q1)  (= sum_j dP_ij P_ij of the attention softmax backward)
+#pragma unroll
+    for (int rr = 0; rr < TM / 8; ++rr) {
+      const int r = warp * (TM / 8) + rr, tk = t0 + r;
+      if (tk >= T) continue;
+      float dx[NE], yv[NE];
+      ln_bwd_row(Ft + r * FT_LD, a.Y + (long long)tk * d, a.mean2[tk], a.rstd2[tk], a.ln_g, d, lane, dx, yv);
+      float dd = 0.f;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        if (c < d) { a.gY[(long long)tk * d + c] = dx[e]; dd = fmaf(dx[e], yv[e] - a.Q1[(long long)tk * d + c], dd); }
+      }
+      dd = warp_sum(dd);
+      if (lane == 0) a.D[tk] = dd;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- backward: attention, warp per token (query role -> gQ, key role -> gK, gV) ------------------------
+struct AttnBwdArgs {
+  const float *Q, *K, *V, *probs, *gY, *D;
+  const int *tok_row, *row_off;
+  float *gQ, *gK, *gV;
+  const int* dT; int d, nh, L, Tcap;
+  float drop_p; uint64_t seed; uint32_t site;
+};
+
+__global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ AttnBwdArgs a) {
+  const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tk >= *a.dT) return;
+  const int d = a.d, L = a.L;
+  const int row = a.tok_row[tk];
+  const int off = a.row_off[row];
+  const int n = a.row_off[row + 1] - off;
+  const int i = tk - off;
+  const int dh = d / a.nh;
+  const float inv_denom = 1.0f / sqrtf((float)dh);
+  float gy[NE], vt[NE], gq[NE], gk[NE], gv[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    gy[e] = (c < d) ? a.gY[(long long)tk * d + c] : 0.f;
+    vt[e] = (c < d) ? a.V[(long long)tk * d + c] : 0.f;
+    gq[e] = gk[e] = gv[e] = 0.f;
+  }
+  const float Di = a.D[tk];
+  for (int h = 0; h < a.nh; ++h) {
+    const int c_lo = h * dh, c_hi = c_lo + dh;
+    // D restricted to this head when nh > 1: D_h = sum_j dP_ij P_ij is recomputed from the head's own columns
+    float Dh = Di;
+    const long long po_i = ((long long)h * a.Tcap + tk) * L;
+    // ---- query role: gQ[i] = sum_{j<=i} dS_ij K[j]
+    if (a.nh > 1) {
+      float acc = 0.f;
+      for (int j = 0; j <= i; ++j) {
+        const float* vr = a.V + (long long)(off + j) * d;
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gy[e], vr[c], p); }
+        p = warp_sum(p);
+        const float P = a.probs[po_i + j];
+        const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
+        acc = fmaf(p * scl, P, acc);
+      }
+      Dh = acc;
+    }
+    for (int j0 = 0; j0 <= i; j0 += 4) {
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, i);
+        const float* vr = a.V + (long long)(off + j) * d;
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gy[e], vr[c], p); }
+        part[u] = p;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dp = warp_sum(part[u]);
+        const int j = j0 + u;
+        if (j <= i) {
+          const float P = a.probs[po_i + j];
+          const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
+          const float ds = P * (dp * scl - Dh) * inv_denom;
+          const float* kr = a.K + (long long)(off + j) * d;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) gq[e] = fmaf(ds, kr[c], gq[e]); }
+        }
+      }
+    }
+    // ---- key role: gK[i] = sum_{i'>=i} dS_i'i Q[i'],  gV[i] = sum_{i'>=i} Pd_i'i gY[i']
+    for (int q0 = i; q0 < n; q0 += 4) {
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int qi = min(q0 + u, n - 1);
+        const float* gr = a.gY + (long long)(off + qi) * d;
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gr[c], vt[e], p); }
+        part[u] = p;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dp = warp_sum(part[u]);
+        const int qi = q0 + u;
+        if (qi < n) {
+          const int tq = off + qi;
+          const long long po = ((long long)h * a.Tcap + tq) * L + i;
+          const float P = a.probs[po];
+          const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+          float Dq = a.D[tq];
+          if (a.nh > 1) {      // per-head D of query qi (rare path: num_heads > 1)
+            float acc = 0.f;
+            const long long pq = ((long long)h * a.Tcap + tq) * L;
+            const float* gr = a.gY + (long long)tq * d;
+            for (int j = 0; j <= qi; ++j) {
+              const float* vr = a.V + (long long)(off + j) * d;
+              float p = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gr[c], vr[c], p); }
+              p = warp_sum(p);
+              const float s2 = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(pq + j), a.drop_p) : 1.f;
+              acc = fmaf(p * s2, a.probs[pq + j], acc);
+            }
+            Dq = acc;
+          }
+          const float ds = P * (dp * scl - Dq) * inv_denom;
+          const float pd = P * scl;
+          const float* qr = a.Q + (long long)tq * d;
+          const float* gr = a.gY + (long long)tq * d;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int c = lane + 32 * e;
+            if (c >= c_lo && c < c_hi) { gk[e] = fmaf(ds, qr[c], gk[e]); gv[e] = fmaf(pd, gr[c], gv[e]); }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) {
+      a.gQ[(long long)tk * d + c] = gq[e];
+      a.gK[(long long)tk * d + c] = gk[e];
+      a.gV[(long long)tk * d + c] = gv[e];
+    }
+  }
+}
+
+// ---- backward: Q/K/V dgrad + LN1 backward --------------------------------------------------------------
+struct QkvBwdArgs {
+  const float *gQ, *gK, *gV, *gY, *X, *mean1, *rstd1, *ln_g;
+  const op_t *Wqb, *Wkb, *Wvb;
+  float *gQ1, *gXin;
+  const int* dT; int d;
+};
+constexpr size_t QKV_BWD_SMEM = 3 * WMAT_BYTES + 3 * ATILE_BYTES + FTILE_BYTES + 2 * TM * 4 + 16;
+static_assert(3 * ATILE_BYTES >= FTILE_BYTES, "second fp32 tile aliases the operand tiles");
+
+__global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ QkvBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  op_t* Wsm = reinterpret_cast<op_t*>(smem);
+  op_t* A1 = reinterpret_cast<op_t*>(smem + 3 * WMAT_BYTES);
+  op_t* A2 = A1 + TM * LDS;
+  op_t* A3 = A2 + TM * LDS;
+  float* Ft2 = reinterpret_cast<float*>(smem + 3 * WMAT_BYTES);              // aliases A1..A3 after the GEMMs
+  float* Ft = reinterpret_cast<float*>(smem + 3 * WMAT_BYTES + 3 * ATILE_BYTES);
+  float* rsq = reinterpret_cast<float*>(smem + 3 * WMAT_BYTES + 3 * ATILE_BYTES + FTILE_BYTES);
+  float* rskv = rsq + TM;
+  const uint32_t bar = smem_u32(smem + 3 * WMAT_BYTES + 3 * ATILE_BYTES + FTILE_BYTES + 2 * TM * 4);
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + TM - 1) / TM;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, 3 * WMAT_BYTES);
+    load_wmat(smem_u32(Wsm), a.Wqb, bar);
+    load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.Wkb, bar);
+    load_wmat(smem_u32(Wsm) + 2 * WMAT_BYTES, a.Wvb, bar);
+  }
+  __syncthreads();
+  const int mt = warp & 1, ng = warp >> 1;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * TM;
+    stage_rows_scaled(A1, rsq, a.gQ, t0, T, d, warp, lane);
+    stage_rows_scaled(A2, rskv, a.gK, t0, T, d, warp, lane, 0.f, 0, 0, nullptr, a.gV, A3);
+    __syncthreads();
+    if (first) { mbar_wait(bar, 0); first = false; }
+    float acc[NT][4];
+    zero_acc(acc);
+    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
+    // gQ1 = gQ . Wq^T + gY   (y = attn + q1)
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (c < d) {
+        float q0 = 0.f, q1 = 0.f;
+        if (t0 + r < T) {
+          const long long e = (long long)(t0 + r) * d + c;
+          const float2 gy = *reinterpret_cast<const float2*>(a.gY + e);
+          q0 = v0 * rsq[r] + gy.x; q1 = v1 * rsq[r] + gy.y;
+          *reinterpret_cast<float2*>(a.gQ1 + e) = make_float2(q0, q1);
+        }
+        *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(q0, q1);
+      }
+    });
+    zero_acc(acc);
+    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    warp_gemm(A3 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
+    __syncthreads();                       // every warp is done reading A1..A3
+    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+      if (c < d) *reinterpret_cast<float2*>(Ft2 + r * FT_LD + c) = make_float2(v0 * rskv[r], v1 * rskv[r]);
+    });
+    __syncthreads();
+    // gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ1)
+#pragma unroll
+    for (int rr = 0; rr < TM / 8; ++rr) {
+      const int r = warp * (TM / 8) + rr, tk = t0 + r;
+      if (tk >= T) continue;
+      float dx[NE], xv[NE];
+      ln_bwd_row(Ft + r * FT_LD, a.X + (long long)tk * d, a.mean1[tk], a.rstd1[tk], a.ln_g, d, lane, dx, xv);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        if (c < d) a.gXin[(long long)tk * d + c] = dx[e] + Ft2[r * FT_LD + c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace fz
+}  // namespace ader

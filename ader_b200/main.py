@@ -63,6 +63,9 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     p.add_argument("--results_root", default="results", type=str)
     p.add_argument("--max_periods", default=0, type=int)
     p.add_argument("--item_num", default=0, type=int)
+    p.add_argument("--loss_impl", default="tc", choices=["tc", "exact"], type=str)      # logits+CE+KD: tcgen05 bf16 / fp32
+    p.add_argument("--encoder_impl", default=None, choices=["tc", "exact"], type=str)  # training encoder (default follows loss_impl)
+    p.add_argument("--infer_encoder_impl", default="exact", choices=["tc", "exact"], type=str)  # eval / herding encoder
     return p
 
 

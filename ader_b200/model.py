@@ -70,6 +70,12 @@ class Ader:
         self.grad_sync = None
         self.global_counts = None       # data parallel: (n_train, n_ex) over all ranks -> global means
         self.loss_impl = getattr(args, "loss_impl", "tc")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
+        # encoder: "tc" = fused bf16 tensor-core kernels, "exact" = fp32.  Training uses encoder_impl; inference
+        # passes (rep / eval / herding: bit-exact index parity with the fp32 reference) use infer_encoder_impl.
+        self.encoder_impl = getattr(args, "encoder_impl", None) or ("exact" if self.loss_impl == "exact" else "tc")
+        self.infer_encoder_impl = getattr(args, "infer_encoder_impl", "exact")
+        if self.hp.hidden_units > 160:
+            self.encoder_impl = self.infer_encoder_impl = "exact"
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
         self._enc_ws = ops.Workspace(self.device)
         self._bwd_ws = ops.Workspace(self.device)
@@ -99,14 +105,15 @@ class Ader:
         return min(max(cap, 1), M * self.hp.maxlen)
 
     def encode(self, ids: torch.Tensor, n_tokens: Optional[int] = None, dropout_rate: float = 0.0,
-               seed: int = 0, out: Optional[torch.Tensor] = None):
+               seed: int = 0, out: Optional[torch.Tensor] = None, impl: Optional[str] = None):
         """ids int32 [M, L] (device) -> rep fp32 [M, d]; returns (rep, Tcap).  The activation
         workspace stays valid until the next encode() (needed by backward)."""
         M = ids.shape[0]
         tcap = self._tcap(ids, n_tokens)
         ws = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, M, tcap))
         rep = out if out is not None else torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
-        ops.encoder_fwd(self.ms, self.theta, ids, tcap, ws, rep, dropout_rate, seed)
+        ops.encoder_fwd(self.ms, self.theta, ids, tcap, ws, rep, dropout_rate, seed,
+                        impl=impl or self.infer_encoder_impl)
         return rep, tcap
 
     def rep(self, seq, n_tokens: Optional[int] = None) -> torch.Tensor:
@@ -170,7 +177,7 @@ class Ader:
             else:
                 raise ValueError("exemplar rows were fed but the loss is vanilla (call update_loss first)")
         seed = (self.seed << 32) + self.global_step
-        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed)
+        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl)
         if _events:
             _events[0].record()
         gc = global_counts if global_counts is not None else self.global_counts
@@ -187,7 +194,8 @@ class Ader:
         if _events:
             _events[1].record()
         bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
-        ops.encoder_bwd(self.ms, self.theta, ids, tcap, self._enc_ws.buf, bws, d_rep, self.grad, dropout_rate, seed)
+        ops.encoder_bwd(self.ms, self.theta, ids, tcap, self._enc_ws.buf, bws, d_rep, self.grad, dropout_rate, seed,
+                        impl=self.encoder_impl)
         if _events:
             _events[2].record()
         if self.grad_sync is not None:      # data parallel: NCCL all-reduce of the flat gradient

@@ -67,16 +67,22 @@ def encoder_ws_slot(ms: AderModel, M: int, Tcap: int, slot: int, block: int = 0)
     return _lib.load().ader_encoder_ws_slot(C.byref(ms), M, Tcap, slot, block)
 
 
-def encoder_fwd(ms: AderModel, theta, ids, Tcap: int, ws, rep, dropout_rate: float = 0.0, seed: int = 0):
-    """ids [M, maxlen] int32 -> rep [M, d] (ADER.py:25-85)."""
+def encoder_fwd(ms: AderModel, theta, ids, Tcap: int, ws, rep, dropout_rate: float = 0.0, seed: int = 0,
+                impl: str = "exact"):
+    """ids [M, maxlen] int32 -> rep [M, d] (ADER.py:25-85).  impl: "exact" (fp32) or "tc" (fused bf16 tensor path)."""
     _require_cuda(theta, ids, ws, rep)
-    check(_lib.load().ader_encoder_fwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
+    lib = _lib.load()
+    fn = lib.ader_encoder_fwd_tc if impl == "tc" else lib.ader_encoder_fwd
+    check(fn(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
                                        float(dropout_rate), C.c_uint64(seed), _stream()), "encoder_fwd")
 
 
-def encoder_bwd(ms: AderModel, theta, ids, Tcap: int, ws, bwd_ws, d_rep, grad, dropout_rate: float = 0.0, seed: int = 0):
+def encoder_bwd(ms: AderModel, theta, ids, Tcap: int, ws, bwd_ws, d_rep, grad, dropout_rate: float = 0.0, seed: int = 0,
+                impl: str = "exact"):
     _require_cuda(theta, ids, ws, bwd_ws, d_rep, grad)
-    check(_lib.load().ader_encoder_bwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
+    lib = _lib.load()
+    fn = lib.ader_encoder_bwd_tc if impl == "tc" else lib.ader_encoder_bwd
+    check(fn(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
                                        _ptr(d_rep), _ptr(grad), float(dropout_rate), C.c_uint64(seed), _stream()),
           "encoder_bwd")
 

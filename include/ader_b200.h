@@ -72,6 +72,17 @@ int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* 
                          int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
                          float dropout_rate, uint64_t seed, void* stream);
 
+/* Same two contracts on the tensor cores: fused sub-layer kernels (LN + Q/K/V, attention + LN, FFN) with bf16
+ * operands / fp32 accumulation, weights staged by bulk async copies; workspaces and slots are identical to
+ * the exact path (same *_ws_bytes queries).  Needs hidden_units <= 160.  Results agree with the exact path
+ * to bf16 operand rounding (tests state the tolerance); weight/bias/LayerNorm gradients are accumulated in
+ * fp32 in a fixed order (deterministic). */
+int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                            int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed, void* stream);
+int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
+                            int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
+                            float dropout_rate, uint64_t seed, void* stream);
+
 /* ---- logits + CE + distillation: ADER.py:88-93, ADER.py:108-138 (subsystem 2) ---------- */
 typedef struct AderLossArgs {
   int32_t M;               /* rows of rep = n_train + n_ex (exemplar rows LAST, main.py:229)   */

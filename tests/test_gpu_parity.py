@@ -400,7 +400,7 @@ def test_full_size_properties():
 @pytest.mark.parametrize("shape", [(24, 16, 450, 400, 500), (333, 256, 3001, 2500, 4000)])
 def test_tc_loss_path_matches_oracle(mode, shape):
     M, Bt, V, Vp, item_num = shape
-    m, hp, params = _model(item_num, loss_impl="tc", disable_distillation=(mode == "er"))
+    m, hp, params = _model(item_num, loss_impl="tc", encoder_impl="exact", disable_distillation=(mode == "er"))
     assert m.loss_impl == "tc"
     rng = np.random.RandomState(21)
     lens = np.minimum(50, rng.geometric(0.25, M))
@@ -446,7 +446,7 @@ def test_tc_full_size_step_tracks_exact_path():
     pos = rng.randint(1, V + 1, Bt).astype(np.int32)
     out = {}
     for impl in ("exact", "tc"):
-        m, hp, _ = _model(43136, scale=0.02, loss_impl=impl)
+        m, hp, _ = _model(43136, scale=0.02, loss_impl=impl, encoder_impl="exact")
         teacher = torch.randn(M - Bt, Vp, device=m.device, generator=torch.Generator(device=m.device).manual_seed(3))
         m.update_loss(0.6)
         loss = float(m.loss_and_grad(ids, pos, V, exemplar_logits=teacher, n_tokens=int(lens.sum())).item())
@@ -572,7 +572,7 @@ def test_vocab_parallel_shards_match_single_kernel(mode, shards):
     M, Bt, V, Vp, item_num = 300, 200, 3001, 2500, 4000
     if mode == "vanilla":
         M = Bt
-    m, hp, _ = _model(item_num, loss_impl="tc", disable_distillation=(mode == "er"))
+    m, hp, _ = _model(item_num, loss_impl="tc", encoder_impl="exact", disable_distillation=(mode == "er"))
     dev = m.device
     g = torch.Generator(device=dev).manual_seed(5)
     rep = torch.randn(M, 150, device=dev, generator=g)
