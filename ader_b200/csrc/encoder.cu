@@ -12,7 +12,7 @@
 namespace ader {
 
 constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
-constexpr int SPLITS = 16;        // split-K partials for weight / LN / bias gradients
+constexpr int SPLITS = 24;        // split-K partials for weight / LN / bias gradients
 constexpr int PG_LANES = 6;       // token lanes per column in the LN / position gradient reductions (160 x 6 = 960 threads)
 
 struct EncWs {
@@ -582,13 +582,17 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, long long s
 // position-table gradient: dP[p,c] = sum over rows having position p of dx0[token(r,p), c]
 __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__ row_len,
                            const int* __restrict__ row_off, int M, int L, int d,
-                           float drop_p, uint64_t seed, float* __restrict__ gpos) {
-  // blockDim = (ceil32(d), 4): thread (c, k) sums rows k, k+4, ...; lanes reduced in fixed order.
+                           float drop_p, uint64_t seed, float* __restrict__ gpos, long long split_stride) {
+  // grid (L, splits): CTA (p, s) sums the rows of chunk s that have position p into partial slot s.
+  // blockDim = (ceil32(d), PG_LANES): thread (c, k) sums rows lo+k, lo+k+PG_LANES, ...; lanes reduced in fixed order.
   __shared__ float part[PG_LANES][256];
   const int p = blockIdx.x, c = threadIdx.x, k = threadIdx.y;
+  const int chunk = (M + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * chunk, hi = min(M, lo + chunk);
+  gpos += (long long)blockIdx.y * split_stride;
   float s = 0.f;
   if (c < d) {
-    for (int r = k; r < M; r += PG_LANES) {
+    for (int r = lo + k; r < hi; r += PG_LANES) {
       int n = row_len[r];
       if (n >= L - p) {
         long long e = (long long)(row_off[r] + p - (L - n)) * d + c;
@@ -797,13 +801,11 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
   const int* dT = w.row_off + M;
   const long long PS = l.dense_count();
   const int ln_threads = ((d + 31) / 32) * 32;
-  // dense parameter gradients: reduce the split partials in fixed order
-  {
-    const long long lo = (long long)L * d, hi = PS;
-    k_reduce_partials<<<cdiv(hi - lo, 256), 256, 0, st>>>(g.partial, PS, SPLITS, lo, hi, grad + l.off_pos);
-  }
-  // position table (ADER.py:41-52) and item-table scatter (modules.py:127-130)
-  k_pos_grad<<<L, dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, grad + l.off_pos);
+  // position table (ADER.py:41-52): per-row-chunk partials into the first L*d entries of the split slots
+  k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, g.partial, PS);
+  // dense parameter gradients (position table included): reduce the split partials in fixed order
+  k_reduce_partials<<<cdiv(PS, 256), 256, 0, st>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
+  // item-table scatter (modules.py:127-130)
   {
     const int ntiles = sort_tiles(Tcap);
     const int bits = key_bits(m->v_tab);
@@ -1033,6 +1035,7 @@ static void fused_attrs() {
   cudaFuncSetAttribute(fz::k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_FWD_SMEM);
   cudaFuncSetAttribute(fz::k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_BWD_SMEM);
   cudaFuncSetAttribute(fz::k_qkv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::QKV_BWD_SMEM);
+  cudaFuncSetAttribute(fz::k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::WGRAD_SMEM);
   done = true;
 }
 static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
@@ -1059,7 +1062,7 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
   k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
   k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
   k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
-  fz::k_pack_weights<<<m->num_blocks * fz::W_PER_BLOCK, 256, 0, st>>>(theta, l, (fz::op_t*)w.wshadow);
+  fz::k_pack_weights<<<dim3(m->num_blocks * 5, fz::KP / fz::PACK_BAND), 256, 0, st>>>(theta, l, (fz::op_t*)w.wshadow);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
@@ -1145,7 +1148,8 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
     ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
     ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.site = 1u + 3u * b;
-    fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
+    if (m->num_heads == 1) fz::k_attn_bwd_w1<<<ln_grid, 256, 0, st>>>(ab);
+    else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
 
     fz::QkvBwdArgs qb;
     qb.gQ = gQ; qb.gK = gK; qb.gV = gV; qb.gY = gY; qb.X = X; qb.mean1 = w.mean1[b]; qb.rstd1 = w.rstd1[b];
@@ -1154,18 +1158,18 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     fz::k_qkv_bwd<<<tile_grid, fz::NTHR, fz::QKV_BWD_SMEM, st>>>(qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
 
-    // weight + bias gradients of the block's five dense layers: one grouped split-K launch (fp32)
+    // weight / bias / LayerNorm-parameter gradients of the block: one launch (TF32 tensor cores, fp32 accumulate)
     const float* gOut = (p > 0.f) ? gO : gX;
-    GemmArgs wg[5] = {
-        wgrad_args(H, gOut, part(bo + l.w2), part(bo + l.b2), PS, Tcap, dT, d),
-        wgrad_args(Z, gH, part(bo + l.w1), part(bo + l.b1), PS, Tcap, dT, d),
-        wgrad_args(Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d),
-        wgrad_args(X, gK, part(bo + l.wk), part(bo + l.bk), PS, Tcap, dT, d),
-        wgrad_args(X, gV, part(bo + l.wv), part(bo + l.bv), PS, Tcap, dT, d)};
-    if (int e = launch_gemm_group(wg, 5, st)) return e;
-    LnPgSet s2 = {gZ, Y, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
-    LnPgSet s1 = {gQ1, X, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
-    k_ln_param_grad2<<<dim3(SPLITS, 2), dim3(ln_threads, PG_LANES), 0, st>>>(s2, s1, dT, d, PS);
+    fz::WgradArgs wa;
+    wa.p[0] = {H, gOut, nullptr, nullptr, part(bo + l.w2), part(bo + l.b2)};
+    wa.p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
+    wa.p[2] = {Q1, gQ, nullptr, nullptr, part(bo + l.wq), part(bo + l.bq)};
+    wa.p[3] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
+    wa.p[4] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
+    wa.p[5] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
+    wa.p[6] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
+    wa.n_gemm = 5; wa.n_ln = 2; wa.dT = dT; wa.d = d; wa.split_stride = PS;
+    fz::k_wgrad<<<dim3(SPLITS, 7), fz::NTHR, fz::WGRAD_SMEM, st>>>(wa);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
     float* t = gX; gX = gXin; gXin = t;
   }

@@ -178,21 +178,35 @@ __device__ __forceinline__ void stage_tile16(op_t* __restrict__ As, const float*
 // ---- weight shadows ------------------------------------------------------------------------------
 // shadow[(b*5 + w)*2 + 0][n][k] = W_w[k][n]   (forward:  out = in . W,   B(k = in,  n = out))
 // shadow[(b*5 + w)*2 + 1][n][k] = W_w[n][k]   (backward: gin = gout . W^T, B(k = out, n = in))
+// grid (5 * NB matrices, 5 bands of 32 output rows): CTA stages W[n0:n0+32, :] and W[:, n0:n0+32] and writes rows
+// n0..n0+31 of both orientations with coalesced 32-bit stores.
+constexpr int PACK_BAND = 32;
 __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ theta, Layout l, op_t* __restrict__ shadow) {
-  const int which = blockIdx.x;                 // (b*5 + w)*2 + orient
-  const int orient = which & 1, w = (which >> 1) % 5, b = (which >> 1) / 5;
+  __shared__ float rowband[PACK_BAND][KP + 1];    // rowband[r][k] = W[n0 + r][k]
+  __shared__ float colband[KP][PACK_BAND + 1];    // colband[k][r] = W[k][n0 + r]
+  const int w = blockIdx.x % 5, b = blockIdx.x / 5;
+  const int n0 = blockIdx.y * PACK_BAND;
   const long long rel[5] = {l.wq, l.wk, l.wv, l.w1, l.w2};
   const float* W = theta + l.block(b) + rel[w];
-  op_t* out = shadow + (size_t)which * (KP * LDS);
   const int d = l.d;
-  for (int idx = threadIdx.x; idx < KP * (LDS / 2); idx += blockDim.x) {
-    const int n = idx / (LDS / 2), k = (idx % (LDS / 2)) * 2;
-    float v0 = 0.f, v1 = 0.f;
-    if (n < d) {
-      if (orient == 0) { if (k < d) v0 = W[(long long)k * d + n]; if (k + 1 < d) v1 = W[(long long)(k + 1) * d + n]; }
-      else             { if (k < d) v0 = W[(long long)n * d + k]; if (k + 1 < d) v1 = W[(long long)n * d + k + 1]; }
-    }
-    st_op2(out + n * LDS + k, v0, v1);
+  for (int idx = threadIdx.x; idx < PACK_BAND * KP; idx += blockDim.x) {
+    const int r = idx / KP, k = idx % KP;
+    rowband[r][k] = (n0 + r < d && k < d) ? W[(long long)(n0 + r) * d + k] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < KP * PACK_BAND; idx += blockDim.x) {
+    const int k = idx / PACK_BAND, r = idx % PACK_BAND;
+    colband[k][r] = (n0 + r < d && k < d) ? W[(long long)k * d + n0 + r] : 0.f;
+  }
+  __syncthreads();
+  op_t* out0 = shadow + (size_t)(blockIdx.x * 2) * (KP * LDS);
+  op_t* out1 = out0 + KP * LDS;
+  for (int idx = threadIdx.x; idx < PACK_BAND * (LDS / 2); idx += blockDim.x) {
+    const int r = idx / (LDS / 2), k = (idx % (LDS / 2)) * 2;
+    if (n0 + r >= KP) continue;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (k < KP) { a0 = colband[k][r]; a1 = colband[k + 1][r]; b0 = rowband[r][k]; b1 = rowband[r][k + 1]; }
+    st_op2(out0 + (n0 + r) * LDS + k, a0, a1);
+    st_op2(out1 + (n0 + r) * LDS + k, b0, b1);
   }
 }
 
@@ -307,6 +321,66 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
   }
 }
 
+// ---- warp-per-token attention building blocks -------------------------------------------------------------
+// Keys / queries are processed in blocks of 8 rows: all 40 row loads of a block are independent (one L2 round
+// trip per block instead of one per key), and the 8 dot products are finished by a reduce-scatter (9 shuffles
+// for 8 sums instead of 40): afterwards EVERY lane holds the sum for row (lane & 7) of the block.
+constexpr int KB = 8;
+__device__ __forceinline__ float reduce_scatter8(float (&v)[KB], int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = (lane & 4) ? v[k] : v[k + 4];
+    const float keep = (lane & 4) ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = (lane & 2) ? v[k] : v[k + 2];
+    const float keep = (lane & 2) ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const float send = (lane & 1) ? v[0] : v[1];
+    const float keep = (lane & 1) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  float r = v[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
+// every lane <- dot(x[.], rows[(lane & 7) * d + .]) over features [c_lo, c_hi) when (lane & 7) < count, else 0.
+__device__ __forceinline__ float block_dots(const float (&x)[NE], const float* __restrict__ rows, int d, int count,
+                                            int c_lo, int c_hi, int lane) {
+  float part[KB];
+#pragma unroll
+  for (int u = 0; u < KB; ++u) {
+    const float* r = rows + (long long)min(u, count - 1) * d;      // clamped duplicate loads hit L1
+    float p = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(x[e], r[c], p); }
+    part[u] = (u < count) ? p : 0.f;
+  }
+  return reduce_scatter8(part, lane);
+}
+// acc[.] += sum_{u < count} w_u * rows[u * d + .], w_u held by lane u (u < 8); features [c_lo, c_hi).  Fixed order.
+__device__ __forceinline__ void block_axpy(float (&acc)[NE], float w, const float* __restrict__ rows, int d, int count,
+                                           int c_lo, int c_hi, int lane) {
+  float v[KB][NE], wu[KB];
+#pragma unroll
+  for (int u = 0; u < KB; ++u) {
+    wu[u] = __shfl_sync(0xffffffffu, w, u);
+    if (u >= count) wu[u] = 0.f;
+    const float* r = rows + (long long)min(u, count - 1) * d;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; v[u][e] = (c >= c_lo && c < c_hi) ? r[c] : 0.f; }
+  }
+#pragma unroll
+  for (int u = 0; u < KB; ++u)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = fmaf(wu[u], v[u][e], acc[e]);
+}
+
 // ---- forward: causal attention + residual + LN2, warp per query token (modules.py:177-223, 40-48) ---
 struct AttnFwdArgs {
   const float *Q, *K, *V, *Q1;
@@ -317,7 +391,7 @@ struct AttnFwdArgs {
   float drop_p; uint64_t seed; uint32_t site;
 };
 
-__global__ void __launch_bounds__(256) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
+__global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
   const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tk >= *a.dT) return;
   const int d = a.d, L = a.L;
@@ -326,65 +400,64 @@ __global__ void __launch_bounds__(256) k_attn_ln_fwd(const __grid_constant__ Att
   const int i = tk - off;                       // query index inside its session; keys 0..i
   const int dh = d / a.nh;
   const float inv_denom = 1.0f / sqrtf((float)dh);
+  const int j8 = lane & 7;
   float q[NE], o[NE];
 #pragma unroll
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; q[e] = (c < d) ? a.Q[(long long)tk * d + c] : 0.f; o[e] = 0.f; }
+  const float* Krow = a.K + (long long)off * d;
+  const float* Vrow = a.V + (long long)off * d;
   for (int h = 0; h < a.nh; ++h) {
     const int c_lo = h * dh, c_hi = c_lo + dh;
-    float s0 = -INFINITY, s1 = -INFINITY;       // score of key `lane` / key `lane + 32`
-    for (int j0 = 0; j0 <= i; j0 += 4) {
-      float part[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = min(j0 + u, i);
-        const float* kr = a.K + (long long)(off + j) * d;
-        float p = 0.f;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(q[e], kr[c], p); }
-        part[u] = p;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float s = warp_sum(part[u]) * inv_denom;
-        const int j = j0 + u;
-        if (j <= i) { if (lane == (j & 31)) { if (j < 32) s0 = s; else s1 = s; } }
-      }
-    }
-    const float mx = warp_max(fmaxf(s0, s1));
-    const float e0 = (lane <= i) ? expf(s0 - mx) : 0.f;
-    const float e1 = (lane + 32 <= i) ? expf(s1 - mx) : 0.f;
-    const float sum = warp_sum(e0 + e1);
-    float p0 = e0 / sum, p1 = e1 / sum;
     const long long po = ((long long)h * a.Tcap + tk) * L;
-    if (lane < L) a.probs[po + lane] = p0;
-    if (lane + 32 < L) a.probs[po + lane + 32] = p1;
-    if (a.drop_p > 0.f) {
-      if (lane < L) p0 *= drop_scale(a.seed, a.site, (uint64_t)(po + lane), a.drop_p);
-      if (lane + 32 < L) p1 *= drop_scale(a.seed, a.site, (uint64_t)(po + lane + 32), a.drop_p);
+    // online softmax over key blocks of 8 (running max m, running sum l); raw scores are parked in the probs
+    // row and normalised in place afterwards
+    float m = -INFINITY, l = 0.f;
+    float oh[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) oh[e] = 0.f;
+    for (int j0 = 0; j0 <= i; j0 += KB) {
+      const int cnt = min(KB, i + 1 - j0);
+      const float sc = block_dots(q, Krow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane) * inv_denom;
+      const bool valid = j8 < cnt;
+      float bm = valid ? sc : -INFINITY;
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+      const float m_new = fmaxf(m, bm);
+      const float corr = expf(m - m_new);
+      float pj = valid ? expf(sc - m_new) : 0.f;
+      float ps = pj;
+      ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      l = l * corr + ps;
+      m = m_new;
+      if (lane < KB && valid) a.probs[po + j0 + j8] = sc;
+      if (a.drop_p > 0.f && valid) pj *= drop_scale(a.seed, a.site, (uint64_t)(po + j0 + j8), a.drop_p);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) oh[e] *= corr;
+      block_axpy(oh, pj, Vrow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane);
     }
-    for (int j0 = 0; j0 <= i; j0 += 4) {
+    const float inv_l = 1.0f / l;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u;
-        const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
-        if (j <= i) {
-          const float* vr = a.V + (long long)(off + j) * d;
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) o[e] = oh[e] * inv_l; }
+    __syncwarp();
 #pragma unroll
-          for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) o[e] = fmaf(pj, vr[c], o[e]); }
-        }
-      }
+    for (int u = 0; u < 2; ++u) {
+      const int j = lane + 32 * u;
+      if (j < L) a.probs[po + j] = (j <= i) ? expf(a.probs[po + j] - m) * inv_l : 0.f;
     }
   }
   // y = attn + q1 (residual on the NORMALISED queries, modules.py:223), z = LN2(y)
-  float y[NE]; float s = 0.f;
+  float y[NE]; float sm = 0.f;
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
     const int c = lane + 32 * e;
     y[e] = (c < d) ? o[e] + a.Q1[(long long)tk * d + c] : 0.f;
     if (c < d) a.Y[(long long)tk * d + c] = y[e];
-    s += y[e];
+    sm += y[e];
   }
-  const float mean = warp_sum(s) / (float)d;
+  const float mean = warp_sum(sm) / (float)d;
   float qq = 0.f;
 #pragma unroll
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = y[e] - mean; qq += u * u; } }
@@ -707,6 +780,67 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
   }
 }
 
+// Single-head fast form of the same kernel: blocks of 8 keys / queries (one L2 round trip per block).
+__global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ AttnBwdArgs a) {
+  const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tk >= *a.dT) return;
+  const int d = a.d, L = a.L;
+  const int row = a.tok_row[tk];
+  const int off = a.row_off[row];
+  const int n = a.row_off[row + 1] - off;
+  const int i = tk - off;
+  const float inv_denom = 1.0f / sqrtf((float)d);
+  const int j8 = lane & 7;
+  float gy[NE], vt[NE], gq[NE], gk[NE], gv[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    gy[e] = (c < d) ? a.gY[(long long)tk * d + c] : 0.f;
+    vt[e] = (c < d) ? a.V[(long long)tk * d + c] : 0.f;
+    gq[e] = gk[e] = gv[e] = 0.f;
+  }
+  const float Di = a.D[tk];
+  const long long po_i = (long long)tk * L;
+  // ---- query role: dS_ij = P_ij (dP_ij - D_i) / sqrt(d),  gQ[i] = sum_{j<=i} dS_ij K[j]
+  for (int j0 = 0; j0 <= i; j0 += KB) {
+    const int cnt = min(KB, i + 1 - j0);
+    const float dp = block_dots(gy, a.V + (long long)(off + j0) * d, d, cnt, 0, d, lane);
+    float ds = 0.f;
+    if (j8 < cnt) {
+      const long long po = po_i + j0 + j8;
+      const float P = a.probs[po];
+      const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+      ds = P * (dp * scl - Di) * inv_denom;
+    }
+    block_axpy(gq, ds, a.K + (long long)(off + j0) * d, d, cnt, 0, d, lane);
+  }
+  // ---- key role: gK[i] = sum_{q>=i} dS_qi Q[q],  gV[i] = sum_{q>=i} Pd_qi gY[q]
+  for (int q0 = i; q0 < n; q0 += KB) {
+    const int cnt = min(KB, n - q0);
+    const float dp = block_dots(vt, a.gY + (long long)(off + q0) * d, d, cnt, 0, d, lane);
+    float ds = 0.f, pd = 0.f;
+    if (j8 < cnt) {
+      const int tq = off + q0 + j8;
+      const long long po = (long long)tq * L + i;
+      const float P = a.probs[po];
+      const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+      ds = P * (dp * scl - a.D[tq]) * inv_denom;
+      pd = P * scl;
+    }
+    block_axpy(gk, ds, a.Q + (long long)(off + q0) * d, d, cnt, 0, d, lane);
+    block_axpy(gv, pd, a.gY + (long long)(off + q0) * d, d, cnt, 0, d, lane);
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) {
+      a.gQ[(long long)tk * d + c] = gq[e];
+      a.gK[(long long)tk * d + c] = gk[e];
+      a.gV[(long long)tk * d + c] = gv[e];
+    }
+  }
+}
+
 // ---- backward: Q/K/V dgrad + LN1 backward --------------------------------------------------------------
 struct QkvBwdArgs {
   const float *gQ, *gK, *gV, *gY, *X, *mean1, *rstd1, *ln_g;
@@ -786,6 +920,121 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- backward: weight / bias / LayerNorm-parameter gradients of one block, ONE launch ------------------
+// dW[c_in][c_out] = sum_t act[t][c_in] * grad[t][c_out] is a [150 x T] x [T x 150] product whose contraction
+// runs over tokens.  TF32 mma.sync.m16n8k8: both operands are read straight from their natural [t][c] fp32
+// layout (cp.async double-buffered token tiles, row stride 168 words -> conflict-free fragment loads), no
+// transposes and no range scaling (8-bit exponent), 10-bit mantissa.  CTA (split, problem) owns a contiguous
+// range of token tiles and a full 160 x 160 fp32 accumulator in registers (8 warps x 5 x 5 mma tiles); the
+// `splits` partials are reduced afterwards in index order (k_reduce_partials) -> deterministic.
+// Problems 0..n_gemm-1: weight + bias gradients; problems n_gemm..: LayerNorm (beta, gamma) gradients
+// (act = LN input x, grad = dout, xhat rebuilt from mean / rstd).
+constexpr int WG_TK = 32;                     // tokens per staged tile
+constexpr int WG_LD = 168;                    // fp32 row stride (168 % 32 == 8)
+constexpr int WG_TILE = WG_TK * WG_LD;        // floats per operand tile
+constexpr size_t WGRAD_SMEM = sizeof(float) * 4 * WG_TILE;   // 2 stages x (act, grad) = 86 016 B
+constexpr int WG_MAXP = 8;
+struct WgradProb { const float *act, *grad, *mean, *rstd; float *out0, *out1; };   // GEMM: out0 = pW, out1 = pb; LN: out0 = pbeta, out1 = pgamma
+struct WgradArgs { WgradProb p[WG_MAXP]; int n_gemm, n_ln; const int* dT; int d; long long split_stride; };
+
+__device__ __forceinline__ uint32_t to_tf32(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void wg_stage(float* __restrict__ dst, const float* __restrict__ G, int t0, int T, int d) {
+  for (int idx = threadIdx.x; idx < WG_TK * (KP / 2); idx += NTHR) {
+    const int r = idx / (KP / 2), c = (idx % (KP / 2)) * 2;
+    const bool ok = (t0 + r < T) && (c < d);
+    const float* src = ok ? G + (long long)(t0 + r) * d + c : G;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst + r * WG_LD + c)), "l"(src), "r"(ok ? 8 : 0) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(16) float wsm[];
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + WG_TK - 1) / WG_TK;
+  const int chunk = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int tile_lo = blockIdx.x * chunk, tile_hi = min(ntiles, tile_lo + chunk);
+  const WgradProb pr = a.p[blockIdx.y];
+  const bool is_ln = (int)blockIdx.y >= a.n_gemm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;           // 5 m16 tiles (rows wm*80..) x 5 n8 tiles (cols wn*40..)
+  float acc[5][5][4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
+  float cs0 = 0.f, cs1 = 0.f;                        // column sums owned by thread tid < 160
+  if (tile_lo < tile_hi) {
+    wg_stage(wsm, pr.act, tile_lo * WG_TK, T, d);
+    wg_stage(wsm + WG_TILE, pr.grad, tile_lo * WG_TK, T, d);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    const int buf = (tile - tile_lo) & 1;
+    if (tile + 1 < tile_hi) {
+      wg_stage(wsm + (buf ^ 1) * 2 * WG_TILE, pr.act, (tile + 1) * WG_TK, T, d);
+      wg_stage(wsm + (buf ^ 1) * 2 * WG_TILE + WG_TILE, pr.grad, (tile + 1) * WG_TK, T, d);
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float* As = wsm + buf * 2 * WG_TILE;
+    const float* Bs = As + WG_TILE;
+    if (!is_ln) {
+#pragma unroll
+      for (int ks = 0; ks < WG_TK / 8; ++ks) {
+        const float* ar = As + (ks * 8 + t4) * WG_LD + wm * 80 + g;
+        const float* br = Bs + (ks * 8 + t4) * WG_LD + wn * 40 + g;
+        uint32_t bf[5][2];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { bf[j][0] = to_tf32(br[j * 8]); bf[j][1] = to_tf32(br[4 * WG_LD + j * 8]); }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const uint32_t a0 = to_tf32(ar[i * 16]), a1 = to_tf32(ar[i * 16 + 8]);
+          const uint32_t a2 = to_tf32(ar[4 * WG_LD + i * 16]), a3 = to_tf32(ar[4 * WG_LD + i * 16 + 8]);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+        }
+      }
+      if (tid < KP) {                                 // bias gradient: column sums of grad, token order
+#pragma unroll 8
+        for (int r = 0; r < WG_TK; ++r) cs0 += Bs[r * WG_LD + tid];
+      }
+    } else if (tid < KP) {                            // LayerNorm parameter gradients
+      const int t0 = tile * WG_TK;
+      const int rmax = min(WG_TK, T - t0);
+      for (int r = 0; r < rmax; ++r) {
+        const float gq = Bs[r * WG_LD + tid];
+        cs0 += gq;
+        cs1 += gq * ((As[r * WG_LD + tid] - pr.mean[t0 + r]) * pr.rstd[t0 + r]);
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const long long so = (long long)blockIdx.x * a.split_stride;
+  if (!is_ln) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int m = wm * 80 + i * 16 + g, n = wn * 40 + j * 8 + 2 * t4;
+        if (n < d) {
+          if (m < d) *reinterpret_cast<float2*>(pr.out0 + so + (long long)m * d + n) = make_float2(acc[i][j][0], acc[i][j][1]);
+          if (m + 8 < d) *reinterpret_cast<float2*>(pr.out0 + so + (long long)(m + 8) * d + n) = make_float2(acc[i][j][2], acc[i][j][3]);
+        }
+      }
+    if (tid < d) pr.out1[so + tid] = cs0;
+  } else if (tid < d) {
+    pr.out0[so + tid] = cs0;
+    pr.out1[so + tid] = cs1;
   }
 }
 

@@ -7,7 +7,8 @@ def main(path, out):
     names = [(r["Kernel Name"], float(r["Metric Value"]) / 1000.0, r.get("Grid Size", "")) for r in rows]
     g = [i for i, (n, _, _) in enumerate(names) if "k_gather_rows" in n]
     # one resident step = from one pair of gathers to the next pair
-    s, e = g[-4], g[-2]
+    starts = [i for k, i in enumerate(g) if k == 0 or g[k - 1] != i - 1]      # first gather of each pair
+    s, e = starts[-2], starts[-1]
     step = names[s:e]
     tot = sum(t for _, t, _ in step)
     agg = collections.OrderedDict()
