@@ -17,6 +17,17 @@
 //   MODE_DREP: same loop; dS (bf16) is staged in shared memory and a second MMA accumulates
 //              dRep[128, 160] in TMEM across the CTA's vocab tiles
 //   MODE_DE  : per vocab-tile CTA, loops over row tiles; second MMA accumulates dE[128, 160]
+//
+// Distillation rows (ADER.py:133-137) enter by LINEARITY, not inside the S-tile epilogues.  With
+// P = softmax(teacher) over the V_prev columns,  KD_i = lse_i(s[:V_prev]) - rep_i . u_i  and
+// dS_i = coef * (softmax(s_i[:V_prev]) - P_i),  where  u = P . E  ([M_e, V_prev] x [V_prev, d]).  So in the
+// three kernels above a distillation row is a label-free softmax row of width V_prev (no teacher traffic,
+// no extra exponentials), and the teacher contributes through two more tensor-core products on bf16 tiles
+// of Pc = coef * P (k_teacher_tiles: coalesced one-pass read of the fp32 teacher rows):
+//   MODE_TU  : uc = Pc . E partials over a vocabulary chunk (second-MMA datapath of DREP with the "dS" operand
+//              bulk-copied instead of computed)   -> loss dot = rep.uc / coef,  d_rep -= uc
+//   MODE_DE  : after its row-tile loop the CTA of a vocabulary tile < V_prev runs one more second-MMA per exemplar
+//              row tile with the A operand NEGATED in the instruction descriptor: dE[v] -= Pc^T . rep
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -32,7 +43,8 @@ constexpr int KSTEPS1 = KP / 16;              // 10 MMAs per S tile
 constexpr int KSTEPS2 = TILE / 16;            // 8 MMAs per gradient tile
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { MODE_FWD = 0, MODE_DREP = 1, MODE_DE = 2 };
+enum { MODE_FWD = 0, MODE_DREP = 1, MODE_DE = 2, MODE_TU = 3 };
+__host__ __device__ constexpr bool is_teach(int mode) { return mode >= MODE_TU; }
 
 struct TcArgs {
   const uint8_t* rep_tiles;     // [n_mtiles][TILE_BYTES]
@@ -52,6 +64,10 @@ struct TcArgs {
   float* grad_table;            // DE: grad + d (row of item 1), row stride d
   int d;
   int* err;                     // device error flag (barrier timeout)
+  // teacher products (MODE_TU, teacher tail of MODE_DE)
+  const uint8_t* pt_tiles;      // [n_et][n_vtp][DS_BYTES] bf16 coef_ex * softmax(teacher) tiles, dS layout
+  int x0_t, n_et, n_vtp, n_chunks_t;   // first row tile holding exemplar rows, their count, teacher vocab tiles, TU chunks
+  float* u_part;                // TU: [n_chunks_t][n_et*128][160]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,57 +156,48 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
 // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn, int a_neg = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_neg << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // per-row description of the loss (shared by all modes)
 struct RowInfo {
-  int kind;           // 0 none (row >= M), 1 one-hot CE over V, 2 KD over V_prev
+  int kind;           // 0 none (row >= M), 1 softmax row of width vlim (one-hot label, or label = -1 for distillation rows)
   int vlim;           // softmax width
   int label;          // 0-based column of the one-hot label (kind 1), else -1
   float coef;         // dS scale
   float lse2;         // lse * log2(e)  (backward)
-  float lset2;        // teacher lse * log2(e)
-  const float* trow;  // teacher row (kind 2)
 };
 __device__ __forceinline__ RowInfo row_info(const TcArgs& a, int gm, bool bwd) {
   // all column indices inside the kernel are LOCAL to this vocabulary shard: labels, softmax widths and the
   // teacher row pointer are shifted by v_off here (a label outside the shard simply never matches)
-  RowInfo r; r.kind = 0; r.vlim = 0; r.label = -1; r.coef = 0.f; r.lse2 = 0.f; r.lset2 = 0.f; r.trow = nullptr;
+  RowInfo r; r.kind = 0; r.vlim = 0; r.label = -1; r.coef = 0.f; r.lse2 = 0.f;
   if (gm >= a.M) return r;
   int vlim_g;
   if (gm < a.n_train) { r.kind = 1; vlim_g = a.V_total; r.label = a.pos[gm] - 1 - a.v_off; r.coef = a.coef_train; }
   else if (a.mode == 2) { r.kind = 1; vlim_g = a.V_total; r.label = a.ex_pos[gm - a.n_train] - 1 - a.v_off; r.coef = a.coef_ex; }
-  else {
-    const int e = gm - a.n_train;
-    r.kind = 2; vlim_g = a.V_prev; r.coef = a.coef_ex;
-    const long long tr = a.teacher_row ? a.teacher_row[e] : e;
-    r.trow = a.teacher + tr * a.teacher_ld + a.v_off;
-    r.lset2 = a.lse_t[e] * LOG2E;
-  }
+  else { r.kind = 1; vlim_g = a.V_prev; r.coef = a.coef_ex; }   // distillation row: softmax over V_prev, no label (teacher term: MODE_TU/TG)
   r.vlim = max(0, min(a.V, vlim_g - a.v_off));
   if (bwd) r.lse2 = a.lse[gm] * LOG2E;
   return r;
 }
 
 constexpr int NTHREADS = 320, NEPI = 256;
+constexpr int DE_LD = 164;     // fp32 row stride of the dE staging tile (164 % 32 == 4: conflict-free 16-byte row writes)
+static_assert(TILE * DE_LD * 4 <= 3 * TILE_BYTES, "dE staging tile must fit the streamed-tile ring");
+
+// Optional per-CTA timeline (debug builds only: -DADER_TC_TIMELINE): clock64 stamps of the pipeline roles.
+#ifdef ADER_TC_TIMELINE
+__device__ long long g_tl[3][192][64];
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TL(slot) do { if (blockIdx.x < 192) g_tl[MODE][blockIdx.x][slot] = gtimer(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
 // streamed-tile ring depth: the backward kernels free a stage only after the SECOND MMA of a tile, so two
 // stages expose the L2 latency of every tile (ncu: epilogue warps 41 % stalled on the S-tile barrier)
-__host__ __device__ constexpr int n_stages(int mode) { return mode == 0 ? 4 : 3; }
-
-// 32 consecutive teacher logits of one row (start column is a multiple of 32)
-__device__ __forceinline__ void load_teacher32(const float* __restrict__ p, bool vec4, float (&tv)[32]) {
-  if (vec4) {
-    const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { const float4 x = __ldg(p4 + q); tv[4 * q] = x.x; tv[4 * q + 1] = x.y; tv[4 * q + 2] = x.z; tv[4 * q + 3] = x.w; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) tv[i] = __ldg(p + i);
-  }
-}
+__host__ __device__ constexpr int n_stages(int mode) { return mode == MODE_FWD ? 4 : 3; }
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
@@ -205,15 +212,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   // barrier ids
-  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 5, B_TFULL = 9, B_TEMPTY = 11, B_DSFULL = 13, B_DSEMPTY = 15, B_ACC = 17;
+  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 5, B_TFULL = 9, B_TEMPTY = 11, B_DSFULL = 13, B_DSEMPTY = 15, B_ACC = 17, B_PFULL = 18;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ADER_TC_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x < 192) {
+    long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tl[MODE][blockIdx.x][0] = gt; g_tl[MODE][blockIdx.x][1] = gt;
+  }
+#endif
 
   // ---- work assignment -------------------------------------------------------------------
   int x_tile, y_lo, y_hi;      // stationary tile index, streamed tile range
   int chunk = 0;
   if (MODE == MODE_DE) { x_tile = blockIdx.x; y_lo = 0; y_hi = a.n_mtiles; }
-  else {
+  else if (MODE == MODE_TU) {
+    x_tile = a.x0_t + blockIdx.x % a.n_et; chunk = blockIdx.x / a.n_et;                            // exemplar row tile; vocab chunk
+    y_lo = (int)((long long)chunk * a.n_vtp / a.n_chunks_t);
+    y_hi = (int)((long long)(chunk + 1) * a.n_vtp / a.n_chunks_t);
+  } else {
     x_tile = blockIdx.x % a.n_mtiles; chunk = blockIdx.x / a.n_mtiles;
     y_lo = (int)((long long)chunk * a.n_vtiles / a.n_chunks);           // balanced split of the vocabulary tiles
     y_hi = (int)((long long)(chunk + 1) * a.n_vtiles / a.n_chunks);
@@ -221,6 +238,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   const int n_it = max(0, y_hi - y_lo);
   const uint8_t* gX = (MODE == MODE_DE ? a.e_tiles : a.rep_tiles) + (size_t)x_tile * TILE_BYTES;
   const uint8_t* gY = (MODE == MODE_DE ? a.rep_tiles : a.e_tiles);
+  // DE: teacher iterations appended after the row-tile loop (this vocabulary tile holds teacher columns)
+  const int n_tt = (MODE == MODE_DE && x_tile < a.n_vtp) ? a.n_et : 0;
 
   // ---- setup ---------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -228,9 +247,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
     for (int s = 0; s < NST; ++s) { mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), NEPI);
-      mbar_init(BAR(B_DSFULL + s), NEPI); mbar_init(BAR(B_DSEMPTY + s), 1);
+      mbar_init(BAR(B_DSFULL + s), is_teach(MODE) ? 1 : NEPI); mbar_init(BAR(B_DSEMPTY + s), 1);
     }
     mbar_init(BAR(B_ACC), 1);
+    mbar_init(BAR(B_PFULL), 1); mbar_init(BAR(B_PFULL + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t TMEM_COLS = (MODE == MODE_FWD) ? 256u : 512u;
@@ -243,28 +263,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t ACC_COL = 256;
+  if (threadIdx.x == 64) TL(2);
 
   if (warp == 0) {
     // ===== producer: one elected lane issues bulk copies ========================================
     if (lane == 0 && n_it > 0) {
-      load_tile(smem_u32(sX), gX, BAR(B_XFULL));
+      if (!is_teach(MODE)) load_tile(smem_u32(sX), gX, BAR(B_XFULL));
+      TL(3);
       for (int it = 0; it < n_it; ++it) {
         const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
         mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
         load_tile(smem_u32(sY + ys * TILE_BYTES), gY + (size_t)(y_lo + it) * TILE_BYTES, BAR(B_YFULL + ys));
+        if (is_teach(MODE)) {               // the "dS" operand is a stored tile of coef * softmax(teacher)
+          const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+          const size_t pt = (size_t)(x_tile - a.x0_t) * a.n_vtp + (y_lo + it);
+          mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+          mbar_expect_tx(BAR(B_DSFULL + s), DS_BYTES);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            bulk_g2s(smem_u32(sD + s * DS_BYTES) + i * (DS_BYTES / 16), a.pt_tiles + pt * DS_BYTES + i * (DS_BYTES / 16),
+                     DS_BYTES / 16, BAR(B_DSFULL + s));
+        }
+        if (it < 8) TL(8 + it);
+      }
+      for (int jt = 0; jt < n_tt; ++jt) {   // DE: rep tile of exemplar row tile jt + its teacher tile for this vocabulary tile
+        const int idx = n_it + jt;
+        const int ys = idx % NST; const uint32_t yph = (idx / NST) & 1;
+        mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
+        load_tile(smem_u32(sY + ys * TILE_BYTES), gY + (size_t)(a.x0_t + jt) * TILE_BYTES, BAR(B_YFULL + ys));
+        const int s = idx & 1; const uint32_t ph = (idx >> 1) & 1;
+        mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+        mbar_expect_tx(BAR(B_PFULL + s), DS_BYTES);
+        const size_t pt = (size_t)jt * a.n_vtp + x_tile;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          bulk_g2s(smem_u32(sD + s * DS_BYTES) + i * (DS_BYTES / 16), a.pt_tiles + pt * DS_BYTES + i * (DS_BYTES / 16),
+                   DS_BYTES / 16, BAR(B_PFULL + s));
       }
     }
+    __syncwarp();       // the CTA barrier below must be reached by converged warps
   } else if (warp == 1) {
     // ===== MMA issuer ===============================================================================
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t IDESC1 = make_idesc(128, 128, 0, 0);
-      constexpr uint32_t IDESC2 = (MODE == MODE_DE) ? make_idesc(128, KP, 1, 1) : make_idesc(128, KP, 0, 1);
+      constexpr bool DE_LIKE = (MODE == MODE_DE);
+      constexpr uint32_t IDESC2 = DE_LIKE ? make_idesc(128, KP, 1, 1) : make_idesc(128, KP, 0, 1);
       const uint32_t xa = smem_u32(sX);
       auto issue_s = [&](int it) {          // S[buf] = rep_tile . e_tile^T
         const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
         const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
         mbar_wait(BAR(B_YFULL + ys), yph, a.err);
+        if (it < 8) TL(48 + it);
         mbar_wait(BAR(B_TEMPTY + s), ph ^ 1, a.err);
+        if (it < 8) TL(16 + it);
         tc_fence_after();
         const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
         const uint32_t A = (MODE == MODE_DE) ? ya : xa;     // rows of S = logits rows (rep)
@@ -275,13 +326,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
         if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + ys));
         umma_commit(BAR(B_TFULL + s));
       };
-      mbar_wait(BAR(B_XFULL), 0, a.err);
-      issue_s(0);
+      if (!is_teach(MODE)) { mbar_wait(BAR(B_XFULL), 0, a.err); issue_s(0); }
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_s(it + 1);
+        if (!is_teach(MODE) && it + 1 < n_it) issue_s(it + 1);
         if (MODE != MODE_FWD) {
           const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
           const int ys = it % NST;
+          if (is_teach(MODE)) mbar_wait(BAR(B_YFULL + ys), (it / NST) & 1, a.err);
           mbar_wait(BAR(B_DSFULL + s), ph, a.err);
           tc_fence_after();
           const uint32_t da = smem_u32(sD + s * DS_BYTES);
@@ -290,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
           for (int k = 0; k < KSTEPS2; ++k) {
             // dS tile: core (vg, mg) at (vg*16 + mg)*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=2048,
             // k-step = 2 v-groups = 4096 B.  DE: A MN-major (M=v, K=m): SBO=2048, LBO=128, k-step = 256 B.
-            const uint64_t ad = (MODE == MODE_DE) ? make_desc(da + k * 256, 128, 2048) : make_desc(da + k * 4096, 2048, 128);
+            const uint64_t ad = DE_LIKE ? make_desc(da + k * 256, 128, 2048) : make_desc(da + k * 4096, 2048, 128);
             // streamed T128 tile as MN-major B (N = feature, K = tile row): SBO=2048, LBO=128, k-step = 256 B
             const uint64_t bd = make_desc(ya + k * 256, 128, 2048);
             umma_bf16(tmem + ACC_COL, ad, bd, IDESC2, (it > 0 || k > 0));
@@ -299,8 +350,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
           umma_commit(BAR(B_DSEMPTY + s));
         }
       }
+      if (MODE == MODE_DE) {                // dE[v] -= Pc^T . rep over the exemplar row tiles (A negated)
+        constexpr uint32_t IDESC2N = make_idesc(128, KP, 1, 1, 1);
+        uint32_t pph[2] = {0u, 0u};
+        for (int jt = 0; jt < n_tt; ++jt) {
+          const int idx = n_it + jt;
+          const int ys = idx % NST; const int s = idx & 1;
+          mbar_wait(BAR(B_YFULL + ys), (idx / NST) & 1, a.err);
+          mbar_wait(BAR(B_PFULL + s), pph[s], a.err); pph[s] ^= 1u;
+          tc_fence_after();
+          const uint32_t da = smem_u32(sD + s * DS_BYTES);
+          const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KSTEPS2; ++k)
+            umma_bf16(tmem + ACC_COL, make_desc(da + k * 256, 128, 2048), make_desc(ya + k * 256, 128, 2048), IDESC2N, 1u);
+          umma_commit(BAR(B_YEMPTY + ys));
+          umma_commit(BAR(B_DSEMPTY + s));
+        }
+      }
       if (MODE != MODE_FWD) umma_commit(BAR(B_ACC));
     }
+    __syncwarp();       // the CTA barrier below must be reached by converged warps
   } else {
     // ===== epilogue: TMEM lane = logits row ===========================================================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
@@ -310,9 +380,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
     RowInfo ri;
     float mx = -INFINITY, sum = 0.f, lab = 0.f, dot = 0.f;
     RowInfo ri_next;
-    if (MODE != MODE_DE) ri = row_info(a, x_tile * TILE + row, MODE != MODE_FWD);
+    if (is_teach(MODE)) { ri = RowInfo(); ri_next = RowInfo(); }
+    else if (MODE != MODE_DE) ri = row_info(a, x_tile * TILE + row, MODE != MODE_FWD);
     else ri_next = row_info(a, y_lo * TILE + row, true);
-    for (int it = 0; it < n_it; ++it) {
+    for (int it = 0; it < (is_teach(MODE) ? 0 : n_it); ++it) {
       const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
       int v0;
       if (MODE == MODE_DE) {          // row description of the NEXT row tile is fetched one iteration ahead
@@ -321,6 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
         v0 = x_tile * TILE;
       } else v0 = (y_lo + it) * TILE;
       mbar_wait(BAR(B_TFULL + s), ph, a.err);
+      if (threadIdx.x == 64 && it < 8) TL(24 + it);
       tc_fence_after();
       // this thread's 64 columns of the S tile -> registers, then hand the TMEM buffer back at once so the
       // next S tile's MMAs overlap with the exponentials below
@@ -356,18 +428,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (vb0 + c * 32 + i == ri.label) lab = __uint_as_float(r[c][i]);
           }
-          if (ri.kind == 2) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float tv[32];
-              load_teacher32(ri.trow + vb0 + c * 32, a.teacher_vec4 != 0, tv);
-              float d4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                d4[i & 3] = fmaf(ex2(fmaf(tv[i], LOG2E, -ri.lset2)), __uint_as_float(r[c][i]), d4[i & 3]);
-              dot += (d4[0] + d4[1]) + (d4[2] + d4[3]);
-            }
-          }
         } else if (ri.kind != 0 && vb0 < ri.vlim) {               // boundary tile: per-element checks
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -387,7 +447,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
                 const float sv = __uint_as_float(r[c][i]);
                 sum += ex2(fmaf(sv, LOG2E, -nm2));
                 if (v == ri.label) lab = sv;
-                if (ri.kind == 2) dot = fmaf(ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)), sv, dot);
               }
             }
           }
@@ -400,19 +459,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
           const int vb = vb0 + c * 32;
           float g[32];
           if (full) {
-            if (ri.kind == 1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
-              if (ri.label >= vb && ri.label < vb + 32) {
+            for (int i = 0; i < 32; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+            if (ri.label >= vb && ri.label < vb + 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
-              }
-            } else {
-              float tv[32];
-              load_teacher32(ri.trow + vb, a.teacher_vec4 != 0, tv);
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                g[i] = ri.coef * (ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2)) - ex2(fmaf(tv[i], LOG2E, -ri.lset2)));
+              for (int i = 0; i < 32; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
             }
           } else {
 #pragma unroll
@@ -421,8 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
               float gv = 0.f;
               if (ri.kind != 0 && v < ri.vlim) {
                 const float p = ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
-                if (ri.kind == 1) gv = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
-                else gv = ri.coef * (p - ex2(fmaf(ri.trow[v], LOG2E, -ri.lset2)));
+                gv = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
               }
               g[i] = gv;
             }
@@ -442,6 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
         fence_async_smem();                    // generic-proxy writes -> visible to the MMA (async proxy)
         mbar_arrive(BAR(B_DSFULL + s));
       }
+      if (threadIdx.x == 64 && it < 8) TL(32 + it);
     }
     if (MODE == MODE_FWD) {
       const int gm = x_tile * TILE + row;
@@ -456,28 +507,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
       for (int c4 = half; c4 < KP / 32; c4 += 2) {
         uint32_t r[32];
         tmem_ld32(tmem + tlane + ACC_COL + c4 * 32, r);
-        if (MODE == MODE_DREP) {
-          float* o = a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP + c4 * 32;
+        if (MODE == MODE_DREP || MODE == MODE_TU) {
+          float* o = (MODE == MODE_DREP)
+                         ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP + c4 * 32
+                         : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE + row) * KP + c4 * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                                             __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        } else {
-          const int v = x_tile * TILE + row;
-          if (v < a.V) {
-            float* o = a.grad_table + (size_t)v * a.d + c4 * 32;
+        } else {                              // DE: stage the [128 v, 160] tile in the (now idle) Y stages
+          float* stg = reinterpret_cast<float*>(sY) + row * DE_LD + c4 * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c4 * 32 + i < a.d) o[i] = __uint_as_float(r[i]);
-          }
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(stg + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                              __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+      }
+      if (MODE == MODE_DE) {                  // ... and write whole table rows (d floats, contiguous) per warp
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+        const float* stg = reinterpret_cast<const float*>(sY);
+        const int ew = warp - 2;
+        for (int rr = ew; rr < TILE; rr += NEPI / 32) {
+          const int v = x_tile * TILE + rr;
+          if (v >= a.V) break;
+          float2* o = reinterpret_cast<float2*>(a.grad_table + (size_t)v * a.d);
+          for (int c2 = lane; c2 < a.d / 2; c2 += 32) o[c2] = *reinterpret_cast<const float2*>(stg + rr * DE_LD + 2 * c2);
         }
       }
       tc_fence_before();
-    } else if (MODE == MODE_DREP) {           // empty chunk: its partial must still be defined
-      float* o = a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP;
+    } else if (MODE == MODE_DREP || MODE == MODE_TU) {           // empty chunk: its partial must still be defined
+      float* o = (MODE == MODE_DREP) ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP
+                                     : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE + row) * KP;
       for (int i = half * (KP / 2); i < (half + 1) * (KP / 2); ++i) o[i] = 0.f;
     }
   }
+  if (threadIdx.x == 64) TL(40);
   __syncthreads();
+  if (threadIdx.x == 0) TL(41);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -535,9 +601,69 @@ __global__ void __launch_bounds__(256) k_teacher_lse(const float* __restrict__ t
   if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < 8; ++w) tot += sh[w]; lse_t[e] = mx + logf(tot); }
 }
 
-// merge the per-chunk online-softmax partials: lse[M], row_loss[M]
+// bf16 tiles of Pc = coef * softmax(teacher) in the dS layout (core (vg, mg) at (vg*16 + mg)*128): tile (et, vt) covers
+// rows (x0 + et)*128 .. +127 of the step (zeros for non-exemplar rows) and LOCAL columns vt*128 .. +127 (teacher
+// column = v_off + local column; zeros beyond V_prev).  Warp per 16 rows, one 16-byte load per lane and row, all
+// 16 loads of a warp in flight together: the teacher is streamed once, coalesced.
+__global__ void __launch_bounds__(256) k_teacher_tiles(const float* __restrict__ teacher, const int* __restrict__ teacher_row,
+                                                       long long ld, int vec4, const float* __restrict__ lse_t, int n_train, int M,
+                                                       int V_prev, int v_off, int x0, int n_vtp, float coef,
+                                                       uint8_t* __restrict__ tiles) {
+  const int vt = blockIdx.x, et = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* tile = tiles + ((size_t)et * n_vtp + vt) * DS_BYTES;
+  const int vl = vt * TILE + lane * 4;                 // local column of this lane's 4 values
+  const int vg = v_off + vl;                           // teacher column
+  float4 t[16]; float l[16];
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int m = warp * 16 + rr;
+    const int e = (x0 + et) * TILE + m - n_train;
+    t[rr] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); l[rr] = 0.f;
+    if (e >= 0 && e + n_train < M && vg < V_prev) {
+      const float* row = teacher + (long long)(teacher_row ? teacher_row[e] : e) * ld;
+      l[rr] = lse_t[e];
+      if (vec4 && vg + 3 < V_prev) t[rr] = __ldg(reinterpret_cast<const float4*>(row + vg));
+      else {
+        t[rr].x = row[vg];
+        if (vg + 1 < V_prev) t[rr].y = row[vg + 1];
+        if (vg + 2 < V_prev) t[rr].z = row[vg + 2];
+        if (vg + 3 < V_prev) t[rr].w = row[vg + 3];
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int m = warp * 16 + rr;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(coef * expf(t[rr].x - l[rr]), coef * expf(t[rr].y - l[rr]));   // exp(-inf) = 0
+    const __nv_bfloat162 b = __floats2bfloat162_rn(coef * expf(t[rr].z - l[rr]), coef * expf(t[rr].w - l[rr]));
+    uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(tile + ((lane >> 1) * 16 + (m >> 3)) * 128 + (m & 7) * 16 + (lane & 1) * 8) = pk;
+  }
+}
+
+// uc[n_et*128, 160] = sum over chunks of the MODE_TU partials (fixed order); udot[row] = rep_row . uc_row.
+// CTA (KP threads) per row.
+__global__ void __launch_bounds__(KP) k_reduce_u(const float* __restrict__ part, int n_chunks, int rows, float* __restrict__ u,
+                                                 const float* __restrict__ rep, int x0, int M, int d, float* __restrict__ udot) {
+  __shared__ float sh[KP / 32];
+  const int r = blockIdx.x, c = threadIdx.x;
+  float s = 0.f;
+  for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows + r) * KP + c];
+  u[(size_t)r * KP + c] = s;
+  const int gm = x0 * TILE + r;
+  float p = (gm < M && c < d) ? s * rep[(size_t)gm * d + c] : 0.f;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  if ((c & 31) == 0) sh[c >> 5] = p;
+  __syncthreads();
+  if (c == 0) { float t = 0.f; for (int w = 0; w < KP / 32; ++w) t += sh[w]; udot[r] = t; }
+}
+
+// merge the per-chunk online-softmax partials: lse[M], row_loss[M].  Distillation rows: dot = rep_i . u_i.
 __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chunks, int n_train, int mode,
-                              float* __restrict__ lse, float* __restrict__ row_loss, float* __restrict__ local_out) {
+                              float* __restrict__ lse, float* __restrict__ row_loss, float* __restrict__ local_out,
+                              const float* __restrict__ udot, int x0, float coef_ex) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   float mx = -INFINITY;
@@ -546,8 +672,10 @@ __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chun
   for (int c = 0; c < n_chunks; ++c) {
     const float4 s = *reinterpret_cast<const float4*>(stats + ((size_t)c * M + i) * 4);
     if (s.x > -INFINITY) sum += s.y * expf(s.x - mx);
-    lab += s.z; dot += s.w;
+    lab += s.z;
   }
+  // distillation rows: sum_j softmax(t)_j s_ij = rep_i . (P.E)_i = rep_i . uc_i / coef  (coef = 0: the term has zero weight)
+  if (i >= n_train && mode == 1 && udot && coef_ex != 0.f) dot = udot[i - x0 * TILE] / coef_ex;
   if (local_out) {      // vocab-parallel: hand the shard's (max, sumexp, label logit, kd dot) to the host-side all-reduce
     *reinterpret_cast<float4*>(local_out + (size_t)i * 4) = make_float4(mx, sum, lab, dot);
     return;
@@ -558,14 +686,15 @@ __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chun
   row_loss[i] = kd ? l - dot : l - lab;
 }
 
-// d_rep[M, d] = sum over chunks of the padded partials
+// d_rep[M, d] = sum over chunks of the padded partials  (- uc = coef_ex * P.E for distillation rows)
 __global__ void k_reduce_drep(const float* __restrict__ part, int n_chunks, int rows_pad, int M, int d,
-                              float* __restrict__ d_rep) {
+                              float* __restrict__ d_rep, const float* __restrict__ u, int x0, int n_train) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * d) return;
   const int i = (int)(idx / d), c = (int)(idx % d);
   float s = 0.f;
   for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows_pad + i) * KP + c];
+  if (u && i >= n_train) s -= u[(size_t)(i - x0 * TILE) * KP + c];
   d_rep[idx] = s;
 }
 
@@ -580,9 +709,10 @@ namespace ader { int launch_loss_reduce(const float* row_loss, int n_train, int 
                                         int den_train, int den_ex); }
 
 struct TcWs {
-  uint8_t *rep_tiles, *e_tiles;
-  float *stats, *lse, *lse_t, *drep_part;
+  uint8_t *rep_tiles, *e_tiles, *pt_tiles;
+  float *stats, *lse, *lse_t, *drep_part, *u_part, *u, *udot;
   int* err;
+  int x0_t, n_et, n_vtp, n_chunks_t;       // teacher products (0 tiles when the step has no distillation rows)
   size_t bytes;
 };
 static int tc_chunks(int n_mtiles, int n_vtiles) {
@@ -597,16 +727,26 @@ static int tc_chunks(int n_mtiles, int n_vtiles) {
   }
   return best;
 }
-static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, char* base) {
+// V = columns of this shard (local), Vp_local = how many of them are teacher columns (0 = no distillation)
+static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, int Vp_local, char* base) {
   TcWs w; size_t o = 0;
   auto take = [&](size_t n) { char* p = base ? base + o : nullptr; o += align_up(n); return p; };
   const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
+  const bool kd = n_ex > 0 && Vp_local > 0;
+  w.x0_t = kd ? (M - n_ex) / TILE : 0;
+  w.n_et = kd ? (M - 1) / TILE - w.x0_t + 1 : 0;
+  w.n_vtp = kd ? cdiv(Vp_local, TILE) : 0;
+  w.n_chunks_t = kd ? tc_chunks(w.n_et, w.n_vtp) : 0;
   w.rep_tiles = (uint8_t*)take((size_t)nm * TILE_BYTES);
   w.e_tiles = (uint8_t*)take((size_t)nv * TILE_BYTES);
   w.stats = (float*)take(sizeof(float) * 4 * (size_t)nc * 2 * M);
   w.lse = (float*)take(sizeof(float) * M);
   w.lse_t = (float*)take(sizeof(float) * (n_ex > 0 ? n_ex : 1));
   w.drep_part = (float*)take(sizeof(float) * (size_t)nc * nm * TILE * KP);
+  w.pt_tiles = (uint8_t*)take((size_t)w.n_et * w.n_vtp * DS_BYTES + 16);
+  w.u_part = (float*)take(sizeof(float) * ((size_t)w.n_chunks_t * w.n_et * TILE * KP + 4));
+  w.u = (float*)take(sizeof(float) * ((size_t)w.n_et * TILE * KP + 4));
+  w.udot = (float*)take(sizeof(float) * ((size_t)w.n_et * TILE + 4));
   w.err = (int*)take(sizeof(int) * 4);
   w.bytes = o;
   return w;
@@ -614,7 +754,30 @@ static TcWs carve_tc(const AderModel* m, int M, int V, int n_ex, char* base) {
 
 extern "C" size_t ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a) {
   if (check_model(m) || !a || a->M <= 0 || a->V <= 0) return 0;
-  return carve_tc(m, a->M, a->V, a->n_ex, nullptr).bytes;
+  return carve_tc(m, a->M, a->V, a->n_ex, a->mode == 1 ? a->V_prev : 0, nullptr).bytes;
+}
+
+// launches shared by the single-GPU and vocab-parallel entry points -----------------------------------------------
+static void set_tc_attrs() {
+  static bool attr_set = false;
+  if (attr_set) return;
+  const int smem_fwd = (1 + n_stages(MODE_FWD)) * TILE_BYTES + 256, smem_bwd = (1 + n_stages(MODE_DREP)) * TILE_BYTES + 2 * DS_BYTES + 256;
+  cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
+  cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+  cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+  cudaFuncSetAttribute(k_tc_logits<MODE_TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+  attr_set = true;
+}
+constexpr int SMEM_FWD = (1 + n_stages(MODE_FWD)) * TILE_BYTES + 256;
+constexpr int SMEM_BWD = (1 + n_stages(MODE_DREP)) * TILE_BYTES + 2 * DS_BYTES + 256;
+// teacher statistics + tiles + u = P.E  (needs rep / E tiles packed; fills w.u)
+static void launch_teacher_u(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, const float* rep, int d,
+                             cudaStream_t st) {
+  k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
+  k_teacher_tiles<<<dim3(w.n_vtp, w.n_et), 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, t.teacher_vec4, w.lse_t,
+                                                        a->n_train, a->M, a->V_prev, v_off, w.x0_t, w.n_vtp, t.coef_ex, w.pt_tiles);
+  k_tc_logits<MODE_TU><<<w.n_et * w.n_chunks_t, NTHREADS, SMEM_BWD, st>>>(t);
+  k_reduce_u<<<w.n_et * TILE, KP, 0, st>>>(w.u_part, w.n_chunks_t, w.n_et * TILE, w.u, rep, w.x0_t, a->M, d, w.udot);
 }
 
 extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
@@ -634,22 +797,14 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int d = m->d, M = a->M, V = a->V;
-  TcWs w = carve_tc(m, M, V, a->n_ex, (char*)ws);
+  const bool kd = a->n_ex > 0 && a->mode == 1;
+  TcWs w = carve_tc(m, M, V, a->n_ex, kd ? a->V_prev : 0, (char*)ws);
   const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
-
-  static bool attr_set = false;
-  const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256, smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
-    cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
-    cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
-    attr_set = true;
-  }
+  const int smem_fwd = SMEM_FWD, smem_bwd = SMEM_BWD;
+  set_tc_attrs();
   cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
   k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
   k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + d, d, V, d, nv, w.e_tiles);
-  const bool kd = a->n_ex > 0 && a->mode == 1;
-  if (kd) k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
   ADER_CHECK_LAUNCH("tc pack");
 
   TcArgs t;
@@ -661,14 +816,18 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0)) ? 1 : 0;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
+  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part;
 
+  if (kd) launch_teacher_u(a, w, t, 0, rep, d, st);
   k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
-  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss, nullptr);
+  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss, nullptr,
+                                              kd ? w.udot : nullptr, w.x0_t, t.coef_ex);
   if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
     k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
-    k_reduce_drep<<<cdiv((long long)M * d, 256), 256, 0, st>>>(w.drep_part, nc, nm * TILE, M, d, d_rep);
+    k_reduce_drep<<<cdiv((long long)M * d, 256), 256, 0, st>>>(w.drep_part, nc, nm * TILE, M, d, d_rep,
+                                                               kd ? w.u : nullptr, w.x0_t, a->n_train);
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {
@@ -679,26 +838,29 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
 }
 
 
+#ifdef ADER_TC_TIMELINE
+extern "C" int32_t ader_debug_tc_timeline(long long* out) {
+  cudaDeviceSynchronize();
+  return (int32_t)cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));
+}
+#endif
+
 // ---- vocab-parallel variant: this rank owns logits columns [v_lo, v_hi) ---------------------
+static int vp_teacher_cols(const AderLossArgs* a, int v_lo, int v_hi) {      // teacher columns inside this shard
+  if (!(a->n_ex > 0 && a->mode == 1)) return 0;
+  const int hi = a->V_prev < v_hi ? a->V_prev : v_hi;
+  return hi > v_lo ? hi - v_lo : 0;
+}
 static int vp_setup(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, int v_lo, int v_hi,
                     void* ws, cudaStream_t st, TcWs& w, TcArgs& t, bool pack) {
   const int d = m->d, M = a->M, Vl = v_hi - v_lo;
-  w = carve_tc(m, M, Vl, a->n_ex, (char*)ws);
+  w = carve_tc(m, M, Vl, a->n_ex, vp_teacher_cols(a, v_lo, v_hi), (char*)ws);
   const int nm = cdiv(M, TILE), nv = cdiv(Vl, TILE), nc = tc_chunks(nm, nv);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256, smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
-    cudaFuncSetAttribute(k_tc_logits<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd);
-    cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
-    cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
-    attr_set = true;
-  }
+  set_tc_attrs();
   if (pack) {
     cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
     k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
     k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + (size_t)(1 + v_lo) * d, d, Vl, d, nv, w.e_tiles);
-    if (a->n_ex > 0 && a->mode == 1)
-      k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
   }
   t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = Vl; t.V_total = a->V; t.v_off = v_lo;
   t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
@@ -706,9 +868,11 @@ static int vp_setup(const AderModel* m, const float* theta, const float* rep, co
   t.coef_train = a->n_train > 0 ? 1.0f / (float)(a->n_train_global > 0 ? a->n_train_global : a->n_train) : 0.f;
   t.coef_ex = a->n_ex > 0 ? a->lambda_ / (float)(a->n_ex_global > 0 ? a->n_ex_global : a->n_ex) : 0.f;
   t.pos = a->pos; t.ex_pos = a->ex_pos; t.teacher = a->teacher; t.teacher_row = a->teacher_row; t.teacher_ld = a->teacher_ld;
-  t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0)) ? 1 : 0;
+  t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0) && v_lo % 4 == 0) ? 1 : 0;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = nullptr;
   t.d = d; t.err = w.err;
+  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part;
+  if (pack && w.n_et > 0) launch_teacher_u(a, w, t, v_lo, rep, d, st);
   return 0;
 }
 
@@ -724,7 +888,7 @@ static int vp_check(const AderModel* m, const AderLossArgs* a, int v_lo, int v_h
 
 extern "C" size_t ader_loss_tc_vp_ws_bytes(const AderModel* m, const AderLossArgs* a, int32_t v_lo, int32_t v_hi) {
   if (check_model(m) || !a || a->M <= 0 || v_hi <= v_lo) return 0;
-  return carve_tc(m, a->M, v_hi - v_lo, a->n_ex, nullptr).bytes;
+  return carve_tc(m, a->M, v_hi - v_lo, a->n_ex, vp_teacher_cols(a, v_lo, v_hi), nullptr).bytes;
 }
 
 extern "C" int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
@@ -734,9 +898,9 @@ extern "C" int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, c
   cudaStream_t st = (cudaStream_t)stream;
   TcWs w; TcArgs t;
   vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, true);
-  const int smem_fwd = (1 + n_stages(0)) * TILE_BYTES + 256;
-  k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_fwd, st>>>(t);
-  k_merge_stats<<<cdiv(a->M, 128), 128, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats);
+  k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, SMEM_FWD, st>>>(t);
+  k_merge_stats<<<cdiv(a->M, 128), 128, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats,
+                                                 w.n_et > 0 ? w.udot : nullptr, w.x0_t, t.coef_ex);
   ADER_CHECK_LAUNCH("loss_tc_vp_fwd");
   return 0;
 }
@@ -751,10 +915,11 @@ extern "C" int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, c
   vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, false);     // tiles were packed by the forward call
   t.lse = lse;
   t.grad_table = grad ? grad + (size_t)(1 + v_lo) * m->d : nullptr;
-  const int smem_bwd = (1 + n_stages(1)) * TILE_BYTES + 2 * DS_BYTES + 256;
+  const int smem_bwd = SMEM_BWD;
   if (d_rep_partial) {
     k_tc_logits<MODE_DREP><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_bwd, st>>>(t);
-    k_reduce_drep<<<cdiv((long long)a->M * m->d, 256), 256, 0, st>>>(w.drep_part, t.n_chunks, t.n_mtiles * TILE, a->M, m->d, d_rep_partial);
+    k_reduce_drep<<<cdiv((long long)a->M * m->d, 256), 256, 0, st>>>(w.drep_part, t.n_chunks, t.n_mtiles * TILE, a->M, m->d, d_rep_partial,
+                                                                     w.n_et > 0 ? w.u : nullptr, w.x0_t, a->n_train);
   }
   if (grad) k_tc_logits<MODE_DE><<<t.n_vtiles, NTHREADS, smem_bwd, st>>>(t);
   ADER_CHECK_LAUNCH("loss_tc_vp_bwd");
