@@ -53,8 +53,8 @@ SIGNATURES = {
     "ader_encoder_ws_slot": (C.c_int64, [_MP, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "ader_encoder_fwd": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_float, C.c_uint64, _P]),
     "ader_encoder_bwd": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, C.c_uint64, _P]),
-    "ader_encoder_fwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_float, C.c_uint64, _P]),
-    "ader_encoder_bwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, C.c_uint64, _P]),
+    "ader_encoder_fwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_float, C.c_uint64, _P, _P]),
+    "ader_encoder_bwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_float, C.c_uint64, _P, _P]),
     "ader_loss_ws_bytes": (C.c_size_t, [_MP, C.POINTER(AderLossArgs)]),
     "ader_loss_fwd_bwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P]),
     "ader_loss_tc_ws_bytes": (C.c_size_t, [_MP, C.POINTER(AderLossArgs)]),

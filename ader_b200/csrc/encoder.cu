@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn_bwd(const float* __restric
 // small elementwise helpers
 // ------------------------------------------------------------------------------------------
 // out[e] = in[e] * dropmask(site, e)   (gradient of an output-dropout site)
-__global__ void k_apply_drop(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ dT,
+__global__ void k_apply_drop(const float* in, float* out, const int* __restrict__ dT,
                              int d, float p, uint64_t seed, uint32_t site) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)(*dT) * d) return;
@@ -582,7 +582,9 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, long long s
 // position-table gradient: dP[p,c] = sum over rows having position p of dx0[token(r,p), c]
 __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__ row_len,
                            const int* __restrict__ row_off, int M, int L, int d,
-                           float drop_p, uint64_t seed, float* __restrict__ gpos, long long split_stride) {
+                           float drop_p, uint64_t seed0, const int* __restrict__ d_step, float* __restrict__ gpos,
+                           long long split_stride) {
+  const uint64_t seed = seed0 + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
   // grid (L, splits): CTA (p, s) sums the rows of chunk s that have position p into partial slot s.
   // blockDim = (ceil32(d), PG_LANES): thread (c, k) sums rows lo+k, lo+k+PG_LANES, ...; lanes reduced in fixed order.
   __shared__ float part[PG_LANES][256];
@@ -704,8 +706,9 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ ke
 // warp per CH sorted positions; the warp owning a segment head sums the whole segment.
 __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys, const int* __restrict__ vals,
                                                     const int* __restrict__ dT, const float* __restrict__ gx,
-                                                    int d, float scale, float drop_p, uint64_t seed,
-                                                    float* __restrict__ gtable) {
+                                                    int d, float scale, float drop_p, uint64_t seed0,
+                                                    const int* __restrict__ d_step, float* __restrict__ gtable) {
+  const uint64_t seed = seed0 + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
   constexpr int CH = 4;
   const int T = *dT;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -795,14 +798,17 @@ static int run_wgrad(cudaStream_t st, const float* act, const float* grad, float
 }
 
 // Tail shared by both encoder paths: split-K partials -> dense gradients, position table, item-table scatter.
+// gX must already carry the embedding-dropout mask (site 0): the callers apply it once when they produce gX, so
+// the position-table reduction and the scatter do not re-hash every element.
 static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
-                               int M, int Tcap, float p, uint64_t seed, float* grad, cudaStream_t st) {
+                               int M, int Tcap, float* grad, cudaStream_t st) {
+  const float p = 0.f; const uint64_t seed = 0; const int* d_step = nullptr;
   const int d = m->d, L = m->maxlen;
   const int* dT = w.row_off + M;
   const long long PS = l.dense_count();
   const int ln_threads = ((d + 31) / 32) * 32;
   // position table (ADER.py:41-52): per-row-chunk partials into the first L*d entries of the split slots
-  k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, g.partial, PS);
+  k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, d_step, g.partial, PS);
   // dense parameter gradients (position table included): reduce the split partials in fixed order
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, st>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
   // item-table scatter (modules.py:127-130)
@@ -819,7 +825,7 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
       kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
     }
     k_seg_reduce<<<cdiv((long long)cdiv(Tcap, 4) * 32, 256), 256, 0, st>>>(kin, vin, dT, gX, d, sqrtf((float)d), p, seed,
-                                                                           grad + l.off_table);
+                                                                           d_step, grad + l.off_table);
   }
   return 0;
 }
@@ -982,7 +988,8 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
     float* t = gX; gX = gXin; gXin = t;
   }
 
-  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, p, seed, grad, st)) return e;
+  if (p > 0.f) k_apply_drop<<<el_grid, 256, 0, st>>>(gX, gX, dT, d, p, seed, 0u);   // x0 = drop(emb) (ADER.py:55)
+  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, grad, st)) return e;
   ADER_CHECK_LAUNCH("encoder_bwd/embedding");
   return 0;
 }
@@ -1045,7 +1052,7 @@ static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
 
 extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
-                                       void* stream) {
+                                       const int32_t* d_step, void* stream) {
   if (int e = check_model(m)) return e;
   if (int e = fused_check(m)) return e;
   ADER_CHECK_ARG(theta && ids && ws && rep, "encoder_fwd_tc: NULL pointer");
@@ -1076,7 +1083,7 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
     qa.X = X; qa.Xw = X; qa.embed = (b == 0);
     qa.table = theta + l.off_table; qa.pos_table = theta + l.off_pos;
     qa.tok_row = w.tok_row; qa.tok_id = w.tok_id; qa.row_len = w.row_len; qa.row_off = w.row_off;
-    qa.sqrt_d = sqrtf((float)d); qa.drop_p = dropout_rate; qa.seed = seed;
+    qa.sqrt_d = sqrtf((float)d); qa.drop_p = dropout_rate; qa.seed = seed; qa.d_step = d_step;
     qa.ln_b = P + l.ln1b; qa.ln_g = P + l.ln1g; qa.Q1 = Q1; qa.mean = w.mean1[b]; qa.rstd = w.rstd1[b];
     qa.Wq = shadow_of(w, b, 0, 0); qa.Wk = shadow_of(w, b, 1, 0); qa.Wv = shadow_of(w, b, 2, 0);
     qa.bq = P + l.bq; qa.bk = P + l.bk; qa.bv = P + l.bv;
@@ -1087,13 +1094,13 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
     aa.Q = Qp; aa.K = Kp; aa.V = Vp; aa.Q1 = Q1; aa.tok_row = w.tok_row; aa.row_off = w.row_off;
     aa.probs = w.probs[b]; aa.Y = Y; aa.Z = Z; aa.mean2 = w.mean2[b]; aa.rstd2 = w.rstd2[b];
     aa.ln_b = P + l.ln2b; aa.ln_g = P + l.ln2g; aa.dT = dT; aa.d = d; aa.nh = m->num_heads; aa.L = L; aa.Tcap = Tcap;
-    aa.drop_p = dropout_rate; aa.seed = seed; aa.site = 1u + 3u * b;
+    aa.drop_p = dropout_rate; aa.seed = seed; aa.d_step = d_step; aa.site = 1u + 3u * b;
     fz::k_attn_ln_fwd<<<warp_grid, 256, 0, st>>>(aa);
 
     fz::FfnFwdArgs fa;
     fa.Z = Z; fa.H = H; fa.Xn = Xn; fa.W1 = shadow_of(w, b, 3, 0); fa.W2 = shadow_of(w, b, 4, 0);
     fa.b1 = P + l.b1; fa.b2 = P + l.b2; fa.dT = dT; fa.d = d;
-    fa.drop_p = dropout_rate; fa.seed = seed; fa.site1 = 2u + 3u * b; fa.site2 = 3u + 3u * b;
+    fa.drop_p = dropout_rate; fa.seed = seed; fa.d_step = d_step; fa.site1 = 2u + 3u * b; fa.site2 = 3u + 3u * b;
     fz::k_ffn_fwd<<<tile_grid, fz::NTHR, fz::FFN_FWD_SMEM, st>>>(fa);
     ADER_CHECK_LAUNCH("encoder_fwd_tc/block");
   }
@@ -1105,7 +1112,7 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
 
 extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
-                                       float dropout_rate, uint64_t seed, void* stream) {
+                                       float dropout_rate, uint64_t seed, const int32_t* d_step, void* stream) {
   if (int e = check_model(m)) return e;
   if (int e = fused_check(m)) return e;
   ADER_CHECK_ARG(theta && ids && ws && bwd_ws && d_rep && grad, "encoder_bwd_tc: NULL pointer");
@@ -1141,13 +1148,13 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
     fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
     fa.gH = gH; fa.gZ = gZ; fa.gY = gY; fa.D = g.Dv; fa.dT = dT; fa.d = d;
-    fa.drop_p = p; fa.seed = seed; fa.site2 = 3u + 3u * b;
+    fa.drop_p = p; fa.seed = seed; fa.d_step = d_step; fa.site2 = 3u + 3u * b;
     fz::k_ffn_bwd<<<tile_grid, fz::NTHR, fz::FFN_BWD_SMEM, st>>>(fa);
 
     fz::AttnBwdArgs ab;
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
     ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
-    ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.site = 1u + 3u * b;
+    ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.d_step = d_step; ab.site = 1u + 3u * b;
     if (m->num_heads == 1) fz::k_attn_bwd_w1<<<ln_grid, 256, 0, st>>>(ab);
     else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
 
@@ -1155,6 +1162,7 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     qb.gQ = gQ; qb.gK = gK; qb.gV = gV; qb.gY = gY; qb.X = X; qb.mean1 = w.mean1[b]; qb.rstd1 = w.rstd1[b];
     qb.ln_g = P + l.ln1g; qb.Wqb = shadow_of(w, b, 0, 1); qb.Wkb = shadow_of(w, b, 1, 1); qb.Wvb = shadow_of(w, b, 2, 1);
     qb.gQ1 = gQ1; qb.gXin = gXin; qb.dT = dT; qb.d = d;
+    qb.drop_p = (b == 0) ? p : 0.f; qb.seed = seed; qb.d_step = d_step;       // block 0: x0 = drop(emb) (ADER.py:55)
     fz::k_qkv_bwd<<<tile_grid, fz::NTHR, fz::QKV_BWD_SMEM, st>>>(qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
 
@@ -1173,7 +1181,7 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
     float* t = gX; gX = gXin; gXin = t;
   }
-  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, p, seed, grad, st)) return e;
+  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, grad, st)) return e;
   ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");
   return 0;
 }

@@ -43,6 +43,12 @@ constexpr int FTILE_BYTES = TM * FT_LD * 4;     // 21 504
 constexpr int NE = 5;                   // features per lane in the warp-per-token kernels (32 x 5 = 160)
 constexpr int W_PER_BLOCK = 10;         // 5 matrices x {forward [out][in], backward [in][out]} shadows
 
+// effective dropout seed: host value + optional device-resident step counter (lets a captured CUDA graph draw
+// fresh masks on every replay: the counter is the Adam step the optimiser kernel increments)
+__device__ __forceinline__ uint64_t eff_seed(uint64_t seed, const int* d_step) {
+  return seed + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
+}
+
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -216,7 +222,7 @@ struct QkvFwdArgs {
   float* Xw;
   int embed;
   const float *table, *pos_table; const int *tok_row, *tok_id, *row_len, *row_off;
-  float sqrt_d, drop_p; uint64_t seed;
+  float sqrt_d, drop_p; uint64_t seed; const int* d_step;
   const float *ln_b, *ln_g; float *Q1, *mean, *rstd;
   const op_t *Wq, *Wk, *Wv; const float *bq, *bk, *bv;
   float *Q, *K, *V;
@@ -225,6 +231,7 @@ struct QkvFwdArgs {
 constexpr size_t QKV_FWD_SMEM = 3 * WMAT_BYTES + 2 * ATILE_BYTES + TM * 4 + 16;
 
 __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ QkvFwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
   op_t* A1 = reinterpret_cast<op_t*>(smem + 3 * WMAT_BYTES);      // LN1(x)
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
             float v = 0.f;
             if (c < d) {
               v = a.table[id * d + c] * a.sqrt_d + a.pos_table[p * d + c];
-              if (a.drop_p > 0.f) v *= drop_scale(a.seed, 0u, (uint64_t)tk * d + c, a.drop_p);
+              if (a.drop_p > 0.f) v *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
               a.Xw[(long long)tk * d + c] = v;
             }
             x[e] = v;
@@ -388,10 +395,11 @@ struct AttnFwdArgs {
   float *probs, *Y, *Z, *mean2, *rstd2;
   const float *ln_b, *ln_g;
   const int* dT; int d, nh, L, Tcap;
-  float drop_p; uint64_t seed; uint32_t site;
+  float drop_p; uint64_t seed; const int* d_step; uint32_t site;
 };
 
 __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tk >= *a.dT) return;
   const int d = a.d, L = a.L;
@@ -433,7 +441,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ 
       l = l * corr + ps;
       m = m_new;
       if (lane < KB && valid) a.probs[po + j0 + j8] = sc;
-      if (a.drop_p > 0.f && valid) pj *= drop_scale(a.seed, a.site, (uint64_t)(po + j0 + j8), a.drop_p);
+      if (a.drop_p > 0.f && valid) pj *= drop_scale(seed_eff, a.site, (uint64_t)(po + j0 + j8), a.drop_p);
 #pragma unroll
       for (int e = 0; e < NE; ++e) oh[e] *= corr;
       block_axpy(oh, pj, Vrow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane);
@@ -475,11 +483,12 @@ struct FfnFwdArgs {
   const float* Z; float *H, *Xn;
   const op_t *W1, *W2; const float *b1, *b2;
   const int* dT; int d;
-  float drop_p; uint64_t seed; uint32_t site1, site2;
+  float drop_p; uint64_t seed; const int* d_step; uint32_t site1, site2;
 };
 constexpr size_t FFN_FWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + 16;
 
 __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ FfnFwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
   op_t* A1 = reinterpret_cast<op_t*>(smem + 2 * WMAT_BYTES);
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
         if (t0 + r < T) {
           const long long e = (long long)(t0 + r) * d + c;
           h0 = fmaxf(v0 + a.b1[c], 0.f); h1 = fmaxf(v1 + a.b1[c + 1], 0.f);
-          if (a.drop_p > 0.f) { h0 *= drop_scale(a.seed, a.site1, (uint64_t)e, a.drop_p); h1 *= drop_scale(a.seed, a.site1, (uint64_t)e + 1, a.drop_p); }
+          if (a.drop_p > 0.f) { h0 *= drop_scale(seed_eff, a.site1, (uint64_t)e, a.drop_p); h1 *= drop_scale(seed_eff, a.site1, (uint64_t)e + 1, a.drop_p); }
           *reinterpret_cast<float2*>(a.H + e) = make_float2(h0, h1);
         }
         st_op2(A2 + r * LDS + c, h0, h1);
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
       if (t0 + r < T && c < d) {
         const long long e = (long long)(t0 + r) * d + c;
         float x0 = v0 + a.b2[c], x1 = v1 + a.b2[c + 1];
-        if (a.drop_p > 0.f) { x0 *= drop_scale(a.seed, a.site2, (uint64_t)e, a.drop_p); x1 *= drop_scale(a.seed, a.site2, (uint64_t)e + 1, a.drop_p); }
+        if (a.drop_p > 0.f) { x0 *= drop_scale(seed_eff, a.site2, (uint64_t)e, a.drop_p); x1 *= drop_scale(seed_eff, a.site2, (uint64_t)e + 1, a.drop_p); }
         const float2 z = *reinterpret_cast<const float2*>(a.Z + e);
         *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + z.x, x1 + z.y);
       }
@@ -561,11 +570,12 @@ struct FfnBwdArgs {
   const op_t *W2b, *W1b;     // backward-orientation shadows
   float *gH, *gZ, *gY, *D;
   const int* dT; int d;
-  float drop_p; uint64_t seed; uint32_t site2;
+  float drop_p; uint64_t seed; const int* d_step; uint32_t site2;
 };
 constexpr size_t FFN_BWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES + TM * 4 + 16;
 
 __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ FfnBwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
   op_t* A1 = reinterpret_cast<op_t*>(smem + 2 * WMAT_BYTES);
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ Ffn
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * TM;
-    stage_rows_scaled(A1, rs, a.gX, t0, T, d, warp, lane, a.drop_p, a.seed, a.site2, a.gO);   // x_out = drop(h.W2 + b2) + z
+    stage_rows_scaled(A1, rs, a.gX, t0, T, d, warp, lane, a.drop_p, seed_eff, a.site2, a.gO);   // x_out = drop(h.W2 + b2) + z
     __syncthreads();
     if (first) { mbar_wait(bar, 0); first = false; }
     float acc[NT][4];
@@ -652,10 +662,11 @@ struct AttnBwdArgs {
   const int *tok_row, *row_off;
   float *gQ, *gK, *gV;
   const int* dT; int d, nh, L, Tcap;
-  float drop_p; uint64_t seed; uint32_t site;
+  float drop_p; uint64_t seed; const int* d_step; uint32_t site;
 };
 
 __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ AttnBwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tk >= *a.dT) return;
   const int d = a.d, L = a.L;
@@ -689,7 +700,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
         for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gy[e], vr[c], p); }
         p = warp_sum(p);
         const float P = a.probs[po_i + j];
-        const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
+        const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
         acc = fmaf(p * scl, P, acc);
       }
       Dh = acc;
@@ -711,7 +722,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
         const int j = j0 + u;
         if (j <= i) {
           const float P = a.probs[po_i + j];
-          const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
+          const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)(po_i + j), a.drop_p) : 1.f;
           const float ds = P * (dp * scl - Dh) * inv_denom;
           const float* kr = a.K + (long long)(off + j) * d;
 #pragma unroll
@@ -739,7 +750,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
           const int tq = off + qi;
           const long long po = ((long long)h * a.Tcap + tq) * L + i;
           const float P = a.probs[po];
-          const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+          const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p) : 1.f;
           float Dq = a.D[tq];
           if (a.nh > 1) {      // per-head D of query qi (rare path: num_heads > 1)
             float acc = 0.f;
@@ -751,7 +762,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
 #pragma unroll
               for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) p = fmaf(gr[c], vr[c], p); }
               p = warp_sum(p);
-              const float s2 = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)(pq + j), a.drop_p) : 1.f;
+              const float s2 = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)(pq + j), a.drop_p) : 1.f;
               acc = fmaf(p * s2, a.probs[pq + j], acc);
             }
             Dq = acc;
@@ -782,6 +793,7 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
 
 // Single-head fast form of the same kernel: blocks of 8 keys / queries (one L2 round trip per block).
 __global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ AttnBwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tk >= *a.dT) return;
   const int d = a.d, L = a.L;
@@ -809,7 +821,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ 
     if (j8 < cnt) {
       const long long po = po_i + j0 + j8;
       const float P = a.probs[po];
-      const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+      const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p) : 1.f;
       ds = P * (dp * scl - Di) * inv_denom;
     }
     block_axpy(gq, ds, a.K + (long long)(off + j0) * d, d, cnt, 0, d, lane);
@@ -823,7 +835,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ 
       const int tq = off + q0 + j8;
       const long long po = (long long)tq * L + i;
       const float P = a.probs[po];
-      const float scl = a.drop_p > 0.f ? drop_scale(a.seed, a.site, (uint64_t)po, a.drop_p) : 1.f;
+      const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p) : 1.f;
       ds = P * (dp * scl - a.D[tq]) * inv_denom;
       pd = P * scl;
     }
@@ -847,11 +859,13 @@ struct QkvBwdArgs {
   const op_t *Wqb, *Wkb, *Wvb;
   float *gQ1, *gXin;
   const int* dT; int d;
+  float drop_p; uint64_t seed; const int* d_step;   // drop_p > 0 (first block only): gXin *= embedding-dropout mask (site 0)
 };
 constexpr size_t QKV_BWD_SMEM = 3 * WMAT_BYTES + 3 * ATILE_BYTES + FTILE_BYTES + 2 * TM * 4 + 16;
 static_assert(3 * ATILE_BYTES >= FTILE_BYTES, "second fp32 tile aliases the operand tiles");
 
 __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ QkvBwdArgs a) {
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
   op_t* A1 = reinterpret_cast<op_t*>(smem + 3 * WMAT_BYTES);
@@ -916,7 +930,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
         const int c = lane + 32 * e;
-        if (c < d) a.gXin[(long long)tk * d + c] = dx[e] + Ft2[r * FT_LD + c];
+        if (c < d) {
+          float v = dx[e] + Ft2[r * FT_LD + c];
+          if (a.drop_p > 0.f) v *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
+          a.gXin[(long long)tk * d + c] = v;
+        }
       }
     }
     __syncthreads();

@@ -1,0 +1,168 @@
+"""The training step as CUDA graphs (one per token-capacity bucket).
+
+After the kernel fusion a YOOCHOOSE-shaped step is ~45 launches of 5-25 us each: issued one by one from
+Python the host, not the GPU, sets the pace.  ``GraphStep`` captures ``Ader.train_step`` (encoder forward,
+logits + CE + distillation, backward, scatter, [NCCL all-reduce], Adam) once per token-capacity bucket into
+a ``torch.cuda.CUDAGraph`` and replays it.  Everything a step needs is either
+
+  * a static device buffer (``ids`` / ``pos`` / ``aux`` or the gather indices ``ti`` / ``ei``), filled before
+    the replay by stream-ordered copies from rotating pinned host buffers,
+  * device-resident state the kernels read themselves: the exact token count T (``row_off[M]``), the Adam step
+    (also the dropout counter: ``d_step``), theta / m / v / grad, or
+  * a constant of the period (lr, lambda, dropout rate, max_item, the stored teacher matrix).
+
+The token capacity only sizes grids and workspaces (surplus CTAs exit at once), so a handful of buckets
+covers every batch; the largest one (M x maxlen) is always safe.  Reference semantics are unchanged: this is
+the same sequence of C-ABI calls as the eager ``train_step`` (main.py:233-256).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class _PinnedRing:
+    """Rotating pinned staging buffers for stream-ordered H2D copies (a slot is reused only after its copy ran)."""
+
+    def __init__(self, shape, n=4):
+        self.bufs = [torch.empty(shape, dtype=torch.int32).pin_memory() for _ in range(n)]
+        self.evs = [None] * n
+        self.i = 0
+
+    def stage(self, src: np.ndarray, dst: torch.Tensor):
+        k = self.i
+        self.i = (k + 1) % len(self.bufs)
+        if self.evs[k] is not None:
+            self.evs[k].synchronize()
+        self.bufs[k].numpy()[...] = src
+        dst.copy_(self.bufs[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.evs[k] = ev
+
+
+class GraphStep:
+    """Captured ``train_step`` for a fixed batch geometry (n_train + n_ex rows) of one period.
+
+    sources: optional ``(t_ids [Nt, L], t_lab [Nt], e_ids [Ne, L], e_aux [Ne])`` device int32 matrices; when
+    given the graph starts by gathering the batch rows from them with the static index buffers ``ti`` / ``ei``
+    (``run_indices``); ``e_aux`` is the teacher row of each exemplar (distillation) or its label (one-hot replay).
+    """
+
+    def __init__(self, model, n_train: int, n_ex: int, max_item: int, lr: float, dropout_rate: float = 0.0,
+                 teacher: Optional[torch.Tensor] = None, sources=None, tcaps: Optional[Sequence[int]] = None):
+        if dropout_rate > 0.0 and model.encoder_impl != "tc":
+            raise ValueError("graph replay with dropout needs the tc encoder (device-side dropout counter)")
+        self.model, self.n_train, self.n_ex = model, int(n_train), int(n_ex)
+        self.max_item, self.lr, self.p = int(max_item), float(lr), float(dropout_rate)
+        self.teacher = teacher
+        dev, L = model.device, model.hp.maxlen
+        M = self.n_train + self.n_ex
+        self.M = M
+        self.ids = torch.zeros((M, L), dtype=torch.int32, device=dev)
+        self.pos = torch.ones(self.n_train, dtype=torch.int32, device=dev)
+        self.aux = torch.zeros(max(self.n_ex, 1), dtype=torch.int32, device=dev)
+        if self.n_ex > 0 and model.mode == model.ER:
+            self.aux.fill_(1)
+        self.sources = sources
+        if sources is not None:
+            self.ti = torch.zeros(self.n_train, dtype=torch.int32, device=dev)
+            self.ei = torch.zeros(max(self.n_ex, 1), dtype=torch.int32, device=dev)
+            self._ring_ti = _PinnedRing((self.n_train,))
+            self._ring_ei = _PinnedRing((max(self.n_ex, 1),))
+        self._ring_ids = _PinnedRing((M, L))
+        self._ring_pos = _PinnedRing((self.n_train,))
+        self._ring_aux = _PinnedRing((max(self.n_ex, 1),))
+        full = M * L
+        caps = sorted({min(max(int(t), 1), full) for t in (tcaps or [])} | {full})
+        self.tcaps = caps
+        self.graphs = {}
+        self._row_loss = {}
+        self._capture_all()
+        # the graphs address these buffers: keep them alive even if the model later grows its workspaces
+        self._held = (model._enc_ws.buf, model._bwd_ws.buf, model._loss_ws.buf, model.theta, model.grad, model.adam_m,
+                      model.adam_v, model.adam_state, model._loss, teacher, sources)
+
+    # ---- capture ------------------------------------------------------------------------------------
+    def _eager(self, tcap: int, device_step: bool):
+        m = self.model
+        if self.sources is not None:
+            t_ids, t_lab, e_ids, e_aux = self.sources
+            ops.gather_rows_i32(t_ids, self.ti, self.ids[:self.n_train])
+            ops.gather_rows_i32(t_lab.view(-1, 1), self.ti, self.pos.view(-1, 1))
+            if self.n_ex > 0:
+                ops.gather_rows_i32(e_ids, self.ei, self.ids[self.n_train:])
+                ops.gather_rows_i32(e_aux.view(-1, 1), self.ei, self.aux.view(-1, 1))
+        kw = {}
+        if self.n_ex > 0:
+            if m.mode == m.KD:
+                kw = dict(exemplar_logits=self.teacher, teacher_rows=self.aux[:self.n_ex])
+            elif m.mode == m.ER:
+                kw = dict(exemplar_pos=self.aux[:self.n_ex])
+        loss = m.train_step(self.ids, self.pos, self.max_item, self.lr, self.p, n_tokens=tcap,
+                            _device_step=device_step, **kw)
+        self._row_loss[tcap] = m.last_row_loss
+        return loss
+
+    def _capture_all(self):
+        m = self.model
+        sd = m.state_dict()
+        gs = m.global_step
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up on the largest capacity: sizes every workspace once
+            self._eager(self.tcaps[-1], False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = None
+        for tcap in reversed(self.tcaps):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._eager(tcap, True)
+            pool = g.pool()
+            self.graphs[tcap] = g
+        m.load_state_dict(sd)                  # the warm-up step must not count
+        m.global_step = gs
+        torch.cuda.synchronize()
+
+    # ---- replay ---------------------------------------------------------------------------------------
+    def _replay(self, n_tokens: Optional[int]):
+        cap = self.tcaps[-1]
+        if n_tokens is not None:
+            for t in self.tcaps:
+                if t >= n_tokens:
+                    cap = t
+                    break
+        self.graphs[cap].replay()
+        self.model.global_step += 1
+        self.model.last_row_loss = self._row_loss[cap]
+        return self.model._loss
+
+    @staticmethod
+    def _put(ring, dst, src):
+        if isinstance(src, torch.Tensor):
+            dst.copy_(src.to(torch.int32).view(dst.shape), non_blocking=True)
+        else:
+            ring.stage(np.asarray(src, dtype=np.int32).reshape(tuple(dst.shape)), dst)
+
+    def run_rows(self, ids, pos, aux=None, n_tokens: Optional[int] = None):
+        """ids [M, L], pos [n_train], aux [n_ex] (teacher rows or exemplar labels): host arrays or device tensors."""
+        self._put(self._ring_ids, self.ids, ids)
+        self._put(self._ring_pos, self.pos, pos)
+        if self.n_ex > 0 and aux is not None:
+            self._put(self._ring_aux, self.aux[:self.n_ex], aux)
+        return self._replay(n_tokens)
+
+    def run_indices(self, ti, ei=None, n_tokens: Optional[int] = None):
+        """Row indices into the ``sources`` matrices (host arrays or device tensors)."""
+        if self.sources is None:
+            raise ValueError("GraphStep was built without row sources")
+        self._put(self._ring_ti, self.ti, ti)
+        if self.n_ex > 0 and ei is not None:
+            self._put(self._ring_ei, self.ei[:self.n_ex], ei)
+        return self._replay(n_tokens)

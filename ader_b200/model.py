@@ -105,7 +105,7 @@ class Ader:
         return min(max(cap, 1), M * self.hp.maxlen)
 
     def encode(self, ids: torch.Tensor, n_tokens: Optional[int] = None, dropout_rate: float = 0.0,
-               seed: int = 0, out: Optional[torch.Tensor] = None, impl: Optional[str] = None):
+               seed: int = 0, out: Optional[torch.Tensor] = None, impl: Optional[str] = None, d_step=None):
         """ids int32 [M, L] (device) -> rep fp32 [M, d]; returns (rep, Tcap).  The activation
         workspace stays valid until the next encode() (needed by backward)."""
         M = ids.shape[0]
@@ -113,7 +113,7 @@ class Ader:
         ws = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, M, tcap))
         rep = out if out is not None else torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
         ops.encoder_fwd(self.ms, self.theta, ids, tcap, ws, rep, dropout_rate, seed,
-                        impl=impl or self.infer_encoder_impl)
+                        impl=impl or self.infer_encoder_impl, d_step=d_step)
         return rep, tcap
 
     def rep(self, seq, n_tokens: Optional[int] = None) -> torch.Tensor:
@@ -137,7 +137,7 @@ class Ader:
     def loss_and_grad(self, seq, pos, max_item: int, exemplar_logits=None, exemplar_pos=None,
                       teacher_rows=None, dropout_rate: float = 0.0, n_tokens: Optional[int] = None,
                       mode: Optional[int] = None, lambda_: Optional[float] = None, _events=None,
-                      global_counts=None) -> torch.Tensor:
+                      global_counts=None, _device_step: bool = False) -> torch.Tensor:
         """Forward + backward of the current loss; fills ``self.grad`` (flat).  Returns the device
         scalar loss.  ``exemplar_logits`` is either a host array / list [M_e, V_prev] (reference feed,
         ADER.py:20) or a device tensor [E, V_prev] indexed by ``teacher_rows`` [M_e]."""
@@ -176,8 +176,11 @@ class Ader:
                 ex_pos_t = _to_i32(exemplar_pos, self.device)
             else:
                 raise ValueError("exemplar rows were fed but the loss is vanilla (call update_loss first)")
-        seed = (self.seed << 32) + self.global_step
-        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl)
+        # dropout stream: (seed, step).  Under CUDA-graph capture the step is read on the device from the Adam
+        # state (incremented by the optimiser kernel), so every replay draws fresh masks.
+        d_step = self.adam_state if _device_step else None
+        seed = (self.seed << 32) + (0 if _device_step else self.global_step)
+        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl, d_step=d_step)
         if _events:
             _events[0].record()
         gc = global_counts if global_counts is not None else self.global_counts
@@ -195,7 +198,7 @@ class Ader:
             _events[1].record()
         bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
         ops.encoder_bwd(self.ms, self.theta, ids, tcap, self._enc_ws.buf, bws, d_rep, self.grad, dropout_rate, seed,
-                        impl=self.encoder_impl)
+                        impl=self.encoder_impl, d_step=d_step)
         if _events:
             _events[2].record()
         if self.grad_sync is not None:      # data parallel: NCCL all-reduce of the flat gradient
@@ -211,13 +214,22 @@ class Ader:
         self.global_step += 1
 
     def train_step(self, seq, pos, max_item: int, lr: Optional[float] = None, dropout_rate: Optional[float] = None,
-                   exemplar_logits=None, exemplar_pos=None, teacher_rows=None, n_tokens: Optional[int] = None):
+                   exemplar_logits=None, exemplar_pos=None, teacher_rows=None, n_tokens: Optional[int] = None,
+                   _device_step: bool = False):
         """sess.run(model.train_op, feed) (main.py:233-256).  Returns the device scalar loss."""
         lr = self.args.lr if lr is None else lr
         p = self.args.dropout_rate if dropout_rate is None else dropout_rate
-        loss = self.loss_and_grad(seq, pos, max_item, exemplar_logits, exemplar_pos, teacher_rows, p, n_tokens)
+        loss = self.loss_and_grad(seq, pos, max_item, exemplar_logits, exemplar_pos, teacher_rows, p, n_tokens,
+                                  _device_step=_device_step)
         self.apply_gradients(max_item, lr)
         return loss
+
+    def graph_step(self, n_train: int, n_ex: int, max_item: int, lr: Optional[float] = None,
+                   dropout_rate: Optional[float] = None, teacher=None, sources=None, tcaps=None):
+        """The same train step captured as CUDA graphs for a fixed batch geometry (see ader_b200/graph.py)."""
+        from .graph import GraphStep
+        return GraphStep(self, n_train, n_ex, max_item, self.args.lr if lr is None else lr,
+                         self.args.dropout_rate if dropout_rate is None else dropout_rate, teacher, sources, tcaps)
 
     # ---- evaluation ---------------------------------------------------------------------------
     def rank_topk(self, seq, gt, max_item: int, k: int = 20, n_tokens: Optional[int] = None):

@@ -68,23 +68,34 @@ def encoder_ws_slot(ms: AderModel, M: int, Tcap: int, slot: int, block: int = 0)
 
 
 def encoder_fwd(ms: AderModel, theta, ids, Tcap: int, ws, rep, dropout_rate: float = 0.0, seed: int = 0,
-                impl: str = "exact"):
-    """ids [M, maxlen] int32 -> rep [M, d] (ADER.py:25-85).  impl: "exact" (fp32) or "tc" (fused bf16 tensor path)."""
+                impl: str = "exact", d_step=None):
+    """ids [M, maxlen] int32 -> rep [M, d] (ADER.py:25-85).  impl: "exact" (fp32) or "tc" (fused tensor-core path).
+    d_step (tc only): device int32 step counter added to the dropout seed on the device (CUDA-graph replays)."""
     _require_cuda(theta, ids, ws, rep)
     lib = _lib.load()
-    fn = lib.ader_encoder_fwd_tc if impl == "tc" else lib.ader_encoder_fwd
-    check(fn(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
-                                       float(dropout_rate), C.c_uint64(seed), _stream()), "encoder_fwd")
+    if impl == "tc":
+        check(lib.ader_encoder_fwd_tc(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
+                                      float(dropout_rate), C.c_uint64(seed), _ptr(d_step), _stream()), "encoder_fwd_tc")
+        return
+    if d_step is not None:
+        raise _lib.AderError("d_step is only supported by the tc encoder")
+    check(lib.ader_encoder_fwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(rep),
+                               float(dropout_rate), C.c_uint64(seed), _stream()), "encoder_fwd")
 
 
 def encoder_bwd(ms: AderModel, theta, ids, Tcap: int, ws, bwd_ws, d_rep, grad, dropout_rate: float = 0.0, seed: int = 0,
-                impl: str = "exact"):
+                impl: str = "exact", d_step=None):
     _require_cuda(theta, ids, ws, bwd_ws, d_rep, grad)
     lib = _lib.load()
-    fn = lib.ader_encoder_bwd_tc if impl == "tc" else lib.ader_encoder_bwd
-    check(fn(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
-                                       _ptr(d_rep), _ptr(grad), float(dropout_rate), C.c_uint64(seed), _stream()),
-          "encoder_bwd")
+    if impl == "tc":
+        check(lib.ader_encoder_bwd_tc(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
+                                      _ptr(d_rep), _ptr(grad), float(dropout_rate), C.c_uint64(seed), _ptr(d_step), _stream()),
+              "encoder_bwd_tc")
+        return
+    if d_step is not None:
+        raise _lib.AderError("d_step is only supported by the tc encoder")
+    check(lib.ader_encoder_bwd(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, _ptr(ws), _ptr(bwd_ws),
+                               _ptr(d_rep), _ptr(grad), float(dropout_rate), C.c_uint64(seed), _stream()), "encoder_bwd")
 
 
 def make_loss_args(M, n_train, n_ex, V, V_prev=0, mode=0, lambda_=0.0, pos=None, ex_pos=None,

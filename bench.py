@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 # ---- workload: YOOCHOOSE ADER, period-4 shape (measured with the reference loaders) ----
 WL = dict(name="yoochoose_ader_train_step(period4 shape)", item_num=25958, B=512, M_e=138, V=18661, V_prev=17421,
-          lam=1.0, lr=5e-4, pool_rows=110699, exemplars=30000)
+          lam=1.0, lr=5e-4, pool_rows=110699, exemplars=30000, dropout=0.3)   # dropout 0.3: main.py:106,141 (ADER runs train with it)
 # P(input length = k), k = 0..50, of YOOCHOOSE period-5 training rows (reference Sampler, seed 0)
 LEN_HIST = [0.0001, 0.3048, 0.1778, 0.1171, 0.0812, 0.0597, 0.0449, 0.0352, 0.0279, 0.0221, 0.018, 0.0148, 0.0124,
             0.0102, 0.0086, 0.0072, 0.0063, 0.0053, 0.0046, 0.0041, 0.0036, 0.0031, 0.0028, 0.0024, 0.0022, 0.0018,
@@ -167,7 +167,7 @@ def reference_arm(args):
 def workload_config(n):
     return {"workload": WL["name"], "batch_size": WL["B"], "exemplar_rows": WL["M_e"], "max_item": WL["V"],
             "prev_max_item": WL["V_prev"], "table_rows": WL["item_num"] + 1, "lambda": WL["lam"], "maxlen": 50,
-            "hidden_units": 150, "num_blocks": 2, "global_batch": (WL["B"] + WL["M_e"]) * n,
+            "hidden_units": 150, "num_blocks": 2, "dropout_rate": WL["dropout"], "global_batch": (WL["B"] + WL["M_e"]) * n,
             "parallelism": "dp%d" % n if n > 1 else "single",
             "l2": "per-step working set (theta+m+v+grad of %d rows, logits workspace) exceeds the 126 MB L2; "
                   "inputs change every step" % (WL["V"] + 1)}
@@ -218,11 +218,26 @@ def gpu_arm(args):
     d_ei = [torch.from_numpy(a).to(dev) for a in ei_all]
     ids_buf = torch.empty((M, 50), dtype=torch.int32, device=dev)
 
+    P = WL["dropout"]
+    gs = None
+    if not args.no_graph:       # the step as CUDA graphs (one per token-capacity bucket); same C-ABI calls as the eager step
+        d_e_row = torch.arange(WL["exemplars"], dtype=torch.int32, device=dev)      # stored teacher row of each exemplar
+        caps = sorted({int(-(-q // 256) * 256) for q in np.quantile(ntok, [0.5, 0.9, 0.99, 1.0])})
+        gs = model.graph_step(B, Me, V, WL["lr"], P, teacher=teacher, sources=(d_t_ids, d_t_lab, d_e_ids, d_e_row), tcaps=caps)
+
     def resident_step(i):
+        if gs is not None:
+            return gs.run_indices(d_ti[i], d_ei[i], ntok[i])
         ops.gather_rows_i32(d_t_ids, d_ti[i], ids_buf[:B])
         ops.gather_rows_i32(d_e_ids, d_ei[i], ids_buf[B:])
         pos = d_t_lab[d_ti[i].long()]
-        return model.train_step(ids_buf, pos, V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=d_ei[i],
+        return model.train_step(ids_buf, pos, V, WL["lr"], P, exemplar_logits=teacher, teacher_rows=d_ei[i],
+                                n_tokens=ntok[i])
+
+    def e2e_step(i):
+        if gs is not None:
+            return gs.run_rows(h_ids[i], h_pos[i], ei_all[i], ntok[i])
+        return model.train_step(h_ids[i], h_pos[i], V, WL["lr"], P, exemplar_logits=teacher, teacher_rows=ei_all[i],
                                 n_tokens=ntok[i])
 
     def barrier():
@@ -256,15 +271,12 @@ def gpu_arm(args):
     h_ids = [np.concatenate([t_ids[a], e_ids[b]]) for a, b in zip(ti_all, ei_all)]
     h_pos = [t_lab[a] for a in ti_all]
     for i in range(min(W, 3)):
-        float(model.train_step(h_ids[i], h_pos[i], V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=ei_all[i],
-                               n_tokens=ntok[i]).item())
+        float(e2e_step(i).item())
     barrier()
     w0 = time.time()
     e0.record()
     for i in range(W, W + K):
-        loss = model.train_step(h_ids[i], h_pos[i], V, WL["lr"], 0.0, exemplar_logits=teacher, teacher_rows=ei_all[i],
-                                n_tokens=ntok[i])
-        last_loss = float(loss.item())
+        last_loss = float(e2e_step(i).item())
     e1.record()
     barrier()
     windows.append((w0, time.time()))
@@ -288,25 +300,67 @@ def gpu_arm(args):
         pos = d_t_lab[d_ti[i].long()]
         evs[r][0].record()
         model.loss_and_grad(ids_buf, pos, V, exemplar_logits=teacher, teacher_rows=d_ei[i], n_tokens=ntok[i],
-                                    _events=evs[r][1:4])
+                            dropout_rate=P, _events=evs[r][1:4])
         model.apply_gradients(V, WL["lr"])
         evs[r][4].record()
     torch.cuda.synchronize()
     for name, a, b in (("encoder_fwd", 0, 1), ("logits_ce_kd_fwd_bwd", 1, 2), ("encoder_bwd_scatter", 2, 3), ("adam", 3, 4)):
         phases[name] = float(np.mean([evs[r][a].elapsed_time(evs[r][b]) for r in range(reps)]))
 
-    # ---- kernel launch count (CUPTI via torch.profiler, outside the timed regions) ----------------
+    # ---- kernel launch count + in-pipeline kernel durations (CUPTI via torch.profiler, outside the timed regions)
     launches_per_step = None
+    kernels_us = {}
     try:
         from torch.profiler import ProfilerActivity, profile
+        nprof = 10
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            resident_step(W)
+            for r in range(nprof):
+                resident_step(W + r)
             torch.cuda.synchronize()
-        names = [e.key for e in prof.key_averages() for _ in range(e.count) if e.device_type.name == "CUDA"]
-        mine = [n for n in names if "ader" in n or n.startswith("k_")]
-        launches_per_step = len(mine)
+        cnt = 0
+        for e in prof.events():
+            if e.device_type.name != "CUDA":
+                continue
+            n = e.name.split("(")[0].replace("void ", "")
+            if "ader" in n or n.startswith("k_"):
+                cnt += 1
+                kernels_us[n] = kernels_us.get(n, 0.0) + e.device_time / nprof
+        launches_per_step = cnt // nprof
     except Exception:
         pass
+
+    # ---- the north-star kernel group alone: logits + CE + KD forward/backward (ader_loss_fwd_bwd_tc), captured as its
+    # own CUDA graph and timed with CUDA events over back-to-back replays (fresh teacher rows every replay) -----------
+    loss_group_ms = None
+    try:
+        rep_in = torch.randn((M, 150), device=dev) * 0.5
+        pos_in = d_t_lab[d_ti[W].long()].contiguous()
+        rows_in = d_ei[W].clone()
+        la = ops.make_loss_args(M, B, Me, V, Vp, model.KD, WL["lam"], pos_in, None, teacher, rows_in)
+        lws = torch.empty(ops.loss_tc_ws_bytes(model.ms, la), dtype=torch.uint8, device=dev)
+        rl, dr, ls = torch.empty(M, device=dev), torch.empty((M, 150), device=dev), torch.zeros(1, device=dev)
+        gsave = model.grad.clone()
+        run_loss = lambda: ops.loss_fwd_bwd_tc(model.ms, model.theta, rep_in, la, lws, ls, rl, dr, model.grad)
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run_loss()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        gl = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gl):
+            run_loss()
+        nrep = 50
+        for r in range(5):
+            rows_in.copy_(d_ei[W + r]); gl.replay()
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for r in range(nrep):
+            rows_in.copy_(d_ei[W + (r % K)]); gl.replay()
+        eb.record(); torch.cuda.synchronize()
+        loss_group_ms = ea.elapsed_time(eb) / nrep
+        model.grad.copy_(gsave)
+    except Exception as ex:      # noqa: BLE001
+        sys.stderr.write("loss-group timing failed: %r\n" % (ex,))
 
     if rank == 0:
         peaks = {}
@@ -317,7 +371,7 @@ def gpu_arm(args):
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
         flops = 6.0 * M * 150 * V                      # fwd + bwd of the output projection, d counted as 150
-        dom_ms = phases["logits_ce_kd_fwd_bwd"]
+        dom_ms = loss_group_ms if loss_group_ms else phases["logits_ce_kd_fwd_bwd"]
         achieved = flops / (dom_ms * 1e-3) / 1e12
         cpu_val, cpu_ms, cores, _ = run_cpu(2, 1)
         line = {"metric": "train sessions/sec", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
@@ -328,8 +382,11 @@ def gpu_arm(args):
                 "gpu_launches": (launches_per_step or 0) * K,
                 "gpu_launches_per_step": launches_per_step,
                 "clocks": clock_info,
-                "phases_ms": phases,
-                "roofline": {"kernel": "logits+CE+KD fwd+bwd group (ader_loss_fwd_bwd)", "bound": "tensor",
+                "phases_ms_eager": phases,
+                "step_mode": "eager launches" if gs is None else "CUDA graph per token-capacity bucket %s" % (gs.tcaps,),
+                "kernels_us_per_step": dict(sorted(((k, round(v, 2)) for k, v in kernels_us.items()), key=lambda kv: -kv[1])[:12]),
+                "loss_group_ms": loss_group_ms,
+                "roofline": {"kernel": "logits+CE+KD fwd+bwd group (ader_loss_fwd_bwd_tc: 13 launches, CUDA-event timed graph replays)", "bound": "tensor",
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "traffic": None, "peak_source": peak_src,
                              "algorithmic_flops_per_launch": flops},
@@ -346,6 +403,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ader_b200")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="issue the step's launches eagerly")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

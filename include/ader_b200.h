@@ -76,12 +76,15 @@ int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* 
  * operands / fp32 accumulation, weights staged by bulk async copies; workspaces and slots are identical to
  * the exact path (same *_ws_bytes queries).  Needs hidden_units <= 160.  Results agree with the exact path
  * to bf16 operand rounding (tests state the tolerance); weight/bias/LayerNorm gradients are accumulated in
- * fp32 in a fixed order (deterministic). */
+ * fp32 in a fixed order (deterministic).
+ * d_step (device int32, may be NULL): added to `seed` on the device, so a captured CUDA graph draws fresh dropout
+ * masks on every replay (pass the Adam state pointer: state[0] is the step counter). */
 int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
-                            int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed, void* stream);
+                            int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
+                            const int32_t* d_step, void* stream);
 int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                             int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
-                            float dropout_rate, uint64_t seed, void* stream);
+                            float dropout_rate, uint64_t seed, const int32_t* d_step, void* stream);
 
 /* ---- logits + CE + distillation: ADER.py:88-93, ADER.py:108-138 (subsystem 2) ---------- */
 typedef struct AderLossArgs {
