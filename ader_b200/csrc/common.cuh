@@ -88,14 +88,17 @@ struct GemmGroup { GemmArgs g[GEMM_GROUP_MAX]; int n, av, bv; };
 int launch_gemm_group(const GemmArgs* gs, int n, cudaStream_t st);
 
 // ---- counter-based dropout mask (shared by fwd and bwd) -----------------------------------
-__host__ __device__ inline uint32_t mix32(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return (uint32_t)x;
+// u = fmix32(idx ^ key(seed, site)) / 2^24: a stateless 32-bit hash (murmur3 finaliser) of the element index,
+// keyed per (seed + step, site).  ~10 integer instructions per element; key terms are loop invariant.
+__host__ __device__ inline uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
 }
 // returns the multiplier (0 or 1/(1-p)) for element `idx` of dropout site `site`.
 __host__ __device__ inline float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
-  uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)site << 40) + idx);
-  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+  const uint32_t key = fmix32((uint32_t)seed * 0x9E3779B1u + (uint32_t)(seed >> 32) * 0x7FEB352Du + site * 0x846CA68Bu + 0x5bd1e995u);
+  const uint32_t r = fmix32(((uint32_t)idx ^ key) + (uint32_t)(idx >> 32) * 0x27d4eb2fu);
+  const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
   return u < p ? 0.0f : 1.0f / (1.0f - p);
 }
 

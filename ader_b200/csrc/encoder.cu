@@ -1050,6 +1050,13 @@ static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
 }
 }  // namespace ader
 
+#ifdef ADER_TC_TIMELINE
+extern "C" int32_t ader_debug_fz_timeline(long long* out) {
+  cudaDeviceSynchronize();
+  return (int32_t)cudaMemcpyFromSymbol(out, fz::g_fz_tl, sizeof(fz::g_fz_tl));
+}
+#endif
+
 extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
                                        const int32_t* d_step, void* stream) {

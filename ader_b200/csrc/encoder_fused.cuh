@@ -49,6 +49,17 @@ __device__ __forceinline__ uint64_t eff_seed(uint64_t seed, const int* d_step) {
   return seed + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
 }
 
+// Optional phase timeline (debug builds: -DADER_TC_TIMELINE): %globaltimer stamps by thread 0 of each CTA.
+#ifdef ADER_TC_TIMELINE
+__device__ long long g_fz_tl[8][160][16];
+__device__ __forceinline__ void fz_tl(int k, int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < 160) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fz_tl[k][blockIdx.x][slot] = t; }
+}
+#define FZ_TL(k, slot) fz_tl(k, slot)
+#else
+#define FZ_TL(k, slot) do { } while (0)
+#endif
+
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -126,58 +137,97 @@ __device__ __forceinline__ float row_scale(float mx) {
   int e; frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
   return ldexpf(1.f, min(max(11 - e, -100), 100));
 }
-// Warp-per-row staging of rows t0 + warp*4 .. +3 of a [T,d] fp32 matrix into a 16-bit operand tile with a
-// per-row power-of-two scale; inv_scale[r] receives 1/s_r.  Optional dropout site applied (and the dropped
-// values written back) first.  Optional second matrix G2 -> As2 shares the row scale (joint maximum).
-__device__ __forceinline__ void stage_rows_scaled(op_t* __restrict__ As, float* __restrict__ inv_scale,
-                                                  const float* __restrict__ G, int t0, int T, int d, int warp, int lane,
-                                                  float drop_p = 0.f, uint64_t seed = 0, uint32_t site = 0,
-                                                  float* __restrict__ dropped_out = nullptr,
-                                                  const float* __restrict__ G2 = nullptr, op_t* __restrict__ As2 = nullptr) {
+// ---- batched row access: every warp owns RPW = 4 consecutive tile rows.  All global loads of a phase are issued
+// before the first use (one L2 round trip per phase instead of one per row), reductions of the 4 rows interleave.
+constexpr int RPW = TM / 8;
+__device__ __forceinline__ void warp_sum_n(float (&v)[RPW]) {
 #pragma unroll
-  for (int rr = 0; rr < TM / 8; ++rr) {
-    const int r = warp * (TM / 8) + rr, tk = t0 + r;
-    float v[NE], v2[NE]; float mx = 0.f;
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) v[r] += __shfl_xor_sync(0xffffffffu, v[r], o);
+}
+__device__ __forceinline__ void warp_max_n(float (&v)[RPW]) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) v[r] = fmaxf(v[r], __shfl_xor_sync(0xffffffffu, v[r], o));
+}
+// x[rr][e] = G[t0 + warp*RPW + rr][lane + 32 e]   (0 outside [0,T) x [0,d))
+__device__ __forceinline__ void load_rows(float (&x)[RPW][NE], const float* __restrict__ G, int t0, int T, int d, int warp, int lane) {
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; x[rr][e] = (tk < T && c < d) ? G[(long long)tk * d + c] : 0.f; }
+  }
+}
+// per-lane scalars of the warp's rows (mean / rstd / D ...)
+__device__ __forceinline__ void load_row_scalars(float (&v)[RPW], const float* __restrict__ G, int t0, int T, int warp) {
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) { const int tk = t0 + warp * RPW + rr; v[rr] = (tk < T) ? G[tk] : 0.f; }
+}
+// registers -> 16-bit operand tile rows with a per-row power-of-two scale (x2, if given, shares the scale: joint max)
+__device__ __forceinline__ void put_rows_scaled(op_t* __restrict__ As, float* __restrict__ inv_scale, const float (&x)[RPW][NE],
+                                                int warp, int lane, const float (*x2)[NE] = nullptr, op_t* __restrict__ As2 = nullptr) {
+  float mx[RPW];
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { m = fmaxf(m, fabsf(x[rr][e])); if (x2) m = fmaxf(m, fabsf(x2[rr][e])); }
+    mx[rr] = m;
+  }
+  warp_max_n(mx);
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = warp * RPW + rr;
+    const float sc = row_scale(mx[rr]);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int c = lane + 32 * e;
-      v[e] = 0.f; v2[e] = 0.f;
-      if (tk < T && c < d) {
-        const long long el = (long long)tk * d + c;
-        v[e] = G[el];
-        if (drop_p > 0.f) { v[e] *= drop_scale(seed, site, (uint64_t)el, drop_p); if (dropped_out) dropped_out[el] = v[e]; }
-        if (G2) v2[e] = G2[el];
-      }
-      mx = fmaxf(mx, fmaxf(fabsf(v[e]), fabsf(v2[e])));
-    }
-    const float sc = row_scale(warp_max(mx));
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int c = lane + 32 * e;
-      As[r * LDS + c] = to_op(v[e] * sc);
-      if (As2) As2[r * LDS + c] = to_op(v2[e] * sc);
+      As[r * LDS + c] = to_op(x[rr][e] * sc);
+      if (x2) As2[r * LDS + c] = to_op(x2[rr][e] * sc);
     }
     if (lane == 0) inv_scale[r] = 1.f / sc;
   }
 }
-// stage rows t0.. of a [T,d] fp32 matrix (optionally scaled by a dropout site) into a op_t tile, zero padded
-__device__ __forceinline__ void stage_tile16(op_t* __restrict__ As, const float* __restrict__ G, int t0, int T, int d,
-                                           float drop_p = 0.f, uint64_t seed = 0, uint32_t site = 0,
-                                           float* __restrict__ dropped_out = nullptr) {
-  for (int idx = threadIdx.x; idx < TM * (KP / 2); idx += NTHR) {
-    const int r = idx / (KP / 2), c = (idx % (KP / 2)) * 2;
-    const int tk = t0 + r;
-    float2 v = make_float2(0.f, 0.f);
-    if (tk < T && c < d) {
-      const long long e = (long long)tk * d + c;
-      v = *reinterpret_cast<const float2*>(G + e);
-      if (drop_p > 0.f) {
-        v.x *= drop_scale(seed, site, (uint64_t)e, drop_p);
-        v.y *= drop_scale(seed, site, (uint64_t)e + 1, drop_p);
-        if (dropped_out) *reinterpret_cast<float2*>(dropped_out + e) = v;
-      }
+__device__ __forceinline__ void put_rows(op_t* __restrict__ As, const float (&x)[RPW][NE], int warp, int lane) {
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) As[(warp * RPW + rr) * LDS + lane + 32 * e] = to_op(x[rr][e]);
+}
+// elements of a [T,d] matrix co-located with this thread's accumulator fragment (row = mt*16 + g + 8h, col pair);
+// issued ahead of the GEMM whose epilogue consumes them
+__device__ __forceinline__ void load_frag(float2 (&v)[NT][2], const float* __restrict__ G, int t0, int T, int d, int mt, int ng, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int c = ng * (NT * 8) + j * 8 + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tk = t0 + mt * 16 + g + 8 * h;
+      v[j][h] = (tk < T && c < d) ? *reinterpret_cast<const float2*>(G + (long long)tk * d + c) : make_float2(0.f, 0.f);
     }
-    st_op2(As + r * LDS + c, v.x, v.y);
+  }
+}
+__device__ __forceinline__ void load_bias_frag(float2 (&b)[NT], const float* __restrict__ bias, int d, int ng, int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int c = ng * (NT * 8) + j * 8 + 2 * t;
+    b[j] = (c < d) ? *reinterpret_cast<const float2*>(bias + c) : make_float2(0.f, 0.f);
+  }
+}
+// visit accumulator elements with their fragment coordinates: f(j, h, tile row, col, v0, v1)
+template <typename F>
+__device__ __forceinline__ void for_frag(const float (&acc)[NT][4], int mt, int ng, int lane, F f) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int col = ng * (NT * 8) + j * 8 + 2 * t;
+    f(j, 0, mt * 16 + g, col, acc[j][0], acc[j][1]);
+    f(j, 1, mt * 16 + g + 8, col, acc[j][2], acc[j][3]);
   }
 }
 
@@ -231,6 +281,7 @@ struct QkvFwdArgs {
 constexpr size_t QKV_FWD_SMEM = 3 * WMAT_BYTES + 2 * ATILE_BYTES + TM * 4 + 16;
 
 __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ QkvFwdArgs a) {
+  FZ_TL(0, 0);
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
@@ -249,82 +300,114 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
     load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.Wk, bar);
     load_wmat(smem_u32(Wsm) + 2 * WMAT_BYTES, a.Wv, bar);
   }
-  __syncthreads();
   const int mt = warp & 1, ng = warp >> 1;
+  float lg[NE], lb[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; lg[e] = (c < d) ? a.ln_g[c] : 0.f; lb[e] = (c < d) ? a.ln_b[c] : 0.f; }
+  float2 bq[NT], bk[NT], bv[NT];
+  load_bias_frag(bq, a.bq, d, ng, lane); load_bias_frag(bk, a.bk, d, ng, lane); load_bias_frag(bv, a.bv, d, ng, lane);
+  __syncthreads();
+  FZ_TL(0, 1);
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * TM;
-    // prologue: warp w owns tile rows w*4 .. w*4+3
+    // ---- prologue: [embedding] + LayerNorm of the warp's 4 rows -> fp32 q1 (HBM) and the two operand tiles
+    float x[RPW][NE];
+    if (a.embed) {         // x = (E0[id]*sqrt(d) + P[pos]) * dropout   (modules.py:124-130, ADER.py:41-60)
+      int rowi[RPW], idv[RPW], pp[RPW];
 #pragma unroll
-    for (int rr = 0; rr < TM / 8; ++rr) {
-      const int r = warp * (TM / 8) + rr, tk = t0 + r;
-      float x[NE];
-      if (tk < T) {
-        if (a.embed) {     // x = (E0[id]*sqrt(d) + P[pos]) * dropout   (modules.py:124-130, ADER.py:41-60)
-          const int row = a.tok_row[tk];
-          const int p = a.L - a.row_len[row] + (tk - a.row_off[row]);
-          const long long id = a.tok_id[tk];
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int tk = t0 + warp * RPW + rr;
+        rowi[rr] = (tk < T) ? a.tok_row[tk] : 0; idv[rr] = (tk < T) ? a.tok_id[tk] : 0;
+      }
 #pragma unroll
-          for (int e = 0; e < NE; ++e) {
-            const int c = lane + 32 * e;
-            float v = 0.f;
-            if (c < d) {
-              v = a.table[id * d + c] * a.sqrt_d + a.pos_table[p * d + c];
-              if (a.drop_p > 0.f) v *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
-              a.Xw[(long long)tk * d + c] = v;
-            }
-            x[e] = v;
-          }
-        } else {
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int tk = t0 + warp * RPW + rr;
+        pp[rr] = (tk < T) ? a.L - a.row_len[rowi[rr]] + (tk - a.row_off[rowi[rr]]) : 0;
+      }
 #pragma unroll
-          for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; x[e] = (c < d) ? a.X[(long long)tk * d + c] : 0.f; }
-        }
-        float s = 0.f, mx = 0.f;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) { s += x[e]; mx = fmaxf(mx, fabsf(x[e])); }
-        const float sc = row_scale(warp_max(mx));
-        const float mean = warp_sum(s) / (float)d;
-        float q = 0.f;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = x[e] - mean; q += u * u; } }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-8f);
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int tk = t0 + warp * RPW + rr;
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
           const int c = lane + 32 * e;
-          float y = 0.f;
-          if (c < d) { y = a.ln_g[c] * ((x[e] - mean) * rstd) + a.ln_b[c]; a.Q1[(long long)tk * d + c] = y; }
-          A1[r * LDS + c] = to_op(y);
-          A2[r * LDS + c] = to_op(x[e] * sc);
+          x[rr][e] = (tk < T && c < d) ? a.table[(long long)idv[rr] * d + c] * a.sqrt_d + a.pos_table[pp[rr] * d + c] : 0.f;
         }
-        if (lane == 0) { a.mean[tk] = mean; a.rstd[tk] = rstd; rs[r] = 1.f / sc; }
-      } else {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; A1[r * LDS + c] = to_op(0.f); A2[r * LDS + c] = to_op(0.f); }
-        if (lane == 0) rs[r] = 1.f;
       }
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int c = lane + 32 * e;
+          if (tk < T && c < d) {
+            if (a.drop_p > 0.f) x[rr][e] *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
+            a.Xw[(long long)tk * d + c] = x[rr][e];
+          }
+        }
+      }
+    } else {
+      load_rows(x, a.X, t0, T, d, warp, lane);
+    }
+    float sm[RPW], mx[RPW], qv[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      float s = 0.f, m = 0.f;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) { s += x[rr][e]; m = fmaxf(m, fabsf(x[rr][e])); }
+      sm[rr] = s; mx[rr] = m;
+    }
+    warp_sum_n(sm); warp_max_n(mx);
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      sm[rr] /= (float)d;
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = x[rr][e] - sm[rr]; q += u * u; } }
+      qv[rr] = q;
+    }
+    warp_sum_n(qv);
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int r = warp * RPW + rr, tk = t0 + r;
+      const float mean = sm[rr], rstd = 1.0f / sqrtf(qv[rr] / (float)d + 1e-8f);
+      const float sc = row_scale(mx[rr]);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        float y = 0.f;
+        if (tk < T && c < d) { y = lg[e] * ((x[rr][e] - mean) * rstd) + lb[e]; a.Q1[(long long)tk * d + c] = y; }
+        A1[r * LDS + c] = to_op(y);
+        A2[r * LDS + c] = to_op(x[rr][e] * sc);
+      }
+      if (lane == 0) { rs[r] = 1.f / sc; if (tk < T) { a.mean[tk] = mean; a.rstd[tk] = rstd; } }
     }
     __syncthreads();
+    FZ_TL(0, 2);
     if (first) { mbar_wait(bar, 0); first = false; }
+    FZ_TL(0, 3);
     float acc[NT][4];
     zero_acc(acc);
     warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.Q + (long long)(t0 + r) * d + c) = make_float2(v0 + a.bq[c], v1 + a.bq[c + 1]);
+        *reinterpret_cast<float2*>(a.Q + (long long)(t0 + r) * d + c) = make_float2(v0 + bq[j].x, v1 + bq[j].y);
     });
+    FZ_TL(0, 4);
     zero_acc(acc);
     warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.K + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + a.bk[c], v1 * rs[r] + a.bk[c + 1]);
+        *reinterpret_cast<float2*>(a.K + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bk[j].x, v1 * rs[r] + bk[j].y);
     });
     zero_acc(acc);
     warp_gemm(A2 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.V + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + a.bv[c], v1 * rs[r] + a.bv[c + 1]);
+        *reinterpret_cast<float2*>(a.V + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bv[j].x, v1 * rs[r] + bv[j].y);
     });
     __syncthreads();
+    FZ_TL(0, 5);
   }
 }
 
@@ -506,23 +589,29 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
   }
   // zero the padding columns of the hidden tile once (the epilogue only writes columns < d)
   for (int idx = tid; idx < TM * LDS; idx += NTHR) A2[idx] = to_op(0.f);
-  __syncthreads();
   const int mt = warp & 1, ng = warp >> 1;
+  float2 b1[NT], b2[NT];
+  load_bias_frag(b1, a.b1, d, ng, lane); load_bias_frag(b2, a.b2, d, ng, lane);
+  __syncthreads();
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * TM;
-    stage_tile16(A1, a.Z, t0, T, d);
+    float z[RPW][NE];
+    load_rows(z, a.Z, t0, T, d, warp, lane);
+    float2 zf[NT][2];
+    load_frag(zf, a.Z, t0, T, d, mt, ng, lane);          // residual operand of the second epilogue
+    put_rows(A1, z, warp, lane);
     __syncthreads();
     if (first) { mbar_wait(bar, 0); first = false; }
     float acc[NT][4];
     zero_acc(acc);
     warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (c < d) {
         float h0 = 0.f, h1 = 0.f;
         if (t0 + r < T) {
           const long long e = (long long)(t0 + r) * d + c;
-          h0 = fmaxf(v0 + a.b1[c], 0.f); h1 = fmaxf(v1 + a.b1[c + 1], 0.f);
+          h0 = fmaxf(v0 + b1[j].x, 0.f); h1 = fmaxf(v1 + b1[j].y, 0.f);
           if (a.drop_p > 0.f) { h0 *= drop_scale(seed_eff, a.site1, (uint64_t)e, a.drop_p); h1 *= drop_scale(seed_eff, a.site1, (uint64_t)e + 1, a.drop_p); }
           *reinterpret_cast<float2*>(a.H + e) = make_float2(h0, h1);
         }
@@ -532,34 +621,44 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
     __syncthreads();
     zero_acc(acc);
     warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (t0 + r < T && c < d) {
         const long long e = (long long)(t0 + r) * d + c;
-        float x0 = v0 + a.b2[c], x1 = v1 + a.b2[c + 1];
+        float x0 = v0 + b2[j].x, x1 = v1 + b2[j].y;
         if (a.drop_p > 0.f) { x0 *= drop_scale(seed_eff, a.site2, (uint64_t)e, a.drop_p); x1 *= drop_scale(seed_eff, a.site2, (uint64_t)e + 1, a.drop_p); }
-        const float2 z = *reinterpret_cast<const float2*>(a.Z + e);
-        *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + z.x, x1 + z.y);
+        *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + zf[j][h].x, x1 + zf[j][h].y);
       }
     });
     __syncthreads();
   }
 }
 
-// ---- LayerNorm backward of one fp32 tile row held in shared memory ------------------------------------
-// dx = rstd*(g - mean(g) - xhat*mean(g*xhat)),  g = dout*gamma.  Returns dx in v[] (lane-strided columns).
-__device__ __forceinline__ void ln_bwd_row(const float* __restrict__ dout_row /*smem*/, const float* __restrict__ x_row,
-                                           float mean, float rstd, const float* __restrict__ gamma, int d, int lane,
-                                           float (&dx)[NE], float (&xv)[NE]) {
-  float g[NE], xh[NE]; float s1 = 0.f, s2 = 0.f;
+// ---- LayerNorm backward of the warp's 4 rows (dout in a shared fp32 tile, x / mean / rstd preloaded) ----------
+// dx = rstd*(g - mean(g) - xhat*mean(g*xhat)),  g = dout*gamma.
+__device__ __forceinline__ void ln_bwd_rows(const float* __restrict__ Ft, const float (&xv)[RPW][NE], const float (&mean)[RPW],
+                                            const float (&rstd)[RPW], const float (&gam)[NE], int d, int warp, int lane,
+                                            float (&dx)[RPW][NE]) {
+  float s1[RPW], s2[RPW];
+  float xh[RPW][NE];
 #pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    if (c < d) { xv[e] = x_row[c]; xh[e] = (xv[e] - mean) * rstd; g[e] = dout_row[c] * gamma[c]; s1 += g[e]; s2 += g[e] * xh[e]; }
-    else { xv[e] = 0.f; xh[e] = 0.f; g[e] = 0.f; }
+  for (int rr = 0; rr < RPW; ++rr) {
+    const float* dr = Ft + (warp * RPW + rr) * FT_LD;
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      if (c < d) { xh[rr][e] = (xv[rr][e] - mean[rr]) * rstd[rr]; dx[rr][e] = dr[c] * gam[e]; a1 += dx[rr][e]; a2 += dx[rr][e] * xh[rr][e]; }
+      else { xh[rr][e] = 0.f; dx[rr][e] = 0.f; }
+    }
+    s1[rr] = a1; s2[rr] = a2;
   }
-  s1 = warp_sum(s1) / (float)d; s2 = warp_sum(s2) / (float)d;
+  warp_sum_n(s1); warp_sum_n(s2);
 #pragma unroll
-  for (int e = 0; e < NE; ++e) dx[e] = rstd * (g[e] - s1 - xh[e] * s2);
+  for (int rr = 0; rr < RPW; ++rr) {
+    const float m1 = s1[rr] / (float)d, m2 = s2[rr] / (float)d;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) dx[rr][e] = rstd[rr] * (dx[rr][e] - m1 - xh[rr][e] * m2);
+  }
 }
 
 // ---- backward: FFN dgrad + LN2 backward --------------------------------------------------------------
@@ -575,6 +674,7 @@ struct FfnBwdArgs {
 constexpr size_t FFN_BWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES + TM * 4 + 16;
 
 __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ FfnBwdArgs a) {
+  FZ_TL(1, 0);
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
   extern __shared__ __align__(128) uint8_t smem[];
   op_t* Wsm = reinterpret_cast<op_t*>(smem);
@@ -594,65 +694,100 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ Ffn
     load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.W1b, bar);
   }
   for (int idx = tid; idx < TM * LDS; idx += NTHR) A2[idx] = to_op(0.f);
+  float gam[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; gam[e] = (c < d) ? a.ln_g[c] : 0.f; }
   __syncthreads();
+  FZ_TL(1, 1);
   const int mt = warp & 1, ng = warp >> 1;
   const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * TM;
-    stage_rows_scaled(A1, rs, a.gX, t0, T, d, warp, lane, a.drop_p, seed_eff, a.site2, a.gO);   // x_out = drop(h.W2 + b2) + z
+    // gOut = gX * dropout(site2): x_out = drop(h.W2 + b2) + z   (modules.py:259-266)
+    float go[RPW][NE];
+    load_rows(go, a.gX, t0, T, d, warp, lane);
+    float2 hf[NT][2], gxf[NT][2];
+    load_frag(hf, a.H, t0, T, d, mt, ng, lane);
+    load_frag(gxf, a.gX, t0, T, d, mt, ng, lane);
+    if (a.drop_p > 0.f) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int c = lane + 32 * e;
+          if (tk < T && c < d) {
+            const long long el = (long long)tk * d + c;
+            go[rr][e] *= drop_scale(seed_eff, a.site2, (uint64_t)el, a.drop_p);
+            a.gO[el] = go[rr][e];
+          }
+        }
+      }
+    }
+    put_rows_scaled(A1, rs, go, warp, lane);
     __syncthreads();
+    FZ_TL(1, 2);
     if (first) { mbar_wait(bar, 0); first = false; }
+    FZ_TL(1, 3);
     float acc[NT][4];
     zero_acc(acc);
     warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
     // gH = (gOut . W2^T) * [h > 0] / (1 - p)   (h is stored post-dropout)
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (c < d) {
         float g0 = 0.f, g1 = 0.f;
         if (t0 + r < T) {
-          const long long e = (long long)(t0 + r) * d + c;
-          const float2 h = *reinterpret_cast<const float2*>(a.H + e);
-          g0 = h.x > 0.f ? v0 * inv_keep : 0.f; g1 = h.y > 0.f ? v1 * inv_keep : 0.f;   // still carries the row scale
-          *reinterpret_cast<float2*>(a.gH + e) = make_float2(g0 * rs[r], g1 * rs[r]);
+          g0 = hf[j][h].x > 0.f ? v0 * inv_keep : 0.f; g1 = hf[j][h].y > 0.f ? v1 * inv_keep : 0.f;   // still carries the row scale
+          *reinterpret_cast<float2*>(a.gH + (long long)(t0 + r) * d + c) = make_float2(g0 * rs[r], g1 * rs[r]);
         }
         st_op2(A2 + r * LDS + c, g0, g1);
       }
     });
+    // rows of the LayerNorm-backward pass: issue their loads now, they land while the second product runs
+    float yv[RPW][NE], q1[RPW][NE], mean[RPW], rstd[RPW];
+    load_rows(yv, a.Y, t0, T, d, warp, lane);
+    load_rows(q1, a.Q1, t0, T, d, warp, lane);
+    load_row_scalars(mean, a.mean2, t0, T, warp);
+    load_row_scalars(rstd, a.rstd2, t0, T, warp);
     __syncthreads();
+    FZ_TL(1, 4);
     zero_acc(acc);
     warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
     // gZ = gH . W1^T + gX   (residual z -> x_out)
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (c < d) {
         float z0 = 0.f, z1 = 0.f;
         if (t0 + r < T) {
-          const long long e = (long long)(t0 + r) * d + c;
-          const float2 gx = *reinterpret_cast<const float2*>(a.gX + e);
-          z0 = v0 * rs[r] + gx.x; z1 = v1 * rs[r] + gx.y;
-          *reinterpret_cast<float2*>(a.gZ + e) = make_float2(z0, z1);
+          z0 = v0 * rs[r] + gxf[j][h].x; z1 = v1 * rs[r] + gxf[j][h].y;
+          *reinterpret_cast<float2*>(a.gZ + (long long)(t0 + r) * d + c) = make_float2(z0, z1);
         }
         *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(z0, z1);
       }
     });
     __syncthreads();
+    FZ_TL(1, 5);
     // gY = LN2 backward;  D = gY . (Y - q1)  (= sum_j dP_ij P_ij of the attention softmax backward)
+    float dx[RPW][NE], dd[RPW];
+    ln_bwd_rows(Ft, yv, mean, rstd, gam, d, warp, lane, dx);
 #pragma unroll
-    for (int rr = 0; rr < TM / 8; ++rr) {
-      const int r = warp * (TM / 8) + rr, tk = t0 + r;
-      if (tk >= T) continue;
-      float dx[NE], yv[NE];
-      ln_bwd_row(Ft + r * FT_LD, a.Y + (long long)tk * d, a.mean2[tk], a.rstd2[tk], a.ln_g, d, lane, dx, yv);
-      float dd = 0.f;
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+      float acc_d = 0.f;
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
         const int c = lane + 32 * e;
-        if (c < d) { a.gY[(long long)tk * d + c] = dx[e]; dd = fmaf(dx[e], yv[e] - a.Q1[(long long)tk * d + c], dd); }
+        if (tk < T && c < d) { a.gY[(long long)tk * d + c] = dx[rr][e]; acc_d = fmaf(dx[rr][e], yv[rr][e] - q1[rr][e], acc_d); }
       }
-      dd = warp_sum(dd);
-      if (lane == 0) a.D[tk] = dd;
+      dd[rr] = acc_d;
+    }
+    warp_sum_n(dd);
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) { const int tk = t0 + warp * RPW + rr; if (tk < T) a.D[tk] = dd[rr]; }
     }
     __syncthreads();
+    FZ_TL(1, 6);
   }
 }
 
@@ -887,51 +1022,64 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
     load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.Wkb, bar);
     load_wmat(smem_u32(Wsm) + 2 * WMAT_BYTES, a.Wvb, bar);
   }
+  float gam[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; gam[e] = (c < d) ? a.ln_g[c] : 0.f; }
   __syncthreads();
   const int mt = warp & 1, ng = warp >> 1;
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t0 = tile * TM;
-    stage_rows_scaled(A1, rsq, a.gQ, t0, T, d, warp, lane);
-    stage_rows_scaled(A2, rskv, a.gK, t0, T, d, warp, lane, 0.f, 0, 0, nullptr, a.gV, A3);
+    {
+      float gq[RPW][NE], gk[RPW][NE], gv[RPW][NE];
+      load_rows(gq, a.gQ, t0, T, d, warp, lane);
+      load_rows(gk, a.gK, t0, T, d, warp, lane);
+      load_rows(gv, a.gV, t0, T, d, warp, lane);
+      put_rows_scaled(A1, rsq, gq, warp, lane);
+      put_rows_scaled(A2, rskv, gk, warp, lane, gv, A3);
+    }
+    float2 gyf[NT][2];
+    load_frag(gyf, a.gY, t0, T, d, mt, ng, lane);
     __syncthreads();
     if (first) { mbar_wait(bar, 0); first = false; }
     float acc[NT][4];
     zero_acc(acc);
     warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
     // gQ1 = gQ . Wq^T + gY   (y = attn + q1)
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (c < d) {
         float q0 = 0.f, q1 = 0.f;
         if (t0 + r < T) {
-          const long long e = (long long)(t0 + r) * d + c;
-          const float2 gy = *reinterpret_cast<const float2*>(a.gY + e);
-          q0 = v0 * rsq[r] + gy.x; q1 = v1 * rsq[r] + gy.y;
-          *reinterpret_cast<float2*>(a.gQ1 + e) = make_float2(q0, q1);
+          q0 = v0 * rsq[r] + gyf[j][h].x; q1 = v1 * rsq[r] + gyf[j][h].y;
+          *reinterpret_cast<float2*>(a.gQ1 + (long long)(t0 + r) * d + c) = make_float2(q0, q1);
         }
         *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(q0, q1);
       }
     });
+    // rows of the LayerNorm-backward pass: loads in flight during the K/V products
+    float xv[RPW][NE], mean[RPW], rstd[RPW];
+    load_rows(xv, a.X, t0, T, d, warp, lane);
+    load_row_scalars(mean, a.mean1, t0, T, warp);
+    load_row_scalars(rstd, a.rstd1, t0, T, warp);
     zero_acc(acc);
     warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
     warp_gemm(A3 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
     __syncthreads();                       // every warp is done reading A1..A3
-    for_acc(acc, mt, ng, lane, [&](int r, int c, float v0, float v1) {
+    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
       if (c < d) *reinterpret_cast<float2*>(Ft2 + r * FT_LD + c) = make_float2(v0 * rskv[r], v1 * rskv[r]);
     });
     __syncthreads();
-    // gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ1)
+    // gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ1)   [* embedding-dropout mask in the first block]
+    float dx[RPW][NE];
+    ln_bwd_rows(Ft, xv, mean, rstd, gam, d, warp, lane, dx);
 #pragma unroll
-    for (int rr = 0; rr < TM / 8; ++rr) {
-      const int r = warp * (TM / 8) + rr, tk = t0 + r;
-      if (tk >= T) continue;
-      float dx[NE], xv[NE];
-      ln_bwd_row(Ft + r * FT_LD, a.X + (long long)tk * d, a.mean1[tk], a.rstd1[tk], a.ln_g, d, lane, dx, xv);
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int r = warp * RPW + rr, tk = t0 + r;
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
         const int c = lane + 32 * e;
-        if (c < d) {
-          float v = dx[e] + Ft2[r * FT_LD + c];
+        if (tk < T && c < d) {
+          float v = dx[rr][e] + Ft2[r * FT_LD + c];
           if (a.drop_p > 0.f) v *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
           a.gXin[(long long)tk * d + c] = v;
         }
