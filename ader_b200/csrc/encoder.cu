@@ -1043,6 +1043,8 @@ static void fused_attrs() {
   cudaFuncSetAttribute(fz::k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_BWD_SMEM);
   cudaFuncSetAttribute(fz::k_qkv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::QKV_BWD_SMEM);
   cudaFuncSetAttribute(fz::k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::WGRAD_SMEM);
+  cudaFuncSetAttribute(fz::k_attn_ln_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * fz::att_rows_cap(64) * fz::KP * 4);
+  cudaFuncSetAttribute(fz::k_attn_bwd_s1, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::att_bwd_smem(64, fz::KP));
   done = true;
 }
 static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
@@ -1080,7 +1082,8 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
-  const int warp_grid = cdiv((long long)Tcap * 32, 256);
+  const int warp_grid = cdiv(Tcap, fz::ATT_TOK);
+  const size_t att_smem = sizeof(float) * 2 * (size_t)fz::att_rows_cap(L) * d;
   for (int b = 0; b < m->num_blocks; ++b) {
     const float* P = theta + l.block(b);
     float* X = w.slot[b][0]; float* Q1 = w.slot[b][1]; float* Qp = w.slot[b][2]; float* Kp = w.slot[b][3];
@@ -1102,7 +1105,7 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
     aa.probs = w.probs[b]; aa.Y = Y; aa.Z = Z; aa.mean2 = w.mean2[b]; aa.rstd2 = w.rstd2[b];
     aa.ln_b = P + l.ln2b; aa.ln_g = P + l.ln2g; aa.dT = dT; aa.d = d; aa.nh = m->num_heads; aa.L = L; aa.Tcap = Tcap;
     aa.drop_p = dropout_rate; aa.seed = seed; aa.d_step = d_step; aa.site = 1u + 3u * b;
-    fz::k_attn_ln_fwd<<<warp_grid, 256, 0, st>>>(aa);
+    fz::k_attn_ln_fwd<<<warp_grid, 256, att_smem, st>>>(aa);
 
     fz::FfnFwdArgs fa;
     fa.Z = Z; fa.H = H; fa.Xn = Xn; fa.W1 = shadow_of(w, b, 3, 0); fa.W2 = shadow_of(w, b, 4, 0);
@@ -1162,7 +1165,7 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
     ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
     ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.d_step = d_step; ab.site = 1u + 3u * b;
-    if (m->num_heads == 1) fz::k_attn_bwd_w1<<<ln_grid, 256, 0, st>>>(ab);
+    if (m->num_heads == 1) fz::k_attn_bwd_s1<<<cdiv(Tcap, fz::ATT_TOK), 256, fz::att_bwd_smem(L, d), st>>>(ab);
     else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
 
     fz::QkvBwdArgs qb;

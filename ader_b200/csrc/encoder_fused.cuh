@@ -481,22 +481,59 @@ struct AttnFwdArgs {
   float drop_p; uint64_t seed; const int* d_step; uint32_t site;
 };
 
+// cooperative copy of n2 float2 (rows are contiguous [n, d] in global memory, 8-byte aligned), 8 loads in flight per thread
+__device__ __forceinline__ void stage_f2(float* __restrict__ dst, const float* __restrict__ src, int n2) {
+  const float2* s2 = reinterpret_cast<const float2*>(src);
+  float2* d2 = reinterpret_cast<float2*>(dst);
+  for (int base = threadIdx.x; base < n2; base += 8 * blockDim.x) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int idx = base + u * blockDim.x; if (idx < n2) v[u] = s2[idx]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int idx = base + u * blockDim.x; if (idx < n2) d2[idx] = v[u]; }
+  }
+}
+constexpr int ATT_TOK = 8;          // tokens (= warps) per CTA of the warp-per-token attention kernels
+__host__ __device__ constexpr int att_rows_cap(int L) { return L + ATT_TOK - 1; }   // K/V rows a CTA can need
+
+// The 8 consecutive tokens of a CTA belong to at most a few sessions, and a token only attends to earlier tokens of
+// its own session, so the union of all keys the CTA needs is ONE contiguous token range [row start of the first
+// token, last token of the CTA]: <= L + 7 rows.  K and V of that range are staged in shared memory by a cooperative,
+// fully overlapped copy (one L2 round trip for the CTA), and the warps then work out of shared memory.
 __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
+  extern __shared__ __align__(16) float att_sm[];
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
-  const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (tk >= *a.dT) return;
+  const int T = *a.dT;
+  const int t0 = blockIdx.x * ATT_TOK;
+  if (t0 >= T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, L = a.L;
+  const int tk = min(t0 + warp, T - 1);          // surplus warps of the last CTA shadow its last token (no stores)
+  const bool live = t0 + warp < T;
   const int row = a.tok_row[tk];
+  const int lo = a.row_off[a.tok_row[t0]];
   const int off = a.row_off[row];
+  const int hi = min(t0 + ATT_TOK, T);
+  float q[NE], o[NE], q1[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    q[e] = (c < d) ? a.Q[(long long)tk * d + c] : 0.f;
+    q1[e] = (c < d) ? a.Q1[(long long)tk * d + c] : 0.f;
+    o[e] = 0.f;
+  }
+  float* Ks = att_sm;
+  float* Vs = att_sm + att_rows_cap(L) * d;
+  stage_f2(Ks, a.K + (long long)lo * d, (hi - lo) * d / 2);
+  stage_f2(Vs, a.V + (long long)lo * d, (hi - lo) * d / 2);
+  __syncthreads();
+  if (!live) return;
   const int i = tk - off;                       // query index inside its session; keys 0..i
   const int dh = d / a.nh;
   const float inv_denom = 1.0f / sqrtf((float)dh);
   const int j8 = lane & 7;
-  float q[NE], o[NE];
-#pragma unroll
-  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; q[e] = (c < d) ? a.Q[(long long)tk * d + c] : 0.f; o[e] = 0.f; }
-  const float* Krow = a.K + (long long)off * d;
-  const float* Vrow = a.V + (long long)off * d;
+  const float* Krow = Ks + (off - lo) * d;
+  const float* Vrow = Vs + (off - lo) * d;
   for (int h = 0; h < a.nh; ++h) {
     const int c_lo = h * dh, c_hi = c_lo + dh;
     const long long po = ((long long)h * a.Tcap + tk) * L;
@@ -544,7 +581,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ 
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
     const int c = lane + 32 * e;
-    y[e] = (c < d) ? o[e] + a.Q1[(long long)tk * d + c] : 0.f;
+    y[e] = (c < d) ? o[e] + q1[e] : 0.f;
     if (c < d) a.Y[(long long)tk * d + c] = y[e];
     sm += y[e];
   }
@@ -976,6 +1013,105 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ 
     }
     block_axpy(gk, ds, a.Q + (long long)(off + q0) * d, d, cnt, 0, d, lane);
     block_axpy(gv, pd, a.gY + (long long)(off + q0) * d, d, cnt, 0, d, lane);
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) {
+      a.gQ[(long long)tk * d + c] = gq[e];
+      a.gK[(long long)tk * d + c] = gk[e];
+      a.gV[(long long)tk * d + c] = gv[e];
+    }
+  }
+}
+
+// Shared-memory form of the single-head backward kernel (same staging idea as the forward kernel).  Phase 1 (query
+// role) stages V and K of [row start of the first token, last token of the CTA]; phase 2 (key role) re-uses the same
+// buffers for gY and Q of [first token of the CTA, end of the last token's session]: both ranges are <= L + 7 rows.
+// The probabilities a token needs (its own row as a query, its column as a key) and the D values of its later
+// queries are fetched into registers up front, so the block loops touch no global memory.
+__host__ __device__ constexpr int att_bwd_smem(int L, int d) { return 2 * att_rows_cap(L) * d * 4; }
+__global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ AttnBwdArgs a) {
+  extern __shared__ __align__(16) float att_sm[];
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
+  const int T = *a.dT;
+  const int t0 = blockIdx.x * ATT_TOK;
+  if (t0 >= T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = a.d, L = a.L;
+  const int tk = min(t0 + warp, T - 1);
+  const bool live = t0 + warp < T;
+  const int row = a.tok_row[tk];
+  const int lo = a.row_off[a.tok_row[t0]];
+  const int hi = min(t0 + ATT_TOK, T);
+  const int hi2 = a.row_off[a.tok_row[hi - 1] + 1];          // end of the session of the CTA's last token
+  const int off = a.row_off[row];
+  const int n = a.row_off[row + 1] - off;
+  const int i = tk - off;
+  const float inv_denom = 1.0f / sqrtf((float)d);
+  const int j8 = lane & 7;
+  float gy[NE], vt[NE], gq[NE], gk[NE], gv[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int c = lane + 32 * e;
+    gy[e] = (c < d) ? a.gY[(long long)tk * d + c] : 0.f;
+    vt[e] = (c < d) ? a.V[(long long)tk * d + c] : 0.f;
+    gq[e] = gk[e] = gv[e] = 0.f;
+  }
+  const float Di = a.D[tk];
+  // probabilities / dropout scales / D: own row (query role: key lane + 32u) and own column (key role: query tk + lane + 32u)
+  float pq[2], sq[2], pk[2], sk[2], dk[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    pq[u] = 0.f; sq[u] = 1.f; pk[u] = 0.f; sk[u] = 1.f; dk[u] = 0.f;
+    if (j <= i) {
+      const long long po = (long long)tk * L + j;
+      pq[u] = a.probs[po];
+      if (a.drop_p > 0.f) sq[u] = drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p);
+    }
+    if (i + j < n) {
+      const int tq = tk + j;
+      const long long po = (long long)tq * L + i;
+      pk[u] = a.probs[po];
+      dk[u] = a.D[tq];
+      if (a.drop_p > 0.f) sk[u] = drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p);
+    }
+  }
+  float* As = att_sm;
+  float* Bs = att_sm + att_rows_cap(L) * d;
+  // ---- phase 1, query role: dS_ij = P_ij (dP_ij - D_i) / sqrt(d),  gQ[i] = sum_{j<=i} dS_ij K[j]
+  stage_f2(As, a.V + (long long)lo * d, (hi - lo) * d / 2);
+  stage_f2(Bs, a.K + (long long)lo * d, (hi - lo) * d / 2);
+  __syncthreads();
+  if (live) {
+    for (int j0 = 0; j0 <= i; j0 += KB) {
+      const int cnt = min(KB, i + 1 - j0);
+      const float dp = block_dots(gy, As + (off - lo + j0) * d, d, cnt, 0, d, lane);
+      const int j = j0 + j8;
+      const float P = __shfl_sync(0xffffffffu, (j < 32) ? pq[0] : pq[1], j & 31);
+      const float scl = __shfl_sync(0xffffffffu, (j < 32) ? sq[0] : sq[1], j & 31);
+      const float ds = (j8 < cnt) ? P * (dp * scl - Di) * inv_denom : 0.f;
+      block_axpy(gq, ds, Bs + (off - lo + j0) * d, d, cnt, 0, d, lane);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2, key role: gK[i] = sum_{q>=i} dS_qi Q[q],  gV[i] = sum_{q>=i} Pd_qi gY[q]
+  stage_f2(As, a.gY + (long long)t0 * d, (hi2 - t0) * d / 2);
+  stage_f2(Bs, a.Q + (long long)t0 * d, (hi2 - t0) * d / 2);
+  __syncthreads();
+  if (!live) return;
+  for (int q0 = 0; i + q0 < n; q0 += KB) {          // queries tk + q0 .. of the same session
+    const int cnt = min(KB, n - i - q0);
+    const float dp = block_dots(vt, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
+    const int u = q0 + j8;
+    const float P = __shfl_sync(0xffffffffu, (u < 32) ? pk[0] : pk[1], u & 31);
+    const float scl = __shfl_sync(0xffffffffu, (u < 32) ? sk[0] : sk[1], u & 31);
+    const float Dq = __shfl_sync(0xffffffffu, (u < 32) ? dk[0] : dk[1], u & 31);
+    const float ds = (j8 < cnt) ? P * (dp * scl - Dq) * inv_denom : 0.f;
+    const float pd = (j8 < cnt) ? P * scl : 0.f;
+    block_axpy(gk, ds, Bs + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
+    block_axpy(gv, pd, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
   }
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
