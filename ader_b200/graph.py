@@ -95,8 +95,8 @@ class GraphStep:
             ops.gather_rows_i32(t_ids, self.ti, self.ids[:self.n_train])
             ops.gather_rows_i32(t_lab.view(-1, 1), self.ti, self.pos.view(-1, 1))
             if self.n_ex > 0:
-                ops.gather_rows_i32(e_ids, self.ei, self.ids[self.n_train:])
-                ops.gather_rows_i32(e_aux.view(-1, 1), self.ei, self.aux.view(-1, 1))
+                ops.gather_rows_i32(e_ids, self.ei[:self.n_ex], self.ids[self.n_train:])
+                ops.gather_rows_i32(e_aux.view(-1, 1), self.ei[:self.n_ex], self.aux[:self.n_ex].view(-1, 1))
         kw = {}
         if self.n_ex > 0:
             if m.mode == m.KD:

@@ -66,6 +66,7 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     p.add_argument("--loss_impl", default="tc", choices=["tc", "exact"], type=str)      # logits+CE+KD: tcgen05 bf16 / fp32
     p.add_argument("--encoder_impl", default=None, choices=["tc", "exact"], type=str)  # training encoder (default follows loss_impl)
     p.add_argument("--infer_encoder_impl", default="exact", choices=["tc", "exact"], type=str)  # eval / herding encoder
+    p.add_argument("--graph", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))  # CUDA-graph train step
     return p
 
 
@@ -84,6 +85,35 @@ class PeriodTrainer:
         self.rows_seen = 0
         self.trace = None
         self.trace_rows = None
+        self.gs = None                  # the step as CUDA graphs (full-size batches; odd-size batches run eagerly)
+        self._graph_tried = False
+
+    def _graph(self, n_train: int, n_ex: int):
+        """Capture the step for this period's batch geometry on first use (ader_b200/graph.py)."""
+        if self._graph_tried or not getattr(self.args, "graph", True):
+            return self.gs
+        self._graph_tried = True
+        m, args = self.model, self.args
+        if m.encoder_impl != "tc" and args.dropout_rate > 0:
+            return None
+        dev = m.device
+        e_ids = e_aux = teacher = None
+        if self.es is not None:
+            if m.disable_distillation:
+                e_aux = self.e_lab
+            elif getattr(self.es, "teacher", None) is not None:
+                e_aux = torch.as_tensor(np.asarray(self.es.logits, dtype=np.int32)).to(dev)
+                teacher = self.es.teacher
+            else:
+                return None              # host-resident teacher lists (reference feed): eager path
+            e_ids = self.e_ids
+        mean_tok = n_train * float(np.mean(self.t_nin)) + (n_ex * float(np.mean(self.e_nin)) if self.es is not None else 0.0)
+        caps = [int(mean_tok * f) + 64 for f in (1.1, 1.3, 1.7)]
+        self.gs = m.graph_step(n_train, n_ex, self.max_item, args.lr, args.dropout_rate, teacher=teacher,
+                               sources=(self.t_ids, self.t_lab, e_ids, e_aux) if self.es is not None
+                               else (self.t_ids, self.t_lab, None, None), tcaps=caps)
+        self.gs_shape = (n_train, n_ex)
+        return self.gs
 
     def step(self):
         loss = self._step()
@@ -96,8 +126,13 @@ class PeriodTrainer:
     def _step(self):
         m, dev, L = self.model, self.model.device, self.model.hp.maxlen
         ti = self.ts.next_indices()
-        ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         n_tok = int(self.t_nin[ti].sum())
+        if self.es is None and len(ti) == self.args.batch_size:
+            gs = self._graph(len(ti), 0)
+            if gs is not None and self.gs_shape == (len(ti), 0):
+                self.rows_seen += len(ti)
+                return gs.run_indices(ti, None, n_tok)
+        ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         if self.es is None:
             ids = torch.empty((len(ti), L), dtype=torch.int32, device=dev)
             ops.gather_rows_i32(self.t_ids, ti_d, ids)
@@ -106,8 +141,13 @@ class PeriodTrainer:
             self.rows_seen += len(ti)
             return loss
         ei = self.es.next_indices()
-        ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         n_tok += int(self.e_nin[ei].sum())
+        if len(ti) == self.args.batch_size and len(ei) == self.es.batch_size and len(ei) > 0:
+            gs = self._graph(len(ti), len(ei))
+            if gs is not None and self.gs_shape == (len(ti), len(ei)):
+                self.rows_seen += len(ti) + len(ei)
+                return gs.run_indices(ti, ei, n_tok)
+        ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         ids = torch.empty((len(ti) + len(ei), L), dtype=torch.int32, device=dev)
         ops.gather_rows_i32(self.t_ids, ti_d, ids[:len(ti)])
         if len(ei):

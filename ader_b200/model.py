@@ -178,7 +178,7 @@ class Ader:
                 raise ValueError("exemplar rows were fed but the loss is vanilla (call update_loss first)")
         # dropout stream: (seed, step).  Under CUDA-graph capture the step is read on the device from the Adam
         # state (incremented by the optimiser kernel), so every replay draws fresh masks.
-        d_step = self.adam_state if _device_step else None
+        d_step = self.adam_state if (_device_step and self.encoder_impl == "tc") else None   # exact encoder: graphs only at p = 0
         seed = (self.seed << 32) + (0 if _device_step else self.global_step)
         rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl, d_step=d_step)
         if _events:

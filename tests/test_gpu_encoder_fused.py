@@ -158,3 +158,39 @@ def test_fused_rejects_wide_models():
     ids = torch.tensor(_ids(np.random.RandomState(0), 4, 50, 90), device=m.device)
     with pytest.raises(_lib.AderError):
         m.encode(ids, impl="tc")
+
+
+def test_graph_step_replays_match_eager_steps():
+    """GraphStep (CUDA-graph capture of train_step, device-side dropout counter) == the eager step, bit for bit:
+    same kernels, same (seed + step) dropout stream, over several steps and both input modes."""
+    rng = np.random.RandomState(7)
+    B, Me, V, Vp, E = 48, 16, 280, 250, 40
+    pool = _ids(rng, 200, 50, V)
+    lab = rng.randint(1, V + 1, 200).astype(np.int32)
+    ex = _ids(rng, E, 50, Vp)
+    steps = [(rng.randint(0, 200, B), rng.randint(0, E, Me)) for _ in range(4)]
+    out = {}
+    for mode in ("eager", "graph"):
+        m, hp, _ = _model(300, loss_impl="tc", lr=1e-3)
+        teacher = torch.randn(E, Vp, device=m.device, generator=torch.Generator(device=m.device).manual_seed(1))
+        m.update_loss(0.7)
+        losses = []
+        if mode == "graph":
+            src = (torch.tensor(pool, device=m.device), torch.tensor(lab, device=m.device), torch.tensor(ex, device=m.device),
+                   torch.arange(E, dtype=torch.int32, device=m.device))
+            gs = m.graph_step(B, Me, V, 1e-3, 0.3, teacher=teacher, sources=src, tcaps=[900])
+        for k, (ti, ei) in enumerate(steps):
+            ids = np.concatenate([pool[ti], ex[ei]])
+            ntok = int((ids != 0).sum())
+            if mode == "eager":
+                loss = m.train_step(ids, lab[ti], V, 1e-3, 0.3, exemplar_logits=teacher, teacher_rows=ei.astype(np.int32), n_tokens=ntok)
+            elif k % 2 == 0:
+                loss = gs.run_indices(ti, ei, ntok)
+            else:
+                loss = gs.run_rows(ids, lab[ti], ei, ntok)
+            losses.append(float(loss.item()))
+        assert m.global_step == len(steps) and int(m.adam_state[0].item()) == len(steps)
+        out[mode] = (losses, m.theta.clone())
+    assert out["eager"][0] == out["graph"][0]
+    assert torch.equal(out["eager"][1], out["graph"][1])
+    assert len(set(out["eager"][0])) == len(steps)          # dropout masks / batches really changed from step to step
