@@ -88,15 +88,17 @@ class GraphStep:
                       model.adam_v, model.adam_state, model._loss, teacher, sources)
 
     # ---- capture ------------------------------------------------------------------------------------
+    def _gather(self):
+        """Batch assembly from the GPU-resident row matrices (its own small graph: run_rows skips it)."""
+        t_ids, t_lab, e_ids, e_aux = self.sources
+        ops.gather_rows_i32(t_ids, self.ti, self.ids[:self.n_train])
+        ops.gather_rows_i32(t_lab.view(-1, 1), self.ti, self.pos.view(-1, 1))
+        if self.n_ex > 0:
+            ops.gather_rows_i32(e_ids, self.ei[:self.n_ex], self.ids[self.n_train:])
+            ops.gather_rows_i32(e_aux.view(-1, 1), self.ei[:self.n_ex], self.aux[:self.n_ex].view(-1, 1))
+
     def _eager(self, tcap: int, device_step: bool):
         m = self.model
-        if self.sources is not None:
-            t_ids, t_lab, e_ids, e_aux = self.sources
-            ops.gather_rows_i32(t_ids, self.ti, self.ids[:self.n_train])
-            ops.gather_rows_i32(t_lab.view(-1, 1), self.ti, self.pos.view(-1, 1))
-            if self.n_ex > 0:
-                ops.gather_rows_i32(e_ids, self.ei[:self.n_ex], self.ids[self.n_train:])
-                ops.gather_rows_i32(e_aux.view(-1, 1), self.ei[:self.n_ex], self.aux[:self.n_ex].view(-1, 1))
         kw = {}
         if self.n_ex > 0:
             if m.mode == m.KD:
@@ -116,10 +118,18 @@ class GraphStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up on the largest capacity: sizes every workspace once
+            if self.sources is not None:
+                self._gather()
             self._eager(self.tcaps[-1], False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = None
+        self.gather_graph = None
+        if self.sources is not None:
+            self.gather_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.gather_graph):
+                self._gather()
+            pool = self.gather_graph.pool()
         for tcap in reversed(self.tcaps):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
@@ -165,4 +175,5 @@ class GraphStep:
         self._put(self._ring_ti, self.ti, ti)
         if self.n_ex > 0 and ei is not None:
             self._put(self._ring_ei, self.ei[:self.n_ex], ei)
+        self.gather_graph.replay()
         return self._replay(n_tokens)
