@@ -83,9 +83,6 @@ struct GemmArgs {
 };
 void gemm_defaults(GemmArgs& g);
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
-constexpr int GEMM_GROUP_MAX = 5;
-struct GemmGroup { GemmArgs g[GEMM_GROUP_MAX]; int n, av, bv; };
-int launch_gemm_group(const GemmArgs* gs, int n, cudaStream_t st);
 
 // ---- counter-based dropout mask (shared by fwd and bwd) -----------------------------------
 // u = fmix32(idx ^ key(seed, site)) / 2^24: a stateless 32-bit hash (murmur3 finaliser) of the element index,

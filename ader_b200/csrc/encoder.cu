@@ -998,33 +998,6 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
 // fused tensor-core path (encoder_fused.cuh): same contract, same workspace slots
 // ------------------------------------------------------------------------------------------
 namespace ader {
-// LayerNorm parameter gradients of BOTH LayerNorms of a block in one launch (blockIdx.y = which).
-struct LnPgSet { const float *dout, *x, *mean, *rstd; float *pbeta, *pgamma; };
-__global__ void k_ln_param_grad2(LnPgSet s0, LnPgSet s1, const int* __restrict__ dT, int d, long long split_stride) {
-  __shared__ float sb_s[PG_LANES][256], sg_s[PG_LANES][256];
-  const LnPgSet s = blockIdx.y ? s1 : s0;
-  const int c = threadIdx.x, k = threadIdx.y;
-  const int count = *dT;
-  const int chunk = (count + gridDim.x - 1) / gridDim.x;
-  const int lo = blockIdx.x * chunk, hi = min(count, lo + chunk);
-  float sb = 0.f, sg = 0.f;
-  if (c < d) {
-    for (int i = lo + k; i < hi; i += PG_LANES) {
-      const float g = s.dout[(long long)i * d + c];
-      sb += g; sg += g * ((s.x[(long long)i * d + c] - s.mean[i]) * s.rstd[i]);
-    }
-  }
-  sb_s[k][c] = sb; sg_s[k][c] = sg;
-  __syncthreads();
-  if (k == 0 && c < d) {
-    float tb = 0.f, tg = 0.f;
-#pragma unroll
-    for (int q = 0; q < PG_LANES; ++q) { tb += sb_s[q][c]; tg += sg_s[q][c]; }
-    s.pbeta[(long long)blockIdx.x * split_stride + c] = tb;
-    s.pgamma[(long long)blockIdx.x * split_stride + c] = tg;
-  }
-}
-
 static int fused_check(const AderModel* m) {
   if (m->d > fz::KP) return fail(-1, "fused encoder path needs hidden_units <= %d (got %d): use the exact path", fz::KP, m->d);
   if (m->maxlen > 64) return fail(-1, "fused encoder path needs maxlen <= 64");

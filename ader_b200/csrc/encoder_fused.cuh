@@ -41,7 +41,6 @@ constexpr int ATILE_BYTES = TM * LDS * 2;       // 10 752
 constexpr int FT_LD = 168;              // row stride (floats) of fp32 staging tiles (168 % 32 == 8: conflict-free float2 stores)
 constexpr int FTILE_BYTES = TM * FT_LD * 4;     // 21 504
 constexpr int NE = 5;                   // features per lane in the warp-per-token kernels (32 x 5 = 160)
-constexpr int W_PER_BLOCK = 10;         // 5 matrices x {forward [out][in], backward [in][out]} shadows
 
 // effective dropout seed: host value + optional device-resident step counter (lets a captured CUDA graph draw
 // fresh masks on every replay: the counter is the Adam step the optimiser kernel increments)
@@ -114,17 +113,6 @@ __device__ __forceinline__ void warp_gemm(const op_t* __restrict__ A, const op_t
 __device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
 #pragma unroll
   for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-}
-// visit the warp's accumulator elements as (tile row, column pair): f(row, col, v0, v1), col even.
-template <typename F>
-__device__ __forceinline__ void for_acc(const float (&acc)[NT][4], int mt, int ng, int lane, F f) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const int col = ng * (NT * 8) + j * 8 + 2 * t;
-    f(mt * 16 + g, col, acc[j][0], acc[j][1]);
-    f(mt * 16 + g + 8, col, acc[j][2], acc[j][3]);
-  }
 }
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 __device__ __forceinline__ void st_op2(op_t* p, float a, float b) {
@@ -951,68 +939,6 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
         }
       }
     }
-  }
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    if (c < d) {
-      a.gQ[(long long)tk * d + c] = gq[e];
-      a.gK[(long long)tk * d + c] = gk[e];
-      a.gV[(long long)tk * d + c] = gv[e];
-    }
-  }
-}
-
-// Single-head fast form of the same kernel: blocks of 8 keys / queries (one L2 round trip per block).
-__global__ void __launch_bounds__(256, 3) k_attn_bwd_w1(const __grid_constant__ AttnBwdArgs a) {
-  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
-  const int tk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (tk >= *a.dT) return;
-  const int d = a.d, L = a.L;
-  const int row = a.tok_row[tk];
-  const int off = a.row_off[row];
-  const int n = a.row_off[row + 1] - off;
-  const int i = tk - off;
-  const float inv_denom = 1.0f / sqrtf((float)d);
-  const int j8 = lane & 7;
-  float gy[NE], vt[NE], gq[NE], gk[NE], gv[NE];
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    gy[e] = (c < d) ? a.gY[(long long)tk * d + c] : 0.f;
-    vt[e] = (c < d) ? a.V[(long long)tk * d + c] : 0.f;
-    gq[e] = gk[e] = gv[e] = 0.f;
-  }
-  const float Di = a.D[tk];
-  const long long po_i = (long long)tk * L;
-  // ---- query role: dS_ij = P_ij (dP_ij - D_i) / sqrt(d),  gQ[i] = sum_{j<=i} dS_ij K[j]
-  for (int j0 = 0; j0 <= i; j0 += KB) {
-    const int cnt = min(KB, i + 1 - j0);
-    const float dp = block_dots(gy, a.V + (long long)(off + j0) * d, d, cnt, 0, d, lane);
-    float ds = 0.f;
-    if (j8 < cnt) {
-      const long long po = po_i + j0 + j8;
-      const float P = a.probs[po];
-      const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p) : 1.f;
-      ds = P * (dp * scl - Di) * inv_denom;
-    }
-    block_axpy(gq, ds, a.K + (long long)(off + j0) * d, d, cnt, 0, d, lane);
-  }
-  // ---- key role: gK[i] = sum_{q>=i} dS_qi Q[q],  gV[i] = sum_{q>=i} Pd_qi gY[q]
-  for (int q0 = i; q0 < n; q0 += KB) {
-    const int cnt = min(KB, n - q0);
-    const float dp = block_dots(vt, a.gY + (long long)(off + q0) * d, d, cnt, 0, d, lane);
-    float ds = 0.f, pd = 0.f;
-    if (j8 < cnt) {
-      const int tq = off + q0 + j8;
-      const long long po = (long long)tq * L + i;
-      const float P = a.probs[po];
-      const float scl = a.drop_p > 0.f ? drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p) : 1.f;
-      ds = P * (dp * scl - a.D[tq]) * inv_denom;
-      pd = P * scl;
-    }
-    block_axpy(gk, ds, a.Q + (long long)(off + q0) * d, d, cnt, 0, d, lane);
-    block_axpy(gv, pd, a.gY + (long long)(off + q0) * d, d, cnt, 0, d, lane);
   }
 #pragma unroll
   for (int e = 0; e < NE; ++e) {

@@ -174,14 +174,6 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g, int a_vec2, i
   sgemm_body<A_KFAST, B_KFAST>(g, a_vec2, b_vec2, blockIdx.z);
 }
 
-// Several independent problems of the same shape class in ONE launch: blockIdx.z = problem * splits + split.
-template <bool A_KFAST, bool B_KFAST>
-__global__ void __launch_bounds__(256, 2) sgemm_group_kernel(const __grid_constant__ GemmGroup grp) {
-  const int splits = grp.g[0].splits;
-  const int p = blockIdx.z / splits;
-  sgemm_body<A_KFAST, B_KFAST>(grp.g[p], grp.av, grp.bv, blockIdx.z - p * splits);
-}
-
 template <bool AK, bool BK_>
 static int launch_one(const GemmArgs& g, dim3 grid, int av, int bv, cudaStream_t st) {
   static bool attr = false;
@@ -206,36 +198,6 @@ int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   else if (bk) launch_one<false, true>(g, grid, av, bv, st);
   else launch_one<false, false>(g, grid, av, bv, st);
   ADER_CHECK_LAUNCH("sgemm_kernel");
-  return 0;
-}
-
-// All problems must share M, N, splits, strides' orientation and vector-load eligibility (true for the
-// weight-gradient batch of one encoder block).
-int launch_gemm_group(const GemmArgs* gs, int n, cudaStream_t st) {
-  if (n <= 0) return 0;
-  if (n > GEMM_GROUP_MAX) return fail(-1, "sgemm group: at most %d problems", GEMM_GROUP_MAX);
-  GemmGroup grp;
-  const GemmArgs& g0 = gs[0];
-  auto vec_ok = [](const float* p, long long fast, long long other) {
-    return fast == 1 && (other % 2 == 0) && ((uintptr_t)p % 8 == 0);
-  };
-  const bool ak = (g0.a_cs == 1), bk = (g0.b_rs == 1);
-  int av = 1, bv = 1;
-  for (int i = 0; i < n; ++i) {
-    const GemmArgs& g = gs[i];
-    if (g.M != g0.M || g.N != g0.N || g.splits != g0.splits || (g.a_cs == 1) != ak || (g.b_rs == 1) != bk)
-      return fail(-1, "sgemm group: problems differ in shape class");
-    av &= ak ? vec_ok(g.A, g.a_cs, g.a_rs) : vec_ok(g.A, g.a_rs, g.a_cs);
-    bv &= bk ? vec_ok(g.B, g.b_rs, g.b_cs) : vec_ok(g.B, g.b_cs, g.b_rs);
-    grp.g[i] = g;
-  }
-  grp.n = n; grp.av = av; grp.bv = bv;
-  if (ak || bk) return fail(-1, "sgemm group: only the row-contiguous (weight-gradient) orientation is instantiated");
-  dim3 grid(cdiv(g0.N, BN), cdiv(g0.M, BM), g0.splits * n);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(sgemm_group_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SGEMM_SMEM); attr = true; }
-  sgemm_group_kernel<false, false><<<grid, 256, SGEMM_SMEM, st>>>(grp);
-  ADER_CHECK_LAUNCH("sgemm_group_kernel");
   return 0;
 }
 

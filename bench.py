@@ -185,6 +185,9 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wd = threading.Timer(900.0, lambda: os._exit(3))      # watchdog: a wedged collective must not hold the box
+    wd.daemon = True
+    wd.start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -393,8 +396,15 @@ def gpu_arm(args):
                 "cpu_baseline": {"value": cpu_val, "unit": "sessions/s", "cores": cores, "kind": "port",
                                  "sample": "2 full steps of %d rows after 1 warm-up, torch-CPU fp32 restatement" % M}}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() with captured graphs that hold NCCL kernels alive
+        # deadlocked at exit (measured at N=2); every rank has finished its work and rank 0 has printed the line.
+        try:
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
 
 
 def main():
