@@ -12,7 +12,7 @@
 namespace ader {
 
 constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
-constexpr int SPLITS = 24;        // split-K partials for weight / LN / bias gradients
+constexpr int SPLITS = 21;        // split-K partials for weight / LN / bias gradients (21 x 7 problems = 147 CTAs: one wave of 148 SMs)
 constexpr int PG_LANES = 6;       // token lanes per column in the LN / position gradient reductions (160 x 6 = 960 threads)
 
 struct EncWs {
@@ -757,6 +757,74 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys
   }
 }
 
+// Small-step form of the same reduction (T <= SS_MAXT tokens): no sort at all.  One warp per token; the warp of
+// the FIRST occurrence of an item id owns that table row: it scans the step's token ids (staged in shared memory,
+// 32 per ballot), collects the later occurrences in token order and sums their gradient rows in that order -- the
+// same order the stable sort + segmented reduction produces, so both forms give bit-identical rows.  Warps of
+// repeated ids find an earlier twin within a few ballots and exit.  One launch instead of seven.
+constexpr int SS_MAXT = 8192;
+constexpr int SS_LIST = 64;
+template <int NEL>   // elements per lane: 5 covers d <= 160, LN_MAXE = 8 covers d <= 256
+__global__ void __launch_bounds__(256) k_scatter_small(const int* __restrict__ tok_id, const int* __restrict__ dT,
+                                                       const float* __restrict__ gx, int d, float scale,
+                                                       float* __restrict__ gtable) {
+  extern __shared__ int ss_sm[];
+  const int T = min(*dT, SS_MAXT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((int)blockIdx.x * 8 >= T) return;
+  int* ids = ss_sm + 8 * SS_LIST;
+  int* mem = ss_sm + warp * SS_LIST;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) ids[i] = tok_id[i];
+  __syncthreads();
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= T) return;
+  const int id = ids[t];
+  for (int j0 = 0; j0 < t; j0 += 32) {                     // an earlier twin owns the row
+    const int j = j0 + lane;
+    if (__any_sync(0xffffffffu, j < t && ids[j] == id)) return;
+  }
+  float acc[NEL];
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+  constexpr int FL = (NEL <= 5) ? 16 : 8;                  // rows in flight
+  auto flush = [&](int n) {                                // acc += rows mem[0..n) in list (= token) order
+    for (int q = 0; q < n; q += FL) {
+      float v[FL][NEL];
+#pragma unroll
+      for (int u = 0; u < FL; ++u) {
+        const bool ok = q + u < n;
+        const long long o = ok ? (long long)mem[q + u] * d : 0;
+#pragma unroll
+        for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; v[u][i] = (ok && c < d) ? gx[o + c] : 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < FL; ++u)
+#pragma unroll
+        for (int i = 0; i < NEL; ++i) acc[i] += v[u][i];
+    }
+  };
+  int cnt = 1;
+  if (lane == 0) mem[0] = t;
+  for (int j0 = t + 1; j0 < T; j0 += 32) {
+    const int j = j0 + lane;
+    const bool eq = j < T && ids[j] == id;
+    const unsigned mask = __ballot_sync(0xffffffffu, eq);
+    if (mask) {
+      if (eq) mem[cnt + __popc(mask & ((1u << lane) - 1u))] = j;
+      cnt += __popc(mask);
+      __syncwarp();
+      if (cnt > SS_LIST - 32) { flush(cnt); cnt = 0; __syncwarp(); }
+    }
+  }
+  __syncwarp();
+  flush(cnt);
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d) gtable[(long long)id * d + c] += scale * acc[i];
+  }
+}
+
 static int key_bits(int v_tab) { int b = 1; while ((1LL << b) < v_tab) ++b; return b; }
 
 }  // namespace ader
@@ -812,7 +880,14 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
   // dense parameter gradients (position table included): reduce the split partials in fixed order
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, st>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
   // item-table scatter (modules.py:127-130)
-  {
+  if (Tcap <= SS_MAXT) {
+    if (d <= 160)
+      k_scatter_small<5><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
+                                                                                           grad + l.off_table);
+    else
+      k_scatter_small<LN_MAXE><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
+                                                                                                 grad + l.off_table);
+  } else {
     const int ntiles = sort_tiles(Tcap);
     const int bits = key_bits(m->v_tab);
     int cur = 0;

@@ -607,3 +607,19 @@ def test_vocab_parallel_shards_match_single_kernel(mode, shards):
     _close(d_sum.cpu(), d_rep.cpu(), 1e-4, 1e-7, "d_rep")
     _close(grad2[150:(V + 1) * 150].cpu(), grad[150:(V + 1) * 150].cpu(), 1e-4, 1e-8, "table grad")
     assert float(grad2[(V + 1) * 150:].abs().max()) == 0.0
+
+
+def test_scatter_small_step_and_sorted_forms_are_bit_identical():
+    """The item-table scatter has two deterministic forms: first-occurrence ownership (token capacity <= 8192) and
+    stable radix sort + segmented reduction (larger steps).  Both add the rows of an item in token order."""
+    m, hp, _ = _model(400)
+    rng = np.random.RandomState(12)
+    M = 180
+    ids = _ids(rng, M, 50, 350, rng.randint(1, 30, M))
+    ids[:, -1] = np.where(rng.rand(M) < 0.5, 7, ids[:, -1])          # a hot item: ~90 occurrences
+    pos = rng.randint(1, 351, M).astype(np.int32)
+    m.loss_and_grad(ids, pos, 350)                                    # capacity M*50 = 9000 -> sorted form
+    g_sorted = m.grad.clone()
+    m.loss_and_grad(ids, pos, 350, n_tokens=int((ids != 0).sum()))    # tight capacity -> small-step form
+    assert int((ids != 0).sum()) <= 8192 < M * 50
+    assert torch.equal(g_sorted, m.grad)
