@@ -72,11 +72,12 @@ int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* 
                          int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
                          float dropout_rate, uint64_t seed, void* stream);
 
-/* Same two contracts on the tensor cores: fused sub-layer kernels (LN + Q/K/V, attention + LN, FFN) with bf16
- * operands / fp32 accumulation, weights staged by bulk async copies; workspaces and slots are identical to
- * the exact path (same *_ws_bytes queries).  Needs hidden_units <= 160.  Results agree with the exact path
- * to bf16 operand rounding (tests state the tolerance); weight/bias/LayerNorm gradients are accumulated in
- * fp32 in a fixed order (deterministic).
+/* Same two contracts on the tensor cores: fused sub-layer kernels ([embed] + LN + Q/K/V, attention + LN, FFN and
+ * their backward twins) with row-scaled fp16 operands / fp32 accumulation, weights staged by bulk async copies;
+ * weight / bias / LayerNorm-parameter gradients on TF32 tensor cores with fp32 accumulation in a fixed order
+ * (deterministic).  Workspaces and slots are identical to the exact path (same *_ws_bytes queries).  Needs
+ * hidden_units <= 160.  Results agree with the exact path to the tolerances stated in
+ * tests/test_gpu_encoder_fused.py (activations 1e-2, gradients 3e-2 rel-L2 per tensor).
  * d_step (device int32, may be NULL): added to `seed` on the device, so a captured CUDA graph draws fresh dropout
  * masks on every replay (pass the Adam state pointer: state[0] is the step counter). */
 int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
@@ -111,8 +112,10 @@ int32_t ader_loss_fwd_bwd(const AderModel* m, const float* theta, const float* r
                           const AderLossArgs* a, void* ws, float* loss, float* row_loss,
                           float* d_rep, float* grad, void* stream);
 /* Same contract on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM): fused
- * logits + online-softmax CE + distillation, [M, V] logits never materialised in HBM.  Results
- * agree with ader_loss_fwd_bwd to bf16 operand rounding (tests state the tolerance). */
+ * logits + online-softmax CE + distillation, [M, V] logits never materialised in HBM.  Distillation
+ * rows enter by linearity: bf16 tiles of coef * softmax(teacher) are MMA operands (uc = Pc.E for the loss and
+ * d_rep, dE -= Pc^T.rep), so the hot kernels never read the fp32 teacher.  Results agree with
+ * ader_loss_fwd_bwd to bf16 operand rounding (tests state the tolerance). */
 size_t  ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a);
 int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
                              const AderLossArgs* a, void* ws, float* loss, float* row_loss,

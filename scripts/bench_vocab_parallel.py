@@ -37,4 +37,4 @@ if rank == 0:
                       "sessions_per_s": M / ms * 1e3, "algorithmic_tflops_total": flops / ms / 1e9,
                       "algorithmic_tflops_per_gpu": flops / ms / 1e9 / world, "loss": float(loss),
                       "d_rep_checksum": float(d_rep.double().abs().sum())}))
-dist.destroy_process_group()
+sys.stdout.flush(); torch.cuda.synchronize(); os._exit(0)   # no NCCL teardown (can wedge at exit)
