@@ -59,9 +59,12 @@ SIGNATURES = {
     "ader_loss_fwd_bwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P]),
     "ader_loss_tc_ws_bytes": (C.c_size_t, [_MP, C.POINTER(AderLossArgs)]),
     "ader_loss_fwd_bwd_tc": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P]),
+    "ader_debug_loss_tc_kernels": (C.c_int32, [_MP, _P, C.POINTER(AderLossArgs), _P, _P, _P]),
     "ader_loss_tc_vp_ws_bytes": (C.c_size_t, [_MP, C.POINTER(AderLossArgs), C.c_int32, C.c_int32]),
     "ader_loss_tc_vp_fwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), C.c_int32, C.c_int32, _P, _P, _P]),
     "ader_loss_tc_vp_bwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "ader_train_fwd_bwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P, _P,
+                                          _P, C.c_float, C.c_uint64, _P, C.c_int32, _P]),
     "ader_logits": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "ader_adam_step": (C.c_int32, [_MP, _P, _P, _P, _P, _P, C.POINTER(AderAdamArgs), _P]),
     "ader_eval_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
@@ -71,6 +74,7 @@ SIGNATURES = {
     "ader_fisher_accumulate": (C.c_int32, [_MP, _P, _P, C.c_int32, _P]),
     "ader_fisher_finalize": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P]),
     "ader_gather_rows_i32": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "ader_gather_batch": (C.c_int32, [_P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -58,6 +58,40 @@ static inline int check_model(const AderModel* m) {
   return 0;
 }
 
+// ---- fork/join plan of one call (step.cu) -----------------------------------------------------
+// The fused training entry (ader_train_fwd_bwd_tc) issues its launches as a DAG over a few internal
+// streams: `main` carries the critical chain, a / b / c carry work that is off it (weight-shadow packing,
+// teacher products, dE, weight gradients, position gradient, partial reductions).  With a == b == c == main
+// every edge is a no-op and the launches are issued in the historical serial order, so the single-stream
+// entry points run the very same code.  Under stream capture the side streams join the capture through
+// the event edges and become parallel branches of the CUDA graph.
+struct Fork {
+  cudaStream_t main, a, b, c;
+  cudaEvent_t* ev; int n_ev, next_ev;      // event pool (timing disabled); reuse is safe: every wait is issued right after its record
+  cudaEvent_t table_ready;                 // recorded on `b` after the dE kernel: the scatter into the item table waits for it
+  bool has_table_ready;
+  static Fork serial(cudaStream_t st) { Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.table_ready = nullptr; f.has_table_ready = false; return f; }
+  bool parallel() const { return a != main; }
+  cudaEvent_t take() { cudaEvent_t e = ev[next_ev % n_ev]; ++next_ev; return e; }
+  // work launched on `to` after this call also waits for everything launched on `from` before it
+  void edge(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    cudaEvent_t e = take();
+    cudaEventRecord(e, from);
+    cudaStreamWaitEvent(to, e, 0);
+  }
+};
+
+// internal forms of the tensor-core entry points (encoder.cu / logits_tc.cu), shared with step.cu
+int enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, int M, int Tcap, void* ws, float* rep,
+                   float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f);
+int enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, int M, int Tcap, const void* ws, void* bwd_ws,
+                   const float* d_rep, float* grad, float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f);
+// phase 0: everything that does not need `rep` (table tiles, teacher statistics / tiles, uc partials) on f.b;
+// phase 1: the rest (rep tiles, forward statistics, loss, d_rep on f.main; dE on f.b)
+int loss_tc_run(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, void* ws, float* loss,
+                float* row_loss, float* d_rep, float* grad, Fork& f, int phase_mask);
+
 // ---- generic fp32 GEMM (sgemm.cu) ----------------------------------------------------------
 // C(m,n) = epilogue( sum_k A(m,k) * B(k,n) ), element (i,j) of X at X[i*rs + j*cs].
 struct GemmArgs {

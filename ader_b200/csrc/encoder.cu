@@ -51,6 +51,8 @@ struct BwdWs {
   float* partial;        // [SPLITS][dense_count]
   int *keys[2], *vals[2], *hist;
   float* Dv;             // fused path: per-token softmax-backward row dots
+  float* g2[8];          // fused path: second set of gO..gQ1 (blocks alternate sets, so the weight-gradient kernel of
+                         // block b may still read its set while block b-1's data-gradient kernels write the other)
   size_t bytes;
 };
 static int sort_tiles(int Tcap) { return cdiv(Tcap, 2048); }
@@ -63,6 +65,7 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
   for (int i = 0; i < 2; ++i) { w.keys[i] = (int*)take(sizeof(int) * Tcap); w.vals[i] = (int*)take(sizeof(int) * Tcap); }
   w.hist = (int*)take(sizeof(int) * 256 * (size_t)sort_tiles(Tcap));
   w.Dv = (float*)take(sizeof(float) * Tcap);
+  for (int i = 0; i < 8; ++i) w.g2[i] = (float*)take(sizeof(float) * (size_t)Tcap * m->d);
   w.bytes = o;
   return w;
 }
@@ -865,6 +868,8 @@ static int run_wgrad(cudaStream_t st, const float* act, const float* grad, float
   return launch_gemm(wgrad_args(act, grad, pW, pb, split_stride, Tcap, dT, d), st);
 }
 
+static int run_table_scatter(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
+                             int M, int Tcap, float* grad, cudaStream_t st);
 // Tail shared by both encoder paths: split-K partials -> dense gradients, position table, item-table scatter.
 // gX must already carry the embedding-dropout mask (site 0): the callers apply it once when they produce gX, so
 // the position-table reduction and the scatter do not re-hash every element.
@@ -879,7 +884,15 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
   k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, st>>>(gX, w.row_len, w.row_off, M, L, d, p, seed, d_step, g.partial, PS);
   // dense parameter gradients (position table included): reduce the split partials in fixed order
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, st>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
-  // item-table scatter (modules.py:127-130)
+  return run_table_scatter(m, l, w, g, gX, M, Tcap, grad, st);
+}
+
+// item-table scatter (modules.py:127-130)
+static int run_table_scatter(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
+                             int M, int Tcap, float* grad, cudaStream_t st) {
+  const float p = 0.f; const uint64_t seed = 0; const int* d_step = nullptr;
+  const int d = m->d;
+  const int* dT = w.row_off + M;
   if (Tcap <= SS_MAXT) {
     if (d <= 160)
       k_scatter_small<5><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
@@ -1110,24 +1123,33 @@ extern "C" int32_t ader_debug_fz_timeline(long long* out) {
 extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, void* ws, float* rep, float dropout_rate, uint64_t seed,
                                        const int32_t* d_step, void* stream) {
+  Fork f = Fork::serial((cudaStream_t)stream);
+  return enc_fwd_tc_run(m, theta, ids, M, Tcap, ws, rep, dropout_rate, seed, d_step, f);
+}
+
+int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, int M, int Tcap, void* ws, float* rep,
+                         float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f) {
   if (int e = check_model(m)) return e;
   if (int e = fused_check(m)) return e;
   ADER_CHECK_ARG(theta && ids && ws && rep, "encoder_fwd_tc: NULL pointer");
   ADER_CHECK_ARG(M > 0 && Tcap > 0 && (long long)Tcap <= (long long)M * m->maxlen, "encoder_fwd_tc: bad M/Tcap (%d, %d)", M, Tcap);
   ADER_CHECK_ARG(dropout_rate >= 0.f && dropout_rate < 1.f, "encoder_fwd_tc: dropout_rate out of range");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = f.main;
   const Layout l = make_layout(m);
   const int d = m->d, L = m->maxlen;
   EncWs w = carve_enc(m, M, Tcap, (char*)ws);
   const int* dT = w.row_off + M;
   fused_attrs();
 
+  // weight shadows depend on theta only: off the packing chain (joined before the first tile kernel)
+  f.edge(st, f.a);
+  fz::k_pack_weights<<<dim3(m->num_blocks * 5, fz::KP / fz::PACK_BAND), 256, 0, f.a>>>(theta, l, (fz::op_t*)w.wshadow);
   cudaMemsetAsync(w.flags, 0, sizeof(int) * 4, st);
   k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
   k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
   k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
-  fz::k_pack_weights<<<dim3(m->num_blocks * 5, fz::KP / fz::PACK_BAND), 256, 0, st>>>(theta, l, (fz::op_t*)w.wshadow);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
+  f.edge(f.a, st);
 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
   const int warp_grid = cdiv(Tcap, fz::ATT_TOK);
@@ -1171,11 +1193,21 @@ extern "C" int32_t ader_encoder_fwd_tc(const AderModel* m, const float* theta, c
 extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
                                        float dropout_rate, uint64_t seed, const int32_t* d_step, void* stream) {
+  Fork f = Fork::serial((cudaStream_t)stream);
+  return enc_bwd_tc_run(m, theta, ids, M, Tcap, ws, bwd_ws, d_rep, grad, dropout_rate, seed, d_step, f);
+}
+
+// Launch plan (f.parallel()): the data-gradient chain lnf_bwd -> per block (ffn_bwd, attn_bwd, qkv_bwd) -> scatter stays on
+// f.main; the weight-gradient kernel of each block, the LayerNorm-parameter / position-table reductions and the fixed-order
+// reduction of the split partials run beside it on f.a / f.c.  Blocks alternate between two sets of gradient buffers and
+// the block-to-block gradient rotates over three, so a weight-gradient kernel never reads a buffer the chain is rewriting.
+int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, int M, int Tcap, const void* ws, void* bwd_ws,
+                         const float* d_rep, float* grad, float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f) {
   if (int e = check_model(m)) return e;
   if (int e = fused_check(m)) return e;
   ADER_CHECK_ARG(theta && ids && ws && bwd_ws && d_rep && grad, "encoder_bwd_tc: NULL pointer");
   ADER_CHECK_ARG(M > 0 && Tcap > 0, "encoder_bwd_tc: bad M/Tcap");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = f.main;
   const Layout l = make_layout(m);
   const int d = m->d, L = m->maxlen;
   const float p = dropout_rate;
@@ -1184,24 +1216,32 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
   const int* dT = w.row_off + M;
   const long long PS = l.dense_count();
   auto part = [&](long long param_off) { return g.partial + (param_off - l.off_pos); };
-  float *gX = g.g[0], *gXin = g.g[1], *gO = g.g[2], *gH = g.g[3], *gZ = g.g[4], *gY = g.g[5],
-        *gQ = g.g[6], *gK = g.g[7], *gV = g.g[8], *gQ1 = g.g[9];
+  float* chain[3] = {g.g[0], g.g[1], g.g[10]};
+  int ci = 0;
   const int ln_grid = cdiv((long long)Tcap * 32, 256);
   const int ln_threads = ((d + 31) / 32) * 32;
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
   fused_attrs();
 
-  k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, gX, dT, d);
-  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+  // final LayerNorm: data gradient on the chain, parameter gradient beside it
+  f.edge(st, f.a);
+  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, f.a>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
+  k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, chain[0], dT, d);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
 
+  cudaEvent_t wg_done[8];                   // weight-gradient kernel of block b finished (f.a), parallel plans only
   for (int b = m->num_blocks - 1; b >= 0; --b) {
     const long long bo = l.block(b);
     const float* P = theta + bo;
     const float* X = w.slot[b][0]; const float* Q1 = w.slot[b][1]; const float* Qp = w.slot[b][2];
     const float* Kp = w.slot[b][3]; const float* Vp = w.slot[b][4]; const float* Y = w.slot[b][5];
     const float* Z = w.slot[b][6]; const float* H = w.slot[b][7];
+    float* const* gs = (b & 1) ? g.g2 : g.g + 2;
+    float *gO = gs[0], *gH = gs[1], *gZ = gs[2], *gY = gs[3], *gQ = gs[4], *gK = gs[5], *gV = gs[6], *gQ1 = gs[7];
+    float* gX = chain[ci % 3]; float* gXin = chain[(ci + 1) % 3]; ++ci;
+    // this block rewrites the buffer set (and chain buffer) last read by the weight-gradient kernel of block b + 2
+    if (f.parallel() && b + 2 < m->num_blocks) cudaStreamWaitEvent(st, wg_done[b + 2], 0);
     fz::FfnBwdArgs fa;
     fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
     fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
@@ -1235,11 +1275,22 @@ extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, c
     wa.p[5] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
     wa.p[6] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
     wa.n_gemm = 5; wa.n_ln = 2; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-    fz::k_wgrad<<<dim3(SPLITS, 7), fz::NTHR, fz::WGRAD_SMEM, st>>>(wa);
+    f.edge(st, f.a);
+    fz::k_wgrad<<<dim3(SPLITS, 7), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
-    float* t = gX; gX = gXin; gXin = t;
+    if (f.parallel()) { wg_done[b] = f.take(); cudaEventRecord(wg_done[b], f.a); }
   }
-  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, grad, st)) return e;
+  const float* gX0 = chain[ci % 3];          // gradient w.r.t. the (dropout-masked) embedding output
+
+  // position table (ADER.py:41-52) beside the scatter; then all split partials -> dense gradients in fixed order
+  f.edge(st, f.c);
+  k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
+  f.edge(f.c, f.a);
+  k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
+  // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
+  if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);
+  if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  f.edge(f.a, st);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");
   return 0;
 }
@@ -1258,5 +1309,38 @@ extern "C" int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, 
   if (n == 0) return 0;
   k_gather_rows<<<cdiv((long long)n * width, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, width, out);
   ADER_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
+// Batch assembly in one launch: rows ti[] of the train matrix (+ their labels) followed by rows ei[] of the exemplar
+// matrix (+ their aux word: teacher row or label) -> ids [n_train + n_ex, width], pos [n_train], aux [n_ex].
+__global__ void k_gather_batch(const int* __restrict__ t_ids, const int* __restrict__ t_lab, const int* __restrict__ ti, int n_train,
+                               const int* __restrict__ e_ids, const int* __restrict__ e_aux, const int* __restrict__ ei, int n_ex,
+                               int width, int* __restrict__ ids, int* __restrict__ pos, int* __restrict__ aux) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w1 = width + 1;
+  if (e >= (long long)(n_train + n_ex) * w1) return;
+  const int row = (int)(e / w1), c = (int)(e % w1);
+  if (row < n_train) {
+    const long long src = ti[row];
+    if (c < width) ids[(long long)row * width + c] = t_ids[src * width + c];
+    else pos[row] = t_lab[src];
+  } else {
+    const int r = row - n_train;
+    const long long src = ei[r];
+    if (c < width) ids[(long long)row * width + c] = e_ids[src * width + c];
+    else if (aux) aux[r] = e_aux ? e_aux[src] : 0;
+  }
+}
+extern "C" int32_t ader_gather_batch(const int32_t* t_ids, const int32_t* t_lab, const int32_t* ti, int32_t n_train,
+                                     const int32_t* e_ids, const int32_t* e_aux, const int32_t* ei, int32_t n_ex,
+                                     int32_t width, int32_t* ids, int32_t* pos, int32_t* aux, void* stream) {
+  ADER_CHECK_ARG(n_train >= 0 && n_ex >= 0 && width > 0 && ids, "gather_batch: bad argument");
+  ADER_CHECK_ARG(n_train == 0 || (t_ids && t_lab && ti && pos), "gather_batch: NULL train pointer");
+  ADER_CHECK_ARG(n_ex == 0 || (e_ids && ei), "gather_batch: NULL exemplar pointer");
+  if (n_train + n_ex == 0) return 0;
+  k_gather_batch<<<cdiv((long long)(n_train + n_ex) * (width + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+      t_ids, t_lab, ti, n_train, e_ids, e_aux, ei, n_ex, width, ids, pos, aux);
+  ADER_CHECK_LAUNCH("gather_batch");
   return 0;
 }

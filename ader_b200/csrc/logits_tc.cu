@@ -770,21 +770,45 @@ static void set_tc_attrs() {
 }
 constexpr int SMEM_FWD = (1 + n_stages(MODE_FWD)) * TILE_BYTES + 256;
 constexpr int SMEM_BWD = (1 + n_stages(MODE_DREP)) * TILE_BYTES + 2 * DS_BYTES + 256;
-// teacher statistics + tiles + u = P.E  (needs rep / E tiles packed; fills w.u)
-static void launch_teacher_u(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, const float* rep, int d,
-                             cudaStream_t st) {
+// teacher statistics + tiles + uc partials (rep-independent), then u = sum of partials and udot = rep . u
+static void launch_teacher_tu(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, cudaStream_t st) {
   k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
   k_teacher_tiles<<<dim3(w.n_vtp, w.n_et), 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, t.teacher_vec4, w.lse_t,
                                                         a->n_train, a->M, a->V_prev, v_off, w.x0_t, w.n_vtp, t.coef_ex, w.pt_tiles);
   k_tc_logits<MODE_TU><<<w.n_et * w.n_chunks_t, NTHREADS, SMEM_BWD, st>>>(t);
+}
+static void launch_reduce_u(const AderLossArgs* a, const TcWs& w, const float* rep, int d, cudaStream_t st) {
   k_reduce_u<<<w.n_et * TILE, KP, 0, st>>>(w.u_part, w.n_chunks_t, w.n_et * TILE, w.u, rep, w.x0_t, a->M, d, w.udot);
+}
+static void launch_teacher_u(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, const float* rep, int d,
+                             cudaStream_t st) {
+  launch_teacher_tu(a, w, t, v_off, st);
+  launch_reduce_u(a, w, rep, d, st);
 }
 
 extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
                                         const AderLossArgs* a, void* ws, float* loss, float* row_loss,
                                         float* d_rep, float* grad, void* stream) {
+  Fork f = Fork::serial((cudaStream_t)stream);
+  return loss_tc_run(m, theta, rep, a, ws, loss, row_loss, d_rep, grad, f, 3);
+}
+
+// Measurement hook (bench.py roofline): re-launches ONLY k_tc_logits<FWD>, <DREP>, <DE> on a workspace that a preceding
+// ader_loss_fwd_bwd_tc call with the same arguments prepared (tiles, lse, teacher tiles); outputs are the same values.
+extern "C" int32_t ader_debug_loss_tc_kernels(const AderModel* m, const float* theta, const AderLossArgs* a, void* ws,
+                                              float* grad, void* stream) {
+  Fork f = Fork::serial((cudaStream_t)stream);
+  return loss_tc_run(m, theta, nullptr, a, ws, nullptr, nullptr, nullptr, grad, f, 4);
+}
+
+// phase_mask bit 0: table tiles + teacher products that do not need `rep`, on f.b;
+// bit 1: everything else.  Forward statistics, loss and d_rep stay on f.main; the scalar loss reduction goes to f.c and
+// the dE kernel to f.b (f.table_ready is recorded behind it: whoever adds into the item-table gradient waits for it).
+int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, void* ws, float* loss,
+                      float* row_loss, float* d_rep, float* grad, Fork& f, int phase_mask) {
   if (int e = check_model(m)) return e;
-  ADER_CHECK_ARG(theta && rep && a && ws && loss && row_loss, "loss_fwd_bwd_tc: NULL pointer");
+  ADER_CHECK_ARG(theta && a && ws, "loss_fwd_bwd_tc: NULL pointer");
+  ADER_CHECK_ARG(!(phase_mask & 2) || (rep && loss && row_loss), "loss_fwd_bwd_tc: NULL pointer");
   ADER_CHECK_ARG(m->d <= KP && m->d % 2 == 0, "loss_fwd_bwd_tc: hidden_units must be <= %d", KP);
   ADER_CHECK_ARG(a->M == a->n_train + a->n_ex && a->M > 0, "loss_fwd_bwd_tc: M != n_train + n_ex");
   ADER_CHECK_ARG(a->V >= 1 && a->V < m->v_tab, "loss_fwd_bwd_tc: max_item outside the table");
@@ -795,17 +819,13 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
     if (a->mode == 1) ADER_CHECK_ARG(a->teacher && a->V_prev >= 1 && a->V_prev <= a->V && a->teacher_ld >= a->V_prev, "loss_fwd_bwd_tc: bad teacher");
     if (a->mode == 2) ADER_CHECK_ARG(a->ex_pos, "loss_fwd_bwd_tc: exemplar_pos is NULL");
   }
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = f.main, sb = f.b;
   const int d = m->d, M = a->M, V = a->V;
   const bool kd = a->n_ex > 0 && a->mode == 1;
   TcWs w = carve_tc(m, M, V, a->n_ex, kd ? a->V_prev : 0, (char*)ws);
   const int nm = cdiv(M, TILE), nv = cdiv(V, TILE), nc = tc_chunks(nm, nv);
   const int smem_fwd = SMEM_FWD, smem_bwd = SMEM_BWD;
   set_tc_attrs();
-  cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
-  k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
-  k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + d, d, V, d, nv, w.e_tiles);
-  ADER_CHECK_LAUNCH("tc pack");
 
   TcArgs t;
   t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = V; t.V_total = V; t.v_off = 0; t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
@@ -818,11 +838,32 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
   t.d = d; t.err = w.err;
   t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part;
 
-  if (kd) launch_teacher_u(a, w, t, 0, rep, d, st);
+  if (phase_mask == 4) {      // measurement only: the three tensor-core kernels on an already prepared workspace
+    k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
+    k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
+    if (grad) k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
+    ADER_CHECK_LAUNCH("tc kernels");
+    return 0;
+  }
+  if (phase_mask & 1) {
+    cudaMemsetAsync(w.err, 0, sizeof(int) * 4, sb);
+    k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, sb>>>(theta + d, d, V, d, nv, w.e_tiles);
+    if (kd) launch_teacher_tu(a, w, t, 0, sb);
+    ADER_CHECK_LAUNCH("tc prep");
+  }
+  if (!(phase_mask & 2)) return 0;
+
+  f.edge(sb, st);
+  k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
+  if (kd) launch_reduce_u(a, w, rep, d, st);
+  ADER_CHECK_LAUNCH("tc pack");
   k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
   k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss, nullptr,
                                               kd ? w.udot : nullptr, w.x0_t, t.coef_ex);
-  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, st, a->n_train_global, a->n_ex_global)) return e;
+  cudaEvent_t lse_ready = nullptr;
+  if (f.parallel()) { lse_ready = f.take(); cudaEventRecord(lse_ready, st); }
+  f.edge(st, f.c);
+  if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, f.c, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
     k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
@@ -831,9 +872,12 @@ extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, 
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {
-    k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
+    if (f.parallel()) cudaStreamWaitEvent(sb, lse_ready, 0);
+    k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, sb>>>(t);
     ADER_CHECK_LAUNCH("tc d_table");
+    if (f.parallel()) { f.table_ready = f.take(); cudaEventRecord(f.table_ready, sb); f.has_table_ready = true; }
   }
+  f.edge(f.c, st);
   return 0;
 }
 

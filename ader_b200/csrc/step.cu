@@ -1,0 +1,66 @@
+// One training pass as a fork/join DAG: encoder forward, logits + CE + distillation forward/backward, encoder
+// backward and the embedding scatter (everything of `train_op` before the optimiser, main.py:233-256).
+//
+// The three tensor-core groups are latency chains of 3-25 us kernels; a third of the launches of a step is not on
+// the critical path (teacher products, table-tile packing, dE, weight / LayerNorm / position gradients, partial
+// reductions).  This entry issues the same kernels as
+//     ader_encoder_fwd_tc -> ader_loss_fwd_bwd_tc -> ader_encoder_bwd_tc
+// with the same arguments -- results are bit-identical -- but puts the off-path work on three internal streams
+// joined by events.  Captured by a CUDA graph the side streams become parallel branches of the graph.
+#include "common.cuh"
+
+namespace ader {
+
+struct StreamPool {
+  cudaStream_t s[3];
+  cudaEvent_t ev[64];
+  bool ok;
+  StreamPool() : ok(false) {}
+  int init() {
+    if (ok) return 0;
+    for (int i = 0; i < 3; ++i)
+      if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
+    for (int i = 0; i < 64; ++i)
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create an event");
+    ok = true;
+    return 0;
+  }
+};
+// one pool per host thread and device (streams belong to the device that was current at creation)
+static thread_local StreamPool g_pool[16];
+
+}  // namespace ader
+
+using namespace ader;
+
+extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                                         const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                                         float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                                         uint64_t seed, const int32_t* d_step, int32_t serial, void* stream) {
+  ADER_CHECK_ARG(m && theta && ids && a && enc_ws && bwd_ws && loss_ws && rep && loss && row_loss && d_rep && grad,
+                 "train_fwd_bwd_tc: NULL pointer");
+  ADER_CHECK_ARG(a->M == M, "train_fwd_bwd_tc: loss rows (%d) != encoder rows (%d)", a->M, M);
+  cudaStream_t st = (cudaStream_t)stream;
+  Fork f = Fork::serial(st);
+  if (!serial) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return fail(-3, "train_fwd_bwd_tc: bad device");
+    StreamPool& p = g_pool[dev];
+    if (int e = p.init()) return e;
+    f.a = p.s[0]; f.b = p.s[1]; f.c = p.s[2];
+    f.ev = p.ev; f.n_ev = 64; f.next_ev = 0;
+  }
+  // teacher products / table tiles need nothing from the encoder: start them first, beside it
+  f.edge(st, f.b);
+  if (int e = loss_tc_run(m, theta, nullptr, a, loss_ws, nullptr, nullptr, nullptr, grad, f, 1)) return e;
+  if (int e = enc_fwd_tc_run(m, theta, ids, M, Tcap, enc_ws, rep, dropout_rate, seed, d_step, f)) return e;
+  if (int e = loss_tc_run(m, theta, rep, a, loss_ws, loss, row_loss, d_rep, grad, f, 2)) return e;
+  if (int e = enc_bwd_tc_run(m, theta, ids, M, Tcap, enc_ws, bwd_ws, d_rep, grad, dropout_rate, seed, d_step, f)) return e;
+  // every side stream is already ordered before the tail of `stream` (a: joined by the backward, b: the scatter
+  // waited for dE, c: joined twice); close the DAG explicitly so nothing depends on that reasoning
+  f.edge(f.a, st);
+  f.edge(f.b, st);
+  f.edge(f.c, st);
+  ADER_CHECK_LAUNCH("train_fwd_bwd_tc");
+  return 0;
+}

@@ -44,6 +44,25 @@ class _PinnedRing:
         ev.record()
         self.evs[k] = ev
 
+    def stage_parts(self, dst: torch.Tensor, parts, keep_tail: bool = False):
+        """Concatenate the host arrays `parts` into one pinned slot and copy it to the front of `dst` in one transfer."""
+        k = self.i
+        self.i = (k + 1) % len(self.bufs)
+        if self.evs[k] is not None:
+            self.evs[k].synchronize()
+        buf = self.bufs[k].numpy()
+        o = 0
+        for a in parts:
+            a = np.asarray(a, dtype=np.int32).reshape(-1)
+            buf[o:o + a.size] = a
+            o += a.size
+        if not keep_tail and o != buf.size:
+            raise ValueError("batch parts hold %d values, the step takes %d" % (o, buf.size))
+        dst[:o].copy_(self.bufs[k][:o], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.evs[k] = ev
+
 
 class GraphStep:
     """Captured ``train_step`` for a fixed batch geometry (n_train + n_ex rows) of one period.
@@ -63,9 +82,13 @@ class GraphStep:
         dev, L = model.device, model.hp.maxlen
         M = self.n_train + self.n_ex
         self.M = M
-        self.ids = torch.zeros((M, L), dtype=torch.int32, device=dev)
-        self.pos = torch.ones(self.n_train, dtype=torch.int32, device=dev)
-        self.aux = torch.zeros(max(self.n_ex, 1), dtype=torch.int32, device=dev)
+        # one static int32 buffer [ids | pos | aux]: a host-fed step is ONE pinned staging copy + ONE H2D transfer
+        n_aux = max(self.n_ex, 1)
+        self.batch = torch.zeros(M * L + self.n_train + n_aux, dtype=torch.int32, device=dev)
+        self.ids = self.batch[:M * L].view(M, L)
+        self.pos = self.batch[M * L:M * L + self.n_train]
+        self.aux = self.batch[M * L + self.n_train:]
+        self.pos.fill_(1)
         if self.n_ex > 0 and model.mode == model.ER:
             self.aux.fill_(1)
         self.sources = sources
@@ -74,6 +97,7 @@ class GraphStep:
             self.ei = torch.zeros(max(self.n_ex, 1), dtype=torch.int32, device=dev)
             self._ring_ti = _PinnedRing((self.n_train,))
             self._ring_ei = _PinnedRing((max(self.n_ex, 1),))
+        self._ring_batch = _PinnedRing((self.batch.numel(),))
         self._ring_ids = _PinnedRing((M, L))
         self._ring_pos = _PinnedRing((self.n_train,))
         self._ring_aux = _PinnedRing((max(self.n_ex, 1),))
@@ -91,11 +115,10 @@ class GraphStep:
     def _gather(self):
         """Batch assembly from the GPU-resident row matrices (its own small graph: run_rows skips it)."""
         t_ids, t_lab, e_ids, e_aux = self.sources
-        ops.gather_rows_i32(t_ids, self.ti, self.ids[:self.n_train])
-        ops.gather_rows_i32(t_lab.view(-1, 1), self.ti, self.pos.view(-1, 1))
         if self.n_ex > 0:
-            ops.gather_rows_i32(e_ids, self.ei[:self.n_ex], self.ids[self.n_train:])
-            ops.gather_rows_i32(e_aux.view(-1, 1), self.ei[:self.n_ex], self.aux[:self.n_ex].view(-1, 1))
+            ops.gather_batch(t_ids, t_lab, self.ti, e_ids, e_aux, self.ei[:self.n_ex], self.ids, self.pos, self.aux[:self.n_ex])
+        else:
+            ops.gather_batch(t_ids, t_lab, self.ti, None, None, None, self.ids, self.pos, None)
 
     def _eager(self, tcap: int, device_step: bool):
         m = self.model
@@ -162,6 +185,11 @@ class GraphStep:
 
     def run_rows(self, ids, pos, aux=None, n_tokens: Optional[int] = None):
         """ids [M, L], pos [n_train], aux [n_ex] (teacher rows or exemplar labels): host arrays or device tensors."""
+        host = not isinstance(ids, torch.Tensor) and not isinstance(pos, torch.Tensor) and not isinstance(aux, torch.Tensor)
+        if host and (self.n_ex == 0 or aux is not None):
+            self._ring_batch.stage_parts(self.batch, (ids, pos) if self.n_ex == 0 else (ids, pos, aux),
+                                         keep_tail=(self.n_ex == 0))
+            return self._replay(n_tokens)
         self._put(self._ring_ids, self.ids, ids)
         self._put(self._ring_pos, self.pos, pos)
         if self.n_ex > 0 and aux is not None:

@@ -12,6 +12,7 @@ All state is device resident: one flat fp32 parameter vector + Adam slots + grad
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -74,6 +75,9 @@ class Ader:
         # passes (rep / eval / herding: bit-exact index parity with the fp32 reference) use infer_encoder_impl.
         self.encoder_impl = getattr(args, "encoder_impl", None) or ("exact" if self.loss_impl == "exact" else "tc")
         self.infer_encoder_impl = getattr(args, "infer_encoder_impl", "exact")
+        # how a tc + tc training pass is issued: "dag" = ader_train_fwd_bwd_tc (fork/join over side streams),
+        # "serial" = the same entry on one stream, "groups" = the three single-group entry points one after another
+        self.step_impl = getattr(args, "step_impl", None) or os.environ.get("ADER_B200_STEP_IMPL", "dag")
         if self.hp.hidden_units > 160:
             self.encoder_impl = self.infer_encoder_impl = "exact"
         self.global_step = 0            # host mirror of adam_state[0] (drives the dropout stream)
@@ -180,13 +184,28 @@ class Ader:
         # state (incremented by the optimiser kernel), so every replay draws fresh masks.
         d_step = self.adam_state if (_device_step and self.encoder_impl == "tc") else None   # exact encoder: graphs only at p = 0
         seed = (self.seed << 32) + (0 if _device_step else self.global_step)
-        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl, d_step=d_step)
-        if _events:
-            _events[0].record()
         gc = global_counts if global_counts is not None else self.global_counts
         a = ops.make_loss_args(M, n_train, n_ex, max_item, v_prev, mode if n_ex > 0 else self.VANILLA, lam,
                                pos_t, ex_pos_t, teacher, trow, *(gc or (0, 0)))
         row_loss = torch.empty(M, dtype=torch.float32, device=self.device)
+        if self.step_impl != "groups" and self.encoder_impl == "tc" and self.loss_impl == "tc" and not _events:
+            # one C call: the three groups as a fork/join DAG over library-owned side streams (same kernels, same bits)
+            tcap = self._tcap(ids, n_tokens)
+            ews = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, M, tcap))
+            bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
+            lws = self._loss_ws.get(ops.loss_tc_ws_bytes(self.ms, a))
+            rep = torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
+            d_rep = torch.empty_like(rep)
+            ops.train_fwd_bwd_tc(self.ms, self.theta, ids, tcap, a, ews, bws, lws, rep, self._loss, row_loss, d_rep,
+                                 self.grad, dropout_rate, seed, d_step, serial=(self.step_impl == "serial"))
+            if self.grad_sync is not None:
+                self.grad_sync()
+            self.last_row_loss = row_loss
+            self._keep = (ids, pos_t, teacher, trow, ex_pos_t, rep, d_rep)
+            return self._loss
+        rep, tcap = self.encode(ids, n_tokens, dropout_rate, seed, impl=self.encoder_impl, d_step=d_step)
+        if _events:
+            _events[0].record()
         d_rep = torch.empty_like(rep)
         if self.loss_impl == "tc":       # tcgen05 fused kernels (bf16 operands)
             ws = self._loss_ws.get(ops.loss_tc_ws_bytes(self.ms, a))

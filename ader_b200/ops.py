@@ -138,6 +138,24 @@ def loss_fwd_bwd_tc(ms: AderModel, theta, rep, a: AderLossArgs, ws, loss, row_lo
                                            _ptr(row_loss), _ptr(d_rep), _ptr(grad), _stream()), "loss_fwd_bwd_tc")
 
 
+def train_fwd_bwd_tc(ms: AderModel, theta, ids, Tcap: int, a: AderLossArgs, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss,
+                     d_rep, grad, dropout_rate: float = 0.0, seed: int = 0, d_step=None, serial: bool = False):
+    """encoder forward -> logits + CE + KD forward/backward -> encoder backward + scatter as one fork/join DAG of the
+    same launches the three single-group entry points issue (bit-identical results; see include/ader_b200.h)."""
+    _require_cuda(theta, ids, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss, d_rep, grad)
+    check(_lib.load().ader_train_fwd_bwd_tc(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, C.byref(a), _ptr(enc_ws),
+                                            _ptr(bwd_ws), _ptr(loss_ws), _ptr(rep), _ptr(loss), _ptr(row_loss), _ptr(d_rep),
+                                            _ptr(grad), float(dropout_rate), C.c_uint64(seed), _ptr(d_step), int(bool(serial)),
+                                            _stream()), "train_fwd_bwd_tc")
+
+
+def debug_loss_tc_kernels(ms: AderModel, theta, a: AderLossArgs, ws, grad):
+    """Measurement hook: only k_tc_logits<FWD/DREP/DE> on a workspace prepared by loss_fwd_bwd_tc (same arguments)."""
+    _require_cuda(theta, ws, grad)
+    check(_lib.load().ader_debug_loss_tc_kernels(C.byref(ms), _ptr(theta), C.byref(a), _ptr(ws), _ptr(grad), _stream()),
+          "debug_loss_tc_kernels")
+
+
 def loss_tc_vp_ws_bytes(ms: AderModel, a: AderLossArgs, v_lo: int, v_hi: int) -> int:
     n = _lib.load().ader_loss_tc_vp_ws_bytes(C.byref(ms), C.byref(a), v_lo, v_hi)
     if n == 0:
@@ -215,6 +233,15 @@ def gather_rows_i32(src, idx, out):
     _require_cuda(src, idx, out)
     check(_lib.load().ader_gather_rows_i32(_ptr(src), _ptr(idx), idx.numel(), src.shape[1], _ptr(out), _stream()),
           "gather_rows_i32")
+
+
+def gather_batch(t_ids, t_lab, ti, e_ids, e_aux, ei, ids, pos, aux):
+    """ids[:n_train] = t_ids[ti], pos = t_lab[ti], ids[n_train:] = e_ids[ei], aux = e_aux[ei] in one launch."""
+    _require_cuda(t_ids, t_lab, ti, e_ids, e_aux, ei, ids, pos, aux)
+    n_train = 0 if ti is None else ti.numel()
+    n_ex = 0 if ei is None else ei.numel()
+    check(_lib.load().ader_gather_batch(_ptr(t_ids), _ptr(t_lab), _ptr(ti), n_train, _ptr(e_ids), _ptr(e_aux), _ptr(ei), n_ex,
+                                        ids.shape[1], _ptr(ids), _ptr(pos), _ptr(aux), _stream()), "gather_batch")
 
 
 # ---- torch.ops registration -------------------------------------------------------------------

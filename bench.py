@@ -335,6 +335,7 @@ def gpu_arm(args):
     # ---- the north-star kernel group alone: logits + CE + KD forward/backward (ader_loss_fwd_bwd_tc), captured as its
     # own CUDA graph and timed with CUDA events over back-to-back replays (fresh teacher rows every replay) -----------
     loss_group_ms = None
+    tc_kernels_ms = None
     try:
         rep_in = torch.randn((M, 150), device=dev) * 0.5
         pos_in = d_t_lab[d_ti[W].long()].contiguous()
@@ -361,6 +362,23 @@ def gpu_arm(args):
             rows_in.copy_(d_ei[W + (r % K)]); gl.replay()
         eb.record(); torch.cuda.synchronize()
         loss_group_ms = ea.elapsed_time(eb) / nrep
+        # ... and the three tcgen05 kernels of that group alone (k_tc_logits<FWD>, <DREP>, <DE>) on the workspace the
+        # group just prepared: the launches the roofline is quoted on
+        run_k = lambda: ops.debug_loss_tc_kernels(model.ms, model.theta, la, lws, model.grad)
+        with torch.cuda.stream(side):
+            run_k()
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk):
+            run_k()
+        for r in range(5):
+            gk.replay()
+        torch.cuda.synchronize()
+        ea.record()
+        for r in range(nrep):
+            gk.replay()
+        eb.record(); torch.cuda.synchronize()
+        tc_kernels_ms = ea.elapsed_time(eb) / nrep
         model.grad.copy_(gsave)
     except Exception as ex:      # noqa: BLE001
         sys.stderr.write("loss-group timing failed: %r\n" % (ex,))
@@ -374,8 +392,15 @@ def gpu_arm(args):
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
         flops = 6.0 * M * 150 * V                      # fwd + bwd of the output projection, d counted as 150
-        dom_ms = loss_group_ms if loss_group_ms else phases["logits_ce_kd_fwd_bwd"]
+        dom_ms = tc_kernels_ms or loss_group_ms or phases["logits_ce_kd_fwd_bwd"]
         achieved = flops / (dom_ms * 1e-3) / 1e12
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the three launches (ncu --set full, profiles/)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "tc_traffic.json")))
+            if tr.get("workload") == WL["name"]:
+                traffic = tr["dram_bytes_per_step"]
+        except Exception:
+            pass
         cpu_val, cpu_ms, cores, _ = run_cpu(2, 1)
         line = {"metric": "train sessions/sec", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
@@ -389,10 +414,14 @@ def gpu_arm(args):
                 "step_mode": "eager launches" if gs is None else "CUDA graph per token-capacity bucket %s" % (gs.tcaps,),
                 "kernels_us_per_step": dict(sorted(((k, round(v, 2)) for k, v in kernels_us.items()), key=lambda kv: -kv[1])[:12]),
                 "loss_group_ms": loss_group_ms,
-                "roofline": {"kernel": "logits+CE+KD fwd+bwd group (ader_loss_fwd_bwd_tc: 13 launches, CUDA-event timed graph replays)", "bound": "tensor",
-                             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                             "traffic": None, "peak_source": peak_src,
-                             "algorithmic_flops_per_launch": flops},
+                "tc_kernels_ms": tc_kernels_ms,
+                "step_impl": model.step_impl,
+                "roofline": {"kernel": "k_tc_logits<FWD> + <DREP> + <DE> (the three tcgen05 launches of logits+CE+KD fwd+bwd; CUDA-event "
+                                       "timed graph replays of exactly these launches; the whole 13-launch group is loss_group_ms)",
+                             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                             "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_flops_per_launch": flops,
+                             "group_achieved": flops / (loss_group_ms * 1e-3) / 1e12 if loss_group_ms else None},
                 "cpu_baseline": {"value": cpu_val, "unit": "sessions/s", "cores": cores, "kind": "port",
                                  "sample": "2 full steps of %d rows after 1 warm-up, torch-CPU fp32 restatement" % M}}
         print(json.dumps(line))

@@ -120,6 +120,10 @@ size_t  ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* a);
 int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
                              const AderLossArgs* a, void* ws, float* loss, float* row_loss,
                              float* d_rep, float* grad, void* stream);
+/* Measurement hook: launches only the three tcgen05 kernels (forward statistics, d_rep partials, dE) on a workspace
+ * prepared by a preceding ader_loss_fwd_bwd_tc call with the same arguments (bench.py times them with CUDA events). */
+int32_t ader_debug_loss_tc_kernels(const AderModel* m, const float* theta, const AderLossArgs* a, void* ws,
+                                   float* grad, void* stream);
 /* Vocab-parallel form of the same kernels (one rank owns logits columns [v_lo, v_hi), v_lo % 128 == 0):
  *   fwd  -> stats [M,4] = this shard's per-row (max, sum exp(s - max), label logit or 0, KD dot);
  *           the caller all-reduces them (max; rescaled sum; sums) into lse [M];
@@ -131,6 +135,22 @@ int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, const float*
 int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a,
                             int32_t v_lo, int32_t v_hi, void* ws, const float* lse, float* d_rep_partial,
                             float* grad, void* stream);
+/* ---- one training pass: sess.run(train_op) minus the optimiser (main.py:233-256) ------------ */
+/* encoder forward -> logits + CE + distillation forward/backward -> encoder backward + scatter, i.e. exactly
+ *   ader_encoder_fwd_tc(.., enc_ws, rep, ..) ; ader_loss_fwd_bwd_tc(.., rep, a, loss_ws, loss, row_loss, d_rep, grad) ;
+ *   ader_encoder_bwd_tc(.., enc_ws, bwd_ws, d_rep, grad, ..)
+ * with the same arguments and bit-identical results, issued as a fork/join DAG: launches that are off the critical
+ * chain (table-tile packing, teacher products, dE, weight-shadow packing, weight / LayerNorm / position gradients,
+ * partial reductions, the scalar loss) go to three library-owned side streams ordered against `stream` by events;
+ * everything is joined back into `stream` before the call returns, so the function stays stream-ordered for the
+ * caller, and under stream capture the side streams become parallel branches of the captured graph.  The side
+ * streams/events are created once per host thread and device on first use (the only allocation in the library:
+ * call once outside capture first).  serial != 0 issues the same launches on `stream` only. */
+int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                              const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                              float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                              uint64_t seed, const int32_t* d_step, int32_t serial, void* stream);
+
 /* logits [M, V] fp32 = rep . E[1..V]^T  (fetch `logits`, util.py:452,482,514). ld = row stride. */
 int32_t ader_logits(const AderModel* m, const float* theta, const float* rep, int32_t M, int32_t V,
                     float* logits, int64_t ld, void* stream);
@@ -178,6 +198,13 @@ int32_t ader_fisher_finalize(const AderModel* m, const double* acc, float* fishe
 /* out[i, :] = src[idx[i], :] for int32 rows (batch assembly from the GPU-resident row matrix). */
 int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
                              int32_t* out, void* stream);
+
+/* the whole batch of a step in one launch (Sampler.sampler + exemplar_sampler, util.py:151-263, on GPU-resident row
+ * matrices): ids [n_train + n_ex, width] = t_ids[ti[.]] then e_ids[ei[.]]; pos [n_train] = t_lab[ti[.]];
+ * aux [n_ex] = e_aux[ei[.]] (teacher row or one-hot label of each exemplar; aux / e_aux may be NULL). */
+int32_t ader_gather_batch(const int32_t* t_ids, const int32_t* t_lab, const int32_t* ti, int32_t n_train,
+                          const int32_t* e_ids, const int32_t* e_aux, const int32_t* ei, int32_t n_ex,
+                          int32_t width, int32_t* ids, int32_t* pos, int32_t* aux, void* stream);
 
 #ifdef __cplusplus
 }

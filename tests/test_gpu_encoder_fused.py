@@ -194,3 +194,42 @@ def test_graph_step_replays_match_eager_steps():
     assert out["eager"][0] == out["graph"][0]
     assert torch.equal(out["eager"][1], out["graph"][1])
     assert len(set(out["eager"][0])) == len(steps)          # dropout masks / batches really changed from step to step
+
+
+@pytest.mark.parametrize("blocks,mode", [(2, "kd"), (3, "kd"), (2, "er"), (1, "vanilla")])
+def test_train_dag_entry_is_bit_identical_to_the_three_groups(blocks, mode):
+    """ader_train_fwd_bwd_tc (fork/join DAG over the library's side streams) == ader_encoder_fwd_tc ->
+    ader_loss_fwd_bwd_tc -> ader_encoder_bwd_tc, bit for bit (loss, row losses, rep, whole gradient), over many
+    different batches (a missing edge shows up as a race), with dropout, and its serial form as well."""
+    rng = np.random.RandomState(11)
+    B, V, Vp, E = 160, 900, 800, 64
+    Me = 0 if mode == "vanilla" else 40
+    models = {}
+    for impl in ("groups", "dag", "serial"):
+        m, hp, _ = _model(1000, loss_impl="tc", num_blocks=blocks, step_impl=impl,
+                          disable_distillation=(mode == "er"))
+        if mode != "vanilla":
+            m.update_loss(0.6)
+        models[impl] = m
+    dev = models["dag"].device
+    teacher = torch.randn(E, Vp, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    for it in range(12):
+        ids = _ids(rng, B + Me, 50, V if Me == 0 else Vp, lens=rng.randint(1, 14, B + Me))
+        pos = rng.randint(1, V + 1, B).astype(np.int32)
+        kw = {}
+        if mode == "kd":
+            kw = dict(exemplar_logits=teacher, teacher_rows=rng.randint(0, E, Me).astype(np.int32))
+        elif mode == "er":
+            kw = dict(exemplar_pos=rng.randint(1, Vp + 1, Me).astype(np.int32))
+        ntok = int((ids != 0).sum())
+        got = {}
+        for impl, m in models.items():
+            m.global_step = it                      # same dropout stream in all three
+            m.grad.zero_()
+            loss = m.loss_and_grad(ids, pos, V, dropout_rate=0.3, n_tokens=ntok, **kw)
+            got[impl] = (loss.clone(), m.last_row_loss.clone(), m._keep[5].clone(), m.grad.clone())
+        torch.cuda.synchronize()
+        for impl in ("dag", "serial"):
+            for k, (x, y) in enumerate(zip(got["groups"], got[impl])):
+                assert torch.equal(x, y), "%s differs from the three-group sequence (output %d, batch %d)" % (impl, k, it)
+    assert float(got["dag"][0].item()) > 0.0
