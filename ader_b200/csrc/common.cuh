@@ -58,6 +58,25 @@ static inline int check_model(const AderModel* m) {
   return 0;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Chain kernels call pdl_wait() before their first access to data of the preceding kernel (a no-op for a normal
+// launch) and pdl_go() right behind it; launch_chain() sets the programmatic-stream-serialization attribute when
+// `pdl` is on, so the next kernel's CTAs are scheduled and run their prologue (barrier init, bulk copies of the weight
+// shadows, LayerNorm parameters) while the previous kernel drains.  ONLY kernels that call pdl_wait() may be launched
+// through launch_chain(.., pdl = true).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 // ---- fork/join plan of one call (step.cu) -----------------------------------------------------
 // The fused training entry (ader_train_fwd_bwd_tc) issues its launches as a DAG over a few internal
 // streams: `main` carries the critical chain, a / b / c carry work that is off it (weight-shadow packing,
@@ -70,7 +89,16 @@ struct Fork {
   cudaEvent_t* ev; int n_ev, next_ev;      // event pool (timing disabled); reuse is safe: every wait is issued right after its record
   cudaEvent_t table_ready;                 // recorded on `b` after the dE kernel: the scatter into the item table waits for it
   bool has_table_ready;
-  static Fork serial(cudaStream_t st) { Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.table_ready = nullptr; f.has_table_ready = false; return f; }
+  cudaEvent_t tok_ready;                   // recorded on `main` once the packed token ids exist (the scatter plan needs only them)
+  bool has_tok_ready;
+  cudaEvent_t plan_ready;                  // recorded on `c` behind the scatter plan (sorted ids)
+  bool plan_done;
+  bool pdl;                                // launch the kernel-to-kernel chain links of `main` as programmatic dependent launches
+  static Fork serial(cudaStream_t st) {
+    Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.pdl = false;
+    f.table_ready = f.tok_ready = f.plan_ready = nullptr; f.has_table_ready = f.has_tok_ready = f.plan_done = false;
+    return f;
+  }
   bool parallel() const { return a != main; }
   cudaEvent_t take() { cudaEvent_t e = ev[next_ev % n_ev]; ++next_ev; return e; }
   // work launched on `to` after this call also waits for everything launched on `from` before it
@@ -87,6 +115,8 @@ int enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, i
                    float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f);
 int enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* ids, int M, int Tcap, const void* ws, void* bwd_ws,
                    const float* d_rep, float* grad, float dropout_rate, uint64_t seed, const int32_t* d_step, Fork& f);
+// the scatter's sort of (item id, token) pairs on f.c, as soon as the token ids are packed (parallel plans only)
+int enc_scatter_plan_run(const AderModel* m, int M, int Tcap, const void* ws, void* bwd_ws, Fork& f);
 // phase 0: everything that does not need `rep` (table tiles, teacher statistics / tiles, uc partials) on f.b;
 // phase 1: the rest (rep tiles, forward statistics, loss, d_rep on f.main; dE on f.b)
 int loss_tc_run(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, void* ws, float* loss,

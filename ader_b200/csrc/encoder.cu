@@ -8,6 +8,7 @@
 // step is stream-ordered with no host synchronisation; grids are sized for the capacity Tcap and
 // surplus CTAs exit at once.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ader {
 
@@ -51,6 +52,7 @@ struct BwdWs {
   float* partial;        // [SPLITS][dense_count]
   int *keys[2], *vals[2], *hist;
   float* Dv;             // fused path: per-token softmax-backward row dots
+  float* spart; int* scount;   // windowed scatter: partial slots [windows][2][SPAD], arrival counters [windows]
   float* g2[8];          // fused path: second set of gO..gQ1 (blocks alternate sets, so the weight-gradient kernel of
                          // block b may still read its set while block b-1's data-gradient kernels write the other)
   size_t bytes;
@@ -66,6 +68,8 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
   w.hist = (int*)take(sizeof(int) * 256 * (size_t)sort_tiles(Tcap));
   w.Dv = (float*)take(sizeof(float) * Tcap);
   for (int i = 0; i < 8; ++i) w.g2[i] = (float*)take(sizeof(float) * (size_t)Tcap * m->d);
+  w.spart = (float*)take(sizeof(float) * (size_t)cdiv(Tcap, 16) * 2 * 256);
+  w.scount = (int*)take(sizeof(int) * (size_t)cdiv(Tcap, 16));
   w.bytes = o;
   return w;
 }
@@ -200,6 +204,7 @@ __global__ void k_ln_last_fwd(const float* __restrict__ x, const int* __restrict
                               const int* __restrict__ row_off, int M, float* __restrict__ rep,
                               float* __restrict__ mean, float* __restrict__ rstd,
                               const float* __restrict__ beta, const float* __restrict__ gamma, int d) {
+  pdl_wait(); pdl_go();
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= M) return;
   int n = row_len[r];
@@ -828,6 +833,114 @@ __global__ void __launch_bounds__(256) k_scatter_small(const int* __restrict__ t
   }
 }
 
+// Windowed form of the segmented reduction (all step sizes): the (item id, token) pairs are radix-sorted OFF the
+// critical path (the ids are known as soon as the batch is packed), so the part that has to wait for the gradient is
+// one launch with no serial tail.  One warp per window of SW consecutive sorted positions: its SW gradient rows are
+// fetched in one batch, runs of equal ids are summed in sorted (= token) order, and
+//   * a run that is a whole segment goes to its table row with one reduction per element (the row has exactly one
+//     contributor, so the result does not depend on any ordering),
+//   * a run that is a PIECE of a longer segment (a hot item spanning several windows) is parked in a partial slot;
+//     the last piece to arrive (per-segment arrival counter) adds the pieces in window order and writes the row.
+// Every row is therefore a fixed function of the sorted order: deterministic, and a 230-occurrence item costs two
+// dependent batches instead of fifteen.
+constexpr int SW = 16;
+constexpr int SPAD = 160 > LN_MAXE * 32 ? 160 : LN_MAXE * 32;      // floats per partial slot
+template <int NEL>
+__global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ keys, const int* __restrict__ vals,
+                                                       const int* __restrict__ dT, const float* __restrict__ gx, int d, float scale,
+                                                       float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter) {
+  const int T = *dT;
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int p0 = w * SW;
+  if (p0 >= T) return;
+  const int n = min(SW, T - p0);
+  const int key_l = (lane < n) ? keys[p0 + lane] : -1;
+  const int val_l = (lane < n) ? vals[p0 + lane] : 0;
+  const int key_prev = (p0 > 0) ? keys[p0 - 1] : -1;
+  const int key_next = (p0 + n < T) ? keys[p0 + n] : -1;
+  float v[SW][NEL];
+#pragma unroll
+  for (int u = 0; u < SW; ++u) {
+    const int tu = __shfl_sync(0xffffffffu, val_l, u);
+    const long long o = (long long)tu * d;
+#pragma unroll
+    for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; v[u][i] = (u < n && c < d) ? gx[o + c] : 0.f; }
+  }
+  float acc[NEL];
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+  int run_start = 0;
+#pragma unroll
+  for (int u = 0; u < SW; ++u) {
+    const int ku = __shfl_sync(0xffffffffu, key_l, u);
+    const int kn = __shfl_sync(0xffffffffu, key_l, (u + 1) & 31);
+    if (u < n) {                                                   // warp-uniform
+#pragma unroll
+      for (int i = 0; i < NEL; ++i) acc[i] += v[u][i];
+      const bool last_in_window = (u + 1 == n);
+      if (last_in_window || kn != ku) {                            // the run [run_start, u] of item ku ends here
+        const bool cont_after = last_in_window && key_next == ku;
+        const bool cont_before = run_start == 0 && key_prev == ku;
+        if (!cont_after && !cont_before) {
+#pragma unroll
+          for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
+        } else {
+          float* mine = part + ((long long)w * 2 + (cont_before ? 0 : 1)) * SPAD;
+#pragma unroll
+          for (int i = 0; i < NEL; ++i) mine[lane + 32 * i] = acc[i];
+          int head = p0 + run_start, end = p0 + u + 1;
+          if (cont_before) {                                       // segment head: last position before p0 with another id, + 1
+            for (int base = p0 - 32;; base -= 32) {
+              const int q = base + lane;
+              const unsigned m = __ballot_sync(0xffffffffu, q < 0 || keys[q] != ku);
+              if (m) { head = base + (31 - __clz(m)) + 1; break; }
+            }
+          }
+          if (cont_after) {                                        // segment end (exclusive)
+            for (int base = p0 + n;; base += 32) {
+              const int q = base + lane;
+              const unsigned m = __ballot_sync(0xffffffffu, q >= T || keys[q] != ku);
+              if (m) { end = base + __ffs(m) - 1; break; }
+            }
+          }
+          const int w1 = head / SW, w2 = (end - 1) / SW;
+          __threadfence();
+          __syncwarp();
+          int old = 0;
+          if (lane == 0) old = atomicAdd(counter + w1, 1);
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old == w2 - w1) {                                    // last piece to arrive: add the pieces in window order
+            __threadfence();
+            float tot[NEL];
+#pragma unroll
+            for (int i = 0; i < NEL; ++i) tot[i] = 0.f;
+            for (int pw = w1; pw <= w2; pw += 8) {
+              float t[8][NEL];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                const bool ok = pw + x <= w2;
+                const float* src = part + ((long long)(ok ? pw + x : w1) * 2 + ((pw + x == w1) ? 1 : 0)) * SPAD;
+#pragma unroll
+                for (int i = 0; i < NEL; ++i) t[x][i] = ok ? __ldcg(src + lane + 32 * i) : 0.f;
+              }
+#pragma unroll
+              for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int i = 0; i < NEL; ++i) tot[i] += t[x][i];
+            }
+#pragma unroll
+            for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * tot[i]); }
+            if (lane == 0) counter[w1] = 0;                        // ready for the next step
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+        run_start = u + 1;
+      }
+    }
+  }
+}
+
 static int key_bits(int v_tab) { int b = 1; while ((1LL << b) < v_tab) ++b; return b; }
 
 }  // namespace ader
@@ -887,12 +1000,54 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
   return run_table_scatter(m, l, w, g, gX, M, Tcap, grad, st);
 }
 
-// item-table scatter (modules.py:127-130)
+// ---- item-table scatter (modules.py:127-130) ------------------------------------------------------------------
+// ADER_B200_SCATTER=legacy selects the previous forms (first-occurrence ownership / sort + per-segment warp).
+static bool scatter_legacy() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADER_B200_SCATTER"); v = (e && e[0] == 'l') ? 1 : 0; }
+  return v == 1;
+}
+static int sort_passes(const AderModel* m) { return (key_bits(m->v_tab) + 7) / 8; }
+// plan: stable LSD radix sort of (item id, token); depends on the packed ids only
+static int run_scatter_plan(const AderModel* m, const EncWs& w, const BwdWs& g, int M, int Tcap, cudaStream_t st) {
+  const int* dT = w.row_off + M;
+  const int ntiles = sort_tiles(Tcap);
+  const int bits = key_bits(m->v_tab);
+  cudaMemsetAsync(g.scount, 0, sizeof(int) * (size_t)cdiv(Tcap, SW), st);
+  int cur = 0;
+  const int* kin = w.tok_id; const int* vin = nullptr;
+  int pass = 0;
+  for (int shift = 0; shift < bits; shift += 8, ++pass) {
+    k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
+    k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
+    k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
+    kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
+  }
+  ADER_CHECK_LAUNCH("scatter plan");
+  return 0;
+}
+static int run_scatter_apply(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
+                             int M, int Tcap, float* grad, cudaStream_t st) {
+  const int d = m->d;
+  const int* dT = w.row_off + M;
+  const int fin = (sort_passes(m) - 1) & 1;
+  const int grid = cdiv((long long)cdiv(Tcap, SW) * 32, 256);
+  if (d <= 160)
+    k_scatter_apply<5><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount);
+  else
+    k_scatter_apply<LN_MAXE><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount);
+  ADER_CHECK_LAUNCH("scatter apply");
+  return 0;
+}
 static int run_table_scatter(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
                              int M, int Tcap, float* grad, cudaStream_t st) {
   const float p = 0.f; const uint64_t seed = 0; const int* d_step = nullptr;
   const int d = m->d;
   const int* dT = w.row_off + M;
+  if (!scatter_legacy()) {
+    if (int e = run_scatter_plan(m, w, g, M, Tcap, st)) return e;
+    return run_scatter_apply(m, l, w, g, gX, M, Tcap, grad, st);
+  }
   if (Tcap <= SS_MAXT) {
     if (d <= 160)
       k_scatter_small<5><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
@@ -1149,6 +1304,7 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
   k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
+  if (f.parallel()) { f.tok_ready = f.take(); cudaEventRecord(f.tok_ready, st); f.has_tok_ready = true; }
   f.edge(f.a, st);
 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
@@ -1168,25 +1324,37 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     qa.Wq = shadow_of(w, b, 0, 0); qa.Wk = shadow_of(w, b, 1, 0); qa.Wv = shadow_of(w, b, 2, 0);
     qa.bq = P + l.bq; qa.bk = P + l.bk; qa.bv = P + l.bv;
     qa.Q = Qp; qa.K = Kp; qa.V = Vp; qa.dT = dT; qa.d = d; qa.L = L;
-    fz::k_qkv_fwd<<<tile_grid, fz::NTHR, fz::QKV_FWD_SMEM, st>>>(qa);
+    launch_chain(fz::k_qkv_fwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_FWD_SMEM, st, f.pdl && b > 0, qa);
 
     fz::AttnFwdArgs aa;
     aa.Q = Qp; aa.K = Kp; aa.V = Vp; aa.Q1 = Q1; aa.tok_row = w.tok_row; aa.row_off = w.row_off;
     aa.probs = w.probs[b]; aa.Y = Y; aa.Z = Z; aa.mean2 = w.mean2[b]; aa.rstd2 = w.rstd2[b];
     aa.ln_b = P + l.ln2b; aa.ln_g = P + l.ln2g; aa.dT = dT; aa.d = d; aa.nh = m->num_heads; aa.L = L; aa.Tcap = Tcap;
     aa.drop_p = dropout_rate; aa.seed = seed; aa.d_step = d_step; aa.site = 1u + 3u * b;
-    fz::k_attn_ln_fwd<<<warp_grid, 256, att_smem, st>>>(aa);
+    launch_chain(fz::k_attn_ln_fwd, dim3(warp_grid), dim3(256), att_smem, st, f.pdl, aa);
 
     fz::FfnFwdArgs fa;
     fa.Z = Z; fa.H = H; fa.Xn = Xn; fa.W1 = shadow_of(w, b, 3, 0); fa.W2 = shadow_of(w, b, 4, 0);
     fa.b1 = P + l.b1; fa.b2 = P + l.b2; fa.dT = dT; fa.d = d;
     fa.drop_p = dropout_rate; fa.seed = seed; fa.d_step = d_step; fa.site1 = 2u + 3u * b; fa.site2 = 3u + 3u * b;
-    fz::k_ffn_fwd<<<tile_grid, fz::NTHR, fz::FFN_FWD_SMEM, st>>>(fa);
+    launch_chain(fz::k_ffn_fwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_FWD_SMEM, st, f.pdl, fa);
     ADER_CHECK_LAUNCH("encoder_fwd_tc/block");
   }
-  k_ln_last_fwd<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.xfinal, w.row_len, w.row_off, M, rep, w.meanf, w.rstdf,
-                                                               theta + l.off_lnf, theta + l.off_lnf + d, d);
+  launch_chain(k_ln_last_fwd, dim3(cdiv((long long)M * 32, 256)), dim3(256), 0, st, f.pdl, (const float*)w.xfinal, (const int*)w.row_len,
+               (const int*)w.row_off, M, rep, w.meanf, w.rstdf, theta + l.off_lnf, theta + l.off_lnf + d, d);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/final_ln");
+  return 0;
+}
+
+int ader::enc_scatter_plan_run(const AderModel* m, int M, int Tcap, const void* ws, void* bwd_ws, Fork& f) {
+  if (!f.parallel() || !f.has_tok_ready || scatter_legacy()) return 0;
+  EncWs w = carve_enc(m, M, Tcap, (char*)ws);
+  BwdWs g = carve_bwd(m, M, Tcap, (char*)bwd_ws);
+  cudaStreamWaitEvent(f.c, f.tok_ready, 0);
+  if (int e = run_scatter_plan(m, w, g, M, Tcap, f.c)) return e;
+  f.plan_ready = f.take();
+  cudaEventRecord(f.plan_ready, f.c);
+  f.plan_done = true;
   return 0;
 }
 
@@ -1241,19 +1409,20 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     float *gO = gs[0], *gH = gs[1], *gZ = gs[2], *gY = gs[3], *gQ = gs[4], *gK = gs[5], *gV = gs[6], *gQ1 = gs[7];
     float* gX = chain[ci % 3]; float* gXin = chain[(ci + 1) % 3]; ++ci;
     // this block rewrites the buffer set (and chain buffer) last read by the weight-gradient kernel of block b + 2
-    if (f.parallel() && b + 2 < m->num_blocks) cudaStreamWaitEvent(st, wg_done[b + 2], 0);
+    const bool joined = f.parallel() && b + 2 < m->num_blocks;
+    if (joined) cudaStreamWaitEvent(st, wg_done[b + 2], 0);
     fz::FfnBwdArgs fa;
     fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
     fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
     fa.gH = gH; fa.gZ = gZ; fa.gY = gY; fa.D = g.Dv; fa.dT = dT; fa.d = d;
     fa.drop_p = p; fa.seed = seed; fa.d_step = d_step; fa.site2 = 3u + 3u * b;
-    fz::k_ffn_bwd<<<tile_grid, fz::NTHR, fz::FFN_BWD_SMEM, st>>>(fa);
+    launch_chain(fz::k_ffn_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_BWD_SMEM, st, f.pdl && !joined, fa);
 
     fz::AttnBwdArgs ab;
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
     ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
     ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.d_step = d_step; ab.site = 1u + 3u * b;
-    if (m->num_heads == 1) fz::k_attn_bwd_s1<<<cdiv(Tcap, fz::ATT_TOK), 256, fz::att_bwd_smem(L, d), st>>>(ab);
+    if (m->num_heads == 1) launch_chain(fz::k_attn_bwd_s1, dim3(cdiv(Tcap, fz::ATT_TOK)), dim3(256), (size_t)fz::att_bwd_smem(L, d), st, f.pdl, ab);
     else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
 
     fz::QkvBwdArgs qb;
@@ -1261,7 +1430,7 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     qb.ln_g = P + l.ln1g; qb.Wqb = shadow_of(w, b, 0, 1); qb.Wkb = shadow_of(w, b, 1, 1); qb.Wvb = shadow_of(w, b, 2, 1);
     qb.gQ1 = gQ1; qb.gXin = gXin; qb.dT = dT; qb.d = d;
     qb.drop_p = (b == 0) ? p : 0.f; qb.seed = seed; qb.d_step = d_step;       // block 0: x0 = drop(emb) (ADER.py:55)
-    fz::k_qkv_bwd<<<tile_grid, fz::NTHR, fz::QKV_BWD_SMEM, st>>>(qb);
+    launch_chain(fz::k_qkv_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_BWD_SMEM, st, f.pdl, qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
 
     // weight / bias / LayerNorm-parameter gradients of the block: one launch (TF32 tensor cores, fp32 accumulate)
@@ -1289,7 +1458,10 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
   // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
   if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);
-  if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  if (f.plan_done) {
+    cudaStreamWaitEvent(st, f.plan_ready, 0);
+    if (int e = run_scatter_apply(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  } else if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
   f.edge(f.a, st);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");
   return 0;

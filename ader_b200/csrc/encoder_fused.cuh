@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; lg[e] = (c < d) ? a.ln_g[c] : 0.f; lb[e] = (c < d) ? a.ln_b[c] : 0.f; }
   float2 bq[NT], bk[NT], bv[NT];
   load_bias_frag(bq, a.bq, d, ng, lane); load_bias_frag(bk, a.bk, d, ng, lane); load_bias_frag(bv, a.bv, d, ng, lane);
+  pdl_wait(); pdl_go();        // everything above reads step constants only (weights, LN parameters, T)
   __syncthreads();
   FZ_TL(0, 1);
   bool first = true;
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ 
   const int T = *a.dT;
   const int t0 = blockIdx.x * ATT_TOK;
   if (t0 >= T) return;
+  pdl_wait(); pdl_go();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, L = a.L;
   const int tk = min(t0 + warp, T - 1);          // surplus warps of the last CTA shadow its last token (no stores)
@@ -617,6 +619,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
   const int mt = warp & 1, ng = warp >> 1;
   float2 b1[NT], b2[NT];
   load_bias_frag(b1, a.b1, d, ng, lane); load_bias_frag(b2, a.b2, d, ng, lane);
+  pdl_wait(); pdl_go();
   __syncthreads();
   bool first = true;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -722,6 +725,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ Ffn
   float gam[NE];
 #pragma unroll
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; gam[e] = (c < d) ? a.ln_g[c] : 0.f; }
+  pdl_wait(); pdl_go();
   __syncthreads();
   FZ_TL(1, 1);
   const int mt = warp & 1, ng = warp >> 1;
@@ -963,6 +967,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ 
   const int T = *a.dT;
   const int t0 = blockIdx.x * ATT_TOK;
   if (t0 >= T) return;
+  pdl_wait(); pdl_go();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, L = a.L;
   const int tk = min(t0 + warp, T - 1);
@@ -1087,6 +1092,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
   float gam[NE];
 #pragma unroll
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; gam[e] = (c < d) ? a.ln_g[c] : 0.f; }
+  pdl_wait(); pdl_go();
   __syncthreads();
   const int mt = warp & 1, ng = warp >> 1;
   bool first = true;

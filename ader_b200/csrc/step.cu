@@ -8,18 +8,23 @@
 // with the same arguments -- results are bit-identical -- but puts the off-path work on three internal streams
 // joined by events.  Captured by a CUDA graph the side streams become parallel branches of the graph.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ader {
 
 struct StreamPool {
-  cudaStream_t s[3];
+  cudaStream_t s[3];     // side streams, lowest priority
+  cudaStream_t hi;       // critical chain, highest priority: its pending CTAs are placed before those of the side streams
   cudaEvent_t ev[64];
   bool ok;
   StreamPool() : ok(false) {}
   int init() {
     if (ok) return 0;
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
     for (int i = 0; i < 3; ++i)
-      if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
+      if (cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, least) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
+    if (cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, greatest) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
     for (int i = 0; i < 64; ++i)
       if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create an event");
     ok = true;
@@ -28,6 +33,13 @@ struct StreamPool {
 };
 // one pool per host thread and device (streams belong to the device that was current at creation)
 static thread_local StreamPool g_pool[16];
+
+// experiment switches (read once): ADER_B200_DAG_PRIO=0 keeps the chain on the caller's stream;
+// ADER_B200_PDL=1 launches the chain links as programmatic dependent launches
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
 
 }  // namespace ader
 
@@ -49,11 +61,16 @@ extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta,
     if (int e = p.init()) return e;
     f.a = p.s[0]; f.b = p.s[1]; f.c = p.s[2];
     f.ev = p.ev; f.n_ev = 64; f.next_ev = 0;
+    static const int prio = env_flag("ADER_B200_DAG_PRIO", 1);
+    if (prio) { f.main = p.hi; f.edge(st, f.main); }
   }
+  static const int pdl = env_flag("ADER_B200_PDL", 0);
+  f.pdl = pdl != 0;
   // teacher products / table tiles need nothing from the encoder: start them first, beside it
-  f.edge(st, f.b);
+  f.edge(f.main, f.b);
   if (int e = loss_tc_run(m, theta, nullptr, a, loss_ws, nullptr, nullptr, nullptr, grad, f, 1)) return e;
   if (int e = enc_fwd_tc_run(m, theta, ids, M, Tcap, enc_ws, rep, dropout_rate, seed, d_step, f)) return e;
+  if (int e = enc_scatter_plan_run(m, M, Tcap, enc_ws, bwd_ws, f)) return e;
   if (int e = loss_tc_run(m, theta, rep, a, loss_ws, loss, row_loss, d_rep, grad, f, 2)) return e;
   if (int e = enc_bwd_tc_run(m, theta, ids, M, Tcap, enc_ws, bwd_ws, d_rep, grad, dropout_rate, seed, d_step, f)) return e;
   // every side stream is already ordered before the tail of `stream` (a: joined by the backward, b: the scatter
@@ -61,6 +78,7 @@ extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta,
   f.edge(f.a, st);
   f.edge(f.b, st);
   f.edge(f.c, st);
+  f.edge(f.main, st);
   ADER_CHECK_LAUNCH("train_fwd_bwd_tc");
   return 0;
 }
