@@ -329,6 +329,8 @@ def gpu_arm(args):
                 cnt += 1
                 kernels_us[n] = kernels_us.get(n, 0.0) + e.device_time / nprof
         launches_per_step = cnt // nprof
+        if os.environ.get("ADER_B200_TRACE") and rank == 0:      # kernel timeline of the replayed steps (critical-path analysis)
+            prof.export_chrome_trace(os.environ["ADER_B200_TRACE"])
     except Exception:
         pass
 
