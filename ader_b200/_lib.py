@@ -65,6 +65,8 @@ SIGNATURES = {
     "ader_loss_tc_vp_bwd": (C.c_int32, [_MP, _P, _P, C.POINTER(AderLossArgs), C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "ader_train_fwd_bwd_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P, _P,
                                           _P, C.c_float, C.c_uint64, _P, C.c_int32, _P]),
+    "ader_train_step_tc": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, C.POINTER(AderLossArgs), _P, _P, _P, _P, _P, _P, _P,
+                                       _P, C.c_float, C.c_uint64, _P, _P, _P, _P, C.POINTER(AderAdamArgs), C.c_int32, _P]),
     "ader_logits": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "ader_adam_step": (C.c_int32, [_MP, _P, _P, _P, _P, _P, C.POINTER(AderAdamArgs), _P]),
     "ader_eval_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),

@@ -84,7 +84,17 @@ static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 b
 // every edge is a no-op and the launches are issued in the historical serial order, so the single-stream
 // entry points run the very same code.  Under stream capture the side streams join the capture through
 // the event edges and become parallel branches of the CUDA graph.
+// optimiser step folded into the fused training entry (single GPU: no gradient all-reduce between backward and Adam)
+struct AdamPlan {
+  float *theta, *m, *v; const float* grad; int32_t* state; AderAdamArgs a;
+  cudaEvent_t prep_ready;       // bias-corrected step size of this step is in state[1]
+};
+int adam_prep_early(const AdamPlan& p, cudaStream_t st);                       // state[1] = lr_t(state[0] + 1); no increment
+int adam_table_part(const AderModel* m, const AdamPlan& p, cudaStream_t st);   // item-table rows 1..V
+int adam_dense_part(const AderModel* m, const AdamPlan& p, cudaStream_t st);   // everything after the table; bumps state[0]
+
 struct Fork {
+  const AdamPlan* adam;
   cudaStream_t main, a, b, c;
   cudaEvent_t* ev; int n_ev, next_ev;      // event pool (timing disabled); reuse is safe: every wait is issued right after its record
   cudaEvent_t table_ready;                 // recorded on `b` after the dE kernel: the scatter into the item table waits for it
@@ -95,7 +105,7 @@ struct Fork {
   bool plan_done;
   bool pdl;                                // launch the kernel-to-kernel chain links of `main` as programmatic dependent launches
   static Fork serial(cudaStream_t st) {
-    Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.pdl = false;
+    Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.pdl = false; f.adam = nullptr;
     f.table_ready = f.tok_ready = f.plan_ready = nullptr; f.has_table_ready = f.has_tok_ready = f.plan_done = false;
     return f;
   }

@@ -254,6 +254,7 @@ __global__ void k_lnf_bwd(const float* __restrict__ d_rep, const float* __restri
                           const float* __restrict__ gamma, const int* __restrict__ tok_row,
                           const int* __restrict__ row_off, float* __restrict__ gx,
                           const int* __restrict__ dT, int d) {
+  pdl_wait(); pdl_go();
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= *dT) return;
   int r = tok_row[t];
@@ -1395,7 +1396,9 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   f.edge(st, f.a);
   k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, f.a>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
-  k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, chain[0], dT, d);
+  // directly behind the d_rep reduction on f.main in the fused step (f.pdl is only set there)
+  launch_chain(k_lnf_bwd, dim3(ln_grid), dim3(256), 0, st, f.pdl, d_rep, (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf,
+               theta + l.off_lnf + d, (const int*)w.tok_row, (const int*)w.row_off, chain[0], dT, d);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
 
   cudaEvent_t wg_done[8];                   // weight-gradient kernel of block b finished (f.a), parallel plans only
@@ -1456,12 +1459,20 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
   f.edge(f.c, f.a);
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
+  if (f.adam) {                              // fused step: the dense parameters are final here
+    cudaStreamWaitEvent(f.a, f.adam->prep_ready, 0);
+    if (int e = adam_dense_part(m, *f.adam, f.a)) return e;
+  }
   // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
   if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);
   if (f.plan_done) {
     cudaStreamWaitEvent(st, f.plan_ready, 0);
     if (int e = run_scatter_apply(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
   } else if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  if (f.adam) {                              // ... and the item-table rows here
+    cudaStreamWaitEvent(st, f.adam->prep_ready, 0);
+    if (int e = adam_table_part(m, *f.adam, st)) return e;
+  }
   f.edge(f.a, st);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");
   return 0;

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t ACC_COL = 256;
+  pdl_wait(); pdl_go();      // barrier init + TMEM allocation above overlap the previous kernel's drain (chain launches)
   if (threadIdx.x == 64) TL(2);
 
   if (warp == 0) {
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__(KP) k_reduce_u(const float* __restrict__ part,
                                                  const float* __restrict__ rep, int x0, int M, int d, float* __restrict__ udot) {
   __shared__ float sh[KP / 32];
   const int r = blockIdx.x, c = threadIdx.x;
+  pdl_wait(); pdl_go();
   float s = 0.f;
   for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows + r) * KP + c];
   u[(size_t)r * KP + c] = s;
@@ -661,19 +663,28 @@ __global__ void __launch_bounds__(KP) k_reduce_u(const float* __restrict__ part,
 }
 
 // merge the per-chunk online-softmax partials: lse[M], row_loss[M].  Distillation rows: dot = rep_i . u_i.
-__global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chunks, int n_train, int mode,
-                              float* __restrict__ lse, float* __restrict__ row_loss, float* __restrict__ local_out,
-                              const float* __restrict__ udot, int x0, float coef_ex) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Warp per row, lanes over the chunk partials (one L2 round trip instead of a serial walk over the chunks);
+// lane partials are combined in a fixed butterfly order.
+__global__ void __launch_bounds__(256) k_merge_stats(const float* __restrict__ stats, int M, int n_chunks, int n_train, int mode,
+                                                     float* __restrict__ lse, float* __restrict__ row_loss, float* __restrict__ local_out,
+                                                     const float* __restrict__ udot, int x0, float coef_ex) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait(); pdl_go();
   if (i >= M) return;
-  float mx = -INFINITY;
-  for (int c = 0; c < n_chunks; ++c) mx = fmaxf(mx, stats[((size_t)c * M + i) * 4]);
-  float sum = 0.f, lab = 0.f, dot = 0.f;
-  for (int c = 0; c < n_chunks; ++c) {
+  float mx = -INFINITY, lab = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) mx = fmaxf(mx, stats[((size_t)c * M + i) * 4]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) {
     const float4 s = *reinterpret_cast<const float4*>(stats + ((size_t)c * M + i) * 4);
     if (s.x > -INFINITY) sum += s.y * expf(s.x - mx);
     lab += s.z;
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); lab += __shfl_xor_sync(0xffffffffu, lab, o); }
+  if (lane) return;
+  float dot = 0.f;
   // distillation rows: sum_j softmax(t)_j s_ij = rep_i . (P.E)_i = rep_i . uc_i / coef  (coef = 0: the term has zero weight)
   if (i >= n_train && mode == 1 && udot && coef_ex != 0.f) dot = udot[i - x0 * TILE] / coef_ex;
   if (local_out) {      // vocab-parallel: hand the shard's (max, sumexp, label logit, kd dot) to the host-side all-reduce
@@ -690,6 +701,7 @@ __global__ void k_merge_stats(const float* __restrict__ stats, int M, int n_chun
 __global__ void k_reduce_drep(const float* __restrict__ part, int n_chunks, int rows_pad, int M, int d,
                               float* __restrict__ d_rep, const float* __restrict__ u, int x0, int n_train) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait(); pdl_go();
   if (idx >= (long long)M * d) return;
   const int i = (int)(idx / d), c = (int)(idx % d);
   float s = 0.f;
@@ -855,20 +867,22 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
 
   f.edge(sb, st);
   k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
-  if (kd) launch_reduce_u(a, w, rep, d, st);
+  // chain links (kernel directly behind a kernel on f.main) may be programmatic dependent launches
+  if (kd) launch_chain(k_reduce_u, dim3(w.n_et * TILE), dim3(KP), 0, st, f.pdl, (const float*)w.u_part, w.n_chunks_t, w.n_et * TILE, w.u, rep,
+                       w.x0_t, a->M, d, w.udot);
   ADER_CHECK_LAUNCH("tc pack");
-  k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
-  k_merge_stats<<<cdiv(M, 128), 128, 0, st>>>(w.stats, M, nc * 2, a->n_train, t.mode, w.lse, row_loss, nullptr,
-                                              kd ? w.udot : nullptr, w.x0_t, t.coef_ex);
+  launch_chain(k_tc_logits<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_fwd, st, f.pdl, t);
+  launch_chain(k_merge_stats, dim3(cdiv((long long)M * 32, 256)), dim3(256), 0, st, f.pdl, (const float*)w.stats, M, nc * 2, a->n_train, t.mode,
+               w.lse, row_loss, (float*)nullptr, (const float*)(kd ? w.udot : nullptr), w.x0_t, t.coef_ex);
   cudaEvent_t lse_ready = nullptr;
   if (f.parallel()) { lse_ready = f.take(); cudaEventRecord(lse_ready, st); }
   f.edge(st, f.c);
   if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, f.c, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
-    k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
-    k_reduce_drep<<<cdiv((long long)M * d, 256), 256, 0, st>>>(w.drep_part, nc, nm * TILE, M, d, d_rep,
-                                                               kd ? w.u : nullptr, w.x0_t, a->n_train);
+    launch_chain(k_tc_logits<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_bwd, st, f.pdl, t);
+    launch_chain(k_reduce_drep, dim3(cdiv((long long)M * d, 256)), dim3(256), 0, st, f.pdl, (const float*)w.drep_part, nc, nm * TILE, M, d, d_rep,
+                 (const float*)(kd ? w.u : nullptr), w.x0_t, a->n_train);
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {
@@ -877,7 +891,7 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
     ADER_CHECK_LAUNCH("tc d_table");
     if (f.parallel()) { f.table_ready = f.take(); cudaEventRecord(f.table_ready, sb); f.has_table_ready = true; }
   }
-  f.edge(f.c, st);
+  // f.c (scalar loss) is joined by the caller's closing edges: a join here would sit between d_rep and the backward chain
   return 0;
 }
 
@@ -943,7 +957,7 @@ extern "C" int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, c
   TcWs w; TcArgs t;
   vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, true);
   k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, SMEM_FWD, st>>>(t);
-  k_merge_stats<<<cdiv(a->M, 128), 128, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats,
+  k_merge_stats<<<cdiv((long long)a->M * 32, 256), 256, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats,
                                                  w.n_et > 0 ? w.udot : nullptr, w.x0_t, t.coef_ex);
   ADER_CHECK_LAUNCH("loss_tc_vp_fwd");
   return 0;

@@ -13,11 +13,19 @@ __global__ void k_adam_prep(int* __restrict__ state, float lr, float beta1, floa
   state[1] = __float_as_int((float)lr_t);
 }
 
+// early form for the fused step: the step size of step t + 1 without touching the counter (the dropout streams of the
+// running step still read state[0]); the dense part of the update bumps the counter when it is done
+__global__ void k_adam_prep_early(int* __restrict__ state, float lr, float beta1, float beta2) {
+  const int t = state[0] + 1;
+  double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+  state[1] = __float_as_int((float)lr_t);
+}
+
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* __restrict__ am, float* __restrict__ av,
                                               const float* __restrict__ grad, const int* __restrict__ state,
                                               long long n_table, long long table_lo, long long dense_lo, long long n_total,
                                               float beta1, float beta2, float eps, float ewc_lambda,
-                                              const float* __restrict__ fisher, const float* __restrict__ theta_star) {
+                                              const float* __restrict__ fisher, const float* __restrict__ theta_star, int bump) {
   const float lr_t = __int_as_float(state[1]);
   // two elements per thread (both ranges start on even offsets because d is even)
   long long i2 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -40,6 +48,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
   *reinterpret_cast<float2*>(theta + e) = th;
   *reinterpret_cast<float2*>(am + e) = m;
   *reinterpret_cast<float2*>(av + e) = v;
+  if (bump && i2 == 0) const_cast<int*>(state)[0] += 1;      // fused step: the counter moves once every reader of it is done
 }
 
 __global__ void __launch_bounds__(256) k_fisher_acc(const float* __restrict__ grad, double* __restrict__ acc,
@@ -79,8 +88,30 @@ extern "C" int32_t ader_adam_step(const AderModel* m, float* theta, float* adam_
   k_adam_prep<<<1, 1, 0, st>>>(state, a->lr, a->beta1, a->beta2);
   k_adam<<<cdiv(n_total / 2 + 1, 256), 256, 0, st>>>(theta, adam_m, adam_v, grad, state, n_table, (long long)m->d,
                                                      l.off_pos, n_total, a->beta1, a->beta2, a->eps, a->ewc_lambda,
-                                                     a->fisher, a->theta_star);
+                                                     a->fisher, a->theta_star, 0);
   ADER_CHECK_LAUNCH("adam");
+  return 0;
+}
+
+int ader::adam_prep_early(const AdamPlan& p, cudaStream_t st) {
+  k_adam_prep_early<<<1, 1, 0, st>>>(p.state, p.a.lr, p.a.beta1, p.a.beta2);
+  ADER_CHECK_LAUNCH("adam prep");
+  return 0;
+}
+int ader::adam_table_part(const AderModel* m, const AdamPlan& p, cudaStream_t st) {
+  const Layout l = make_layout(m);
+  const long long n_table = (long long)p.a.V * m->d;
+  k_adam<<<cdiv(n_table / 2 + 1, 256), 256, 0, st>>>(p.theta, p.m, p.v, p.grad, p.state, n_table, (long long)m->d, l.off_pos, n_table,
+                                                     p.a.beta1, p.a.beta2, p.a.eps, p.a.ewc_lambda, p.a.fisher, p.a.theta_star, 0);
+  ADER_CHECK_LAUNCH("adam table");
+  return 0;
+}
+int ader::adam_dense_part(const AderModel* m, const AdamPlan& p, cudaStream_t st) {
+  const Layout l = make_layout(m);
+  const long long n_dense = l.dense_count();
+  k_adam<<<cdiv(n_dense / 2 + 1, 256), 256, 0, st>>>(p.theta, p.m, p.v, p.grad, p.state, 0, (long long)m->d, l.off_pos, n_dense,
+                                                     p.a.beta1, p.a.beta2, p.a.eps, p.a.ewc_lambda, p.a.fisher, p.a.theta_star, 1);
+  ADER_CHECK_LAUNCH("adam dense");
   return 0;
 }
 

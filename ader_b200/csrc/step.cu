@@ -45,18 +45,17 @@ static int env_flag(const char* name, int dflt) {
 
 using namespace ader;
 
-extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
-                                         const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
-                                         float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
-                                         uint64_t seed, const int32_t* d_step, int32_t serial, void* stream) {
+static int run_step(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                    const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                    float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                    uint64_t seed, const int32_t* d_step, int32_t serial, cudaStream_t st, AdamPlan* adam) {
   ADER_CHECK_ARG(m && theta && ids && a && enc_ws && bwd_ws && loss_ws && rep && loss && row_loss && d_rep && grad,
-                 "train_fwd_bwd_tc: NULL pointer");
-  ADER_CHECK_ARG(a->M == M, "train_fwd_bwd_tc: loss rows (%d) != encoder rows (%d)", a->M, M);
-  cudaStream_t st = (cudaStream_t)stream;
+                 "train step: NULL pointer");
+  ADER_CHECK_ARG(a->M == M, "train step: loss rows (%d) != encoder rows (%d)", a->M, M);
   Fork f = Fork::serial(st);
   if (!serial) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return fail(-3, "train_fwd_bwd_tc: bad device");
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return fail(-3, "train step: bad device");
     StreamPool& p = g_pool[dev];
     if (int e = p.init()) return e;
     f.a = p.s[0]; f.b = p.s[1]; f.c = p.s[2];
@@ -64,21 +63,53 @@ extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta,
     static const int prio = env_flag("ADER_B200_DAG_PRIO", 1);
     if (prio) { f.main = p.hi; f.edge(st, f.main); }
   }
-  static const int pdl = env_flag("ADER_B200_PDL", 0);
+  static const int pdl = env_flag("ADER_B200_PDL", 1);
   f.pdl = pdl != 0;
   // teacher products / table tiles need nothing from the encoder: start them first, beside it
   f.edge(f.main, f.b);
   if (int e = loss_tc_run(m, theta, nullptr, a, loss_ws, nullptr, nullptr, nullptr, grad, f, 1)) return e;
+  if (adam) {                 // the step size of this update depends on the step counter only
+    if (f.parallel()) {
+      f.edge(f.main, f.c);
+      if (int e = adam_prep_early(*adam, f.c)) return e;
+      adam->prep_ready = f.take();
+      cudaEventRecord(adam->prep_ready, f.c);
+      f.adam = adam;
+    }
+  }
   if (int e = enc_fwd_tc_run(m, theta, ids, M, Tcap, enc_ws, rep, dropout_rate, seed, d_step, f)) return e;
   if (int e = enc_scatter_plan_run(m, M, Tcap, enc_ws, bwd_ws, f)) return e;
   if (int e = loss_tc_run(m, theta, rep, a, loss_ws, loss, row_loss, d_rep, grad, f, 2)) return e;
   if (int e = enc_bwd_tc_run(m, theta, ids, M, Tcap, enc_ws, bwd_ws, d_rep, grad, dropout_rate, seed, d_step, f)) return e;
-  // every side stream is already ordered before the tail of `stream` (a: joined by the backward, b: the scatter
-  // waited for dE, c: joined twice); close the DAG explicitly so nothing depends on that reasoning
+  // close the DAG: every side stream (and the priority chain) is ordered before the tail of the caller's stream
   f.edge(f.a, st);
   f.edge(f.b, st);
   f.edge(f.c, st);
   f.edge(f.main, st);
-  ADER_CHECK_LAUNCH("train_fwd_bwd_tc");
+  ADER_CHECK_LAUNCH("train step");
+  if (adam && !f.adam)        // serial plan: the ordinary optimiser call behind the pass
+    return ader_adam_step(m, adam->theta, adam->m, adam->v, adam->grad, adam->state, &adam->a, (void*)st);
   return 0;
+}
+
+extern "C" int32_t ader_train_fwd_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                                         const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                                         float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                                         uint64_t seed, const int32_t* d_step, int32_t serial, void* stream) {
+  return run_step(m, theta, ids, M, Tcap, a, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss, d_rep, grad, dropout_rate, seed,
+                  d_step, serial, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int32_t ader_train_step_tc(const AderModel* m, float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                                      const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                                      float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                                      uint64_t seed, const int32_t* d_step, float* adam_m, float* adam_v, int32_t* state,
+                                      const AderAdamArgs* opt, int32_t serial, void* stream) {
+  ADER_CHECK_ARG(adam_m && adam_v && state && opt, "train_step_tc: NULL optimiser pointer");
+  ADER_CHECK_ARG(opt->V >= 1 && opt->V < m->v_tab, "train_step_tc: max_item %d outside table", opt->V);
+  ADER_CHECK_ARG(opt->ewc_lambda == 0.f || (opt->fisher && opt->theta_star), "train_step_tc: EWC needs fisher and theta_star");
+  AdamPlan plan;
+  plan.theta = theta; plan.m = adam_m; plan.v = adam_v; plan.grad = grad; plan.state = state; plan.a = *opt; plan.prep_ready = nullptr;
+  return run_step(m, theta, ids, M, Tcap, a, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss, d_rep, grad, dropout_rate, seed,
+                  d_step, serial, (cudaStream_t)stream, &plan);
 }

@@ -120,7 +120,7 @@ class GraphStep:
         else:
             ops.gather_batch(t_ids, t_lab, self.ti, None, None, None, self.ids, self.pos, None)
 
-    def _eager(self, tcap: int, device_step: bool):
+    def _eager(self, tcap: int, device_step: bool, indexed: bool = False):
         m = self.model
         kw = {}
         if self.n_ex > 0:
@@ -130,7 +130,7 @@ class GraphStep:
                 kw = dict(exemplar_pos=self.aux[:self.n_ex])
         loss = m.train_step(self.ids, self.pos, self.max_item, self.lr, self.p, n_tokens=tcap,
                             _device_step=device_step, **kw)
-        self._row_loss[tcap] = m.last_row_loss
+        self._row_loss[(tcap, indexed)] = m.last_row_loss
         return loss
 
     def _capture_all(self):
@@ -147,33 +147,34 @@ class GraphStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = None
-        self.gather_graph = None
-        if self.sources is not None:
-            self.gather_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.gather_graph):
-                self._gather()
-            pool = self.gather_graph.pool()
+        self.graphs_idx = {}                   # index-fed form: batch gather + step in ONE graph (no gap between two replays)
         for tcap in reversed(self.tcaps):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 self._eager(tcap, True)
             pool = g.pool()
             self.graphs[tcap] = g
+            if self.sources is not None:
+                gi = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gi, pool=pool):
+                    self._gather()
+                    self._eager(tcap, True, indexed=True)
+                self.graphs_idx[tcap] = gi
         m.load_state_dict(sd)                  # the warm-up step must not count
         m.global_step = gs
         torch.cuda.synchronize()
 
     # ---- replay ---------------------------------------------------------------------------------------
-    def _replay(self, n_tokens: Optional[int]):
+    def _replay(self, n_tokens: Optional[int], indexed: bool = False):
         cap = self.tcaps[-1]
         if n_tokens is not None:
             for t in self.tcaps:
                 if t >= n_tokens:
                     cap = t
                     break
-        self.graphs[cap].replay()
+        (self.graphs_idx if indexed else self.graphs)[cap].replay()
         self.model.global_step += 1
-        self.model.last_row_loss = self._row_loss[cap]
+        self.model.last_row_loss = self._row_loss[(cap, indexed)]
         return self.model._loss
 
     @staticmethod
@@ -203,5 +204,4 @@ class GraphStep:
         self._put(self._ring_ti, self.ti, ti)
         if self.n_ex > 0 and ei is not None:
             self._put(self._ring_ei, self.ei[:self.n_ex], ei)
-        self.gather_graph.replay()
-        return self._replay(n_tokens)
+        return self._replay(n_tokens, indexed=True)

@@ -141,7 +141,7 @@ class Ader:
     def loss_and_grad(self, seq, pos, max_item: int, exemplar_logits=None, exemplar_pos=None,
                       teacher_rows=None, dropout_rate: float = 0.0, n_tokens: Optional[int] = None,
                       mode: Optional[int] = None, lambda_: Optional[float] = None, _events=None,
-                      global_counts=None, _device_step: bool = False) -> torch.Tensor:
+                      global_counts=None, _device_step: bool = False, _opt=None) -> torch.Tensor:
         """Forward + backward of the current loss; fills ``self.grad`` (flat).  Returns the device
         scalar loss.  ``exemplar_logits`` is either a host array / list [M_e, V_prev] (reference feed,
         ADER.py:20) or a device tensor [E, V_prev] indexed by ``teacher_rows`` [M_e]."""
@@ -196,8 +196,18 @@ class Ader:
             lws = self._loss_ws.get(ops.loss_tc_ws_bytes(self.ms, a))
             rep = torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
             d_rep = torch.empty_like(rep)
-            ops.train_fwd_bwd_tc(self.ms, self.theta, ids, tcap, a, ews, bws, lws, rep, self._loss, row_loss, d_rep,
-                                 self.grad, dropout_rate, seed, d_step, serial=(self.step_impl == "serial"))
+            self._opt_applied = False
+            if _opt is not None and self.grad_sync is None:
+                # one GPU: the optimiser joins the DAG (table rows right behind the scatter, dense parameters behind
+                # their partial reduction)
+                V_, lr_, lam_, fis_, star_ = _opt
+                ops.train_step_tc(self.ms, self.theta, ids, tcap, a, ews, bws, lws, rep, self._loss, row_loss, d_rep,
+                                  self.grad, self.adam_m, self.adam_v, self.adam_state, V_, lr_, dropout_rate, seed, d_step,
+                                  lam_, fis_, star_, serial=(self.step_impl == "serial"))
+                self._opt_applied = True
+            else:
+                ops.train_fwd_bwd_tc(self.ms, self.theta, ids, tcap, a, ews, bws, lws, rep, self._loss, row_loss, d_rep,
+                                     self.grad, dropout_rate, seed, d_step, serial=(self.step_impl == "serial"))
             if self.grad_sync is not None:
                 self.grad_sync()
             self.last_row_loss = row_loss
@@ -238,10 +248,18 @@ class Ader:
         """sess.run(model.train_op, feed) (main.py:233-256).  Returns the device scalar loss."""
         lr = self.args.lr if lr is None else lr
         p = self.args.dropout_rate if dropout_rate is None else dropout_rate
+        self._opt_applied = False
         loss = self.loss_and_grad(seq, pos, max_item, exemplar_logits, exemplar_pos, teacher_rows, p, n_tokens,
-                                  _device_step=_device_step)
-        self.apply_gradients(max_item, lr)
+                                  _device_step=_device_step, _opt=self._opt_args(max_item, lr))
+        if self._opt_applied:
+            self.global_step += 1
+        else:
+            self.apply_gradients(max_item, lr)
         return loss
+
+    def _opt_args(self, max_item: int, lr: float):
+        """(V, lr, ewc_lambda, fisher, theta_star) of the update ``apply_gradients`` would run."""
+        return (max_item, lr, 0.0, None, None)
 
     def graph_step(self, n_train: int, n_ex: int, max_item: int, lr: Optional[float] = None,
                    dropout_rate: Optional[float] = None, teacher=None, sources=None, tcaps=None):
@@ -343,6 +361,11 @@ class Ewc(Ader):
         self.ewc_lambda = float(lambda_)
         self._graph_fisher = self.fisher.clone()
         self._graph_star = self.theta_star.clone()
+
+    def _opt_args(self, max_item: int, lr: float):
+        if self.ewc_lambda != 0.0:
+            return (max_item, lr, self.ewc_lambda, self._graph_fisher, self._graph_star)
+        return (max_item, lr, 0.0, None, None)
 
     def apply_gradients(self, max_item: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None):
         if self.ewc_lambda != 0.0:

@@ -149,6 +149,20 @@ def train_fwd_bwd_tc(ms: AderModel, theta, ids, Tcap: int, a: AderLossArgs, enc_
                                             _stream()), "train_fwd_bwd_tc")
 
 
+def train_step_tc(ms: AderModel, theta, ids, Tcap: int, a: AderLossArgs, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss,
+                  d_rep, grad, adam_m, adam_v, state, V: int, lr: float, dropout_rate: float = 0.0, seed: int = 0, d_step=None,
+                  ewc_lambda: float = 0.0, fisher=None, theta_star=None, beta1=0.9, beta2=0.999, eps=1e-8, serial: bool = False):
+    """train_fwd_bwd_tc + adam_step as one DAG (single GPU; bit-identical to the two calls)."""
+    _require_cuda(theta, ids, enc_ws, bwd_ws, loss_ws, rep, loss, row_loss, d_rep, grad, adam_m, adam_v, state, fisher, theta_star)
+    opt = AderAdamArgs(lr, beta1, beta2, eps, V, ewc_lambda,
+                       fisher.data_ptr() if fisher is not None else None,
+                       theta_star.data_ptr() if theta_star is not None else None)
+    check(_lib.load().ader_train_step_tc(C.byref(ms), _ptr(theta), _ptr(ids), ids.shape[0], Tcap, C.byref(a), _ptr(enc_ws),
+                                         _ptr(bwd_ws), _ptr(loss_ws), _ptr(rep), _ptr(loss), _ptr(row_loss), _ptr(d_rep),
+                                         _ptr(grad), float(dropout_rate), C.c_uint64(seed), _ptr(d_step), _ptr(adam_m),
+                                         _ptr(adam_v), _ptr(state), C.byref(opt), int(bool(serial)), _stream()), "train_step_tc")
+
+
 def debug_loss_tc_kernels(ms: AderModel, theta, a: AderLossArgs, ws, grad):
     """Measurement hook: only k_tc_logits<FWD/DREP/DE> on a workspace prepared by loss_fwd_bwd_tc (same arguments)."""
     _require_cuda(theta, ws, grad)

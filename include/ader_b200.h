@@ -168,6 +168,17 @@ typedef struct AderAdamArgs {
 int32_t ader_adam_step(const AderModel* m, float* theta, float* adam_m, float* adam_v,
                        const float* grad, int32_t* state, const AderAdamArgs* a, void* stream);
 
+/* The same pass with the optimiser folded in (one GPU: nothing sits between backward and Adam): identical to
+ * ader_train_fwd_bwd_tc followed by ader_adam_step(theta, adam_m, adam_v, grad, state, opt), bit for bit, but the
+ * step size is prepared at the start of the DAG, the item-table rows are updated as soon as the scatter has added
+ * into them and the dense parameters as soon as their split partials are reduced (the weight-gradient tail and the
+ * table update overlap).  state[0] is incremented by the dense update, after the last reader of the dropout counter. */
+int32_t ader_train_step_tc(const AderModel* m, float* theta, const int32_t* ids, int32_t M, int32_t Tcap,
+                           const AderLossArgs* a, void* enc_ws, void* bwd_ws, void* loss_ws, float* rep,
+                           float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
+                           uint64_t seed, const int32_t* d_step, float* adam_m, float* adam_v, int32_t* state,
+                           const AderAdamArgs* opt, int32_t serial, void* stream);
+
 /* ---- evaluation: ADER.py:99-103, util.py:309-339 (subsystem 5) -------------------------- */
 size_t  ader_eval_ws_bytes(const AderModel* m, int32_t M, int32_t V);
 /* rep [M,d], gt [M] (1..V) -> rank [M] (0-based rank of gt, ties -> lower index first),

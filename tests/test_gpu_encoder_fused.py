@@ -233,3 +233,44 @@ def test_train_dag_entry_is_bit_identical_to_the_three_groups(blocks, mode):
             for k, (x, y) in enumerate(zip(got["groups"], got[impl])):
                 assert torch.equal(x, y), "%s differs from the three-group sequence (output %d, batch %d)" % (impl, k, it)
     assert float(got["dag"][0].item()) > 0.0
+
+
+@pytest.mark.parametrize("ewc", [False, True])
+def test_fused_train_step_matches_groups_then_adam(ewc):
+    """ader_train_step_tc (optimiser inside the DAG: early step size, table rows behind the scatter, dense parameters
+    behind their partial reduction, counter bumped last) == three groups + ader_adam_step: parameters, both Adam
+    slots and the step counter bit for bit after several steps with dropout (the counter feeds the dropout stream)."""
+    from ader_b200.model import Ewc
+    from test_gpu_parity import _args
+    rng = np.random.RandomState(21)
+    B, Me, V, Vp, E = 96, 32, 700, 650, 48
+    batches = []
+    for _ in range(5):
+        ids = _ids(rng, B + Me, 50, Vp, lens=rng.randint(1, 12, B + Me))
+        batches.append((ids, rng.randint(1, V + 1, B).astype(np.int32), rng.randint(0, E, Me).astype(np.int32)))
+    out = {}
+    for impl in ("groups", "dag"):
+        if ewc:
+            m = Ewc(800, _args(loss_impl="tc", step_impl=impl), init_seed=0)
+            g = torch.Generator(device=m.device).manual_seed(5)
+            m.fisher = torch.rand(m.layout.total, device=m.device, generator=g)
+            m.theta_star = m.theta.clone() + 0.01
+            m.update_loss(50.0)
+        else:
+            m, _, _ = _model(800, loss_impl="tc", step_impl=impl)
+            m.update_loss(0.9)
+        teacher = torch.randn(E, Vp, device=m.device, generator=torch.Generator(device=m.device).manual_seed(2))
+        losses = []
+        for ids, pos, rows in batches:
+            ntok = int((ids != 0).sum())
+            if ewc:
+                loss = m.train_step(ids[:B], pos, V, 1e-3, 0.0, n_tokens=int((ids[:B] != 0).sum()))
+            else:
+                loss = m.train_step(ids, pos, V, 1e-3, 0.3, exemplar_logits=teacher, teacher_rows=rows, n_tokens=ntok)
+            losses.append(float(loss.item()))
+        out[impl] = (losses, m.theta.clone(), m.adam_m.clone(), m.adam_v.clone(), m.adam_state.clone(), m.global_step)
+    assert out["groups"][0] == out["dag"][0]
+    for k in range(1, 5):
+        assert torch.equal(out["groups"][k], out["dag"][k]), "state tensor %d differs" % k
+    assert out["groups"][5] == out["dag"][5] == len(batches)
+    assert int(out["dag"][4][0].item()) == len(batches)
