@@ -1393,8 +1393,8 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   fused_attrs();
 
   // final LayerNorm: data gradient on the chain, parameter gradient beside it
-  f.edge(st, f.a);
-  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, f.a>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+  f.edge(st, f.c);
+  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, f.c>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
   // directly behind the d_rep reduction on f.main in the fused step (f.pdl is only set there)
   launch_chain(k_lnf_bwd, dim3(ln_grid), dim3(256), 0, st, f.pdl, d_rep, (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf,
@@ -1420,6 +1420,18 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     fa.gH = gH; fa.gZ = gZ; fa.gY = gY; fa.D = g.Dv; fa.dT = dT; fa.d = d;
     fa.drop_p = p; fa.seed = seed; fa.d_step = d_step; fa.site2 = 3u + 3u * b;
     launch_chain(fz::k_ffn_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_BWD_SMEM, st, f.pdl && !joined, fa);
+    // weight / bias / LayerNorm-parameter gradients (TF32 tensor cores, fp32 accumulate, split partials): launched in three
+    // pieces on f.a, each as soon as its gradients exist, so most of the work is done while the chain is still running
+    const float* gOut = (p > 0.f) ? gO : gX;
+    {
+      fz::WgradArgs wa;
+      wa.p[0] = {H, gOut, nullptr, nullptr, part(bo + l.w2), part(bo + l.b2)};
+      wa.p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
+      wa.p[2] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
+      wa.n_gemm = 2; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
+      f.edge(st, f.a);
+      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+    }
 
     fz::AttnBwdArgs ab;
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
@@ -1427,6 +1439,15 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.d_step = d_step; ab.site = 1u + 3u * b;
     if (m->num_heads == 1) launch_chain(fz::k_attn_bwd_s1, dim3(cdiv(Tcap, fz::ATT_TOK)), dim3(256), (size_t)fz::att_bwd_smem(L, d), st, f.pdl, ab);
     else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
+    {
+      fz::WgradArgs wa;
+      wa.p[0] = {Q1, gQ, nullptr, nullptr, part(bo + l.wq), part(bo + l.bq)};
+      wa.p[1] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
+      wa.p[2] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
+      wa.n_gemm = 3; wa.n_ln = 0; wa.dT = dT; wa.d = d; wa.split_stride = PS;
+      f.edge(st, f.a);
+      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+    }
 
     fz::QkvBwdArgs qb;
     qb.gQ = gQ; qb.gK = gK; qb.gV = gV; qb.gY = gY; qb.X = X; qb.mean1 = w.mean1[b]; qb.rstd1 = w.rstd1[b];
@@ -1436,19 +1457,13 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     launch_chain(fz::k_qkv_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_BWD_SMEM, st, f.pdl, qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
 
-    // weight / bias / LayerNorm-parameter gradients of the block: one launch (TF32 tensor cores, fp32 accumulate)
-    const float* gOut = (p > 0.f) ? gO : gX;
-    fz::WgradArgs wa;
-    wa.p[0] = {H, gOut, nullptr, nullptr, part(bo + l.w2), part(bo + l.b2)};
-    wa.p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
-    wa.p[2] = {Q1, gQ, nullptr, nullptr, part(bo + l.wq), part(bo + l.bq)};
-    wa.p[3] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
-    wa.p[4] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
-    wa.p[5] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
-    wa.p[6] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
-    wa.n_gemm = 5; wa.n_ln = 2; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-    f.edge(st, f.a);
-    fz::k_wgrad<<<dim3(SPLITS, 7), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+    {
+      fz::WgradArgs wa;
+      wa.p[0] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
+      wa.n_gemm = 0; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
+      f.edge(st, f.a);
+      fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+    }
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
     if (f.parallel()) { wg_done[b] = f.take(); cudaEventRecord(wg_done[b], f.a); }
   }

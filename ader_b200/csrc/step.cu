@@ -15,7 +15,7 @@ namespace ader {
 struct StreamPool {
   cudaStream_t s[3];     // side streams, lowest priority
   cudaStream_t hi;       // critical chain, highest priority: its pending CTAs are placed before those of the side streams
-  cudaEvent_t ev[64];
+  cudaEvent_t ev[128];
   bool ok;
   StreamPool() : ok(false) {}
   int init() {
@@ -25,7 +25,7 @@ struct StreamPool {
     for (int i = 0; i < 3; ++i)
       if (cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, least) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
     if (cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, greatest) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
-    for (int i = 0; i < 64; ++i)
+    for (int i = 0; i < 128; ++i)
       if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create an event");
     ok = true;
     return 0;
@@ -59,7 +59,7 @@ static int run_step(const AderModel* m, const float* theta, const int32_t* ids, 
     StreamPool& p = g_pool[dev];
     if (int e = p.init()) return e;
     f.a = p.s[0]; f.b = p.s[1]; f.c = p.s[2];
-    f.ev = p.ev; f.n_ev = 64; f.next_ev = 0;
+    f.ev = p.ev; f.n_ev = 128; f.next_ev = 0;
     static const int prio = env_flag("ADER_B200_DAG_PRIO", 1);
     if (prio) { f.main = p.hi; f.edge(st, f.main); }
   }
