@@ -96,6 +96,7 @@ int adam_dense_part(const AderModel* m, const AdamPlan& p, cudaStream_t st);   /
 struct Fork {
   const AdamPlan* adam;
   cudaStream_t main, a, b, c;
+  cudaStream_t wg[3];                      // the three weight-gradient pieces of a block run beside each other (wg[0] == a)
   cudaEvent_t* ev; int n_ev, next_ev;      // event pool (timing disabled); reuse is safe: every wait is issued right after its record
   cudaEvent_t table_ready;                 // recorded on `b` after the dE kernel: the scatter into the item table waits for it
   bool has_table_ready;
@@ -105,7 +106,7 @@ struct Fork {
   bool plan_done;
   bool pdl;                                // launch the kernel-to-kernel chain links of `main` as programmatic dependent launches
   static Fork serial(cudaStream_t st) {
-    Fork f; f.main = f.a = f.b = f.c = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.pdl = false; f.adam = nullptr;
+    Fork f; f.main = f.a = f.b = f.c = st; f.wg[0] = f.wg[1] = f.wg[2] = st; f.ev = nullptr; f.n_ev = f.next_ev = 0; f.pdl = false; f.adam = nullptr;
     f.table_ready = f.tok_ready = f.plan_ready = nullptr; f.has_table_ready = f.has_tok_ready = f.plan_done = false;
     return f;
   }

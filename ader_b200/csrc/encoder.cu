@@ -1401,7 +1401,7 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
                theta + l.off_lnf + d, (const int*)w.tok_row, (const int*)w.row_off, chain[0], dT, d);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
 
-  cudaEvent_t wg_done[8];                   // weight-gradient kernel of block b finished (f.a), parallel plans only
+  cudaEvent_t wg_done[8][3];                // weight-gradient pieces of block b finished (f.wg[k]), parallel plans only
   for (int b = m->num_blocks - 1; b >= 0; --b) {
     const long long bo = l.block(b);
     const float* P = theta + bo;
@@ -1413,7 +1413,7 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     float* gX = chain[ci % 3]; float* gXin = chain[(ci + 1) % 3]; ++ci;
     // this block rewrites the buffer set (and chain buffer) last read by the weight-gradient kernel of block b + 2
     const bool joined = f.parallel() && b + 2 < m->num_blocks;
-    if (joined) cudaStreamWaitEvent(st, wg_done[b + 2], 0);
+    if (joined) for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(st, wg_done[b + 2][k], 0);
     fz::FfnBwdArgs fa;
     fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
     fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
@@ -1429,8 +1429,8 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
       wa.p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
       wa.p[2] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
       wa.n_gemm = 2; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.a);
-      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+      f.edge(st, f.wg[0]);
+      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa);
     }
 
     fz::AttnBwdArgs ab;
@@ -1445,8 +1445,8 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
       wa.p[1] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
       wa.p[2] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
       wa.n_gemm = 3; wa.n_ln = 0; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.a);
-      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+      f.edge(st, f.wg[1]);
+      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[1]>>>(wa);
     }
 
     fz::QkvBwdArgs qb;
@@ -1461,11 +1461,12 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
       fz::WgradArgs wa;
       wa.p[0] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
       wa.n_gemm = 0; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.a);
-      fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.a>>>(wa);
+      f.edge(st, f.wg[2]);
+      fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.wg[2]>>>(wa);
     }
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
-    if (f.parallel()) { wg_done[b] = f.take(); cudaEventRecord(wg_done[b], f.a); }
+    if (f.parallel())
+      for (int k = 0; k < 3; ++k) { wg_done[b][k] = f.take(); cudaEventRecord(wg_done[b][k], f.wg[k]); }
   }
   const float* gX0 = chain[ci % 3];          // gradient w.r.t. the (dropout-masked) embedding output
 
@@ -1473,6 +1474,8 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   f.edge(st, f.c);
   k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
   f.edge(f.c, f.a);
+  f.edge(f.wg[1], f.a);
+  f.edge(f.wg[2], f.a);
   k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
   if (f.adam) {                              // fused step: the dense parameters are final here
     cudaStreamWaitEvent(f.a, f.adam->prep_ready, 0);

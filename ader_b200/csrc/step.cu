@@ -13,7 +13,7 @@
 namespace ader {
 
 struct StreamPool {
-  cudaStream_t s[3];     // side streams, lowest priority
+  cudaStream_t s[5];     // side streams, lowest priority (3 general + 2 more for weight-gradient pieces)
   cudaStream_t hi;       // critical chain, highest priority: its pending CTAs are placed before those of the side streams
   cudaEvent_t ev[128];
   bool ok;
@@ -22,7 +22,7 @@ struct StreamPool {
     if (ok) return 0;
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 5; ++i)
       if (cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, least) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
     if (cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, greatest) != cudaSuccess) return fail(-3, "train_fwd_bwd_tc: cannot create a stream");
     for (int i = 0; i < 128; ++i)
@@ -59,8 +59,9 @@ static int run_step(const AderModel* m, const float* theta, const int32_t* ids, 
     StreamPool& p = g_pool[dev];
     if (int e = p.init()) return e;
     f.a = p.s[0]; f.b = p.s[1]; f.c = p.s[2];
+    f.wg[0] = f.a; f.wg[1] = p.s[3]; f.wg[2] = p.s[4];
     f.ev = p.ev; f.n_ev = 128; f.next_ev = 0;
-    static const int prio = env_flag("ADER_B200_DAG_PRIO", 1);
+    static const int prio = env_flag("ADER_B200_DAG_PRIO", 0);
     if (prio) { f.main = p.hi; f.edge(st, f.main); }
   }
   static const int pdl = env_flag("ADER_B200_PDL", 1);
@@ -85,6 +86,8 @@ static int run_step(const AderModel* m, const float* theta, const int32_t* ids, 
   f.edge(f.a, st);
   f.edge(f.b, st);
   f.edge(f.c, st);
+  f.edge(f.wg[1], st);
+  f.edge(f.wg[2], st);
   f.edge(f.main, st);
   ADER_CHECK_LAUNCH("train step");
   if (adam && !f.adam)        // serial plan: the ordinary optimiser call behind the pass
