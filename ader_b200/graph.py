@@ -64,6 +64,17 @@ class _PinnedRing:
         self.evs[k] = ev
 
 
+class PendingLoss:
+    """Loss of a replayed step on its way to the host (pinned 4-byte D2H copy issued right behind the step)."""
+
+    def __init__(self, buf: torch.Tensor, ev: torch.cuda.Event):
+        self.buf, self.ev = buf, ev
+
+    def result(self) -> float:
+        self.ev.synchronize()
+        return float(self.buf[0])
+
+
 class GraphStep:
     """Captured ``train_step`` for a fixed batch geometry (n_train + n_ex rows) of one period.
 
@@ -99,6 +110,8 @@ class GraphStep:
             self._ring_ei = _PinnedRing((max(self.n_ex, 1),))
         self._ring_batch = _PinnedRing((self.batch.numel(),))
         self._ring_ids = _PinnedRing((M, L))
+        self._loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self._loss_i = 0
         self._ring_pos = _PinnedRing((self.n_train,))
         self._ring_aux = _PinnedRing((max(self.n_ex, 1),))
         full = M * L
@@ -196,6 +209,17 @@ class GraphStep:
         if self.n_ex > 0 and aux is not None:
             self._put(self._ring_aux, self.aux[:self.n_ex], aux)
         return self._replay(n_tokens)
+
+    def fetch_loss(self) -> PendingLoss:
+        """Queue the device->host read of the step just replayed; ``.result()`` blocks until it has landed.  Lets a host
+        loop that wants every step's loss (main.py:233-256 returns it from sess.run) keep one step in flight: feed step
+        i+1, then read the loss of step i."""
+        k = self._loss_i
+        self._loss_i = (k + 1) % len(self._loss_host)
+        self._loss_host[k].copy_(self.model._loss.view(-1)[:1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return PendingLoss(self._loss_host[k], ev)
 
     def run_indices(self, ti, ei=None, n_tokens: Optional[int] = None):
         """Row indices into the ``sources`` matrices (host arrays or device tensors)."""

@@ -66,6 +66,7 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     p.add_argument("--loss_impl", default="tc", choices=["tc", "exact"], type=str)      # logits+CE+KD: tcgen05 bf16 / fp32
     p.add_argument("--encoder_impl", default=None, choices=["tc", "exact"], type=str)  # training encoder (default follows loss_impl)
     p.add_argument("--infer_encoder_impl", default="exact", choices=["tc", "exact"], type=str)  # eval / herding encoder
+    p.add_argument("--step_impl", default=None, choices=["dag", "serial", "groups"], type=str)   # how a tc train step is issued (model.py)
     p.add_argument("--graph", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))  # CUDA-graph train step
     return p
 

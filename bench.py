@@ -278,8 +278,20 @@ def gpu_arm(args):
     barrier()
     w0 = time.time()
     e0.record()
-    for i in range(W, W + K):
-        last_loss = float(e2e_step(i).item())
+    if gs is not None:
+        # every step: host batch -> pinned staging -> ONE H2D copy -> graph replay -> pinned D2H of its loss; the host
+        # reads the loss of step i after it has fed step i+1 (one step in flight), all K losses inside the timed region
+        pend = None
+        for i in range(W, W + K):
+            e2e_step(i)
+            nxt = gs.fetch_loss()
+            if pend is not None:
+                last_loss = pend.result()
+            pend = nxt
+        last_loss = pend.result()
+    else:
+        for i in range(W, W + K):
+            last_loss = float(e2e_step(i).item())
     e1.record()
     barrier()
     windows.append((w0, time.time()))
@@ -408,7 +420,8 @@ def gpu_arm(args):
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (logits+CE+KD on tcgen05), f32 elsewhere", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / K, "last_loss": last_loss},
+                        "ms_per_step": ms_e2e / K, "last_loss": last_loss,
+                        "loss_read": "sync .item() per step" if gs is None else "pinned D2H per step, read one step behind"},
                 "gpu_launches": (launches_per_step or 0) * K,
                 "gpu_launches_per_step": launches_per_step,
                 "clocks": clock_info,

@@ -188,6 +188,8 @@ def test_graph_step_replays_match_eager_steps():
                 loss = gs.run_indices(ti, ei, ntok)
             else:
                 loss = gs.run_rows(ids, lab[ti], ei, ntok)
+                pending = gs.fetch_loss()                 # async pinned read of the same scalar
+                assert pending.result() == float(loss.item())
             losses.append(float(loss.item()))
         assert m.global_step == len(steps) and int(m.adam_state[0].item()) == len(steps)
         out[mode] = (losses, m.theta.clone())
