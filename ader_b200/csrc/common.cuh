@@ -84,6 +84,16 @@ static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 b
 // every edge is a no-op and the launches are issued in the historical serial order, so the single-stream
 // entry points run the very same code.  Under stream capture the side streams join the capture through
 // the event edges and become parallel branches of the CUDA graph.
+// one element of tf.train.AdamOptimizer (ADER.py:96; epsilon outside the bias correction) + EWC penalty gradient
+// (EWC.py:115-124); the single definition both optimiser kernels evaluate
+__device__ __forceinline__ void adam_update_elem(float g, float& th, float& m, float& v, float lr_t, float beta1, float beta2,
+                                                 float eps, float ewc_lambda, float fisher, float theta_star) {
+  if (ewc_lambda != 0.f) g += ewc_lambda * fisher * (th - theta_star);
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  th -= lr_t * m / (sqrtf(v) + eps);
+}
+
 // optimiser step folded into the fused training entry (single GPU: no gradient all-reduce between backward and Adam)
 struct AdamPlan {
   float *theta, *m, *v; const float* grad; int32_t* state; AderAdamArgs a;
@@ -91,7 +101,6 @@ struct AdamPlan {
 };
 int adam_prep_early(const AdamPlan& p, cudaStream_t st);                       // state[1] = lr_t(state[0] + 1); no increment
 int adam_table_part(const AderModel* m, const AdamPlan& p, cudaStream_t st);   // item-table rows 1..V
-int adam_dense_part(const AderModel* m, const AdamPlan& p, cudaStream_t st);   // everything after the table; bumps state[0]
 
 struct Fork {
   const AdamPlan* adam;

@@ -77,7 +77,8 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
 // ------------------------------------------------------------------------------------------
 // packing
 // ------------------------------------------------------------------------------------------
-__global__ void k_row_len(const int* __restrict__ ids, int M, int L, int* __restrict__ row_len) {
+__global__ void k_row_len(const int* __restrict__ ids, int M, int L, int* __restrict__ row_len, int* __restrict__ flags) {
+  if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;     // workspace flags (a memset node costs ~10 us in a graph)
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= M) return;
   int c = 0;
@@ -576,6 +577,23 @@ __global__ void k_apply_drop(const float* in, float* out, const int* __restrict_
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)(*dT) * d) return;
   out[e] = in[e] * drop_scale(seed, site, (uint64_t)e, p);
+}
+
+// fused-step form of k_reduce_partials over the whole dense range: the reduced gradient is stored AND the TF1-Adam
+// update of that element (optim.cu: adam_update_elem, the very expression k_adam evaluates) is applied in place;
+// thread 0 bumps the step counter (every reader of it has finished by now)
+__global__ void k_reduce_partials_adam(const float* __restrict__ partial, long long stride, int splits, long long n,
+                                       float* __restrict__ gout, float* __restrict__ theta, float* __restrict__ am,
+                                       float* __restrict__ av, int* __restrict__ state, float beta1, float beta2, float eps,
+                                       float ewc_lambda, const float* __restrict__ fisher, const float* __restrict__ theta_star) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(long long)k * stride + i];
+  gout[i] = s;
+  const float lr_t = __int_as_float(state[1]);
+  adam_update_elem(s, theta[i], am[i], av[i], lr_t, beta1, beta2, eps, ewc_lambda, fisher ? fisher[i] : 0.f, theta_star ? theta_star[i] : 0.f);
+  if (i == 0) state[0] += 1;
 }
 
 // grad_dense[i] = sum_s partial[s][i] for i in [lo, hi)
@@ -1117,8 +1135,7 @@ extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, cons
   EncWs w = carve_enc(m, M, Tcap, (char*)ws);
   const int* dT = w.row_off + M;
 
-  cudaMemsetAsync(w.flags, 0, sizeof(int) * 4, st);
-  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
+  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len, w.flags);
   k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
   k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
   k_embed<<<cdiv((long long)Tcap * d, 256), 256, 0, st>>>(theta + l.off_table, theta + l.off_pos, w.tok_row, w.tok_id,
@@ -1300,8 +1317,7 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   // weight shadows depend on theta only: off the packing chain (joined before the first tile kernel)
   f.edge(st, f.a);
   fz::k_pack_weights<<<dim3(m->num_blocks * 5, fz::KP / fz::PACK_BAND), 256, 0, f.a>>>(theta, l, (fz::op_t*)w.wshadow);
-  cudaMemsetAsync(w.flags, 0, sizeof(int) * 4, st);
-  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len);
+  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len, w.flags);
   k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
   k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
@@ -1476,10 +1492,15 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   f.edge(f.c, f.a);
   f.edge(f.wg[1], f.a);
   f.edge(f.wg[2], f.a);
-  k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
-  if (f.adam) {                              // fused step: the dense parameters are final here
-    cudaStreamWaitEvent(f.a, f.adam->prep_ready, 0);
-    if (int e = adam_dense_part(m, *f.adam, f.a)) return e;
+  if (f.adam) {                              // fused step: reduce the partials and update the dense parameters in one launch
+    const AdamPlan& ap = *f.adam;
+    cudaStreamWaitEvent(f.a, ap.prep_ready, 0);
+    k_reduce_partials_adam<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, PS, grad + l.off_pos, ap.theta + l.off_pos,
+                                                           ap.m + l.off_pos, ap.v + l.off_pos, ap.state, ap.a.beta1, ap.a.beta2, ap.a.eps,
+                                                           ap.a.ewc_lambda, ap.a.fisher ? ap.a.fisher + l.off_pos : nullptr,
+                                                           ap.a.theta_star ? ap.a.theta_star + l.off_pos : nullptr);
+  } else {
+    k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
   }
   // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
   if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);

@@ -14,7 +14,7 @@ __global__ void k_adam_prep(int* __restrict__ state, float lr, float beta1, floa
 }
 
 // early form for the fused step: the step size of step t + 1 without touching the counter (the dropout streams of the
-// running step still read state[0]); the dense part of the update bumps the counter when it is done
+// running step still read state[0]); the dense update (encoder.cu: k_reduce_partials_adam) bumps the counter when it is done
 __global__ void k_adam_prep_early(int* __restrict__ state, float lr, float beta1, float beta2) {
   const int t = state[0] + 1;
   double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
                                               const float* __restrict__ grad, const int* __restrict__ state,
                                               long long n_table, long long table_lo, long long dense_lo, long long n_total,
                                               float beta1, float beta2, float eps, float ewc_lambda,
-                                              const float* __restrict__ fisher, const float* __restrict__ theta_star, int bump) {
+                                              const float* __restrict__ fisher, const float* __restrict__ theta_star) {
   const float lr_t = __int_as_float(state[1]);
   // two elements per thread (both ranges start on even offsets because d is even)
   long long i2 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -35,20 +35,16 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ theta, float* 
   float2 th = *reinterpret_cast<const float2*>(theta + e);
   float2 m = *reinterpret_cast<const float2*>(am + e);
   float2 v = *reinterpret_cast<const float2*>(av + e);
+  float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
   if (ewc_lambda != 0.f) {
-    float2 f = *reinterpret_cast<const float2*>(fisher + e);
-    float2 ts = *reinterpret_cast<const float2*>(theta_star + e);
-    g.x += ewc_lambda * f.x * (th.x - ts.x);
-    g.y += ewc_lambda * f.y * (th.y - ts.y);
+    f = *reinterpret_cast<const float2*>(fisher + e);
+    ts = *reinterpret_cast<const float2*>(theta_star + e);
   }
-  m.x = beta1 * m.x + (1.f - beta1) * g.x;  m.y = beta1 * m.y + (1.f - beta1) * g.y;
-  v.x = beta2 * v.x + (1.f - beta2) * g.x * g.x;  v.y = beta2 * v.y + (1.f - beta2) * g.y * g.y;
-  th.x -= lr_t * m.x / (sqrtf(v.x) + eps);
-  th.y -= lr_t * m.y / (sqrtf(v.y) + eps);
+  adam_update_elem(g.x, th.x, m.x, v.x, lr_t, beta1, beta2, eps, ewc_lambda, f.x, ts.x);
+  adam_update_elem(g.y, th.y, m.y, v.y, lr_t, beta1, beta2, eps, ewc_lambda, f.y, ts.y);
   *reinterpret_cast<float2*>(theta + e) = th;
   *reinterpret_cast<float2*>(am + e) = m;
   *reinterpret_cast<float2*>(av + e) = v;
-  if (bump && i2 == 0) const_cast<int*>(state)[0] += 1;      // fused step: the counter moves once every reader of it is done
 }
 
 __global__ void __launch_bounds__(256) k_fisher_acc(const float* __restrict__ grad, double* __restrict__ acc,
@@ -88,7 +84,7 @@ extern "C" int32_t ader_adam_step(const AderModel* m, float* theta, float* adam_
   k_adam_prep<<<1, 1, 0, st>>>(state, a->lr, a->beta1, a->beta2);
   k_adam<<<cdiv(n_total / 2 + 1, 256), 256, 0, st>>>(theta, adam_m, adam_v, grad, state, n_table, (long long)m->d,
                                                      l.off_pos, n_total, a->beta1, a->beta2, a->eps, a->ewc_lambda,
-                                                     a->fisher, a->theta_star, 0);
+                                                     a->fisher, a->theta_star);
   ADER_CHECK_LAUNCH("adam");
   return 0;
 }
@@ -102,19 +98,10 @@ int ader::adam_table_part(const AderModel* m, const AdamPlan& p, cudaStream_t st
   const Layout l = make_layout(m);
   const long long n_table = (long long)p.a.V * m->d;
   k_adam<<<cdiv(n_table / 2 + 1, 256), 256, 0, st>>>(p.theta, p.m, p.v, p.grad, p.state, n_table, (long long)m->d, l.off_pos, n_table,
-                                                     p.a.beta1, p.a.beta2, p.a.eps, p.a.ewc_lambda, p.a.fisher, p.a.theta_star, 0);
+                                                     p.a.beta1, p.a.beta2, p.a.eps, p.a.ewc_lambda, p.a.fisher, p.a.theta_star);
   ADER_CHECK_LAUNCH("adam table");
   return 0;
 }
-int ader::adam_dense_part(const AderModel* m, const AdamPlan& p, cudaStream_t st) {
-  const Layout l = make_layout(m);
-  const long long n_dense = l.dense_count();
-  k_adam<<<cdiv(n_dense / 2 + 1, 256), 256, 0, st>>>(p.theta, p.m, p.v, p.grad, p.state, 0, (long long)m->d, l.off_pos, n_dense,
-                                                     p.a.beta1, p.a.beta2, p.a.eps, p.a.ewc_lambda, p.a.fisher, p.a.theta_star, 1);
-  ADER_CHECK_LAUNCH("adam dense");
-  return 0;
-}
-
 extern "C" int32_t ader_fisher_accumulate(const AderModel* m, const float* grad, double* acc, int32_t V, void* stream) {
   if (int e = check_model(m)) return e;
   ADER_CHECK_ARG(grad && acc && V >= 1 && V < m->v_tab, "fisher_accumulate: bad argument");
