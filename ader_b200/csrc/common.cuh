@@ -88,10 +88,11 @@ static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 b
 // (EWC.py:115-124); the single definition both optimiser kernels evaluate
 __device__ __forceinline__ void adam_update_elem(float g, float& th, float& m, float& v, float lr_t, float beta1, float beta2,
                                                  float eps, float ewc_lambda, float fisher, float theta_star) {
-  if (ewc_lambda != 0.f) g += ewc_lambda * fisher * (th - theta_star);
-  m = beta1 * m + (1.f - beta1) * g;
-  v = beta2 * v + (1.f - beta2) * g * g;
-  th -= lr_t * m / (sqrtf(v) + eps);
+  // explicit rounding intrinsics: the compiler may not re-associate or contract differently in the two kernels
+  if (ewc_lambda != 0.f) g = __fmaf_rn(__fmul_rn(ewc_lambda, fisher), __fsub_rn(th, theta_star), g);
+  m = __fmaf_rn(beta1, m, __fmul_rn(__fsub_rn(1.f, beta1), g));
+  v = __fmaf_rn(beta2, v, __fmul_rn(__fmul_rn(__fsub_rn(1.f, beta2), g), g));
+  th = __fsub_rn(th, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
 }
 
 // optimiser step folded into the fused training entry (single GPU: no gradient all-reduce between backward and Adam)
