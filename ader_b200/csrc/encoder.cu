@@ -642,8 +642,9 @@ __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// embedding-gradient scatter (subsystem 3): stable LSD radix sort of (item id, token) + warp
-// segmented reduction.  No float atomics; every table row is summed in token order by one warp.
+// embedding-gradient scatter (subsystem 3): stable LSD radix sort of (item id, token) (the "plan", depends on the
+// packed ids only) + windowed segmented reduction (k_scatter_apply).  Deterministic: every table row is a fixed
+// function of the sorted order; the only float reductions to memory have exactly one contributor per address.
 // ------------------------------------------------------------------------------------------
 constexpr int SORT_TILE = 2048;
 
@@ -730,129 +731,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ ke
   }
 }
 
-// warp per CH sorted positions; the warp owning a segment head sums the whole segment.
-__global__ void __launch_bounds__(256) k_seg_reduce(const int* __restrict__ keys, const int* __restrict__ vals,
-                                                    const int* __restrict__ dT, const float* __restrict__ gx,
-                                                    int d, float scale, float drop_p, uint64_t seed0,
-                                                    const int* __restrict__ d_step, float* __restrict__ gtable) {
-  const uint64_t seed = seed0 + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
-  constexpr int CH = 4;
-  const int T = *dT;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int p0 = w * CH;
-  if (p0 >= T) return;
-  for (int p = p0; p < min(T, p0 + CH); ++p) {
-    int key = keys[p];
-    if (p > 0 && keys[p - 1] == key) continue;        // not a head
-    float acc[LN_MAXE];
-#pragma unroll
-    for (int i = 0; i < LN_MAXE; ++i) acc[i] = 0.f;
-    int qe = p + 1;                                    // segment end: lanes probe 32 positions at a time
-    for (;;) {
-      int q = qe + lane;
-      unsigned diff = __ballot_sync(0xffffffffu, q >= T || keys[q] != key);
-      if (diff) { qe += __ffs(diff) - 1; break; }
-      qe += 32;
-    }
-    for (int q = p; q < qe; q += 8) {                  // 8 rows in flight, added in token order
-      float v[8][LN_MAXE];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool ok = q + u < qe;
-        long long o = ok ? (long long)vals[q + u] * d : 0;
-#pragma unroll
-        for (int i = 0; i < LN_MAXE; ++i) {
-          int c = lane + 32 * i;
-          float x = 0.f;
-          if (ok && c < d) {
-            x = gx[o + c];
-            if (drop_p > 0.f) x *= drop_scale(seed, 0u, (uint64_t)(o + c), drop_p);
-          }
-          v[u][i] = x;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int i = 0; i < LN_MAXE; ++i) acc[i] += v[u][i];
-    }
-#pragma unroll
-    for (int i = 0; i < LN_MAXE; ++i) {
-      int c = lane + 32 * i;
-      if (c < d) gtable[(long long)key * d + c] += scale * acc[i];
-    }
-  }
-}
-
-// Small-step form of the same reduction (T <= SS_MAXT tokens): no sort at all.  One warp per token; the warp of
-// the FIRST occurrence of an item id owns that table row: it scans the step's token ids (staged in shared memory,
-// 32 per ballot), collects the later occurrences in token order and sums their gradient rows in that order -- the
-// same order the stable sort + segmented reduction produces, so both forms give bit-identical rows.  Warps of
-// repeated ids find an earlier twin within a few ballots and exit.  One launch instead of seven.
-constexpr int SS_MAXT = 8192;
-constexpr int SS_LIST = 64;
-template <int NEL>   // elements per lane: 5 covers d <= 160, LN_MAXE = 8 covers d <= 256
-__global__ void __launch_bounds__(256) k_scatter_small(const int* __restrict__ tok_id, const int* __restrict__ dT,
-                                                       const float* __restrict__ gx, int d, float scale,
-                                                       float* __restrict__ gtable) {
-  extern __shared__ int ss_sm[];
-  const int T = min(*dT, SS_MAXT);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((int)blockIdx.x * 8 >= T) return;
-  int* ids = ss_sm + 8 * SS_LIST;
-  int* mem = ss_sm + warp * SS_LIST;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) ids[i] = tok_id[i];
-  __syncthreads();
-  const int t = blockIdx.x * 8 + warp;
-  if (t >= T) return;
-  const int id = ids[t];
-  for (int j0 = 0; j0 < t; j0 += 32) {                     // an earlier twin owns the row
-    const int j = j0 + lane;
-    if (__any_sync(0xffffffffu, j < t && ids[j] == id)) return;
-  }
-  float acc[NEL];
-#pragma unroll
-  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
-  constexpr int FL = (NEL <= 5) ? 16 : 8;                  // rows in flight
-  auto flush = [&](int n) {                                // acc += rows mem[0..n) in list (= token) order
-    for (int q = 0; q < n; q += FL) {
-      float v[FL][NEL];
-#pragma unroll
-      for (int u = 0; u < FL; ++u) {
-        const bool ok = q + u < n;
-        const long long o = ok ? (long long)mem[q + u] * d : 0;
-#pragma unroll
-        for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; v[u][i] = (ok && c < d) ? gx[o + c] : 0.f; }
-      }
-#pragma unroll
-      for (int u = 0; u < FL; ++u)
-#pragma unroll
-        for (int i = 0; i < NEL; ++i) acc[i] += v[u][i];
-    }
-  };
-  int cnt = 1;
-  if (lane == 0) mem[0] = t;
-  for (int j0 = t + 1; j0 < T; j0 += 32) {
-    const int j = j0 + lane;
-    const bool eq = j < T && ids[j] == id;
-    const unsigned mask = __ballot_sync(0xffffffffu, eq);
-    if (mask) {
-      if (eq) mem[cnt + __popc(mask & ((1u << lane) - 1u))] = j;
-      cnt += __popc(mask);
-      __syncwarp();
-      if (cnt > SS_LIST - 32) { flush(cnt); cnt = 0; __syncwarp(); }
-    }
-  }
-  __syncwarp();
-  flush(cnt);
-#pragma unroll
-  for (int i = 0; i < NEL; ++i) {
-    const int c = lane + 32 * i;
-    if (c < d) gtable[(long long)id * d + c] += scale * acc[i];
-  }
-}
-
-// Windowed form of the segmented reduction (all step sizes): the (item id, token) pairs are radix-sorted OFF the
+// Segmented reduction over the sorted pairs, windowed: the (item id, token) pairs are radix-sorted OFF the
 // critical path (the ids are known as soon as the batch is packed), so the part that has to wait for the gradient is
 // one launch with no serial tail.  One warp per window of SW consecutive sorted positions: its SW gradient rows are
 // fetched in one batch, runs of equal ids are summed in sorted (= token) order, and
@@ -1020,12 +899,6 @@ static int run_embedding_grads(const AderModel* m, const Layout& l, const EncWs&
 }
 
 // ---- item-table scatter (modules.py:127-130) ------------------------------------------------------------------
-// ADER_B200_SCATTER=legacy selects the previous forms (first-occurrence ownership / sort + per-segment warp).
-static bool scatter_legacy() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ADER_B200_SCATTER"); v = (e && e[0] == 'l') ? 1 : 0; }
-  return v == 1;
-}
 static int sort_passes(const AderModel* m) { return (key_bits(m->v_tab) + 7) / 8; }
 // plan: stable LSD radix sort of (item id, token); depends on the packed ids only
 static int run_scatter_plan(const AderModel* m, const EncWs& w, const BwdWs& g, int M, int Tcap, cudaStream_t st) {
@@ -1060,36 +933,8 @@ static int run_scatter_apply(const AderModel* m, const Layout& l, const EncWs& w
 }
 static int run_table_scatter(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
                              int M, int Tcap, float* grad, cudaStream_t st) {
-  const float p = 0.f; const uint64_t seed = 0; const int* d_step = nullptr;
-  const int d = m->d;
-  const int* dT = w.row_off + M;
-  if (!scatter_legacy()) {
-    if (int e = run_scatter_plan(m, w, g, M, Tcap, st)) return e;
-    return run_scatter_apply(m, l, w, g, gX, M, Tcap, grad, st);
-  }
-  if (Tcap <= SS_MAXT) {
-    if (d <= 160)
-      k_scatter_small<5><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
-                                                                                           grad + l.off_table);
-    else
-      k_scatter_small<LN_MAXE><<<cdiv(Tcap, 8), 256, sizeof(int) * (8 * SS_LIST + Tcap), st>>>(w.tok_id, dT, gX, d, sqrtf((float)d),
-                                                                                                 grad + l.off_table);
-  } else {
-    const int ntiles = sort_tiles(Tcap);
-    const int bits = key_bits(m->v_tab);
-    int cur = 0;
-    const int* kin = w.tok_id; const int* vin = nullptr;
-    int pass = 0;
-    for (int shift = 0; shift < bits; shift += 8, ++pass) {
-      k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
-      k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
-      k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
-      kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
-    }
-    k_seg_reduce<<<cdiv((long long)cdiv(Tcap, 4) * 32, 256), 256, 0, st>>>(kin, vin, dT, gX, d, sqrtf((float)d), p, seed,
-                                                                           d_step, grad + l.off_table);
-  }
-  return 0;
+  if (int e = run_scatter_plan(m, w, g, M, Tcap, st)) return e;
+  return run_scatter_apply(m, l, w, g, gX, M, Tcap, grad, st);
 }
 
 }  // namespace ader
@@ -1364,7 +1209,7 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
 }
 
 int ader::enc_scatter_plan_run(const AderModel* m, int M, int Tcap, const void* ws, void* bwd_ws, Fork& f) {
-  if (!f.parallel() || !f.has_tok_ready || scatter_legacy()) return 0;
+  if (!f.parallel() || !f.has_tok_ready) return 0;
   EncWs w = carve_enc(m, M, Tcap, (char*)ws);
   BwdWs g = carve_bwd(m, M, Tcap, (char*)bwd_ws);
   cudaStreamWaitEvent(f.c, f.tok_ready, 0);

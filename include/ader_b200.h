@@ -67,7 +67,8 @@ int32_t ader_encoder_fwd(const AderModel* m, const float* theta, const int32_t* 
 /* d_rep [M, d] -> grad (flat, same layout as theta): writes the pos_table and all block / lnf
  * gradients, and ADDS the input-lookup scatter (ADER.py:29-38, sqrt(d)-scaled) into the item
  * table rows of `grad` (which must already hold the output-projection gradient, or zeros).
- * The scatter is a stable radix sort by item id + segmented reduction: no float atomics. */
+ * The scatter is a stable radix sort by item id + windowed segmented reduction: deterministic (every row is a fixed
+ * function of the sorted order; float reductions to memory have exactly one contributor per address). */
 int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                          int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
                          float dropout_rate, uint64_t seed, void* stream);
