@@ -4,10 +4,10 @@
 // Operand format in HBM ("T128"): the bf16 shadow of the item table and of `rep` are stored as
 // tiles of 128 rows x 160 k (d = 150 zero-padded to 160), each tile pre-arranged as the UMMA
 // no-swizzle canonical layout: 8x8 core matrices (8 rows x 16 B, 128 B contiguous), core (rg, kc)
-// at byte kc*KPITCH + rg*128 (KPITCH = 2048 + 16 B of padding).  One tile = 41 280 contiguous bytes = ONE cp.async.bulk into shared
+// at byte (kc*16 + rg)*128.  One tile = 40 960 contiguous bytes = ONE cp.async.bulk into shared
 // memory, no tensor map, no swizzle.  The same tile serves as
-//   - K-major operand (K = feature): SBO = 128 B (row groups), LBO = KPITCH (k groups), and
-//   - MN-major B operand (N = feature, K = row): SBO = KPITCH, LBO = 128 B
+//   - K-major operand (K = feature): SBO = 128 B (row groups), LBO = 2048 B (k groups), and
+//   - MN-major B operand (N = feature, K = row): SBO = 2048 B, LBO = 128 B
 // so forward (S = rep.E^T) and both backward products (dRep = dS.E, dE = dS^T.rep) read the same bytes.
 //
 // Kernel roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane) +
@@ -37,19 +37,8 @@ namespace tc {
 
 constexpr int TILE = 128;
 constexpr int KP = 160;                       // padded feature dim
-// Pitch between the 2 KB column groups of a tile.  The k-groups of a T128 tile (v-groups of a dS tile) are the MN
-// direction when the tile is an MN-major operand of the second product; at a pitch of exactly 2048 B the eight 16-byte
-// granules the tensor core gathers across them fall into the same shared-memory banks (measured: the 128x160x128
-// second product took ~1.7 us instead of ~0.35 us).  16 B of padding per group spreads them over all banks; K-major
-// reads (whole 128 B core rows) are unaffected.
-#ifndef ADER_TC_PAD
-#define ADER_TC_PAD 16
-#endif
-constexpr int KPITCH = 2048 + ADER_TC_PAD;              // T128 tile: bytes from k-group kc to kc + 1
-constexpr int DPITCH = 2048 + ADER_TC_PAD;              // dS tile:   bytes from v-group vg to vg + 1
-constexpr int TILE_BYTES = (KP / 8) * KPITCH;           // 41 280 (40 960 unpadded)
-constexpr int DS_BYTES = (TILE / 8) * DPITCH;           // 33 024 (32 768 unpadded)
-static_assert(TILE_BYTES % (16 * 20) == 0 && DS_BYTES % (16 * 16) == 0, "bulk-copy pieces must be multiples of 16 bytes");
+constexpr int TILE_BYTES = TILE * KP * 2;     // 40960
+constexpr int DS_BYTES = TILE * TILE * 2;     // 32768
 constexpr int KSTEPS1 = KP / 16;              // 10 MMAs per S tile
 constexpr int KSTEPS2 = TILE / 16;            // 8 MMAs per gradient tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -334,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
         const uint32_t B = (MODE == MODE_DE) ? xa : ya;
 #pragma unroll
         for (int k = 0; k < KSTEPS1; ++k)
-          umma_bf16(tmem + s * 128, make_desc(A + k * 2 * KPITCH, KPITCH, 128), make_desc(B + k * 2 * KPITCH, KPITCH, 128), IDESC1, k > 0);
+          umma_bf16(tmem + s * 128, make_desc(A + k * 4096, 2048, 128), make_desc(B + k * 4096, 2048, 128), IDESC1, k > 0);
         if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + ys));
         umma_commit(BAR(B_TFULL + s));
       };
@@ -351,11 +340,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
           const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < KSTEPS2; ++k) {
-            // dS tile: core (vg, mg) at vg*DPITCH + mg*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=DPITCH,
-            // k-step = 2 v-groups.  DE: A MN-major (M=v, K=m): SBO=DPITCH, LBO=128, k-step = 256 B.
-            const uint64_t ad = DE_LIKE ? make_desc(da + k * 256, 128, DPITCH) : make_desc(da + k * 2 * DPITCH, DPITCH, 128);
-            // streamed T128 tile as MN-major B (N = feature, K = tile row): SBO=KPITCH, LBO=128, k-step = 256 B
-            const uint64_t bd = make_desc(ya + k * 256, 128, KPITCH);
+            // dS tile: core (vg, mg) at (vg*16 + mg)*128.  DREP: A K-major (M=m, K=v): SBO=128, LBO=2048,
+            // k-step = 2 v-groups = 4096 B.  DE: A MN-major (M=v, K=m): SBO=2048, LBO=128, k-step = 256 B.
+            const uint64_t ad = DE_LIKE ? make_desc(da + k * 256, 128, 2048) : make_desc(da + k * 4096, 2048, 128);
+            // streamed T128 tile as MN-major B (N = feature, K = tile row): SBO=2048, LBO=128, k-step = 256 B
+            const uint64_t bd = make_desc(ya + k * 256, 128, 2048);
             umma_bf16(tmem + ACC_COL, ad, bd, IDESC2, (it > 0 || k > 0));
           }
           umma_commit(BAR(B_YEMPTY + ys));
@@ -375,7 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
           const uint32_t ya = smem_u32(sY + ys * TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < KSTEPS2; ++k)
-            umma_bf16(tmem + ACC_COL, make_desc(da + k * 256, 128, DPITCH), make_desc(ya + k * 256, 128, KPITCH), IDESC2N, 1u);
+            umma_bf16(tmem + ACC_COL, make_desc(da + k * 256, 128, 2048), make_desc(ya + k * 256, 128, 2048), IDESC2N, 1u);
           umma_commit(BAR(B_YEMPTY + ys));
           umma_commit(BAR(B_DSEMPTY + s));
         }
@@ -498,7 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
               pk[u] = *reinterpret_cast<uint32_t*>(&h);
             }
             const int vg = (half * 2 + c) * 4 + gq;
-            *reinterpret_cast<uint4*>(ds + vg * DPITCH + (row >> 3) * 128 + (row & 7) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(ds + (vg * 16 + (row >> 3)) * 128 + (row & 7) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         fence_async_smem();                    // generic-proxy writes -> visible to the MMA (async proxy)
@@ -585,7 +574,7 @@ __global__ void k_pack_tiles(const float* __restrict__ src, long long ld, int n_
     __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
     pk[i] = *reinterpret_cast<uint32_t*>(&h);
   }
-  *reinterpret_cast<uint4*>(tiles + (size_t)tile * TILE_BYTES + kc * KPITCH + (r >> 3) * 128 + (r & 7) * 16) =
+  *reinterpret_cast<uint4*>(tiles + (size_t)tile * TILE_BYTES + (kc * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
       make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
@@ -613,7 +602,7 @@ __global__ void __launch_bounds__(256) k_teacher_lse(const float* __restrict__ t
   if (threadIdx.x == 0) { float tot = 0.f; for (int w = 0; w < 8; ++w) tot += sh[w]; lse_t[e] = mx + logf(tot); }
 }
 
-// bf16 tiles of Pc = coef * softmax(teacher) in the dS layout (core (vg, mg) at vg*DPITCH + mg*128): tile (et, vt) covers
+// bf16 tiles of Pc = coef * softmax(teacher) in the dS layout (core (vg, mg) at (vg*16 + mg)*128): tile (et, vt) covers
 // rows (x0 + et)*128 .. +127 of the step (zeros for non-exemplar rows) and LOCAL columns vt*128 .. +127 (teacher
 // column = v_off + local column; zeros beyond V_prev).  Warp per 16 rows, one 16-byte load per lane and row, all
 // 16 loads of a warp in flight together: the teacher is streamed once, coalesced.
@@ -650,7 +639,7 @@ __global__ void __launch_bounds__(256) k_teacher_tiles(const float* __restrict__
     const __nv_bfloat162 a = __floats2bfloat162_rn(coef * expf(t[rr].x - l[rr]), coef * expf(t[rr].y - l[rr]));   // exp(-inf) = 0
     const __nv_bfloat162 b = __floats2bfloat162_rn(coef * expf(t[rr].z - l[rr]), coef * expf(t[rr].w - l[rr]));
     uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(tile + (lane >> 1) * DPITCH + (m >> 3) * 128 + (m & 7) * 16 + (lane & 1) * 8) = pk;
+    *reinterpret_cast<uint2*>(tile + ((lane >> 1) * 16 + (m >> 3)) * 128 + (m & 7) * 16 + (lane & 1) * 8) = pk;
   }
 }
 
