@@ -23,7 +23,7 @@ from . import ops
 
 # ---- util.py:17-107 ----------------------------------------------------------------------------
 class DataLoader:
-    def __init__(self, dataset: str, data_root: Optional[str] = None):
+    def __init__(self, dataset: str, data_root: Optional[str] = None, cache_dir: Optional[str] = None):
         """`dataset` is a name under `data_root` (reference: '../../data/<dataset>', util.py:28)
         or a directory that directly holds period_<k>.txt files."""
         if data_root is None:
@@ -32,39 +32,79 @@ class DataLoader:
         if not os.path.isdir(self.path) and os.path.isdir(dataset):
             self.path = dataset
         self.item_set = set()                                   # util.py:26
+        # every period file is parsed once into a binary (session id, item id) pair file and grouped with
+        # array operations afterwards.  cache_dir=None (ADER_CACHE_DIR unset) keeps everything in memory.
+        self.cache_dir = cache_dir if cache_dir is not None else os.environ.get("ADER_CACHE_DIR")
+        self._pairs: Dict[int, Tuple[np.ndarray, np.ndarray]] = {}
 
-    def _read(self, period: int):
-        with open(os.path.join(self.path, "period_%d.txt" % period)) as f:
-            for line in f:
-                s, i = line.rstrip().split(" ")
-                yield int(s), int(i)
+    # ---- period file -> (session ids, item ids) arrays, cached -------------------------------------
+    def _cache_file(self, period: int) -> Optional[str]:
+        if not self.cache_dir:
+            return None
+        tag = os.path.basename(os.path.normpath(self.path)) or "data"
+        return os.path.join(self.cache_dir, "%s.period_%d.pairs.npy" % (tag, period))
+
+    def _read(self, period: int) -> Tuple[np.ndarray, np.ndarray]:
+        """The "<session> <item>" lines of period_<k>.txt (util.py:36-40) as two int64 arrays in file order."""
+        if period in self._pairs:
+            return self._pairs[period]
+        src = os.path.join(self.path, "period_%d.txt" % period)
+        st = os.stat(src)
+        cf = self._cache_file(period)
+        pairs = None
+        if cf and os.path.exists(cf):
+            try:
+                arr = np.load(cf)
+                # header row = (source size, source mtime in ns): a changed source file invalidates the cache
+                if arr.ndim == 2 and arr.shape[1] == 2 and arr[0, 0] == st.st_size and arr[0, 1] == st.st_mtime_ns:
+                    pairs = arr[1:]
+            except Exception:
+                pairs = None
+        if pairs is None:
+            with open(src, "rb") as f:
+                flat = np.array(f.read().split(), dtype=np.int64)
+            if flat.size % 2:
+                raise ValueError("%s: expected '<session> <item>' pairs" % src)
+            pairs = flat.reshape(-1, 2)
+            if cf:
+                os.makedirs(self.cache_dir, exist_ok=True)
+                tmp = cf + ".%d.tmp.npy" % os.getpid()
+                np.save(tmp, np.concatenate([np.array([[st.st_size, st.st_mtime_ns]], dtype=np.int64), pairs]))
+                os.replace(tmp, cf)
+        out = (np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1]))
+        self._pairs[period] = out
+        return out
+
+    @staticmethod
+    def _group(sess: np.ndarray, item: np.ndarray) -> List[List[int]]:
+        """dict-of-lists grouping of the reference (util.py:41-48): sessions in order of first appearance, items of a
+        session in file order -- as one stable sort instead of a Python loop over every line."""
+        if sess.size == 0:
+            return []
+        order = np.argsort(sess, kind="stable")
+        ss = sess[order]
+        starts = np.flatnonzero(np.concatenate([[True], ss[1:] != ss[:-1]]))
+        ends = np.concatenate([starts[1:], [ss.size]])
+        first = order[starts]                                   # file position of each session's first line
+        items_sorted = item[order].tolist()
+        return [items_sorted[starts[g]:ends[g]] for g in np.argsort(first, kind="stable")]
 
     def train_loader(self, period: int) -> Tuple[List[List[int]], str]:        # util.py:32-58
-        by_sess: Dict[int, List[int]] = {}
-        n = 0
-        for s, i in self._read(period):
-            self.item_set.add(i)
-            by_sess.setdefault(s, []).append(i)
-            n += 1
-        info = "Train set information: total number of action: %d." % n
+        sess, item = self._read(period)
+        self.item_set.update(np.unique(item).tolist())
+        info = "Train set information: total number of action: %d." % sess.size
         print(info)
-        return list(by_sess.values()), info
+        return self._group(sess, item), info
 
     def evaluate_loader(self, period: int) -> Tuple[List[List[int]], str]:     # util.py:60-102
-        by_sess: Dict[int, List[int]] = {}
-        total = removed = 0
-        for s, i in self._read(period):
-            total += 1
-            if i not in self.item_set:
-                removed += 1
-                continue
-            by_sess.setdefault(s, []).append(i)
-        kept = []
-        for items in by_sess.values():
-            if len(items) == 1:
-                removed += 1
-            else:
-                kept.append(items)
+        sess, item = self._read(period)
+        total = int(sess.size)
+        known = np.fromiter(self.item_set, dtype=np.int64, count=len(self.item_set))
+        keep = np.isin(item, known)
+        removed = total - int(keep.sum())
+        groups = self._group(sess[keep], item[keep])
+        kept = [g for g in groups if len(g) > 1]
+        removed += len(groups) - len(kept)
         info = "Test set information: original total number of action: %d, removed number of action: %d." % (total, removed)
         print(info)
         return kept, info

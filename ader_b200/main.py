@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .data import DataLoader, Evaluator, ExemplarGenerator, ExemplarSet, Sampler
+from .data import DataLoader, Evaluator, ExemplarGenerator, ExemplarSet, Sampler, pack_rows
 from .model import Ader, Ewc
 
 ITEM_NUM = {"DIGINETICA": 43136, "YOOCHOOSE": 25958}     # main.py:133-138
@@ -66,6 +66,10 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     p.add_argument("--loss_impl", default="tc", choices=["tc", "exact"], type=str)      # logits+CE+KD: tcgen05 bf16 / fp32
     p.add_argument("--encoder_impl", default=None, choices=["tc", "exact"], type=str)  # training encoder (default follows loss_impl)
     p.add_argument("--infer_encoder_impl", default="exact", choices=["tc", "exact"], type=str)  # eval / herding encoder
+    # per-period checkpoint + resume (the reference cannot resume a run), binary cache of the period files
+    p.add_argument("--checkpoint", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))
+    p.add_argument("--resume", default=False, type=lambda v: str(v).lower() not in ("0", "false", "no"))
+    p.add_argument("--cache_dir", default=None, type=str)
     p.add_argument("--step_impl", default=None, choices=["dag", "serial", "groups"], type=str)   # how a tc train step is issued (model.py)
     p.add_argument("--graph", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))  # CUDA-graph train step
     return p
@@ -170,17 +174,76 @@ class PeriodTrainer:
         return loss
 
 
+# ---- per-period checkpoint -------------------------------------------------------------------
+# One file per run, rewritten atomically at the end of every period: everything the next period reads from the
+# previous ones -- best weights + Adam slots + step counter, the exemplar SESSIONS (their teacher logits are
+# recomputed from those weights on resume: the exact inference path is deterministic, so they come back bit-identical
+# without writing up to 5 GB per period), item universe, early-stop counter, metrics, both host RNG states, EWC state.
+CKPT_NAME = "checkpoint.pt"
+
+
+def save_period_checkpoint(path: str, period: int, model, dataloader, fast_exemplar, carry: dict) -> None:
+    st = {"format": 1, "period": int(period), "model": {k: (v.cpu() if isinstance(v, torch.Tensor) else v)
+                                                      for k, v in model.state_dict().items()},
+          "item_set": np.array(sorted(dataloader.item_set), dtype=np.int64),
+          "exemplar_sessions": None if fast_exemplar is None else [list(map(int, x)) for x in fast_exemplar.sessions],
+          "teacher_width": None if fast_exemplar is None or fast_exemplar.teacher is None else int(fast_exemplar.teacher.shape[1]),
+          "carry": carry, "py_random": random.getstate(), "np_random": np.random.get_state()}
+    if isinstance(model, Ewc):
+        st["ewc"] = {"fisher": None if model.fisher is None else model.fisher.cpu(),
+                     "theta_star": None if model.theta_star is None else model.theta_star.cpu()}
+    tmp = path + ".tmp"
+    torch.save(st, tmp)
+    os.replace(tmp, path)
+
+
+def rebuild_exemplars(model, sessions, teacher_width: int, maxlen: int, chunk: int = 4096) -> ExemplarSet:
+    """Exemplar store of a resumed run: stored logits = logits of the saved sessions under the restored weights
+    (what ExemplarGenerator._store computed with the same weights at the end of the period, util.py:433)."""
+    rows = [list(x) for x in sessions]
+    if teacher_width is None:
+        return ExemplarSet(rows, None)
+    ids, _, n_in = pack_rows(rows, maxlen)
+    out = []
+    for lo in range(0, len(rows), chunk):
+        r = model.rep(ids[lo:lo + chunk], n_tokens=int(n_in[lo:lo + chunk].sum()))
+        out.append(model.logits(r.contiguous(), teacher_width))
+    teacher = torch.cat(out) if out else torch.zeros((0, teacher_width), device=model.device)
+    return ExemplarSet(rows, teacher)
+
+
+def load_period_checkpoint(path: str, model, dataloader, maxlen: int):
+    st = torch.load(path, map_location="cpu", weights_only=False)
+    if st.get("format") != 1:
+        raise ValueError("%s: unknown checkpoint format" % path)
+    model.load_state_dict({k: (v.to(model.device) if isinstance(v, torch.Tensor) else v) for k, v in st["model"].items()})
+    dataloader.item_set = set(int(x) for x in st["item_set"])
+    if isinstance(model, Ewc) and st.get("ewc"):
+        e = st["ewc"]
+        model.fisher = None if e["fisher"] is None else e["fisher"].to(model.device)
+        model.theta_star = None if e["theta_star"] is None else e["theta_star"].to(model.device)
+    ex = None
+    if st["exemplar_sessions"] is not None:
+        ex = rebuild_exemplars(model, st["exemplar_sessions"], st["teacher_width"], maxlen)
+    random.setstate(st["py_random"])
+    np.random.set_state(st["np_random"])
+    return st["period"], ex, st["carry"]
+
+
 def run(args) -> dict:
     res_dir = os.path.join(args.results_root, os.path.basename(args.dataset.rstrip("/")) + "-" + args.save_dir)
     os.makedirs(res_dir, exist_ok=True)
-    logs = open(os.path.join(res_dir, "Training_logs.txt"), mode="w")
-    logs.write("\n".join([str(k) + "," + str(v) for k, v in sorted(vars(args).items(), key=lambda x: x[0])]))
+    ckpt_path = os.path.join(res_dir, CKPT_NAME)
+    resuming = bool(getattr(args, "resume", False)) and os.path.exists(ckpt_path)
+    logs = open(os.path.join(res_dir, "Training_logs.txt"), mode="a" if resuming else "w")
+    if not resuming:
+        logs.write("\n".join([str(k) + "," + str(v) for k, v in sorted(vars(args).items(), key=lambda x: x[0])]))
 
     torch.cuda.set_device(args.device_num)
     np.random.seed(args.random_seed)                           # main.py:123-125
     random.seed(args.random_seed)
 
-    dataloader = DataLoader(args.dataset, args.data_root)
+    dataloader = DataLoader(args.dataset, args.data_root, cache_dir=getattr(args, "cache_dir", None))
     item_num = args.item_num or ITEM_NUM.get(os.path.basename(args.dataset.rstrip("/")))
     if not item_num:
         raise ValueError("Invalid dataset name")
@@ -202,7 +265,19 @@ def run(args) -> dict:
     trace = {"periods": []} if getattr(args, "trace", False) else None
     no_replay = args.finetune or args.dropout or args.joint
 
+    done_period = 0
+    if resuming:                                               # continue after the last finished period
+        done_period, fast_exemplar, carry = load_period_checkpoint(ckpt_path, model, dataloader, args.maxlen)
+        best_epoch, item_num_prev, stop_counter = carry["best_epoch"], carry["item_num_prev"], carry["stop_counter"]
+        metrics, stats = carry["metrics"], carry["stats"]
+        ckpt = {(done_period, best_epoch): model.state_dict()}
+        info = "Resumed after period %d from %s" % (done_period, ckpt_path)
+        print(info)
+        logs.write(info + "\n")
+
     for period in periods:
+        if period <= done_period:
+            continue
         print("Period %d:" % period)
         logs.write("Period %d:\n" % period)
         best_performance, performance = 0, 0
@@ -323,6 +398,10 @@ def run(args) -> dict:
             model.variables_prev = model.snapshot_variables()
             rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
             model.compute_fisher(None, rnd, 50, max_item)
+        if getattr(args, "checkpoint", True):
+            save_period_checkpoint(ckpt_path, period, model, dataloader, fast_exemplar,
+                                   {"best_epoch": best_epoch, "item_num_prev": item_num_prev, "stop_counter": stop_counter,
+                                    "metrics": metrics, "stats": stats})
         logs.flush()
 
     avg = {k: float(np.array(v).mean()) for k, v in metrics.items()}

@@ -562,6 +562,28 @@ def test_end_to_end_tc_path_reaches_same_metrics(tmp_path):
     np.testing.assert_allclose(rb["trace"]["periods"][0]["losses"][:10], ra["trace"]["periods"][0]["losses"][:10], rtol=2e-3)
 
 
+@pytest.mark.parametrize("selection,kw", [("herding", {}), ("random", {"loss_impl": "tc", "dropout_rate": 0.3})])
+def test_resume_after_a_period_reproduces_the_uninterrupted_run(tmp_path, selection, kw):
+    """a run stopped after period 2 and resumed (--resume) finishes period 3 exactly like the run that
+    never stopped -- same step losses, best epoch, test ranks, exemplar set and final weights, bit for bit.  The
+    checkpoint holds weights + Adam state, exemplar sessions (teacher logits are recomputed from the weights), item
+    universe, early-stop counter, metrics and both host RNG streams."""
+    from ader_b200.main import run, CKPT_NAME
+    full = run(_e2e_args(tmp_path / "full", selection=selection, max_periods=3, **kw))
+    part = run(_e2e_args(tmp_path / "cut", selection=selection, max_periods=2, **kw))
+    assert os.path.exists(os.path.join(str(tmp_path / "cut"), "tiny_data-" + _e2e_args(tmp_path).save_dir, CKPT_NAME))
+    rest = run(_e2e_args(tmp_path / "cut", selection=selection, max_periods=3, resume=True, **kw))
+    assert len(rest["trace"]["periods"]) == 1                      # only period 3 was run again
+    a, b = full["trace"]["periods"][2], rest["trace"]["periods"][0]
+    assert a["losses"] == b["losses"]
+    assert a["best_epoch"] == b["best_epoch"] and a["test"] == b["test"] and a["test_ranks"] == b["test_ranks"]
+    assert a["exemplars"] == b["exemplars"]
+    assert torch.equal(full["model"].theta, rest["model"].theta)
+    assert full["per_period"] == rest["per_period"]                # metrics of periods 1-2 came from the checkpoint
+    for p_full, p_cut in zip(full["trace"]["periods"][:2], part["trace"]["periods"]):
+        assert p_full["losses"] == p_cut["losses"]
+
+
 @pytest.mark.parametrize("mode,shards", [("vanilla", 2), ("kd", 3), ("er", 2)])
 def test_vocab_parallel_shards_match_single_kernel(mode, shards):
     """Vocab-parallel kernels (column offset, per-shard stats, partial d_rep, own-row dE) emulated with

@@ -105,3 +105,39 @@ def test_pack_rows_label_generator():
     for r in (1, 2):
         seq, pos = P.row_to_input(rows[r], 50)
         assert np.array_equal(ids[r], seq) and label[r] == pos
+
+
+def test_dataloader_binary_cache_matches_text_parse(golden_dir, tmp_path):
+    """the cached (session, item) pair file gives the same sessions / infos as parsing the text, is reused on
+    the second construction, and is invalidated when the source file changes."""
+    import shutil
+    src = os.path.join(golden_dir, "tiny_data")
+    data = tmp_path / "tiny_data"
+    shutil.copytree(src, data)
+    cache = tmp_path / "cache"
+
+    def load(cache_dir):
+        dl = D.DataLoader(str(data), cache_dir=cache_dir)
+        tr, i1 = dl.train_loader(0)
+        te, i2 = dl.evaluate_loader(1)
+        return tr, i1, te, i2, dl.max_item()
+
+    plain = load(None)
+    first = load(str(cache))
+    files = sorted(os.listdir(cache))
+    assert len(files) == 2 and all(f.endswith(".pairs.npy") for f in files)
+    stamp = {f: os.stat(cache / f).st_mtime_ns for f in files}
+    second = load(str(cache))
+    assert plain == first == second
+    assert {f: os.stat(cache / f).st_mtime_ns for f in files} == stamp          # reused, not rewritten
+    # reference semantics of the grouping: sessions by first appearance, items in file order
+    by = {}
+    for line in open(data / "period_0.txt"):
+        s, i = line.split()
+        by.setdefault(int(s), []).append(int(i))
+    assert plain[0] == list(by.values())
+    # a changed source invalidates the cache entry
+    with open(data / "period_0.txt", "a") as f:
+        f.write("999999 1\n999999 2\n")
+    third = load(str(cache))
+    assert third[0][:-1] == plain[0] and third[0][-1] == [1, 2]
