@@ -118,6 +118,7 @@ class GraphStep:
         caps = sorted({min(max(int(t), 1), full) for t in (tcaps or [])} | {full})
         self.tcaps = caps
         self.graphs = {}
+        self.use_count = {}                    # replays per token-capacity bucket
         self._row_loss = {}
         self._capture_all()
         # the graphs address these buffers: keep them alive even if the model later grows its workspaces
@@ -159,23 +160,40 @@ class GraphStep:
             self._eager(self.tcaps[-1], False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        pool = None
-        self.graphs_idx = {}                   # index-fed form: batch gather + step in ONE graph (no gap between two replays)
-        for tcap in reversed(self.tcaps):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                self._eager(tcap, True)
-            pool = g.pool()
-            self.graphs[tcap] = g
-            if self.sources is not None:
-                gi = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gi, pool=pool):
-                    self._gather()
-                    self._eager(tcap, True, indexed=True)
-                self.graphs_idx[tcap] = gi
         m.load_state_dict(sd)                  # the warm-up step must not count
         m.global_step = gs
         torch.cuda.synchronize()
+        # graphs are captured on first use, one per (token-capacity bucket, feed form): a period that is over after a few
+        # hundred steps pays for the two or three it replays, not for all of them
+        self._pool = None
+        self._held_more = []
+        self.graphs_idx = {}                   # index-fed form: batch gather + step in ONE graph (no gap between two replays)
+
+    def _graph_for(self, tcap: int, indexed: bool) -> torch.cuda.CUDAGraph:
+        table = self.graphs_idx if indexed else self.graphs
+        g = table.get(tcap)
+        if g is None:
+            m = self.model
+            gs = m.global_step                 # capture records launches, it runs nothing: only the host counter moves
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool):
+                if indexed:
+                    self._gather()
+                self._eager(tcap, True, indexed=indexed)
+            self._pool = g.pool()
+            m.global_step = gs
+            table[tcap] = g
+            # the graph addresses the workspaces as they are NOW (another pass may have grown them since construction)
+            self._held_more.append((m._enc_ws.buf, m._bwd_ws.buf, m._loss_ws.buf))
+        return g
+
+    def precapture(self, indexed: Optional[bool] = None):
+        """Capture every bucket now (benchmarks: keep capture time out of the timed region)."""
+        for tcap in self.tcaps:
+            for form in ((False, True) if indexed is None else (indexed,)):
+                if form and self.sources is None:
+                    continue
+                self._graph_for(tcap, form)
 
     # ---- replay ---------------------------------------------------------------------------------------
     def _replay(self, n_tokens: Optional[int], indexed: bool = False):
@@ -185,7 +203,8 @@ class GraphStep:
                 if t >= n_tokens:
                     cap = t
                     break
-        (self.graphs_idx if indexed else self.graphs)[cap].replay()
+        self.use_count[cap] = self.use_count.get(cap, 0) + 1
+        self._graph_for(cap, indexed).replay()
         self.model.global_step += 1
         self.model.last_row_loss = self._row_loss[(cap, indexed)]
         return self.model._loss

@@ -92,6 +92,7 @@ class PeriodTrainer:
         self.trace_rows = None
         self.gs = None                  # the step as CUDA graphs (full-size batches; odd-size batches run eagerly)
         self._graph_tried = False
+        self.n_eager = 0                # steps issued launch by launch (odd batch geometry / no graph)
 
     def _graph(self, n_train: int, n_ex: int):
         """Capture the step for this period's batch geometry on first use (ader_b200/graph.py)."""
@@ -132,13 +133,14 @@ class PeriodTrainer:
         m, dev, L = self.model, self.model.device, self.model.hp.maxlen
         ti = self.ts.next_indices()
         n_tok = int(self.t_nin[ti].sum())
-        if self.es is None and len(ti) == self.args.batch_size:
-            gs = self._graph(len(ti), 0)
-            if gs is not None and self.gs_shape == (len(ti), 0):
-                self.rows_seen += len(ti)
-                return gs.run_indices(ti, None, n_tok)
-        ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         if self.es is None:
+            if len(ti) == self.args.batch_size:
+                gs = self._graph(len(ti), 0)
+                if gs is not None and self.gs_shape == (len(ti), 0):
+                    self.rows_seen += len(ti)
+                    return gs.run_indices(ti, None, n_tok)
+            self.n_eager += 1                                    # odd batch size (last batch of a pass) / no graph
+            ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
             ids = torch.empty((len(ti), L), dtype=torch.int32, device=dev)
             ops.gather_rows_i32(self.t_ids, ti_d, ids)
             pos = self.t_lab[ti_d.long()]
@@ -152,6 +154,8 @@ class PeriodTrainer:
             if gs is not None and self.gs_shape == (len(ti), len(ei)):
                 self.rows_seen += len(ti) + len(ei)
                 return gs.run_indices(ti, ei, n_tok)
+        self.n_eager += 1
+        ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         ids = torch.empty((len(ti) + len(ei), L), dtype=torch.int32, device=dev)
         ops.gather_rows_i32(self.t_ids, ti_d, ids[:len(ti)])
@@ -362,7 +366,9 @@ def run(args) -> dict:
         metrics["MRR_10"].append(r[2]); metrics["Recall_10"].append(r[3])
         sps = trainer.rows_seen / max(train_time, 1e-9)
         stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps})
-        info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s)" % (period, sps, trainer.rows_seen, train_time)
+        use = dict(sorted(trainer.gs.use_count.items())) if trainer.gs is not None else {}
+        info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by token capacity %s, eager steps %d)" % (
+            period, sps, trainer.rows_seen, train_time, use, trainer.n_eager)
         print(info)
         logs.write(info + "\n")
 
