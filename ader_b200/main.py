@@ -90,17 +90,43 @@ class PeriodTrainer:
         self.rows_seen = 0
         self.trace = None
         self.trace_rows = None
-        self.gs = None                  # the step as CUDA graphs (full-size batches; odd-size batches run eagerly)
-        self._graph_tried = False
-        self.n_eager = 0                # steps issued launch by launch (odd batch geometry / no graph)
+        # the step as CUDA graphs, one GraphStep per batch geometry (n_train, n_ex).  The reference drops rows of length <= 1
+        # from a batch (util.py:228-229), so a few rows are missing from about half of the batches of some periods: the
+        # full geometry is captured at once, any other after its third appearance (at most MAX_GEOM of them)
+        self.gs_map = {}
+        self._geom_seen = {}
+        self._graph_off = False
+        self.n_eager = 0                # steps issued launch by launch (rare batch geometry / no graph)
+
+    MAX_GEOM = 8
+
+    @property
+    def gs(self):
+        """The GraphStep of the full batch geometry (None before its first use)."""
+        full = (self.args.batch_size, self.es.batch_size if self.es is not None else 0)
+        return self.gs_map.get(full)
+
+    def graph_use(self) -> dict:
+        out = {}
+        for (nt, ne), g in sorted(self.gs_map.items()):
+            out["%d+%d" % (nt, ne)] = dict(sorted(g.use_count.items()))
+        return out
 
     def _graph(self, n_train: int, n_ex: int):
-        """Capture the step for this period's batch geometry on first use (ader_b200/graph.py)."""
-        if self._graph_tried or not getattr(self.args, "graph", True):
-            return self.gs
-        self._graph_tried = True
+        """GraphStep for this batch geometry (ader_b200/graph.py), built on demand; None = run the step eagerly."""
+        key = (n_train, n_ex)
+        gs = self.gs_map.get(key)
+        if gs is not None:
+            return gs
         m, args = self.model, self.args
+        if self._graph_off or not getattr(args, "graph", True):
+            return None
         if m.encoder_impl != "tc" and args.dropout_rate > 0:
+            self._graph_off = True
+            return None
+        full = (args.batch_size, self.es.batch_size if self.es is not None else 0)
+        seen = self._geom_seen[key] = self._geom_seen.get(key, 0) + 1
+        if key != full and (seen < 3 or len(self.gs_map) >= self.MAX_GEOM):
             return None
         dev = m.device
         e_ids = e_aux = teacher = None
@@ -111,15 +137,16 @@ class PeriodTrainer:
                 e_aux = torch.as_tensor(np.asarray(self.es.logits, dtype=np.int32)).to(dev)
                 teacher = self.es.teacher
             else:
-                return None              # host-resident teacher lists (reference feed): eager path
+                self._graph_off = True   # host-resident teacher lists (reference feed): eager path
+                return None
             e_ids = self.e_ids
         mean_tok = n_train * float(np.mean(self.t_nin)) + (n_ex * float(np.mean(self.e_nin)) if self.es is not None else 0.0)
         caps = [int(mean_tok * f) + 64 for f in (1.1, 1.3, 1.7)]
-        self.gs = m.graph_step(n_train, n_ex, self.max_item, args.lr, args.dropout_rate, teacher=teacher,
-                               sources=(self.t_ids, self.t_lab, e_ids, e_aux) if self.es is not None
-                               else (self.t_ids, self.t_lab, None, None), tcaps=caps)
-        self.gs_shape = (n_train, n_ex)
-        return self.gs
+        gs = m.graph_step(n_train, n_ex, self.max_item, args.lr, args.dropout_rate, teacher=teacher,
+                          sources=(self.t_ids, self.t_lab, e_ids, e_aux) if self.es is not None
+                          else (self.t_ids, self.t_lab, None, None), tcaps=caps)
+        self.gs_map[key] = gs
+        return gs
 
     def step(self):
         loss = self._step()
@@ -134,12 +161,12 @@ class PeriodTrainer:
         ti = self.ts.next_indices()
         n_tok = int(self.t_nin[ti].sum())
         if self.es is None:
-            if len(ti) == self.args.batch_size:
+            if len(ti) > 0:
                 gs = self._graph(len(ti), 0)
-                if gs is not None and self.gs_shape == (len(ti), 0):
+                if gs is not None:
                     self.rows_seen += len(ti)
                     return gs.run_indices(ti, None, n_tok)
-            self.n_eager += 1                                    # odd batch size (last batch of a pass) / no graph
+            self.n_eager += 1                                    # rare batch size / no graph
             ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
             ids = torch.empty((len(ti), L), dtype=torch.int32, device=dev)
             ops.gather_rows_i32(self.t_ids, ti_d, ids)
@@ -149,9 +176,9 @@ class PeriodTrainer:
             return loss
         ei = self.es.next_indices()
         n_tok += int(self.e_nin[ei].sum())
-        if len(ti) == self.args.batch_size and len(ei) == self.es.batch_size and len(ei) > 0:
+        if len(ti) > 0 and len(ei) > 0:
             gs = self._graph(len(ti), len(ei))
-            if gs is not None and self.gs_shape == (len(ti), len(ei)):
+            if gs is not None:
                 self.rows_seen += len(ti) + len(ei)
                 return gs.run_indices(ti, ei, n_tok)
         self.n_eager += 1
@@ -366,9 +393,8 @@ def run(args) -> dict:
         metrics["MRR_10"].append(r[2]); metrics["Recall_10"].append(r[3])
         sps = trainer.rows_seen / max(train_time, 1e-9)
         stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps})
-        use = dict(sorted(trainer.gs.use_count.items())) if trainer.gs is not None else {}
-        info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by token capacity %s, eager steps %d)" % (
-            period, sps, trainer.rows_seen, train_time, use, trainer.n_eager)
+        info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by batch geometry / token capacity %s, eager steps %d)" % (
+            period, sps, trainer.rows_seen, train_time, trainer.graph_use(), trainer.n_eager)
         print(info)
         logs.write(info + "\n")
 
