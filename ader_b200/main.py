@@ -10,6 +10,7 @@ Extra flags (not in the reference): --data_root, --max_periods, --results_root.
 from __future__ import annotations
 
 import argparse
+import gc
 import math
 import os
 import random
@@ -361,8 +362,16 @@ def run(args) -> dict:
         for epoch in range(1, args.num_epochs + 1):
             torch.cuda.synchronize()
             t0 = time.time()
-            for _ in range(batch_num):
-                trainer.step()
+            # the host holds millions of small Python objects (session lists): a generation-2 collection in the middle of
+            # the batch loop stalls the launch thread for 0.1-0.5 s while the GPU idles -- collect between epochs instead
+            gc_on = gc.isenabled()
+            gc.disable()
+            try:
+                for _ in range(batch_num):
+                    trainer.step()
+            finally:
+                if gc_on:
+                    gc.enable()
             torch.cuda.synchronize()
             train_time += time.time() - t0
             if period > 1 and args.ewc:                        # main.py:258-262 (no effect on train_op, S13)
