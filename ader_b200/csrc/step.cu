@@ -5,8 +5,10 @@
 // the critical path (teacher products, table-tile packing, dE, weight / LayerNorm / position gradients, partial
 // reductions).  This entry issues the same kernels as
 //     ader_encoder_fwd_tc -> ader_loss_fwd_bwd_tc -> ader_encoder_bwd_tc
-// with the same arguments -- results are bit-identical -- but puts the off-path work on three internal streams
-// joined by events.  Captured by a CUDA graph the side streams become parallel branches of the graph.
+// with the same arguments -- results are bit-identical -- but puts the off-path work on five library-owned streams
+// joined by events, and launches the kernel-to-kernel links of the chain as programmatic dependent launches.
+// Captured by a CUDA graph the side streams become parallel branches of the graph.  ader_train_step_tc adds the
+// optimiser to the same DAG.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -14,7 +16,7 @@ namespace ader {
 
 struct StreamPool {
   cudaStream_t s[5];     // side streams, lowest priority (3 general + 2 more for weight-gradient pieces)
-  cudaStream_t hi;       // critical chain, highest priority: its pending CTAs are placed before those of the side streams
+  cudaStream_t hi;       // optional highest-priority chain stream (ADER_B200_DAG_PRIO=1)
   cudaEvent_t ev[128];
   bool ok;
   StreamPool() : ok(false) {}
@@ -34,8 +36,9 @@ struct StreamPool {
 // one pool per host thread and device (streams belong to the device that was current at creation)
 static thread_local StreamPool g_pool[16];
 
-// experiment switches (read once): ADER_B200_DAG_PRIO=0 keeps the chain on the caller's stream;
-// ADER_B200_PDL=1 launches the chain links as programmatic dependent launches
+// switches (read once).  ADER_B200_DAG_PRIO=1 moves the chain to a highest-priority stream: measured slower (the
+// hardware schedules strictly by priority without back-fill, the side streams starve), so the default keeps the chain
+// on the caller's stream.  ADER_B200_PDL=0 turns the programmatic dependent launches of the chain off.
 static int env_flag(const char* name, int dflt) {
   const char* e = getenv(name);
   return e && e[0] ? atoi(e) : dflt;
@@ -108,7 +111,7 @@ extern "C" int32_t ader_train_step_tc(const AderModel* m, float* theta, const in
                                       float* loss, float* row_loss, float* d_rep, float* grad, float dropout_rate,
                                       uint64_t seed, const int32_t* d_step, float* adam_m, float* adam_v, int32_t* state,
                                       const AderAdamArgs* opt, int32_t serial, void* stream) {
-  ADER_CHECK_ARG(adam_m && adam_v && state && opt, "train_step_tc: NULL optimiser pointer");
+  ADER_CHECK_ARG(m && adam_m && adam_v && state && opt, "train_step_tc: NULL pointer");
   ADER_CHECK_ARG(opt->V >= 1 && opt->V < m->v_tab, "train_step_tc: max_item %d outside table", opt->V);
   ADER_CHECK_ARG(opt->ewc_lambda == 0.f || (opt->fisher && opt->theta_star), "train_step_tc: EWC needs fisher and theta_star");
   AdamPlan plan;
