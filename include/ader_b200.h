@@ -142,7 +142,9 @@ int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, const float*
  *   ader_encoder_bwd_tc(.., enc_ws, bwd_ws, d_rep, grad, ..)
  * with the same arguments and bit-identical results, issued as a fork/join DAG: launches that are off the critical
  * chain (table-tile packing, teacher products, dE, weight-shadow packing, weight / LayerNorm / position gradients,
- * partial reductions, the scalar loss) go to three library-owned side streams ordered against `stream` by events;
+ * partial reductions, the scalar loss) go to five library-owned side streams ordered against `stream` by events, and
+ * the kernel-to-kernel links of the chain are programmatic dependent launches (the next kernel's prologue overlaps the
+ * previous kernel's drain);
  * everything is joined back into `stream` before the call returns, so the function stays stream-ordered for the
  * caller, and under stream capture the side streams become parallel branches of the captured graph.  The side
  * streams/events are created once per host thread and device on first use (the only allocation in the library:
