@@ -37,8 +37,18 @@ class AderAdamArgs(C.Structure):
                 ("theta_star", C.c_void_p)]
 
 
+DP_MAX_RANKS = 16
+DP_FLAG_WORDS = 64
+
+
+class AderDpComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("theta", C.c_void_p * DP_MAX_RANKS),
+                ("grad", C.c_void_p * DP_MAX_RANKS), ("flags", C.c_void_p * DP_MAX_RANKS)]
+
+
 _P = C.c_void_p
 _MP = C.POINTER(AderModel)
+_CP = C.POINTER(AderDpComm)
 
 # name -> (restype, argtypes); mirrors include/ader_b200.h one to one (tests/test_abi.py checks
 # that every symbol declared in the header is exported and listed here).
@@ -75,6 +85,12 @@ SIGNATURES = {
     "ader_herding_segmented": (C.c_int32, [_MP, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ader_fisher_accumulate": (C.c_int32, [_MP, _P, _P, C.c_int32, _P]),
     "ader_fisher_finalize": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P]),
+    "ader_dp_wait": (C.c_int32, [_CP, _P]),
+    "ader_dp_adam_step": (C.c_int32, [_MP, _CP, _P, _P, _P, C.POINTER(AderAdamArgs), _P]),
+    "ader_dp_status": (C.c_int32, [_CP, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
+    "ader_ipc_export": (C.c_int32, [_P, _P, C.POINTER(C.c_int64)]),
+    "ader_ipc_open": (C.c_int32, [_P, C.POINTER(C.c_void_p)]),
+    "ader_ipc_close": (C.c_int32, [_P]),
     "ader_gather_rows_i32": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "ader_gather_batch": (C.c_int32, [_P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
@@ -91,9 +107,14 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    # build() returns at once when the .so is newer than every source / header (mtime check), so a pulled kernel change
+    # can never run against a stale library; a box without nvcc (or a read-only tree) uses the shipped .so as it is
     path = _build.LIB_PATH
-    if not os.path.exists(path) or (os.environ.get("ADER_B200_REBUILD") == "1"):
-        path = _build.build()
+    try:
+        path = _build.build(force=os.environ.get("ADER_B200_REBUILD") == "1")
+    except Exception:
+        if not os.path.exists(path):
+            raise
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly

@@ -1,0 +1,254 @@
+// Data-parallel optimiser step over NVLink peer memory (the reference is single-device:
+// main.py:96,120,143, so everything here is new).
+//
+// One process per GPU; every rank holds a full replica of theta and its own gradient of the step
+// (rows of the batch are sharded, loss denominators are the GLOBAL counts, so the wanted gradient is
+// the plain SUM over ranks).  Instead of  all-reduce(grad) -> Adam on every rank  (2 x 7/8 of the
+// gradient over the links AND the full 28 B/param optimiser traffic on every GPU), ONE kernel does
+//
+//     reduce-scatter (peer loads)  ->  TF1 Adam on the owned slice  ->  all-gather (peer stores)
+//
+// Rank r owns a contiguous slice of the update index space [item-table rows 1..V | dense parameters]
+// (the same index space k_adam walks).  For its slice it loads the gradient of every rank over NVLink
+// (ld.global.cv: peer lines must not be served from a stale L1), adds them in rank order 0..N-1
+// (fixed order: run-to-run deterministic, and every replica receives the same bits), applies
+// adam_update_elem (the very expression the single-GPU kernels evaluate) with its LOCAL m / v --
+// the optimiser state of a slice is only ever touched by its owner -- and stores the new theta
+// into every replica.  Link traffic per GPU and step: (N-1)/N of the gradient in, (N-1)/N of theta out.
+//
+// Synchronisation (no host, graph-capturable): a flag block per rank in peer-mapped memory,
+//   flags[src] (src < N): arrival counter written by rank `src` (monotonic epoch numbers),
+//   EPOCH: this rank's epoch (2 per step), DONE: CTA completion counter, ERR: timeout marker.
+// k_dp_arrive (one warp, directly in front of k_dp_adam): publishes "my gradient is complete" (epoch e+1) to every
+// rank and waits until all ranks have published (A).  k_dp_adam works, and the last CTA to finish publishes
+// e+2 = "I have read your gradients and written your theta" (B).  ader_dp_wait (first kernel of the next step) waits
+// for B from every rank before anything overwrites the gradient or reads theta.  Only single-warp kernels ever spin
+// (they leave the SMs to whatever the other ranks still have to run -- also when several emulated ranks share one
+// GPU in the tests); spins time out (~20 s) and mark ERR instead of hanging the GPU.
+#include "common.cuh"
+#include <string.h>
+
+namespace ader {
+namespace dp {
+
+constexpr int F_EPOCH = 32, F_DONE = 33, F_ERR = 34;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_cv2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cv.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until flags[src] >= want (signed distance: epochs wrap after 2^31 steps); false on timeout
+__device__ __forceinline__ bool wait_flag(const uint32_t* f, uint32_t want, uint32_t* err) {
+  const unsigned long long t0 = gtime();
+  while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
+    if (gtime() - t0 > 20000000000ull) { atomicExch(err, 1u); return false; }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+struct DpFlags {
+  int rank, world;
+  uint32_t* flags[ADER_DP_MAX_RANKS];
+};
+
+struct DpArgs {
+  int rank, world;
+  float* theta[ADER_DP_MAX_RANKS];
+  const float* grad[ADER_DP_MAX_RANKS];
+  uint32_t* flags[ADER_DP_MAX_RANKS];
+  float *m, *v;
+  int* state;
+  long long n_table, table_lo, dense_lo, n_total;     // index space in elements (all even)
+  long long lo2, hi2;                                 // owned slice in float2 units
+  float lr, beta1, beta2, eps, ewc_lambda;
+  const float *fisher, *theta_star;
+};
+
+__global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
+  __shared__ float s_lr;
+  __shared__ uint32_t s_epoch;
+  uint32_t* myf = a.flags[a.rank];
+  if (threadIdx.x == 0) {
+    s_epoch = ld_acquire_sys(myf + F_EPOCH);
+    const int t = a.state[0] + 1;
+    const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.beta2, (double)t)) / (1.0 - pow((double)a.beta1, (double)t));
+    s_lr = (float)lr_t;
+  }
+  __syncthreads();
+  const uint32_t e = s_epoch;
+
+  const float lr_t = s_lr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i2 = a.lo2 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < a.hi2; i2 += stride) {
+    const long long i = i2 * 2;
+    const long long el = (i < a.n_table) ? a.table_lo + i : a.dense_lo + (i - a.n_table);
+    float2 g = make_float2(0.f, 0.f);
+    float2 gr[ADER_DP_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
+      if (r < a.world) gr[r] = ld_cv2(a.grad[r] + el);             // all peer loads in flight together
+#pragma unroll
+    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
+      if (r < a.world) { g.x = __fadd_rn(g.x, gr[r].x); g.y = __fadd_rn(g.y, gr[r].y); }
+    float2 th = *reinterpret_cast<const float2*>(a.theta[a.rank] + el);
+    float2 m = *reinterpret_cast<const float2*>(a.m + el);
+    float2 v = *reinterpret_cast<const float2*>(a.v + el);
+    float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
+    if (a.ewc_lambda != 0.f) {
+      f = *reinterpret_cast<const float2*>(a.fisher + el);
+      ts = *reinterpret_cast<const float2*>(a.theta_star + el);
+    }
+    adam_update_elem(g.x, th.x, m.x, v.x, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
+    adam_update_elem(g.y, th.y, m.y, v.y, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
+    *reinterpret_cast<float2*>(a.m + el) = m;
+    *reinterpret_cast<float2*>(a.v + el) = v;
+#pragma unroll
+    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
+      if (r < a.world) *reinterpret_cast<float2*>(a.theta[r] + el) = th;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                            // this CTA's peer stores are performed before its ticket
+    const uint32_t done = atomicAdd(myf + F_DONE, 1u);
+    if (done == gridDim.x - 1) {                       // last CTA: publish B and advance the local state
+      myf[F_DONE] = 0u;
+      a.state[0] = a.state[0] + 1;
+      a.state[1] = __float_as_int(lr_t);
+      st_release_sys(myf + F_EPOCH, e + 2);
+      __threadfence_system();
+      for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, e + 2);
+    }
+  }
+}
+
+// A: stream order puts every gradient write of this rank before this kernel
+__global__ void k_dp_arrive(DpFlags a) {
+  uint32_t* myf = a.flags[a.rank];
+  const uint32_t e = ld_acquire_sys(myf + F_EPOCH);
+  if ((int)threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + a.rank, e + 1);
+    wait_flag(myf + threadIdx.x, e + 1, myf + F_ERR);
+  }
+}
+
+__global__ void k_dp_wait(int rank, int world, uint32_t* myf) {
+  const uint32_t e = ld_acquire_sys(myf + F_EPOCH);
+  if ((int)threadIdx.x < world) wait_flag(myf + threadIdx.x, e, myf + F_ERR);
+}
+
+}  // namespace dp
+}  // namespace ader
+
+using namespace ader;
+using namespace ader::dp;
+
+static int check_comm(const AderDpComm* c) {
+  ADER_CHECK_ARG(c, "dp: comm is NULL");
+  ADER_CHECK_ARG(c->world >= 1 && c->world <= ADER_DP_MAX_RANKS && c->rank >= 0 && c->rank < c->world, "dp: bad rank %d / world %d", c->rank, c->world);
+  for (int r = 0; r < c->world; ++r) ADER_CHECK_ARG(c->theta[r] && c->grad[r] && c->flags[r], "dp: NULL pointer for rank %d", r);
+  return 0;
+}
+
+extern "C" int32_t ader_dp_wait(const AderDpComm* c, void* stream) {
+  if (int e = check_comm(c)) return e;
+  k_dp_wait<<<1, 32, 0, (cudaStream_t)stream>>>(c->rank, c->world, c->flags[c->rank]);
+  ADER_CHECK_LAUNCH("dp_wait");
+  return 0;
+}
+
+extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, float* adam_m, float* adam_v, int32_t* state,
+                                     const AderAdamArgs* a, void* stream) {
+  if (int e = check_model(m)) return e;
+  if (int e = check_comm(c)) return e;
+  ADER_CHECK_ARG(adam_m && adam_v && state && a, "dp_adam_step: NULL pointer");
+  ADER_CHECK_ARG(a->V >= 1 && a->V < m->v_tab, "dp_adam_step: max_item %d outside table", a->V);
+  ADER_CHECK_ARG(a->ewc_lambda == 0.f || (a->fisher && a->theta_star), "dp_adam_step: EWC needs fisher and theta_star");
+  const Layout l = make_layout(m);
+  DpArgs d;
+  d.rank = c->rank; d.world = c->world;
+  for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) {
+    d.theta[r] = r < c->world ? c->theta[r] : nullptr;
+    d.grad[r] = r < c->world ? c->grad[r] : nullptr;
+    d.flags[r] = r < c->world ? c->flags[r] : nullptr;
+  }
+  d.m = adam_m; d.v = adam_v; d.state = state;
+  d.n_table = (long long)a->V * m->d; d.table_lo = m->d; d.dense_lo = l.off_pos; d.n_total = d.n_table + l.dense_count();
+  const long long n2 = d.n_total / 2;                 // both ranges are even (d is even)
+  d.lo2 = n2 * c->rank / c->world;
+  d.hi2 = n2 * (c->rank + 1) / c->world;
+  d.lr = a->lr; d.beta1 = a->beta1; d.beta2 = a->beta2; d.eps = a->eps; d.ewc_lambda = a->ewc_lambda;
+  d.fisher = a->fisher; d.theta_star = a->theta_star;
+  const long long mine = d.hi2 - d.lo2;
+  int grid = cdiv(mine > 0 ? mine : 1, 256);
+  if (grid > 148 * 4) grid = 148 * 4;                 // grid-stride over the owned slice, whole waves of the 148 SMs
+  DpFlags fl;
+  fl.rank = c->rank; fl.world = c->world;
+  for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
+  k_dp_arrive<<<1, 32, 0, (cudaStream_t)stream>>>(fl);
+  k_dp_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
+  ADER_CHECK_LAUNCH("dp_adam_step");
+  return 0;
+}
+
+extern "C" int32_t ader_dp_status(const AderDpComm* c, int32_t* err_out, uint32_t* epoch_out) {
+  if (int e = check_comm(c)) return e;
+  uint32_t w[3] = {0, 0, 0};
+  if (cudaMemcpy(w, c->flags[c->rank] + F_EPOCH, sizeof(w), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(-3, "dp_status: %s", cudaGetErrorString(cudaGetLastError()));
+  if (epoch_out) *epoch_out = w[0];
+  if (err_out) *err_out = (int32_t)w[2];
+  return 0;
+}
+
+// ---- CUDA IPC plumbing: map another process's device allocation (one process per GPU) -------------------
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+
+extern "C" int32_t ader_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset) {
+  ADER_CHECK_ARG(dev_ptr && handle64 && offset, "ipc_export: NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+    return fail(-3, "ipc_export: cuMemGetAddressRange unavailable");
+  unsigned long long base = 0; size_t size = 0;
+  if (((cuMemGetAddressRange_t)fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0)
+    return fail(-3, "ipc_export: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(-3, "ipc_export: %s", cudaGetErrorString(e)); }
+  memcpy(handle64, &h, 64);
+  *offset = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return 0;
+}
+
+extern "C" int32_t ader_ipc_open(const void* handle64, void** base_ptr) {
+  ADER_CHECK_ARG(handle64 && base_ptr, "ipc_open: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(base_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(-3, "ipc_open: %s", cudaGetErrorString(e)); }
+  return 0;
+}
+
+extern "C" int32_t ader_ipc_close(void* base_ptr) {
+  if (!base_ptr) return 0;
+  cudaError_t e = cudaIpcCloseMemHandle(base_ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(-3, "ipc_close: %s", cudaGetErrorString(e)); }
+  return 0;
+}

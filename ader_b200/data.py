@@ -275,8 +275,9 @@ def load_exemplars(exemplar_pre) -> "ExemplarSet":                              
 # ---- util.py:276-350 -----------------------------------------------------------------------------
 class Evaluator:
     def __init__(self, data: list, is_subseq: bool, maxlen: int, batch_size: int, max_item: int, mode: str,
-                 model, sess=None, chunk_rows: int = 8192):
+                 model, sess=None, chunk_rows: int = 8192, dp=None):
         self.max_item, self.model, self.mode = max_item, model, mode
+        self.dp = dp                      # (rank, world): rows of a pass are sharded over the ranks, ranks all-gathered
         self.ranks: List[int] = []
         self.desc = "Validating epoch " if mode == "valid" else "Testing epoch "
         self.evaluate_sampler = Sampler(data, maxlen, batch_size, is_subseq=is_subseq)
@@ -292,12 +293,39 @@ class Evaluator:
         ids, label, n_in = s.packed()
         ranks = []
         tops = []
+        n_all = len(order)
+        if self.dp is not None and self.dp[1] > 1:          # evaluation rows are independent -> shard them
+            from .dist import shard_range
+            lo_r, hi_r = shard_range(n_all, self.dp[0], self.dp[1])
+            order = order[lo_r:hi_r]
         for lo in range(0, len(order), self.chunk_rows):
             idx = order[lo:lo + self.chunk_rows]
             r, items, _ = self.model.rank_topk(ids[idx], label[idx], self.max_item, k, n_tokens=int(n_in[idx].sum()))
             ranks.append(r)
             tops.append(items)
-        if ranks:
+        if self.dp is not None and self.dp[1] > 1:
+            import torch.distributed as dist
+            from .dist import shard_range
+            world = self.dp[1]
+            sizes = [shard_range(n_all, r, world)[1] - shard_range(n_all, r, world)[0] for r in range(world)]
+            cap = max(max(sizes), 1)
+            dev = self.model.device
+            mine = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+            if ranks:
+                r_loc = torch.cat(ranks)
+                mine[:r_loc.numel()] = r_loc
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            ranks = [p[:n] for p, n in zip(parts, sizes)]
+            if k > 0:
+                mine_t = torch.zeros((cap, k), dtype=torch.int32, device=dev)
+                if tops:
+                    t_loc = torch.cat(tops)
+                    mine_t[:t_loc.shape[0]] = t_loc
+                parts_t = [torch.empty_like(mine_t) for _ in range(world)]
+                dist.all_gather(parts_t, mine_t)
+                tops = [p[:n] for p, n in zip(parts_t, sizes)]
+        if ranks and n_all > 0:
             self.ranks = torch.cat(ranks).cpu().numpy().tolist()
             self.topk = torch.cat(tops) if k > 0 else None
         else:

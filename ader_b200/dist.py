@@ -1,12 +1,20 @@
 """Multi-GPU plumbing for the two ways the path shards; torch.distributed is plumbing only.
 
 * Data parallel (configs 1-4): every rank runs the step on its own rows with the GLOBAL mean
-  denominators (AderLossArgs.n_train_global / n_ex_global), then ONE all-reduce (sum) of the flat
-  gradient; Adam is identical on every rank.  Row order inside a rank stays [train; exemplar].
+  denominators (AderLossArgs.n_train_global / n_ex_global); the gradients of the ranks are SUMMED.
+  Two interchangeable back ends behind ``Ader.dp``:
+    - ``PeerComm`` (default): theta / grad / a flag block of every rank are mapped into every process
+      (CUDA IPC over NVLink) and ONE kernel per step (csrc/dp.cu, ader_dp_adam_step) does
+      reduce-scatter by peer loads -> TF1 Adam on the owned slice -> all-gather by peer stores;
+      the optimiser state of a slice is only touched by its owner.  No host in the loop, graph-capturable.
+    - ``NcclComm``: all-reduce (sum) of the live gradient ranges (table rows 1..max_item and the dense
+      parameters: rows above max_item are identically zero), then the ordinary Adam on every rank.
+  Row order inside a rank stays [train; exemplar].
 * Vocab parallel (config 5, 1 M items): the table rows (and Adam state) are sharded by vocabulary
-  range; each rank produces per-row (max, sumexp) partials over its columns -- exactly what
-  k_tc_logits<FWD> emits per vocabulary chunk -- and the log-sum-exp is merged with an all-reduce(max)
-  + all-reduce(sum).  `merge_lse` is that merge; the kernel wiring is the next round's work.
+  range; each rank produces per-row (max, sumexp, label logit, KD dot) partials over its columns --
+  exactly what k_tc_logits<FWD> emits per vocabulary chunk -- and the log-sum-exp is merged with an
+  all-reduce(max) + all-reduce(sum) (``VocabParallelLoss``: ader_loss_tc_vp_fwd / _bwd on the shard,
+  partial d_rep all-reduced).
 """
 from __future__ import annotations
 
@@ -51,16 +59,135 @@ def merge_lse(local_max: torch.Tensor, local_sumexp: torch.Tensor, group=None) -
     return gmax + torch.log(scaled)
 
 
-class DataParallel:
-    """Wrap an `Ader` / `Ewc` model: shard each step's rows over the ranks, sum the flat gradient."""
+class NcclComm:
+    """Gradient all-reduce over NCCL + replicated Adam (fallback back end, and the one gloo tests drive on CPU)."""
+
+    kind = "nccl"
 
     def __init__(self, model, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def begin_step(self, model):
+        pass
+
+    def apply(self, model, max_item: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None):
+        from . import ops
+        d = model.hp.hidden_units
+        g = model.grad
+        # live ranges only: rows > max_item of the table never receive gradient (28 % of the buffer at the bench shape)
+        dist.all_reduce(g[d:(max_item + 1) * d], op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(g[model.layout.offset(1):], op=dist.ReduceOp.SUM, group=self.group)
+        ops.adam_step(model.ms, model.theta, model.adam_m, model.adam_v, g, model.adam_state, max_item, lr,
+                      ewc_lambda, fisher, theta_star)
+
+    def check(self):
+        pass
+
+
+class PeerComm:
+    """Peer-memory back end: see csrc/dp.cu.  `peers` = list of (theta_ptr, grad_ptr, flags_ptr) per rank."""
+
+    kind = "p2p"
+
+    def __init__(self, model, rank: int, world: int, peers, flags: torch.Tensor, opened=()):
+        from . import ops
+        self.rank, self.world = rank, world
+        self.flags = flags                                   # keep the local flag block alive
+        self._opened = list(opened)                          # IPC mappings to close
+        self.comm = ops.dp_comm(rank, world, [p[0] for p in peers], [p[1] for p in peers], [p[2] for p in peers])
+        self._ops = ops
+
+    @classmethod
+    def from_process_group(cls, model, group=None):
+        """Exchange CUDA IPC handles of (theta, grad, flags) through the process group and map the peers."""
+        from . import ops
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world > ops._lib.DP_MAX_RANKS:
+            raise ValueError("PeerComm supports up to %d ranks" % ops._lib.DP_MAX_RANKS)
+        flags = torch.zeros(ops._lib.DP_FLAG_WORDS, dtype=torch.int32, device=model.device)
+        torch.cuda.synchronize(model.device)
+        mine = [ops.ipc_export(t) for t in (model.theta, model.grad, flags)]
+        allh = [None] * world
+        dist.all_gather_object(allh, mine, group=group)
+        opened = {}
+        peers = []
+        for r in range(world):
+            if r == rank:
+                peers.append((model.theta.data_ptr(), model.grad.data_ptr(), flags.data_ptr()))
+                continue
+            ptrs = []
+            for handle, off in allh[r]:
+                if handle not in opened:                      # two tensors may live in one allocation: map it once
+                    opened[handle] = ops.ipc_open(handle)
+                ptrs.append(opened[handle] + off)
+            peers.append(tuple(ptrs))
+        dist.barrier(group=group)                             # every rank has mapped every flag block before the first step
+        return cls(model, rank, world, peers, flags, opened.values())
+
+    def begin_step(self, model):
+        self._ops.dp_wait(self.comm)
+
+    def apply(self, model, max_item: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None):
+        self._ops.dp_adam_step(model.ms, self.comm, model.adam_m, model.adam_v, model.adam_state, max_item, lr,
+                               ewc_lambda, fisher, theta_star)
+
+    def check(self):
+        err, _ = self._ops.dp_status(self.comm)
+        if err:
+            raise self._ops._lib.AderError("data-parallel peer wait timed out (a rank did not reach the step)")
+
+    def close(self):
+        for b in self._opened:
+            try:
+                self._ops.ipc_close(b)
+            except Exception:
+                pass
+        self._opened = []
+
+
+def local_peer_group(models):
+    """Emulated ranks inside ONE process (tests on a single GPU): every model replica becomes a rank whose peers are
+    the other replicas' buffers.  Returns the PeerComm list (also installed as ``model.dp``)."""
+    from . import ops
+    world = len(models)
+    flags = [torch.zeros(ops._lib.DP_FLAG_WORDS, dtype=torch.int32, device=m.device) for m in models]
+    peers = [(m.theta.data_ptr(), m.grad.data_ptr(), f.data_ptr()) for m, f in zip(models, flags)]
+    comms = []
+    for r, m in enumerate(models):
+        m.dp = PeerComm(m, r, world, peers, flags[r])
+        m.dp._all_flags = flags
+        comms.append(m.dp)
+    return comms
+
+
+def make_comm(model, group=None, backend: str = None):
+    """Pick the data-parallel back end: ADER_B200_DP=p2p|nccl (default p2p, NCCL when the peer mapping fails)."""
+    backend = backend or os.environ.get("ADER_B200_DP", "p2p")
+    if backend == "p2p" and model.device.type == "cuda":
+        ok = torch.ones(1, device=model.device)
+        comm = None
+        try:
+            comm = PeerComm.from_process_group(model, group)
+        except Exception as ex:      # noqa: BLE001 -- e.g. IPC not permitted in this container: every rank must agree
+            import sys
+            sys.stderr.write("[ader_b200] peer-memory data parallel unavailable on rank %d (%r); using NCCL\n" % (dist.get_rank(group), ex))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) > 0:
+            return comm
+        if comm is not None:
+            comm.close()
+    return NcclComm(model, group)
+
+
+class DataParallel:
+    """Wrap an `Ader` / `Ewc` model: shard each step's rows over the ranks, sum the gradients (``model.dp``)."""
+
+    def __init__(self, model, group=None, backend: str = None):
         self.model, self.group = model, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        model.grad_sync = self._sync
-
-    def _sync(self):
-        dist.all_reduce(self.model.grad, op=dist.ReduceOp.SUM, group=self.group)
+        model.dp = make_comm(model, group, backend)
 
     def train_step(self, seq, pos, max_item, lr=None, dropout_rate=None, exemplar_logits=None, exemplar_pos=None,
                    teacher_rows=None):
@@ -84,6 +211,7 @@ class DataParallel:
         m = self.model
         m.global_counts = (n_train, n_ex)
         loss = m.train_step(seq_l, pos[tl:th], max_item, lr, dropout_rate, **kw)
+        loss = loss.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss
 

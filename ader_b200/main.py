@@ -73,6 +73,10 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     p.add_argument("--cache_dir", default=None, type=str)
     p.add_argument("--step_impl", default=None, choices=["dag", "serial", "groups"], type=str)   # how a tc train step is issued (model.py)
     p.add_argument("--graph", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))  # CUDA-graph train step
+    # data parallel under torchrun (one process per GPU).  Every rank runs the same host protocol with the same
+    # seeds (identical batches, splits, exemplar sets); a step's train rows and exemplar rows are split over the ranks,
+    # losses use the global-mean denominators, gradients are summed (ader_b200/dist.py), evaluation rows are sharded.
+    p.add_argument("--dp", default=False, type=lambda v: str(v).lower() not in ("0", "false", "no"))
     return p
 
 
@@ -98,6 +102,8 @@ class PeriodTrainer:
         self._geom_seen = {}
         self._graph_off = False
         self.n_eager = 0                # steps issued launch by launch (rare batch geometry / no graph)
+        # data parallel: this rank's shard of every batch (train rows and exemplar rows split separately, main.py:229 order kept)
+        self.rank, self.world = getattr(args, "dp_rank", 0), getattr(args, "dp_world", 1)
 
     MAX_GEOM = 8
 
@@ -113,8 +119,13 @@ class PeriodTrainer:
             out["%d+%d" % (nt, ne)] = dict(sorted(g.use_count.items()))
         return out
 
+    def _shard(self, n_train: int, n_ex: int):
+        from .dist import shard_rows
+        return shard_rows(n_train, n_ex, self.rank, self.world)
+
     def _graph(self, n_train: int, n_ex: int):
-        """GraphStep for this batch geometry (ader_b200/graph.py), built on demand; None = run the step eagerly."""
+        """GraphStep for this (global) batch geometry (ader_b200/graph.py), built on demand; None = run the step eagerly.
+        Data parallel: the decision depends on global quantities only, so every rank takes the same branch."""
         key = (n_train, n_ex)
         gs = self.gs_map.get(key)
         if gs is not None:
@@ -122,6 +133,8 @@ class PeriodTrainer:
         m, args = self.model, self.args
         if self._graph_off or not getattr(args, "graph", True):
             return None
+        if self.world > 1 and (n_train < self.world or (self.es is not None and n_ex < self.world)):
+            return None                 # a rank would be left without rows: rare tail batch, eager on every rank
         if m.encoder_impl != "tc" and args.dropout_rate > 0:
             self._graph_off = True
             return None
@@ -141,6 +154,10 @@ class PeriodTrainer:
                 self._graph_off = True   # host-resident teacher lists (reference feed): eager path
                 return None
             e_ids = self.e_ids
+        (tl, th), (el, eh) = self._shard(n_train, n_ex)
+        if self.world > 1:
+            m.global_counts = (n_train, n_ex)       # baked into the captured loss arguments
+        n_train, n_ex = th - tl, eh - el
         mean_tok = n_train * float(np.mean(self.t_nin)) + (n_ex * float(np.mean(self.e_nin)) if self.es is not None else 0.0)
         caps = [int(mean_tok * f) + 64 for f in (1.1, 1.3, 1.7)]
         gs = m.graph_step(n_train, n_ex, self.max_item, args.lr, args.dropout_rate, teacher=teacher,
@@ -160,50 +177,35 @@ class PeriodTrainer:
     def _step(self):
         m, dev, L = self.model, self.model.device, self.model.hp.maxlen
         ti = self.ts.next_indices()
-        n_tok = int(self.t_nin[ti].sum())
-        if self.es is None:
-            if len(ti) > 0:
-                gs = self._graph(len(ti), 0)
-                if gs is not None:
-                    self.rows_seen += len(ti)
-                    return gs.run_indices(ti, None, n_tok)
-            self.n_eager += 1                                    # rare batch size / no graph
-            ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
-            ids = torch.empty((len(ti), L), dtype=torch.int32, device=dev)
-            ops.gather_rows_i32(self.t_ids, ti_d, ids)
-            pos = self.t_lab[ti_d.long()]
-            loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
-            self.rows_seen += len(ti)
-            return loss
-        ei = self.es.next_indices()
-        n_tok += int(self.e_nin[ei].sum())
-        if len(ti) > 0 and len(ei) > 0:
-            gs = self._graph(len(ti), len(ei))
-            if gs is not None:
-                self.rows_seen += len(ti) + len(ei)
-                return gs.run_indices(ti, ei, n_tok)
-        self.n_eager += 1
+        ei = self.es.next_indices() if self.es is not None else np.zeros(0, np.int64)
+        gs = self._graph(len(ti), len(ei)) if (len(ti) > 0 and (self.es is None or len(ei) > 0)) else None
+        self.rows_seen += len(ti) + len(ei)                      # rows of the whole step (all ranks)
+        if self.world > 1:                                       # keep this rank's rows; the means stay global
+            m.global_counts = (len(ti), len(ei))
+            (tl, th), (el, eh) = self._shard(len(ti), len(ei))
+            ti, ei = ti[tl:th], ei[el:eh]
+        n_tok = int(self.t_nin[ti].sum()) + (int(self.e_nin[ei].sum()) if self.es is not None else 0)
+        if gs is not None:
+            return gs.run_indices(ti, ei if self.es is not None else None, n_tok)
+        self.n_eager += 1                                        # rare batch geometry / no graph
         ti_d = torch.from_numpy(ti.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
-        ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         ids = torch.empty((len(ti) + len(ei), L), dtype=torch.int32, device=dev)
         ops.gather_rows_i32(self.t_ids, ti_d, ids[:len(ti)])
+        pos = self.t_lab[ti_d.long()]
+        if self.es is None:
+            return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
+        ei_d = torch.from_numpy(ei.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
         if len(ei):
             ops.gather_rows_i32(self.e_ids, ei_d, ids[len(ti):])
-        pos = self.t_lab[ti_d.long()]
         if m.disable_distillation:
-            loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
+            return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
                                 exemplar_pos=self.e_lab[ei_d.long()], n_tokens=n_tok)
-        else:
-            if getattr(self.es, "teacher", None) is not None:
-                rows = torch.as_tensor(np.asarray([self.es.logits[i] for i in ei], dtype=np.int32)).to(dev)
-                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
-                                    exemplar_logits=self.es.teacher, teacher_rows=rows, n_tokens=n_tok)
-            else:
-                lg = np.asarray([self.es.logits[i] for i in ei], dtype=np.float32)
-                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
-                                    exemplar_logits=lg, n_tokens=n_tok)
-        self.rows_seen += len(ti) + len(ei)
-        return loss
+        if getattr(self.es, "teacher", None) is not None:
+            rows = torch.as_tensor(np.asarray([self.es.logits[i] for i in ei], dtype=np.int32)).to(dev)
+            return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate,
+                                exemplar_logits=self.es.teacher, teacher_rows=rows, n_tokens=n_tok)
+        lg = np.asarray([self.es.logits[i] for i in ei], dtype=np.float32)
+        return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_logits=lg, n_tokens=n_tok)
 
 
 # ---- per-period checkpoint -------------------------------------------------------------------
@@ -267,7 +269,17 @@ def run(args) -> dict:
     os.makedirs(res_dir, exist_ok=True)
     ckpt_path = os.path.join(res_dir, CKPT_NAME)
     resuming = bool(getattr(args, "resume", False)) and os.path.exists(ckpt_path)
-    logs = open(os.path.join(res_dir, "Training_logs.txt"), mode="a" if resuming else "w")
+    # data parallel: one process per GPU under torchrun; rank 0 owns the log and the checkpoint
+    args.dp_rank, args.dp_world = 0, 1
+    if getattr(args, "dp", False) and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        args.device_num = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(args.device_num)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", args.device_num))
+        args.dp_rank, args.dp_world = dist.get_rank(), dist.get_world_size()
+    lead = args.dp_rank == 0
+    logs = open(os.path.join(res_dir, "Training_logs.txt") if lead else os.devnull, mode="a" if resuming else "w")
     if not resuming:
         logs.write("\n".join([str(k) + "," + str(v) for k, v in sorted(vars(args).items(), key=lambda x: x[0])]))
 
@@ -281,6 +293,14 @@ def run(args) -> dict:
         raise ValueError("Invalid dataset name")
     args.dropout_rate = 0 if (args.ewc or args.finetune) else args.dropout_rate      # main.py:141
     model = Ader(item_num, args) if not args.ewc else Ewc(item_num, args)
+    dp = None
+    if args.dp_world > 1:
+        from .dist import make_comm
+        model.dp = make_comm(model)
+        dp = (args.dp_rank, args.dp_world)
+        info = "Data parallel: %d ranks, gradient back end %s" % (args.dp_world, model.dp.kind)
+        print(info) if lead else None
+        logs.write("\n" + info + "\n")
 
     periods = get_periods(dataloader.path)
     if args.max_periods:
@@ -378,7 +398,7 @@ def run(args) -> dict:
                 model.variables_prev = model.snapshot_variables()
                 rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
                 model.compute_fisher(None, rnd, 50, max_item)
-            valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None)
+            valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None, dp=dp)
             info = valid_evaluator.evaluate(epoch)
             logs.write(info + "\n")
             performance = valid_evaluator.results()[1]
@@ -393,7 +413,7 @@ def run(args) -> dict:
                 best_performance = performance
                 ckpt = {(period, epoch): model.state_dict()}
         model.load_state_dict(ckpt[(period, best_epoch)])      # main.py:283
-        test_evaluator = Evaluator(test_sess, False, args.maxlen, args.test_batch, max_item, "test", model, None)
+        test_evaluator = Evaluator(test_sess, False, args.maxlen, args.test_batch, max_item, "test", model, None, dp=dp)
         info = test_evaluator.evaluate(best_epoch)
         logs.write(info + "\n")
         r = test_evaluator.results()
@@ -439,7 +459,7 @@ def run(args) -> dict:
             model.variables_prev = model.snapshot_variables()
             rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
             model.compute_fisher(None, rnd, 50, max_item)
-        if getattr(args, "checkpoint", True):
+        if getattr(args, "checkpoint", True) and lead:
             save_period_checkpoint(ckpt_path, period, model, dataloader, fast_exemplar,
                                    {"best_epoch": best_epoch, "item_num_prev": item_num_prev, "stop_counter": stop_counter,
                                     "metrics": metrics, "stats": stats})
@@ -455,12 +475,21 @@ def run(args) -> dict:
     logs.write("Total time: %.2f minutes\nDone." % minutes)
     logs.close()
     print("Done.")
+    if model.dp is not None:
+        torch.cuda.synchronize()
+        model.dp.check()
     return {"average": avg, "per_period": metrics, "throughput": stats, "minutes": minutes, "trace": trace, "model": model}
 
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    return run(args)
+    out = run(args)
+    if args.dp_world > 1:
+        # leave without tearing NCCL down: destroy_process_group() with live CUDA graphs that hold NCCL kernels can wedge
+        import sys
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+    return out
 
 
 if __name__ == "__main__":

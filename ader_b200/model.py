@@ -68,7 +68,8 @@ class Ader:
         self.disable_distillation = bool(getattr(args, "disable_distillation", False))
         self.mode = self.VANILLA
         self.lambda_ = 0.0
-        self.grad_sync = None
+        self.grad_sync = None           # optional callable run between backward and the optimiser (legacy hook)
+        self.dp = None                  # data parallel back end (ader_b200.dist.PeerComm / NcclComm): sums gradients over ranks
         self.global_counts = None       # data parallel: (n_train, n_ex) over all ranks -> global means
         self.loss_impl = getattr(args, "loss_impl", "tc")   # "tc": tcgen05 fused logits+CE+KD; "exact": fp32
         # encoder: "tc" = fused bf16 tensor-core kernels, "exact" = fp32.  Training uses encoder_impl; inference
@@ -197,7 +198,7 @@ class Ader:
             rep = torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
             d_rep = torch.empty_like(rep)
             self._opt_applied = False
-            if _opt is not None and self.grad_sync is None:
+            if _opt is not None and self.grad_sync is None and self.dp is None:
                 # one GPU: the optimiser joins the DAG (table rows right behind the scatter, dense parameters behind
                 # their partial reduction)
                 V_, lr_, lam_, fis_, star_ = _opt
@@ -249,9 +250,14 @@ class Ader:
         lr = self.args.lr if lr is None else lr
         p = self.args.dropout_rate if dropout_rate is None else dropout_rate
         self._opt_applied = False
+        if self.dp is not None:          # peer back end: every rank has finished the previous update (first launch of the step)
+            self.dp.begin_step(self)
         loss = self.loss_and_grad(seq, pos, max_item, exemplar_logits, exemplar_pos, teacher_rows, p, n_tokens,
                                   _device_step=_device_step, _opt=self._opt_args(max_item, lr))
         if self._opt_applied:
+            self.global_step += 1
+        elif self.dp is not None:        # gradients summed over the ranks + TF1 Adam (one kernel over peer memory, or NCCL + Adam)
+            self.dp.apply(self, *self._opt_args(max_item, lr))
             self.global_step += 1
         else:
             self.apply_gradients(max_item, lr)
@@ -304,13 +310,21 @@ class Ader:
         return {"theta": self.theta.clone(), "adam_m": self.adam_m.clone(), "adam_v": self.adam_v.clone(),
                 "adam_state": self.adam_state.clone(), "global_step": self.global_step}
 
+    def _dp_quiesce(self):
+        """Peer back end: other ranks store into this replica's theta during their update; wait (stream-ordered) until
+        every rank has finished the last one before the host rewrites theta."""
+        if self.dp is not None:
+            self.dp.begin_step(self)
+
     def load_state_dict(self, sd):
+        self._dp_quiesce()
         self.theta.copy_(sd["theta"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"])
         self.adam_state.copy_(sd["adam_state"]); self.global_step = int(sd["global_step"])
 
     def reinitialize(self, seed: Optional[int] = None):
         """sess.run(tf.global_variables_initializer()) (main.py:213)."""
         s = self.seed if seed is None else seed
+        self._dp_quiesce()
         self.theta.copy_(torch.from_numpy(self.layout.init_flat(s)))
         self.adam_m.zero_(); self.adam_v.zero_(); self.adam_state.zero_(); self.global_step = 0
 

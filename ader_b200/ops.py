@@ -206,6 +206,55 @@ def adam_step(ms: AderModel, theta, m, v, grad, state, V: int, lr: float, ewc_la
                                      _stream()), "adam_step")
 
 
+# ---- data parallel over peer memory (csrc/dp.cu) -------------------------------------------------------
+def dp_comm(rank: int, world: int, theta_ptrs, grad_ptrs, flag_ptrs) -> "_lib.AderDpComm":
+    c = _lib.AderDpComm()
+    c.rank, c.world = rank, world
+    for r in range(world):
+        c.theta[r], c.grad[r], c.flags[r] = int(theta_ptrs[r]), int(grad_ptrs[r]), int(flag_ptrs[r])
+    return c
+
+
+def dp_wait(comm):
+    check(_lib.load().ader_dp_wait(C.byref(comm), _stream()), "dp_wait")
+
+
+def dp_adam_step(ms: AderModel, comm, m, v, state, V: int, lr: float, ewc_lambda: float = 0.0, fisher=None, theta_star=None,
+                 beta1=0.9, beta2=0.999, eps=1e-8):
+    _require_cuda(m, v, state, fisher, theta_star)
+    a = AderAdamArgs(lr, beta1, beta2, eps, V, ewc_lambda,
+                     fisher.data_ptr() if fisher is not None else None,
+                     theta_star.data_ptr() if theta_star is not None else None)
+    check(_lib.load().ader_dp_adam_step(C.byref(ms), C.byref(comm), _ptr(m), _ptr(v), _ptr(state), C.byref(a), _stream()),
+          "dp_adam_step")
+
+
+def dp_status(comm):
+    err, ep = C.c_int32(0), C.c_uint32(0)
+    check(_lib.load().ader_dp_status(C.byref(comm), C.byref(err), C.byref(ep)), "dp_status")
+    return int(err.value), int(ep.value)
+
+
+def ipc_export(t: torch.Tensor):
+    """(64-byte handle, byte offset) of the device allocation behind tensor `t` (another process maps it with ipc_open)."""
+    _require_cuda(t)
+    h = (C.c_ubyte * 64)()
+    off = C.c_int64(0)
+    check(_lib.load().ader_ipc_export(_ptr(t), h, C.byref(off)), "ipc_export")
+    return bytes(h), int(off.value)
+
+
+def ipc_open(handle: bytes) -> int:
+    base = C.c_void_p(0)
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    check(_lib.load().ader_ipc_open(buf, C.byref(base)), "ipc_open")
+    return int(base.value)
+
+
+def ipc_close(base: int):
+    check(_lib.load().ader_ipc_close(C.c_void_p(base)), "ipc_close")
+
+
 def eval_ws_bytes(ms: AderModel, M: int, V: int) -> int:
     n = _lib.load().ader_eval_ws_bytes(C.byref(ms), M, V)
     if n == 0:

@@ -9,8 +9,10 @@ shipped split), synthetic sessions with the YOOCHOOSE length histogr
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 (under torchrun): data parallel, one rank per GPU, per-rank batch fixed (weak scaling), one
-NCCL all-reduce (avg) of the flat gradient per step.  `--impl reference` times the reference's own
+N > 1 (under torchrun): data parallel, one rank per GPU, per-rank batch fixed (weak scaling); the gradients
+are summed and Adam applied by one kernel over NVLink peer memory (csrc/dp.cu; ADER_B200_DP=nccl selects the
+NCCL all-reduce + replicated Adam instead).  The same run also times the reference's global batch split over
+the ranks (strong scaling, `strong_scaling` in the JSON line).  `--impl reference` times the reference's own
 CPU implementation of the same step (its torch-CPU restatement under oracle/, TensorFlow is not
 installable here) on the host cores.
 """
@@ -109,6 +111,11 @@ class ClockSampler:
 def cpu_step_fn():
     import torch
     from oracle import sasrec as S
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every host core it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     hp = S.Hyper(WL["item_num"])
     params = S.init_params(hp, 0)
     rng = np.random.RandomState(1)
@@ -185,37 +192,58 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    wd = threading.Timer(900.0, lambda: os._exit(3))      # watchdog: a wedged collective must not hold the box
+    t_boot = time.time()
+
+    def crumb(stage):                  # per-rank breadcrumbs: a wedged multi-GPU run shows where every rank stopped
+        sys.stderr.write("[bench rank %d/%d +%.1fs] %s\n" % (rank, world, time.time() - t_boot, stage))
+        sys.stderr.flush()
+
+    def on_timeout():
+        crumb("WATCHDOG: no result after 600 s, leaving")
+        os._exit(3)
+
+    wd = threading.Timer(600.0, on_timeout)     # a wedged collective must not hold the box (the driver's own limit is 870 s)
     wd.daemon = True
     wd.start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        crumb("process group up")
     K, W = args.steps, max(args.warmup, 3)
     B, Me, V, Vp = WL["B"], WL["M_e"], WL["V"], WL["V_prev"]
     M = B + Me
 
     model = Ader(WL["item_num"], make_args(), device=dev, init_seed=0)
     model.update_loss(WL["lam"])
-    if world > 1:       # data parallel: global-mean denominators + one all-reduce (sum) of the flat gradient
-        def sync_grad():
-            dist.all_reduce(model.grad, op=dist.ReduceOp.SUM)
-        model.grad_sync = sync_grad
-        model.global_counts = (WL["B"] * world, WL["M_e"] * world)
-    rng = np.random.RandomState(100 + rank)
+    dp_kind = None
+    if world > 1:       # data parallel: global-mean denominators, gradients summed over the ranks (ader_b200/dist.py)
+        from ader_b200.dist import make_comm, shard_rows
+        model.dp = make_comm(model)
+        dp_kind = model.dp.kind
+        crumb("data-parallel back end: %s" % dp_kind)
+    # every rank builds the SAME row pools and the index streams of ALL ranks (host integers): the graph buckets below are
+    # then identical on every rank, so all ranks capture the same graphs in the same order (a rank-dependent bucket set
+    # left ranks inside NCCL graph capture while the others were already replaying: the round-1 hang at N = 8)
+    rng = np.random.RandomState(100)
     pool = 32768
     t_ids, t_lab, t_len = synth_rows(rng, pool, V)
     e_ids, e_lab, e_len = synth_rows(rng, WL["exemplars"], Vp)
     d_t_ids, d_t_lab = torch.from_numpy(t_ids).to(dev), torch.from_numpy(t_lab).to(dev)
     d_e_ids = torch.from_numpy(e_ids).to(dev)
-    gen = torch.Generator(device=dev); gen.manual_seed(5 + rank)
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
     ld_t = (Vp + 3) // 4 * 4     # rows 16-byte aligned, as ExemplarGenerator stores them
     teacher = (torch.randn((WL["exemplars"], ld_t), device=dev, generator=gen) * 2.0)[:, :Vp]   # stored exemplar logits, HBM resident
 
     nsteps = W + K
-    ti_all = [rng.randint(0, pool, B).astype(np.int32) for _ in range(nsteps)]
-    ei_all = [rng.randint(0, WL["exemplars"], Me).astype(np.int32) for _ in range(nsteps)]
+    ntok_all = []
+    for r in range(world):
+        rr = np.random.RandomState(1000 + r)
+        ti_r = [rr.randint(0, pool, B).astype(np.int32) for _ in range(nsteps)]
+        ei_r = [rr.randint(0, WL["exemplars"], Me).astype(np.int32) for _ in range(nsteps)]
+        ntok_all += [int(t_len[a].sum() + e_len[b].sum()) for a, b in zip(ti_r, ei_r)]
+        if r == rank:
+            ti_all, ei_all = ti_r, ei_r
     ntok = [int(t_len[a].sum() + e_len[b].sum()) for a, b in zip(ti_all, ei_all)]
     d_ti = [torch.from_numpy(a).to(dev) for a in ti_all]
     d_ei = [torch.from_numpy(a).to(dev) for a in ei_all]
@@ -223,11 +251,15 @@ def gpu_arm(args):
 
     P = WL["dropout"]
     gs = None
+    d_e_row = torch.arange(WL["exemplars"], dtype=torch.int32, device=dev)      # stored teacher row of each exemplar
+    if world > 1:
+        model.global_counts = (B * world, Me * world)
     if not args.no_graph:       # the step as CUDA graphs (one per token-capacity bucket); same C-ABI calls as the eager step
-        d_e_row = torch.arange(WL["exemplars"], dtype=torch.int32, device=dev)      # stored teacher row of each exemplar
-        caps = sorted({int(-(-q // 256) * 256) for q in np.quantile(ntok, [0.5, 0.9, 0.99, 1.0])})
+        caps = sorted({int(-(-q // 256) * 256) for q in np.quantile(ntok_all, [0.5, 0.9, 0.99, 1.0])})
         gs = model.graph_step(B, Me, V, WL["lr"], P, teacher=teacher, sources=(d_t_ids, d_t_lab, d_e_ids, d_e_row), tcaps=caps)
+        crumb("graph step built, buckets %s" % (gs.tcaps,))
         gs.precapture()          # graphs are captured on first use otherwise: keep that out of the timed regions
+        crumb("graphs captured")
 
     def resident_step(i):
         if gs is not None:
@@ -305,9 +337,47 @@ def gpu_arm(args):
     h2d = M * 50 * 4 + B * 4 + Me * 4
     clock_info = clocks.stop(windows) if clocks else None
 
+    crumb("weak-scaling + e2e regions timed")
+
+    # ---- strong scaling (N > 1): the REFERENCE's global batch (B + M_e rows, the parity configuration of SURVEY 8e) split
+    # over the ranks -- train rows and exemplar rows separately, global-mean denominators -- reported beside the weak line
+    strong = None
+    if world > 1 and gs is not None:
+        (tl, th), (el, eh) = shard_rows(B, Me, rank, world)
+        rg = np.random.RandomState(999)
+        ti_g = [rg.randint(0, pool, B).astype(np.int32) for _ in range(nsteps)]
+        ei_g = [rg.randint(0, WL["exemplars"], Me).astype(np.int32) for _ in range(nsteps)]
+        nt_rank = [[int(t_len[a[slice(*shard_rows(B, Me, r, world)[0])]].sum() + e_len[b[slice(*shard_rows(B, Me, r, world)[1])]].sum())
+                    for a, b in zip(ti_g, ei_g)] for r in range(world)]
+        caps_s = sorted({int(-(-q // 128) * 128) for q in np.quantile(np.concatenate(nt_rank), [0.5, 0.9, 1.0])})
+        model.global_counts = (B, Me)
+        gss = model.graph_step(th - tl, eh - el, V, WL["lr"], P, teacher=teacher, sources=(d_t_ids, d_t_lab, d_e_ids, d_e_row), tcaps=caps_s)
+        gss.precapture(indexed=True)
+        crumb("strong-scaling graphs captured (%d + %d rows per rank)" % (th - tl, eh - el))
+        d_tis = [torch.from_numpy(a[tl:th].copy()).to(dev) for a in ti_g]
+        d_eis = [torch.from_numpy(b[el:eh].copy()).to(dev) for b in ei_g]
+        for i in range(W):
+            gss.run_indices(d_tis[i], d_eis[i], nt_rank[rank][i])
+        barrier()
+        e0.record()
+        for i in range(W, W + K):
+            gss.run_indices(d_tis[i], d_eis[i], nt_rank[rank][i])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_s = float(t.item())
+        strong = {"value": M * K / (ms_s / 1e3), "unit": "sessions/s", "ms_per_step": ms_s / K, "global_batch": M,
+                  "rows_per_rank": [th - tl, eh - el], "scaling": "strong",
+                  "note": "reference batch size kept (parity configuration): latency-bound, the all-gather of theta is on the chain"}
+        model.global_counts = (B * world, Me * world)
+        crumb("strong-scaling region timed")
+    if model.dp is not None:
+        model.dp.check()        # a timed-out peer wait would have produced garbage: fail loudly
+
     # ---- per-phase device times (CUDA events on the launching stream), averaged over the timed inputs
     phases = {}
-    reps = min(K, 50)
+    reps = min(K, 50) if world == 1 else 0      # eager single-rank launches (a lone rank must not enter the collective)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(reps)]
     for r in range(reps):
         i = W + r
@@ -321,7 +391,7 @@ def gpu_arm(args):
         evs[r][4].record()
     torch.cuda.synchronize()
     for name, a, b in (("encoder_fwd", 0, 1), ("logits_ce_kd_fwd_bwd", 1, 2), ("encoder_bwd_scatter", 2, 3), ("adam", 3, 4)):
-        phases[name] = float(np.mean([evs[r][a].elapsed_time(evs[r][b]) for r in range(reps)]))
+        phases[name] = float(np.mean([evs[r][a].elapsed_time(evs[r][b]) for r in range(reps)])) if reps else None
 
     # ---- kernel launch count + in-pipeline kernel durations (CUPTI via torch.profiler, outside the timed regions)
     launches_per_step = None
@@ -408,6 +478,8 @@ def gpu_arm(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"
         flops = 6.0 * M * 150 * V                      # fwd + bwd of the output projection, d counted as 150
         dom_ms = tc_kernels_ms or loss_group_ms or phases["logits_ce_kd_fwd_bwd"]
+        if not dom_ms:
+            raise RuntimeError("the tcgen05 loss kernels could not be timed")
         achieved = flops / (dom_ms * 1e-3) / 1e12
         traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the three launches (ncu --set full, profiles/)
         try:
@@ -432,6 +504,8 @@ def gpu_arm(args):
                 "loss_group_ms": loss_group_ms,
                 "tc_kernels_ms": tc_kernels_ms,
                 "step_impl": model.step_impl,
+                "dp_backend": dp_kind,
+                "strong_scaling": strong,
                 "roofline": {"kernel": "k_tc_logits<FWD> + <DREP> + <DE> (the three tcgen05 launches of logits+CE+KD fwd+bwd; CUDA-event "
                                        "timed graph replays of exactly these launches; the whole 13-launch group is loss_group_ms)",
                              "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

@@ -208,6 +208,36 @@ int32_t ader_fisher_accumulate(const AderModel* m, const float* grad, double* ac
 int32_t ader_fisher_finalize(const AderModel* m, const double* acc, float* fisher, int32_t V,
                              int32_t n_data, void* stream);
 
+/* ---- data parallel over NVLink peer memory --------------------------------------
+ * The reference is single-device (main.py:96,120,143: one CUDA_VISIBLE_DEVICES id, one tf.Session); a rank here is a
+ * process that runs `sess.run(train_op)` (main.py:233-256) on its shard of the step's rows with the GLOBAL mean
+ * denominators (AderLossArgs.n_*_global).  ader_dp_adam_step then replaces all-reduce(grad) + ader_adam_step by ONE
+ * kernel: rank r owns a slice of [table rows 1..V | dense parameters]; it loads that slice of every rank's gradient
+ * through peer pointers, sums in rank order, applies the TF1-Adam expression of ader_adam_step with its local m / v,
+ * and stores the new theta slice into every replica.  Cross-rank ordering uses epoch flags in peer memory (no host,
+ * graph-capturable); a wait that sees no progress for ~20 s marks the error word instead of hanging the GPU.
+ *   flags[r]: ADER_DP_FLAG_WORDS zero-initialised uint32 of rank r, mapped into every rank.
+ * ader_dp_wait must be the first launch of a step (before anything rewrites grad or reads theta): it waits until every
+ * rank has finished the previous ader_dp_adam_step.  Pointers of other processes come from ader_ipc_export/open. */
+#define ADER_DP_MAX_RANKS 16
+#define ADER_DP_FLAG_WORDS 64
+typedef struct AderDpComm {
+  int32_t   rank, world;
+  float*    theta[ADER_DP_MAX_RANKS];
+  float*    grad[ADER_DP_MAX_RANKS];
+  uint32_t* flags[ADER_DP_MAX_RANKS];
+} AderDpComm;
+int32_t ader_dp_wait(const AderDpComm* c, void* stream);
+int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, float* adam_m, float* adam_v, int32_t* state,
+                          const AderAdamArgs* a, void* stream);
+/* synchronous read of this rank's flag block: err != 0 after a timed-out wait; epoch = 2 x completed steps */
+int32_t ader_dp_status(const AderDpComm* c, int32_t* err_out, uint32_t* epoch_out);
+/* CUDA IPC: 64-byte handle of the allocation that holds dev_ptr + the byte offset of dev_ptr inside it (exporter);
+ * ader_ipc_open maps that allocation into this process and returns its base (importer adds the offset). */
+int32_t ader_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
+int32_t ader_ipc_open(const void* handle64, void** base_ptr);
+int32_t ader_ipc_close(void* base_ptr);
+
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* out[i, :] = src[idx[i], :] for int32 rows (batch assembly from the GPU-resident row matrix). */
 int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
