@@ -79,6 +79,10 @@ struct DpArgs {
   const float *fisher, *theta_star;
 };
 
+// W = upper bound of the world size (array extents in registers), U = float2 elements per thread and trip: U * W peer
+// loads of 8 bytes are in flight per thread before the first add (NVLink round trips are ~2-3 us: the link only
+// fills with megabytes outstanding).
+template <int W, int U>
 __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
   __shared__ float s_lr;
   __shared__ uint32_t s_epoch;
@@ -94,32 +98,42 @@ __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
 
   const float lr_t = s_lr;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i2 = a.lo2 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i2 < a.hi2; i2 += stride) {
-    const long long i = i2 * 2;
-    const long long el = (i < a.n_table) ? a.table_lo + i : a.dense_lo + (i - a.n_table);
-    float2 g = make_float2(0.f, 0.f);
-    float2 gr[ADER_DP_MAX_RANKS];
+  const bool ewc = a.ewc_lambda != 0.f;
+  for (long long base = a.lo2 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.hi2; base += stride * U) {
+    long long el[U];
+    float2 gr[U][W];
 #pragma unroll
-    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
-      if (r < a.world) gr[r] = ld_cv2(a.grad[r] + el);             // all peer loads in flight together
+    for (int u = 0; u < U; ++u) {
+      const long long i2 = base + (long long)u * stride;
+      const long long i = i2 * 2;
+      el[u] = (i2 < a.hi2) ? ((i < a.n_table) ? a.table_lo + i : a.dense_lo + (i - a.n_table)) : -1;
 #pragma unroll
-    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
-      if (r < a.world) { g.x = __fadd_rn(g.x, gr[r].x); g.y = __fadd_rn(g.y, gr[r].y); }
-    float2 th = *reinterpret_cast<const float2*>(a.theta[a.rank] + el);
-    float2 m = *reinterpret_cast<const float2*>(a.m + el);
-    float2 v = *reinterpret_cast<const float2*>(a.v + el);
-    float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
-    if (a.ewc_lambda != 0.f) {
-      f = *reinterpret_cast<const float2*>(a.fisher + el);
-      ts = *reinterpret_cast<const float2*>(a.theta_star + el);
+      for (int r = 0; r < W; ++r)
+        if (r < a.world && el[u] >= 0) gr[u][r] = ld_cv2(a.grad[r] + el[u]);      // all peer loads in flight together
     }
-    adam_update_elem(g.x, th.x, m.x, v.x, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
-    adam_update_elem(g.y, th.y, m.y, v.y, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
-    *reinterpret_cast<float2*>(a.m + el) = m;
-    *reinterpret_cast<float2*>(a.v + el) = v;
 #pragma unroll
-    for (int r = 0; r < ADER_DP_MAX_RANKS; ++r)
-      if (r < a.world) *reinterpret_cast<float2*>(a.theta[r] + el) = th;
+    for (int u = 0; u < U; ++u) {
+      if (el[u] < 0) continue;
+      float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < a.world) { g.x = __fadd_rn(g.x, gr[u][r].x); g.y = __fadd_rn(g.y, gr[u][r].y); }   // rank order: deterministic
+      float2 th = *reinterpret_cast<const float2*>(a.theta[a.rank] + el[u]);
+      float2 m = *reinterpret_cast<const float2*>(a.m + el[u]);
+      float2 v = *reinterpret_cast<const float2*>(a.v + el[u]);
+      float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
+      if (ewc) {
+        f = *reinterpret_cast<const float2*>(a.fisher + el[u]);
+        ts = *reinterpret_cast<const float2*>(a.theta_star + el[u]);
+      }
+      adam_update_elem(g.x, th.x, m.x, v.x, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
+      adam_update_elem(g.y, th.y, m.y, v.y, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
+      *reinterpret_cast<float2*>(a.m + el[u]) = m;
+      *reinterpret_cast<float2*>(a.v + el[u]) = v;
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < a.world) *reinterpret_cast<float2*>(a.theta[r] + el[u]) = th;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -195,13 +209,18 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
   d.lr = a->lr; d.beta1 = a->beta1; d.beta2 = a->beta2; d.eps = a->eps; d.ewc_lambda = a->ewc_lambda;
   d.fisher = a->fisher; d.theta_star = a->theta_star;
   const long long mine = d.hi2 - d.lo2;
-  int grid = cdiv(mine > 0 ? mine : 1, 256);
-  if (grid > 148 * 4) grid = 148 * 4;                 // grid-stride over the owned slice, whole waves of the 148 SMs
+  const int U = c->world <= 2 ? 8 : c->world <= 4 ? 4 : c->world <= 8 ? 2 : 1;
+  int grid = cdiv(mine > 0 ? mine : 1, 256 * U);
+  if (grid > 148 * 2) grid = 148 * 2;                 // grid-stride over the owned slice, whole waves of the 148 SMs
   DpFlags fl;
   fl.rank = c->rank; fl.world = c->world;
   for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
   k_dp_arrive<<<1, 32, 0, (cudaStream_t)stream>>>(fl);
-  k_dp_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->world <= 2) k_dp_adam<2, 8><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 4) k_dp_adam<4, 4><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 8) k_dp_adam<8, 2><<<grid, 256, 0, st>>>(d);
+  else k_dp_adam<16, 1><<<grid, 256, 0, st>>>(d);
   ADER_CHECK_LAUNCH("dp_adam_step");
   return 0;
 }

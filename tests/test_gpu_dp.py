@@ -36,6 +36,21 @@ def _model(loss_impl, item_num=400):
     return m
 
 
+def _warm(m, stream, ids, pos, V, **kw):
+    """One throw-away step WITHOUT the back end, rolled back: emulated ranks share one GPU and one host thread, so a
+    host call that waits for the device (first-use pinned / device allocations inside train_step) issued while another
+    rank's arrive kernel is spinning would stall until the 20 s timeout.  Real ranks are separate processes on separate
+    GPUs and have no such coupling."""
+    sd = m.state_dict()
+    comm, m.dp = m.dp, None
+    with torch.cuda.stream(stream):
+        m.train_step(ids, pos, V, 5e-4, 0.0, **kw)
+    torch.cuda.synchronize()
+    m.load_state_dict(sd)
+    m.dp = comm
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("loss_impl", ["exact", "tc"])
 def test_peer_memory_dp_equals_full_batch(world, loss_impl):
@@ -49,6 +64,12 @@ def test_peer_memory_dp_equals_full_batch(world, loss_impl):
     comms = local_peer_group(models)
     streams = [torch.cuda.Stream() for _ in range(world)]
     torch.cuda.synchronize()
+    for r, m in enumerate(models):
+        ids, pos, teacher = batches[0]
+        (tl, th), (el, eh) = shard_rows(len(pos), len(ids) - len(pos), r, world)
+        rows = list(range(tl, th)) + list(range(len(pos) + el, len(pos) + eh))
+        m.global_counts = (len(pos), len(ids) - len(pos))
+        _warm(m, streams[r], ids[rows], pos[tl:th], V, exemplar_logits=teacher[el:eh])
     losses = []
     for ids, pos, teacher in batches:
         n_train, n_ex = len(pos), len(ids) - len(pos)
@@ -107,6 +128,12 @@ def test_peer_memory_dp_graph_replay_and_state_restore():
         gsteps[-1].precapture(indexed=False)       # capture synchronises the device: do it before any rank is replaying
     torch.cuda.synchronize()
     sd0 = [m.state_dict() for m in graph]
+    for r in range(world):
+        (tl, th), (el, eh) = shards[r]
+        ids, pos, teacher = batches[0]
+        rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
+        eager[r].global_counts = (n_train, n_ex)
+        _warm(eager[r], streams[r], ids[rows], pos[tl:th], V, exemplar_logits=teach[r], teacher_rows=np.arange(el, eh, dtype=np.int32))
     for it, (ids, pos, teacher) in enumerate(batches):
         for r in range(world):
             (tl, th), (el, eh) = shards[r]
