@@ -29,6 +29,7 @@
 //   MODE_DE  : after its row-tile loop the CTA of a vocabulary tile < V_prev runs one more second-MMA per exemplar
 //              row tile with the A operand NEGATED in the instruction descriptor: dE[v] -= Pc^T . rep
 #include "common.cuh"
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -68,6 +69,7 @@ struct TcArgs {
   const uint8_t* pt_tiles;      // [n_et][n_vtp][DS_BYTES] bf16 coef_ex * softmax(teacher) tiles, dS layout
   int x0_t, n_et, n_vtp, n_chunks_t;   // first row tile holding exemplar rows, their count, teacher vocab tiles, TU chunks
   float* u_part;                // TU: [n_chunks_t][n_et*128][160]
+  int n2;                       // tc2: N of the gradient products (160, or 192 = three whole swizzle atoms; ADER_B200_TC2_N2)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -551,6 +553,447 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_logits(TcArgs a) {
   }
 }
 
+// =====================================================================================================================
+// Second generation of the same four kernels ("tc2", the default): operands are plain row-major bf16 matrices
+// [rows][160] in HBM, tiles reach shared memory through TMA tensor maps (cp.async.bulk.tensor, SWIZZLE_128B) and every
+// MMA operand is a canonical 128-byte-swizzled UMMA layout:
+//   a tile = 128 rows x 192 k in shared memory = three "regions" of [128 rows][64 k = 128 B] (16 KB each; the TMA box of
+//   region 2 hangs over the 160-column matrix and is zero-filled, so nothing beyond column 159 is ever read from HBM);
+//   * K-major operand of  S = rep . E^T : k-step s (16 k) starts at region s/4, byte (s%4)*32; SBO = 1024 (8-row groups);
+//   * MN-major operand (N or M = the 64 contiguous elements of a region row, K = tile row) of the gradient products:
+//     k-step s (16 rows) starts at byte s*2048; LBO = 16384 (next region = next 64 MN elements), SBO = 1024.
+//   The dS tile the epilogue writes ([128 m][128 v] bf16 = two regions, 16-byte chunks XOR-swizzled by row & 7) is the
+//   K-major A operand of dRep = dS . E (M = m) and, read MN-major, the A operand of dE = dS^T . rep (M = v).
+// The first generation stored pre-tiled no-swizzle operands and read the gradient products' operands MN-major out of that
+// layout, which ran the second product at ~1.9 us per tile against ~0.4 us for the first (profiles/r1f).
+constexpr int REG2 = 16384;                  // one region: 128 rows x 128 B
+constexpr int TILE2_BYTES = 3 * REG2;        // 49152
+constexpr int DS2_BYTES = 2 * REG2;          // 32768
+constexpr int ROW16 = KP;                    // bf16 row pitch (elements) of the HBM operand matrices
+__host__ __device__ constexpr int n_stages2(int mode) { return 3; }
+__host__ __device__ constexpr int n_ds2(int mode) { return mode == MODE_FWD ? 0 : 1; }
+constexpr int smem_tc2(int mode) { return 1024 + (1 + n_stages2(mode)) * TILE2_BYTES + n_ds2(mode) * DS2_BYTES + 256; }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// 128 rows x 160 (192) k starting at matrix row `row0`
+__device__ __forceinline__ void load_tile2(uint32_t dst, const CUtensorMap* tm, int row0, uint32_t bar) {
+  mbar_expect_tx(bar, TILE2_BYTES);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) tma_load_2d(dst + j * REG2, tm, 64 * j, row0, bar);
+}
+// 128 rows x 128 columns of the teacher-probability matrix starting at (row0, col0)
+__device__ __forceinline__ void load_ds2(uint32_t dst, const CUtensorMap* tm, int col0, int row0, uint32_t bar) {
+  mbar_expect_tx(bar, DS2_BYTES);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) tma_load_2d(dst + j * REG2, tm, col0 + 64 * j, row0, bar);
+}
+// shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2 in bits [61,64)), version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kstep) {      // 16 k of a K-major tile
+  return make_desc_sw128(base + (kstep >> 2) * REG2 + (kstep & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int kstep) {     // 16 rows (= K) of an MN-major tile
+  return make_desc_sw128(base + kstep * 2048, REG2, 1024);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_constant__ CUtensorMap tm_rep,
+                                                     const __grid_constant__ CUtensorMap tm_e,
+                                                     const __grid_constant__ CUtensorMap tm_pt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 atoms: 1 KB aligned
+  constexpr int NST = n_stages2(MODE), ND = n_ds2(MODE);
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + TILE2_BYTES;
+  uint8_t* sD = smem + (1 + NST) * TILE2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + NST) * TILE2_BYTES + ND * DS2_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int B_XFULL = 0, B_YFULL = 1, B_YEMPTY = 5, B_TFULL = 9, B_TEMPTY = 11, B_DSFULL = 13, B_DSEMPTY = 15, B_ACC = 17, B_PFULL = 18;
+  constexpr int NDS = ND > 0 ? ND : 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work assignment (as in the first generation) ---------------------------------------------
+  int x_tile, y_lo, y_hi, chunk = 0;
+  if (MODE == MODE_DE) { x_tile = blockIdx.x; y_lo = 0; y_hi = a.n_mtiles; }
+  else if (MODE == MODE_TU) {
+    x_tile = a.x0_t + blockIdx.x % a.n_et; chunk = blockIdx.x / a.n_et;
+    y_lo = (int)((long long)chunk * a.n_vtp / a.n_chunks_t);
+    y_hi = (int)((long long)(chunk + 1) * a.n_vtp / a.n_chunks_t);
+  } else {
+    x_tile = blockIdx.x % a.n_mtiles; chunk = blockIdx.x / a.n_mtiles;
+    y_lo = (int)((long long)chunk * a.n_vtiles / a.n_chunks);
+    y_hi = (int)((long long)(chunk + 1) * a.n_vtiles / a.n_chunks);
+  }
+  const int n_it = max(0, y_hi - y_lo);
+  const CUtensorMap* tmX = (MODE == MODE_DE) ? &tm_e : &tm_rep;
+  const CUtensorMap* tmY = (MODE == MODE_DE) ? &tm_rep : &tm_e;
+  const int n_tt = (MODE == MODE_DE && x_tile < a.n_vtp) ? a.n_et : 0;
+
+  // ---- setup ---------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(B_XFULL), 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(BAR(B_YFULL + s), 1); mbar_init(BAR(B_YEMPTY + s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(B_TFULL + s), 1); mbar_init(BAR(B_TEMPTY + s), NEPI);
+      mbar_init(BAR(B_DSFULL + s), is_teach(MODE) ? 1 : NEPI); mbar_init(BAR(B_DSEMPTY + s), 1);
+    }
+    mbar_init(BAR(B_ACC), 1);
+    mbar_init(BAR(B_PFULL), 1); mbar_init(BAR(B_PFULL + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmY) : "memory");
+    if (is_teach(MODE) || MODE == MODE_DE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_pt) : "memory");
+  }
+  constexpr uint32_t TMEM_COLS = (MODE == MODE_FWD) ? 256u : 512u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t ACC_COL = 256;
+  pdl_wait(); pdl_go();
+
+  if (warp == 0) {
+    // ===== producer: one elected lane issues the TMA loads ==========================================
+    if (lane == 0 && n_it > 0) {
+      if (!is_teach(MODE)) load_tile2(smem_u32(sX), tmX, x_tile * TILE, BAR(B_XFULL));
+      for (int it = 0; it < n_it; ++it) {
+        const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
+        mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
+        load_tile2(smem_u32(sY + ys * TILE2_BYTES), tmY, (y_lo + it) * TILE, BAR(B_YFULL + ys));
+        if (is_teach(MODE)) {               // the "dS" operand is a stored tile of coef * softmax(teacher)
+          const int s = it % NDS; const uint32_t ph = (it / NDS) & 1;
+          mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+          load_ds2(smem_u32(sD + s * DS2_BYTES), &tm_pt, (y_lo + it) * TILE, (x_tile - a.x0_t) * TILE, BAR(B_DSFULL + s));
+        }
+      }
+      for (int jt = 0; jt < n_tt; ++jt) {   // DE: rep tile of exemplar row tile jt + its teacher tile for this vocabulary tile
+        const int idx = n_it + jt;
+        const int ys = idx % NST; const uint32_t yph = (idx / NST) & 1;
+        mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
+        load_tile2(smem_u32(sY + ys * TILE2_BYTES), tmY, (a.x0_t + jt) * TILE, BAR(B_YFULL + ys));
+        const int s = idx % NDS; const uint32_t ph = (idx / NDS) & 1;
+        mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
+        load_ds2(smem_u32(sD + s * DS2_BYTES), &tm_pt, x_tile * TILE, jt * TILE, BAR(B_PFULL + s));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer ===================================================================================
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t IDESC1 = make_idesc(128, 128, 0, 0);
+      constexpr bool DE_LIKE = (MODE == MODE_DE);
+      const uint32_t IDESC2 = DE_LIKE ? make_idesc(128, a.n2, 1, 1) : make_idesc(128, a.n2, 0, 1);
+      const uint32_t xa = smem_u32(sX);
+      auto issue_s = [&](int it) {          // S[buf] = rep_tile . e_tile^T  (both operands K-major)
+        const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+        const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
+        mbar_wait(BAR(B_YFULL + ys), yph, a.err);
+        mbar_wait(BAR(B_TEMPTY + s), ph ^ 1, a.err);
+        tc_fence_after();
+        const uint32_t ya = smem_u32(sY + ys * TILE2_BYTES);
+        const uint32_t A = (MODE == MODE_DE) ? ya : xa;     // rows of S = logits rows (rep)
+        const uint32_t B = (MODE == MODE_DE) ? xa : ya;
+#pragma unroll
+        for (int k = 0; k < KSTEPS1; ++k)
+          umma_bf16(tmem + s * 128, desc_kmajor(A, k), desc_kmajor(B, k), IDESC1, k > 0);
+        if (MODE == MODE_FWD) umma_commit(BAR(B_YEMPTY + ys));
+        umma_commit(BAR(B_TFULL + s));
+      };
+      if (!is_teach(MODE)) { mbar_wait(BAR(B_XFULL), 0, a.err); issue_s(0); }
+      for (int it = 0; it < n_it; ++it) {
+        if (!is_teach(MODE) && it + 1 < n_it) issue_s(it + 1);
+        if (MODE != MODE_FWD) {
+          const int s = it % NDS; const uint32_t ph = (it / NDS) & 1;
+          const int ys = it % NST;
+          if (is_teach(MODE)) mbar_wait(BAR(B_YFULL + ys), (it / NST) & 1, a.err);
+          mbar_wait(BAR(B_DSFULL + s), ph, a.err);
+          tc_fence_after();
+          const uint32_t da = smem_u32(sD + s * DS2_BYTES);
+          const uint32_t ya = smem_u32(sY + ys * TILE2_BYTES);
+#pragma unroll
+          for (int k = 0; k < KSTEPS2; ++k) {
+            // dS tile [128 m][128 v]: DREP / TU read it K-major (M = m, K = v), DE reads it MN-major (M = v, K = m);
+            // the streamed tile is the MN-major B operand (N = feature, K = tile row)
+            const uint64_t ad = DE_LIKE ? desc_mnmajor(da, k) : desc_kmajor(da, k);
+            umma_bf16(tmem + ACC_COL, ad, desc_mnmajor(ya, k), IDESC2, (it > 0 || k > 0));
+          }
+          umma_commit(BAR(B_YEMPTY + ys));
+          umma_commit(BAR(B_DSEMPTY + s));
+        }
+      }
+      if (MODE == MODE_DE) {                // dE[v] -= Pc^T . rep over the exemplar row tiles (A negated)
+        const uint32_t IDESC2N = make_idesc(128, a.n2, 1, 1, 1);
+        uint32_t pph[2] = {0u, 0u};
+        for (int jt = 0; jt < n_tt; ++jt) {
+          const int idx = n_it + jt;
+          const int ys = idx % NST; const int s = idx % NDS;
+          mbar_wait(BAR(B_YFULL + ys), (idx / NST) & 1, a.err);
+          mbar_wait(BAR(B_PFULL + s), pph[s], a.err); pph[s] ^= 1u;
+          tc_fence_after();
+          const uint32_t da = smem_u32(sD + s * DS2_BYTES);
+          const uint32_t ya = smem_u32(sY + ys * TILE2_BYTES);
+#pragma unroll
+          for (int k = 0; k < KSTEPS2; ++k)
+            umma_bf16(tmem + ACC_COL, desc_mnmajor(da, k), desc_mnmajor(ya, k), IDESC2N, 1u);
+          umma_commit(BAR(B_YEMPTY + ys));
+          umma_commit(BAR(B_DSEMPTY + s));
+        }
+      }
+      if (MODE != MODE_FWD) umma_commit(BAR(B_ACC));
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM lane = logits row ===============================================================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    RowInfo ri, ri_next;
+    float mx = -INFINITY, sum = 0.f, lab = 0.f, dot = 0.f;
+    if (is_teach(MODE)) { ri = RowInfo(); ri_next = RowInfo(); }
+    else if (MODE != MODE_DE) ri = row_info(a, x_tile * TILE + row, MODE != MODE_FWD);
+    else ri_next = row_info(a, y_lo * TILE + row, true);
+    for (int it = 0; it < (is_teach(MODE) ? 0 : n_it); ++it) {
+      const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+      int v0;
+      if (MODE == MODE_DE) {
+        ri = ri_next;
+        if (it + 1 < n_it) ri_next = row_info(a, (y_lo + it + 1) * TILE + row, true);
+        v0 = x_tile * TILE;
+      } else v0 = (y_lo + it) * TILE;
+      mbar_wait(BAR(B_TFULL + s), ph, a.err);
+      tc_fence_after();
+      uint32_t r[2][32];
+      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2) * 32, r[0]);
+      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2 + 1) * 32, r[1]);
+      tmem_ld_wait(r[0]);
+      tmem_ld_wait(r[1]);
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + s));
+      const int vb0 = v0 + half * 64;
+      const bool full = (ri.kind != 0) && (vb0 + 64 <= ri.vlim);
+      if (MODE == MODE_FWD) {
+        if (full) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[c][i]));
+          const float nm = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          sum *= ex2((mx - nm) * LOG2E);
+          mx = nm;
+          const float nm2 = nm * LOG2E;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s4[i & 3] += ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -nm2));
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          if (ri.label >= vb0 && ri.label < vb0 + 64) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (vb0 + c * 32 + i == ri.label) lab = __uint_as_float(r[c][i]);
+          }
+        } else if (ri.kind != 0 && vb0 < ri.vlim) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int vb = vb0 + c * 32;
+            if (vb >= ri.vlim) break;
+            float cm = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(r[c][i]));
+            const float nm = fmaxf(mx, cm);
+            sum *= ex2((mx - nm) * LOG2E);
+            mx = nm;
+            const float nm2 = nm * LOG2E;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int v = vb + i;
+              if (v < ri.vlim) {
+                const float sv = __uint_as_float(r[c][i]);
+                sum += ex2(fmaf(sv, LOG2E, -nm2));
+                if (v == ri.label) lab = sv;
+              }
+            }
+          }
+        }
+      } else {
+        const int sd = it % NDS; const uint32_t dph = (it / NDS) & 1;
+        uint32_t pk[2][16];                    // this thread's 64 gradient values as bf16 pairs
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int vb = vb0 + c * 32;
+          float g[32];
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+            if (ri.label >= vb && ri.label < vb + 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int v = vb + i;
+              float gv = 0.f;
+              if (ri.kind != 0 && v < ri.vlim) {
+                const float p = ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+                gv = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
+              }
+              g[i] = gv;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * u], g[2 * u + 1]);
+            pk[c][u] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        // the exponentials above overlap the second product of the previous tile; only the stores wait for its dS buffer
+        mbar_wait(BAR(B_DSEMPTY + sd), dph ^ 1, a.err);
+        // region `half` (this thread's 64 columns), row `row`: eight 16-byte chunks, chunk j at position j ^ (row & 7)
+        uint8_t* drow = sD + sd * DS2_BYTES + half * REG2 + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = j >> 2, u = (j & 3) * 4;
+          *reinterpret_cast<uint4*>(drow + ((j ^ (row & 7)) << 4)) = make_uint4(pk[c][u], pk[c][u + 1], pk[c][u + 2], pk[c][u + 3]);
+        }
+        fence_async_smem();
+        mbar_arrive(BAR(B_DSFULL + sd));
+      }
+    }
+    if (MODE == MODE_FWD) {
+      const int gm = x_tile * TILE + row;
+      if (gm < a.M) {
+        float4 o = make_float4(mx, sum, lab, dot);
+        *reinterpret_cast<float4*>(a.stats + ((size_t)(chunk * 2 + half) * a.M + gm) * 4) = o;
+      }
+    } else if (n_it > 0) {
+      mbar_wait(BAR(B_ACC), 0, a.err);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c4 = half; c4 < KP / 32; c4 += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem + tlane + ACC_COL + c4 * 32, r);
+        if (MODE == MODE_DREP || MODE == MODE_TU) {
+          float* o = (MODE == MODE_DREP)
+                         ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP + c4 * 32
+                         : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE + row) * KP + c4 * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                            __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        } else {                              // DE: stage the [128 v, 160] tile in the (now idle) Y stages
+          float* stg = reinterpret_cast<float*>(sY) + row * DE_LD + c4 * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(stg + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                              __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+      }
+      if (MODE == MODE_DE) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+        const float* stg = reinterpret_cast<const float*>(sY);
+        const int ew = warp - 2;
+        for (int rr = ew; rr < TILE; rr += NEPI / 32) {
+          const int v = x_tile * TILE + rr;
+          if (v >= a.V) break;
+          float2* o = reinterpret_cast<float2*>(a.grad_table + (size_t)v * a.d);
+          for (int c2 = lane; c2 < a.d / 2; c2 += 32) o[c2] = *reinterpret_cast<const float2*>(stg + rr * DE_LD + 2 * c2);
+        }
+      }
+      tc_fence_before();
+    } else if (MODE == MODE_DREP || MODE == MODE_TU) {
+      float* o = (MODE == MODE_DREP) ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP
+                                     : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE + row) * KP;
+      for (int i = half * (KP / 2); i < (half + 1) * (KP / 2); ++i) o[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// fp32 rows -> row-major bf16 [rows_pad][160] (rows >= n_rows and columns >= d are zero): the HBM operand of the tc2 kernels
+__global__ void k_pack_rows16(const float* __restrict__ src, long long ld, int n_rows, int d, int rows_pad,
+                              __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)rows_pad * (ROW16 / 8);
+  if (idx >= total) return;
+  const int kc = (int)(idx % (ROW16 / 8));
+  const long long row = idx / (ROW16 / 8);
+  uint32_t pk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v0 = 0.f, v1 = 0.f;
+    const int k = kc * 8 + i * 2;
+    if (row < n_rows) {
+      if (k < d) v0 = src[row * ld + k];
+      if (k + 1 < d) v1 = src[row * ld + k + 1];
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + row * ROW16 + kc * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// Pc = coef * softmax(teacher) as ONE row-major bf16 matrix [n_et*128][n_vtp*128] (row = step row - x0*128, column = local
+// vocabulary column; zeros outside the exemplar rows / beyond V_prev): TMA cuts the dS-layout tiles out of it.
+__global__ void __launch_bounds__(256) k_teacher_rows16(const float* __restrict__ teacher, const int* __restrict__ teacher_row,
+                                                        long long ld, int vec4, const float* __restrict__ lse_t, int n_train, int M,
+                                                        int V_prev, int v_off, int x0, int n_vtp, float coef,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const int vt = blockIdx.x, et = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ldo = (long long)n_vtp * TILE;
+  const int vl = vt * TILE + lane * 4;
+  const int vg = v_off + vl;
+  float4 t[16]; float l[16];
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int m = warp * 16 + rr;
+    const int e = (x0 + et) * TILE + m - n_train;
+    t[rr] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); l[rr] = 0.f;
+    if (e >= 0 && e + n_train < M && vg < V_prev) {
+      const float* row = teacher + (long long)(teacher_row ? teacher_row[e] : e) * ld;
+      l[rr] = lse_t[e];
+      if (vec4 && vg + 3 < V_prev) t[rr] = __ldg(reinterpret_cast<const float4*>(row + vg));
+      else {
+        t[rr].x = row[vg];
+        if (vg + 1 < V_prev) t[rr].y = row[vg + 1];
+        if (vg + 2 < V_prev) t[rr].z = row[vg + 2];
+        if (vg + 3 < V_prev) t[rr].w = row[vg + 3];
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int m = warp * 16 + rr;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(coef * expf(t[rr].x - l[rr]), coef * expf(t[rr].y - l[rr]));
+    const __nv_bfloat162 b = __floats2bfloat162_rn(coef * expf(t[rr].z - l[rr]), coef * expf(t[rr].w - l[rr]));
+    uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + ((long long)et * TILE + m) * ldo + vl) = pk;
+  }
+}
+
 // ---- operand packing: fp32 rows -> bf16 T128 tiles --------------------------------------------
 // one thread per (row, 8-wide k group); rows >= n_rows and k >= d are zero.
 __global__ void k_pack_tiles(const float* __restrict__ src, long long ld, int n_rows, int d, int n_tiles,
@@ -650,8 +1093,18 @@ __global__ void __launch_bounds__(KP) k_reduce_u(const float* __restrict__ part,
   __shared__ float sh[KP / 32];
   const int r = blockIdx.x, c = threadIdx.x;
   pdl_wait(); pdl_go();
+  const float* pp = part + (size_t)r * KP + c;
+  const size_t cs = (size_t)rows * KP;
   float s = 0.f;
-  for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows + r) * KP + c];
+  int k = 0;
+  for (; k + 8 <= n_chunks; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = pp[(size_t)(k + j) * cs];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; k < n_chunks; ++k) s += pp[(size_t)k * cs];
   u[(size_t)r * KP + c] = s;
   const int gm = x0 * TILE + r;
   float p = (gm < M && c < d) ? s * rep[(size_t)gm * d + c] : 0.f;
@@ -704,8 +1157,20 @@ __global__ void k_reduce_drep(const float* __restrict__ part, int n_chunks, int 
   pdl_wait(); pdl_go();
   if (idx >= (long long)M * d) return;
   const int i = (int)(idx / d), c = (int)(idx % d);
+  // same left-to-right sum as a plain loop, but eight independent loads are in flight per trip (the plain loop paid one
+  // L2 round trip per chunk: ~20 us for 24 chunks on the critical chain)
+  const float* p = part + (size_t)i * KP + c;
+  const size_t cs = (size_t)rows_pad * KP;
   float s = 0.f;
-  for (int k = 0; k < n_chunks; ++k) s += part[((size_t)k * rows_pad + i) * KP + c];
+  int k = 0;
+  for (; k + 8 <= n_chunks; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(k + j) * cs];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; k < n_chunks; ++k) s += p[(size_t)k * cs];
   if (u && i >= n_train) s -= u[(size_t)(i - x0 * TILE) * KP + c];
   d_rep[idx] = s;
 }
@@ -769,6 +1234,53 @@ extern "C" size_t ader_loss_tc_ws_bytes(const AderModel* m, const AderLossArgs* 
   return carve_tc(m, a->M, a->V, a->n_ex, a->mode == 1 ? a->V_prev : 0, nullptr).bytes;
 }
 
+// ---- tc2: TMA tensor maps over the row-major bf16 operand matrices ---------------------------------------------------
+// generation switch: ADER_B200_TC=1 selects the first-generation kernels (pre-tiled no-swizzle operands), default 2
+static int tc_gen() {
+  static int g = -1;
+  if (g < 0) { const char* e = getenv("ADER_B200_TC"); g = (e && e[0] == '1') ? 1 : 2; }
+  return g;
+}
+static int tc2_n2() {
+  static int n = 0;
+  if (!n) { const char* e = getenv("ADER_B200_TC2_N2"); n = (e && atoi(e) == 192) ? 192 : 160; }
+  return n;
+}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// bf16 matrix [rows][cols], row pitch in bytes (multiple of 16); box = 64 columns (128 B, one swizzle span) x 128 rows
+static int make_map2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return fail(-3, "loss_tc: cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    }
+    enc = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "loss_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+struct TcMaps { CUtensorMap rep, e, pt; };
+static int make_tc_maps(const TcWs& w, int nm, int nv, TcMaps& mp) {
+  if (int e = make_map2d(&mp.rep, w.rep_tiles, ROW16, (uint64_t)nm * TILE, ROW16 * 2)) return e;
+  if (int e = make_map2d(&mp.e, w.e_tiles, ROW16, (uint64_t)nv * TILE, ROW16 * 2)) return e;
+  if (w.n_et > 0 && w.n_vtp > 0) {
+    if (int e = make_map2d(&mp.pt, w.pt_tiles, (uint64_t)w.n_vtp * TILE, (uint64_t)w.n_et * TILE, (uint64_t)w.n_vtp * TILE * 2)) return e;
+  } else mp.pt = mp.e;       // never dereferenced (no teacher tiles), but the parameter must be a valid map
+  return 0;
+}
+
 // launches shared by the single-GPU and vocab-parallel entry points -----------------------------------------------
 static void set_tc_attrs() {
   static bool attr_set = false;
@@ -778,13 +1290,24 @@ static void set_tc_attrs() {
   cudaFuncSetAttribute(k_tc_logits<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
   cudaFuncSetAttribute(k_tc_logits<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
   cudaFuncSetAttribute(k_tc_logits<MODE_TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd);
+  cudaFuncSetAttribute(k_tc2<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc2(MODE_FWD));
+  cudaFuncSetAttribute(k_tc2<MODE_DREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc2(MODE_DREP));
+  cudaFuncSetAttribute(k_tc2<MODE_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc2(MODE_DE));
+  cudaFuncSetAttribute(k_tc2<MODE_TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc2(MODE_TU));
   attr_set = true;
 }
 constexpr int SMEM_FWD = (1 + n_stages(MODE_FWD)) * TILE_BYTES + 256;
 constexpr int SMEM_BWD = (1 + n_stages(MODE_DREP)) * TILE_BYTES + 2 * DS_BYTES + 256;
 // teacher statistics + tiles + uc partials (rep-independent), then u = sum of partials and udot = rep . u
-static void launch_teacher_tu(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, cudaStream_t st) {
+static void launch_teacher_tu(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, cudaStream_t st, const TcMaps* mp) {
   k_teacher_lse<<<a->n_ex, 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, a->V_prev, w.lse_t);
+  if (mp) {
+    k_teacher_rows16<<<dim3(w.n_vtp, w.n_et), 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, t.teacher_vec4, w.lse_t,
+                                                           a->n_train, a->M, a->V_prev, v_off, w.x0_t, w.n_vtp, t.coef_ex,
+                                                           reinterpret_cast<__nv_bfloat16*>(w.pt_tiles));
+    k_tc2<MODE_TU><<<w.n_et * w.n_chunks_t, NTHREADS, smem_tc2(MODE_TU), st>>>(t, mp->rep, mp->e, mp->pt);
+    return;
+  }
   k_teacher_tiles<<<dim3(w.n_vtp, w.n_et), 256, 0, st>>>(a->teacher, a->teacher_row, a->teacher_ld, t.teacher_vec4, w.lse_t,
                                                         a->n_train, a->M, a->V_prev, v_off, w.x0_t, w.n_vtp, t.coef_ex, w.pt_tiles);
   k_tc_logits<MODE_TU><<<w.n_et * w.n_chunks_t, NTHREADS, SMEM_BWD, st>>>(t);
@@ -793,9 +1316,17 @@ static void launch_reduce_u(const AderLossArgs* a, const TcWs& w, const float* r
   k_reduce_u<<<w.n_et * TILE, KP, 0, st>>>(w.u_part, w.n_chunks_t, w.n_et * TILE, w.u, rep, w.x0_t, a->M, d, w.udot);
 }
 static void launch_teacher_u(const AderLossArgs* a, const TcWs& w, const TcArgs& t, int v_off, const float* rep, int d,
-                             cudaStream_t st) {
-  launch_teacher_tu(a, w, t, v_off, st);
+                             cudaStream_t st, const TcMaps* mp) {
+  launch_teacher_tu(a, w, t, v_off, st, mp);
   launch_reduce_u(a, w, rep, d, st);
+}
+// operand packing of either generation: fp32 rows -> bf16 (T128 tiles, or the row-major matrix the tensor maps describe)
+static void launch_pack(const float* src, long long ld, int n_rows, int d, int n_tiles, uint8_t* out, cudaStream_t st) {
+  if (tc_gen() == 2)
+    k_pack_rows16<<<cdiv((long long)n_tiles * TILE * (ROW16 / 8), 256), 256, 0, st>>>(src, ld, n_rows, d, n_tiles * TILE,
+                                                                                      reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    k_pack_tiles<<<cdiv((long long)n_tiles * TILE * (KP / 8), 256), 256, 0, st>>>(src, ld, n_rows, d, n_tiles, out);
 }
 
 extern "C" int32_t ader_loss_fwd_bwd_tc(const AderModel* m, const float* theta, const float* rep,
@@ -848,30 +1379,40 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
   t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0)) ? 1 : 0;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = grad ? grad + d : nullptr;
   t.d = d; t.err = w.err;
-  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part;
+  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part; t.n2 = tc2_n2();
 
+  const bool g2 = tc_gen() == 2;
+  TcMaps mp;
+  if (g2) { if (int e = make_tc_maps(w, nm, nv, mp)) return e; }
   if (phase_mask == 4) {      // measurement only: the three tensor-core kernels on an already prepared workspace
-    k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
-    k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
-    if (grad) k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
+    if (g2) {
+      k_tc2<MODE_FWD><<<nm * nc, NTHREADS, smem_tc2(MODE_FWD), st>>>(t, mp.rep, mp.e, mp.pt);
+      k_tc2<MODE_DREP><<<nm * nc, NTHREADS, smem_tc2(MODE_DREP), st>>>(t, mp.rep, mp.e, mp.pt);
+      if (grad) k_tc2<MODE_DE><<<nv, NTHREADS, smem_tc2(MODE_DE), st>>>(t, mp.rep, mp.e, mp.pt);
+    } else {
+      k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
+      k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);
+      if (grad) k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, st>>>(t);
+    }
     ADER_CHECK_LAUNCH("tc kernels");
     return 0;
   }
   if (phase_mask & 1) {
     cudaMemsetAsync(w.err, 0, sizeof(int) * 4, sb);
-    k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, sb>>>(theta + d, d, V, d, nv, w.e_tiles);
-    if (kd) launch_teacher_tu(a, w, t, 0, sb);
+    launch_pack(theta + d, d, V, d, nv, w.e_tiles, sb);
+    if (kd) launch_teacher_tu(a, w, t, 0, sb, g2 ? &mp : nullptr);
     ADER_CHECK_LAUNCH("tc prep");
   }
   if (!(phase_mask & 2)) return 0;
 
   f.edge(sb, st);
-  k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
+  launch_pack(rep, d, M, d, nm, w.rep_tiles, st);
   // chain links (kernel directly behind a kernel on f.main) may be programmatic dependent launches
   if (kd) launch_chain(k_reduce_u, dim3(w.n_et * TILE), dim3(KP), 0, st, f.pdl, (const float*)w.u_part, w.n_chunks_t, w.n_et * TILE, w.u, rep,
                        w.x0_t, a->M, d, w.udot);
   ADER_CHECK_LAUNCH("tc pack");
-  launch_chain(k_tc_logits<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_fwd, st, f.pdl, t);
+  if (g2) launch_chain(k_tc2<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_FWD), st, f.pdl, t, mp.rep, mp.e, mp.pt);
+  else launch_chain(k_tc_logits<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_fwd, st, f.pdl, t);
   launch_chain(k_merge_stats, dim3(cdiv((long long)M * 32, 256)), dim3(256), 0, st, f.pdl, (const float*)w.stats, M, nc * 2, a->n_train, t.mode,
                w.lse, row_loss, (float*)nullptr, (const float*)(kd ? w.udot : nullptr), w.x0_t, t.coef_ex);
   cudaEvent_t lse_ready = nullptr;
@@ -880,14 +1421,16 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
   if (int e = launch_loss_reduce(row_loss, a->n_train, a->n_ex, a->lambda_, loss, f.c, a->n_train_global, a->n_ex_global)) return e;
   ADER_CHECK_LAUNCH("tc fwd");
   if (d_rep) {
-    launch_chain(k_tc_logits<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_bwd, st, f.pdl, t);
+    if (g2) launch_chain(k_tc2<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_DREP), st, f.pdl, t, mp.rep, mp.e, mp.pt);
+    else launch_chain(k_tc_logits<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_bwd, st, f.pdl, t);
     launch_chain(k_reduce_drep, dim3(cdiv((long long)M * d, 256)), dim3(256), 0, st, f.pdl, (const float*)w.drep_part, nc, nm * TILE, M, d, d_rep,
                  (const float*)(kd ? w.u : nullptr), w.x0_t, a->n_train);
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {
     if (f.parallel()) cudaStreamWaitEvent(sb, lse_ready, 0);
-    k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, sb>>>(t);
+    if (g2) k_tc2<MODE_DE><<<nv, NTHREADS, smem_tc2(MODE_DE), sb>>>(t, mp.rep, mp.e, mp.pt);
+    else k_tc_logits<MODE_DE><<<nv, NTHREADS, smem_bwd, sb>>>(t);
     ADER_CHECK_LAUNCH("tc d_table");
     if (f.parallel()) { f.table_ready = f.take(); cudaEventRecord(f.table_ready, sb); f.has_table_ready = true; }
   }
@@ -910,15 +1453,16 @@ static int vp_teacher_cols(const AderLossArgs* a, int v_lo, int v_hi) {      // 
   return hi > v_lo ? hi - v_lo : 0;
 }
 static int vp_setup(const AderModel* m, const float* theta, const float* rep, const AderLossArgs* a, int v_lo, int v_hi,
-                    void* ws, cudaStream_t st, TcWs& w, TcArgs& t, bool pack) {
+                    void* ws, cudaStream_t st, TcWs& w, TcArgs& t, bool pack, TcMaps& mp) {
   const int d = m->d, M = a->M, Vl = v_hi - v_lo;
   w = carve_tc(m, M, Vl, a->n_ex, vp_teacher_cols(a, v_lo, v_hi), (char*)ws);
   const int nm = cdiv(M, TILE), nv = cdiv(Vl, TILE), nc = tc_chunks(nm, nv);
   set_tc_attrs();
+  if (tc_gen() == 2) { if (int e = make_tc_maps(w, nm, nv, mp)) return e; }
   if (pack) {
     cudaMemsetAsync(w.err, 0, sizeof(int) * 4, st);
-    k_pack_tiles<<<cdiv((long long)nm * TILE * (KP / 8), 256), 256, 0, st>>>(rep, d, M, d, nm, w.rep_tiles);
-    k_pack_tiles<<<cdiv((long long)nv * TILE * (KP / 8), 256), 256, 0, st>>>(theta + (size_t)(1 + v_lo) * d, d, Vl, d, nv, w.e_tiles);
+    launch_pack(rep, d, M, d, nm, w.rep_tiles, st);
+    launch_pack(theta + (size_t)(1 + v_lo) * d, d, Vl, d, nv, w.e_tiles, st);
   }
   t.rep_tiles = w.rep_tiles; t.e_tiles = w.e_tiles; t.M = M; t.V = Vl; t.V_total = a->V; t.v_off = v_lo;
   t.n_mtiles = nm; t.n_vtiles = nv; t.n_chunks = nc;
@@ -929,8 +1473,8 @@ static int vp_setup(const AderModel* m, const float* theta, const float* rep, co
   t.teacher_vec4 = (a->teacher && a->teacher_ld % 4 == 0 && ((uintptr_t)a->teacher % 16 == 0) && v_lo % 4 == 0) ? 1 : 0;
   t.lse = w.lse; t.lse_t = w.lse_t; t.stats = w.stats; t.drep_part = w.drep_part; t.grad_table = nullptr;
   t.d = d; t.err = w.err;
-  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part;
-  if (pack && w.n_et > 0) launch_teacher_u(a, w, t, v_lo, rep, d, st);
+  t.pt_tiles = w.pt_tiles; t.x0_t = w.x0_t; t.n_et = w.n_et; t.n_vtp = w.n_vtp; t.n_chunks_t = w.n_chunks_t; t.u_part = w.u_part; t.n2 = tc2_n2();
+  if (pack && w.n_et > 0) launch_teacher_u(a, w, t, v_lo, rep, d, st, tc_gen() == 2 ? &mp : nullptr);
   return 0;
 }
 
@@ -954,9 +1498,10 @@ extern "C" int32_t ader_loss_tc_vp_fwd(const AderModel* m, const float* theta, c
   if (int e = vp_check(m, a, v_lo, v_hi)) return e;
   ADER_CHECK_ARG(theta && rep && ws && stats, "loss_tc_vp_fwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  TcWs w; TcArgs t;
-  vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, true);
-  k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, SMEM_FWD, st>>>(t);
+  TcWs w; TcArgs t; TcMaps mp;
+  if (int e = vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, true, mp)) return e;
+  if (tc_gen() == 2) k_tc2<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_tc2(MODE_FWD), st>>>(t, mp.rep, mp.e, mp.pt);
+  else k_tc_logits<MODE_FWD><<<t.n_mtiles * t.n_chunks, NTHREADS, SMEM_FWD, st>>>(t);
   k_merge_stats<<<cdiv((long long)a->M * 32, 256), 256, 0, st>>>(w.stats, a->M, t.n_chunks * 2, a->n_train, t.mode, nullptr, nullptr, stats,
                                                  w.n_et > 0 ? w.udot : nullptr, w.x0_t, t.coef_ex);
   ADER_CHECK_LAUNCH("loss_tc_vp_fwd");
@@ -969,17 +1514,22 @@ extern "C" int32_t ader_loss_tc_vp_bwd(const AderModel* m, const float* theta, c
   if (int e = vp_check(m, a, v_lo, v_hi)) return e;
   ADER_CHECK_ARG(theta && rep && ws && lse, "loss_tc_vp_bwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  TcWs w; TcArgs t;
-  vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, false);     // tiles were packed by the forward call
+  TcWs w; TcArgs t; TcMaps mp;
+  if (int e = vp_setup(m, theta, rep, a, v_lo, v_hi, ws, st, w, t, false, mp)) return e;     // operands were packed by the forward call
   t.lse = lse;
   t.grad_table = grad ? grad + (size_t)(1 + v_lo) * m->d : nullptr;
   const int smem_bwd = SMEM_BWD;
+  const bool g2 = tc_gen() == 2;
   if (d_rep_partial) {
-    k_tc_logits<MODE_DREP><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_bwd, st>>>(t);
+    if (g2) k_tc2<MODE_DREP><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_tc2(MODE_DREP), st>>>(t, mp.rep, mp.e, mp.pt);
+    else k_tc_logits<MODE_DREP><<<t.n_mtiles * t.n_chunks, NTHREADS, smem_bwd, st>>>(t);
     k_reduce_drep<<<cdiv((long long)a->M * m->d, 256), 256, 0, st>>>(w.drep_part, t.n_chunks, t.n_mtiles * TILE, a->M, m->d, d_rep_partial,
                                                                      w.n_et > 0 ? w.u : nullptr, w.x0_t, a->n_train);
   }
-  if (grad) k_tc_logits<MODE_DE><<<t.n_vtiles, NTHREADS, smem_bwd, st>>>(t);
+  if (grad) {
+    if (g2) k_tc2<MODE_DE><<<t.n_vtiles, NTHREADS, smem_tc2(MODE_DE), st>>>(t, mp.rep, mp.e, mp.pt);
+    else k_tc_logits<MODE_DE><<<t.n_vtiles, NTHREADS, smem_bwd, st>>>(t);
+  }
   ADER_CHECK_LAUNCH("loss_tc_vp_bwd");
   return 0;
 }

@@ -107,6 +107,9 @@ def run(data_dir: str, item_num: int, args, n_periods: int) -> dict:
                 else:
                     fn = lambda ps: S.loss_vanilla(ps, ids, pos_t, max_item, hp)
                 loss, grads = S.grads_of(fn, params)
+                if ewc:                                      # cross-entropy part alone (what a product step reports)
+                    with torch.no_grad():
+                        rec.setdefault("ce_losses", []).append(float(S.loss_vanilla(params, ids, pos_t, max_item, hp)))
                 if getattr(args, "trace_rows", False):
                     with torch.no_grad():
                         lg = S.logits_of(S.forward_rep(params, ids, hp), params[0], max_item)

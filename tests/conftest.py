@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# tests/test_gpu_dp.py runs several emulated data-parallel ranks on ONE GPU, each with its own streams / CUDA graphs; with
+# the default of 8 hardware work queues, streams of different ranks can alias onto one queue and a rank's kernels would sit
+# behind another rank's spinning arrive kernel (false dependency).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun)")

@@ -487,13 +487,15 @@ def test_default_tc_path_matches_oracle_at_baseline_shapes(shape):
     ref, grads = S.grads_of(fn, params)
     assert loss == pytest.approx(ref, rel=1e-3)
     worst = []
+    gscale = max(float(w.abs().max()) for w in grads)
+    floor_ = 1e-5 * gscale          # absolute floor: tensors whose true gradient is identically zero (the key bias: softmax is shift invariant)
     for i, (name, _) in enumerate(S.param_shapes(hp)):
         g, w = got[i].double(), grads[i].double()
         if i == 0:
             assert float(g[V + 1:].abs().max()) == 0.0 if g[V + 1:].numel() else True
             g, w = g[1:V + 1], w[1:V + 1]
-        rel = float((g - w).norm() / w.norm())
-        mx = float((g - w).abs().max() / w.abs().max())
+        rel = float((g - w).norm() / (w.norm() + floor_ * w.numel() ** 0.5))
+        mx = float((g - w).abs().max() / (w.abs().max() + floor_))
         worst.append((rel, mx, name))
         assert rel <= 3e-2 and mx <= 0.15, "%s: rel-L2 %.3e, max-abs/max|g| %.3e" % (name, rel, mx)
     w_rel, w_mx = max(worst), max(worst, key=lambda t: t[1])
@@ -606,11 +608,16 @@ def test_end_to_end_herding_periods(tmp_path):
 
 
 # ---- the baseline / ablation flags of main.py:82-91 against the oracle driver, three periods each ----
-def _compare_periods(got, want, n, loss_rtol=1e-5, exemplars=True):
+def _compare_periods(got, want, n, loss_rtol=1e-5, exemplars=True, loss_key="losses", head_rtol=None):
+    """Step losses: fp32 rounding differences between the CPU and the GPU trajectory grow with the number of Adam steps
+    (chaotic amplification, ~1e-5 after 40 steps, ~1e-4 after 100), so the first steps of a period carry the tight bound
+    (`head_rtol`, where the period starts from a common state) and the whole period `loss_rtol`."""
     assert len(got["trace"]["periods"]) == n
     for p, (g, w) in enumerate(zip(got["trace"]["periods"], want["periods"])):
-        assert len(g["losses"]) == len(w["losses"]), "period %d step count" % (p + 1)
-        np.testing.assert_allclose(g["losses"], w["losses"], rtol=loss_rtol, err_msg="period %d losses" % (p + 1))
+        assert len(g["losses"]) == len(w[loss_key]), "period %d step count" % (p + 1)
+        np.testing.assert_allclose(g["losses"], w[loss_key], rtol=loss_rtol, err_msg="period %d losses" % (p + 1))
+        if head_rtol is not None and p == 0:
+            np.testing.assert_allclose(g["losses"][:20], w[loss_key][:20], rtol=head_rtol, err_msg="period %d first losses" % (p + 1))
         assert g["best_epoch"] == w["best_epoch"], "period %d best epoch" % (p + 1)
         gr, wr = np.array(g["test_ranks"]), np.array(w["test_ranks"])
         assert len(gr) == len(wr)
@@ -636,7 +643,8 @@ def test_end_to_end_baseline_modes_match_oracle_driver(tmp_path, flags):
     with S.literal_masks(False):
         want = reference_loop.run(a2.dataset, a2.item_num, a2, n_periods=3)
     no_replay = bool(flags.get("finetune") or flags.get("dropout") or flags.get("joint"))
-    _compare_periods(got, want, 3, exemplars=not no_replay)
+    # --joint restarts every period from the initial weights and runs up to ~130 steps per epoch: longest trajectories
+    _compare_periods(got, want, 3, loss_rtol=3e-3 if flags.get("joint") else 3e-4, head_rtol=1e-5, exemplars=not no_replay)
     if no_replay:
         assert all(p["exemplars"] is None for p in got["trace"]["periods"])
     if flags.get("joint"):          # period 3 trains on periods 0..2: more steps per epoch than period 1
@@ -659,7 +667,9 @@ def test_end_to_end_ewc_matches_oracle_driver(tmp_path):
     a2.dropout_rate = 0
     with S.literal_masks(False):
         want = reference_loop.run(a2.dataset, a2.item_num, a2, n_periods=3)
-    _compare_periods(got, want, 3, loss_rtol=2e-5)
+    # the product's step returns the cross entropy (the penalty only enters the gradient); the oracle records both
+    _compare_periods(got, want, 3, loss_rtol=3e-4, head_rtol=1e-5, loss_key="ce_losses")
+    assert max(w - c for p_ in want["periods"][1:] for w, c in zip(p_["losses"], p_["ce_losses"])) > 1e-3   # penalty is live
     m = got["model"]
     fish = torch.cat([f.reshape(-1) for f in want["periods"][2]["fisher"]])
     _close(m.fisher.cpu(), fish, 1e-3, 1e-12, "Fisher after period 3")
