@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(256) k_herding(const float* __restrict__ rep, 
       float fv = bestv[0]; int fj = bestj[0];
       for (int q = 1; q < 8; ++q)
         if (bestv[q] > fv || (bestv[q] == fv && bestj[q] < fj)) { fv = bestv[q]; fj = bestj[q]; }
+      // every dot product NaN (a zero-norm rep row: 0/0 in the normalisation): no comparison succeeded; np.argmax
+      // returns index 0 for an all-NaN vector (util.py:426), and the index must stay inside the segment
+      if (fj < 0 || fj >= n) fj = 0;
       pick_s = fj;
       if (!selected[off + fj]) { selected[off + fj] = 1; picks[off + cnt_s] = fj; cnt_s = cnt_s + 1; }
     }

@@ -194,8 +194,10 @@ static_assert(TILE * DE_LD * 4 <= 3 * TILE_BYTES, "dE staging tile must fit the 
 __device__ long long g_tl[3][192][64];
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TL(slot) do { if (blockIdx.x < 192) g_tl[MODE][blockIdx.x][slot] = gtimer(); } while (0)
+#define TL2(slot) do { if (blockIdx.x < 192 && MODE < 3) g_tl[MODE][blockIdx.x][slot] = gtimer(); } while (0)
 #else
 #define TL(slot) do { } while (0)
+#define TL2(slot) do { } while (0)
 #endif
 // streamed-tile ring depth: the backward kernels free a stage only after the SECOND MMA of a tile, so two
 // stages expose the L2 latency of every tile (ncu: epilogue warps 41 % stalled on the S-tile barrier)
@@ -620,6 +622,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
   constexpr int NDS = ND > 0 ? ND : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ADER_TC_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x < 192 && MODE < 3) { const long long gt = gtimer(); g_tl[MODE][blockIdx.x][0] = gt; g_tl[MODE][blockIdx.x][1] = gt; }
+#endif
 
   // ---- work assignment (as in the first generation) ---------------------------------------------
   int x_tile, y_lo, y_hi, chunk = 0;
@@ -666,21 +671,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t ACC_COL = 256;
   pdl_wait(); pdl_go();
+  if (threadIdx.x == 64) TL2(2);
 
   if (warp == 0) {
     // ===== producer: one elected lane issues the TMA loads ==========================================
     if (lane == 0 && n_it > 0) {
       if (!is_teach(MODE)) load_tile2(smem_u32(sX), tmX, x_tile * TILE, BAR(B_XFULL));
+      TL2(3);
       for (int it = 0; it < n_it; ++it) {
         const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
         mbar_wait(BAR(B_YEMPTY + ys), yph ^ 1, a.err);
         load_tile2(smem_u32(sY + ys * TILE2_BYTES), tmY, (y_lo + it) * TILE, BAR(B_YFULL + ys));
+        if (it < 8) TL2(8 + it);
         if (is_teach(MODE)) {               // the "dS" operand is a stored tile of coef * softmax(teacher)
           const int s = it % NDS; const uint32_t ph = (it / NDS) & 1;
           mbar_wait(BAR(B_DSEMPTY + s), ph ^ 1, a.err);
           load_ds2(smem_u32(sD + s * DS2_BYTES), &tm_pt, (y_lo + it) * TILE, (x_tile - a.x0_t) * TILE, BAR(B_DSFULL + s));
         }
       }
+      // The dS buffer(s) were cycled by the EPILOGUE during the row-tile loop; this warp has not followed their phases, so a
+      // parity wait on DSEMPTY alone could be satisfied by a completion several tiles back.  Every second product also
+      // commits to the Y stage it read: wait for the LAST row tile's commit (a phase this warp has not consumed yet), after
+      // which the DSEMPTY phase count is exactly n_it and the sequential parity waits below are unambiguous.
+      if (n_tt > 0) mbar_wait(BAR(B_YEMPTY + (n_it - 1) % NST), ((n_it - 1) / NST) & 1, a.err);
       for (int jt = 0; jt < n_tt; ++jt) {   // DE: rep tile of exemplar row tile jt + its teacher tile for this vocabulary tile
         const int idx = n_it + jt;
         const int ys = idx % NST; const uint32_t yph = (idx / NST) & 1;
@@ -703,7 +716,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
         const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
         const int ys = it % NST; const uint32_t yph = (it / NST) & 1;
         mbar_wait(BAR(B_YFULL + ys), yph, a.err);
+        if (it < 8) TL2(48 + it);
         mbar_wait(BAR(B_TEMPTY + s), ph ^ 1, a.err);
+        if (it < 8) TL2(16 + it);
         tc_fence_after();
         const uint32_t ya = smem_u32(sY + ys * TILE2_BYTES);
         const uint32_t A = (MODE == MODE_DE) ? ya : xa;     // rows of S = logits rows (rep)
@@ -722,6 +737,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
           const int ys = it % NST;
           if (is_teach(MODE)) mbar_wait(BAR(B_YFULL + ys), (it / NST) & 1, a.err);
           mbar_wait(BAR(B_DSFULL + s), ph, a.err);
+          if (it < 8) TL2(56 + it);
           tc_fence_after();
           const uint32_t da = smem_u32(sD + s * DS2_BYTES);
           const uint32_t ya = smem_u32(sY + ys * TILE2_BYTES);
@@ -777,6 +793,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
         v0 = x_tile * TILE;
       } else v0 = (y_lo + it) * TILE;
       mbar_wait(BAR(B_TFULL + s), ph, a.err);
+      if (threadIdx.x == 64 && it < 8) TL2(24 + it);
       tc_fence_after();
       uint32_t r[2][32];
       tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2) * 32, r[0]);
@@ -877,6 +894,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
         fence_async_smem();
         mbar_arrive(BAR(B_DSFULL + sd));
       }
+      if (threadIdx.x == 64 && it < 8) TL2(32 + it);
     }
     if (MODE == MODE_FWD) {
       const int gm = x_tile * TILE + row;
@@ -925,7 +943,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
       for (int i = half * (KP / 2); i < (half + 1) * (KP / 2); ++i) o[i] = 0.f;
     }
   }
+  if (threadIdx.x == 64) TL2(40);
   __syncthreads();
+  if (threadIdx.x == 0) TL2(41);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");

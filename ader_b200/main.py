@@ -216,8 +216,22 @@ class PeriodTrainer:
 CKPT_NAME = "checkpoint.pt"
 
 
-def save_period_checkpoint(path: str, period: int, model, dataloader, fast_exemplar, carry: dict) -> None:
-    st = {"format": 1, "period": int(period), "model": {k: (v.cpu() if isinstance(v, torch.Tensor) else v)
+PROTOCOL_KEYS = ("dataset", "exemplar_size", "lambda_", "finetune", "dropout", "ewc", "joint", "ewc_sample_num", "selection",
+                 "disable_distillation", "equal_exemplar", "fix_lambda", "batch_size", "lr", "num_blocks", "num_heads",
+                 "random_seed", "hidden_units", "maxlen", "dropout_rate", "item_num")
+
+
+def protocol_args(args) -> dict:
+    """The flags that define the run's protocol: a checkpoint only resumes under the same ones."""
+    out = {}
+    for k in PROTOCOL_KEYS:
+        v = getattr(args, k, None)
+        out[k] = os.path.basename(str(v).rstrip("/")) if k == "dataset" else v
+    return out
+
+
+def save_period_checkpoint(path: str, period: int, model, dataloader, fast_exemplar, carry: dict, args=None) -> None:
+    st = {"format": 1, "period": int(period), "args": None if args is None else protocol_args(args), "model": {k: (v.cpu() if isinstance(v, torch.Tensor) else v)
                                                       for k, v in model.state_dict().items()},
           "item_set": np.array(sorted(dataloader.item_set), dtype=np.int64),
           "exemplar_sessions": None if fast_exemplar is None else [list(map(int, x)) for x in fast_exemplar.sessions],
@@ -238,18 +252,25 @@ def rebuild_exemplars(model, sessions, teacher_width: int, maxlen: int, chunk: i
     if teacher_width is None:
         return ExemplarSet(rows, None)
     ids, _, n_in = pack_rows(rows, maxlen)
-    out = []
+    # one [E, ld] buffer with 16-byte aligned rows (ld % 4 == 0), as ExemplarGenerator._store builds it: the teacher kernels
+    # read stored logits with 128-bit loads only then
+    ld = (teacher_width + 3) // 4 * 4
+    teacher = torch.zeros((len(rows), ld), dtype=torch.float32, device=model.device)[:, :teacher_width]
     for lo in range(0, len(rows), chunk):
         r = model.rep(ids[lo:lo + chunk], n_tokens=int(n_in[lo:lo + chunk].sum()))
-        out.append(model.logits(r.contiguous(), teacher_width))
-    teacher = torch.cat(out) if out else torch.zeros((0, teacher_width), device=model.device)
+        teacher[lo:lo + chunk] = model.logits(r.contiguous(), teacher_width)
     return ExemplarSet(rows, teacher)
 
 
-def load_period_checkpoint(path: str, model, dataloader, maxlen: int):
+def load_period_checkpoint(path: str, model, dataloader, maxlen: int, args=None):
     st = torch.load(path, map_location="cpu", weights_only=False)
     if st.get("format") != 1:
         raise ValueError("%s: unknown checkpoint format" % path)
+    if args is not None and st.get("args") is not None:      # refuse to continue a run under a different protocol
+        now = protocol_args(args)
+        diff = {k: (st["args"].get(k), now[k]) for k in now if st["args"].get(k) != now[k]}
+        if diff:
+            raise ValueError("%s was written by a run with different flags (saved, now): %s" % (path, diff))
     model.load_state_dict({k: (v.to(model.device) if isinstance(v, torch.Tensor) else v) for k, v in st["model"].items()})
     dataloader.item_set = set(int(x) for x in st["item_set"])
     if isinstance(model, Ewc) and st.get("ewc"):
@@ -319,7 +340,7 @@ def run(args) -> dict:
 
     done_period = 0
     if resuming:                                               # continue after the last finished period
-        done_period, fast_exemplar, carry = load_period_checkpoint(ckpt_path, model, dataloader, args.maxlen)
+        done_period, fast_exemplar, carry = load_period_checkpoint(ckpt_path, model, dataloader, args.maxlen, args)
         best_epoch, item_num_prev, stop_counter = carry["best_epoch"], carry["item_num_prev"], carry["stop_counter"]
         metrics, stats = carry["metrics"], carry["stats"]
         ckpt = {(done_period, best_epoch): model.state_dict()}
@@ -394,6 +415,8 @@ def run(args) -> dict:
                     gc.enable()
             torch.cuda.synchronize()
             train_time += time.time() - t0
+            if model.token_overflow():                          # a step was given a token capacity below its real token count
+                raise ops._lib.AderError("period %d epoch %d: encoder token capacity overflow (tokens were dropped)" % (period, epoch))
             if period > 1 and args.ewc:                        # main.py:258-262 (no effect on train_op, S13)
                 model.variables_prev = model.snapshot_variables()
                 rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
@@ -462,7 +485,7 @@ def run(args) -> dict:
         if getattr(args, "checkpoint", True) and lead:
             save_period_checkpoint(ckpt_path, period, model, dataloader, fast_exemplar,
                                    {"best_epoch": best_epoch, "item_num_prev": item_num_prev, "stop_counter": stop_counter,
-                                    "metrics": metrics, "stats": stats})
+                                    "metrics": metrics, "stats": stats}, args)
         logs.flush()
 
     avg = {k: float(np.array(v).mean()) for k, v in metrics.items()}

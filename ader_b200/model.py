@@ -88,6 +88,8 @@ class Ader:
         self._eval_ws = ops.Workspace(self.device)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.last_row_loss: Optional[torch.Tensor] = None
+        self._tight_cap = False
+        self._last_enc = None           # (M, Tcap) of the last encoder pass (locates the overflow flag in the workspace)
 
     # ---- reference surface ----------------------------------------------------------------
     @property
@@ -107,7 +109,25 @@ class Ader:
     def _tcap(self, ids: torch.Tensor, n_tokens: Optional[int]) -> int:
         M = ids.shape[0]
         cap = M * self.hp.maxlen if n_tokens is None else max(int(n_tokens), 1)
+        self._tight_cap = n_tokens is not None and cap < M * self.hp.maxlen
         return min(max(cap, 1), M * self.hp.maxlen)
+
+    def token_overflow(self) -> bool:
+        """True if an encoder pass since the last call was given a token capacity below the real token count (the kernels
+        clamp and set flags[0] in the activation workspace: tokens were dropped, reps / gradients are wrong).  One small
+        synchronous read; the period loop calls it once per epoch, eval / selection passes after every call."""
+        buf = self._enc_ws.buf
+        if buf is None or getattr(self, "_last_enc", None) is None:
+            return False
+        M, tcap = self._last_enc
+        off = ops.encoder_ws_slot(self.ms, M, tcap, -4, 0)
+        flag = buf[off:off + 4].view(torch.int32)
+        hit = bool(int(flag.item()) != 0)
+        return hit
+
+    def _check_overflow(self):
+        if self._tight_cap and self.token_overflow():
+            raise ops._lib.AderError("encoder: n_tokens was smaller than the number of real tokens in the batch (tokens dropped)")
 
     def encode(self, ids: torch.Tensor, n_tokens: Optional[int] = None, dropout_rate: float = 0.0,
                seed: int = 0, out: Optional[torch.Tensor] = None, impl: Optional[str] = None, d_step=None):
@@ -119,12 +139,15 @@ class Ader:
         rep = out if out is not None else torch.empty((M, self.hp.hidden_units), dtype=torch.float32, device=self.device)
         ops.encoder_fwd(self.ms, self.theta, ids, tcap, ws, rep, dropout_rate, seed,
                         impl=impl or self.infer_encoder_impl, d_step=d_step)
+        self._last_enc = (M, tcap)
         return rep, tcap
 
     def rep(self, seq, n_tokens: Optional[int] = None) -> torch.Tensor:
         """fetch ``model.rep`` in eval mode (util.py:452)."""
         ids = _to_ids(seq, self.hp.maxlen, self.device)
-        return self.encode(ids, n_tokens)[0]
+        r = self.encode(ids, n_tokens)[0]
+        self._check_overflow()           # inference passes are few and large: verify the caller's token capacity every time
+        return r
 
     def logits(self, rep: torch.Tensor, max_item: int) -> torch.Tensor:
         """fetch ``model.logits`` (ADER.py:91): [M, max_item] fp32."""
@@ -192,6 +215,7 @@ class Ader:
         if self.step_impl != "groups" and self.encoder_impl == "tc" and self.loss_impl == "tc" and not _events:
             # one C call: the three groups as a fork/join DAG over library-owned side streams (same kernels, same bits)
             tcap = self._tcap(ids, n_tokens)
+            self._last_enc = (M, tcap)
             ews = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, M, tcap))
             bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, M, tcap))
             lws = self._loss_ws.get(ops.loss_tc_ws_bytes(self.ms, a))
@@ -281,6 +305,7 @@ class Ader:
         ids = _to_ids(seq, self.hp.maxlen, self.device)
         gt_t = _to_i32(gt, self.device)
         rep, _ = self.encode(ids, n_tokens)
+        self._check_overflow()
         M = ids.shape[0]
         ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
         rank = torch.empty(M, dtype=torch.int32, device=self.device)

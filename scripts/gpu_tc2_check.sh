@@ -5,7 +5,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 : > gpurun_out/legs_tc2.txt
 T0=$(date +%s)
 leg() { echo "$1 rc=$2 t=$(( $(date +%s) - T0 ))" >> gpurun_out/legs_tc2.txt; }
-for cfg in "2 160" "2 192" "1 160"; do
+for cfg in "2 160" "2 192"; do
   set -- $cfg
   ADER_B200_TC=$1 ADER_B200_TC2_N2=$2 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
     -k "tc_loss_path or tc_full_size or vocab_parallel or default_tc_path" > gpurun_out/pytest_tc_$1_$2.log 2>&1; leg "pytest_tc gen=$1 n2=$2" $?

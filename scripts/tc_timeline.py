@@ -34,6 +34,7 @@ for mode, name in enumerate(["FWD", "DREP", "DE"]):
     fast = used[np.argsort((t[used, 41] - t[used, 1]))[:1]]
     for c in list(slow) + list(fast):
         r = lambda s: (t[c, s] - t[c, 1]) / MHZ if t[c, s] else float("nan")
-        print(" CTA %3d start+%.1fus: setup %.1f | Xissue %.1f | Yissue %s | Yfull %s | Sissue %s | Tfull %s | epi_done %s | end %.1f / %.1f" % (
+        print(" CTA %3d start+%.1fus: setup %.1f | Xissue %.1f | Yissue %s | Yfull %s | Sissue %s | Tfull %s | epi_done %s | P2issue %s | end %.1f / %.1f" % (
             c, (t[c, 0] - g0) / 1e3, r(2), r(3), ["%.1f" % r(8 + i) for i in range(7)], ["%.1f" % r(48 + i) for i in range(7)],
-            ["%.1f" % r(16 + i) for i in range(7)], ["%.1f" % r(24 + i) for i in range(7)], ["%.1f" % r(32 + i) for i in range(7)], r(40), r(41)))
+            ["%.1f" % r(16 + i) for i in range(7)], ["%.1f" % r(24 + i) for i in range(7)], ["%.1f" % r(32 + i) for i in range(7)],
+            ["%.1f" % r(56 + i) for i in range(7)], r(40), r(41)))
