@@ -28,9 +28,7 @@
 //              bulk-copied instead of computed)   -> loss dot = rep.uc / coef,  d_rep -= uc
 //   MODE_DE  : after its row-tile loop the CTA of a vocabulary tile < V_prev runs one more second-MMA per exemplar
 //              row tile with the A operand NEGATED in the instruction descriptor: dE[v] -= Pc^T . rep
-#include "common.cuh"
-#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace ader {
@@ -72,32 +70,6 @@ struct TcArgs {
   int n2;                       // tc2: N of the gradient products (160, or 192 = three whole swizzle atoms; ADER_B200_TC2_N2)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && spin > (1u << 24)) {            // a broken pipeline must not hang the GPU
-      if (err) atomicExch(err, 1);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 // one T128 tile as LOAD_SPLIT independent bulk copies (a single 40 KB bulk copy keeps only a few
 // 128 B requests in flight: measured ~50 us per tile from HBM; many smaller ones overlap)
 constexpr int LOAD_SPLIT = 20;
@@ -107,62 +79,6 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const uint8_t* src, uint
   for (int i = 0; i < LOAD_SPLIT; ++i)
     bulk_g2s(dst + i * (TILE_BYTES / LOAD_SPLIT), src + i * (TILE_BYTES / LOAD_SPLIT), TILE_BYTES / LOAD_SPLIT, bar);
 }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 consecutive TMEM columns of this thread's lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
-}
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-// wait for outstanding tcgen05.ld; the registers are passed as in/out operands so the compiler cannot
-// schedule their first use ahead of the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
-}
-__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start>>4 [0,14),
-// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
-// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn, int a_neg = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_neg << 13) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 // per-row description of the loss (shared by all modes)
 struct RowInfo {
   int kind;           // 0 none (row >= M), 1 softmax row of width vlim (one-hot label, or label = -1 for distillation rows)
@@ -576,10 +492,6 @@ __host__ __device__ constexpr int n_stages2(int mode) { return 3; }
 __host__ __device__ constexpr int n_ds2(int mode) { return mode == MODE_FWD ? 0 : 1; }
 constexpr int smem_tc2(int mode) { return 1024 + (1 + n_stages2(mode)) * TILE2_BYTES + n_ds2(mode) * DS2_BYTES + 256; }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
 // 128 rows x 160 (192) k starting at matrix row `row0`
 __device__ __forceinline__ void load_tile2(uint32_t dst, const CUtensorMap* tm, int row0, uint32_t bar) {
   mbar_expect_tx(bar, TILE2_BYTES);
@@ -591,11 +503,6 @@ __device__ __forceinline__ void load_ds2(uint32_t dst, const CUtensorMap* tm, in
   mbar_expect_tx(bar, DS2_BYTES);
 #pragma unroll
   for (int j = 0; j < 2; ++j) tma_load_2d(dst + j * REG2, tm, col0 + 64 * j, row0, bar);
-}
-// shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2 in bits [61,64)), version 1
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kstep) {      // 16 k of a K-major tile
   return make_desc_sw128(base + (kstep >> 2) * REG2 + (kstep & 3) * 32, 16, 1024);
@@ -795,102 +702,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
       mbar_wait(BAR(B_TFULL + s), ph, a.err);
       if (threadIdx.x == 64 && it < 8) TL2(24 + it);
       tc_fence_after();
-      uint32_t r[2][32];
-      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2) * 32, r[0]);
-      tmem_ld32_nowait(tmem + tlane + s * 128 + (half * 2 + 1) * 32, r[1]);
-      tmem_ld_wait(r[0]);
-      tmem_ld_wait(r[1]);
-      tc_fence_before();
-      mbar_arrive(BAR(B_TEMPTY + s));
+      // This thread's 64 columns in four chunks of 16: the TMEM load of chunk c+1 is in flight while chunk c goes through
+      // the exponentials (a 128x128 fp32 tile is 64 KB of TMEM reads: as long as the MUFU work, so they must overlap);
+      // the S buffer goes back to the MMA warp as soon as the last chunk has landed.
+      uint32_t rb[2][16];
+      const uint32_t tcol = tmem + tlane + s * 128 + half * 64;
+      tmem_ld16_nowait(tcol, rb[0]);
+      tmem_ld_wait16(rb[0]);
       const int vb0 = v0 + half * 64;
       const bool full = (ri.kind != 0) && (vb0 + 64 <= ri.vlim);
-      if (MODE == MODE_FWD) {
-        if (full) {
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t pk[32];                         // BWD: this thread's 64 gradient values as bf16 pairs
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&cur)[16] = rb[c & 1];
+        if (c < 3) tmem_ld16_nowait(tcol + (c + 1) * 16, rb[(c + 1) & 1]);
+        const int vb = vb0 + c * 16;
+        if (MODE == MODE_FWD) {
+          if (full) {
+            float cm = __uint_as_float(cur[0]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[c][i]));
-          const float nm = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-          sum *= ex2((mx - nm) * LOG2E);
-          mx = nm;
-          const float nm2 = nm * LOG2E;
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 1; i < 16; ++i) cm = fmaxf(cm, __uint_as_float(cur[i]));
+            const float nm = fmaxf(mx, cm);
+            sum *= ex2((mx - nm) * LOG2E);
+            mx = nm;
+            const float nm2 = nm * LOG2E;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+            for (int i = 0; i < 16; ++i) s4[i & 3] += ex2(fmaf(__uint_as_float(cur[i]), LOG2E, -nm2));
+            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            if (ri.label >= vb && ri.label < vb + 16) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s4[i & 3] += ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -nm2));
-          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          if (ri.label >= vb0 && ri.label < vb0 + 64) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (vb0 + c * 32 + i == ri.label) lab = __uint_as_float(r[c][i]);
-          }
-        } else if (ri.kind != 0 && vb0 < ri.vlim) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int vb = vb0 + c * 32;
-            if (vb >= ri.vlim) break;
+              for (int i = 0; i < 16; ++i) if (vb + i == ri.label) lab = __uint_as_float(cur[i]);
+            }
+          } else if (ri.kind != 0 && vb < ri.vlim) {               // boundary chunk: per-element checks
             float cm = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(r[c][i]));
+            for (int i = 0; i < 16; ++i) if (vb + i < ri.vlim) cm = fmaxf(cm, __uint_as_float(cur[i]));
             const float nm = fmaxf(mx, cm);
             sum *= ex2((mx - nm) * LOG2E);
             mx = nm;
             const float nm2 = nm * LOG2E;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const int v = vb + i;
               if (v < ri.vlim) {
-                const float sv = __uint_as_float(r[c][i]);
+                const float sv = __uint_as_float(cur[i]);
                 sum += ex2(fmaf(sv, LOG2E, -nm2));
                 if (v == ri.label) lab = sv;
               }
             }
           }
-        }
-      } else {
-        const int sd = it % NDS; const uint32_t dph = (it / NDS) & 1;
-        uint32_t pk[2][16];                    // this thread's 64 gradient values as bf16 pairs
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int vb = vb0 + c * 32;
-          float g[32];
+        } else {
+          float g[16];
           if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
-            if (ri.label >= vb && ri.label < vb + 32) {
+            for (int i = 0; i < 16; ++i) g[i] = ri.coef * ex2(fmaf(__uint_as_float(cur[i]), LOG2E, -ri.lse2));
+            if (ri.label >= vb && ri.label < vb + 16) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
+              for (int i = 0; i < 16; ++i) if (vb + i == ri.label) g[i] -= ri.coef;
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const int v = vb + i;
               float gv = 0.f;
               if (ri.kind != 0 && v < ri.vlim) {
-                const float p = ex2(fmaf(__uint_as_float(r[c][i]), LOG2E, -ri.lse2));
+                const float p = ex2(fmaf(__uint_as_float(cur[i]), LOG2E, -ri.lse2));
                 gv = ri.coef * (p - (v == ri.label ? 1.f : 0.f));
               }
               g[i] = gv;
             }
           }
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
+          for (int u = 0; u < 8; ++u) {
             __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * u], g[2 * u + 1]);
-            pk[c][u] = *reinterpret_cast<uint32_t*>(&h);
+            pk[c * 8 + u] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
+        if (c < 3) tmem_ld_wait16(rb[(c + 1) & 1]);
+        if (c == 2) {                          // all 64 columns are in registers: hand the S buffer back
+          tc_fence_before();
+          mbar_arrive(BAR(B_TEMPTY + s));
+        }
+      }
+      if (MODE != MODE_FWD) {
+        const int sd = it % NDS; const uint32_t dph = (it / NDS) & 1;
         // the exponentials above overlap the second product of the previous tile; only the stores wait for its dS buffer
         mbar_wait(BAR(B_DSEMPTY + sd), dph ^ 1, a.err);
         // region `half` (this thread's 64 columns), row `row`: eight 16-byte chunks, chunk j at position j ^ (row & 7)
         uint8_t* drow = sD + sd * DS2_BYTES + half * REG2 + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = j >> 2, u = (j & 3) * 4;
-          *reinterpret_cast<uint4*>(drow + ((j ^ (row & 7)) << 4)) = make_uint4(pk[c][u], pk[c][u + 1], pk[c][u + 2], pk[c][u + 3]);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(drow + ((j ^ (row & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_async_smem();
         mbar_arrive(BAR(B_DSFULL + sd));
       }
@@ -905,30 +808,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
     } else if (n_it > 0) {
       mbar_wait(BAR(B_ACC), 0, a.err);
       tc_fence_after();
+      // accumulator [128 rows, 160] -> the (now idle) Y stages, row pitch DE_LD floats (conflict-free 16-byte row writes) ...
 #pragma unroll 1
       for (int c4 = half; c4 < KP / 32; c4 += 2) {
         uint32_t r[32];
         tmem_ld32(tmem + tlane + ACC_COL + c4 * 32, r);
-        if (MODE == MODE_DREP || MODE == MODE_TU) {
-          float* o = (MODE == MODE_DREP)
-                         ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE + row) * KP + c4 * 32
-                         : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE + row) * KP + c4 * 32;
+        float* stg = reinterpret_cast<float*>(sY) + row * DE_LD + c4 * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stg + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                                                             __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        } else {                              // DE: stage the [128 v, 160] tile in the (now idle) Y stages
-          float* stg = reinterpret_cast<float*>(sY) + row * DE_LD + c4 * 32;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(stg + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                              __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        }
       }
-      if (MODE == MODE_DE) {
-        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-        const float* stg = reinterpret_cast<const float*>(sY);
-        const int ew = warp - 2;
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+      const float* stg = reinterpret_cast<const float*>(sY);
+      const int ew = warp - 2;
+      if (MODE == MODE_DREP || MODE == MODE_TU) {
+        // ... and out as ONE contiguous 80 KB block (partials are [rows][160] fp32): fully coalesced 16-byte stores
+        float* o = (MODE == MODE_DREP) ? a.drep_part + ((size_t)chunk * a.n_mtiles * TILE + (size_t)x_tile * TILE) * KP
+                                       : a.u_part + ((size_t)chunk * a.n_et * TILE + (size_t)(x_tile - a.x0_t) * TILE) * KP;
+        for (int f = ew * 32 + lane; f < TILE * (KP / 4); f += NEPI) {
+          const int rr = f / (KP / 4), c4 = f % (KP / 4);
+          *reinterpret_cast<float4*>(o + (size_t)rr * KP + c4 * 4) = *reinterpret_cast<const float4*>(stg + rr * DE_LD + c4 * 4);
+        }
+      } else {                                // DE: whole table rows (d floats, contiguous) per warp
         for (int rr = ew; rr < TILE; rr += NEPI / 32) {
           const int v = x_tile * TILE + rr;
           if (v >= a.V) break;
@@ -1266,31 +1168,6 @@ static int tc2_n2() {
   if (!n) { const char* e = getenv("ADER_B200_TC2_N2"); n = (e && atoi(e) == 192) ? 192 : 160; }
   return n;
 }
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// bf16 matrix [rows][cols], row pitch in bytes (multiple of 16); box = 64 columns (128 B, one swizzle span) x 128 rows
-static int make_map2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes) {
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
-      cudaGetLastError();
-      return fail(-3, "loss_tc: cuTensorMapEncodeTiled is unavailable (driver too old?)");
-    }
-    enc = (EncodeTiledFn)fn;
-  }
-  const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstr[1] = {pitch_bytes};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(-3, "loss_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return 0;
-}
 struct TcMaps { CUtensorMap rep, e, pt; };
 static int make_tc_maps(const TcWs& w, int nm, int nv, TcMaps& mp) {
   if (int e = make_map2d(&mp.rep, w.rep_tiles, ROW16, (uint64_t)nm * TILE, ROW16 * 2)) return e;
@@ -1405,10 +1282,10 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
   TcMaps mp;
   if (g2) { if (int e = make_tc_maps(w, nm, nv, mp)) return e; }
   if (phase_mask == 4) {      // measurement only: the three tensor-core kernels on an already prepared workspace
-    if (g2) {
-      k_tc2<MODE_FWD><<<nm * nc, NTHREADS, smem_tc2(MODE_FWD), st>>>(t, mp.rep, mp.e, mp.pt);
-      k_tc2<MODE_DREP><<<nm * nc, NTHREADS, smem_tc2(MODE_DREP), st>>>(t, mp.rep, mp.e, mp.pt);
-      if (grad) k_tc2<MODE_DE><<<nv, NTHREADS, smem_tc2(MODE_DE), st>>>(t, mp.rep, mp.e, mp.pt);
+    if (g2) {               // launched as in the step: programmatic dependent launches along the chain
+      launch_chain(k_tc2<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_FWD), st, true, t, mp.rep, mp.e, mp.pt);
+      launch_chain(k_tc2<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_DREP), st, true, t, mp.rep, mp.e, mp.pt);
+      if (grad) launch_chain(k_tc2<MODE_DE>, dim3(nv), dim3(NTHREADS), (size_t)smem_tc2(MODE_DE), st, true, t, mp.rep, mp.e, mp.pt);
     } else {
       k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
       k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);

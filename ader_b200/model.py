@@ -76,6 +76,9 @@ class Ader:
         # passes (rep / eval / herding: bit-exact index parity with the fp32 reference) use infer_encoder_impl.
         self.encoder_impl = getattr(args, "encoder_impl", None) or ("exact" if self.loss_impl == "exact" else "tc")
         self.infer_encoder_impl = getattr(args, "infer_encoder_impl", "exact")
+        # evaluation ranks: "tc" = fused tcgen05 scoring + exact refinement (identical ranks), "exact" = fp32 [M, V] scores
+        self.eval_impl = getattr(args, "eval_impl", None) or os.environ.get("ADER_B200_EVAL", "tc")
+        self.eval_fallbacks = 0
         # how a tc + tc training pass is issued: "dag" = ader_train_fwd_bwd_tc (fork/join over side streams),
         # "serial" = the same entry on one stream, "groups" = the three single-group entry points one after another
         self.step_impl = getattr(args, "step_impl", None) or os.environ.get("ADER_B200_STEP_IMPL", "dag")
@@ -307,8 +310,18 @@ class Ader:
         rep, _ = self.encode(ids, n_tokens)
         self._check_overflow()
         M = ids.shape[0]
-        ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
         rank = torch.empty(M, dtype=torch.int32, device=self.device)
+        if k <= 0 and self.eval_impl == "tc" and self.hp.hidden_units <= 160:
+            # metrics only need rank(gt): tcgen05 scores + exact refinement of the columns inside the certainty band
+            # (ader_eval_rank_tc: identical ranks, the [M, V] scores are never written)
+            ws = self._eval_ws.get(ops.eval_rank_tc_ws_bytes(self.ms, M, max_item))
+            over = torch.zeros(1, dtype=torch.int32, device=self.device)
+            ops.eval_rank_tc(self.ms, self.theta, rep, gt_t, max_item, ws, rank, over)
+            if int(over.item()) == 0:
+                empty = torch.empty((M, 1), dtype=torch.int32, device=self.device)
+                return rank, empty, empty.float()
+            self.eval_fallbacks += 1          # a band held more than ADER_EVAL_CAND_CAP columns: exact path for this batch
+        ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
         items = torch.empty((M, max(k, 1)), dtype=torch.int32, device=self.device)
         scores = torch.empty((M, max(k, 1)), dtype=torch.float32, device=self.device)
         ops.eval_rank_topk(self.ms, self.theta, rep, gt_t, max_item, k, ws, rank, items, scores)

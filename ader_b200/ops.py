@@ -268,6 +268,20 @@ def eval_rank_topk(ms: AderModel, theta, rep, gt, V: int, k: int, ws, rank, topk
                                           _ptr(rank), _ptr(topk_item), _ptr(topk_score), _stream()), "eval_rank_topk")
 
 
+def eval_rank_tc_ws_bytes(ms: AderModel, R: int, V: int) -> int:
+    n = _lib.load().ader_eval_rank_tc_ws_bytes(C.byref(ms), R, V)
+    if n == 0:
+        raise _lib.AderError("eval_rank_tc_ws_bytes: bad model / sizes")
+    return n
+
+
+def eval_rank_tc(ms: AderModel, theta, rep, gt, V: int, ws, rank, overflow):
+    """Fused tensor-core ranking (scores never materialised); overflow[0] != 0 -> use eval_rank_topk for this batch."""
+    _require_cuda(theta, rep, gt, ws, rank, overflow)
+    check(_lib.load().ader_eval_rank_tc(C.byref(ms), _ptr(theta), _ptr(rep), _ptr(gt), rep.shape[0], V, _ptr(ws), _ptr(rank),
+                                        _ptr(overflow), _stream()), "eval_rank_tc")
+
+
 def herding_ws_bytes(ms: AderModel, N: int) -> int:
     n = _lib.load().ader_herding_ws_bytes(C.byref(ms), N)
     if n == 0:

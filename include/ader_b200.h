@@ -190,6 +190,18 @@ int32_t ader_eval_rank_topk(const AderModel* m, const float* theta, const float*
                             int32_t M, int32_t V, int32_t k, void* ws, int32_t* rank,
                             int32_t* topk_item, float* topk_score, void* stream);
 
+/* The same ranks on the tcgen05 tensor cores, the [R, V] score matrix never written (the metrics of util.py:329-339 only
+ * read rank(gt)).  Filter and refine: the exact fp32 score of the ground-truth item anchors a certainty band
+ * s_gt +- eps_i, eps_i = 2^-12 ||rep_i|| max_j ||E_j||; approximate scores from a two-term bf16 split of both operands
+ * (three products hi.hi + hi.lo + lo.hi accumulated in TMEM) are counted when certainly above, and the few columns inside
+ * the band are re-scored with the exact fmaf chain of ader_eval_rank_topk -- ranks are identical to that entry, ties
+ * included.  overflow[0] (device int) != 0: a row had more than ADER_EVAL_CAND_CAP columns inside its band; the caller
+ * must then use ader_eval_rank_topk for this batch.  Needs hidden_units <= 160. */
+#define ADER_EVAL_CAND_CAP 256
+size_t  ader_eval_rank_tc_ws_bytes(const AderModel* m, int32_t R, int32_t V);
+int32_t ader_eval_rank_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
+                          int32_t V, void* ws, int32_t* rank, int32_t* overflow, void* stream);
+
 /* ---- exemplar selection: util.py:401-461 (subsystem 4) ---------------------------------- */
 /* Segmented herding.  rep [N,d]; segment s owns candidate rows cand[seg_off[s] .. seg_off[s+1])
  * (indices into rep, in the reference's sess_by_item order); quota[s] = min(m, n_s);
