@@ -94,6 +94,8 @@ SIGNATURES = {
     "ader_ipc_open": (C.c_int32, [_P, C.POINTER(C.c_void_p)]),
     "ader_ipc_close": (C.c_int32, [_P]),
     "ader_gather_rows_i32": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "ader_gather_batch_q": (C.c_int32, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "ader_queue_advance": (C.c_int32, [_P, _P]),
     "ader_gather_batch": (C.c_int32, [_P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 

@@ -1411,3 +1411,50 @@ extern "C" int32_t ader_gather_batch(const int32_t* t_ids, const int32_t* t_lab,
   ADER_CHECK_LAUNCH("gather_batch");
   return 0;
 }
+
+// The same batch assembly fed from an epoch-resident index queue (the host leaves the training loop): `q`
+// holds the row indices of every step of the epoch back to back ([train indices | exemplar indices] per step), q_off[s]
+// is where step s starts, *counter is the running step.  A captured step graph replays with no host-to-device traffic at
+// all; ader_queue_advance (stream-ordered behind the gather) moves to the next step.
+__global__ void k_gather_batch_q(const int* __restrict__ t_ids, const int* __restrict__ t_lab, int n_train,
+                                 const int* __restrict__ e_ids, const int* __restrict__ e_aux, int n_ex,
+                                 const int* __restrict__ q, const long long* __restrict__ q_off, const int* __restrict__ counter,
+                                 int width, int* __restrict__ ids, int* __restrict__ pos, int* __restrict__ aux) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w1 = width + 1;
+  if (e >= (long long)(n_train + n_ex) * w1) return;
+  const int* ti = q + q_off[*counter];
+  const int* ei = ti + n_train;
+  const int row = (int)(e / w1), c = (int)(e % w1);
+  if (row < n_train) {
+    const long long src = ti[row];
+    if (c < width) ids[(long long)row * width + c] = t_ids[src * width + c];
+    else pos[row] = t_lab[src];
+  } else {
+    const int r = row - n_train;
+    const long long src = ei[r];
+    if (c < width) ids[(long long)row * width + c] = e_ids[src * width + c];
+    else if (aux) aux[r] = e_aux ? e_aux[src] : 0;
+  }
+}
+__global__ void k_queue_advance(int* counter) { *counter += 1; }
+
+extern "C" int32_t ader_gather_batch_q(const int32_t* t_ids, const int32_t* t_lab, int32_t n_train, const int32_t* e_ids,
+                                       const int32_t* e_aux, int32_t n_ex, const int32_t* q, const int64_t* q_off,
+                                       const int32_t* counter, int32_t width, int32_t* ids, int32_t* pos, int32_t* aux,
+                                       void* stream) {
+  ADER_CHECK_ARG(n_train >= 0 && n_ex >= 0 && width > 0 && ids && q && q_off && counter, "gather_batch_q: bad argument");
+  ADER_CHECK_ARG(n_train == 0 || (t_ids && t_lab && pos), "gather_batch_q: NULL train pointer");
+  ADER_CHECK_ARG(n_ex == 0 || e_ids, "gather_batch_q: NULL exemplar pointer");
+  if (n_train + n_ex == 0) return 0;
+  k_gather_batch_q<<<cdiv((long long)(n_train + n_ex) * (width + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+      t_ids, t_lab, n_train, e_ids, e_aux, n_ex, q, (const long long*)q_off, counter, width, ids, pos, aux);
+  ADER_CHECK_LAUNCH("gather_batch_q");
+  return 0;
+}
+extern "C" int32_t ader_queue_advance(int32_t* counter, void* stream) {
+  ADER_CHECK_ARG(counter, "queue_advance: NULL pointer");
+  k_queue_advance<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+  ADER_CHECK_LAUNCH("queue_advance");
+  return 0;
+}

@@ -709,6 +709,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
       const uint32_t tcol = tmem + tlane + s * 128 + half * 64;
       tmem_ld16_nowait(tcol, rb[0]);
       tmem_ld_wait16(rb[0]);
+      if (threadIdx.x == 64 && it == 2) TL2(4);
       const int vb0 = v0 + half * 64;
       const bool full = (ri.kind != 0) && (vb0 + 64 <= ri.vlim);
       uint32_t pk[32];                         // BWD: this thread's 64 gradient values as bf16 pairs
@@ -785,10 +786,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
           mbar_arrive(BAR(B_TEMPTY + s));
         }
       }
+      if (threadIdx.x == 64 && it == 2) TL2(5);
       if (MODE != MODE_FWD) {
         const int sd = it % NDS; const uint32_t dph = (it / NDS) & 1;
         // the exponentials above overlap the second product of the previous tile; only the stores wait for its dS buffer
         mbar_wait(BAR(B_DSEMPTY + sd), dph ^ 1, a.err);
+        if (threadIdx.x == 64 && it == 2) TL2(6);
         // region `half` (this thread's 64 columns), row `row`: eight 16-byte chunks, chunk j at position j ^ (row & 7)
         uint8_t* drow = sD + sd * DS2_BYTES + half * REG2 + row * 128;
 #pragma unroll
@@ -1282,10 +1285,12 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
   TcMaps mp;
   if (g2) { if (int e = make_tc_maps(w, nm, nv, mp)) return e; }
   if (phase_mask == 4) {      // measurement only: the three tensor-core kernels on an already prepared workspace
-    if (g2) {               // launched as in the step: programmatic dependent launches along the chain
-      launch_chain(k_tc2<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_FWD), st, true, t, mp.rep, mp.e, mp.pt);
-      launch_chain(k_tc2<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_DREP), st, true, t, mp.rep, mp.e, mp.pt);
-      if (grad) launch_chain(k_tc2<MODE_DE>, dim3(nv), dim3(NTHREADS), (size_t)smem_tc2(MODE_DE), st, true, t, mp.rep, mp.e, mp.pt);
+    if (g2) {               // launched as in the step: programmatic dependent launches along the chain (ADER_B200_PDL=0: plain)
+      const char* pe = getenv("ADER_B200_PDL");
+      const bool pdl = !(pe && pe[0] == '0');
+      launch_chain(k_tc2<MODE_FWD>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_FWD), st, pdl, t, mp.rep, mp.e, mp.pt);
+      launch_chain(k_tc2<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_DREP), st, pdl, t, mp.rep, mp.e, mp.pt);
+      if (grad) launch_chain(k_tc2<MODE_DE>, dim3(nv), dim3(NTHREADS), (size_t)smem_tc2(MODE_DE), st, pdl, t, mp.rep, mp.e, mp.pt);
     } else {
       k_tc_logits<MODE_FWD><<<nm * nc, NTHREADS, smem_fwd, st>>>(t);
       k_tc_logits<MODE_DREP><<<nm * nc, NTHREADS, smem_bwd, st>>>(t);

@@ -84,7 +84,7 @@ class GraphStep:
     """
 
     def __init__(self, model, n_train: int, n_ex: int, max_item: int, lr: float, dropout_rate: float = 0.0,
-                 teacher: Optional[torch.Tensor] = None, sources=None, tcaps: Optional[Sequence[int]] = None):
+                 teacher: Optional[torch.Tensor] = None, sources=None, tcaps: Optional[Sequence[int]] = None, queue=None):
         if dropout_rate > 0.0 and model.encoder_impl != "tc":
             raise ValueError("graph replay with dropout needs the tc encoder (device-side dropout counter)")
         self.model, self.n_train, self.n_ex = model, int(n_train), int(n_ex)
@@ -103,6 +103,10 @@ class GraphStep:
         if self.n_ex > 0 and model.mode == model.ER:
             self.aux.fill_(1)
         self.sources = sources
+        # epoch-resident index queue (q int32, q_off int64, counter int32[1]) shared by the GraphSteps of a period: the
+        # "queued" graph form gathers step `counter` from it and advances the counter -- no host-to-device copy per step
+        self.queue = queue
+        self.graphs_q = {}
         if sources is not None:
             self.ti = torch.zeros(self.n_train, dtype=torch.int32, device=dev)
             self.ei = torch.zeros(max(self.n_ex, 1), dtype=torch.int32, device=dev)
@@ -133,6 +137,13 @@ class GraphStep:
             ops.gather_batch(t_ids, t_lab, self.ti, e_ids, e_aux, self.ei[:self.n_ex], self.ids, self.pos, self.aux[:self.n_ex])
         else:
             ops.gather_batch(t_ids, t_lab, self.ti, None, None, None, self.ids, self.pos, None)
+
+    def _gather_q(self):
+        t_ids, t_lab, e_ids, e_aux = self.sources
+        q, q_off, counter = self.queue
+        ops.gather_batch_q(t_ids, t_lab, self.n_train, e_ids if self.n_ex > 0 else None, e_aux if self.n_ex > 0 else None,
+                           self.n_ex, q, q_off, counter, self.ids, self.pos, self.aux[:self.n_ex] if self.n_ex > 0 else None)
+        ops.queue_advance(counter)
 
     def _eager(self, tcap: int, device_step: bool, indexed: bool = False):
         m = self.model
@@ -169,15 +180,19 @@ class GraphStep:
         self._held_more = []
         self.graphs_idx = {}                   # index-fed form: batch gather + step in ONE graph (no gap between two replays)
 
-    def _graph_for(self, tcap: int, indexed: bool) -> torch.cuda.CUDAGraph:
-        table = self.graphs_idx if indexed else self.graphs
+    def _graph_for(self, tcap: int, indexed) -> torch.cuda.CUDAGraph:
+        """indexed: False = rows fed into the static batch buffer, True = index-fed (gather inside the graph),
+        "q" = gather from the epoch-resident queue inside the graph."""
+        table = self.graphs_q if indexed == "q" else (self.graphs_idx if indexed else self.graphs)
         g = table.get(tcap)
         if g is None:
             m = self.model
             gs = m.global_step                 # capture records launches, it runs nothing: only the host counter moves
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self._pool):
-                if indexed:
+                if indexed == "q":
+                    self._gather_q()
+                elif indexed:
                     self._gather()
                 self._eager(tcap, True, indexed=indexed)
             self._pool = g.pool()
@@ -196,7 +211,7 @@ class GraphStep:
                 self._graph_for(tcap, form)
 
     # ---- replay ---------------------------------------------------------------------------------------
-    def _replay(self, n_tokens: Optional[int], indexed: bool = False):
+    def _replay(self, n_tokens: Optional[int], indexed=False):
         cap = self.tcaps[-1]
         if n_tokens is not None:
             for t in self.tcaps:
@@ -239,6 +254,12 @@ class GraphStep:
         ev = torch.cuda.Event()
         ev.record()
         return PendingLoss(self._loss_host[k], ev)
+
+    def run_queued(self, n_tokens: Optional[int] = None):
+        """Replay the step whose rows are the next entry of the epoch-resident queue (no copies: the host only launches)."""
+        if self.queue is None or self.sources is None:
+            raise ValueError("GraphStep was built without an index queue")
+        return self._replay(n_tokens, indexed="q")
 
     def run_indices(self, ti, ei=None, n_tokens: Optional[int] = None):
         """Row indices into the ``sources`` matrices (host arrays or device tensors)."""

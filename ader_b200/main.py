@@ -76,6 +76,7 @@ def build_parser() -> argparse.ArgumentParser:             # main.py:75-108 (typ
     # data parallel under torchrun (one process per GPU).  Every rank runs the same host protocol with the same
     # seeds (identical batches, splits, exemplar sets); a step's train rows and exemplar rows are split over the ranks,
     # losses use the global-mean denominators, gradients are summed (ader_b200/dist.py), evaluation rows are sharded.
+    p.add_argument("--epoch_queue", default=True, type=lambda v: str(v).lower() not in ("0", "false", "no"))  # host out of the step loop
     p.add_argument("--dp", default=False, type=lambda v: str(v).lower() not in ("0", "false", "no"))
     return p
 
@@ -104,6 +105,15 @@ class PeriodTrainer:
         self.n_eager = 0                # steps issued launch by launch (rare batch geometry / no graph)
         # data parallel: this rank's shard of every batch (train rows and exemplar rows split separately, main.py:229 order kept)
         self.rank, self.world = getattr(args, "dp_rank", 0), getattr(args, "dp_world", 1)
+        # epoch-resident index queue: the row indices of a whole epoch are uploaded once, every step is then a graph
+        # replay that gathers its batch from the queue on the device (run_epoch)
+        steps = max(train_sampler.batch_num(), 1)
+        width = train_sampler.batch_size + (exemplar_sampler.batch_size if exemplar_sampler is not None else 0)
+        self.q = torch.zeros(steps * max(width, 1), dtype=torch.int32, device=dev)
+        self.q_off = torch.zeros(steps, dtype=torch.int64, device=dev)
+        self.q_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._q_host = torch.zeros(steps * max(width, 1), dtype=torch.int32).pin_memory()
+        self._qoff_host = torch.zeros(steps, dtype=torch.int64).pin_memory()
 
     MAX_GEOM = 8
 
@@ -162,9 +172,76 @@ class PeriodTrainer:
         caps = [int(mean_tok * f) + 64 for f in (1.1, 1.3, 1.7)]
         gs = m.graph_step(n_train, n_ex, self.max_item, args.lr, args.dropout_rate, teacher=teacher,
                           sources=(self.t_ids, self.t_lab, e_ids, e_aux) if self.es is not None
-                          else (self.t_ids, self.t_lab, None, None), tcaps=caps)
+                          else (self.t_ids, self.t_lab, None, None), tcaps=caps, queue=(self.q, self.q_off, self.q_counter))
         self.gs_map[key] = gs
         return gs
+
+    def run_epoch(self, n_steps: int):
+        """One epoch (main.py:220-256) with the host out of the loop: the samplers are advanced for all `n_steps` steps first
+        (same calls in the same order as step-by-step, so both host RNG streams move identically), the row indices go to
+        the device in ONE copy, and every step is a graph replay that gathers its batch from that queue.  A step whose
+        batch geometry has no graph (rare tail batches) runs eagerly from the same queue."""
+        m, dev, L = self.model, self.model.device, self.model.hp.maxlen
+        plan = []
+        qh, oh = self._q_host.numpy(), self._qoff_host.numpy()
+        o = 0
+        for s_ in range(n_steps):
+            ti = self.ts.next_indices()
+            ei = self.es.next_indices() if self.es is not None else np.zeros(0, np.int64)
+            key = (len(ti), len(ei))
+            self.rows_seen += len(ti) + len(ei)
+            if self.world > 1:
+                (tl, th), (el, eh) = self._shard(len(ti), len(ei))
+                ti, ei = ti[tl:th], ei[el:eh]
+            n_tok = int(self.t_nin[ti].sum()) + (int(self.e_nin[ei].sum()) if self.es is not None else 0)
+            oh[s_] = o
+            qh[o:o + len(ti)] = ti
+            qh[o + len(ti):o + len(ti) + len(ei)] = ei
+            o += len(ti) + len(ei)
+            plan.append((key, len(ti), len(ei), n_tok))
+        self.q.copy_(self._q_host, non_blocking=True)
+        self.q_off.copy_(self._qoff_host, non_blocking=True)
+        self.q_counter.zero_()
+        loss = None
+        for key, nt, ne, n_tok in plan:
+            gs = self._graph(*key) if (key[0] > 0 and (self.es is None or key[1] > 0)) else None
+            if self.world > 1:
+                m.global_counts = key
+            if gs is not None:
+                loss = gs.run_queued(n_tok)
+                continue
+            self.n_eager += 1                                    # rare batch geometry: eager launches, same queue
+            ids = torch.empty((nt + ne, L), dtype=torch.int32, device=dev)
+            pos = torch.empty(nt, dtype=torch.int32, device=dev)
+            aux = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+            e_aux = None
+            if self.es is not None:
+                e_aux = self.e_lab if m.disable_distillation else self._teacher_rows()
+            ops.gather_batch_q(self.t_ids, self.t_lab, nt, self.e_ids if ne else None, e_aux if ne else None, ne, self.q, self.q_off,
+                               self.q_counter, ids, pos, aux[:ne] if ne else None)
+            ops.queue_advance(self.q_counter)
+            if self.es is None or ne == 0:
+                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
+            elif m.disable_distillation:
+                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_pos=aux[:ne], n_tokens=n_tok)
+            else:
+                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_logits=self.es.teacher,
+                                    teacher_rows=aux[:ne], n_tokens=n_tok)
+        return loss
+
+    def _teacher_rows(self):
+        if getattr(self, "_trows", None) is None:
+            self._trows = torch.as_tensor(np.asarray(self.es.logits, dtype=np.int32)).to(self.model.device)
+        return self._trows
+
+    def can_queue(self) -> bool:
+        """The queued epoch needs GPU-resident exemplar logits (ExemplarSet.teacher) or no exemplars at all."""
+        if not getattr(self.args, "graph", True):
+            return False
+        m = self.model
+        if m.encoder_impl != "tc" and self.args.dropout_rate > 0:
+            return False
+        return self.es is None or m.disable_distillation or getattr(self.es, "teacher", None) is not None
 
     def step(self):
         loss = self._step()
@@ -408,8 +485,11 @@ def run(args) -> dict:
             gc_on = gc.isenabled()
             gc.disable()
             try:
-                for _ in range(batch_num):
-                    trainer.step()
+                if trainer.trace is None and trainer.can_queue() and getattr(args, "epoch_queue", True):
+                    trainer.run_epoch(batch_num)
+                else:
+                    for _ in range(batch_num):
+                        trainer.step()
             finally:
                 if gc_on:
                     gc.enable()

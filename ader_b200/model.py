@@ -295,11 +295,11 @@ class Ader:
         return (max_item, lr, 0.0, None, None)
 
     def graph_step(self, n_train: int, n_ex: int, max_item: int, lr: Optional[float] = None,
-                   dropout_rate: Optional[float] = None, teacher=None, sources=None, tcaps=None):
+                   dropout_rate: Optional[float] = None, teacher=None, sources=None, tcaps=None, queue=None):
         """The same train step captured as CUDA graphs for a fixed batch geometry (see ader_b200/graph.py)."""
         from .graph import GraphStep
         return GraphStep(self, n_train, n_ex, max_item, self.args.lr if lr is None else lr,
-                         self.args.dropout_rate if dropout_rate is None else dropout_rate, teacher, sources, tcaps)
+                         self.args.dropout_rate if dropout_rate is None else dropout_rate, teacher, sources, tcaps, queue)
 
     # ---- evaluation ---------------------------------------------------------------------------
     def rank_topk(self, seq, gt, max_item: int, k: int = 20, n_tokens: Optional[int] = None):

@@ -321,6 +321,18 @@ def gather_batch(t_ids, t_lab, ti, e_ids, e_aux, ei, ids, pos, aux):
                                         ids.shape[1], _ptr(ids), _ptr(pos), _ptr(aux), _stream()), "gather_batch")
 
 
+def gather_batch_q(t_ids, t_lab, n_train: int, e_ids, e_aux, n_ex: int, q, q_off, counter, ids, pos, aux):
+    """Batch assembly of step `counter[0]` from the epoch-resident index queue (q int32, q_off int64)."""
+    _require_cuda(t_ids, t_lab, e_ids, e_aux, q, q_off, counter, ids, pos, aux)
+    check(_lib.load().ader_gather_batch_q(_ptr(t_ids), _ptr(t_lab), n_train, _ptr(e_ids), _ptr(e_aux), n_ex, _ptr(q), _ptr(q_off),
+                                          _ptr(counter), ids.shape[1], _ptr(ids), _ptr(pos), _ptr(aux), _stream()), "gather_batch_q")
+
+
+def queue_advance(counter):
+    _require_cuda(counter)
+    check(_lib.load().ader_queue_advance(_ptr(counter), _stream()), "queue_advance")
+
+
 # ---- torch.ops registration -------------------------------------------------------------------
 _registered = False
 

@@ -262,6 +262,14 @@ int32_t ader_gather_batch(const int32_t* t_ids, const int32_t* t_lab, const int3
                           const int32_t* e_ids, const int32_t* e_aux, const int32_t* ei, int32_t n_ex,
                           int32_t width, int32_t* ids, int32_t* pos, int32_t* aux, void* stream);
 
+/* the same assembly fed from an epoch-resident index queue: q = the row indices of every step of the epoch back to back
+ * ([n_train train indices | n_ex exemplar indices] per step), q_off[s] = start of step s, *counter = running step.  A captured
+ * step replays without any host-to-device copy; ader_queue_advance (stream-ordered) moves to the next step. */
+int32_t ader_gather_batch_q(const int32_t* t_ids, const int32_t* t_lab, int32_t n_train, const int32_t* e_ids,
+                            const int32_t* e_aux, int32_t n_ex, const int32_t* q, const int64_t* q_off,
+                            const int32_t* counter, int32_t width, int32_t* ids, int32_t* pos, int32_t* aux, void* stream);
+int32_t ader_queue_advance(int32_t* counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,4 +46,5 @@ for mode, name in enumerate(["FWD", "DREP", "DE"]):
         r = lambda s: (t[c, s] - t[c, 1]) / 1e3 if t[c, s] else float("nan")
         f = lambda b: " ".join("%5.1f" % r(b + i) for i in range(7))
         print(" CTA %3d start+%.1fus  setup %.1f  Xissue %.1f  end %.1f / %.1f" % (c, (t[c, 0] - g0) / 1e3, r(2), r(3), r(40), r(41)))
+        print("    tile 2 epilogue: Tfull %.2f  first-ld %.2f  computed %.2f  dsempty %.2f  done %.2f" % (r(26), r(4), r(5), r(6), r(34)))
         print("    Yissue   %s\n    Yfull    %s\n    Sissue   %s\n    Tfull    %s\n    epi_done %s\n    P2issue  %s" % (f(8), f(48), f(16), f(24), f(32), f(56)))

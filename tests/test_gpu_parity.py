@@ -712,6 +712,22 @@ def test_resume_after_a_period_reproduces_the_uninterrupted_run(tmp_path, select
         assert p_full["losses"] == p_cut["losses"]
 
 
+@pytest.mark.parametrize("kw", [dict(selection="random"), dict(selection="random", loss_impl="tc", dropout_rate=0.3),
+                                dict(selection="loss", disable_distillation=True), dict(finetune=True)],
+                         ids=["exact_kd", "tc_dropout_kd", "exact_er", "finetune"])
+def test_epoch_queue_run_equals_step_by_step_run(tmp_path, kw):
+    """the epoch-resident index queue (all row indices of an epoch uploaded once, every step a graph replay
+    that gathers its batch on the device) is the same computation as feeding the indices step by step: same samplers,
+    same RNG consumption, same kernels -- final weights, metrics and exemplar sets are bit-identical."""
+    from ader_b200.main import run
+    a = run(_e2e_args(tmp_path / "q", trace=False, epoch_queue=True, **kw))
+    b = run(_e2e_args(tmp_path / "s", trace=False, epoch_queue=False, **kw))
+    assert torch.equal(a["model"].theta, b["model"].theta)
+    assert torch.equal(a["model"].adam_v, b["model"].adam_v)
+    assert a["per_period"] == b["per_period"]
+    assert [t["train_rows"] for t in a["throughput"]] == [t["train_rows"] for t in b["throughput"]]
+
+
 @pytest.mark.parametrize("mode,shards", [("vanilla", 2), ("kd", 3), ("er", 2)])
 def test_vocab_parallel_shards_match_single_kernel(mode, shards):
     """Vocab-parallel kernels (column offset, per-shard stats, partial d_rep, own-row dE) emulated with
