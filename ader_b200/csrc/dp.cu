@@ -73,15 +73,33 @@ struct DpArgs {
   uint32_t* flags[ADER_DP_MAX_RANKS];
   float *m, *v;
   int* state;
-  long long n_table, table_lo, dense_lo, n_total;     // index space in elements (all even)
-  long long lo2, hi2;                                 // owned slice in float2 units
+  // update index space = two element ranges (item-table rows 1..V, dense parameters), walked in QUADS of four
+  // floats so that peer traffic moves in 16-byte accesses.  A range starts on an even element; when its byte offset is
+  // 8 mod 16 the first quad holds only its upper float2 (ph = 1), and a range may end with a half quad.
+  long long e0[2];            // first element of the range
+  long long n2[2];            // float2 units in the range
+  int ph[2];                  // 1: unit 0 sits in the upper half of quad 0
+  long long q0[2];            // first global quad of the range (q0[0] = 0), q_total = all quads
+  long long q_lo, q_hi;       // quads owned by this rank
   float lr, beta1, beta2, eps, ewc_lambda;
   const float *fisher, *theta_star;
 };
 
-// W = upper bound of the world size (array extents in registers), U = float2 elements per thread and trip: U * W peer
-// loads of 8 bytes are in flight per thread before the first add (NVLink round trips are ~2-3 us: the link only
-// fills with megabytes outstanding).
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ld_cg2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+// W = upper bound of the world size (array extents in registers), U = quads per thread and trip: U * W peer loads of
+// 16 bytes are in flight per thread before the first add (NVLink round trips are ~2-3 us: the link only fills with
+// megabytes outstanding, and only with 16-byte accesses -- 8-byte ones reached ~150 GB/s per direction).
+// Peer lines are never in this SM's L1 at kernel start (L1 is invalidated at launch boundaries) and .cg keeps them out.
 template <int W, int U>
 __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
   __shared__ float s_lr;
@@ -99,40 +117,67 @@ __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
   const float lr_t = s_lr;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool ewc = a.ewc_lambda != 0.f;
-  for (long long base = a.lo2 + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.hi2; base += stride * U) {
-    long long el[U];
-    float2 gr[U][W];
+  for (long long base = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.q_hi; base += stride * U) {
+    long long el[U];           // element of the quad's first float (16-byte aligned), -1: no such quad
+    int msk[U];                // bit 0: lower float2 valid, bit 1: upper float2 valid
+    float4 gr[U][W];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i2 = base + (long long)u * stride;
-      const long long i = i2 * 2;
-      el[u] = (i2 < a.hi2) ? ((i < a.n_table) ? a.table_lo + i : a.dense_lo + (i - a.n_table)) : -1;
+      const long long q = base + (long long)u * stride;
+      el[u] = -1; msk[u] = 0;
+      if (q < a.q_hi) {
+        const int s = q >= a.q0[1] ? 1 : 0;
+        const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];                 // unit of the quad's lower half
+        el[u] = a.e0[s] + 2 * u0;
+        msk[u] = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
+      }
 #pragma unroll
-      for (int r = 0; r < W; ++r)
-        if (r < a.world && el[u] >= 0) gr[u][r] = ld_cv2(a.grad[r] + el[u]);      // all peer loads in flight together
+      for (int r = 0; r < W; ++r) {
+        if (r < a.world && msk[u]) {
+          if (msk[u] == 3) gr[u][r] = ld_cg4(a.grad[r] + el[u]);
+          else {
+            const float2 h = ld_cg2(a.grad[r] + el[u] + (msk[u] == 2 ? 2 : 0));
+            gr[u][r] = (msk[u] == 2) ? make_float4(0.f, 0.f, h.x, h.y) : make_float4(h.x, h.y, 0.f, 0.f);
+          }
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (el[u] < 0) continue;
-      float2 g = make_float2(0.f, 0.f);
+      if (!msk[u]) continue;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int r = 0; r < W; ++r)
-        if (r < a.world) { g.x = __fadd_rn(g.x, gr[u][r].x); g.y = __fadd_rn(g.y, gr[u][r].y); }   // rank order: deterministic
-      float2 th = *reinterpret_cast<const float2*>(a.theta[a.rank] + el[u]);
-      float2 m = *reinterpret_cast<const float2*>(a.m + el[u]);
-      float2 v = *reinterpret_cast<const float2*>(a.v + el[u]);
-      float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
-      if (ewc) {
-        f = *reinterpret_cast<const float2*>(a.fisher + el[u]);
-        ts = *reinterpret_cast<const float2*>(a.theta_star + el[u]);
+        if (r < a.world) {                                                    // rank order: deterministic
+          g[0] = __fadd_rn(g[0], gr[u][r].x); g[1] = __fadd_rn(g[1], gr[u][r].y);
+          g[2] = __fadd_rn(g[2], gr[u][r].z); g[3] = __fadd_rn(g[3], gr[u][r].w);
+        }
+      const int lo = (msk[u] & 1) ? 0 : 2, hi = (msk[u] & 2) ? 4 : 2;
+      float th[4], m[4], v[4];
+#pragma unroll
+      for (int h = 0; h < 4; h += 2) {
+        if (h < lo || h >= hi) continue;
+        const long long x = el[u] + h;
+        const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
+        const float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
+        const float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
+        float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
+        if (ewc) {
+          f = *reinterpret_cast<const float2*>(a.fisher + x);
+          ts = *reinterpret_cast<const float2*>(a.theta_star + x);
+        }
+        th[h] = t2.x; th[h + 1] = t2.y; m[h] = m2.x; m[h + 1] = m2.y; v[h] = v2.x; v[h + 1] = v2.y;
+        adam_update_elem(g[h], th[h], m[h], v[h], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
+        adam_update_elem(g[h + 1], th[h + 1], m[h + 1], v[h + 1], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
+        *reinterpret_cast<float2*>(a.m + x) = make_float2(m[h], m[h + 1]);
+        *reinterpret_cast<float2*>(a.v + x) = make_float2(v[h], v[h + 1]);
       }
-      adam_update_elem(g.x, th.x, m.x, v.x, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
-      adam_update_elem(g.y, th.y, m.y, v.y, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
-      *reinterpret_cast<float2*>(a.m + el[u]) = m;
-      *reinterpret_cast<float2*>(a.v + el[u]) = v;
 #pragma unroll
-      for (int r = 0; r < W; ++r)
-        if (r < a.world) *reinterpret_cast<float2*>(a.theta[r] + el[u]) = th;
+      for (int r = 0; r < W; ++r) {
+        if (r >= a.world) continue;
+        if (msk[u] == 3) *reinterpret_cast<float4*>(a.theta[r] + el[u]) = make_float4(th[0], th[1], th[2], th[3]);
+        else *reinterpret_cast<float2*>(a.theta[r] + el[u] + lo) = make_float2(th[lo], th[lo + 1]);
+      }
     }
   }
   __syncthreads();
@@ -179,9 +224,9 @@ static void dp_preload() {
   static bool done = false;
   if (done) return;
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, k_dp_adam<2, 8>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<4, 4>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<8, 2>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<2, 4>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<4, 2>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<8, 1>);
   cudaFuncGetAttributes(&fa, k_dp_adam<16, 1>);
   cudaFuncGetAttributes(&fa, k_dp_arrive);
   cudaFuncGetAttributes(&fa, k_dp_wait);
@@ -220,24 +265,36 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
     d.flags[r] = r < c->world ? c->flags[r] : nullptr;
   }
   d.m = adam_m; d.v = adam_v; d.state = state;
-  d.n_table = (long long)a->V * m->d; d.table_lo = m->d; d.dense_lo = l.off_pos; d.n_total = d.n_table + l.dense_count();
-  const long long n2 = d.n_total / 2;                 // both ranges are even (d is even)
-  d.lo2 = n2 * c->rank / c->world;
-  d.hi2 = n2 * (c->rank + 1) / c->world;
+  // two element ranges, both starting and ending on even elements (d is even); quads are 16-byte aligned float4s
+  const long long starts[2] = {(long long)m->d, l.off_pos};
+  const long long counts[2] = {(long long)a->V * m->d, l.dense_count()};
+  long long q = 0;
+  for (int s = 0; s < 2; ++s) {
+    d.e0[s] = starts[s]; d.n2[s] = counts[s] / 2;
+    d.ph[s] = (int)((starts[s] / 2) & 1);                    // byte offset 8 mod 16 <=> odd float2 index
+    d.q0[s] = q;
+    q += (d.n2[s] + d.ph[s] + 1) / 2;
+  }
+  const long long q_total = q;
+  d.q_lo = q_total * c->rank / c->world;
+  d.q_hi = q_total * (c->rank + 1) / c->world;
   d.lr = a->lr; d.beta1 = a->beta1; d.beta2 = a->beta2; d.eps = a->eps; d.ewc_lambda = a->ewc_lambda;
   d.fisher = a->fisher; d.theta_star = a->theta_star;
-  const long long mine = d.hi2 - d.lo2;
-  const int U = c->world <= 2 ? 8 : c->world <= 4 ? 4 : c->world <= 8 ? 2 : 1;
+  ADER_CHECK_ARG(((uintptr_t)adam_m % 16) == 0 && ((uintptr_t)adam_v % 16) == 0, "dp_adam_step: optimiser slots must be 16-byte aligned");
+  for (int r = 0; r < c->world; ++r)
+    ADER_CHECK_ARG(((uintptr_t)c->theta[r] % 16) == 0 && ((uintptr_t)c->grad[r] % 16) == 0, "dp_adam_step: theta / grad of rank %d must be 16-byte aligned", r);
+  const long long mine = d.q_hi - d.q_lo;
+  const int U = c->world <= 2 ? 4 : c->world <= 4 ? 2 : 1;
   int grid = cdiv(mine > 0 ? mine : 1, 256 * U);
-  if (grid > 148 * 2) grid = 148 * 2;                 // grid-stride over the owned slice, whole waves of the 148 SMs
+  if (grid > 148 * 2) grid = 148 * 2;                 // grid-stride over the owned quads, whole waves of the 148 SMs
   DpFlags fl;
   fl.rank = c->rank; fl.world = c->world;
   for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
   k_dp_arrive<<<1, 32, 0, (cudaStream_t)stream>>>(fl);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->world <= 2) k_dp_adam<2, 8><<<grid, 256, 0, st>>>(d);
-  else if (c->world <= 4) k_dp_adam<4, 4><<<grid, 256, 0, st>>>(d);
-  else if (c->world <= 8) k_dp_adam<8, 2><<<grid, 256, 0, st>>>(d);
+  if (c->world <= 2) k_dp_adam<2, 4><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 4) k_dp_adam<4, 2><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 8) k_dp_adam<8, 1><<<grid, 256, 0, st>>>(d);
   else k_dp_adam<16, 1><<<grid, 256, 0, st>>>(d);
   ADER_CHECK_LAUNCH("dp_adam_step");
   return 0;

@@ -77,3 +77,55 @@ def test_data_parallel_step_matches_single_gpu(backend):
         # one Adam step moves weights by ~lr; gradients agree to ~1e-6 relative
         assert np.abs(out[r][1] - ref).max() < 3e-5
     assert np.array_equal(out[0][1], out[1][1])          # replicas stay bit-identical
+
+
+def _graph_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from ader_b200.dist import DataParallel, shard_rows
+    from ader_b200.model import Ader
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        args = _args(); args.loss_impl = "tc"
+        res = {}
+        ids, pos, teacher, V = _batch()
+        n_train, n_ex = len(pos), len(ids) - len(pos)
+        (tl, th), (el, eh) = shard_rows(n_train, n_ex, rank, world)
+        rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
+        for mode in ("eager", "graph"):
+            m = Ader(400, args, device=torch.device("cuda", rank), init_seed=0)
+            m.theta.add_(torch.randn(m.theta.shape, generator=torch.Generator().manual_seed(1)).to(m.device) * 0.05)
+            m.update_loss(0.7)
+            DataParallel(m, backend="p2p")
+            assert m.dp.kind == "p2p"
+            m.global_counts = (n_train, n_ex)
+            t_dev = torch.from_numpy(teacher).to(m.device)
+            trows = np.arange(el, eh, dtype=np.int32)
+            gs = m.graph_step(th - tl, eh - el, V, 5e-4, 0.0, teacher=t_dev) if mode == "graph" else None
+            for _ in range(3):
+                if gs is None:
+                    m.train_step(ids[rows], pos[tl:th], V, 5e-4, 0.0, exemplar_logits=t_dev, teacher_rows=trows)
+                else:
+                    gs.run_rows(ids[rows], pos[tl:th], trows)
+            torch.cuda.synchronize()
+            m.dp.check()
+            dist.barrier()
+            res[mode] = m.theta.cpu().numpy()
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_graph_replay_equals_eager_step_across_gpus():
+    """The peer-memory data-parallel step captured as a CUDA graph (what bench.py and the period loop replay) gives the
+    same bits as the eager step, on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_graph_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        assert np.array_equal(out[r]["eager"], out[r]["graph"])
+    assert np.array_equal(out[0]["graph"], out[1]["graph"])

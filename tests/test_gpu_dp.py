@@ -52,15 +52,19 @@ def _warm(m, stream, ids, pos, V, **kw):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("loss_impl", ["exact", "tc"])
-def test_peer_memory_dp_equals_full_batch(world, loss_impl):
+@pytest.mark.parametrize("loss_impl,item_num,V", [("exact", 400, 380), ("tc", 400, 380), ("exact", 399, 379), ("exact", 400, 399)],
+                         ids=["exact", "tc", "exact_even_table_odd_V", "exact_V_is_last_row"])
+def test_peer_memory_dp_equals_full_batch(world, loss_impl, item_num, V):
+    """item_num / V parities move the 16-byte phase of the two update ranges (table rows 1..V start 600 bytes in, the dense
+    parameters start at (item_num + 1) * 600): head / tail half quads and the V = last-row case are all exercised."""
     from ader_b200.dist import local_peer_group, shard_rows
     steps = 3
-    batches, V = _batches(steps)
-    ref = _model(loss_impl)
+    batches, V = _batches(steps, V=V, Vp=min(300, V))
+    _m = lambda li: _model(li, item_num=item_num)
+    ref = _m(loss_impl)
     ref_losses = [float(ref.train_step(ids, pos, V, 5e-4, 0.0, exemplar_logits=t).item()) for ids, pos, t in batches]
 
-    models = [_model(loss_impl) for _ in range(world)]
+    models = [_m(loss_impl) for _ in range(world)]
     comms = local_peer_group(models)
     streams = [torch.cuda.Stream() for _ in range(world)]
     torch.cuda.synchronize()
@@ -101,64 +105,56 @@ def test_peer_memory_dp_equals_full_batch(world, loss_impl):
     assert not np.logical_and(touched[0], touched[1]).any()
 
 
-def test_peer_memory_dp_graph_replay_and_state_restore():
-    """The peer step captured as CUDA graphs (GraphStep) == the eager peer step, and load_state_dict between steps
-    (the period loop restores the best epoch, main.py:283) keeps the replicas identical."""
+def test_peer_memory_dp_state_restore_keeps_replicas_identical():
+    """load_state_dict between steps (the period loop restores the best epoch, main.py:283): peers store into a replica's
+    theta during their update, so the restore waits for every rank's last update first (Ader._dp_quiesce); replicas stay
+    bit-identical before and after, and further steps still agree.  (The CUDA-graph form of the peer step is compared
+    with the eager form across real GPUs in tests/test_gpu_dist.py: two multi-branch graphs of emulated ranks replayed
+    side by side on ONE GPU can be serialised by the hardware queue assignment.)"""
     from ader_b200.dist import local_peer_group, shard_rows
     world, steps = 2, 4
     batches, V = _batches(steps, seed=11)
-    # the single-stream form of the step: two multi-branch graphs replayed side by side on ONE GPU may be serialised by the
-    # hardware queue assignment (a rank's graph behind the other rank's spinning arrive kernel); across real GPUs
-    # (bench.py, tests/test_gpu_dist.py) the fork/join form is what runs
-    eager = [_model("tc", step_impl="serial") for _ in range(world)]
-    local_peer_group(eager)
-    graph = [_model("tc", step_impl="serial") for _ in range(world)]
-    local_peer_group(graph)
+    models = [_model("tc") for _ in range(world)]
+    local_peer_group(models)
     streams = [torch.cuda.Stream() for _ in range(world)]
     n_train, n_ex = 25, 12
     shards = [shard_rows(n_train, n_ex, r, world) for r in range(world)]
-    teach = [torch.zeros((n_ex, 300), device="cuda") for _ in range(world)]      # static teacher storage per replica
-    gsteps = []
-    for r, m in enumerate(graph):
-        (tl, th), (el, eh) = shards[r]
-        m.global_counts = (n_train, n_ex)
-        # GraphStep's constructor runs one eager warm-up step; with emulated ranks built one after the other in one
-        # process that step would wait for a peer that does not exist yet, so it runs without the back end (it only
-        # sizes workspaces and is rolled back); the graphs themselves are captured on first use, with the peer kernels
-        comm, m.dp = m.dp, None
-        gsteps.append(m.graph_step(th - tl, eh - el, V, 5e-4, 0.0, teacher=teach[r]))
-        m.dp = comm
-        gsteps[-1].precapture(indexed=False)       # capture synchronises the device: do it before any rank is replaying
-    torch.cuda.synchronize()
-    sd0 = [m.state_dict() for m in graph]
-    for r in range(world):
-        (tl, th), (el, eh) = shards[r]
+
+    def step(batch):
+        ids, pos, teacher = batch
+        for r, m in enumerate(models):
+            (tl, th), (el, eh) = shards[r]
+            rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
+            m.global_counts = (n_train, n_ex)
+            with torch.cuda.stream(streams[r]):
+                m.train_step(ids[rows], pos[tl:th], V, 5e-4, 0.0, exemplar_logits=teacher[el:eh])
+        torch.cuda.synchronize()
+
+    for r, m in enumerate(models):
         ids, pos, teacher = batches[0]
+        (tl, th), (el, eh) = shards[r]
         rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
-        eager[r].global_counts = (n_train, n_ex)
-        _warm(eager[r], streams[r], ids[rows], pos[tl:th], V, exemplar_logits=teach[r], teacher_rows=np.arange(el, eh, dtype=np.int32))
-    for it, (ids, pos, teacher) in enumerate(batches):
-        for r in range(world):
-            (tl, th), (el, eh) = shards[r]
-            rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
-            eager[r].global_counts = (n_train, n_ex)
-            teach[r].copy_(torch.from_numpy(teacher))
-            torch.cuda.synchronize()
-            with torch.cuda.stream(streams[r]):
-                eager[r].train_step(ids[rows], pos[tl:th], V, 5e-4, 0.0, exemplar_logits=teach[r],
-                                    teacher_rows=np.arange(el, eh, dtype=np.int32))
-        torch.cuda.synchronize()
-        for r in range(world):
-            (tl, th), (el, eh) = shards[r]
-            rows = list(range(tl, th)) + list(range(n_train + el, n_train + eh))
-            with torch.cuda.stream(streams[r]):
-                gsteps[r].run_rows(ids[rows], pos[tl:th], np.arange(el, eh, dtype=np.int32))
-        torch.cuda.synchronize()
-        for r in range(world):
-            assert torch.equal(eager[r].theta, graph[r].theta), (it, r)
-    assert torch.equal(graph[0].theta, graph[1].theta)
-    for r, m in enumerate(graph):                            # restore: replicas equal again, next step still consistent
+        m.global_counts = (n_train, n_ex)
+        _warm(m, streams[r], ids[rows], pos[tl:th], V, exemplar_logits=teacher[el:eh])
+    step(batches[0])
+    sd = [m.state_dict() for m in models]
+    after1 = models[0].theta.clone()
+    step(batches[1]); step(batches[2])
+    assert torch.equal(models[0].theta, models[1].theta) and not torch.equal(models[0].theta, after1)
+    for r, m in enumerate(models):
         with torch.cuda.stream(streams[r]):
-            m.load_state_dict(sd0[r])
+            m.load_state_dict(sd[r])
     torch.cuda.synchronize()
-    assert torch.equal(graph[0].theta, graph[1].theta)
+    assert torch.equal(models[0].theta, after1) and torch.equal(models[1].theta, after1)
+    step(batches[1]); step(batches[2])
+    a = models[0].theta.clone()
+    assert torch.equal(models[0].theta, models[1].theta)
+    for c in (m.dp for m in models):
+        c.check()
+    # same two steps from the same restored state give the same bits again (deterministic reduction order)
+    for r, m in enumerate(models):
+        with torch.cuda.stream(streams[r]):
+            m.load_state_dict(sd[r])
+    torch.cuda.synchronize()
+    step(batches[1]); step(batches[2])
+    assert torch.equal(models[0].theta, a)
