@@ -101,6 +101,85 @@ __device__ __forceinline__ float2 ld_cg2(const float* p) {
 // megabytes outstanding, and only with 16-byte accesses -- 8-byte ones reached ~150 GB/s per direction).
 // Peer lines are never in this SM's L1 at kernel start (L1 is invalidated at launch boundaries) and .cg keeps them out.
 template <int W, int U>
+struct DpTrip {
+  long long el[U];           // element of the quad's first float (16-byte aligned)
+  int msk[U];                // bit 0: lower float2 valid, bit 1: upper float2 valid; 0: no quad
+  float4 gr[U][W];
+};
+
+template <int W, int U>
+__device__ __forceinline__ void dp_load(const DpArgs& a, long long base, long long stride, DpTrip<W, U>& t) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long q = base + (long long)u * stride;
+    t.el[u] = 0; t.msk[u] = 0;
+    if (q < a.q_hi) {
+      const int s = q >= a.q0[1] ? 1 : 0;
+      const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];                 // unit of the quad's lower half
+      t.el[u] = a.e0[s] + 2 * u0;
+      t.msk[u] = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
+    }
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+      if (r < a.world && t.msk[u]) {
+        if (t.msk[u] == 3) t.gr[u][r] = ld_cg4(a.grad[r] + t.el[u]);
+        else {
+          const float2 h = ld_cg2(a.grad[r] + t.el[u] + (t.msk[u] == 2 ? 2 : 0));
+          t.gr[u][r] = (t.msk[u] == 2) ? make_float4(0.f, 0.f, h.x, h.y) : make_float4(h.x, h.y, 0.f, 0.f);
+        }
+      }
+    }
+  }
+}
+
+template <int W, int U>
+__device__ __forceinline__ void dp_apply(const DpArgs& a, const DpTrip<W, U>& t, float lr_t, bool ewc) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!t.msk[u]) continue;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+      if (r < a.world) {                                                    // rank order: deterministic
+        g[0] = __fadd_rn(g[0], t.gr[u][r].x); g[1] = __fadd_rn(g[1], t.gr[u][r].y);
+        g[2] = __fadd_rn(g[2], t.gr[u][r].z); g[3] = __fadd_rn(g[3], t.gr[u][r].w);
+      }
+    const int lo = (t.msk[u] & 1) ? 0 : 2, hi = (t.msk[u] & 2) ? 4 : 2;
+    float th[4], m[4], v[4];
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+      if (h < lo || h >= hi) continue;
+      const long long x = t.el[u] + h;
+      const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
+      const float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
+      const float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
+      float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
+      if (ewc) {
+        f = *reinterpret_cast<const float2*>(a.fisher + x);
+        ts = *reinterpret_cast<const float2*>(a.theta_star + x);
+      }
+      th[h] = t2.x; th[h + 1] = t2.y; m[h] = m2.x; m[h + 1] = m2.y; v[h] = v2.x; v[h + 1] = v2.y;
+      adam_update_elem(g[h], th[h], m[h], v[h], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
+      adam_update_elem(g[h + 1], th[h + 1], m[h + 1], v[h + 1], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
+      *reinterpret_cast<float2*>(a.m + x) = make_float2(m[h], m[h + 1]);
+      *reinterpret_cast<float2*>(a.v + x) = make_float2(v[h], v[h + 1]);
+    }
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+      if (r >= a.world) continue;
+      if (t.msk[u] == 3) *reinterpret_cast<float4*>(a.theta[r] + t.el[u]) = make_float4(th[0], th[1], th[2], th[3]);
+      else *reinterpret_cast<float2*>(a.theta[r] + t.el[u] + lo) = make_float2(th[lo], th[lo + 1]);
+    }
+  }
+}
+
+// W = upper bound of the world size (array extents in registers), U = quads per thread and trip.  Software pipeline over
+// the trips of a thread: the peer LOADS of trip k+1 are issued before trip k is summed, updated and STORED into the
+// peers, so the inbound direction of the link (gradient loads) and the outbound one (theta stores, and the replies to
+// the peers' loads) are busy at the same time; the host sizes the grid for ~4 trips per thread with >= 2.5 MB of peer
+// loads in flight.  Peer accesses are 16 bytes wide.  Peer lines are never in this SM's L1 at kernel start (L1 is
+// invalidated at launch boundaries) and .cg keeps them out.
+template <int W, int U>
 __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
   __shared__ float s_lr;
   __shared__ uint32_t s_epoch;
@@ -116,69 +195,19 @@ __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
 
   const float lr_t = s_lr;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long step = stride * U;
   const bool ewc = a.ewc_lambda != 0.f;
-  for (long long base = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.q_hi; base += stride * U) {
-    long long el[U];           // element of the quad's first float (16-byte aligned), -1: no such quad
-    int msk[U];                // bit 0: lower float2 valid, bit 1: upper float2 valid
-    float4 gr[U][W];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long q = base + (long long)u * stride;
-      el[u] = -1; msk[u] = 0;
-      if (q < a.q_hi) {
-        const int s = q >= a.q0[1] ? 1 : 0;
-        const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];                 // unit of the quad's lower half
-        el[u] = a.e0[s] + 2 * u0;
-        msk[u] = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
-      }
-#pragma unroll
-      for (int r = 0; r < W; ++r) {
-        if (r < a.world && msk[u]) {
-          if (msk[u] == 3) gr[u][r] = ld_cg4(a.grad[r] + el[u]);
-          else {
-            const float2 h = ld_cg2(a.grad[r] + el[u] + (msk[u] == 2 ? 2 : 0));
-            gr[u][r] = (msk[u] == 2) ? make_float4(0.f, 0.f, h.x, h.y) : make_float4(h.x, h.y, 0.f, 0.f);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!msk[u]) continue;
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int r = 0; r < W; ++r)
-        if (r < a.world) {                                                    // rank order: deterministic
-          g[0] = __fadd_rn(g[0], gr[u][r].x); g[1] = __fadd_rn(g[1], gr[u][r].y);
-          g[2] = __fadd_rn(g[2], gr[u][r].z); g[3] = __fadd_rn(g[3], gr[u][r].w);
-        }
-      const int lo = (msk[u] & 1) ? 0 : 2, hi = (msk[u] & 2) ? 4 : 2;
-      float th[4], m[4], v[4];
-#pragma unroll
-      for (int h = 0; h < 4; h += 2) {
-        if (h < lo || h >= hi) continue;
-        const long long x = el[u] + h;
-        const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
-        const float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
-        const float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
-        float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
-        if (ewc) {
-          f = *reinterpret_cast<const float2*>(a.fisher + x);
-          ts = *reinterpret_cast<const float2*>(a.theta_star + x);
-        }
-        th[h] = t2.x; th[h + 1] = t2.y; m[h] = m2.x; m[h + 1] = m2.y; v[h] = v2.x; v[h + 1] = v2.y;
-        adam_update_elem(g[h], th[h], m[h], v[h], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
-        adam_update_elem(g[h + 1], th[h + 1], m[h + 1], v[h + 1], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
-        *reinterpret_cast<float2*>(a.m + x) = make_float2(m[h], m[h + 1]);
-        *reinterpret_cast<float2*>(a.v + x) = make_float2(v[h], v[h + 1]);
-      }
-#pragma unroll
-      for (int r = 0; r < W; ++r) {
-        if (r >= a.world) continue;
-        if (msk[u] == 3) *reinterpret_cast<float4*>(a.theta[r] + el[u]) = make_float4(th[0], th[1], th[2], th[3]);
-        else *reinterpret_cast<float2*>(a.theta[r] + el[u] + lo) = make_float2(th[lo], th[lo + 1]);
-      }
-    }
+  long long base = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  DpTrip<W, U> t0, t1;
+  if (base < a.q_hi) dp_load<W, U>(a, base, stride, t0);
+  while (base < a.q_hi) {
+    if (base + step < a.q_hi) dp_load<W, U>(a, base + step, stride, t1);
+    dp_apply<W, U>(a, t0, lr_t, ewc);
+    base += step;
+    if (base >= a.q_hi) break;
+    if (base + step < a.q_hi) dp_load<W, U>(a, base + step, stride, t0);
+    dp_apply<W, U>(a, t1, lr_t, ewc);
+    base += step;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -224,8 +253,8 @@ static void dp_preload() {
   static bool done = false;
   if (done) return;
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, k_dp_adam<2, 4>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<4, 2>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<2, 2>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<4, 1>);
   cudaFuncGetAttributes(&fa, k_dp_adam<8, 1>);
   cudaFuncGetAttributes(&fa, k_dp_adam<16, 1>);
   cudaFuncGetAttributes(&fa, k_dp_arrive);
@@ -284,16 +313,20 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
   for (int r = 0; r < c->world; ++r)
     ADER_CHECK_ARG(((uintptr_t)c->theta[r] % 16) == 0 && ((uintptr_t)c->grad[r] % 16) == 0, "dp_adam_step: theta / grad of rank %d must be 16-byte aligned", r);
   const long long mine = d.q_hi - d.q_lo;
-  const int U = c->world <= 2 ? 4 : c->world <= 4 ? 2 : 1;
-  int grid = cdiv(mine > 0 ? mine : 1, 256 * U);
-  if (grid > 148 * 2) grid = 148 * 2;                 // grid-stride over the owned quads, whole waves of the 148 SMs
+  const int U = c->world <= 2 ? 2 : 1;
+  int grid = cdiv(mine > 0 ? mine : 1, 256 * U * 4);  // ~4 pipelined trips per thread
+  const long long per_thread = (long long)U * (c->world > 1 ? c->world - 1 : 1) * 16;
+  const int min_grid = cdiv(2500000, 256 * per_thread);     // >= 2.5 MB of peer loads in flight (link bandwidth x latency)
+  if (grid < min_grid) grid = min_grid;
+  if (grid > 148 * 2) grid = 148 * 2;
+  if ((long long)grid * 256 * U > mine && mine > 0) grid = cdiv(mine, 256 * U);
   DpFlags fl;
   fl.rank = c->rank; fl.world = c->world;
   for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
   k_dp_arrive<<<1, 32, 0, (cudaStream_t)stream>>>(fl);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->world <= 2) k_dp_adam<2, 4><<<grid, 256, 0, st>>>(d);
-  else if (c->world <= 4) k_dp_adam<4, 2><<<grid, 256, 0, st>>>(d);
+  if (c->world <= 2) k_dp_adam<2, 2><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 4) k_dp_adam<4, 1><<<grid, 256, 0, st>>>(d);
   else if (c->world <= 8) k_dp_adam<8, 1><<<grid, 256, 0, st>>>(d);
   else k_dp_adam<16, 1><<<grid, 256, 0, st>>>(d);
   ADER_CHECK_LAUNCH("dp_adam_step");

@@ -477,6 +477,7 @@ def run(args) -> dict:
             trace["periods"].append(rec)
         best_epoch = 1
         train_time = 0.0
+        eval_time, eval_rows = 0.0, 0
         for epoch in range(1, args.num_epochs + 1):
             torch.cuda.synchronize()
             t0 = time.time()
@@ -502,7 +503,10 @@ def run(args) -> dict:
                 rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
                 model.compute_fisher(None, rnd, 50, max_item)
             valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None, dp=dp)
+            t0 = time.time()
             info = valid_evaluator.evaluate(epoch)
+            eval_time += time.time() - t0                         # evaluate() ends with the ranks on the host
+            eval_rows += len(valid_evaluator.ranks)
             logs.write(info + "\n")
             performance = valid_evaluator.results()[1]
             rec["valid"].append(valid_evaluator.results())
@@ -517,14 +521,19 @@ def run(args) -> dict:
                 ckpt = {(period, epoch): model.state_dict()}
         model.load_state_dict(ckpt[(period, best_epoch)])      # main.py:283
         test_evaluator = Evaluator(test_sess, False, args.maxlen, args.test_batch, max_item, "test", model, None, dp=dp)
+        t0 = time.time()
         info = test_evaluator.evaluate(best_epoch)
+        eval_time += time.time() - t0
+        eval_rows += len(test_evaluator.ranks)
         logs.write(info + "\n")
         r = test_evaluator.results()
         rec["best_epoch"], rec["test"], rec["test_ranks"] = best_epoch, r, list(test_evaluator.ranks)
         metrics["MRR_20"].append(r[0]); metrics["Recall_20"].append(r[1])
         metrics["MRR_10"].append(r[2]); metrics["Recall_10"].append(r[3])
         sps = trainer.rows_seen / max(train_time, 1e-9)
-        stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps})
+        stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps,
+                      "eval_rows": eval_rows, "eval_s": eval_time, "eval_rows_per_s": eval_rows / max(eval_time, 1e-9),
+                      "epochs": epoch, "max_item": int(max_item), "eager_steps": trainer.n_eager})
         info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by batch geometry / token capacity %s, eager steps %d)" % (
             period, sps, trainer.rows_seen, train_time, trainer.graph_use(), trainer.n_eager)
         print(info)

@@ -171,6 +171,157 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------------
+# the metric as BASELINE.json words it: train sessions/sec PER PERIOD on the shipped split + eval rows/sec
+# --------------------------------------------------------------------------------------------------
+def find_data_root():
+    for root in (os.environ.get("ADER_DATA_ROOT"), os.path.join(ROOT, "data_cache"), os.path.join(ROOT, "data")):
+        if root and os.path.isdir(os.path.join(root, "YOOCHOOSE")):
+            return root
+    return None
+
+
+def real_period_run(n_periods=2, num_epochs=3):
+    """YOOCHOOSE ADER (BASELINE configs[1]: --lambda_=1.0 --batch_size=512 --test_batch=64) through the product driver
+    (ader_b200.main.run: real samplers, epoch-resident index queue, early stopping, evaluation, herding), bounded to the
+    first periods / epochs; returns the driver's own per-period throughput records."""
+    import io, tempfile, contextlib
+    from ader_b200.main import build_parser, run
+    root = find_data_root()
+    if root is None:
+        return {"unavailable": "no YOOCHOOSE period files (ADER_DATA_ROOT / data_cache are not tracked in git)"}
+    a = build_parser().parse_args([])
+    a.dataset, a.data_root, a.lambda_, a.batch_size, a.test_batch = "YOOCHOOSE", root, 1.0, 512, 64
+    a.max_periods, a.num_epochs, a.checkpoint = n_periods, num_epochs, False
+    tmp = tempfile.mkdtemp(prefix="ader_bench_")
+    a.results_root, a.cache_dir = tmp, os.path.join(tmp, "cache")
+    t0 = time.time()
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = run(a)
+    wall = time.time() - t0
+    recs = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in out["throughput"]]
+    return {"dataset": "YOOCHOOSE (shipped split)", "periods": recs, "wall_s": round(wall, 2), "epochs_cap": num_epochs,
+            "note": "train_s = epoch loops only (valid eval excluded), eval_s = validation passes + test pass incl. the rank D2H; "
+                    "dropout 0.3, herding exemplars, adaptive distillation from period 2"}
+
+
+def gpu_components(dev):
+    """Kernel-group throughputs beside the train step (BASELINE.md section 3, C4-C6 counterparts): evaluation ranking at the
+    DIGINETICA period-10 shape, segmented herding, EWC Fisher."""
+    import torch
+    from ader_b200 import ops
+    from ader_b200.model import Ader, Ewc
+    out = {}
+    rng = np.random.RandomState(7)
+    # evaluation: R rows, V = 40 135 (SURVEY A.4 period 10), fused tcgen05 ranking vs the exact fp32 path
+    a = make_args()
+    m = Ader(43136, a, device=dev, init_seed=0)
+    R, V = 16384, 40135
+    ids, lab, lens = synth_rows(rng, R, V)
+    gt = torch.from_numpy(lab).to(dev)
+    ids_d = torch.from_numpy(ids).to(dev)
+    for impl in ("tc", "exact"):
+        m.eval_impl = impl
+        m.rank_topk(ids_d, gt, V, 0, n_tokens=int(lens.sum()))
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(3):
+            m.rank_topk(ids_d, gt, V, 0, n_tokens=int(lens.sum()))
+        torch.cuda.synchronize()
+        out["eval_rows_per_s_" + impl] = R * 3 / (time.time() - t0)
+    out["eval_shape"] = {"rows": R, "max_item": V, "includes": "encoder pass (exact fp32) + ranking"}
+    out["eval_fallbacks"] = m.eval_fallbacks
+    # herding: N candidate rows in segments with the YOOCHOOSE-like size mix (median 3, a few large)
+    sizes = np.minimum(3000, np.maximum(1, (rng.pareto(1.1, 12000) * 2).astype(np.int64) + 1))
+    N = int(sizes.sum())
+    rep = torch.randn(N, 150, device=dev)
+    seg_off = np.zeros(len(sizes) + 1, np.int32); np.cumsum(sizes, out=seg_off[1:])
+    quota = np.minimum(sizes, np.maximum(1, sizes // 2)).astype(np.int32)
+    steps = np.ceil(1.1 * quota).astype(np.int32)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    cand = torch.arange(N, dtype=torch.int32, device=dev)
+    picks = torch.zeros(N, dtype=torch.int32, device=dev); n_p = torch.zeros(len(sizes), dtype=torch.int32, device=dev)
+    ws = torch.empty(ops.herding_ws_bytes(m.ms, N), dtype=torch.uint8, device=dev)
+    args_h = (m.ms, rep, cand, t(seg_off), t(quota), t(steps), ws, picks, n_p)
+    ops.herding_segmented(*args_h); torch.cuda.synchronize()
+    t0 = time.time(); ops.herding_segmented(*args_h); torch.cuda.synchronize()
+    dt = time.time() - t0
+    out["herding"] = {"candidate_rows": N, "segments": int(len(sizes)), "largest": int(sizes.max()), "seconds": dt, "rows_per_s": N / dt,
+                      "gbs_compulsory": N * 150 * 4 / dt / 1e9}
+    # EWC Fisher (EWC.py:126-164): S sessions at batch-1 semantics, V_tab = 43 137
+    e = Ewc(43136, a, device=dev, init_seed=0)
+    S_ = 200
+    sess = [list(rng.randint(1, V + 1, int(n) + 1)) for n in np.minimum(50, rng.geometric(0.22, S_) + 1)]
+    import random
+    random.seed(0)
+    torch.cuda.synchronize(); t0 = time.time()
+    e.compute_fisher(None, sess, 50, V)
+    torch.cuda.synchronize()
+    out["fisher_samples_per_s"] = S_ / (time.time() - t0)
+    del m, e
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_components(budget_s=6.0):
+    """CPU baselines C4-C7 of BASELINE.md section 3 on bounded samples (oracle restatement, all host cores)."""
+    import torch
+    from oracle import protocol as P
+    from oracle import sasrec as S
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
+    out = {"cores": torch.get_num_threads()}
+    rng = np.random.RandomState(11)
+    hp = S.Hyper(43136)
+    params = S.init_params(hp, 0)
+    V = 40135
+    # C4: evaluation at test_batch = 64 with argsort(argsort(-logits)) semantics (ADER.py:99-103, util.py:323-339)
+    ids, lab, _ = synth_rows(rng, 64, V)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        with torch.no_grad():
+            lg = S.logits_of(S.forward_rep(params, torch.tensor(ids).long(), hp), params[0], V)
+            ranks = torch.argsort(torch.argsort(-lg, dim=1), dim=1)          # the reference's double argsort
+            _ = ranks[torch.arange(64), torch.tensor(lab).long() - 1]
+        n += 64
+    out["C4_eval_rows_per_s"] = n / (time.perf_counter() - t0)
+    # C5: herding, the reference's per-item NumPy loop (util.py:419-434)
+    sizes = np.minimum(3000, np.maximum(1, (rng.pareto(1.1, 4000) * 2).astype(np.int64) + 1))
+    reps = [rng.randn(int(k), 150).astype(np.float32) for k in sizes]
+    n, t0 = 0, time.perf_counter()
+    for r in reps:
+        P.herding_picks(r, max(1, len(r) // 2))
+        n += len(r)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    out["C5_herding_rows_per_s"] = n / (time.perf_counter() - t0)
+    # C6: Fisher, one full forward + backward per sample (EWC.py:142-161)
+    ids, lab, _ = synth_rows(rng, 8, V)
+    n, t0 = 0, time.perf_counter()
+    for i in range(8):
+        S.fisher_diag(params, torch.tensor(ids[i:i + 1]).long(), torch.tensor(lab[i:i + 1]), V, hp, 1)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    out["C6_fisher_samples_per_s"] = n / (time.perf_counter() - t0)
+    # C7: logits + CE forward / backward at the synthetic 1 M-item vocabulary, row-chunked (16 GB of logits otherwise)
+    E = torch.randn(1000001, 150) * 0.05
+    rep = torch.randn(64, 150, requires_grad=True)
+    Et = E[1:].clone().requires_grad_(True)
+    pos = torch.randint(0, 1000000, (64,))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        loss = torch.nn.functional.cross_entropy(rep @ Et.t(), pos)
+        loss.backward()
+        rep.grad = None; Et.grad = None
+        n += 64
+    out["C7_synthetic1m_logits_sessions_per_s"] = n / (time.perf_counter() - t0)
+    out["sample"] = "each figure: as many units as fit in ~%.0f s on the host cores (64-row eval batches at V=40135; herding items of the YOOCHOOSE size mix; single-sample Fisher passes at V_tab=43137; 64-row chunks of the 1M-item logits+CE fwd/bwd)" % budget_s
+    return out
+
+
 def workload_config(n):
     return {"workload": WL["name"], "batch_size": WL["B"], "exemplar_rows": WL["M_e"], "max_item": WL["V"],
             "prev_max_item": WL["V_prev"], "table_rows": WL["item_num"] + 1, "lambda": WL["lam"], "maxlen": 50,
@@ -489,6 +640,17 @@ def gpu_arm(args):
         except Exception:
             pass
         cpu_val, cpu_ms, cores, _ = run_cpu(2, 1)
+        period = components = cpu_comp = None
+        if world == 1 and not args.no_period:
+            try:
+                period = real_period_run()
+            except Exception as ex:      # noqa: BLE001
+                period = {"error": repr(ex)}
+            try:
+                components = gpu_components(dev)
+                cpu_comp = cpu_components()
+            except Exception as ex:      # noqa: BLE001
+                components = {"error": repr(ex)}
         line = {"metric": "train sessions/sec", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (logits+CE+KD on tcgen05), f32 elsewhere", "data": "synthetic", "config": workload_config(world),
@@ -506,6 +668,9 @@ def gpu_arm(args):
                 "step_impl": model.step_impl,
                 "dp_backend": dp_kind,
                 "strong_scaling": strong,
+                "period_metric": period,
+                "components": components,
+                "cpu_components": cpu_comp,
                 "roofline": {"kernel": "k_tc_logits<FWD> + <DREP> + <DE> (the three tcgen05 launches of logits+CE+KD fwd+bwd; CUDA-event "
                                        "timed graph replays of exactly these launches; the whole 13-launch group is loss_group_ms)",
                              "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
@@ -533,6 +698,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ader_b200")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="issue the step's launches eagerly")
+    ap.add_argument("--no-period", dest="no_period", action="store_true",
+                    help="skip the real-period run on the shipped split and the component figures (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
