@@ -87,6 +87,8 @@ SIGNATURES = {
     "ader_herding_segmented": (C.c_int32, [_MP, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ader_fisher_accumulate": (C.c_int32, [_MP, _P, _P, C.c_int32, _P]),
     "ader_fisher_finalize": (C.c_int32, [_MP, _P, _P, C.c_int32, C.c_int32, _P]),
+    "ader_fisher_batched_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
+    "ader_fisher_batched": (C.c_int32, [_MP, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "ader_dp_wait": (C.c_int32, [_CP, _P]),
     "ader_dp_adam_step": (C.c_int32, [_MP, _CP, _P, _P, _P, C.POINTER(AderAdamArgs), _P]),
     "ader_dp_status": (C.c_int32, [_CP, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),

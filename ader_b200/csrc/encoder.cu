@@ -1021,13 +1021,269 @@ extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, cons
   return 0;
 }
 
+// ---- batched EWC Fisher diagonal (EWC.py:126-164) ---------------------------------------------------------------------
+// The reference runs one forward + backward PER SAMPLE and squares the dense 26 MB gradient each time.  Here ONE batched
+// exact forward / data-gradient backward serves all S samples, and wherever the ordinary backward would SUM a weight
+// gradient over the tokens of the batch, the hook below sums over the tokens of ONE sample, squares (fp32, np.square on
+// float32) and accumulates over samples in fp64 (F_accum is float64):
+//   linear layers   g_s[i][j] = sum_{t in s} x[t][i] dy[t][j]          (k_fisher_linear, + bias = sum_t dy)
+//   LayerNorm       dbeta_s = sum_t dout[t], dgamma_s = sum_t dout[t] xhat[t]   (k_fisher_ln)
+//   position table  row p receives dx0 of the one token of s at p     (k_fisher_pos)
+//   item table      g_s[v] = dl_s[v] rep_s  (+ sqrt(d) sum of dx0 over the tokens of s with id v):
+//                   sum_s (dl_s[v] rep_s[f])^2 for all v by k_fisher_table over row chunks of dl = softmax - onehot,
+//                   the few (s, v) with an input occurrence corrected by k_fisher_scatter_fix.
+struct FisherHook {
+  double* acc;                 // flat fp64, theta layout
+  const int* tok_row;          // sample of each packed token
+  const float* rep;            // [S, d]
+  const float* lse;            // [S] log-sum-exp of the sample's logits
+  const int* pos;              // [S] labels
+  const float* theta;
+  int S, V;
+};
+
+struct FLMat { const float* X; const float* G; double* accW; double* accb; };
+struct FLArgs { FLMat p[3]; const int* tok_row; const int* dT; int d; };
+constexpr int FL_TT = 32, FL_IB = 8;
+// grid (ceil(d / 8), n_mat), 160 threads: thread j owns entries (i0 .. i0+7, j) of W (in-major [i][j]) -- exclusive, no atomics
+__global__ void __launch_bounds__(160) k_fisher_linear(FLArgs a) {
+  __shared__ float sG[FL_TT][160];
+  __shared__ float sX[FL_TT][FL_IB];
+  __shared__ int sRow[FL_TT];
+  const FLMat P = a.p[blockIdx.y];
+  const int d = a.d, i0 = blockIdx.x * FL_IB, j = threadIdx.x, T = *a.dT;
+  double acc[FL_IB], accb = 0.0;
+  float gs[FL_IB], gb = 0.f;
+#pragma unroll
+  for (int ii = 0; ii < FL_IB; ++ii) { acc[ii] = 0.0; gs[ii] = 0.f; }
+  int cur = -1;
+  for (int t0 = 0; t0 < T; t0 += FL_TT) {
+    const int nt = min(FL_TT, T - t0);
+    for (int e = threadIdx.x; e < nt * d; e += 160) sG[e / d][e % d] = P.G[(long long)t0 * d + e];
+    for (int e = threadIdx.x; e < nt * FL_IB; e += 160) {
+      const int tt = e / FL_IB, ii = e % FL_IB;
+      sX[tt][ii] = (i0 + ii < d) ? P.X[(long long)(t0 + tt) * d + i0 + ii] : 0.f;
+    }
+    if (threadIdx.x < nt) sRow[threadIdx.x] = a.tok_row[t0 + threadIdx.x];
+    __syncthreads();
+    if (j < d) {
+      for (int tt = 0; tt < nt; ++tt) {
+        const int r = sRow[tt];
+        if (r != cur) {
+          if (cur >= 0) {
+#pragma unroll
+            for (int ii = 0; ii < FL_IB; ++ii) { acc[ii] += (double)__fmul_rn(gs[ii], gs[ii]); gs[ii] = 0.f; }
+            accb += (double)__fmul_rn(gb, gb); gb = 0.f;
+          }
+          cur = r;
+        }
+        const float g = sG[tt][j];
+#pragma unroll
+        for (int ii = 0; ii < FL_IB; ++ii) gs[ii] = fmaf(sX[tt][ii], g, gs[ii]);
+        gb += g;
+      }
+    }
+    __syncthreads();
+  }
+  if (j < d && cur >= 0) {
+#pragma unroll
+    for (int ii = 0; ii < FL_IB; ++ii) acc[ii] += (double)__fmul_rn(gs[ii], gs[ii]);
+    accb += (double)__fmul_rn(gb, gb);
+  }
+  if (j < d) {
+#pragma unroll
+    for (int ii = 0; ii < FL_IB; ++ii) if (i0 + ii < d) P.accW[(long long)(i0 + ii) * d + j] += acc[ii];
+    if (blockIdx.x == 0) P.accb[j] += accb;
+  }
+}
+
+// one CTA, 160 threads (feature c): per-sample LayerNorm parameter gradients.  rows == nullptr: token mode (dout, x, mean,
+// rstd per token); else "last token" mode of the final LayerNorm (dout, mean, rstd per row, x at the row's last token).
+__global__ void __launch_bounds__(160) k_fisher_ln(const float* __restrict__ dout, const float* __restrict__ x,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   const int* __restrict__ tok_row, const int* __restrict__ dT, int M,
+                                                   const int* __restrict__ row_len, const int* __restrict__ row_off, int d,
+                                                   double* __restrict__ acc_beta, double* __restrict__ acc_gamma) {
+  const int c = threadIdx.x;
+  if (c >= d) return;
+  double ab = 0.0, ag = 0.0;
+  if (row_off) {
+    for (int r = 0; r < M; ++r) {
+      if (row_len[r] == 0) continue;
+      const float g = dout[(long long)r * d + c];
+      const float xh = (x[(long long)(row_off[r + 1] - 1) * d + c] - mean[r]) * rstd[r];
+      const float gg = g * xh;
+      ab += (double)__fmul_rn(g, g); ag += (double)__fmul_rn(gg, gg);
+    }
+  } else {
+    const int T = *dT;
+    float sb = 0.f, sg = 0.f; int cur = -1;
+    for (int t0 = 0; t0 < T; t0 += 8) {                      // eight tokens' loads in flight, then the ordered accumulation
+      float g8[8], x8[8], mu8[8], rs8[8]; int r8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = min(t0 + k, T - 1);
+        g8[k] = dout[(long long)t * d + c]; x8[k] = x[(long long)t * d + c]; mu8[k] = mean[t]; rs8[k] = rstd[t]; r8[k] = tok_row[t];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (t0 + k >= T) break;
+        if (r8[k] != cur) {
+          if (cur >= 0) { ab += (double)__fmul_rn(sb, sb); ag += (double)__fmul_rn(sg, sg); sb = 0.f; sg = 0.f; }
+          cur = r8[k];
+        }
+        sb += g8[k]; sg += g8[k] * ((x8[k] - mu8[k]) * rs8[k]);
+      }
+    }
+    if (cur >= 0) { ab += (double)__fmul_rn(sb, sb); ag += (double)__fmul_rn(sg, sg); }
+  }
+  acc_beta[c] += ab; acc_gamma[c] += ag;
+}
+
+// grid L (position p), 160 threads: acc_pos[p][c] += sum over samples holding position p of dx0^2
+__global__ void __launch_bounds__(160) k_fisher_pos(const float* __restrict__ gx, const int* __restrict__ row_len,
+                                                    const int* __restrict__ row_off, int M, int L, int d, double* __restrict__ acc_pos) {
+  const int p = blockIdx.x, c = threadIdx.x;
+  if (c >= d) return;
+  double a = 0.0;
+  for (int r0 = 0; r0 < M; r0 += 8) {
+    float v8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = min(r0 + k, M - 1);
+      const int n = row_len[r];
+      v8[k] = (r0 + k < M && n >= L - p) ? gx[(long long)(row_off[r] + p - (L - n)) * d + c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += (double)__fmul_rn(v8[k], v8[k]);
+  }
+  acc_pos[(long long)p * d + c] += a;
+}
+
+// dl = softmax(logits) - onehot in place over a chunk of rows (CTA per row), lse out
+__global__ void __launch_bounds__(256) k_fisher_softmax(float* __restrict__ lg, long long ld, int V, const int* __restrict__ pos,
+                                                        float* __restrict__ lse) {
+  __shared__ float sh[8];
+  float* s = lg + (long long)blockIdx.x * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += 256) mx = fmaxf(mx, s[j]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sh[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < V; j += 256) sum += expf(s[j] - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += sh[w];
+  const float l = mx + logf(tot);
+  const int g = pos[blockIdx.x] - 1;
+  for (int j = threadIdx.x; j < V; j += 256) s[j] = expf(s[j] - l) - (j == g ? 1.f : 0.f);
+  if (threadIdx.x == 0) lse[blockIdx.x] = l;
+}
+
+// acc_tab[v][f] += sum over the chunk's samples of (dl[s][v] * rep[s][f])^2.  CTA = 64 items x all features, 256 threads:
+// thread (v = t / 4, fq = t % 4) owns features fq, fq + 4, ...; samples staged 16 at a time.
+constexpr int FT_V = 64, FT_S = 16, FT_F = 40;
+__global__ void __launch_bounds__(256) k_fisher_table(const float* __restrict__ dl, long long ld, const float* __restrict__ rep,
+                                                      int n_rows, int V, int d, double* __restrict__ acc_tab) {
+  __shared__ float sD[FT_S][FT_V];
+  __shared__ float sR[FT_S][160];
+  const int v0 = blockIdx.x * FT_V, vl = threadIdx.x >> 2, fq = threadIdx.x & 3;
+  double acc[FT_F];
+#pragma unroll
+  for (int k = 0; k < FT_F; ++k) acc[k] = 0.0;
+  for (int s0 = 0; s0 < n_rows; s0 += FT_S) {
+    const int ns = min(FT_S, n_rows - s0);
+    for (int e = threadIdx.x; e < ns * FT_V; e += 256) {
+      const int ss = e / FT_V, vv = e % FT_V;
+      sD[ss][vv] = (v0 + vv < V) ? dl[(long long)(s0 + ss) * ld + v0 + vv] : 0.f;
+    }
+    for (int e = threadIdx.x; e < ns * d; e += 256) sR[e / d][e % d] = rep[(long long)s0 * d + e];
+    __syncthreads();
+    for (int ss = 0; ss < ns; ++ss) {
+      const float x = sD[ss][vl];
+#pragma unroll
+      for (int k = 0; k < FT_F; ++k) {
+        const int f = fq + 4 * k;
+        if (f < d) { const float g = __fmul_rn(x, sR[ss][f]); acc[k] += (double)__fmul_rn(g, g); }
+      }
+    }
+    __syncthreads();
+  }
+  if (v0 + vl < V) {
+#pragma unroll
+    for (int k = 0; k < FT_F; ++k) { const int f = fq + 4 * k; if (f < d) acc_tab[(long long)(v0 + vl) * d + f] += acc[k]; }
+  }
+}
+
+// CTA per sample, 160 threads: rows of the item table that also receive the sample's input-lookup scatter get
+// (dl rep + sc)^2 instead of (dl rep)^2.  Different samples may share an item: fp64 atomics (order changes the sum by ~1e-16).
+__global__ void __launch_bounds__(160) k_fisher_scatter_fix(FisherHook h, const float* __restrict__ gx0, const int* __restrict__ tok_id,
+                                                            const int* __restrict__ row_len, const int* __restrict__ row_off, int d,
+                                                            float sqrt_d, double* __restrict__ acc_tab) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, c = threadIdx.x;
+  const int n = row_len[r], off = row_off[r];
+  if (n == 0) return;
+  const float l = h.lse[r];
+  const int g = h.pos[r];
+  const float rp = c < d ? h.rep[(long long)r * d + c] : 0.f;
+  for (int t = 0; t < n; ++t) {
+    const int id = tok_id[off + t];
+    bool first = true;
+    for (int u = 0; u < t; ++u) if (tok_id[off + u] == id) { first = false; break; }
+    if (!first) continue;                                     // uniform over the CTA
+    float sc = 0.f;
+    for (int u = t; u < n; ++u) if (tok_id[off + u] == id && c < d) sc += gx0[(long long)(off + u) * d + c];
+    sc *= sqrt_d;
+    float part = c < d ? rp * h.theta[(long long)id * d + c] : 0.f;      // logit of item `id` for this sample
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
+    if ((c & 31) == 0) red[c >> 5] = part;
+    __syncthreads();
+    float logit = 0.f;
+    for (int w = 0; w < 5; ++w) logit += red[w];
+    const float dlv = expf(logit - l) - (id == g ? 1.f : 0.f);
+    if (c < d && id <= h.V) {
+      const float a0 = __fmul_rn(dlv, rp);
+      const float a1 = __fadd_rn(a0, sc);
+      atomicAdd(acc_tab + (long long)id * d + c, (double)__fmul_rn(a1, a1) - (double)__fmul_rn(a0, a0));
+    }
+  }
+}
+
+static int fisher_linear(const FisherHook& fh, cudaStream_t st, int n, const float* const* X, const float* const* G,
+                         const long long* offW, const long long* offb, const int* dT, int d) {
+  FLArgs a; a.tok_row = fh.tok_row; a.dT = dT; a.d = d;
+  for (int k = 0; k < n; ++k) a.p[k] = {X[k], G[k], fh.acc + offW[k], fh.acc + offb[k]};
+  k_fisher_linear<<<dim3(cdiv(d, FL_IB), n), 160, 0, st>>>(a);
+  return 0;
+}
+
+static int enc_bwd_exact(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap, const void* ws,
+                         void* bwd_ws, const float* d_rep, float* grad, float dropout_rate, uint64_t seed, cudaStream_t st,
+                         const FisherHook* fh);
+
 extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                     int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
                                     float dropout_rate, uint64_t seed, void* stream) {
   if (int e = check_model(m)) return e;
   ADER_CHECK_ARG(theta && ids && ws && bwd_ws && d_rep && grad, "encoder_bwd: NULL pointer");
   ADER_CHECK_ARG(M > 0 && Tcap > 0, "encoder_bwd: bad M/Tcap");
-  cudaStream_t st = (cudaStream_t)stream;
+  return enc_bwd_exact(m, theta, ids, M, Tcap, ws, bwd_ws, d_rep, grad, dropout_rate, seed, (cudaStream_t)stream, nullptr);
+}
+
+static int enc_bwd_exact(const AderModel* m, const float* theta, const int32_t* ids, int32_t M, int32_t Tcap, const void* ws,
+                         void* bwd_ws, const float* d_rep, float* grad, float dropout_rate, uint64_t seed, cudaStream_t st,
+                         const FisherHook* fh) {
   const Layout l = make_layout(m);
   const int d = m->d, L = m->maxlen;
   const float p = dropout_rate;
@@ -1052,7 +1308,9 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
 
   // final LayerNorm (ADER.py:82): only the last token of each row carries gradient
   k_lnf_bwd<<<ln_grid, 256, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, theta + l.off_lnf + d, w.tok_row, w.row_off, gX, dT, d);
-  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+  if (fh) k_fisher_ln<<<1, 160, 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, w.tok_row, dT, M, w.row_len, w.row_off, d,
+                                         fh->acc + l.off_lnf, fh->acc + l.off_lnf + d);
+  else k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
   ADER_CHECK_LAUNCH("encoder_bwd/final_ln");
 
@@ -1067,37 +1325,99 @@ extern "C" int32_t ader_encoder_bwd(const AderModel* m, const float* theta, cons
       k_apply_drop<<<el_grid, 256, 0, st>>>(gX, gO, dT, d, p, seed, 3u + 3u * b);
       gOut = gO;
     }
-    if (int e = run_wgrad(st, H, gOut, part(bo + l.w2), part(bo + l.b2), PS, Tcap, dT, d)) return e;
+    if (fh) { const float* Xs[1] = {H}; const float* Gs[1] = {gOut}; const long long ow[1] = {bo + l.w2}, ob[1] = {bo + l.b2};
+              fisher_linear(*fh, st, 1, Xs, Gs, ow, ob, dT, d); }
+    else if (int e = run_wgrad(st, H, gOut, part(bo + l.w2), part(bo + l.b2), PS, Tcap, dT, d)) return e;
     // gH = (gOut . W2^T) * [h > 0] * 1/(1-p)   (h is stored post-dropout)
     if (int e = run_dense(st, gOut, P + l.w2, nullptr, gH, Tcap, dT, d, true, 0, nullptr, H, 0,
                           p > 0.f ? 1.f / (1.f - p) : 1.f, 0.f, 0, 0)) return e;
-    if (int e = run_wgrad(st, Z, gH, part(bo + l.w1), part(bo + l.b1), PS, Tcap, dT, d)) return e;
+    if (fh) { const float* Xs[1] = {Z}; const float* Gs[1] = {gH}; const long long ow[1] = {bo + l.w1}, ob[1] = {bo + l.b1};
+              fisher_linear(*fh, st, 1, Xs, Gs, ow, ob, dT, d); }
+    else if (int e = run_wgrad(st, Z, gH, part(bo + l.w1), part(bo + l.b1), PS, Tcap, dT, d)) return e;
     // gZ = gH . W1^T + gX   (residual z -> x_out)
     if (int e = run_dense(st, gH, P + l.w1, nullptr, gZ, Tcap, dT, d, true, 0, gX, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     k_ln_bwd<<<ln_grid, 256, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], P + l.ln2g, gY, dT, d, 0);
-    k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
+    if (fh) k_fisher_ln<<<1, 160, 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], w.tok_row, dT, 0, nullptr, nullptr, d,
+                                           fh->acc + bo + l.ln2b, fh->acc + bo + l.ln2g);
+    else k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gZ, Y, w.mean2[b], w.rstd2[b], dT, 0, nullptr, nullptr, d,
                                                    part(bo + l.ln2b), part(bo + l.ln2g), PS);
     k_attn_bwd<<<M, ATT_THREADS, attn_smem, st>>>(Qp, Kp, Vp, w.probs[b], gY, w.row_len, w.row_off, d, m->num_heads, L, Tcap,
                                           p, seed, 1u + 3u * b, gQ, gK, gV);
     ADER_CHECK_LAUNCH("encoder_bwd/attn");
-    if (int e = run_wgrad(st, Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d)) return e;
-    if (int e = run_wgrad(st, X, gK, part(bo + l.wk), part(bo + l.bk), PS, Tcap, dT, d)) return e;
-    if (int e = run_wgrad(st, X, gV, part(bo + l.wv), part(bo + l.bv), PS, Tcap, dT, d)) return e;
+    if (fh) {
+      const float* Xs[3] = {Q1, X, X}; const float* Gs[3] = {gQ, gK, gV};
+      const long long ow[3] = {bo + l.wq, bo + l.wk, bo + l.wv}, ob[3] = {bo + l.bq, bo + l.bk, bo + l.bv};
+      fisher_linear(*fh, st, 3, Xs, Gs, ow, ob, dT, d);
+    } else {
+      if (int e = run_wgrad(st, Q1, gQ, part(bo + l.wq), part(bo + l.bq), PS, Tcap, dT, d)) return e;
+      if (int e = run_wgrad(st, X, gK, part(bo + l.wk), part(bo + l.bk), PS, Tcap, dT, d)) return e;
+      if (int e = run_wgrad(st, X, gV, part(bo + l.wv), part(bo + l.bv), PS, Tcap, dT, d)) return e;
+    }
     // gQ1 = gQ . Wq^T + gY   (y = attn + q)
     if (int e = run_dense(st, gQ, P + l.wq, nullptr, gQ1, Tcap, dT, d, true, 0, gY, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     if (int e = run_dense(st, gK, P + l.wk, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 0, 1.f, 0.f, 0, 0)) return e;
     if (int e = run_dense(st, gV, P + l.wv, nullptr, gXin, Tcap, dT, d, true, 0, nullptr, nullptr, 1, 1.f, 0.f, 0, 0)) return e;
     k_ln_bwd<<<ln_grid, 256, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], P + l.ln1g, gXin, dT, d, 1);
-    k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], dT, 0, nullptr, nullptr, d,
+    if (fh) k_fisher_ln<<<1, 160, 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], w.tok_row, dT, 0, nullptr, nullptr, d,
+                                           fh->acc + bo + l.ln1b, fh->acc + bo + l.ln1g);
+    else k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, st>>>(gQ1, X, w.mean1[b], w.rstd1[b], dT, 0, nullptr, nullptr, d,
                                                    part(bo + l.ln1b), part(bo + l.ln1g), PS);
     ADER_CHECK_LAUNCH("encoder_bwd/block");
     float* t = gX; gX = gXin; gXin = t;
   }
 
   if (p > 0.f) k_apply_drop<<<el_grid, 256, 0, st>>>(gX, gX, dT, d, p, seed, 0u);   // x0 = drop(emb) (ADER.py:55)
-  if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, grad, st)) return e;
+  if (fh) {
+    k_fisher_pos<<<L, 160, 0, st>>>(gX, w.row_len, w.row_off, M, L, d, fh->acc + l.off_pos);
+    k_fisher_scatter_fix<<<M, 160, 0, st>>>(*fh, gX, w.tok_id, w.row_len, w.row_off, d, sqrtf((float)d), fh->acc + l.off_table);
+  } else if (int e = run_embedding_grads(m, l, w, g, gX, M, Tcap, grad, st)) return e;
   ADER_CHECK_LAUNCH("encoder_bwd/embedding");
   return 0;
+}
+
+// workspace of ader_fisher_batched: rep [S, d], d_rep [S, d], lse [S], a chunk of logits / dl [FISHER_CHUNK, ld(V)]
+constexpr int FISHER_CHUNK = 256;
+static long long fisher_ld(int V) { return ((long long)V + 3) / 4 * 4; }
+extern "C" size_t ader_fisher_batched_ws_bytes(const AderModel* m, int32_t S, int32_t V) {
+  if (check_model(m) || S <= 0 || V <= 0 || m->d > 160) return 0;
+  return 2 * align_up(sizeof(float) * (size_t)S * m->d) + align_up(sizeof(float) * (size_t)S) +
+         align_up(sizeof(float) * (size_t)FISHER_CHUNK * fisher_ld(V));
+}
+
+extern "C" int32_t ader_fisher_batched(const AderModel* m, const float* theta, const int32_t* ids, const int32_t* pos, int32_t S,
+                                       int32_t Tcap, int32_t V, void* enc_ws, void* bwd_ws, void* ws, double* acc, void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && ids && pos && enc_ws && bwd_ws && ws && acc, "fisher_batched: NULL pointer");
+  ADER_CHECK_ARG(S > 0 && Tcap > 0 && V >= 1 && V < m->v_tab, "fisher_batched: bad sizes");
+  ADER_CHECK_ARG(m->d <= 160, "fisher_batched: hidden_units must be <= 160");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = m->d;
+  const Layout l = make_layout(m);
+  char* base = (char*)ws; size_t o = 0;
+  auto take = [&](size_t n) { char* p = base + o; o += align_up(n); return p; };
+  float* rep = (float*)take(sizeof(float) * (size_t)S * d);
+  float* d_rep = (float*)take(sizeof(float) * (size_t)S * d);
+  float* lse = (float*)take(sizeof(float) * (size_t)S);
+  float* lg = (float*)take(sizeof(float) * (size_t)FISHER_CHUNK * fisher_ld(V));
+  const long long ld = fisher_ld(V);
+  if (int e = ader_encoder_fwd(m, theta, ids, S, Tcap, enc_ws, rep, 0.f, 0, stream)) return e;      // eval mode (EWC.py:151-152)
+  for (int r0 = 0; r0 < S; r0 += FISHER_CHUNK) {
+    const int nr = (S - r0 < FISHER_CHUNK) ? S - r0 : FISHER_CHUNK;
+    if (int e = ader_logits(m, theta, rep + (size_t)r0 * d, nr, V, lg, ld, stream)) return e;
+    k_fisher_softmax<<<nr, 256, 0, st>>>(lg, ld, V, pos + r0, lse + r0);
+    GemmArgs g; gemm_defaults(g);                            // d_rep = dl . E[1..V]   (K = V)
+    g.A = lg; g.a_rs = ld; g.a_cs = 1;
+    g.B = theta + d; g.b_rs = d; g.b_cs = 1;
+    g.C = d_rep + (size_t)r0 * d; g.c_rs = d; g.c_cs = 1;
+    g.M = nr; g.N = d; g.K = V;
+    if (int e = launch_gemm(g, st)) return e;
+    k_fisher_table<<<cdiv(V, FT_V), 256, 0, st>>>(lg, ld, rep + (size_t)r0 * d, nr, V, d, acc + l.off_table + d);
+    ADER_CHECK_LAUNCH("fisher_batched/table");
+  }
+  EncWs w = carve_enc(m, S, Tcap, (char*)enc_ws);
+  FisherHook fh;
+  fh.acc = acc; fh.tok_row = w.tok_row; fh.rep = rep; fh.lse = lse; fh.pos = pos; fh.theta = theta; fh.S = S; fh.V = V;
+  return enc_bwd_exact(m, theta, ids, S, Tcap, enc_ws, bwd_ws, d_rep, nullptr, 0.f, 0, st, &fh);
 }
 
 // ------------------------------------------------------------------------------------------

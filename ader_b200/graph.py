@@ -220,6 +220,7 @@ class GraphStep:
                     break
         self.use_count[cap] = self.use_count.get(cap, 0) + 1
         self._graph_for(cap, indexed).replay()
+        self.model._last_enc = (self.M, cap)           # geometry of the pass whose overflow flag token_overflow() reads
         self.model.global_step += 1
         self.model.last_row_loss = self._row_loss[(cap, indexed)]
         return self.model._loss

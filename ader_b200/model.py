@@ -385,6 +385,8 @@ class Ewc(Ader):
         self.ewc_lambda = 0.0
         self._graph_fisher = None
         self._graph_star = None
+        # "batched": ader_fisher_batched (one pass for all samples); "loop": one forward + backward per sample like EWC.py:142-161
+        self.fisher_impl = getattr(args, "fisher_impl", None) or os.environ.get("ADER_B200_FISHER", "batched")
 
     @property
     def variables_prev(self):
@@ -435,12 +437,31 @@ class Ewc(Ader):
             self._fisher_acc = torch.zeros(self.layout.total, dtype=torch.float64, device=self.device)
         acc = self._fisher_acc
         acc.zero_()
+        batched = self.fisher_impl == "batched" and self.hp.hidden_units <= 160
+        rows_ids, rows_pos = [], []
         for _ in range(sampler.batch_num()):
             seq, pos = sampler.sampler_arrays()
-            for i in range(seq.shape[0]):
+            if batched:
+                rows_ids.append(seq); rows_pos.append(pos)
+                continue
+            for i in range(seq.shape[0]):                    # the reference's own shape of work: one pass per sample
                 self.loss_and_grad(seq[i:i + 1], pos[i:i + 1], max_item, mode=self.VANILLA, lambda_=0.0,
                                    n_tokens=int((seq[i] != 0).sum()))
                 ops.fisher_accumulate(self.ms, self.grad, acc, max_item)
+        if batched and rows_ids:
+            ids_all = np.concatenate(rows_ids).astype(np.int32)
+            pos_all = np.concatenate(rows_pos).astype(np.int32)
+            CH = 1024                                        # samples per batched pass (bounds the activation workspaces)
+            for lo in range(0, ids_all.shape[0], CH):
+                ids = _to_ids(ids_all[lo:lo + CH], self.hp.maxlen, self.device)
+                pos_t = _to_i32(pos_all[lo:lo + CH], self.device)
+                S_ = ids.shape[0]
+                tcap = max(int((ids_all[lo:lo + CH] != 0).sum()), 1)
+                ews = self._enc_ws.get(ops.encoder_ws_bytes(self.ms, S_, tcap))
+                bws = self._bwd_ws.get(ops.encoder_bwd_ws_bytes(self.ms, S_, tcap))
+                fws = self._eval_ws.get(ops.fisher_batched_ws_bytes(self.ms, S_, max_item))
+                ops.fisher_batched(self.ms, self.theta, ids, pos_t, tcap, max_item, ews, bws, fws, acc)
+                self._last_enc = (S_, tcap)
         if self.fisher is None:
             self.fisher = torch.empty(self.layout.total, dtype=torch.float32, device=self.device)
         ops.fisher_finalize(self.ms, acc, self.fisher, max_item, len(data))

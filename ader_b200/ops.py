@@ -306,6 +306,20 @@ def fisher_finalize(ms: AderModel, acc, fisher, V: int, n_data: int):
     check(_lib.load().ader_fisher_finalize(C.byref(ms), _ptr(acc), _ptr(fisher), V, n_data, _stream()), "fisher_finalize")
 
 
+def fisher_batched_ws_bytes(ms: AderModel, S: int, V: int) -> int:
+    n = _lib.load().ader_fisher_batched_ws_bytes(C.byref(ms), S, V)
+    if n == 0:
+        raise _lib.AderError("fisher_batched_ws_bytes: bad model / sizes")
+    return n
+
+
+def fisher_batched(ms: AderModel, theta, ids, pos, Tcap: int, V: int, enc_ws, bwd_ws, ws, acc):
+    """acc (fp64, flat) += sum over the rows of `ids` of the squared per-sample gradient (EWC.py:142-161), one batched pass."""
+    _require_cuda(theta, ids, pos, enc_ws, bwd_ws, ws, acc)
+    check(_lib.load().ader_fisher_batched(C.byref(ms), _ptr(theta), _ptr(ids), _ptr(pos), ids.shape[0], Tcap, V, _ptr(enc_ws),
+                                          _ptr(bwd_ws), _ptr(ws), _ptr(acc), _stream()), "fisher_batched")
+
+
 def gather_rows_i32(src, idx, out):
     _require_cuda(src, idx, out)
     check(_lib.load().ader_gather_rows_i32(_ptr(src), _ptr(idx), idx.numel(), src.shape[1], _ptr(out), _stream()),

@@ -250,6 +250,18 @@ int32_t ader_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
 int32_t ader_ipc_open(const void* handle64, void** base_ptr);
 int32_t ader_ipc_close(void* base_ptr);
 
+/* The same statistic for S samples in ONE batched pass (Ewc.compute_fisher's loop over `sess.run(self.gradient)` at batch 1,
+ * EWC.py:142-161): acc (fp64, flat) += sum_s (d CE_s / d theta)^2 over table rows 1..V and all dense parameters, with
+ * per-sample (batch-of-one, eval mode) semantics.  One exact forward + data-gradient backward over all samples; the
+ * per-sample weight gradients are formed where the ordinary backward would sum over the batch (outer products over the
+ * tokens of one sample), squared in fp32 and accumulated in fp64; the item-table part is the product of squares
+ * (softmax - onehot)^2 x rep^2 over row chunks plus an exact correction of the (sample, item) pairs that also receive
+ * the input-lookup scatter.  ids [S, maxlen] left-padded, every row with >= 1 token; pos [S] labels.  enc_ws / bwd_ws
+ * sized for (S, Tcap) by the encoder queries.  Follow with ader_fisher_finalize. */
+size_t  ader_fisher_batched_ws_bytes(const AderModel* m, int32_t S, int32_t V);
+int32_t ader_fisher_batched(const AderModel* m, const float* theta, const int32_t* ids, const int32_t* pos, int32_t S,
+                            int32_t Tcap, int32_t V, void* enc_ws, void* bwd_ws, void* ws, double* acc, void* stream);
+
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* out[i, :] = src[idx[i], :] for int32 rows (batch assembly from the GPU-resident row matrix). */
 int32_t ader_gather_rows_i32(const int32_t* src, const int32_t* idx, int32_t n, int32_t width,
