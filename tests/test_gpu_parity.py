@@ -333,6 +333,58 @@ def test_fisher_and_ewc_step():
         _close(got[i], new[i], 0, 2e-5, "ewc step %s" % name)
 
 
+@pytest.mark.parametrize("heads,blocks", [(1, 2), (2, 1)])
+def test_batched_fisher_matches_per_sample_passes_and_oracle(heads, blocks):
+    """ader_fisher_batched (one batched pass, per-sample squares formed inside the backward) == the reference's own shape of
+    work (one forward + backward per sample, EWC.py:142-161) == the oracle, incl. sessions with a repeated item, items shared
+    by several samples (the item-table cross term) and labels that also occur as inputs."""
+    from ader_b200.model import Ewc
+    import random
+    item_num, V = 950, 900
+    rng = np.random.RandomState(21)
+    data = [rng.randint(1, V + 1, rng.randint(2, 12)).tolist() for _ in range(70)]
+    data[3] = [5, 9, 5, 5, 12]                     # repeated input item
+    data[4] = [9, 5, 77, 5]                        # items shared with sample 3; label 5 is also an input
+    data[5] = [13] + list(range(20, 75))           # longer than maxlen: truncated to the last 50 inputs
+    out = {}
+    for impl in ("loop", "batched"):
+        m = Ewc(item_num, _args(num_heads=heads, num_blocks=blocks, fisher_impl=impl), init_seed=0)
+        hp = S.Hyper(item_num, 150, 50, blocks, heads)
+        params = S.randomize_params(S.init_params(hp, 0), 2, 0.05)
+        m.theta.copy_(torch.cat([p.reshape(-1) for p in params]))
+        assert m.fisher_impl == impl
+        random.seed(4)
+        m.compute_fisher(None, data, 50, V)
+        out[impl] = _views(m, m.fisher)
+    for i, (name, _) in enumerate(S.param_shapes(hp)):
+        _close(out["batched"][i], out["loop"][i], 2e-5, 1e-14, "batched vs per-sample fisher %s" % name)
+    random.seed(4)
+    s_ = P.RefSampler(data, 50, 50, is_subseq=True)
+    rows = []
+    for _ in range(s_.batch_num()):
+        q, p_ = s_.sampler()
+        rows += list(zip(q, p_))
+    ids = torch.tensor(np.array([r[0] for r in rows])).long()
+    pos = torch.tensor([r[1] for r in rows])
+    want = S.fisher_diag(params, ids[:24], pos[:24], V, hp, 24)        # oracle on the first 24 samples of the same order
+    m = Ewc(item_num, _args(num_heads=heads, num_blocks=blocks, fisher_impl="batched"), init_seed=0)
+    m.theta.copy_(torch.cat([p.reshape(-1) for p in params]))
+    acc = torch.zeros(m.layout.total, dtype=torch.float64, device=m.device)
+    from ader_b200 import ops
+    idt = ids[:24].to(torch.int32).to(m.device).contiguous()
+    tcap = int((ids[:24] != 0).sum())
+    ops.fisher_batched(m.ms, m.theta, idt, pos[:24].to(torch.int32).to(m.device), tcap, V,
+                       torch.empty(ops.encoder_ws_bytes(m.ms, 24, tcap), dtype=torch.uint8, device=m.device),
+                       torch.empty(ops.encoder_bwd_ws_bytes(m.ms, 24, tcap), dtype=torch.uint8, device=m.device),
+                       torch.empty(ops.fisher_batched_ws_bytes(m.ms, 24, V), dtype=torch.uint8, device=m.device), acc)
+    got = _views(m, (acc / 24).float())
+    for i, (name, _) in enumerate(S.param_shapes(hp)):
+        g, w = got[i], torch.tensor(want[i])
+        if i == 0:
+            g, w = g[1:V + 1], w[1:V + 1]
+        _close(g, w, 1e-4, 1e-12, "batched fisher vs oracle %s" % name)
+
+
 def test_dropout_masks_are_consistent_fwd_bwd():
     """dropout>0 cannot match TF's stream; check instead that the loss decreases along the
     negative gradient for a FIXED mask (same seed/step), i.e. forward and backward use the same masks."""
