@@ -478,7 +478,9 @@ def run(args) -> dict:
         best_epoch = 1
         train_time = 0.0
         eval_time, eval_rows = 0.0, 0
+        epoch_s, epoch_rows = [], []
         for epoch in range(1, args.num_epochs + 1):
+            rows0 = trainer.rows_seen
             torch.cuda.synchronize()
             t0 = time.time()
             # the host holds millions of small Python objects (session lists): a generation-2 collection in the middle of
@@ -496,6 +498,8 @@ def run(args) -> dict:
                     gc.enable()
             torch.cuda.synchronize()
             train_time += time.time() - t0
+            epoch_s.append(time.time() - t0)
+            epoch_rows.append(trainer.rows_seen - rows0)
             if model.token_overflow():                          # a step was given a token capacity below its real token count
                 raise ops._lib.AderError("period %d epoch %d: encoder token capacity overflow (tokens were dropped)" % (period, epoch))
             if period > 1 and args.ewc:                        # main.py:258-262 (no effect on train_op, S13)
@@ -533,7 +537,10 @@ def run(args) -> dict:
         sps = trainer.rows_seen / max(train_time, 1e-9)
         stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps,
                       "eval_rows": eval_rows, "eval_s": eval_time, "eval_rows_per_s": eval_rows / max(eval_time, 1e-9),
-                      "epochs": epoch, "max_item": int(max_item), "eager_steps": trainer.n_eager})
+                      "epochs": epoch, "max_item": int(max_item), "eager_steps": trainer.n_eager,
+                      "epoch_s": epoch_s, "epoch_rows": epoch_rows,
+                      # epochs after the first: the CUDA graphs of the period's batch geometries exist by then
+                      "steady_sessions_per_s": (sum(epoch_rows[1:]) / max(sum(epoch_s[1:]), 1e-9)) if len(epoch_s) > 1 else None})
         info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by batch geometry / token capacity %s, eager steps %d)" % (
             period, sps, trainer.rows_seen, train_time, trainer.graph_use(), trainer.n_eager)
         print(info)

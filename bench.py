@@ -181,7 +181,7 @@ def find_data_root():
     return None
 
 
-def real_period_run(n_periods=2, num_epochs=3):
+def real_period_run(n_periods=2, num_epochs=4):
     """YOOCHOOSE ADER (BASELINE configs[1]: --lambda_=1.0 --batch_size=512 --test_batch=64) through the product driver
     (ader_b200.main.run: real samplers, epoch-resident index queue, early stopping, evaluation, herding), bounded to the
     first periods / epochs; returns the driver's own per-period throughput records."""
@@ -199,7 +199,8 @@ def real_period_run(n_periods=2, num_epochs=3):
     with contextlib.redirect_stdout(io.StringIO()):
         out = run(a)
     wall = time.time() - t0
-    recs = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in out["throughput"]]
+    recs = [{k: (round(v, 4) if isinstance(v, float) else ([round(x, 4) for x in v] if isinstance(v, list) and v and isinstance(v[0], float) else v))
+             for k, v in r.items()} for r in out["throughput"]]
     return {"dataset": "YOOCHOOSE (shipped split)", "periods": recs, "wall_s": round(wall, 2), "epochs_cap": num_epochs,
             "note": "train_s = epoch loops only (valid eval excluded), eval_s = validation passes + test pass incl. the rank D2H; "
                     "dropout 0.3, herding exemplars, adaptive distillation from period 2"}
