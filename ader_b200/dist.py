@@ -90,12 +90,13 @@ class PeerComm:
 
     kind = "p2p"
 
-    def __init__(self, model, rank: int, world: int, peers, flags: torch.Tensor, opened=()):
+    def __init__(self, model, rank: int, world: int, peers, flags: torch.Tensor, opened=(), separate_arrive: bool = False):
         from . import ops
         self.rank, self.world = rank, world
         self.flags = flags                                   # keep the local flag block alive
         self._opened = list(opened)                          # IPC mappings to close
-        self.comm = ops.dp_comm(rank, world, [p[0] for p in peers], [p[1] for p in peers], [p[2] for p in peers])
+        self.comm = ops.dp_comm(rank, world, [p[0] for p in peers], [p[1] for p in peers], [p[2] for p in peers],
+                                separate_arrive=separate_arrive)
         self._ops = ops
 
     @classmethod
@@ -155,7 +156,7 @@ def local_peer_group(models):
     peers = [(m.theta.data_ptr(), m.grad.data_ptr(), f.data_ptr()) for m, f in zip(models, flags)]
     comms = []
     for r, m in enumerate(models):
-        m.dp = PeerComm(m, r, world, peers, flags[r])
+        m.dp = PeerComm(m, r, world, peers, flags[r], separate_arrive=True)
         m.dp._all_flags = flags
         comms.append(m.dp)
     return comms

@@ -207,9 +207,9 @@ def adam_step(ms: AderModel, theta, m, v, grad, state, V: int, lr: float, ewc_la
 
 
 # ---- data parallel over peer memory (csrc/dp.cu) -------------------------------------------------------
-def dp_comm(rank: int, world: int, theta_ptrs, grad_ptrs, flag_ptrs) -> "_lib.AderDpComm":
+def dp_comm(rank: int, world: int, theta_ptrs, grad_ptrs, flag_ptrs, separate_arrive: bool = False) -> "_lib.AderDpComm":
     c = _lib.AderDpComm()
-    c.rank, c.world = rank, world
+    c.rank, c.world, c.separate_arrive, c.reserved = rank, world, int(separate_arrive), 0
     for r in range(world):
         c.theta[r], c.grad[r], c.flags[r] = int(theta_ptrs[r]), int(grad_ptrs[r]), int(flag_ptrs[r])
     return c

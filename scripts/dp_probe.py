@@ -36,6 +36,31 @@ for _ in range(200):
 e1.record(); torch.cuda.synchronize()
 t_dp = e0.elapsed_time(e1) / 200 * 1e3
 m.dp.check()
+# where the time goes: the same step with the peer pointers replaced by local ones (results are meaningless, timing is not)
+import ctypes as C
+def variant(local_grad, local_theta):
+    c = m.dp.comm
+    th = [c.theta[r] for r in range(world)]; gr = [c.grad[r] for r in range(world)]; fl = [c.flags[r] for r in range(world)]
+    if local_grad: gr = [gr[rank]] * world
+    if local_theta: th = [th[rank]] * world
+    c2 = ops.dp_comm(rank, world, th, gr, fl, separate_arrive=bool(c.separate_arrive))
+    def run2():
+        ops.dp_wait(c2)
+        ops.dp_adam_step(m.ms, c2, m.adam_m, m.adam_v, m.adam_state, V, 5e-4)
+    for _ in range(3): run2()
+    torch.cuda.synchronize(); dist.barrier()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        run2()
+    for _ in range(5): g2.replay()
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    for _ in range(200): g2.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 200 * 1e3
+tv = {k: variant(*k) for k in ((True, False), (False, True), (True, True))}
+if rank == 0:
+    print("variants (us): peer loads only %.1f | peer stores only %.1f | no peer traffic (flags only) %.1f" % (tv[(False, True)], tv[(True, False)], tv[(True, True)]))
 # reference: single-GPU Adam over the same index space
 e0.record()
 for _ in range(200):
