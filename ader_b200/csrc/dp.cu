@@ -20,18 +20,20 @@
 //   flags[src] (src < N): arrival counter written by rank `src` (monotonic epoch numbers),
 //   EPOCH: this rank's epoch (2 per step), DONE: CTA completion counter, ERR: timeout marker.
 // k_dp_arrive (one warp, directly in front of k_dp_adam): publishes "my gradient is complete" (epoch e+1) to every
-// rank and waits until all ranks have published (A).  k_dp_adam works, and the last CTA to finish publishes
-// e+2 = "I have read your gradients and written your theta" (B).  ader_dp_wait (first kernel of the next step) waits
-// for B from every rank before anything overwrites the gradient or reads theta.  Only single-warp kernels ever spin
-// (they leave the SMs to whatever the other ranks still have to run -- also when several emulated ranks share one
-// GPU in the tests); spins time out (~20 s) and mark ERR instead of hanging the GPU.
+// rank and waits until all ranks have published (A); it also prepares the bias-corrected step size.  k_dp_adam works;
+// k_dp_publish (one warp, directly behind it: the kernel boundary orders every peer load / store of the update before
+// it) publishes e+2 = "I have read your gradients and written your theta" (B).  ader_dp_wait (first kernel of the next
+// step) waits for B from every rank before anything overwrites the gradient or reads theta.  Only single-warp kernels
+// ever spin (they leave the SMs to whatever the other ranks still have to run -- also when several emulated ranks share
+// one GPU in the tests); spins time out (~20 s) and mark ERR instead of hanging the GPU.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace ader {
 namespace dp {
 
-constexpr int F_EPOCH = 32, F_DONE = 33, F_ERR = 34;
+constexpr int F_EPOCH = 32, F_DONE = 33, F_ERR = 34, F_LR = 35;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -93,7 +95,6 @@ struct DpArgs {
   long long q_lo, q_hi;       // quads owned by this rank
   float lr, beta1, beta2, eps, ewc_lambda;
   const float *fisher, *theta_star;
-  int fused_arrive;
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) {
@@ -111,139 +112,93 @@ __device__ __forceinline__ float2 ld_cg2(const float* p) {
 // 16 bytes are in flight per thread before the first add (NVLink round trips are ~2-3 us: the link only fills with
 // megabytes outstanding, and only with 16-byte accesses -- 8-byte ones reached ~150 GB/s per direction).
 // Peer lines are never in this SM's L1 at kernel start (L1 is invalidated at launch boundaries) and .cg keeps them out.
-template <int W, int U>
-struct DpTrip {
-  long long el[U];           // element of the quad's first float (16-byte aligned)
-  int msk[U];                // bit 0: lower float2 valid, bit 1: upper float2 valid; 0: no quad
-  float4 gr[U][W];
-};
-
-template <int W, int U>
-__device__ __forceinline__ void dp_load(const DpArgs& a, long long base, long long stride, DpTrip<W, U>& t) {
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const long long q = base + (long long)u * stride;
-    t.el[u] = 0; t.msk[u] = 0;
-    if (q < a.q_hi) {
-      const int s = q >= a.q0[1] ? 1 : 0;
-      const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];                 // unit of the quad's lower half
-      t.el[u] = a.e0[s] + 2 * u0;
-      t.msk[u] = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
-    }
-#pragma unroll
-    for (int r = 0; r < W; ++r) {
-      if (r < a.world && t.msk[u]) {
-        if (t.msk[u] == 3) t.gr[u][r] = ld_cg4(a.grad[r] + t.el[u]);
-        else {
-          const float2 h = ld_cg2(a.grad[r] + t.el[u] + (t.msk[u] == 2 ? 2 : 0));
-          t.gr[u][r] = (t.msk[u] == 2) ? make_float4(0.f, 0.f, h.x, h.y) : make_float4(h.x, h.y, 0.f, 0.f);
-        }
-      }
-    }
-  }
-}
-
-template <int W, int U>
-__device__ __forceinline__ void dp_apply(const DpArgs& a, const DpTrip<W, U>& t, float lr_t, bool ewc) {
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (!t.msk[u]) continue;
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < W; ++r)
-      if (r < a.world) {                                                    // rank order: deterministic
-        g[0] = __fadd_rn(g[0], t.gr[u][r].x); g[1] = __fadd_rn(g[1], t.gr[u][r].y);
-        g[2] = __fadd_rn(g[2], t.gr[u][r].z); g[3] = __fadd_rn(g[3], t.gr[u][r].w);
-      }
-    const int lo = (t.msk[u] & 1) ? 0 : 2, hi = (t.msk[u] & 2) ? 4 : 2;
-    float th[4], m[4], v[4];
-#pragma unroll
-    for (int h = 0; h < 4; h += 2) {
-      if (h < lo || h >= hi) continue;
-      const long long x = t.el[u] + h;
-      const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
-      const float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
-      const float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
-      float2 f = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
-      if (ewc) {
-        f = *reinterpret_cast<const float2*>(a.fisher + x);
-        ts = *reinterpret_cast<const float2*>(a.theta_star + x);
-      }
-      th[h] = t2.x; th[h + 1] = t2.y; m[h] = m2.x; m[h + 1] = m2.y; v[h] = v2.x; v[h + 1] = v2.y;
-      adam_update_elem(g[h], th[h], m[h], v[h], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.x, ts.x);
-      adam_update_elem(g[h + 1], th[h + 1], m[h + 1], v[h + 1], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f.y, ts.y);
-      *reinterpret_cast<float2*>(a.m + x) = make_float2(m[h], m[h + 1]);
-      *reinterpret_cast<float2*>(a.v + x) = make_float2(v[h], v[h + 1]);
-    }
-#pragma unroll
-    for (int r = 0; r < W; ++r) {
-      if (r >= a.world) continue;
-      if (t.msk[u] == 3) *reinterpret_cast<float4*>(a.theta[r] + t.el[u]) = make_float4(th[0], th[1], th[2], th[3]);
-      else *reinterpret_cast<float2*>(a.theta[r] + t.el[u] + lo) = make_float2(th[lo], th[lo + 1]);
-    }
-  }
-}
-
-// W = upper bound of the world size (array extents in registers), U = quads per thread and trip.  Software pipeline over
-// the trips of a thread: the peer LOADS of trip k+1 are issued before trip k is summed, updated and STORED into the
-// peers, so the inbound direction of the link (gradient loads) and the outbound one (theta stores, and the replies to
-// the peers' loads) are busy at the same time; the host sizes the grid for ~4 trips per thread with >= 2.5 MB of peer
-// loads in flight.  Peer accesses are 16 bytes wide.  Peer lines are never in this SM's L1 at kernel start (L1 is
-// invalidated at launch boundaries) and .cg keeps them out.
-template <int W, int U>
+// One quad (four floats, 16-byte peer accesses) per thread, launched like the single-GPU Adam kernel: tens of thousands of
+// resident threads keep megabytes of peer loads in flight (NVLink round trips are 2-3 us), and there is NO in-kernel
+// completion protocol -- a first version closed with a system fence + ticket per CTA and ran 2x slower than plain Adam on
+// purely local data; now the kernel boundary is the fence and k_dp_publish (one warp, stream-ordered behind this kernel)
+// announces "read your gradients, wrote your theta".  W = upper bound of the world size (register array extents).
+template <int W>
 __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
-  __shared__ float s_lr;
-  __shared__ uint32_t s_epoch;
-  uint32_t* myf = a.flags[a.rank];
-  if (threadIdx.x == 0) {
-    s_epoch = ld_acquire_sys(myf + F_EPOCH);
-    const int t = a.state[0] + 1;
-    const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.beta2, (double)t)) / (1.0 - pow((double)a.beta1, (double)t));
-    s_lr = (float)lr_t;
-  }
-  __syncthreads();
-  const uint32_t e = s_epoch;
-  if (a.fused_arrive) {        // barrier A inside this kernel (one launch less on the chain): CTA 0 publishes, every CTA waits
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, e + 1);
-    if ((int)threadIdx.x < a.world) wait_flag(myf + threadIdx.x, e + 1, myf + F_ERR);
-    __syncthreads();
-  }
-
-  const float lr_t = s_lr;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long step = stride * U;
-  const bool ewc = a.ewc_lambda != 0.f;
-  long long base = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  DpTrip<W, U> t0, t1;
-  if (base < a.q_hi) dp_load<W, U>(a, base, stride, t0);
-  while (base < a.q_hi) {
-    if (base + step < a.q_hi) dp_load<W, U>(a, base + step, stride, t1);
-    dp_apply<W, U>(a, t0, lr_t, ewc);
-    base += step;
-    if (base >= a.q_hi) break;
-    if (base + step < a.q_hi) dp_load<W, U>(a, base + step, stride, t0);
-    dp_apply<W, U>(a, t1, lr_t, ewc);
-    base += step;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();                            // this CTA's peer stores are performed before its ticket
-    const uint32_t done = atomicAdd(myf + F_DONE, 1u);
-    if (done == gridDim.x - 1) {                       // last CTA: publish B and advance the local state
-      myf[F_DONE] = 0u;
-      a.state[0] = a.state[0] + 1;
-      a.state[1] = __float_as_int(lr_t);
-      st_release_sys(myf + F_EPOCH, e + 2);
-      __threadfence_system();
-      for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, e + 2);
+  const long long q = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.q_hi) return;
+  const float lr_t = __uint_as_float(ld_relaxed_sys(a.flags[a.rank] + F_LR));       // prepared by k_dp_arrive
+  const int s = q >= a.q0[1] ? 1 : 0;
+  const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];                 // float2 unit of the quad's lower half
+  const long long el = a.e0[s] + 2 * u0;                            // 16-byte aligned element
+  const int msk = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
+  float4 gr[W];
+#pragma unroll
+  for (int r = 0; r < W; ++r) {
+    if (r < a.world) {
+      if (msk == 3) gr[r] = ld_cg4(a.grad[r] + el);
+      else {
+        const float2 h = ld_cg2(a.grad[r] + el + (msk == 2 ? 2 : 0));
+        gr[r] = (msk == 2) ? make_float4(0.f, 0.f, h.x, h.y) : make_float4(h.x, h.y, 0.f, 0.f);
+      }
     }
   }
+  const int lo = (msk & 1) ? 0 : 2, hi = (msk & 2) ? 4 : 2;
+  float th[4], m[4], v[4], f[4] = {0.f, 0.f, 0.f, 0.f}, ts[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool ewc = a.ewc_lambda != 0.f;
+#pragma unroll
+  for (int h = 0; h < 4; h += 2) {
+    if (h < lo || h >= hi) continue;
+    const long long x = el + h;
+    const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
+    const float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
+    const float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
+    th[h] = t2.x; th[h + 1] = t2.y; m[h] = m2.x; m[h + 1] = m2.y; v[h] = v2.x; v[h + 1] = v2.y;
+    if (ewc) {
+      const float2 f2 = *reinterpret_cast<const float2*>(a.fisher + x);
+      const float2 s2 = *reinterpret_cast<const float2*>(a.theta_star + x);
+      f[h] = f2.x; f[h + 1] = f2.y; ts[h] = s2.x; ts[h + 1] = s2.y;
+    }
+  }
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < W; ++r)
+    if (r < a.world) {                                                    // rank order: deterministic
+      g[0] = __fadd_rn(g[0], gr[r].x); g[1] = __fadd_rn(g[1], gr[r].y);
+      g[2] = __fadd_rn(g[2], gr[r].z); g[3] = __fadd_rn(g[3], gr[r].w);
+    }
+#pragma unroll
+  for (int h = 0; h < 4; h += 2) {
+    if (h < lo || h >= hi) continue;
+    const long long x = el + h;
+    adam_update_elem(g[h], th[h], m[h], v[h], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f[h], ts[h]);
+    adam_update_elem(g[h + 1], th[h + 1], m[h + 1], v[h + 1], lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f[h + 1], ts[h + 1]);
+    *reinterpret_cast<float2*>(a.m + x) = make_float2(m[h], m[h + 1]);
+    *reinterpret_cast<float2*>(a.v + x) = make_float2(v[h], v[h + 1]);
+  }
+#pragma unroll
+  for (int r = 0; r < W; ++r) {
+    if (r >= a.world) continue;
+    if (msk == 3) *reinterpret_cast<float4*>(a.theta[r] + el) = make_float4(th[0], th[1], th[2], th[3]);
+    else *reinterpret_cast<float2*>(a.theta[r] + el + lo) = make_float2(th[lo], th[lo + 1]);
+  }
+}
+
+// B: stream order puts every load / store of k_dp_adam before this kernel (the kernel boundary is the system-wide fence)
+__global__ void k_dp_publish(DpFlags a, int* state) {
+  uint32_t* myf = a.flags[a.rank];
+  const uint32_t e = ld_relaxed_sys(myf + F_EPOCH);
+  if (threadIdx.x == 0) {
+    state[0] = state[0] + 1;
+    state[1] = (int)ld_relaxed_sys(myf + F_LR);
+    st_release_sys(myf + F_EPOCH, e + 2);
+  }
+  if ((int)threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, e + 2);
 }
 
 // A: stream order puts every gradient write of this rank before this kernel
-__global__ void k_dp_arrive(DpFlags a) {
+__global__ void k_dp_arrive(DpFlags a, const int* state, float lr, float beta1, float beta2) {
   uint32_t* myf = a.flags[a.rank];
   const uint32_t e = ld_acquire_sys(myf + F_EPOCH);
+  if (threadIdx.x == 31) {                             // bias-corrected step size of this update (TF1 Adam), off the waiting lanes
+    const int t = state[0] + 1;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+    myf[F_LR] = __float_as_uint((float)lr_t);
+  }
   if ((int)threadIdx.x < a.world) {
     st_release_sys(a.flags[threadIdx.x] + a.rank, e + 1);       // kernel boundary: the gradient is already in device memory
     wait_flag(myf + threadIdx.x, e + 1, myf + F_ERR);
@@ -268,10 +223,11 @@ static void dp_preload() {
   static bool done = false;
   if (done) return;
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, k_dp_adam<2, 2>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<4, 1>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<8, 1>);
-  cudaFuncGetAttributes(&fa, k_dp_adam<16, 1>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<2>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<4>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<8>);
+  cudaFuncGetAttributes(&fa, k_dp_adam<16>);
+  cudaFuncGetAttributes(&fa, k_dp_publish);
   cudaFuncGetAttributes(&fa, k_dp_arrive);
   cudaFuncGetAttributes(&fa, k_dp_wait);
   cudaGetLastError();
@@ -328,25 +284,17 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
   for (int r = 0; r < c->world; ++r)
     ADER_CHECK_ARG(((uintptr_t)c->theta[r] % 16) == 0 && ((uintptr_t)c->grad[r] % 16) == 0, "dp_adam_step: theta / grad of rank %d must be 16-byte aligned", r);
   const long long mine = d.q_hi - d.q_lo;
-  const int U = c->world <= 2 ? 2 : 1;
-  int grid = cdiv(mine > 0 ? mine : 1, 256 * U * 4);  // ~4 pipelined trips per thread
-  const long long per_thread = (long long)U * (c->world > 1 ? c->world - 1 : 1) * 16;
-  const int min_grid = cdiv(2500000, 256 * per_thread);     // >= 2.5 MB of peer loads in flight (link bandwidth x latency)
-  if (grid < min_grid) grid = min_grid;
-  if (grid > 148 * 2) grid = 148 * 2;
-  if ((long long)grid * 256 * U > mine && mine > 0) grid = cdiv(mine, 256 * U);
+  const int grid = cdiv(mine > 0 ? mine : 1, 256);
   DpFlags fl;
   fl.rank = c->rank; fl.world = c->world;
   for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
   cudaStream_t st = (cudaStream_t)stream;
-  // separate_arrive != 0: barrier A as its own single-warp kernel, so that no multi-CTA grid ever spins (several emulated
-  // ranks sharing ONE GPU in the tests); real ranks fold it into the update kernel
-  d.fused_arrive = c->separate_arrive ? 0 : 1;
-  if (c->separate_arrive) k_dp_arrive<<<1, 32, 0, st>>>(fl);
-  if (c->world <= 2) k_dp_adam<2, 2><<<grid, 256, 0, st>>>(d);
-  else if (c->world <= 4) k_dp_adam<4, 1><<<grid, 256, 0, st>>>(d);
-  else if (c->world <= 8) k_dp_adam<8, 1><<<grid, 256, 0, st>>>(d);
-  else k_dp_adam<16, 1><<<grid, 256, 0, st>>>(d);
+  k_dp_arrive<<<1, 32, 0, st>>>(fl, state, a->lr, a->beta1, a->beta2);
+  if (c->world <= 2) k_dp_adam<2><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 4) k_dp_adam<4><<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 8) k_dp_adam<8><<<grid, 256, 0, st>>>(d);
+  else k_dp_adam<16><<<grid, 256, 0, st>>>(d);
+  k_dp_publish<<<1, 32, 0, st>>>(fl, state);
   ADER_CHECK_LAUNCH("dp_adam_step");
   return 0;
 }

@@ -119,3 +119,18 @@ def test_live_reference_sampler_and_herding(golden_dir):
         seq = np.zeros((n, 51), np.int64); seq[:, -1] = 1; seq[:, -2] = np.arange(1, n + 1)
         gen.herding(rep, np.zeros((n, 1), np.float32), seq, 0, m)
         assert [e[0][0] - 1 for e in gen.exemplars[0]] == P.herding_picks(rep, m)
+
+
+def test_oracle_herding_matches_reference_on_large_segments(golden_dir):
+    """oracle/protocol.py herding_picks against KATs minted from the reference's own ExemplarGenerator.herding on segments of
+    400 .. 3 100 candidates (tests/golden/make_golden_herding_big.py)."""
+    import sys
+    import numpy as np
+    from oracle import protocol as P
+    sys.path.insert(0, golden_dir)
+    from make_golden_herding_big import make_rep
+    z = np.load(os.path.join(golden_dir, "herding_big.npz"))
+    for c in range(len(z["n"])):
+        rep = make_rep(int(z["seed"][c]), int(z["n"][c]))
+        want = z["picks"][z["pick_off"][c]:z["pick_off"][c + 1]].tolist()
+        assert P.herding_picks(rep, int(z["m"][c])) == want
