@@ -84,6 +84,8 @@ SIGNATURES = {
     "ader_eval_rank_topk": (C.c_int32, [_MP, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "ader_eval_rank_tc_ws_bytes": (C.c_size_t, [_MP, C.c_int32, C.c_int32]),
     "ader_eval_rank_tc": (C.c_int32, [_MP, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "ader_eval_topk_chunks": (C.c_int32, [_MP, C.c_int32, C.c_int32]),
+    "ader_eval_rank_topk_tc": (C.c_int32, [_MP, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ader_herding_ws_bytes": (C.c_size_t, [_MP, C.c_int32]),
     "ader_herding_segmented": (C.c_int32, [_MP, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ader_fisher_accumulate": (C.c_int32, [_MP, _P, _P, C.c_int32, _P]),

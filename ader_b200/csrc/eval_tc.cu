@@ -48,7 +48,13 @@ struct EvalArgs {
   int* cand;                 // [R][cap]
   int cap;
   int* flags;                // [0] candidate overflow, [1] pipeline timeout
+  // top-k (modes MAX / BOTH)
+  float* maxbuf;             // MAX: [n_chunks * 2][R] largest approximate score seen by each (chunk, column half) of a row
+  const float* lo_topk;      // BOTH: [R] columns with S~ >= lo_topk[i] are top-k candidates
+  int* tk_cnt;               // [R]
+  int* tk_cand;              // [R][cap]
 };
+enum { EV_RANK = 0, EV_MAX = 1, EV_BOTH = 2 };
 
 // fp32 rows -> [rows_pad][320] bf16 (hi | lo), optional row norms and their maximum (as int bits of a non-negative float)
 __global__ void __launch_bounds__(256) k_pack_hilo(const float* __restrict__ src, long long ld, int n_rows, int d, int rows_pad,
@@ -93,6 +99,7 @@ __device__ __forceinline__ uint64_t desc_col(uint32_t base, int col, int reg) {
   return make_desc_sw128(base + (col >> 6) * reg + (col & 63) * 2, 16, 1024);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_eval_tc(EvalArgs a, const __grid_constant__ CUtensorMap tm_x,
                                                          const __grid_constant__ CUtensorMap tm_y) {
   extern __shared__ uint8_t smem_raw[];
@@ -174,7 +181,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_eval_tc(EvalArgs a, const __gri
     const int row = q * 32 + lane, gi = x_tile * TM + row;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const bool live = gi < a.R;
-    const float lo = live ? a.lo_thr[gi] : INFINITY, hi = live ? a.hi_thr[gi] : INFINITY;
+    const bool ranking = MODE != EV_MAX;
+    const float lo = (live && ranking) ? a.lo_thr[gi] : INFINITY, hi = (live && ranking) ? a.hi_thr[gi] : INFINITY;
+    const float lo_k = (live && MODE == EV_BOTH) ? a.lo_topk[gi] : INFINITY;
+    float vmax = -INFINITY;
     int above = 0;
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -185,35 +195,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_eval_tc(EvalArgs a, const __gri
       tc_fence_before();
       mbar_arrive(BAR(B_TEMPTY + s));
       const int j0 = (y_lo + it) * TN + half * 32;
-      if (live) {
-        if (j0 + 32 <= a.V) {
-          int unsure = 0;
+      if (!live) continue;
+      const bool whole = j0 + 32 <= a.V;          // else: zero padding rows of the table matrix are not items
+      if (MODE == EV_MAX) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            above += (v > hi) ? 1 : 0;
-            unsure |= (v >= lo && v <= hi) ? (1 << i) : 0;
-          }
-          while (unsure) {                                  // rare: a handful of columns per row in the whole pass
-            const int i = __ffs(unsure) - 1; unsure &= unsure - 1;
-            const int pos = atomicAdd(a.cand_cnt + gi, 1);
-            if (pos < a.cap) a.cand[(long long)gi * a.cap + pos] = j0 + i; else atomicExch(a.flags, 1);
-          }
-        } else {
+        for (int i = 0; i < 32; ++i) if (whole || j0 + i < a.V) vmax = fmaxf(vmax, __uint_as_float(r[i]));
+        continue;
+      }
+      unsigned unsure = 0u, topc = 0u;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (j0 + i >= a.V) continue;                    // zero padding rows of the table matrix are not items
-            const float v = __uint_as_float(r[i]);
-            if (v > hi) ++above;
-            else if (v >= lo) {
-              const int pos = atomicAdd(a.cand_cnt + gi, 1);
-              if (pos < a.cap) a.cand[(long long)gi * a.cap + pos] = j0 + i; else atomicExch(a.flags, 1);
-            }
-          }
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float v = __uint_as_float(r[i]);
+        const bool ok = whole || j0 + i < a.V;
+        above += (ok && v > hi) ? 1 : 0;
+        unsure |= (ok && v >= lo && v <= hi) ? (1u << i) : 0u;
+        if (MODE == EV_BOTH) topc |= (ok && v >= lo_k) ? (1u << i) : 0u;
+      }
+      while (unsure) {                            // rare: a handful of columns per row in the whole pass
+        const int i = __ffs(unsure) - 1; unsure &= unsure - 1;
+        const int pos = atomicAdd(a.cand_cnt + gi, 1);
+        if (pos < a.cap) a.cand[(long long)gi * a.cap + pos] = j0 + i; else atomicExch(a.flags, 1);
+      }
+      while (topc) {
+        const int i = __ffs(topc) - 1; topc &= topc - 1;
+        const int pos = atomicAdd(a.tk_cnt + gi, 1);
+        if (pos < a.cap) a.tk_cand[(long long)gi * a.cap + pos] = j0 + i; else atomicExch(a.flags, 1);
       }
     }
-    if (live && above) atomicAdd(a.above + gi, above);
+    if (live && MODE == EV_MAX) a.maxbuf[(long long)(chunk * 2 + half) * a.R + gi] = vmax;
+    if (live && ranking && above) atomicAdd(a.above + gi, above);
   }
   __syncthreads();
   if (warp == 1) {
@@ -246,9 +256,81 @@ __global__ void __launch_bounds__(256) k_refine(const float* __restrict__ table1
   if (lane == 0) rank[i] = above[i] + c;
 }
 
+// tau = the k-th largest of a row's local maxima (each belongs to a different item, so at least k items score >= tau - eps);
+// every top-k item then has an approximate score >= tau - 2 eps.  Warp per row.
+__global__ void __launch_bounds__(256) k_topk_threshold(const float* __restrict__ maxbuf, int n_slots, int R, int k,
+                                                        const float* __restrict__ rnorm, const int* __restrict__ max_norm,
+                                                        float* __restrict__ lo_topk) {
+  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= R) return;
+  float v[8];                                     // n_slots <= 256
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const int sidx = lane + 32 * q; v[q] = sidx < n_slots ? maxbuf[(long long)sidx * R + i] : -INFINITY; }
+  float kth = -INFINITY;
+  for (int round = 0; round < k; ++round) {       // k rounds of "remove the current maximum"
+    float best = -INFINITY; int bq = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (v[q] > best) { best = v[q]; bq = q; }
+    float wb = best;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wb = fmaxf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+    const unsigned who = __ballot_sync(0xffffffffu, best == wb && bq >= 0);
+    if (who && lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (q == bq) v[q] = -INFINITY;
+    }
+    kth = wb;
+  }
+  if (lane == 0) lo_topk[i] = kth - 2.f * C_ERR * rnorm[i] * __int_as_float(*max_norm);
+}
+
+// exact re-score of the top-k candidates of a row and selection of the k best (score descending, ties -> lower index):
+// warp per row, up to 8 candidates per lane (cap = 256)
+__global__ void __launch_bounds__(256) k_topk_refine(const float* __restrict__ table1, const float* __restrict__ rep, int R, int d,
+                                                     const int* __restrict__ tk_cnt, const int* __restrict__ tk_cand, int cap, int k,
+                                                     int* __restrict__ topk_item, float* __restrict__ topk_score) {
+  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= R) return;
+  const int n = min(tk_cnt[i], cap);
+  const float* a = rep + (long long)i * d;
+  float sc[8]; int id[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int t = lane + 32 * q;
+    sc[q] = -INFINITY; id[q] = 0x7fffffff;
+    if (t < n) {
+      const int j = tk_cand[(long long)i * cap + t];
+      const float* b = table1 + (long long)j * d;
+      float acc = 0.f;
+      for (int c = 0; c < d; ++c) acc = fmaf(a[c], b[c], acc);
+      sc[q] = acc; id[q] = j;
+    }
+  }
+  for (int round = 0; round < k; ++round) {
+    float bs = -INFINITY; int bi = 0x7fffffff, bq = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (id[q] != 0x7fffffff && (sc[q] > bs || (sc[q] == bs && id[q] < bi))) { bs = sc[q]; bi = id[q]; bq = q; }
+    float ws = bs; int wi = bi;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ws, o); const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (os > ws || (os == ws && oi < wi)) { ws = os; wi = oi; }
+    }
+    if (bq >= 0 && bi == wi) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (q == bq) id[q] = 0x7fffffff;
+    }
+    if (lane == 0) {
+      const bool ok = wi != 0x7fffffff;
+      topk_item[(long long)i * k + round] = ok ? wi + 1 : 0;
+      topk_score[(long long)i * k + round] = ok ? ws : -INFINITY;
+    }
+  }
+}
+
 static int eval_chunks(int n_mtiles, int n_vtiles) {
   int best = 1; double best_eff = 0.0;
-  const int cmax = n_vtiles / 8 > 1 ? (n_vtiles / 8 < 148 ? n_vtiles / 8 : 148) : 1;      // >= 8 streamed tiles per CTA
+  const int cmax = n_vtiles / 8 > 1 ? (n_vtiles / 8 < 128 ? n_vtiles / 8 : 128) : 1;      // >= 8 streamed tiles per CTA, <= 256 top-k slots per row
   for (int c = 1; c <= cmax; ++c) {
     const long long ctas = (long long)n_mtiles * c;
     const long long waves = (ctas + 147) / 148;
@@ -261,7 +343,8 @@ static int eval_chunks(int n_mtiles, int n_vtiles) {
 struct EvalWs {
   __nv_bfloat16 *x16, *y16;
   float *rnorm, *sg, *lo, *hi;
-  int *max_norm, *above, *cand_cnt, *cand, *flags;
+  int *max_norm, *above, *cand_cnt, *cand, *flags, *tk_cnt, *tk_cand;
+  float *lo_topk, *maxbuf;
   size_t bytes;
 };
 static EvalWs carve(int R, int V, int cap, char* base) {
@@ -278,6 +361,10 @@ static EvalWs carve(int R, int V, int cap, char* base) {
   w.max_norm = (int*)take(sizeof(int) * (8 + 2 * (size_t)R));
   w.flags = w.max_norm + 4; w.above = w.max_norm + 8; w.cand_cnt = w.above + R;
   w.cand = (int*)take(sizeof(int) * (size_t)R * cap);
+  w.tk_cnt = (int*)take(sizeof(int) * (size_t)R);
+  w.tk_cand = (int*)take(sizeof(int) * (size_t)R * cap);
+  w.lo_topk = (float*)take(sizeof(float) * (size_t)R);
+  w.maxbuf = (float*)take(sizeof(float) * (size_t)R * 2 * 128);
   w.bytes = o;
   return w;
 }
@@ -293,18 +380,19 @@ extern "C" size_t ader_eval_rank_tc_ws_bytes(const AderModel* m, int32_t R, int3
   return carve(R, V, ADER_EVAL_CAND_CAP, nullptr).bytes;
 }
 
-extern "C" int32_t ader_eval_rank_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
-                                     int32_t V, void* ws, int32_t* rank, int32_t* overflow, void* stream) {
-  if (int e = check_model(m)) return e;
-  ADER_CHECK_ARG(theta && rep && gt && ws && rank && overflow, "eval_rank_tc: NULL pointer");
-  ADER_CHECK_ARG(R > 0 && V >= 1 && V < m->v_tab, "eval_rank_tc: bad sizes");
-  ADER_CHECK_ARG(m->d <= HALF, "eval_rank_tc: hidden_units must be <= %d", HALF);
-  cudaStream_t st = (cudaStream_t)stream;
+static int eval_tc_run(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int R, int V, int k, void* ws,
+                       int32_t* rank, int32_t* topk_item, float* topk_score, int32_t* overflow, cudaStream_t st) {
   const int d = m->d, cap = ADER_EVAL_CAND_CAP;
   EvalWs w = carve(R, V, cap, (char*)ws);
   const int nm = cdiv(R, TM), nv = cdiv(V, TN), nc = eval_chunks(nm, nv);
+  ADER_CHECK_ARG(k == 0 || (2 * nc >= k && 2 * nc <= 256), "eval_rank_tc: top-%d needs %d..128 vocabulary chunks per row tile (have %d): use ader_eval_rank_topk", k, (k + 1) / 2, nc);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EVAL); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(k_eval_tc<EV_RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EVAL);
+    cudaFuncSetAttribute(k_eval_tc<EV_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EVAL);
+    cudaFuncSetAttribute(k_eval_tc<EV_BOTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EVAL);
+    attr = true;
+  }
   CUtensorMap tx, ty;
   if (int e = make_map2d(&tx, w.x16, D2, (uint64_t)nm * TM, D2 * 2, TM)) return e;
   if (int e = make_map2d(&ty, w.y16, D2, (uint64_t)nv * TN, D2 * 2, TN)) return e;
@@ -316,9 +404,42 @@ extern "C" int32_t ader_eval_rank_tc(const AderModel* m, const float* theta, con
   EvalArgs a;
   a.R = R; a.V = V; a.n_mtiles = nm; a.n_vtiles = nv; a.n_chunks = nc;
   a.lo_thr = w.lo; a.hi_thr = w.hi; a.above = w.above; a.cand_cnt = w.cand_cnt; a.cand = w.cand; a.cap = cap; a.flags = w.flags;
-  k_eval_tc<<<nm * nc, NTHREADS, SMEM_EVAL, st>>>(a, tx, ty);
+  a.maxbuf = w.maxbuf; a.lo_topk = w.lo_topk; a.tk_cnt = w.tk_cnt; a.tk_cand = w.tk_cand;
+  if (k > 0) {
+    cudaMemsetAsync(w.tk_cnt, 0, sizeof(int) * (size_t)R, st);
+    k_eval_tc<EV_MAX><<<nm * nc, NTHREADS, SMEM_EVAL, st>>>(a, tx, ty);
+    k_topk_threshold<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(w.maxbuf, 2 * nc, R, k, w.rnorm, w.max_norm, w.lo_topk);
+    k_eval_tc<EV_BOTH><<<nm * nc, NTHREADS, SMEM_EVAL, st>>>(a, tx, ty);
+    k_topk_refine<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(table1, rep, R, d, w.tk_cnt, w.tk_cand, cap, k, topk_item, topk_score);
+  } else {
+    k_eval_tc<EV_RANK><<<nm * nc, NTHREADS, SMEM_EVAL, st>>>(a, tx, ty);
+  }
   k_refine<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(table1, rep, gt, R, d, w.sg, w.above, w.cand_cnt, w.cand, cap, rank);
   cudaMemcpyAsync(overflow, w.flags, sizeof(int), cudaMemcpyDeviceToDevice, st);
   ADER_CHECK_LAUNCH("eval_rank_tc");
   return 0;
+}
+
+extern "C" int32_t ader_eval_rank_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
+                                     int32_t V, void* ws, int32_t* rank, int32_t* overflow, void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && rep && gt && ws && rank && overflow, "eval_rank_tc: NULL pointer");
+  ADER_CHECK_ARG(R > 0 && V >= 1 && V < m->v_tab, "eval_rank_tc: bad sizes");
+  ADER_CHECK_ARG(m->d <= HALF, "eval_rank_tc: hidden_units must be <= %d", HALF);
+  return eval_tc_run(m, theta, rep, gt, R, V, 0, ws, rank, nullptr, nullptr, overflow, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ader_eval_topk_chunks(const AderModel* m, int32_t R, int32_t V) {
+  if (check_model(m) || R <= 0 || V <= 0) return 0;
+  return eval_chunks(cdiv(R, TM), cdiv(V, TN));
+}
+
+extern "C" int32_t ader_eval_rank_topk_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
+                                          int32_t V, int32_t k, void* ws, int32_t* rank, int32_t* topk_item, float* topk_score,
+                                          int32_t* overflow, void* stream) {
+  if (int e = check_model(m)) return e;
+  ADER_CHECK_ARG(theta && rep && gt && ws && rank && overflow && topk_item && topk_score, "eval_rank_topk_tc: NULL pointer");
+  ADER_CHECK_ARG(R > 0 && V >= 1 && V < m->v_tab && k >= 1 && k <= 32, "eval_rank_topk_tc: bad sizes");
+  ADER_CHECK_ARG(m->d <= HALF, "eval_rank_topk_tc: hidden_units must be <= %d", HALF);
+  return eval_tc_run(m, theta, rep, gt, R, V, k, ws, rank, topk_item, topk_score, overflow, (cudaStream_t)stream);
 }

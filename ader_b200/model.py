@@ -311,15 +311,21 @@ class Ader:
         self._check_overflow()
         M = ids.shape[0]
         rank = torch.empty(M, dtype=torch.int32, device=self.device)
-        if k <= 0 and self.eval_impl == "tc" and self.hp.hidden_units <= 160:
-            # metrics only need rank(gt): tcgen05 scores + exact refinement of the columns inside the certainty band
-            # (ader_eval_rank_tc: identical ranks, the [M, V] scores are never written)
+        if self.eval_impl == "tc" and self.hp.hidden_units <= 160 and (k <= 0 or 2 * ops.eval_topk_chunks(self.ms, M, max_item) >= k):
+            # tcgen05 scores + exact refinement of the columns inside the certainty bands (ader_eval_rank_tc /
+            # ader_eval_rank_topk_tc: identical ranks and top-k lists, the [M, V] scores are never written)
             ws = self._eval_ws.get(ops.eval_rank_tc_ws_bytes(self.ms, M, max_item))
             over = torch.zeros(1, dtype=torch.int32, device=self.device)
-            ops.eval_rank_tc(self.ms, self.theta, rep, gt_t, max_item, ws, rank, over)
+            if k <= 0:
+                ops.eval_rank_tc(self.ms, self.theta, rep, gt_t, max_item, ws, rank, over)
+                items = torch.empty((M, 1), dtype=torch.int32, device=self.device)
+                scores = items.float()
+            else:
+                items = torch.empty((M, k), dtype=torch.int32, device=self.device)
+                scores = torch.empty((M, k), dtype=torch.float32, device=self.device)
+                ops.eval_rank_topk_tc(self.ms, self.theta, rep, gt_t, max_item, k, ws, rank, items, scores, over)
             if int(over.item()) == 0:
-                empty = torch.empty((M, 1), dtype=torch.int32, device=self.device)
-                return rank, empty, empty.float()
+                return rank, items, scores
             self.eval_fallbacks += 1          # a band held more than ADER_EVAL_CAND_CAP columns: exact path for this batch
         ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
         items = torch.empty((M, max(k, 1)), dtype=torch.int32, device=self.device)

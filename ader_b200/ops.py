@@ -282,6 +282,17 @@ def eval_rank_tc(ms: AderModel, theta, rep, gt, V: int, ws, rank, overflow):
                                         _ptr(overflow), _stream()), "eval_rank_tc")
 
 
+def eval_topk_chunks(ms: AderModel, R: int, V: int) -> int:
+    return int(_lib.load().ader_eval_topk_chunks(C.byref(ms), R, V))
+
+
+def eval_rank_topk_tc(ms: AderModel, theta, rep, gt, V: int, k: int, ws, rank, topk_item, topk_score, overflow):
+    """Fused tensor-core ranking + exact top-k (see include/ader_b200.h); needs 2 * eval_topk_chunks(R, V) >= k."""
+    _require_cuda(theta, rep, gt, ws, rank, topk_item, topk_score, overflow)
+    check(_lib.load().ader_eval_rank_topk_tc(C.byref(ms), _ptr(theta), _ptr(rep), _ptr(gt), rep.shape[0], V, k, _ptr(ws), _ptr(rank),
+                                             _ptr(topk_item), _ptr(topk_score), _ptr(overflow), _stream()), "eval_rank_topk_tc")
+
+
 def herding_ws_bytes(ms: AderModel, N: int) -> int:
     n = _lib.load().ader_herding_ws_bytes(C.byref(ms), N)
     if n == 0:

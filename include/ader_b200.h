@@ -201,6 +201,16 @@ int32_t ader_eval_rank_topk(const AderModel* m, const float* theta, const float*
 size_t  ader_eval_rank_tc_ws_bytes(const AderModel* m, int32_t R, int32_t V);
 int32_t ader_eval_rank_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
                           int32_t V, void* ws, int32_t* rank, int32_t* overflow, void* stream);
+/* ... plus the top-k items of every row (ids 1-based, best first, ties -> lower id; exact fp32 scores), identical to
+ * ader_eval_rank_topk: a first tensor-core pass keeps the largest approximate score of every (vocabulary chunk, column
+ * half) of a row -- each belongs to a different item, so the k-th largest of them, minus 2 eps, bounds the approximate
+ * score of every top-k item from below; a second pass collects the columns above that bound (and does the rank counting
+ * of ader_eval_rank_tc), and the candidates are re-scored exactly and sorted.  Needs 2 * ader_eval_topk_chunks(R, V) >= k
+ * (enough distinct local maxima; small vocabularies use ader_eval_rank_topk).  Same workspace query, same overflow flag. */
+int32_t ader_eval_topk_chunks(const AderModel* m, int32_t R, int32_t V);
+int32_t ader_eval_rank_topk_tc(const AderModel* m, const float* theta, const float* rep, const int32_t* gt, int32_t R,
+                               int32_t V, int32_t k, void* ws, int32_t* rank, int32_t* topk_item, float* topk_score,
+                               int32_t* overflow, void* stream);
 
 /* ---- exemplar selection: util.py:401-461 (subsystem 4) ---------------------------------- */
 /* Segmented herding.  rep [N,d]; segment s owns candidate rows cand[seg_off[s] .. seg_off[s+1])

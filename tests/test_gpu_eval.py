@@ -119,3 +119,45 @@ def test_evaluator_metrics_unchanged_by_the_fused_path():
         ev.evaluate(1)
         out[impl] = (list(ev.ranks), ev.results())
     assert out["exact"][0] == out["tc"][0] and out["exact"][1] == out["tc"][1]
+
+
+@pytest.mark.parametrize("R,V,item_num", [(300, 40135, 43136), (1500, 18661, 25958)])
+def test_fused_topk_equals_exact_topk(R, V, item_num):
+    """Top-20 lists (ids and exact fp32 scores) of the two-pass tensor-core path == the exact path, tie order included."""
+    m, hp, params = _model(item_num)
+    rng = np.random.RandomState(8)
+    tab = m.layout.views(m.theta)[0]
+    ids = _ids(rng, R, 50, V)
+    gt = rng.randint(1, V + 1, R).astype(np.int32)
+    m.eval_impl = "exact"
+    r0, it0, sc0 = m.rank_topk(ids, gt, V, 20)
+    # plant ties INSIDE the top lists: the best item of row 0 gets two bit-equal twins, the 20th of row 1 one twin
+    b0, b1 = int(it0[0, 0]), int(it0[1, 19])
+    for twin, src in ((V - 5, b0), (7, b0), (V - 9, b1)):
+        tab[twin].copy_(tab[src])
+    r0, it0, sc0 = m.rank_topk(ids, gt, V, 20)
+    m.eval_impl = "tc"
+    from ader_b200 import ops
+    assert 2 * ops.eval_topk_chunks(m.ms, R, V) >= 20
+    r1, it1, sc1 = m.rank_topk(ids, gt, V, 20)
+    assert m.eval_fallbacks == 0
+    assert torch.equal(r0, r1)
+    assert torch.equal(it0, it1)
+    assert torch.equal(sc0, sc1)
+    assert bool((sc1[:, :-1] >= sc1[:, 1:]).all())
+    row0 = it1[0].cpu().tolist()
+    assert sorted(row0[:3]) == sorted([b0, 7, V - 5]) and row0[:3] == sorted(row0[:3])     # three-way tie: ascending ids
+
+
+def test_small_vocabulary_topk_uses_the_exact_path():
+    m, hp, _ = _model(500)
+    rng = np.random.RandomState(9)
+    ids = _ids(rng, 40, 50, 450)
+    gt = rng.randint(1, 451, 40).astype(np.int32)
+    from ader_b200 import ops
+    assert 2 * ops.eval_topk_chunks(m.ms, 40, 450) < 20
+    m.eval_impl = "tc"
+    r1, it1, sc1 = m.rank_topk(ids, gt, 450, 20)
+    m.eval_impl = "exact"
+    r0, it0, sc0 = m.rank_topk(ids, gt, 450, 20)
+    assert torch.equal(r0, r1) and torch.equal(it0, it1) and torch.equal(sc0, sc1)
