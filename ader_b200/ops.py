@@ -359,41 +359,102 @@ def queue_advance(counter):
 
 
 # ---- torch.ops registration -------------------------------------------------------------------
+# Every compute entry point of include/ader_b200.h is also reachable through the dispatcher as torch.ops.ader_b200.<name>
+# (CUDA key only: there is no CPU implementation to fall back to).  The POD structs of the C ABI are flattened:
+#   model  = int[5]   (v_tab, d, maxlen, num_blocks, num_heads)
+#   loss   = int[8]   (M, n_train, n_ex, V, V_prev, mode, n_train_global, n_ex_global) + float lambda_ + Tensor? pos, ex_pos,
+#                     teacher, teacher_row
+#   dp comm = int rank, int world, int[] theta_ptrs, int[] grad_ptrs, int[] flag_ptrs  (peer-mapped device addresses)
+# Workspace-size queries, IPC plumbing and status reads are host-only helpers and stay plain Python functions.
 _registered = False
+
+_SCHEMAS = {
+    "encoder_fwd": "(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor(a!) ws, Tensor(b!) rep, float dropout_rate, int seed) -> ()",
+    "encoder_fwd_tc": "(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor(a!) ws, Tensor(b!) rep, float dropout_rate, int seed, Tensor? d_step) -> ()",
+    "encoder_bwd": "(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor ws, Tensor(a!) bwd_ws, Tensor d_rep, Tensor(b!) grad, float dropout_rate, int seed) -> ()",
+    "encoder_bwd_tc": "(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor ws, Tensor(a!) bwd_ws, Tensor d_rep, Tensor(b!) grad, float dropout_rate, int seed, Tensor? d_step) -> ()",
+    "loss_fwd_bwd": "(int[] model, Tensor theta, Tensor rep, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, Tensor(a!) ws, Tensor(b!) loss, Tensor(c!) row_loss, Tensor(d!) d_rep, Tensor(e!) grad) -> ()",
+    "loss_fwd_bwd_tc": "(int[] model, Tensor theta, Tensor rep, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, Tensor(a!) ws, Tensor(b!) loss, Tensor(c!) row_loss, Tensor(d!) d_rep, Tensor(e!) grad) -> ()",
+    "loss_tc_vp_fwd": "(int[] model, Tensor theta, Tensor rep, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, int v_lo, int v_hi, Tensor(a!) ws, Tensor(b!) stats) -> ()",
+    "loss_tc_vp_bwd": "(int[] model, Tensor theta, Tensor rep, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, int v_lo, int v_hi, Tensor(a!) ws, Tensor lse, Tensor(b!) d_rep_partial, Tensor(c!) grad) -> ()",
+    "train_fwd_bwd_tc": "(int[] model, Tensor theta, Tensor ids, int Tcap, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, Tensor(a!) enc_ws, Tensor(b!) bwd_ws, Tensor(c!) loss_ws, Tensor(d!) rep, Tensor(e!) loss, Tensor(f!) row_loss, Tensor(g!) d_rep, Tensor(h!) grad, float dropout_rate, int seed, Tensor? d_step, bool serial) -> ()",
+    "train_step_tc": "(int[] model, Tensor(a!) theta, Tensor ids, int Tcap, int[] loss_dims, float lambda_, Tensor? pos, Tensor? ex_pos, Tensor? teacher, Tensor? teacher_row, Tensor(b!) enc_ws, Tensor(c!) bwd_ws, Tensor(d!) loss_ws, Tensor(e!) rep, Tensor(f!) loss, Tensor(g!) row_loss, Tensor(h!) d_rep, Tensor(i!) grad, Tensor(j!) adam_m, Tensor(k!) adam_v, Tensor(l!) state, int V, float lr, float dropout_rate, int seed, Tensor? d_step, float ewc_lambda, Tensor? fisher, Tensor? theta_star, bool serial) -> ()",
+    "logits": "(int[] model, Tensor theta, Tensor rep, int V, Tensor(a!) out) -> ()",
+    "adam_step": "(int[] model, Tensor(a!) theta, Tensor(b!) m, Tensor(c!) v, Tensor grad, Tensor(d!) state, int V, float lr, float ewc_lambda, Tensor? fisher, Tensor? theta_star) -> ()",
+    "dp_wait": "(int rank, int world, int[] theta_ptrs, int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) flags) -> ()",
+    "dp_adam_step": "(int[] model, int rank, int world, int[] theta_ptrs, int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) theta, Tensor(b!) m, Tensor(c!) v, Tensor(d!) state, int V, float lr, float ewc_lambda, Tensor? fisher, Tensor? theta_star) -> ()",
+    "eval_rank_topk": "(int[] model, Tensor theta, Tensor rep, Tensor gt, int V, int k, Tensor(a!) ws, Tensor(b!) rank, Tensor(c!) topk_item, Tensor(d!) topk_score) -> ()",
+    "eval_rank_tc": "(int[] model, Tensor theta, Tensor rep, Tensor gt, int V, Tensor(a!) ws, Tensor(b!) rank, Tensor(c!) overflow) -> ()",
+    "eval_rank_topk_tc": "(int[] model, Tensor theta, Tensor rep, Tensor gt, int V, int k, Tensor(a!) ws, Tensor(b!) rank, Tensor(c!) topk_item, Tensor(d!) topk_score, Tensor(e!) overflow) -> ()",
+    "herding_segmented": "(int[] model, Tensor rep, Tensor cand, Tensor seg_off, Tensor quota, Tensor max_steps, Tensor(a!) ws, Tensor(b!) picks, Tensor(c!) n_picked) -> ()",
+    "fisher_accumulate": "(int[] model, Tensor grad, Tensor(a!) acc, int V) -> ()",
+    "fisher_finalize": "(int[] model, Tensor acc, Tensor(a!) fisher, int V, int n_data) -> ()",
+    "fisher_batched": "(int[] model, Tensor theta, Tensor ids, Tensor pos, int Tcap, int V, Tensor(a!) enc_ws, Tensor(b!) bwd_ws, Tensor(c!) ws, Tensor(d!) acc) -> ()",
+    "gather_rows_i32": "(Tensor src, Tensor idx, Tensor(a!) out) -> ()",
+    "gather_batch": "(Tensor t_ids, Tensor t_lab, Tensor ti, Tensor? e_ids, Tensor? e_aux, Tensor? ei, Tensor(a!) ids, Tensor(b!) pos, Tensor(c!)? aux) -> ()",
+    "gather_batch_q": "(Tensor t_ids, Tensor t_lab, int n_train, Tensor? e_ids, Tensor? e_aux, int n_ex, Tensor q, Tensor q_off, Tensor counter, Tensor(a!) ids, Tensor(b!) pos, Tensor(c!)? aux) -> ()",
+    "queue_advance": "(Tensor(a!) counter) -> ()",
+}
 
 
 def register_torch_ops() -> None:
-    """Expose the kernel groups as ``torch.ops.ader_b200.*`` (CUDA implementations only)."""
+    """Expose every compute entry point as ``torch.ops.ader_b200.*`` (CUDA implementations only)."""
     global _registered
     if _registered:
         return
     lib = torch.library.Library("ader_b200", "DEF")
-    lib.define("encoder_fwd(int[] model, Tensor theta, Tensor ids, int Tcap, Tensor(a!) ws, Tensor(b!) rep, "
-               "float dropout_rate, int seed) -> ()")
-    lib.define("logits(int[] model, Tensor theta, Tensor rep, int V, Tensor(a!) out) -> ()")
-    lib.define("eval_rank_topk(int[] model, Tensor theta, Tensor rep, Tensor gt, int V, int k, Tensor(a!) ws, "
-               "Tensor(b!) rank, Tensor(c!) topk_item, Tensor(d!) topk_score) -> ()")
-    lib.define("adam_step(int[] model, Tensor(a!) theta, Tensor(b!) m, Tensor(c!) v, Tensor grad, Tensor(d!) state, "
-               "int V, float lr) -> ()")
 
     def _ms(model):
         return AderModel(*[int(x) for x in model])
 
-    def _enc(model, theta, ids, Tcap, ws, rep, dropout_rate, seed):
-        encoder_fwd(_ms(model), theta, ids, Tcap, ws, rep, dropout_rate, seed)
+    def _la(dims, lam, pos, ex_pos, teacher, teacher_row):
+        M, n_train, n_ex, V, V_prev, mode, ntg, neg = [int(x) for x in dims]
+        return make_loss_args(M, n_train, n_ex, V, V_prev, mode, lam, pos, ex_pos, teacher, teacher_row, ntg, neg)
 
-    def _logits(model, theta, rep, V, out):
-        logits(_ms(model), theta, rep, V, out)
+    def _comm(rank, world, tp, gp, fp):
+        return dp_comm(int(rank), int(world), list(tp), list(gp), list(fp))
 
-    def _eval(model, theta, rep, gt, V, k, ws, rank, topk_item, topk_score):
-        eval_rank_topk(_ms(model), theta, rep, gt, V, k, ws, rank, topk_item, topk_score)
-
-    def _adam(model, theta, m, v, grad, state, V, lr):
-        adam_step(_ms(model), theta, m, v, grad, state, V, lr)
-
-    lib.impl("encoder_fwd", _enc, "CUDA")
-    lib.impl("logits", _logits, "CUDA")
-    lib.impl("eval_rank_topk", _eval, "CUDA")
-    lib.impl("adam_step", _adam, "CUDA")
+    impls = {
+        "encoder_fwd": lambda model, theta, ids, Tcap, ws, rep, p, seed: encoder_fwd(_ms(model), theta, ids, Tcap, ws, rep, p, seed),
+        "encoder_fwd_tc": lambda model, theta, ids, Tcap, ws, rep, p, seed, d_step: encoder_fwd(_ms(model), theta, ids, Tcap, ws, rep, p, seed, impl="tc", d_step=d_step),
+        "encoder_bwd": lambda model, theta, ids, Tcap, ws, bws, d_rep, grad, p, seed: encoder_bwd(_ms(model), theta, ids, Tcap, ws, bws, d_rep, grad, p, seed),
+        "encoder_bwd_tc": lambda model, theta, ids, Tcap, ws, bws, d_rep, grad, p, seed, d_step: encoder_bwd(_ms(model), theta, ids, Tcap, ws, bws, d_rep, grad, p, seed, impl="tc", d_step=d_step),
+        "loss_fwd_bwd": lambda model, theta, rep, dims, lam, pos, ex_pos, teacher, trow, ws, loss, row_loss, d_rep, grad:
+            loss_fwd_bwd(_ms(model), theta, rep, _la(dims, lam, pos, ex_pos, teacher, trow), ws, loss, row_loss, d_rep, grad),
+        "loss_fwd_bwd_tc": lambda model, theta, rep, dims, lam, pos, ex_pos, teacher, trow, ws, loss, row_loss, d_rep, grad:
+            loss_fwd_bwd_tc(_ms(model), theta, rep, _la(dims, lam, pos, ex_pos, teacher, trow), ws, loss, row_loss, d_rep, grad),
+        "loss_tc_vp_fwd": lambda model, theta, rep, dims, lam, pos, ex_pos, teacher, trow, v_lo, v_hi, ws, stats:
+            loss_tc_vp_fwd(_ms(model), theta, rep, _la(dims, lam, pos, ex_pos, teacher, trow), v_lo, v_hi, ws, stats),
+        "loss_tc_vp_bwd": lambda model, theta, rep, dims, lam, pos, ex_pos, teacher, trow, v_lo, v_hi, ws, lse, d_part, grad:
+            loss_tc_vp_bwd(_ms(model), theta, rep, _la(dims, lam, pos, ex_pos, teacher, trow), v_lo, v_hi, ws, lse, d_part, grad),
+        "train_fwd_bwd_tc": lambda model, theta, ids, Tcap, dims, lam, pos, ex_pos, teacher, trow, ews, bws, lws, rep, loss, row_loss, d_rep, grad, p, seed, d_step, serial:
+            train_fwd_bwd_tc(_ms(model), theta, ids, Tcap, _la(dims, lam, pos, ex_pos, teacher, trow), ews, bws, lws, rep, loss, row_loss, d_rep, grad, p, seed, d_step, serial),
+        "train_step_tc": lambda model, theta, ids, Tcap, dims, lam, pos, ex_pos, teacher, trow, ews, bws, lws, rep, loss, row_loss, d_rep, grad, am, av, state, V, lr, p, seed, d_step, ewc_lambda, fisher, theta_star, serial:
+            train_step_tc(_ms(model), theta, ids, Tcap, _la(dims, lam, pos, ex_pos, teacher, trow), ews, bws, lws, rep, loss, row_loss, d_rep, grad, am, av, state, V, lr, p, seed, d_step, ewc_lambda, fisher, theta_star, serial=serial),
+        "logits": lambda model, theta, rep, V, out: logits(_ms(model), theta, rep, V, out),
+        "adam_step": lambda model, theta, m, v, grad, state, V, lr, ewc_lambda, fisher, theta_star: adam_step(_ms(model), theta, m, v, grad, state, V, lr, ewc_lambda, fisher, theta_star),
+        "dp_wait": lambda rank, world, tp, gp, fp, flags: dp_wait(_comm(rank, world, tp, gp, fp)),
+        "dp_adam_step": lambda model, rank, world, tp, gp, fp, theta, m, v, state, V, lr, ewc_lambda, fisher, theta_star:
+            dp_adam_step(_ms(model), _comm(rank, world, tp, gp, fp), m, v, state, V, lr, ewc_lambda, fisher, theta_star),
+        "eval_rank_topk": lambda model, theta, rep, gt, V, k, ws, rank, items, scores: eval_rank_topk(_ms(model), theta, rep, gt, V, k, ws, rank, items, scores),
+        "eval_rank_tc": lambda model, theta, rep, gt, V, ws, rank, overflow: eval_rank_tc(_ms(model), theta, rep, gt, V, ws, rank, overflow),
+        "eval_rank_topk_tc": lambda model, theta, rep, gt, V, k, ws, rank, items, scores, overflow: eval_rank_topk_tc(_ms(model), theta, rep, gt, V, k, ws, rank, items, scores, overflow),
+        "herding_segmented": lambda model, rep, cand, seg_off, quota, max_steps, ws, picks, n_picked: herding_segmented(_ms(model), rep, cand, seg_off, quota, max_steps, ws, picks, n_picked),
+        "fisher_accumulate": lambda model, grad, acc, V: fisher_accumulate(_ms(model), grad, acc, V),
+        "fisher_finalize": lambda model, acc, fisher, V, n_data: fisher_finalize(_ms(model), acc, fisher, V, n_data),
+        "fisher_batched": lambda model, theta, ids, pos, Tcap, V, ews, bws, ws, acc: fisher_batched(_ms(model), theta, ids, pos, Tcap, V, ews, bws, ws, acc),
+        "gather_rows_i32": lambda src, idx, out: gather_rows_i32(src, idx, out),
+        "gather_batch": lambda t_ids, t_lab, ti, e_ids, e_aux, ei, ids, pos, aux: gather_batch(t_ids, t_lab, ti, e_ids, e_aux, ei, ids, pos, aux),
+        "gather_batch_q": lambda t_ids, t_lab, n_train, e_ids, e_aux, n_ex, q, q_off, counter, ids, pos, aux: gather_batch_q(t_ids, t_lab, n_train, e_ids, e_aux, n_ex, q, q_off, counter, ids, pos, aux),
+        "queue_advance": lambda counter: queue_advance(counter),
+    }
+    assert set(impls) == set(_SCHEMAS)
+    for name, schema in _SCHEMAS.items():
+        lib.define(name + schema)
+        lib.impl(name, impls[name], "CUDA")
     register_torch_ops._lib = lib      # keep alive
     _registered = True
+
+
+def registered_op_names():
+    return sorted(_SCHEMAS)

@@ -98,3 +98,16 @@ def test_model_needs_cuda():
     args = type("A", (), dict(hidden_units=150, maxlen=50, num_blocks=2, num_heads=1, random_seed=0, lr=5e-4, dropout_rate=0.0))()
     with pytest.raises(RuntimeError):
         Ader(100, args)
+
+
+def test_every_compute_entry_point_is_a_torch_op(lib):
+    """north_star: the C ABI is 'exposed as PyTorch custom ops'.  Every entry point that launches device work is registered
+    as torch.ops.ader_b200.<name>; size queries, introspection, IPC plumbing, status reads and debug hooks are host helpers."""
+    import torch
+    ops.register_torch_ops()
+    host_only = ("_ws_bytes", "_ws_slot", "abi_version", "last_error", "param_count", "param_offset", "dense_count", "ipc_",
+                 "dp_status", "debug_", "eval_topk_chunks")
+    want = sorted(s[len("ader_"):] for s in _declared_symbols() if not any(h in s for h in host_only))
+    assert want == ops.registered_op_names()
+    for name in want:
+        assert hasattr(torch.ops.ader_b200, name)
