@@ -110,11 +110,13 @@ __global__ void __launch_bounds__(256) k_herding(const float* __restrict__ rep, 
 // max 3 342; DIGINETICA: median 2, max 98):
 //   n <= 16   one WARP per segment, D and w in registers (5 values per lane and row): no shared memory, no barriers;
 //   n <= 350  one CTA per segment, D in shared memory (<= 210 KB);
-//   n <= 2800 one CLUSTER of 8 CTAs per segment, D split over their shared memories; per step the 8 local arg-maxima meet
+//   larger    one CLUSTER of 8 CTAs per segment, D split over their shared memories (8 x 350 rows; a segment beyond 2 800
+//             keeps the remainder of each CTA's slice in global memory / L2); per step the 8 local arg-maxima meet
 //             in CTA 0 (DSMEM), the owner of the pick broadcasts its row into every CTA (DSMEM), two cluster barriers;
-//   larger    k_herding (D in global memory / L2).
+//   > 16 384  k_herding (D in global memory / L2).
 // A prologue kernel sorts the segment ids into the four classes.
 constexpr int HS_MAX = 16, HM_MAX = 350, HB_CTAS = 8, HB_PER = 350, HB_MAX = HB_CTAS * HB_PER;
+constexpr int HB_NMAX = 16384, HB_BM_WORDS = HB_NMAX / 32;      // largest segment of the cluster form (picked-candidate bitmap)
 constexpr int HD = 150;                        // rows are padded to 5 x 32 lanes; d <= 160
 constexpr int HREG = 5;
 
@@ -127,7 +129,7 @@ __global__ void k_herding_classify(const int* __restrict__ seg_off, const int* _
   if (n <= 0 || min(quota[s], n) <= 0) { n_picked[s] = 0; return; }
   if (n <= HS_MAX) l_small[atomicAdd(cnt + 0, 1)] = s;
   else if (n <= HM_MAX) l_mid[atomicAdd(cnt + 1, 1)] = s;
-  else if (n <= HB_MAX) l_big[atomicAdd(cnt + 2, 1)] = s;
+  else if (n <= HB_NMAX) l_big[atomicAdd(cnt + 2, 1)] = s;     // > 2800: the rows beyond 8 x 350 spill to global memory
   else l_huge[atomicAdd(cnt + 3, 1)] = s;
 }
 
@@ -195,30 +197,37 @@ __global__ void __launch_bounds__(256) k_herding_small(const float* __restrict__
 }
 
 // ---- shared by the CTA and cluster forms: rows [j0, j0 + nl) of the segment normalised into shared memory ---------------
+// rows beyond `cap_s` (only in segments larger than the cluster's shared memories) go to the global spill gD [*, 160]
 __device__ __forceinline__ void load_norm_rows(const float* __restrict__ rep, int d, const int* __restrict__ cand, int off, int j0, int nl,
-                                               float* __restrict__ sD, float* __restrict__ snrm) {
-  for (int j = threadIdx.x; j < nl; j += blockDim.x) snrm[j] = sqrtf(np_pairwise_sq(rep + (long long)cand[off + j0 + j] * d, d));
-  __syncthreads();
+                                               float* __restrict__ sD, float* __restrict__ snrm, int cap_s = 0x7fffffff,
+                                               float* __restrict__ gD = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < nl; j += nw) {
-    const float* x = rep + (long long)cand[off + j0 + j] * d;
-    const float nrm = snrm[j];
-    for (int c = lane; c < 160; c += 32) sD[j * 160 + c] = c < d ? __fdiv_rn(x[c], nrm) : 0.f;
+  for (int b0 = 0; b0 < nl; b0 += cap_s) {             // norms staged cap_s rows at a time (snrm holds cap_s entries)
+    const int nb = min(cap_s, nl - b0);
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) snrm[j] = sqrtf(np_pairwise_sq(rep + (long long)cand[off + j0 + b0 + j] * d, d));
+    __syncthreads();
+    for (int j = warp; j < nb; j += nw) {
+      const float* x = rep + (long long)cand[off + j0 + b0 + j] * d;
+      const float nrm = snrm[j];
+      float* o = (b0 + j < cap_s) ? sD + (b0 + j) * 160 : gD + (long long)(b0 + j - cap_s) * 160;
+      for (int c = lane; c < 160; c += 32) o[c] = c < d ? __fdiv_rn(x[c], nrm) : 0.f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 // local first-max over rows [0, nl) of sD against w (shared): result (value, local index) of this CTA
 __device__ __forceinline__ void local_argmax(const float* __restrict__ sD, const float* __restrict__ sw, int nl, float* bestv, int* bestj,
-                                             float& fv, int& fj) {
+                                             float& fv, int& fj, int cap_s = 0x7fffffff, const float* __restrict__ gD = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float wv[HREG];
 #pragma unroll
   for (int i = 0; i < HREG; ++i) wv[i] = sw[lane + 32 * i];
   float bv = -INFINITY; int bj = 0x7fffffff;
-  for (int j = warp; j < nl; j += nw) {
+  for (int j = warp; j < nl; j += nw) {                // j ascending per warp, warps merged below by (value, index): first max
+    const float* row = j < cap_s ? sD + j * 160 : gD + (long long)(j - cap_s) * 160;
     float Dv[HREG];
 #pragma unroll
-    for (int i = 0; i < HREG; ++i) Dv[i] = sD[j * 160 + lane + 32 * i];
+    for (int i = 0; i < HREG; ++i) Dv[i] = row[lane + 32 * i];
     const float a = warp_dot(wv, Dv);
     if (a > bv) { bv = a; bj = j; }
   }
@@ -287,7 +296,7 @@ __device__ __forceinline__ void st_cluster_s32(uint32_t addr, int v) { asm volat
 __global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(256)
 k_herding_big(const float* __restrict__ rep, int d, const int* __restrict__ cand, const int* __restrict__ seg_off,
               const int* __restrict__ quota, const int* __restrict__ max_steps, const int* __restrict__ list,
-              const int* __restrict__ cnt, int* __restrict__ picks, int* __restrict__ n_picked) {
+              const int* __restrict__ cnt, float* __restrict__ Dn, int* __restrict__ picks, int* __restrict__ n_picked) {
   extern __shared__ float hs[];
   const int ci = blockIdx.x / HB_CTAS;
   if (ci >= cnt[2]) return;                        // uniform over the cluster
@@ -305,10 +314,11 @@ k_herding_big(const float* __restrict__ rep, int d, const int* __restrict__ cand
   const int s = list[ci];
   const int off = seg_off[s], n = seg_off[s + 1] - off;
   const int m = min(quota[s], n), tid = threadIdx.x;
-  const int per = (n + HB_CTAS - 1) / HB_CTAS;     // candidates per CTA (<= HB_PER), contiguous ranges in candidate order
-  const int j0 = min(n, (int)cr * per), nl = min(n, j0 + per) - j0;
-  load_norm_rows(rep, d, cand, off, j0, nl, sD, snrm);
-  for (int q = tid; q < (HB_MAX + 31) / 32; q += blockDim.x) bm[q] = 0u;
+  const int per = (n + HB_CTAS - 1) / HB_CTAS;     // candidates per CTA, contiguous ranges in candidate order; the first HB_PER
+  const int j0 = min(n, (int)cr * per), nl = min(n, j0 + per) - j0;   // of them sit in shared memory, the rest (segments > 2800) in gD
+  float* gD = Dn + (long long)(off + j0) * 160;    // this CTA's slice of the spill (row stride 160)
+  load_norm_rows(rep, d, cand, off, j0, nl, sD, snrm, HB_PER, gD);
+  for (int q = tid; q < HB_BM_WORDS; q += blockDim.x) bm[q] = 0u;
   if (tid == 0) cnt_s = 0;
   // mean: ONE sequential sum over the candidates in order (D.mean(axis=1) adds candidate by candidate): CTA r continues
   // the partial of CTA r-1, the last one divides and hands mu (= the initial w) to everybody
@@ -317,7 +327,7 @@ k_herding_big(const float* __restrict__ rep, int d, const int* __restrict__ cand
   for (uint32_t r = 0; r < HB_CTAS; ++r) {
     if (cr == r && tid < 160) {
       float acc = spart[tid];
-      for (int j = 0; j < nl; ++j) acc = __fadd_rn(acc, sD[j * 160 + tid]);
+      for (int j = 0; j < nl; ++j) acc = __fadd_rn(acc, j < HB_PER ? sD[j * 160 + tid] : gD[(long long)(j - HB_PER) * 160 + tid]);
       if (r + 1 < HB_CTAS) st_cluster_f32(map_to_cta(spart + tid, r + 1), acc);
       else {
         const float mv = tid < d ? __fdiv_rn(acc, (float)n) : 0.f;
@@ -330,7 +340,7 @@ k_herding_big(const float* __restrict__ rep, int d, const int* __restrict__ cand
   const uint32_t av = map_to_cta(gv, 0), aj = map_to_cta(gj, 0);
   for (int step = 0; step < steps; ++step) {
     float fv; int fj;
-    local_argmax(sD, sw, nl, bestv, bestj, fv, fj);
+    local_argmax(sD, sw, nl, bestv, bestj, fv, fj, HB_PER, gD);
     if (tid == 0) {                                // (value, GLOBAL candidate index) of this CTA -> CTA 0
       st_cluster_f32(av + 4u * cr, nl > 0 ? fv : -INFINITY);
       st_cluster_s32(aj + 4u * cr, nl > 0 ? j0 + fj : 0x7fffffff);
@@ -348,7 +358,8 @@ k_herding_big(const float* __restrict__ rep, int d, const int* __restrict__ cand
     if (bjj >= j0 && bjj < j0 + nl) {              // owner: record the pick, broadcast its row into every CTA
       if (tid == 0 && is_new) picks[off + cnt_s] = bjj;
       if (tid < 160) {
-        const float v = sD[(bjj - j0) * 160 + tid];
+        const int lj = bjj - j0;
+        const float v = lj < HB_PER ? sD[lj * 160 + tid] : gD[(long long)(lj - HB_PER) * 160 + tid];
         for (uint32_t q = 0; q < HB_CTAS; ++q) st_cluster_f32(map_to_cta(srow + tid, q), v);
       }
     }
@@ -369,7 +380,7 @@ using namespace ader;
 extern "C" size_t ader_herding_ws_bytes(const AderModel* m, int32_t N) {
   if (check_model(m) || N <= 0) return 0;
   // [Dn fp32 N x d (global-memory fallback for segments > 2800)] [selected N] [class lists 4 x N] [counters]
-  return align_up(sizeof(float) * (size_t)N * m->d) + align_up(sizeof(int) * (size_t)N) + 4 * align_up(sizeof(int) * (size_t)N) + 256;
+  return align_up(sizeof(float) * (size_t)N * 160) + align_up(sizeof(int) * (size_t)N) + 4 * align_up(sizeof(int) * (size_t)N) + 256;
 }
 
 extern "C" int32_t ader_herding_segmented(const AderModel* m, const float* rep, int32_t N, const int32_t* cand,
@@ -382,7 +393,7 @@ extern "C" int32_t ader_herding_segmented(const AderModel* m, const float* rep, 
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)ws; size_t o = 0;
   auto take = [&](size_t n) { char* p = base + o; o += align_up(n); return p; };
-  float* Dn = (float*)take(sizeof(float) * (size_t)N * m->d);
+  float* Dn = (float*)take(sizeof(float) * (size_t)N * 160);
   int* selected = (int*)take(sizeof(int) * (size_t)N);
   int* lists[4];
   for (int k = 0; k < 4; ++k) lists[k] = (int*)take(sizeof(int) * (size_t)N);
@@ -394,7 +405,7 @@ extern "C" int32_t ader_herding_segmented(const AderModel* m, const float* rep, 
     return 0;
   }
   constexpr int SMEM_MID = (HM_MAX * 160 + 2 * 160 + HM_MAX) * 4;
-  constexpr int SMEM_BIG = (HB_PER * 160 + 4 * 160 + HB_PER) * 4 + ((HB_MAX + 31) / 32) * 4;
+  constexpr int SMEM_BIG = (HB_PER * 160 + 4 * 160 + HB_PER) * 4 + HB_BM_WORDS * 4;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_herding_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MID);
@@ -405,10 +416,10 @@ extern "C" int32_t ader_herding_segmented(const AderModel* m, const float* rep, 
   k_herding_classify<<<cdiv(n_seg, 256), 256, 0, st>>>(seg_off, quota, n_seg, cnt, lists[0], lists[1], lists[2], lists[3], n_picked);
   // grids are upper bounds of the class sizes (a class-c segment has more than its lower size bound of candidates);
   // CTAs beyond the device-side count leave at once
-  const int g_small = n_seg, g_mid = N / (HS_MAX + 1) + 1, g_big = N / (HM_MAX + 1) + 1, g_huge = N / (HB_MAX + 1) + 1;
+  const int g_small = n_seg, g_mid = N / (HS_MAX + 1) + 1, g_big = N / (HM_MAX + 1) + 1, g_huge = N / (HB_NMAX + 1) + 1;
   k_herding_small<<<cdiv((long long)g_small * 32, 256), 256, 0, st>>>(rep, m->d, cand, seg_off, quota, max_steps, lists[0], cnt, picks, n_picked);
   k_herding_mid<<<g_mid < n_seg ? g_mid : n_seg, 256, SMEM_MID, st>>>(rep, m->d, cand, seg_off, quota, max_steps, lists[1], cnt, selected, picks, n_picked);
-  k_herding_big<<<(g_big < n_seg ? g_big : n_seg) * HB_CTAS, 256, SMEM_BIG, st>>>(rep, m->d, cand, seg_off, quota, max_steps, lists[2], cnt, picks, n_picked);
+  k_herding_big<<<(g_big < n_seg ? g_big : n_seg) * HB_CTAS, 256, SMEM_BIG, st>>>(rep, m->d, cand, seg_off, quota, max_steps, lists[2], cnt, Dn, picks, n_picked);
   k_herding<<<g_huge < n_seg ? g_huge : n_seg, 256, 0, st>>>(rep, m->d, cand, seg_off, quota, max_steps, Dn, selected, picks, n_picked, lists[3], cnt + 3);
   ADER_CHECK_LAUNCH("herding");
   return 0;
