@@ -112,6 +112,7 @@ class PeriodTrainer:
         self.q = torch.zeros(steps * max(width, 1), dtype=torch.int32, device=dev)
         self.q_off = torch.zeros(steps, dtype=torch.int64, device=dev)
         self.q_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.host_s = {"plan": 0.0, "launch": 0.0}         # host seconds spent planning epochs / launching their steps
         self._q_host = torch.zeros(steps * max(width, 1), dtype=torch.int32).pin_memory()
         self._qoff_host = torch.zeros(steps, dtype=torch.int64).pin_memory()
 
@@ -182,6 +183,7 @@ class PeriodTrainer:
         the device in ONE copy, and every step is a graph replay that gathers its batch from that queue.  A step whose
         batch geometry has no graph (rare tail batches) runs eagerly from the same queue."""
         m, dev, L = self.model, self.model.device, self.model.hp.maxlen
+        t_plan0 = time.time()
         plan = []
         qh, oh = self._q_host.numpy(), self._qoff_host.numpy()
         o = 0
@@ -202,6 +204,8 @@ class PeriodTrainer:
         self.q.copy_(self._q_host, non_blocking=True)
         self.q_off.copy_(self._qoff_host, non_blocking=True)
         self.q_counter.zero_()
+        self.host_s["plan"] += time.time() - t_plan0
+        t_l0 = time.time()
         loss = None
         for key, nt, ne, n_tok in plan:
             gs = self._graph(*key) if (key[0] > 0 and (self.es is None or key[1] > 0)) else None
@@ -227,6 +231,7 @@ class PeriodTrainer:
             else:
                 loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_logits=self.es.teacher,
                                     teacher_rows=aux[:ne], n_tokens=n_tok)
+        self.host_s["launch"] += time.time() - t_l0
         return loss
 
     def _teacher_rows(self):
@@ -538,7 +543,7 @@ def run(args) -> dict:
         stats.append({"period": period, "train_rows": trainer.rows_seen, "train_s": train_time, "sessions_per_s": sps,
                       "eval_rows": eval_rows, "eval_s": eval_time, "eval_rows_per_s": eval_rows / max(eval_time, 1e-9),
                       "epochs": epoch, "max_item": int(max_item), "eager_steps": trainer.n_eager,
-                      "epoch_s": epoch_s, "epoch_rows": epoch_rows,
+                      "epoch_s": epoch_s, "epoch_rows": epoch_rows, "host_plan_s": trainer.host_s["plan"], "host_launch_s": trainer.host_s["launch"],
                       # epochs after the first: the CUDA graphs of the period's batch geometries exist by then
                       "steady_sessions_per_s": (sum(epoch_rows[1:]) / max(sum(epoch_s[1:]), 1e-9)) if len(epoch_s) > 1 else None})
         info = "Period %d train throughput: %.0f sessions/s (%d rows in %.2f s; graph replays by batch geometry / token capacity %s, eager steps %d)" % (

@@ -251,14 +251,16 @@ def gpu_components(dev):
                       "gbs_compulsory": N * 150 * 4 / dt / 1e9}
     # EWC Fisher (EWC.py:126-164): S sessions at batch-1 semantics, V_tab = 43 137
     e = Ewc(43136, a, device=dev, init_seed=0)
-    S_ = 200
+    S_ = 4096
     sess = [list(rng.randint(1, V + 1, int(n) + 1)) for n in np.minimum(50, rng.geometric(0.22, S_) + 1)]
     import random
     random.seed(0)
+    e.compute_fisher(None, sess[:256], 50, V)                        # warm-up (workspace allocation, first launches)
     torch.cuda.synchronize(); t0 = time.time()
     e.compute_fisher(None, sess, 50, V)
     torch.cuda.synchronize()
     out["fisher_samples_per_s"] = S_ / (time.time() - t0)
+    out["fisher_shape"] = {"samples": S_, "v_tab": 43137, "includes": "host session sampling + batched exact backward + fp64 accumulation"}
     del m, e
     torch.cuda.empty_cache()
     return out
