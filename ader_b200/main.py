@@ -113,6 +113,7 @@ class PeriodTrainer:
         self.q_off = torch.zeros(steps, dtype=torch.int64, device=dev)
         self.q_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.host_s = {"plan": 0.0, "launch": 0.0}         # host seconds spent planning epochs / launching their steps
+        self._q_copied = None                               # event: the last epoch's queue copies are done
         self._q_host = torch.zeros(steps * max(width, 1), dtype=torch.int32).pin_memory()
         self._qoff_host = torch.zeros(steps, dtype=torch.int64).pin_memory()
 
@@ -178,61 +179,76 @@ class PeriodTrainer:
         return gs
 
     def run_epoch(self, n_steps: int):
-        """One epoch (main.py:220-256) with the host out of the loop: the samplers are advanced for all `n_steps` steps first
-        (same calls in the same order as step-by-step, so both host RNG streams move identically), the row indices go to
-        the device in ONE copy, and every step is a graph replay that gathers its batch from that queue.  A step whose
+        """One epoch (main.py:220-256) with the host out of the loop: the samplers are advanced a chunk of steps ahead of the
+        GPU (same calls in the same order as step-by-step, so both host RNG streams move identically), the row indices go to
+        the device chunk by chunk, and every step is a graph replay that gathers its batch from that queue.  A step whose
         batch geometry has no graph (rare tail batches) runs eagerly from the same queue."""
-        m, dev, L = self.model, self.model.device, self.model.hp.maxlen
-        t_plan0 = time.time()
-        plan = []
+        m = self.model
+        if self._q_copied is not None:
+            self._q_copied.synchronize()                         # last epoch's queue copies have left the pinned buffers
         qh, oh = self._q_host.numpy(), self._qoff_host.numpy()
-        o = 0
-        for s_ in range(n_steps):
-            ti = self.ts.next_indices()
-            ei = self.es.next_indices() if self.es is not None else np.zeros(0, np.int64)
-            key = (len(ti), len(ei))
-            self.rows_seen += len(ti) + len(ei)
-            if self.world > 1:
-                (tl, th), (el, eh) = self._shard(len(ti), len(ei))
-                ti, ei = ti[tl:th], ei[el:eh]
-            n_tok = int(self.t_nin[ti].sum()) + (int(self.e_nin[ei].sum()) if self.es is not None else 0)
-            oh[s_] = o
-            qh[o:o + len(ti)] = ti
-            qh[o + len(ti):o + len(ti) + len(ei)] = ei
-            o += len(ti) + len(ei)
-            plan.append((key, len(ti), len(ei), n_tok))
-        self.q.copy_(self._q_host, non_blocking=True)
-        self.q_off.copy_(self._qoff_host, non_blocking=True)
         self.q_counter.zero_()
-        self.host_s["plan"] += time.time() - t_plan0
-        t_l0 = time.time()
-        loss = None
-        for key, nt, ne, n_tok in plan:
-            gs = self._graph(*key) if (key[0] > 0 and (self.es is None or key[1] > 0)) else None
-            if self.world > 1:
-                m.global_counts = key
-            if gs is not None:
-                loss = gs.run_queued(n_tok)
-                continue
-            self.n_eager += 1                                    # rare batch geometry: eager launches, same queue
-            ids = torch.empty((nt + ne, L), dtype=torch.int32, device=dev)
-            pos = torch.empty(nt, dtype=torch.int32, device=dev)
-            aux = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
-            e_aux = None
-            if self.es is not None:
-                e_aux = self.e_lab if m.disable_distillation else self._teacher_rows()
-            ops.gather_batch_q(self.t_ids, self.t_lab, nt, self.e_ids if ne else None, e_aux if ne else None, ne, self.q, self.q_off,
-                               self.q_counter, ids, pos, aux[:ne] if ne else None)
-            ops.queue_advance(self.q_counter)
-            if self.es is None or ne == 0:
-                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
-            elif m.disable_distillation:
-                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_pos=aux[:ne], n_tokens=n_tok)
-            else:
-                loss = m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_logits=self.es.teacher,
-                                    teacher_rows=aux[:ne], n_tokens=n_tok)
-        self.host_s["launch"] += time.time() - t_l0
+        o, s0, loss = 0, 0, None
+        # planned and launched in chunks, so the host plans chunk k+1 while the GPU runs chunk k (first chunk short: the
+        # GPU starts after a few steps' worth of planning)
+        while s0 < n_steps:
+            s1 = min(n_steps, s0 + (self.CHUNK0 if s0 == 0 else self.CHUNK))
+            t0 = time.time()
+            plan, o0 = [], o
+            for s_ in range(s0, s1):
+                ti = self.ts.next_indices()
+                ei = self.es.next_indices() if self.es is not None else np.zeros(0, np.int64)
+                key = (len(ti), len(ei))
+                self.rows_seen += len(ti) + len(ei)
+                if self.world > 1:
+                    (tl, th), (el, eh) = self._shard(len(ti), len(ei))
+                    ti, ei = ti[tl:th], ei[el:eh]
+                n_tok = int(self.t_nin[ti].sum()) + (int(self.e_nin[ei].sum()) if self.es is not None else 0)
+                oh[s_] = o
+                qh[o:o + len(ti)] = ti
+                qh[o + len(ti):o + len(ti) + len(ei)] = ei
+                o += len(ti) + len(ei)
+                plan.append((key, len(ti), len(ei), n_tok))
+            if o > o0:
+                self.q[o0:o].copy_(self._q_host[o0:o], non_blocking=True)
+            self.q_off[s0:s1].copy_(self._qoff_host[s0:s1], non_blocking=True)
+            t1 = time.time()
+            self.host_s["plan"] += t1 - t0
+            for item in plan:
+                loss = self._launch_queued(*item)
+            self.host_s["launch"] += time.time() - t1
+            s0 = s1
+        if self._q_copied is None:
+            self._q_copied = torch.cuda.Event()
+        self._q_copied.record()
         return loss
+
+    CHUNK0, CHUNK = 8, 48
+
+    def _launch_queued(self, key, nt, ne, n_tok):
+        """One step of a queued epoch: graph replay, or (rare batch geometry) eager launches from the same queue."""
+        m, dev, L = self.model, self.model.device, self.model.hp.maxlen
+        gs = self._graph(*key) if (key[0] > 0 and (self.es is None or key[1] > 0)) else None
+        if self.world > 1:
+            m.global_counts = key
+        if gs is not None:
+            return gs.run_queued(n_tok)
+        self.n_eager += 1
+        ids = torch.empty((nt + ne, L), dtype=torch.int32, device=dev)
+        pos = torch.empty(nt, dtype=torch.int32, device=dev)
+        aux = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+        e_aux = None
+        if self.es is not None:
+            e_aux = self.e_lab if m.disable_distillation else self._teacher_rows()
+        ops.gather_batch_q(self.t_ids, self.t_lab, nt, self.e_ids if ne else None, e_aux if ne else None, ne, self.q, self.q_off,
+                           self.q_counter, ids, pos, aux[:ne] if ne else None)
+        ops.queue_advance(self.q_counter)
+        if self.es is None or ne == 0:
+            return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, n_tokens=n_tok)
+        if m.disable_distillation:
+            return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_pos=aux[:ne], n_tokens=n_tok)
+        return m.train_step(ids, pos, self.max_item, self.args.lr, self.args.dropout_rate, exemplar_logits=self.es.teacher,
+                            teacher_rows=aux[:ne], n_tokens=n_tok)
 
     def _teacher_rows(self):
         if getattr(self, "_trows", None) is None:
