@@ -176,12 +176,24 @@ __host__ __device__ inline uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
   return h;
 }
-// returns the multiplier (0 or 1/(1-p)) for element `idx` of dropout site `site`.
+// Dropout site: everything that does not depend on the element (hash key of (seed, site), integer drop threshold,
+// keep scale 1/(1-p)) is computed ONCE; drop_mul() is then one 32-bit mix, a compare and a select per element.
+// u = (r >> 8) * 2^-24 < p  <=>  (r >> 8) < ceil(p * 2^24)   (both sides exact in fp32).
+struct DropSite { uint32_t key, thr; float keep; };
+__host__ __device__ inline DropSite drop_site(uint64_t seed, uint32_t site, float p) {
+  DropSite s;
+  s.key = fmix32((uint32_t)seed * 0x9E3779B1u + (uint32_t)(seed >> 32) * 0x7FEB352Du + site * 0x846CA68Bu + 0x5bd1e995u);
+  s.thr = p > 0.f ? (uint32_t)ceilf(p * 16777216.0f) : 0u;
+  s.keep = 1.0f / (1.0f - p);
+  return s;
+}
+// multiplier (0 or 1/(1-p)) for element `idx` of the site
+__host__ __device__ inline float drop_mul(const DropSite& s, uint64_t idx) {
+  const uint32_t r = fmix32(((uint32_t)idx ^ s.key) + (uint32_t)(idx >> 32) * 0x27d4eb2fu);
+  return (r >> 8) < s.thr ? 0.0f : s.keep;
+}
 __host__ __device__ inline float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
-  const uint32_t key = fmix32((uint32_t)seed * 0x9E3779B1u + (uint32_t)(seed >> 32) * 0x7FEB352Du + site * 0x846CA68Bu + 0x5bd1e995u);
-  const uint32_t r = fmix32(((uint32_t)idx ^ key) + (uint32_t)(idx >> 32) * 0x27d4eb2fu);
-  const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.0f : 1.0f / (1.0f - p);
+  return drop_mul(drop_site(seed, site, p), idx);
 }
 
 }  // namespace ader

@@ -14,7 +14,15 @@ namespace ader {
 
 constexpr int NSLOT = 8;          // per-block [Tcap,d] activation slots
 constexpr int SPLITS = 21;        // split-K partials for weight / LN / bias gradients (21 x 7 problems = 147 CTAs: one wave of 148 SMs)
+constexpr int CHAIN_SPLITS = 14;  // chained encoder path: 14 splits x 10 weight matrices = 140 CTAs in ONE launch
 constexpr int PG_LANES = 6;       // token lanes per column in the LN / position gradient reductions (160 x 6 = 960 threads)
+
+// workspace flag words: [0..3] packing / overflow flags, then the neighbour flags of the chained encoder kernels
+// (encoder_chain.cuh): forward [block][CTA], backward [block][CTA], backward completion counter.  k_row_len (first
+// kernel of every forward) zeroes all of them.
+constexpr int CHF_STRIDE = 160;                    // >= CTAs of a chained kernel (one per SM)
+constexpr int CHF_FWD = 4, CHF_BWD = CHF_FWD + 2 * CHF_STRIDE, CHF_DONE = CHF_BWD + 2 * CHF_STRIDE;
+constexpr int N_WS_FLAGS = CHF_DONE + 4;
 
 struct EncWs {
   int *row_len, *row_off, *tok_row, *tok_id, *flags;
@@ -33,7 +41,7 @@ static EncWs carve_enc(const AderModel* m, int M, int Tcap, char* base) {
   w.row_off = (int*)take(sizeof(int) * (M + 1));
   w.tok_row = (int*)take(sizeof(int) * Tcap);
   w.tok_id  = (int*)take(sizeof(int) * Tcap);
-  w.flags   = (int*)take(sizeof(int) * 4);
+  w.flags   = (int*)take(sizeof(int) * N_WS_FLAGS);
   for (int b = 0; b < m->num_blocks; ++b) {
     for (int s = 0; s < NSLOT; ++s) w.slot[b][s] = (float*)take(sizeof(float) * Tcap * d);
     w.mean1[b] = (float*)take(sizeof(float) * Tcap); w.rstd1[b] = (float*)take(sizeof(float) * Tcap);
@@ -78,7 +86,7 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
 // packing
 // ------------------------------------------------------------------------------------------
 __global__ void k_row_len(const int* __restrict__ ids, int M, int L, int* __restrict__ row_len, int* __restrict__ flags) {
-  if (blockIdx.x == 0 && threadIdx.x < 4) flags[threadIdx.x] = 0;     // workspace flags (a memset node costs ~10 us in a graph)
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < N_WS_FLAGS; i += blockDim.x) flags[i] = 0;   // (a memset node costs ~10 us in a graph)
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= M) return;
   int c = 0;
@@ -843,6 +851,7 @@ static int key_bits(int v_tab) { int b = 1; while ((1LL << b) < v_tab) ++b; retu
 
 }  // namespace ader
 #include "encoder_fused.cuh"
+#include "encoder_chain.cuh"
 namespace ader {
 
 // ------------------------------------------------------------------------------------------
@@ -1444,8 +1453,29 @@ static void fused_attrs() {
   cudaFuncSetAttribute(fz::k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::WGRAD_SMEM);
   cudaFuncSetAttribute(fz::k_attn_ln_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * fz::att_rows_cap(64) * fz::KP * 4);
   cudaFuncSetAttribute(fz::k_attn_bwd_s1, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::att_bwd_smem(64, fz::KP));
+  cudaFuncSetAttribute(fz::k_attn_ln_fwd_team, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::att_tile_smem(64));
+  cudaFuncSetAttribute(fz::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::CHAIN_FWD_SMEM);
+  cudaFuncSetAttribute(fz::k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::CHAIN_BWD_SMEM);
   done = true;
 }
+// The chained kernels (encoder_chain.cuh) apply when the attention staging fits beside the weight slots, the model has at
+// most CH_MAXB blocks and one head (the reference's configuration); ADER_B200_CHAIN=0 keeps the per-sub-layer kernels.
+static bool chain_ok(const AderModel* m) {
+  // Opt-in (ADER_B200_CHAIN=1): measured slower than the per-sub-layer kernels at the reference's batch sizes (DESIGN.md
+  // section 3.6).  Read per call: tests compare the two paths in one process.
+  const char* e = getenv("ADER_B200_CHAIN");
+  if (!(e && e[0] == '1') || m->num_blocks > fz::CH_MAXB || m->num_heads != 1 || (m->d & 1)) return false;
+  const size_t stage = sizeof(float) * 2 * (size_t)fz::att_rows_cap(m->maxlen) * m->d;
+  return fz::att_tile_smem(m->maxlen) <= fz::CHAIN_FWD_STAGE && stage <= fz::CHAIN_BWD_STAGE && m->d <= fz::TEAM * fz::TE;
+}
+// attention with a team of 8 lanes per query (encoder_chain.cuh) instead of a warp per query: single head, d <= 152.
+// Opt-in (ADER_B200_TEAM_ATTN=1): as a kernel of its own it has 4x fewer warps in flight than the warp-per-query kernel and
+// measured slower (21 vs 17 us per launch at the bench shape); it is what the chained kernels use.
+static bool team_attention(const AderModel* m) {
+  const char* e = getenv("ADER_B200_TEAM_ATTN");
+  return (e && e[0] == '1') && m->num_heads == 1 && m->d <= fz::TEAM * fz::TE && !(m->d & 1);
+}
+static int chain_grid(int Tcap) { return max(1, min(min(sm_count(), CHF_STRIDE), cdiv(Tcap, 16))); }
 static const fz::op_t* shadow_of(const EncWs& w, int b, int which, int orient) {
   return (const fz::op_t*)w.wshadow + (size_t)((b * 5 + which) * 2 + orient) * (fz::KP * fz::LDS);
 }
@@ -1492,6 +1522,8 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
   const int warp_grid = cdiv(Tcap, fz::ATT_TOK);
   const size_t att_smem = sizeof(float) * 2 * (size_t)fz::att_rows_cap(L) * d;
+  const bool chain = chain_ok(m);
+  fz::ChainFwdArgs ca;
   for (int b = 0; b < m->num_blocks; ++b) {
     const float* P = theta + l.block(b);
     float* X = w.slot[b][0]; float* Q1 = w.slot[b][1]; float* Qp = w.slot[b][2]; float* Kp = w.slot[b][3];
@@ -1506,21 +1538,31 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     qa.Wq = shadow_of(w, b, 0, 0); qa.Wk = shadow_of(w, b, 1, 0); qa.Wv = shadow_of(w, b, 2, 0);
     qa.bq = P + l.bq; qa.bk = P + l.bk; qa.bv = P + l.bv;
     qa.Q = Qp; qa.K = Kp; qa.V = Vp; qa.dT = dT; qa.d = d; qa.L = L;
-    launch_chain(fz::k_qkv_fwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_FWD_SMEM, st, f.pdl && b > 0, qa);
 
     fz::AttnFwdArgs aa;
     aa.Q = Qp; aa.K = Kp; aa.V = Vp; aa.Q1 = Q1; aa.tok_row = w.tok_row; aa.row_off = w.row_off;
     aa.probs = w.probs[b]; aa.Y = Y; aa.Z = Z; aa.mean2 = w.mean2[b]; aa.rstd2 = w.rstd2[b];
     aa.ln_b = P + l.ln2b; aa.ln_g = P + l.ln2g; aa.dT = dT; aa.d = d; aa.nh = m->num_heads; aa.L = L; aa.Tcap = Tcap;
     aa.drop_p = dropout_rate; aa.seed = seed; aa.d_step = d_step; aa.site = 1u + 3u * b;
-    launch_chain(fz::k_attn_ln_fwd, dim3(warp_grid), dim3(256), att_smem, st, f.pdl, aa);
 
     fz::FfnFwdArgs fa;
     fa.Z = Z; fa.H = H; fa.Xn = Xn; fa.W1 = shadow_of(w, b, 3, 0); fa.W2 = shadow_of(w, b, 4, 0);
     fa.b1 = P + l.b1; fa.b2 = P + l.b2; fa.dT = dT; fa.d = d;
     fa.drop_p = dropout_rate; fa.seed = seed; fa.d_step = d_step; fa.site1 = 2u + 3u * b; fa.site2 = 3u + 3u * b;
+    if (chain) { ca.q[b] = qa; ca.at[b] = aa; ca.f[b] = fa; continue; }
+    launch_chain(fz::k_qkv_fwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_FWD_SMEM, st, f.pdl && b > 0, qa);
+    if (team_attention(m)) launch_chain(fz::k_attn_ln_fwd_team, dim3(cdiv(Tcap, fz::TM)), dim3(fz::NTHR), fz::att_tile_smem(L), st, f.pdl, aa);
+    else launch_chain(fz::k_attn_ln_fwd, dim3(warp_grid), dim3(256), att_smem, st, f.pdl, aa);
     launch_chain(fz::k_ffn_fwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_FWD_SMEM, st, f.pdl, fa);
     ADER_CHECK_LAUNCH("encoder_fwd_tc/block");
+  }
+  if (chain) {       // all blocks + the final LayerNorm in one persistent kernel: a CTA owns whole sessions
+    ca.nb = m->num_blocks; ca.M = M; ca.xfinal = w.xfinal; ca.rep = rep; ca.meanf = w.meanf; ca.rstdf = w.rstdf;
+    ca.lnf_b = theta + l.off_lnf; ca.lnf_g = theta + l.off_lnf + d;
+    ca.flags = w.flags + CHF_FWD; ca.flag_stride = CHF_STRIDE;
+    launch_chain(fz::k_chain_fwd, dim3(chain_grid(Tcap)), dim3(fz::NTHR), fz::CHAIN_FWD_SMEM, st, false, ca);
+    ADER_CHECK_LAUNCH("encoder_fwd_tc/chain");
+    return 0;
   }
   launch_chain(k_ln_last_fwd, dim3(cdiv((long long)M * 32, 256)), dim3(256), 0, st, f.pdl, (const float*)w.xfinal, (const int*)w.row_len,
                (const int*)w.row_off, M, rep, w.meanf, w.rstdf, theta + l.off_lnf, theta + l.off_lnf + d, d);
@@ -1573,16 +1615,24 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   const int tile_grid = min(cdiv(Tcap, fz::TM), sm_count());
   fused_attrs();
 
+  const bool chained = chain_ok(m);
+  // token splits of the weight / LayerNorm / position gradient partials: the chained path runs ALL weight gradients in
+  // one launch behind the data-gradient kernel (10 problems x 14 splits = 140 CTAs, one wave)
+  const int splits = chained ? CHAIN_SPLITS : SPLITS;
   // final LayerNorm: data gradient on the chain, parameter gradient beside it
   f.edge(st, f.c);
-  k_ln_param_grad<<<SPLITS, dim3(ln_threads, PG_LANES), 0, f.c>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+  k_ln_param_grad<<<splits, dim3(ln_threads, PG_LANES), 0, f.c>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
                                                  part(l.off_lnf), part(l.off_lnf + d), PS);
-  // directly behind the d_rep reduction on f.main in the fused step (f.pdl is only set there)
-  launch_chain(k_lnf_bwd, dim3(ln_grid), dim3(256), 0, st, f.pdl, d_rep, (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf,
-               theta + l.off_lnf + d, (const int*)w.tok_row, (const int*)w.row_off, chain[0], dT, d);
-  ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
+  fz::ChainBwdArgs ca;
+  if (!chained) {
+    // directly behind the d_rep reduction on f.main in the fused step (f.pdl is only set there)
+    launch_chain(k_lnf_bwd, dim3(ln_grid), dim3(256), 0, st, f.pdl, d_rep, (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf,
+                 theta + l.off_lnf + d, (const int*)w.tok_row, (const int*)w.row_off, chain[0], dT, d);
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln");
+  }
 
   cudaEvent_t wg_done[8][3];                // weight-gradient pieces of block b finished (f.wg[k]), parallel plans only
+  fz::WgradArgs wgs[fz::CH_MAXB][3];        // chained path: the weight-gradient launches follow the data-gradient kernel
   for (int b = m->num_blocks - 1; b >= 0; --b) {
     const long long bo = l.block(b);
     const float* P = theta + bo;
@@ -1593,79 +1643,101 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     float *gO = gs[0], *gH = gs[1], *gZ = gs[2], *gY = gs[3], *gQ = gs[4], *gK = gs[5], *gV = gs[6], *gQ1 = gs[7];
     float* gX = chain[ci % 3]; float* gXin = chain[(ci + 1) % 3]; ++ci;
     // this block rewrites the buffer set (and chain buffer) last read by the weight-gradient kernel of block b + 2
-    const bool joined = f.parallel() && b + 2 < m->num_blocks;
+    const bool joined = !chained && f.parallel() && b + 2 < m->num_blocks;
     if (joined) for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(st, wg_done[b + 2][k], 0);
     fz::FfnBwdArgs fa;
     fa.gX = gX; fa.gO = gO; fa.H = H; fa.Y = Y; fa.Q1 = Q1; fa.mean2 = w.mean2[b]; fa.rstd2 = w.rstd2[b];
     fa.ln_g = P + l.ln2g; fa.W2b = shadow_of(w, b, 4, 1); fa.W1b = shadow_of(w, b, 3, 1);
     fa.gH = gH; fa.gZ = gZ; fa.gY = gY; fa.D = g.Dv; fa.dT = dT; fa.d = d;
     fa.drop_p = p; fa.seed = seed; fa.d_step = d_step; fa.site2 = 3u + 3u * b;
-    launch_chain(fz::k_ffn_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_BWD_SMEM, st, f.pdl && !joined, fa);
-    // weight / bias / LayerNorm-parameter gradients (TF32 tensor cores, fp32 accumulate, split partials): launched in three
-    // pieces on f.a, each as soon as its gradients exist, so most of the work is done while the chain is still running
-    const float* gOut = (p > 0.f) ? gO : gX;
-    {
-      fz::WgradArgs wa;
-      wa.p[0] = {H, gOut, nullptr, nullptr, part(bo + l.w2), part(bo + l.b2)};
-      wa.p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
-      wa.p[2] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
-      wa.n_gemm = 2; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.wg[0]);
-      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa);
-    }
-
     fz::AttnBwdArgs ab;
     ab.Q = Qp; ab.K = Kp; ab.V = Vp; ab.probs = w.probs[b]; ab.gY = gY; ab.D = g.Dv;
     ab.tok_row = w.tok_row; ab.row_off = w.row_off; ab.gQ = gQ; ab.gK = gK; ab.gV = gV;
     ab.dT = dT; ab.d = d; ab.nh = m->num_heads; ab.L = L; ab.Tcap = Tcap; ab.drop_p = p; ab.seed = seed; ab.d_step = d_step; ab.site = 1u + 3u * b;
-    if (m->num_heads == 1) launch_chain(fz::k_attn_bwd_s1, dim3(cdiv(Tcap, fz::ATT_TOK)), dim3(256), (size_t)fz::att_bwd_smem(L, d), st, f.pdl, ab);
-    else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
-    {
-      fz::WgradArgs wa;
-      wa.p[0] = {Q1, gQ, nullptr, nullptr, part(bo + l.wq), part(bo + l.bq)};
-      wa.p[1] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
-      wa.p[2] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
-      wa.n_gemm = 3; wa.n_ln = 0; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.wg[1]);
-      fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[1]>>>(wa);
-    }
-
     fz::QkvBwdArgs qb;
     qb.gQ = gQ; qb.gK = gK; qb.gV = gV; qb.gY = gY; qb.X = X; qb.mean1 = w.mean1[b]; qb.rstd1 = w.rstd1[b];
     qb.ln_g = P + l.ln1g; qb.Wqb = shadow_of(w, b, 0, 1); qb.Wkb = shadow_of(w, b, 1, 1); qb.Wvb = shadow_of(w, b, 2, 1);
     qb.gQ1 = gQ1; qb.gXin = gXin; qb.dT = dT; qb.d = d;
     qb.drop_p = (b == 0) ? p : 0.f; qb.seed = seed; qb.d_step = d_step;       // block 0: x0 = drop(emb) (ADER.py:55)
+    // weight / bias / LayerNorm-parameter gradients (TF32 tensor cores, fp32 accumulate, split partials) in three pieces
+    const float* gOut = (p > 0.f) ? gO : gX;
+    fz::WgradArgs wa[3];
+    wa[0].p[0] = {H, gOut, nullptr, nullptr, part(bo + l.w2), part(bo + l.b2)};
+    wa[0].p[1] = {Z, gH, nullptr, nullptr, part(bo + l.w1), part(bo + l.b1)};
+    wa[0].p[2] = {Y, gZ, w.mean2[b], w.rstd2[b], part(bo + l.ln2b), part(bo + l.ln2g)};
+    wa[0].n_gemm = 2; wa[0].n_ln = 1;
+    wa[1].p[0] = {Q1, gQ, nullptr, nullptr, part(bo + l.wq), part(bo + l.bq)};
+    wa[1].p[1] = {X, gK, nullptr, nullptr, part(bo + l.wk), part(bo + l.bk)};
+    wa[1].p[2] = {X, gV, nullptr, nullptr, part(bo + l.wv), part(bo + l.bv)};
+    wa[1].n_gemm = 3; wa[1].n_ln = 0;
+    wa[2].p[0] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
+    wa[2].n_gemm = 0; wa[2].n_ln = 1;
+    for (int k = 0; k < 3; ++k) { wa[k].dT = dT; wa[k].d = d; wa[k].split_stride = PS; }
+    if (chained) {
+      ca.f[b] = fa; ca.at[b] = ab; ca.q[b] = qb;
+      for (int k = 0; k < 3; ++k) wgs[b][k] = wa[k];
+      continue;
+    }
+    // per-sub-layer kernels: each weight-gradient piece is launched on its own stream as soon as its gradients exist, so
+    // most of that work is done while the data-gradient chain is still running
+    launch_chain(fz::k_ffn_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_BWD_SMEM, st, f.pdl && !joined, fa);
+    f.edge(st, f.wg[0]);
+    fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa[0]);
+    if (m->num_heads == 1) launch_chain(fz::k_attn_bwd_s1, dim3(cdiv(Tcap, fz::ATT_TOK)), dim3(256), (size_t)fz::att_bwd_smem(L, d), st, f.pdl, ab);
+    else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
+    f.edge(st, f.wg[1]);
+    fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[1]>>>(wa[1]);
     launch_chain(fz::k_qkv_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_BWD_SMEM, st, f.pdl, qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
-
-    {
-      fz::WgradArgs wa;
-      wa.p[0] = {X, gQ1, w.mean1[b], w.rstd1[b], part(bo + l.ln1b), part(bo + l.ln1g)};
-      wa.n_gemm = 0; wa.n_ln = 1; wa.dT = dT; wa.d = d; wa.split_stride = PS;
-      f.edge(st, f.wg[2]);
-      fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.wg[2]>>>(wa);
-    }
+    f.edge(st, f.wg[2]);
+    fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.wg[2]>>>(wa[2]);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
     if (f.parallel())
       for (int k = 0; k < 3; ++k) { wg_done[b][k] = f.take(); cudaEventRecord(wg_done[b][k], f.wg[k]); }
+  }
+  if (chained) {     // every data gradient of every block in one persistent kernel (a CTA owns whole sessions), then the
+                     // weight-gradient pieces of all blocks side by side
+    ca.nb = m->num_blocks; ca.M = M; ca.row_off = w.row_off; ca.tok_row = w.tok_row;
+    ca.flags = w.flags + CHF_BWD; ca.flag_stride = CHF_STRIDE; ca.done_at = CHF_DONE - CHF_BWD;
+    ca.d_rep = d_rep; ca.xfinal = w.xfinal; ca.meanf = w.meanf; ca.rstdf = w.rstdf; ca.lnf_g = theta + l.off_lnf + d; ca.gx_top = chain[0];
+    launch_chain(fz::k_chain_bwd, dim3(chain_grid(Tcap)), dim3(fz::NTHR), fz::CHAIN_BWD_SMEM, st, f.pdl, ca);
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/chain");
+    fz::WgradArgs wa;                         // the 5 weight matrices (+ biases) of every block: one launch
+    int np = 0;
+    for (int b = m->num_blocks - 1; b >= 0; --b) {
+      wa.p[np++] = wgs[b][0].p[0]; wa.p[np++] = wgs[b][0].p[1];
+      wa.p[np++] = wgs[b][1].p[0]; wa.p[np++] = wgs[b][1].p[1]; wa.p[np++] = wgs[b][1].p[2];
+    }
+    wa.n_gemm = np; wa.n_ln = 0; wa.dT = dT; wa.d = d; wa.split_stride = PS;
+    f.edge(st, f.wg[0]);
+    fz::k_wgrad<<<dim3(splits, np), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa);
+    for (int k = 1; k < 3; ++k) {             // LayerNorm-parameter gradients of the blocks beside it
+      f.edge(st, f.wg[k]);
+      for (int b = m->num_blocks - 1; b >= 0; --b) {
+        const fz::WgradProb& lp = (k == 1) ? wgs[b][0].p[2] : wgs[b][2].p[0];
+        k_ln_param_grad<<<splits, dim3(ln_threads, PG_LANES), 0, f.wg[k]>>>(lp.grad, lp.act, lp.mean, lp.rstd, dT, 0, nullptr, nullptr, d,
+                                                                        lp.out0, lp.out1, PS);
+      }
+    }
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
   }
   const float* gX0 = chain[ci % 3];          // gradient w.r.t. the (dropout-masked) embedding output
 
   // position table (ADER.py:41-52) beside the scatter; then all split partials -> dense gradients in fixed order
   f.edge(st, f.c);
-  k_pos_grad<<<dim3(L, SPLITS), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
+  k_pos_grad<<<dim3(L, splits), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
   f.edge(f.c, f.a);
   f.edge(f.wg[1], f.a);
   f.edge(f.wg[2], f.a);
   if (f.adam) {                              // fused step: reduce the partials and update the dense parameters in one launch
     const AdamPlan& ap = *f.adam;
     cudaStreamWaitEvent(f.a, ap.prep_ready, 0);
-    k_reduce_partials_adam<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, PS, grad + l.off_pos, ap.theta + l.off_pos,
+    k_reduce_partials_adam<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, splits, PS, grad + l.off_pos, ap.theta + l.off_pos,
                                                            ap.m + l.off_pos, ap.v + l.off_pos, ap.state, ap.a.beta1, ap.a.beta2, ap.a.eps,
                                                            ap.a.ewc_lambda, ap.a.fisher ? ap.a.fisher + l.off_pos : nullptr,
                                                            ap.a.theta_star ? ap.a.theta_star + l.off_pos : nullptr);
   } else {
-    k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, SPLITS, 0, PS, grad + l.off_pos);
+    k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, splits, 0, PS, grad + l.off_pos);
   }
   // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
   if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);

@@ -55,8 +55,10 @@ __device__ __forceinline__ void fz_tl(int k, int slot) {
   if (threadIdx.x == 0 && blockIdx.x < 160) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fz_tl[k][blockIdx.x][slot] = t; }
 }
 #define FZ_TL(k, slot) fz_tl(k, slot)
+#define FZ_TLV(k, slot, v) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_fz_tl[k][blockIdx.x][slot] = (v); } while (0)
 #else
 #define FZ_TL(k, slot) do { } while (0)
+#define FZ_TLV(k, slot, v) do { } while (0)
 #endif
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -119,11 +121,14 @@ __device__ __forceinline__ void st_op2(op_t* p, float a, float b) {
   *reinterpret_cast<__half2*>(p) = __floats2half2_rn(clamp_h(a), clamp_h(b));
 }
 __device__ __forceinline__ op_t to_op(float v) { return __float2half_rn(clamp_h(v)); }
-// power-of-two scale s with max * s in [2^10, 2^11): 16x headroom for the chained product, exact to undo
-__device__ __forceinline__ float row_scale(float mx) {
-  if (!(mx > 0.f)) return 1.f;
-  int e; frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
-  return ldexpf(1.f, min(max(11 - e, -100), 100));
+// power-of-two scale s with max * s in [2^10, 2^11): 16x headroom for the chained product, exact to undo (inv = 1/s).
+// Exponent arithmetic on the bit pattern: mx = m * 2^e with m in [0.5, 1)  ->  s = 2^(11 - e), clamped to 2^+-100.
+__device__ __forceinline__ float row_scale(float mx, float& inv) {
+  if (!(mx > 0.f)) { inv = 1.f; return 1.f; }
+  const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;      // subnormal (field 0) -> clamps to 2^100 like any tiny value
+  const int k = min(max(11 - e, -100), 100);
+  inv = __uint_as_float((uint32_t)(127 - k) << 23);
+  return __uint_as_float((uint32_t)(127 + k) << 23);
 }
 // ---- batched row access: every warp owns RPW = 4 consecutive tile rows.  All global loads of a phase are issued
 // before the first use (one L2 round trip per phase instead of one per row), reductions of the 4 rows interleave.
@@ -141,7 +146,7 @@ __device__ __forceinline__ void warp_max_n(float (&v)[RPW]) {
     for (int r = 0; r < RPW; ++r) v[r] = fmaxf(v[r], __shfl_xor_sync(0xffffffffu, v[r], o));
 }
 // x[rr][e] = G[t0 + warp*RPW + rr][lane + 32 e]   (0 outside [0,T) x [0,d))
-__device__ __forceinline__ void load_rows(float (&x)[RPW][NE], const float* __restrict__ G, int t0, int T, int d, int warp, int lane) {
+__device__ __forceinline__ void load_rows(float (&x)[RPW][NE], const float* G, int t0, int T, int d, int warp, int lane) {
 #pragma unroll
   for (int rr = 0; rr < RPW; ++rr) {
     const int tk = t0 + warp * RPW + rr;
@@ -150,7 +155,7 @@ __device__ __forceinline__ void load_rows(float (&x)[RPW][NE], const float* __re
   }
 }
 // per-lane scalars of the warp's rows (mean / rstd / D ...)
-__device__ __forceinline__ void load_row_scalars(float (&v)[RPW], const float* __restrict__ G, int t0, int T, int warp) {
+__device__ __forceinline__ void load_row_scalars(float (&v)[RPW], const float* G, int t0, int T, int warp) {
 #pragma unroll
   for (int rr = 0; rr < RPW; ++rr) { const int tk = t0 + warp * RPW + rr; v[rr] = (tk < T) ? G[tk] : 0.f; }
 }
@@ -169,14 +174,15 @@ __device__ __forceinline__ void put_rows_scaled(op_t* __restrict__ As, float* __
 #pragma unroll
   for (int rr = 0; rr < RPW; ++rr) {
     const int r = warp * RPW + rr;
-    const float sc = row_scale(mx[rr]);
+    float inv;
+    const float sc = row_scale(mx[rr], inv);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int c = lane + 32 * e;
       As[r * LDS + c] = to_op(x[rr][e] * sc);
       if (x2) As2[r * LDS + c] = to_op(x2[rr][e] * sc);
     }
-    if (lane == 0) inv_scale[r] = 1.f / sc;
+    if (lane == 0) inv_scale[r] = inv;
   }
 }
 __device__ __forceinline__ void put_rows(op_t* __restrict__ As, const float (&x)[RPW][NE], int warp, int lane) {
@@ -187,7 +193,7 @@ __device__ __forceinline__ void put_rows(op_t* __restrict__ As, const float (&x)
 }
 // elements of a [T,d] matrix co-located with this thread's accumulator fragment (row = mt*16 + g + 8h, col pair);
 // issued ahead of the GEMM whose epilogue consumes them
-__device__ __forceinline__ void load_frag(float2 (&v)[NT][2], const float* __restrict__ G, int t0, int T, int d, int mt, int ng, int lane) {
+__device__ __forceinline__ void load_frag(float2 (&v)[NT][2], const float* G, int t0, int T, int d, int mt, int ng, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
@@ -268,6 +274,122 @@ struct QkvFwdArgs {
 };
 constexpr size_t QKV_FWD_SMEM = 3 * WMAT_BYTES + 2 * ATILE_BYTES + TM * 4 + 16;
 
+// One 32-token tile [t0, t0 + TM) of the rows below T: [embedding] + LN1 -> operand tiles, Q / K / V products.  wait_q() /
+// wait_kv() block until the Wq / (Wk, Wv) shadows have landed in shared memory (no-ops once they have).
+template <class WaitQ, class WaitKV>
+__device__ __forceinline__ void qkv_fwd_tile(const QkvFwdArgs& a, int t0, int T, uint64_t seed_eff, op_t* __restrict__ A1, op_t* __restrict__ A2,
+                                             float* __restrict__ rs, const op_t* Wq_s, const op_t* Wk_s, const op_t* Wv_s,
+                                             const float (&lg)[NE], const float (&lb)[NE], const float2 (&bq)[NT], const float2 (&bk)[NT],
+                                             const float2 (&bv)[NT], WaitQ wait_q, WaitKV wait_kv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mt = warp & 1, ng = warp >> 1;
+  const int d = a.d;
+  const DropSite ds0 = drop_site(seed_eff, 0u, a.drop_p);
+  FZ_TL(0, 6);
+  // ---- prologue: [embedding] + LayerNorm of the warp's 4 rows -> fp32 q1 (HBM) and the two operand tiles
+  float x[RPW][NE];
+  if (a.embed) {         // x = (E0[id]*sqrt(d) + P[pos]) * dropout   (modules.py:124-130, ADER.py:41-60)
+    int rowi[RPW], idv[RPW], pp[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+      rowi[rr] = (tk < T) ? a.tok_row[tk] : 0; idv[rr] = (tk < T) ? a.tok_id[tk] : 0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+      pp[rr] = (tk < T) ? a.L - a.row_len[rowi[rr]] + (tk - a.row_off[rowi[rr]]) : 0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        x[rr][e] = (tk < T && c < d) ? a.table[(long long)idv[rr] * d + c] * a.sqrt_d + a.pos_table[pp[rr] * d + c] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        if (tk < T && c < d) {
+          if (a.drop_p > 0.f) x[rr][e] *= drop_mul(ds0, (uint64_t)tk * d + c);
+          a.Xw[(long long)tk * d + c] = x[rr][e];
+        }
+      }
+    }
+  } else {
+    load_rows(x, a.X, t0, T, d, warp, lane);
+  }
+  float sm[RPW], mx[RPW], qv[RPW];
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    float s = 0.f, m = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { s += x[rr][e]; m = fmaxf(m, fabsf(x[rr][e])); }
+    sm[rr] = s; mx[rr] = m;
+  }
+  warp_sum_n(sm); warp_max_n(mx);
+  FZ_TL(0, 7);
+  const float inv_d = 1.0f / (float)d;
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    sm[rr] *= inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = x[rr][e] - sm[rr]; q += u * u; } }
+    qv[rr] = q;
+  }
+  warp_sum_n(qv);
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = warp * RPW + rr, tk = t0 + r;
+    const float mean = sm[rr], rstd = rsqrtf(qv[rr] * inv_d + 1e-8f);
+    float sci;
+    const float sc = row_scale(mx[rr], sci);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      float y = 0.f;
+      if (tk < T && c < d) { y = lg[e] * ((x[rr][e] - mean) * rstd) + lb[e]; a.Q1[(long long)tk * d + c] = y; }
+      A1[r * LDS + c] = to_op(y);
+      A2[r * LDS + c] = to_op(x[rr][e] * sc);
+    }
+    if (lane == 0) { rs[r] = sci; if (tk < T) { a.mean[tk] = mean; a.rstd[tk] = rstd; } }
+  }
+  __syncthreads();
+  FZ_TL(0, 2);
+  wait_q();
+  FZ_TL(0, 3);
+  float acc[NT][4];
+  zero_acc(acc);
+  warp_gemm(A1 + mt * 16 * LDS, Wq_s + ng * (NT * 8) * LDS, acc, lane);
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (t0 + r < T && c < d)
+      *reinterpret_cast<float2*>(a.Q + (long long)(t0 + r) * d + c) = make_float2(v0 + bq[j].x, v1 + bq[j].y);
+  });
+  FZ_TL(0, 4);
+  wait_kv();
+  zero_acc(acc);
+  warp_gemm(A2 + mt * 16 * LDS, Wk_s + ng * (NT * 8) * LDS, acc, lane);
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (t0 + r < T && c < d)
+      *reinterpret_cast<float2*>(a.K + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bk[j].x, v1 * rs[r] + bk[j].y);
+  });
+  FZ_TL(0, 8);
+  zero_acc(acc);
+  warp_gemm(A2 + mt * 16 * LDS, Wv_s + ng * (NT * 8) * LDS, acc, lane);
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (t0 + r < T && c < d)
+      *reinterpret_cast<float2*>(a.V + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bv[j].x, v1 * rs[r] + bv[j].y);
+  });
+  __syncthreads();
+  FZ_TL(0, 5);
+}
+
 __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ QkvFwdArgs a) {
   FZ_TL(0, 0);
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
@@ -288,7 +410,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
     load_wmat(smem_u32(Wsm) + WMAT_BYTES, a.Wk, bar);
     load_wmat(smem_u32(Wsm) + 2 * WMAT_BYTES, a.Wv, bar);
   }
-  const int mt = warp & 1, ng = warp >> 1;
+  const int ng = warp >> 1;
   float lg[NE], lb[NE];
 #pragma unroll
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; lg[e] = (c < d) ? a.ln_g[c] : 0.f; lb[e] = (c < d) ? a.ln_b[c] : 0.f; }
@@ -298,106 +420,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_fwd(const __grid_constant__ Qkv
   __syncthreads();
   FZ_TL(0, 1);
   bool first = true;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t0 = tile * TM;
-    // ---- prologue: [embedding] + LayerNorm of the warp's 4 rows -> fp32 q1 (HBM) and the two operand tiles
-    float x[RPW][NE];
-    if (a.embed) {         // x = (E0[id]*sqrt(d) + P[pos]) * dropout   (modules.py:124-130, ADER.py:41-60)
-      int rowi[RPW], idv[RPW], pp[RPW];
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int tk = t0 + warp * RPW + rr;
-        rowi[rr] = (tk < T) ? a.tok_row[tk] : 0; idv[rr] = (tk < T) ? a.tok_id[tk] : 0;
-      }
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int tk = t0 + warp * RPW + rr;
-        pp[rr] = (tk < T) ? a.L - a.row_len[rowi[rr]] + (tk - a.row_off[rowi[rr]]) : 0;
-      }
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int tk = t0 + warp * RPW + rr;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const int c = lane + 32 * e;
-          x[rr][e] = (tk < T && c < d) ? a.table[(long long)idv[rr] * d + c] * a.sqrt_d + a.pos_table[pp[rr] * d + c] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int tk = t0 + warp * RPW + rr;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const int c = lane + 32 * e;
-          if (tk < T && c < d) {
-            if (a.drop_p > 0.f) x[rr][e] *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
-            a.Xw[(long long)tk * d + c] = x[rr][e];
-          }
-        }
-      }
-    } else {
-      load_rows(x, a.X, t0, T, d, warp, lane);
-    }
-    float sm[RPW], mx[RPW], qv[RPW];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      float s = 0.f, m = 0.f;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) { s += x[rr][e]; m = fmaxf(m, fabsf(x[rr][e])); }
-      sm[rr] = s; mx[rr] = m;
-    }
-    warp_sum_n(sm); warp_max_n(mx);
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      sm[rr] /= (float)d;
-      float q = 0.f;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = x[rr][e] - sm[rr]; q += u * u; } }
-      qv[rr] = q;
-    }
-    warp_sum_n(qv);
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int r = warp * RPW + rr, tk = t0 + r;
-      const float mean = sm[rr], rstd = 1.0f / sqrtf(qv[rr] / (float)d + 1e-8f);
-      const float sc = row_scale(mx[rr]);
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int c = lane + 32 * e;
-        float y = 0.f;
-        if (tk < T && c < d) { y = lg[e] * ((x[rr][e] - mean) * rstd) + lb[e]; a.Q1[(long long)tk * d + c] = y; }
-        A1[r * LDS + c] = to_op(y);
-        A2[r * LDS + c] = to_op(x[rr][e] * sc);
-      }
-      if (lane == 0) { rs[r] = 1.f / sc; if (tk < T) { a.mean[tk] = mean; a.rstd[tk] = rstd; } }
-    }
-    __syncthreads();
-    FZ_TL(0, 2);
-    if (first) { mbar_wait(bar, 0); first = false; }
-    FZ_TL(0, 3);
-    float acc[NT][4];
-    zero_acc(acc);
-    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.Q + (long long)(t0 + r) * d + c) = make_float2(v0 + bq[j].x, v1 + bq[j].y);
-    });
-    FZ_TL(0, 4);
-    zero_acc(acc);
-    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.K + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bk[j].x, v1 * rs[r] + bk[j].y);
-    });
-    zero_acc(acc);
-    warp_gemm(A2 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (t0 + r < T && c < d)
-        *reinterpret_cast<float2*>(a.V + (long long)(t0 + r) * d + c) = make_float2(v0 * rs[r] + bv[j].x, v1 * rs[r] + bv[j].y);
-    });
-    __syncthreads();
-    FZ_TL(0, 5);
-  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    qkv_fwd_tile(a, tile * TM, T, seed_eff, A1, A2, rs, Wsm, Wsm + KP * LDS, Wsm + 2 * KP * LDS, lg, lb, bq, bk, bv,
+                 [&] { if (first) { mbar_wait(bar, 0); first = false; } }, [] {});
 }
 
 // ---- warp-per-token attention building blocks -------------------------------------------------------------
@@ -471,7 +496,7 @@ struct AttnFwdArgs {
 };
 
 // cooperative copy of n2 float2 (rows are contiguous [n, d] in global memory, 8-byte aligned), 8 loads in flight per thread
-__device__ __forceinline__ void stage_f2(float* __restrict__ dst, const float* __restrict__ src, int n2) {
+__device__ __forceinline__ void stage_f2(float* __restrict__ dst, const float* src, int n2) {
   const float2* s2 = reinterpret_cast<const float2*>(src);
   float2* d2 = reinterpret_cast<float2*>(dst);
   for (int base = threadIdx.x; base < n2; base += 8 * blockDim.x) {
@@ -489,13 +514,9 @@ __host__ __device__ constexpr int att_rows_cap(int L) { return L + ATT_TOK - 1; 
 // its own session, so the union of all keys the CTA needs is ONE contiguous token range [row start of the first
 // token, last token of the CTA]: <= L + 7 rows.  K and V of that range are staged in shared memory by a cooperative,
 // fully overlapped copy (one L2 round trip for the CTA), and the warps then work out of shared memory.
-__global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
-  extern __shared__ __align__(16) float att_sm[];
-  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
-  const int T = *a.dT;
-  const int t0 = blockIdx.x * ATT_TOK;
-  if (t0 >= T) return;
-  pdl_wait(); pdl_go();
+// One group of ATT_TOK consecutive query tokens [t0, t0 + ATT_TOK) of the rows below T (all threads of the CTA call it:
+// cooperative staging + one __syncthreads inside).
+__device__ __forceinline__ void attn_fwd_group(const AttnFwdArgs& a, int t0, int T, float* __restrict__ att_sm, uint64_t seed_eff) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, L = a.L;
   const int tk = min(t0 + warp, T - 1);          // surplus warps of the last CTA shadow its last token (no stores)
@@ -514,78 +535,98 @@ __global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ 
   }
   float* Ks = att_sm;
   float* Vs = att_sm + att_rows_cap(L) * d;
+  const DropSite dsp = drop_site(seed_eff, a.site, a.drop_p);
+  FZ_TL(4, 0);
   stage_f2(Ks, a.K + (long long)lo * d, (hi - lo) * d / 2);
   stage_f2(Vs, a.V + (long long)lo * d, (hi - lo) * d / 2);
   __syncthreads();
-  if (!live) return;
-  const int i = tk - off;                       // query index inside its session; keys 0..i
-  const int dh = d / a.nh;
-  const float inv_denom = 1.0f / sqrtf((float)dh);
-  const int j8 = lane & 7;
-  const float* Krow = Ks + (off - lo) * d;
-  const float* Vrow = Vs + (off - lo) * d;
-  for (int h = 0; h < a.nh; ++h) {
-    const int c_lo = h * dh, c_hi = c_lo + dh;
-    const long long po = ((long long)h * a.Tcap + tk) * L;
-    // online softmax over key blocks of 8 (running max m, running sum l); raw scores are parked in the probs
-    // row and normalised in place afterwards
-    float m = -INFINITY, l = 0.f;
-    float oh[NE];
-#pragma unroll
-    for (int e = 0; e < NE; ++e) oh[e] = 0.f;
-    for (int j0 = 0; j0 <= i; j0 += KB) {
-      const int cnt = min(KB, i + 1 - j0);
-      const float sc = block_dots(q, Krow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane) * inv_denom;
-      const bool valid = j8 < cnt;
-      float bm = valid ? sc : -INFINITY;
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-      const float m_new = fmaxf(m, bm);
-      const float corr = expf(m - m_new);
-      float pj = valid ? expf(sc - m_new) : 0.f;
-      float ps = pj;
-      ps += __shfl_xor_sync(0xffffffffu, ps, 4);
-      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-      l = l * corr + ps;
-      m = m_new;
-      if (lane < KB && valid) a.probs[po + j0 + j8] = sc;
-      if (a.drop_p > 0.f && valid) pj *= drop_scale(seed_eff, a.site, (uint64_t)(po + j0 + j8), a.drop_p);
-#pragma unroll
-      for (int e = 0; e < NE; ++e) oh[e] *= corr;
-      block_axpy(oh, pj, Vrow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane);
+  FZ_TL(4, 1);
+  if (live) {
+    const int i = tk - off;                       // query index inside its session; keys 0..i
+    const int dh = d / a.nh;
+    const float inv_denom = 1.0f / sqrtf((float)dh);
+    const int j8 = lane & 7;
+    const float* Krow = Ks + (off - lo) * d;
+    const float* Vrow = Vs + (off - lo) * d;
+    for (int h = 0; h < a.nh; ++h) {
+      const int c_lo = h * dh, c_hi = c_lo + dh;
+      const long long po = ((long long)h * a.Tcap + tk) * L;
+      // online softmax over key blocks of 8 (running max m, running sum l); raw scores are parked in the probs
+      // row and normalised in place afterwards
+      float m = -INFINITY, l = 0.f;
+      float oh[NE];
+  #pragma unroll
+      for (int e = 0; e < NE; ++e) oh[e] = 0.f;
+      for (int j0 = 0; j0 <= i; j0 += KB) {
+        const int cnt = min(KB, i + 1 - j0);
+        const float sc = block_dots(q, Krow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane) * inv_denom;
+        const bool valid = j8 < cnt;
+        float bm = valid ? sc : -INFINITY;
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+        const float m_new = fmaxf(m, bm);
+        const float corr = expf(m - m_new);
+        float pj = valid ? expf(sc - m_new) : 0.f;
+        float ps = pj;
+        ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+        l = l * corr + ps;
+        m = m_new;
+        if (lane < KB && valid) a.probs[po + j0 + j8] = sc;
+        if (a.drop_p > 0.f && valid) pj *= drop_mul(dsp, (uint64_t)(po + j0 + j8));
+  #pragma unroll
+        for (int e = 0; e < NE; ++e) oh[e] *= corr;
+        block_axpy(oh, pj, Vrow + (long long)j0 * d, d, cnt, c_lo, c_hi, lane);
+      }
+      const float inv_l = 1.0f / l;
+  #pragma unroll
+      for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) o[e] = oh[e] * inv_l; }
+      __syncwarp();
+  #pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        if (j < L) a.probs[po + j] = (j <= i) ? expf(a.probs[po + j] - m) * inv_l : 0.f;
+      }
     }
-    const float inv_l = 1.0f / l;
-#pragma unroll
-    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c >= c_lo && c < c_hi) o[e] = oh[e] * inv_l; }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = lane + 32 * u;
-      if (j < L) a.probs[po + j] = (j <= i) ? expf(a.probs[po + j] - m) * inv_l : 0.f;
+    FZ_TL(4, 2);
+    // y = attn + q1 (residual on the NORMALISED queries, modules.py:223), z = LN2(y)
+    float y[NE]; float sm = 0.f;
+    float lg[NE], lb[NE];              // loaded BEFORE the stores below: a load behind a store through an unrelated pointer is not hoisted
+  #pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; lg[e] = (c < d) ? a.ln_g[c] : 0.f; lb[e] = (c < d) ? a.ln_b[c] : 0.f; }
+  #pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      y[e] = (c < d) ? o[e] + q1[e] : 0.f;
+      if (c < d) a.Y[(long long)tk * d + c] = y[e];
+      sm += y[e];
     }
+    const float inv_d = 1.0f / (float)d;
+    const float mean = warp_sum(sm) * inv_d;
+    float qq = 0.f;
+  #pragma unroll
+    for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = y[e] - mean; qq += u * u; } }
+    const float rstd = rsqrtf(warp_sum(qq) * inv_d + 1e-8f);
+  #pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      if (c < d) a.Z[(long long)tk * d + c] = lg[e] * ((y[e] - mean) * rstd) + lb[e];
+    }
+    if (lane == 0) { a.mean2[tk] = mean; a.rstd2[tk] = rstd; }
   }
-  // y = attn + q1 (residual on the NORMALISED queries, modules.py:223), z = LN2(y)
-  float y[NE]; float sm = 0.f;
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    y[e] = (c < d) ? o[e] + q1[e] : 0.f;
-    if (c < d) a.Y[(long long)tk * d + c] = y[e];
-    sm += y[e];
-  }
-  const float mean = warp_sum(sm) / (float)d;
-  float qq = 0.f;
-#pragma unroll
-  for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; if (c < d) { const float u = y[e] - mean; qq += u * u; } }
-  const float rstd = 1.0f / sqrtf(warp_sum(qq) / (float)d + 1e-8f);
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    if (c < d) a.Z[(long long)tk * d + c] = a.ln_g[c] * ((y[e] - mean) * rstd) + a.ln_b[c];
-  }
-  if (lane == 0) { a.mean2[tk] = mean; a.rstd2[tk] = rstd; }
+  FZ_TL(4, 3);
+}
+
+__global__ void __launch_bounds__(256, 3) k_attn_ln_fwd(const __grid_constant__ AttnFwdArgs a) {
+  extern __shared__ __align__(16) float att_sm[];
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
+  const int T = *a.dT;
+  const int t0 = blockIdx.x * ATT_TOK;
+  if (t0 >= T) return;
+  pdl_wait(); pdl_go();
+  attn_fwd_group(a, t0, T, att_sm, seed_eff);
 }
 
 // ---- forward: FFN1 + ReLU + FFN2 + residual (modules.py:252-271) -----------------------------------
@@ -596,6 +637,56 @@ struct FfnFwdArgs {
   float drop_p; uint64_t seed; const int* d_step; uint32_t site1, site2;
 };
 constexpr size_t FFN_FWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + 16;
+
+// One 32-token tile: FFN1 + ReLU (+ dropout) -> H, FFN2 (+ dropout) + residual -> Xn.  A2's padding columns must be zero.
+template <class WaitW>
+__device__ __forceinline__ void ffn_fwd_tile(const FfnFwdArgs& a, int t0, int T, uint64_t seed_eff, op_t* __restrict__ A1, op_t* __restrict__ A2,
+                                             const op_t* W1_s, const op_t* W2_s, const float2 (&b1)[NT], const float2 (&b2)[NT], WaitW wait_w) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mt = warp & 1, ng = warp >> 1;
+  const int d = a.d;
+  const DropSite ds1 = drop_site(seed_eff, a.site1, a.drop_p), ds2 = drop_site(seed_eff, a.site2, a.drop_p);
+  FZ_TL(5, 0);
+  float z[RPW][NE];
+  load_rows(z, a.Z, t0, T, d, warp, lane);
+  float2 zf[NT][2];
+  load_frag(zf, a.Z, t0, T, d, mt, ng, lane);          // residual operand of the second epilogue
+  put_rows(A1, z, warp, lane);
+  __syncthreads();
+  FZ_TL(5, 1);
+  wait_w();
+  FZ_TL(5, 2);
+  float acc[NT][4];
+  zero_acc(acc);
+  warp_gemm(A1 + mt * 16 * LDS, W1_s + ng * (NT * 8) * LDS, acc, lane);
+  FZ_TL(5, 5);
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (c < d) {
+      float h0 = 0.f, h1 = 0.f;
+      if (t0 + r < T) {
+        const long long e = (long long)(t0 + r) * d + c;
+        h0 = fmaxf(v0 + b1[j].x, 0.f); h1 = fmaxf(v1 + b1[j].y, 0.f);
+        if (a.drop_p > 0.f) { h0 *= drop_mul(ds1, (uint64_t)e); h1 *= drop_mul(ds1, (uint64_t)e + 1); }
+        *reinterpret_cast<float2*>(a.H + e) = make_float2(h0, h1);
+      }
+      st_op2(A2 + r * LDS + c, h0, h1);
+    }
+  });
+  __syncthreads();
+  FZ_TL(5, 3);
+  zero_acc(acc);
+  warp_gemm(A2 + mt * 16 * LDS, W2_s + ng * (NT * 8) * LDS, acc, lane);
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (t0 + r < T && c < d) {
+      const long long e = (long long)(t0 + r) * d + c;
+      float x0 = v0 + b2[j].x, x1 = v1 + b2[j].y;
+      if (a.drop_p > 0.f) { x0 *= drop_mul(ds2, (uint64_t)e); x1 *= drop_mul(ds2, (uint64_t)e + 1); }
+      *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + zf[j][h].x, x1 + zf[j][h].y);
+    }
+  });
+  __syncthreads();
+  FZ_TL(5, 4);
+}
 
 __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ FfnFwdArgs a) {
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
@@ -616,49 +707,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_fwd(const __grid_constant__ Ffn
   }
   // zero the padding columns of the hidden tile once (the epilogue only writes columns < d)
   for (int idx = tid; idx < TM * LDS; idx += NTHR) A2[idx] = to_op(0.f);
-  const int mt = warp & 1, ng = warp >> 1;
+  const int ng = warp >> 1;
   float2 b1[NT], b2[NT];
   load_bias_frag(b1, a.b1, d, ng, lane); load_bias_frag(b2, a.b2, d, ng, lane);
   pdl_wait(); pdl_go();
   __syncthreads();
   bool first = true;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t0 = tile * TM;
-    float z[RPW][NE];
-    load_rows(z, a.Z, t0, T, d, warp, lane);
-    float2 zf[NT][2];
-    load_frag(zf, a.Z, t0, T, d, mt, ng, lane);          // residual operand of the second epilogue
-    put_rows(A1, z, warp, lane);
-    __syncthreads();
-    if (first) { mbar_wait(bar, 0); first = false; }
-    float acc[NT][4];
-    zero_acc(acc);
-    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (c < d) {
-        float h0 = 0.f, h1 = 0.f;
-        if (t0 + r < T) {
-          const long long e = (long long)(t0 + r) * d + c;
-          h0 = fmaxf(v0 + b1[j].x, 0.f); h1 = fmaxf(v1 + b1[j].y, 0.f);
-          if (a.drop_p > 0.f) { h0 *= drop_scale(seed_eff, a.site1, (uint64_t)e, a.drop_p); h1 *= drop_scale(seed_eff, a.site1, (uint64_t)e + 1, a.drop_p); }
-          *reinterpret_cast<float2*>(a.H + e) = make_float2(h0, h1);
-        }
-        st_op2(A2 + r * LDS + c, h0, h1);
-      }
-    });
-    __syncthreads();
-    zero_acc(acc);
-    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (t0 + r < T && c < d) {
-        const long long e = (long long)(t0 + r) * d + c;
-        float x0 = v0 + b2[j].x, x1 = v1 + b2[j].y;
-        if (a.drop_p > 0.f) { x0 *= drop_scale(seed_eff, a.site2, (uint64_t)e, a.drop_p); x1 *= drop_scale(seed_eff, a.site2, (uint64_t)e + 1, a.drop_p); }
-        *reinterpret_cast<float2*>(a.Xn + e) = make_float2(x0 + zf[j][h].x, x1 + zf[j][h].y);
-      }
-    });
-    __syncthreads();
-  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    ffn_fwd_tile(a, tile * TM, T, seed_eff, A1, A2, Wsm, Wsm + KP * LDS, b1, b2, [&] { if (first) { mbar_wait(bar, 0); first = false; } });
 }
 
 // ---- LayerNorm backward of the warp's 4 rows (dout in a shared fp32 tile, x / mean / rstd preloaded) ----------
@@ -681,9 +737,10 @@ __device__ __forceinline__ void ln_bwd_rows(const float* __restrict__ Ft, const 
     s1[rr] = a1; s2[rr] = a2;
   }
   warp_sum_n(s1); warp_sum_n(s2);
+  const float inv_d = 1.0f / (float)d;
 #pragma unroll
   for (int rr = 0; rr < RPW; ++rr) {
-    const float m1 = s1[rr] / (float)d, m2 = s2[rr] / (float)d;
+    const float m1 = s1[rr] * inv_d, m2 = s2[rr] * inv_d;
 #pragma unroll
     for (int e = 0; e < NE; ++e) dx[rr][e] = rstd[rr] * (dx[rr][e] - m1 - xh[rr][e] * m2);
   }
@@ -700,6 +757,102 @@ struct FfnBwdArgs {
   float drop_p; uint64_t seed; const int* d_step; uint32_t site2;
 };
 constexpr size_t FFN_BWD_SMEM = 2 * WMAT_BYTES + 2 * ATILE_BYTES + FTILE_BYTES + TM * 4 + 16;
+
+// One 32-token tile: gOut -> gH -> gZ (two products against the backward-orientation shadows), LN2 backward -> gY, D.
+// A2's padding columns must be zero.
+template <class WaitW>
+__device__ __forceinline__ void ffn_bwd_tile(const FfnBwdArgs& a, int t0, int T, uint64_t seed_eff, op_t* __restrict__ A1, op_t* __restrict__ A2,
+                                             float* __restrict__ Ft, float* __restrict__ rs, const op_t* W2_s, const op_t* W1_s,
+                                             const float (&gam)[NE], float inv_keep, WaitW wait_w) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mt = warp & 1, ng = warp >> 1;
+  const int d = a.d;
+  // gOut = gX * dropout(site2): x_out = drop(h.W2 + b2) + z   (modules.py:259-266)
+  float go[RPW][NE];
+  load_rows(go, a.gX, t0, T, d, warp, lane);
+  float2 hf[NT][2], gxf[NT][2];
+  load_frag(hf, a.H, t0, T, d, mt, ng, lane);
+  load_frag(gxf, a.gX, t0, T, d, mt, ng, lane);
+  if (a.drop_p > 0.f) {
+    const DropSite ds2 = drop_site(seed_eff, a.site2, a.drop_p);
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int tk = t0 + warp * RPW + rr;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int c = lane + 32 * e;
+        if (tk < T && c < d) {
+          const long long el = (long long)tk * d + c;
+          go[rr][e] *= drop_mul(ds2, (uint64_t)el);
+          a.gO[el] = go[rr][e];
+        }
+      }
+    }
+  }
+  put_rows_scaled(A1, rs, go, warp, lane);
+  __syncthreads();
+  FZ_TL(1, 2);
+  wait_w();
+  FZ_TL(1, 3);
+  float acc[NT][4];
+  zero_acc(acc);
+  warp_gemm(A1 + mt * 16 * LDS, W2_s + ng * (NT * 8) * LDS, acc, lane);
+  // gH = (gOut . W2^T) * [h > 0] / (1 - p)   (h is stored post-dropout)
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (c < d) {
+      float g0 = 0.f, g1 = 0.f;
+      if (t0 + r < T) {
+        g0 = hf[j][h].x > 0.f ? v0 * inv_keep : 0.f; g1 = hf[j][h].y > 0.f ? v1 * inv_keep : 0.f;   // still carries the row scale
+        *reinterpret_cast<float2*>(a.gH + (long long)(t0 + r) * d + c) = make_float2(g0 * rs[r], g1 * rs[r]);
+      }
+      st_op2(A2 + r * LDS + c, g0, g1);
+    }
+  });
+  // rows of the LayerNorm-backward pass: issue their loads now, they land while the second product runs
+  float yv[RPW][NE], q1[RPW][NE], mean[RPW], rstd[RPW];
+  load_rows(yv, a.Y, t0, T, d, warp, lane);
+  load_rows(q1, a.Q1, t0, T, d, warp, lane);
+  load_row_scalars(mean, a.mean2, t0, T, warp);
+  load_row_scalars(rstd, a.rstd2, t0, T, warp);
+  __syncthreads();
+  FZ_TL(1, 4);
+  zero_acc(acc);
+  warp_gemm(A2 + mt * 16 * LDS, W1_s + ng * (NT * 8) * LDS, acc, lane);
+  // gZ = gH . W1^T + gX   (residual z -> x_out)
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (c < d) {
+      float z0 = 0.f, z1 = 0.f;
+      if (t0 + r < T) {
+        z0 = v0 * rs[r] + gxf[j][h].x; z1 = v1 * rs[r] + gxf[j][h].y;
+        *reinterpret_cast<float2*>(a.gZ + (long long)(t0 + r) * d + c) = make_float2(z0, z1);
+      }
+      *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(z0, z1);
+    }
+  });
+  __syncthreads();
+  FZ_TL(1, 5);
+  // gY = LN2 backward;  D = gY . (Y - q1)  (= sum_j dP_ij P_ij of the attention softmax backward)
+  float dx[RPW][NE], dd[RPW];
+  ln_bwd_rows(Ft, yv, mean, rstd, gam, d, warp, lane, dx);
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int tk = t0 + warp * RPW + rr;
+    float acc_d = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      if (tk < T && c < d) { a.gY[(long long)tk * d + c] = dx[rr][e]; acc_d = fmaf(dx[rr][e], yv[rr][e] - q1[rr][e], acc_d); }
+    }
+    dd[rr] = acc_d;
+  }
+  warp_sum_n(dd);
+  if (lane == 0) {
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) { const int tk = t0 + warp * RPW + rr; if (tk < T) a.D[tk] = dd[rr]; }
+  }
+  __syncthreads();
+  FZ_TL(1, 6);
+}
 
 __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ FfnBwdArgs a) {
   FZ_TL(1, 0);
@@ -728,96 +881,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_ffn_bwd(const __grid_constant__ Ffn
   pdl_wait(); pdl_go();
   __syncthreads();
   FZ_TL(1, 1);
-  const int mt = warp & 1, ng = warp >> 1;
   const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   bool first = true;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t0 = tile * TM;
-    // gOut = gX * dropout(site2): x_out = drop(h.W2 + b2) + z   (modules.py:259-266)
-    float go[RPW][NE];
-    load_rows(go, a.gX, t0, T, d, warp, lane);
-    float2 hf[NT][2], gxf[NT][2];
-    load_frag(hf, a.H, t0, T, d, mt, ng, lane);
-    load_frag(gxf, a.gX, t0, T, d, mt, ng, lane);
-    if (a.drop_p > 0.f) {
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int tk = t0 + warp * RPW + rr;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const int c = lane + 32 * e;
-          if (tk < T && c < d) {
-            const long long el = (long long)tk * d + c;
-            go[rr][e] *= drop_scale(seed_eff, a.site2, (uint64_t)el, a.drop_p);
-            a.gO[el] = go[rr][e];
-          }
-        }
-      }
-    }
-    put_rows_scaled(A1, rs, go, warp, lane);
-    __syncthreads();
-    FZ_TL(1, 2);
-    if (first) { mbar_wait(bar, 0); first = false; }
-    FZ_TL(1, 3);
-    float acc[NT][4];
-    zero_acc(acc);
-    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    // gH = (gOut . W2^T) * [h > 0] / (1 - p)   (h is stored post-dropout)
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (c < d) {
-        float g0 = 0.f, g1 = 0.f;
-        if (t0 + r < T) {
-          g0 = hf[j][h].x > 0.f ? v0 * inv_keep : 0.f; g1 = hf[j][h].y > 0.f ? v1 * inv_keep : 0.f;   // still carries the row scale
-          *reinterpret_cast<float2*>(a.gH + (long long)(t0 + r) * d + c) = make_float2(g0 * rs[r], g1 * rs[r]);
-        }
-        st_op2(A2 + r * LDS + c, g0, g1);
-      }
-    });
-    // rows of the LayerNorm-backward pass: issue their loads now, they land while the second product runs
-    float yv[RPW][NE], q1[RPW][NE], mean[RPW], rstd[RPW];
-    load_rows(yv, a.Y, t0, T, d, warp, lane);
-    load_rows(q1, a.Q1, t0, T, d, warp, lane);
-    load_row_scalars(mean, a.mean2, t0, T, warp);
-    load_row_scalars(rstd, a.rstd2, t0, T, warp);
-    __syncthreads();
-    FZ_TL(1, 4);
-    zero_acc(acc);
-    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    // gZ = gH . W1^T + gX   (residual z -> x_out)
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (c < d) {
-        float z0 = 0.f, z1 = 0.f;
-        if (t0 + r < T) {
-          z0 = v0 * rs[r] + gxf[j][h].x; z1 = v1 * rs[r] + gxf[j][h].y;
-          *reinterpret_cast<float2*>(a.gZ + (long long)(t0 + r) * d + c) = make_float2(z0, z1);
-        }
-        *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(z0, z1);
-      }
-    });
-    __syncthreads();
-    FZ_TL(1, 5);
-    // gY = LN2 backward;  D = gY . (Y - q1)  (= sum_j dP_ij P_ij of the attention softmax backward)
-    float dx[RPW][NE], dd[RPW];
-    ln_bwd_rows(Ft, yv, mean, rstd, gam, d, warp, lane, dx);
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int tk = t0 + warp * RPW + rr;
-      float acc_d = 0.f;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int c = lane + 32 * e;
-        if (tk < T && c < d) { a.gY[(long long)tk * d + c] = dx[rr][e]; acc_d = fmaf(dx[rr][e], yv[rr][e] - q1[rr][e], acc_d); }
-      }
-      dd[rr] = acc_d;
-    }
-    warp_sum_n(dd);
-    if (lane == 0) {
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) { const int tk = t0 + warp * RPW + rr; if (tk < T) a.D[tk] = dd[rr]; }
-    }
-    __syncthreads();
-    FZ_TL(1, 6);
-  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    ffn_bwd_tile(a, tile * TM, T, seed_eff, A1, A2, Ft, rs, Wsm, Wsm + KP * LDS, gam, inv_keep,
+                 [&] { if (first) { mbar_wait(bar, 0); first = false; } });
 }
 
 // ---- backward: attention, warp per token (query role -> gQ, key role -> gK, gV) ------------------------
@@ -961,13 +1029,9 @@ __global__ void __launch_bounds__(256) k_attn_bwd_w(const __grid_constant__ Attn
 // The probabilities a token needs (its own row as a query, its column as a key) and the D values of its later
 // queries are fetched into registers up front, so the block loops touch no global memory.
 __host__ __device__ constexpr int att_bwd_smem(int L, int d) { return 2 * att_rows_cap(L) * d * 4; }
-__global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ AttnBwdArgs a) {
-  extern __shared__ __align__(16) float att_sm[];
-  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
-  const int T = *a.dT;
-  const int t0 = blockIdx.x * ATT_TOK;
-  if (t0 >= T) return;
-  pdl_wait(); pdl_go();
+// One group of ATT_TOK consecutive tokens [t0, t0 + ATT_TOK) of the rows below T (all threads of the CTA call it; the
+// caller separates two groups by a __syncthreads: the staging buffers are reused).
+__device__ __forceinline__ void attn_bwd_group(const AttnBwdArgs& a, int t0, int T, float* __restrict__ att_sm, uint64_t seed_eff) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, L = a.L;
   const int tk = min(t0 + warp, T - 1);
@@ -990,6 +1054,7 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ 
     gq[e] = gk[e] = gv[e] = 0.f;
   }
   const float Di = a.D[tk];
+  const DropSite dsp = drop_site(seed_eff, a.site, a.drop_p);
   // probabilities / dropout scales / D: own row (query role: key lane + 32u) and own column (key role: query tk + lane + 32u)
   float pq[2], sq[2], pk[2], sk[2], dk[2];
 #pragma unroll
@@ -999,14 +1064,14 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ 
     if (j <= i) {
       const long long po = (long long)tk * L + j;
       pq[u] = a.probs[po];
-      if (a.drop_p > 0.f) sq[u] = drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p);
+      if (a.drop_p > 0.f) sq[u] = drop_mul(dsp, (uint64_t)po);
     }
     if (i + j < n) {
       const int tq = tk + j;
       const long long po = (long long)tq * L + i;
       pk[u] = a.probs[po];
       dk[u] = a.D[tq];
-      if (a.drop_p > 0.f) sk[u] = drop_scale(seed_eff, a.site, (uint64_t)po, a.drop_p);
+      if (a.drop_p > 0.f) sk[u] = drop_mul(dsp, (uint64_t)po);
     }
   }
   float* As = att_sm;
@@ -1031,28 +1096,39 @@ __global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ 
   stage_f2(As, a.gY + (long long)t0 * d, (hi2 - t0) * d / 2);
   stage_f2(Bs, a.Q + (long long)t0 * d, (hi2 - t0) * d / 2);
   __syncthreads();
-  if (!live) return;
-  for (int q0 = 0; i + q0 < n; q0 += KB) {          // queries tk + q0 .. of the same session
-    const int cnt = min(KB, n - i - q0);
-    const float dp = block_dots(vt, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
-    const int u = q0 + j8;
-    const float P = __shfl_sync(0xffffffffu, (u < 32) ? pk[0] : pk[1], u & 31);
-    const float scl = __shfl_sync(0xffffffffu, (u < 32) ? sk[0] : sk[1], u & 31);
-    const float Dq = __shfl_sync(0xffffffffu, (u < 32) ? dk[0] : dk[1], u & 31);
-    const float ds = (j8 < cnt) ? P * (dp * scl - Dq) * inv_denom : 0.f;
-    const float pd = (j8 < cnt) ? P * scl : 0.f;
-    block_axpy(gk, ds, Bs + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
-    block_axpy(gv, pd, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
-  }
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int c = lane + 32 * e;
-    if (c < d) {
-      a.gQ[(long long)tk * d + c] = gq[e];
-      a.gK[(long long)tk * d + c] = gk[e];
-      a.gV[(long long)tk * d + c] = gv[e];
+  if (live) {
+    for (int q0 = 0; i + q0 < n; q0 += KB) {          // queries tk + q0 .. of the same session
+      const int cnt = min(KB, n - i - q0);
+      const float dp = block_dots(vt, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
+      const int u = q0 + j8;
+      const float P = __shfl_sync(0xffffffffu, (u < 32) ? pk[0] : pk[1], u & 31);
+      const float scl = __shfl_sync(0xffffffffu, (u < 32) ? sk[0] : sk[1], u & 31);
+      const float Dq = __shfl_sync(0xffffffffu, (u < 32) ? dk[0] : dk[1], u & 31);
+      const float ds = (j8 < cnt) ? P * (dp * scl - Dq) * inv_denom : 0.f;
+      const float pd = (j8 < cnt) ? P * scl : 0.f;
+      block_axpy(gk, ds, Bs + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
+      block_axpy(gv, pd, As + (tk - t0 + q0) * d, d, cnt, 0, d, lane);
+    }
+  #pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      if (c < d) {
+        a.gQ[(long long)tk * d + c] = gq[e];
+        a.gK[(long long)tk * d + c] = gk[e];
+        a.gV[(long long)tk * d + c] = gv[e];
+      }
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 3) k_attn_bwd_s1(const __grid_constant__ AttnBwdArgs a) {
+  extern __shared__ __align__(16) float att_sm[];
+  const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
+  const int T = *a.dT;
+  const int t0 = blockIdx.x * ATT_TOK;
+  if (t0 >= T) return;
+  pdl_wait(); pdl_go();
+  attn_bwd_group(a, t0, T, att_sm, seed_eff);
 }
 
 // ---- backward: Q/K/V dgrad + LN1 backward --------------------------------------------------------------
@@ -1065,6 +1141,76 @@ struct QkvBwdArgs {
 };
 constexpr size_t QKV_BWD_SMEM = 3 * WMAT_BYTES + 3 * ATILE_BYTES + FTILE_BYTES + 2 * TM * 4 + 16;
 static_assert(3 * ATILE_BYTES >= FTILE_BYTES, "second fp32 tile aliases the operand tiles");
+
+// One 32-token tile: gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ.Wq^T + gY).  The K/V products run first (their shadows
+// arrive first in the chained kernel), the Q product second; wait_kv() / wait_q() block until the shadows have landed.
+template <class WaitKV, class WaitQ>
+__device__ __forceinline__ void qkv_bwd_tile(const QkvBwdArgs& a, int t0, int T, uint64_t seed_eff, op_t* __restrict__ A1, op_t* __restrict__ A2,
+                                             op_t* __restrict__ A3, float* __restrict__ Ft, float* __restrict__ Ft2, float* __restrict__ rsq,
+                                             float* __restrict__ rskv, const op_t* Wq_s, const op_t* Wk_s, const op_t* Wv_s,
+                                             const float (&gam)[NE], WaitKV wait_kv, WaitQ wait_q) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mt = warp & 1, ng = warp >> 1;
+  const int d = a.d;
+  {
+    float gq[RPW][NE], gk[RPW][NE], gv[RPW][NE];
+    load_rows(gq, a.gQ, t0, T, d, warp, lane);
+    load_rows(gk, a.gK, t0, T, d, warp, lane);
+    load_rows(gv, a.gV, t0, T, d, warp, lane);
+    put_rows_scaled(A1, rsq, gq, warp, lane);
+    put_rows_scaled(A2, rskv, gk, warp, lane, gv, A3);
+  }
+  float2 gyf[NT][2];
+  load_frag(gyf, a.gY, t0, T, d, mt, ng, lane);
+  __syncthreads();
+  wait_kv();
+  float acc_kv[NT][4], acc[NT][4];
+  zero_acc(acc_kv);
+  warp_gemm(A2 + mt * 16 * LDS, Wk_s + ng * (NT * 8) * LDS, acc_kv, lane);
+  warp_gemm(A3 + mt * 16 * LDS, Wv_s + ng * (NT * 8) * LDS, acc_kv, lane);
+  // rows of the LayerNorm-backward pass: loads in flight during the Q product
+  float xv[RPW][NE], mean[RPW], rstd[RPW];
+  load_rows(xv, a.X, t0, T, d, warp, lane);
+  load_row_scalars(mean, a.mean1, t0, T, warp);
+  load_row_scalars(rstd, a.rstd1, t0, T, warp);
+  wait_q();
+  zero_acc(acc);
+  warp_gemm(A1 + mt * 16 * LDS, Wq_s + ng * (NT * 8) * LDS, acc, lane);
+  // gQ1 = gQ . Wq^T + gY   (y = attn + q1)
+  for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (c < d) {
+      float q0 = 0.f, q1 = 0.f;
+      if (t0 + r < T) {
+        q0 = v0 * rsq[r] + gyf[j][h].x; q1 = v1 * rsq[r] + gyf[j][h].y;
+        *reinterpret_cast<float2*>(a.gQ1 + (long long)(t0 + r) * d + c) = make_float2(q0, q1);
+      }
+      *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(q0, q1);
+    }
+  });
+  __syncthreads();                       // every warp is done reading A1..A3 (Ft2 aliases them)
+  for_frag(acc_kv, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
+    if (c < d) *reinterpret_cast<float2*>(Ft2 + r * FT_LD + c) = make_float2(v0 * rskv[r], v1 * rskv[r]);
+  });
+  __syncthreads();
+  // gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ1)   [* embedding-dropout mask in the first block]
+  float dx[RPW][NE];
+  ln_bwd_rows(Ft, xv, mean, rstd, gam, d, warp, lane, dx);
+  const DropSite ds0 = drop_site(seed_eff, 0u, a.drop_p);
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = warp * RPW + rr, tk = t0 + r;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int c = lane + 32 * e;
+      if (tk < T && c < d) {
+        float v = dx[rr][e] + Ft2[r * FT_LD + c];
+        if (a.drop_p > 0.f) v *= drop_mul(ds0, (uint64_t)tk * d + c);
+        a.gXin[(long long)tk * d + c] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ QkvBwdArgs a) {
   const uint64_t seed_eff = eff_seed(a.seed, a.d_step);
@@ -1094,67 +1240,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
   for (int e = 0; e < NE; ++e) { const int c = lane + 32 * e; gam[e] = (c < d) ? a.ln_g[c] : 0.f; }
   pdl_wait(); pdl_go();
   __syncthreads();
-  const int mt = warp & 1, ng = warp >> 1;
   bool first = true;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t0 = tile * TM;
-    {
-      float gq[RPW][NE], gk[RPW][NE], gv[RPW][NE];
-      load_rows(gq, a.gQ, t0, T, d, warp, lane);
-      load_rows(gk, a.gK, t0, T, d, warp, lane);
-      load_rows(gv, a.gV, t0, T, d, warp, lane);
-      put_rows_scaled(A1, rsq, gq, warp, lane);
-      put_rows_scaled(A2, rskv, gk, warp, lane, gv, A3);
-    }
-    float2 gyf[NT][2];
-    load_frag(gyf, a.gY, t0, T, d, mt, ng, lane);
-    __syncthreads();
-    if (first) { mbar_wait(bar, 0); first = false; }
-    float acc[NT][4];
-    zero_acc(acc);
-    warp_gemm(A1 + mt * 16 * LDS, Wsm + ng * (NT * 8) * LDS, acc, lane);
-    // gQ1 = gQ . Wq^T + gY   (y = attn + q1)
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (c < d) {
-        float q0 = 0.f, q1 = 0.f;
-        if (t0 + r < T) {
-          q0 = v0 * rsq[r] + gyf[j][h].x; q1 = v1 * rsq[r] + gyf[j][h].y;
-          *reinterpret_cast<float2*>(a.gQ1 + (long long)(t0 + r) * d + c) = make_float2(q0, q1);
-        }
-        *reinterpret_cast<float2*>(Ft + r * FT_LD + c) = make_float2(q0, q1);
-      }
-    });
-    // rows of the LayerNorm-backward pass: loads in flight during the K/V products
-    float xv[RPW][NE], mean[RPW], rstd[RPW];
-    load_rows(xv, a.X, t0, T, d, warp, lane);
-    load_row_scalars(mean, a.mean1, t0, T, warp);
-    load_row_scalars(rstd, a.rstd1, t0, T, warp);
-    zero_acc(acc);
-    warp_gemm(A2 + mt * 16 * LDS, Wsm + KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    warp_gemm(A3 + mt * 16 * LDS, Wsm + 2 * KP * LDS + ng * (NT * 8) * LDS, acc, lane);
-    __syncthreads();                       // every warp is done reading A1..A3
-    for_frag(acc, mt, ng, lane, [&](int j, int h, int r, int c, float v0, float v1) {
-      if (c < d) *reinterpret_cast<float2*>(Ft2 + r * FT_LD + c) = make_float2(v0 * rskv[r], v1 * rskv[r]);
-    });
-    __syncthreads();
-    // gXin = gK.Wk^T + gV.Wv^T + LN1 backward(gQ1)   [* embedding-dropout mask in the first block]
-    float dx[RPW][NE];
-    ln_bwd_rows(Ft, xv, mean, rstd, gam, d, warp, lane, dx);
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int r = warp * RPW + rr, tk = t0 + r;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int c = lane + 32 * e;
-        if (tk < T && c < d) {
-          float v = dx[rr][e] + Ft2[r * FT_LD + c];
-          if (a.drop_p > 0.f) v *= drop_scale(seed_eff, 0u, (uint64_t)tk * d + c, a.drop_p);
-          a.gXin[(long long)tk * d + c] = v;
-        }
-      }
-    }
-    __syncthreads();
-  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    qkv_bwd_tile(a, tile * TM, T, seed_eff, A1, A2, A3, Ft, Ft2, rsq, rskv, Wsm, Wsm + KP * LDS, Wsm + 2 * KP * LDS, gam,
+                 [&] { if (first) { mbar_wait(bar, 0); first = false; } }, [] {});
 }
 
 // ---- backward: weight / bias / LayerNorm-parameter gradients of one block, ONE launch ------------------
@@ -1170,7 +1259,7 @@ constexpr int WG_TK = 32;                     // tokens per staged tile
 constexpr int WG_LD = 168;                    // fp32 row stride (168 % 32 == 8)
 constexpr int WG_TILE = WG_TK * WG_LD;        // floats per operand tile
 constexpr size_t WGRAD_SMEM = sizeof(float) * 4 * WG_TILE;   // 2 stages x (act, grad) = 86 016 B
-constexpr int WG_MAXP = 8;
+constexpr int WG_MAXP = 10;                   // problems of one launch (chained path: the 5 matrices of 2 blocks)
 struct WgradProb { const float *act, *grad, *mean, *rstd; float *out0, *out1; };   // GEMM: out0 = pW, out1 = pb; LN: out0 = pbeta, out1 = pgamma
 struct WgradArgs { WgradProb p[WG_MAXP]; int n_gemm, n_ln; const int* dT; int d; long long split_stride; };
 

@@ -151,6 +151,56 @@ def test_fused_dropout_masks_match_exact_path():
     assert differ < 5e-3, differ        # only ReLU sign flips of near-zero pre-activations may differ
 
 
+@pytest.mark.parametrize("case", ["ragged", "bench", "one_row", "long_rows"])
+def test_chained_kernels_match_the_per_sublayer_kernels(case, monkeypatch):
+    """encoder_chain.cuh (one forward kernel, one data-gradient kernel: a CTA owns whole sessions) runs the same tile
+    GEMM / LayerNorm tile bodies as the per-sub-layer kernels of encoder_fused.cuh (bit-identical up to the first
+    attention) and an fp32 attention with a different summation order (8 lanes per query instead of a warp), so every
+    saved activation, rep, the loss and the gradient agree to fp32 rounding noise - with dropout, for ragged batches
+    with empty rows, one-row batches, sessions cut by a range boundary and CTAs that own no token at all."""
+    rng = np.random.RandomState(13)
+    if case == "ragged":
+        lens = [1, 50, 2, 49, 33, 0] + list(rng.randint(1, 51, 60)) + [0, 7, 0]
+    elif case == "bench":
+        lens = list(np.minimum(50, rng.geometric(0.2, 650)))
+    elif case == "one_row":
+        lens = [9]
+    else:
+        lens = [50] * 40 + [0, 0, 50, 1]
+    M = len(lens)
+    ids = _ids(rng, M, 50, 280, lens)
+    live = [i for i, n in enumerate(lens) if n]
+    pos = rng.randint(1, 281, M).astype(np.int32)
+    ntok = int(sum(lens))
+    out = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("ADER_B200_CHAIN", chain)
+        monkeypatch.setenv("ADER_B200_TEAM_ATTN", "0")
+        m, hp, _ = _model(300, encoder_impl="tc")
+        m.global_step = 5
+        loss = m.loss_and_grad(ids, pos, 280, dropout_rate=0.3, n_tokens=ntok)
+        slots = [_slots(m, M, ntok, b) for b in range(2)]
+        out[chain] = (loss.clone(), m._keep[5].clone(), m.grad.clone(), slots)
+    a, b = out["1"], out["0"]
+    def near(x, y, what, tol=2e-5):
+        x, y = x.double(), y.double()
+        assert float((x - y).abs().max()) <= tol * max(float(y.abs().max()), 1e-30), what
+
+    for blk in range(2):
+        assert a[3][blk][0] == b[3][blk][0] == ntok
+        for s in a[3][blk][1]:
+            if blk == 0 and s <= 4:           # x, q1, Q, K, V of the first block: the very same tile bodies
+                assert torch.equal(a[3][blk][1][s], b[3][blk][1][s]), "block %d slot %d" % (blk, s)
+            elif s in (5, 6, 9):              # y, z, probs of the first block: same fp32 sums in a different order
+                near(a[3][blk][1][s], b[3][blk][1][s], "block %d slot %d" % (blk, s), 2e-5 if blk == 0 else 1e-3)
+            else:                             # behind the next fp16-operand product: a 1e-6 change of an operand can
+                near(a[3][blk][1][s], b[3][blk][1][s], "block %d slot %d" % (blk, s), 1e-3)   # flip its fp16 rounding
+    near(a[1], b[1], "rep", 2e-3)
+    assert float(a[0].item()) == pytest.approx(float(b[0].item()), rel=1e-4)
+    near(a[2], b[2], "gradient", 5e-2)
+    assert float(a[2].abs().max()) > 0.0
+
+
 def test_fused_rejects_wide_models():
     from ader_b200 import _lib, ops
     m, hp, _ = _model(100, hidden_units=192, num_heads=1)
