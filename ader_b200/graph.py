@@ -180,24 +180,31 @@ class GraphStep:
         self._held_more = []
         self.graphs_idx = {}                   # index-fed form: batch gather + step in ONE graph (no gap between two replays)
 
-    def _graph_for(self, tcap: int, indexed) -> torch.cuda.CUDAGraph:
+    def _graph_for(self, tcap: int, indexed, nsteps: int = 1) -> torch.cuda.CUDAGraph:
         """indexed: False = rows fed into the static batch buffer, True = index-fed (gather inside the graph),
-        "q" = gather from the epoch-resident queue inside the graph."""
+        "q" = gather from the epoch-resident queue inside the graph.  nsteps > 1 (queue form only): that many
+        consecutive steps in ONE graph - every step reads its rows, the token count, the Adam step and the dropout
+        counter from the device, so the captured launches are the same for each; the launch gap between two graph
+        replays (~20 us) is paid once per nsteps."""
         table = self.graphs_q if indexed == "q" else (self.graphs_idx if indexed else self.graphs)
-        g = table.get(tcap)
+        key = tcap if nsteps == 1 else (tcap, nsteps)
+        g = table.get(key)
         if g is None:
+            if nsteps > 1 and indexed != "q":
+                raise ValueError("multi-step graphs need the epoch-resident queue")
             m = self.model
             gs = m.global_step                 # capture records launches, it runs nothing: only the host counter moves
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self._pool):
-                if indexed == "q":
-                    self._gather_q()
-                elif indexed:
-                    self._gather()
-                self._eager(tcap, True, indexed=indexed)
+                for _ in range(nsteps):
+                    if indexed == "q":
+                        self._gather_q()
+                    elif indexed:
+                        self._gather()
+                    self._eager(tcap, True, indexed=indexed)
             self._pool = g.pool()
             m.global_step = gs
-            table[tcap] = g
+            table[key] = g
             # the graph addresses the workspaces as they are NOW (another pass may have grown them since construction)
             self._held_more.append((m._enc_ws.buf, m._bwd_ws.buf, m._loss_ws.buf))
         return g
@@ -211,17 +218,20 @@ class GraphStep:
                 self._graph_for(tcap, form)
 
     # ---- replay ---------------------------------------------------------------------------------------
-    def _replay(self, n_tokens: Optional[int], indexed=False):
-        cap = self.tcaps[-1]
+    def cap_for(self, n_tokens: Optional[int]) -> int:
+        """Smallest token-capacity bucket that holds n_tokens."""
         if n_tokens is not None:
             for t in self.tcaps:
                 if t >= n_tokens:
-                    cap = t
-                    break
-        self.use_count[cap] = self.use_count.get(cap, 0) + 1
-        self._graph_for(cap, indexed).replay()
+                    return t
+        return self.tcaps[-1]
+
+    def _replay(self, n_tokens: Optional[int], indexed=False, nsteps: int = 1):
+        cap = self.cap_for(n_tokens)
+        self.use_count[cap] = self.use_count.get(cap, 0) + nsteps
+        self._graph_for(cap, indexed, nsteps).replay()
         self.model._last_enc = (self.M, cap)           # geometry of the pass whose overflow flag token_overflow() reads
-        self.model.global_step += 1
+        self.model.global_step += nsteps
         self.model.last_row_loss = self._row_loss[(cap, indexed)]
         return self.model._loss
 
@@ -256,11 +266,12 @@ class GraphStep:
         ev.record()
         return PendingLoss(self._loss_host[k], ev)
 
-    def run_queued(self, n_tokens: Optional[int] = None):
-        """Replay the step whose rows are the next entry of the epoch-resident queue (no copies: the host only launches)."""
+    def run_queued(self, n_tokens: Optional[int] = None, nsteps: int = 1):
+        """Replay the step(s) whose rows are the next entries of the epoch-resident queue (no copies: the host only
+        launches).  n_tokens: the LARGEST token count among the nsteps steps."""
         if self.queue is None or self.sources is None:
             raise ValueError("GraphStep was built without an index queue")
-        return self._replay(n_tokens, indexed="q")
+        return self._replay(n_tokens, indexed="q", nsteps=nsteps)
 
     def run_indices(self, ti, ei=None, n_tokens: Optional[int] = None):
         """Row indices into the ``sources`` matrices (host arrays or device tensors)."""

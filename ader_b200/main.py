@@ -214,8 +214,22 @@ class PeriodTrainer:
             self.q_off[s0:s1].copy_(self._qoff_host[s0:s1], non_blocking=True)
             t1 = time.time()
             self.host_s["plan"] += t1 - t0
-            for item in plan:
-                loss = self._launch_queued(*item)
+            i = 0
+            while i < len(plan):
+                # runs of GROUP consecutive steps of one batch geometry go out as ONE graph replay (capacity = the largest
+                # of their buckets): the replay-to-replay launch gap is paid once per GROUP steps
+                key, _, _, n_tok = plan[i]
+                n = self.GROUP
+                if n > 1 and i + n <= len(plan) and all(plan[i + k][0] == key for k in range(1, n)):
+                    gs = self.gs_map.get(key)
+                    if gs is not None and self._geom_multi(key):
+                        if self.world > 1:
+                            m.global_counts = key
+                        loss = gs.run_queued(max(plan[i + k][3] for k in range(n)), nsteps=n)
+                        i += n
+                        continue
+                loss = self._launch_queued(*plan[i])
+                i += 1
             self.host_s["launch"] += time.time() - t1
             s0 = s1
         if self._q_copied is None:
@@ -224,6 +238,13 @@ class PeriodTrainer:
         return loss
 
     CHUNK0, CHUNK = 8, 48
+    GROUP = int(os.environ.get("ADER_B200_GRAPH_STEPS", "1"))     # steps per graph replay in a queued epoch (measured: 4 buys < 1 %, costs captures)
+
+    def _geom_multi(self, key) -> bool:
+        """Multi-step graphs only for the full batch geometry (nearly every step of an epoch; rare geometries are not
+        worth another capture)."""
+        full = (self.args.batch_size, self.es.batch_size if self.es is not None else 0)
+        return key == full
 
     def _launch_queued(self, key, nt, ne, n_tok):
         """One step of a queued epoch: graph replay, or (rare batch geometry) eager launches from the same queue."""

@@ -325,6 +325,9 @@ def cpu_components(budget_s=6.0):
     return out
 
 
+GROUP = int(os.environ.get("ADER_B200_GRAPH_STEPS", "1"))      # steps per graph replay of the resident region (the product default: 1)
+
+
 def workload_config(n):
     return {"workload": WL["name"], "batch_size": WL["B"], "exemplar_rows": WL["M_e"], "max_item": WL["V"],
             "prev_max_item": WL["V_prev"], "table_rows": WL["item_num"] + 1, "lambda": WL["lam"], "maxlen": 50,
@@ -410,9 +413,19 @@ def gpu_arm(args):
         model.global_counts = (B * world, Me * world)
     if not args.no_graph:       # the step as CUDA graphs (one per token-capacity bucket); same C-ABI calls as the eager step
         caps = sorted({int(-(-q // 256) * 256) for q in np.quantile(ntok_all, [0.5, 0.9, 0.99, 1.0])})
-        gs = model.graph_step(B, Me, V, WL["lr"], P, teacher=teacher, sources=(d_t_ids, d_t_lab, d_e_ids, d_e_row), tcaps=caps)
+        # epoch-resident index queue (ader_b200/main.py PeriodTrainer.run_epoch): the row indices of every step of the
+        # resident region live in HBM, a step graph gathers its batch from the queue, GROUP consecutive steps are one replay
+        q_host = np.concatenate([np.concatenate([a, b]) for a, b in zip(ti_all, ei_all)]).astype(np.int32)
+        queue = (torch.from_numpy(q_host).to(dev), torch.arange(nsteps, dtype=torch.int64, device=dev) * (B + Me),
+                 torch.zeros(1, dtype=torch.int32, device=dev))
+        gs = model.graph_step(B, Me, V, WL["lr"], P, teacher=teacher, sources=(d_t_ids, d_t_lab, d_e_ids, d_e_row), tcaps=caps,
+                              queue=queue)
         crumb("graph step built, buckets %s" % (gs.tcaps,))
         gs.precapture()          # graphs are captured on first use otherwise: keep that out of the timed regions
+        for cap in gs.tcaps:
+            gs._graph_for(cap, "q")
+            if GROUP > 1:
+                gs._graph_for(cap, "q", GROUP)
         crumb("graphs captured")
 
     def resident_step(i):
@@ -439,14 +452,24 @@ def gpu_arm(args):
     windows = []
 
     # ---- value: inputs resident in HBM -----------------------------------------------------------
-    for i in range(W):
-        resident_step(i)
+    def resident_run(lo, hi):
+        """Steps [lo, hi) of the resident region: the queued epoch loop of the product (GROUP steps per graph replay)."""
+        if gs is None:
+            for i in range(lo, hi):
+                resident_step(i)
+            return
+        i = lo
+        while i < hi:
+            n = GROUP if (GROUP > 1 and i + GROUP <= hi) else 1
+            gs.run_queued(max(ntok[i:i + n]), nsteps=n)
+            i += n
+
+    resident_run(0, W)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
-    for i in range(W, W + K):
-        resident_step(i)
+    resident_run(W, W + K)
     e1.record()
     barrier()
     windows.append((w0, time.time()))
@@ -664,7 +687,7 @@ def gpu_arm(args):
                 "gpu_launches_per_step": launches_per_step,
                 "clocks": clock_info,
                 "phases_ms_eager": phases,
-                "step_mode": "eager launches" if gs is None else "CUDA graph per token-capacity bucket %s" % (gs.tcaps,),
+                "step_mode": "eager launches" if gs is None else "CUDA graph per token-capacity bucket %s; resident region: epoch-resident index queue, %d steps per graph replay" % (gs.tcaps, GROUP),
                 "kernels_us_per_step": dict(sorted(((k, round(v, 2)) for k, v in kernels_us.items()), key=lambda kv: -kv[1])[:12]),
                 "loss_group_ms": loss_group_ms,
                 "tc_kernels_ms": tc_kernels_ms,
