@@ -4,9 +4,10 @@
   denominators (AderLossArgs.n_train_global / n_ex_global); the gradients of the ranks are SUMMED.
   Two interchangeable back ends behind ``Ader.dp``:
     - ``PeerComm`` (default): theta / grad / a flag block of every rank are mapped into every process
-      (CUDA IPC over NVLink) and ONE kernel per step (csrc/dp.cu, ader_dp_adam_step) does
-      reduce-scatter by peer loads -> TF1 Adam on the owned slice -> all-gather by peer stores;
-      the optimiser state of a slice is only touched by its owner.  No host in the loop, graph-capturable.
+      (CUDA IPC over NVLink) and the optimiser step is the collective (csrc/dp.cu, ader_dp_adam_step:
+      arrive -> reduce-scatter by peer loads + TF1 Adam on the owned slice + all-gather by peer stores ->
+      publish; ader_dp_wait at the start of the next step); the optimiser state of a slice is only touched
+      by its owner.  No host in the loop, graph-capturable.
     - ``NcclComm``: all-reduce (sum) of the live gradient ranges (table rows 1..max_item and the dense
       parameters: rows above max_item are identically zero), then the ordinary Adam on every rank.
   Row order inside a rank stays [train; exemplar].

@@ -697,7 +697,7 @@ def gpu_arm(args):
                 "period_metric": period,
                 "components": components,
                 "cpu_components": cpu_comp,
-                "roofline": {"kernel": "k_tc_logits<FWD> + <DREP> + <DE> (the three tcgen05 launches of logits+CE+KD fwd+bwd; CUDA-event "
+                "roofline": {"kernel": "k_tc2<FWD> + <DREP> + <DE> (the three tcgen05 launches of logits+CE+KD fwd+bwd; CUDA-event "
                                        "timed graph replays of exactly these launches; the whole 13-launch group is loss_group_ms)",
                              "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "traffic": traffic, "peak_source": peak_src,

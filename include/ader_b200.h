@@ -245,8 +245,8 @@ int32_t ader_fisher_finalize(const AderModel* m, const double* acc, float* fishe
 #define ADER_DP_FLAG_WORDS 64
 typedef struct AderDpComm {
   int32_t   rank, world;
-  int32_t   separate_arrive;            /* != 0: the "gradients complete" barrier runs as its own single-warp kernel (ranks
-                                           emulated on one GPU); 0: folded into the update kernel (one process per GPU) */
+  int32_t   separate_arrive;            /* kept for layout compatibility, ignored: the "gradients complete" barrier always runs
+                                           as its own single-warp kernel (k_dp_arrive) ahead of the full-occupancy update */
   int32_t   reserved;
   float*    theta[ADER_DP_MAX_RANKS];
   float*    grad[ADER_DP_MAX_RANKS];
