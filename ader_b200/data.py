@@ -231,16 +231,22 @@ class Sampler:
         idx = self.next_indices()
         return tuple(ids[idx]), tuple(label[idx]), [self.logits[i] for i in idx]
 
-    def epoch_order(self) -> np.ndarray:
+    def epoch_order(self, defer_shuffle: bool = False) -> np.ndarray:
         """All row indices of one full pass in batch order (rows of length <= 1 dropped); consumes
-        the wrap reshuffle like batch_num() calls to sampler() would.  Cursor must be at 0."""
+        the wrap reshuffle like batch_num() calls to sampler() would.  Cursor must be at 0.
+        defer_shuffle: the caller runs ``finish_epoch_order()`` itself (same RNG draws, later in wall time: the
+        Python-level shuffle of a 50 000-row list takes ~25 ms, which an evaluation pass hides behind its GPU work)."""
         assert self.batch_counter == 0
         _, _, n_in = self.packed()
         idx = np.asarray(self.data_indices, dtype=np.int64)
         idx = idx[n_in[idx] > 0] if idx.size else idx
+        if not defer_shuffle:
+            self.finish_epoch_order()
+        return idx
+
+    def finish_epoch_order(self):
         if self.batch_num() > 0:
             random.shuffle(self.data_indices)
-        return idx
 
 
 # ---- exemplar store ------------------------------------------------------------------------------
@@ -275,21 +281,30 @@ def load_exemplars(exemplar_pre) -> "ExemplarSet":                              
 # ---- util.py:276-350 -----------------------------------------------------------------------------
 class Evaluator:
     def __init__(self, data: list, is_subseq: bool, maxlen: int, batch_size: int, max_item: int, mode: str,
-                 model, sess=None, chunk_rows: int = 8192, dp=None):
+                 model, sess=None, chunk_rows: int = 8192, dp=None, cache: Optional[dict] = None):
+        """cache: a dict the caller keeps for as long as `data` is unchanged (main.py builds a new Evaluator over the SAME
+        validation rows after every epoch, main.py:263): the packed row matrices and their device copies are stored in it
+        by the first Evaluator and reused by the next ones (the Sampler itself is rebuilt every time: its constructor
+        draws from `random`, util.py:148-149)."""
         self.max_item, self.model, self.mode = max_item, model, mode
+        self.cache = cache
         self.dp = dp                      # (rank, world): rows of a pass are sharded over the ranks, ranks all-gathered
         self.ranks: List[int] = []
         self.desc = "Validating epoch " if mode == "valid" else "Testing epoch "
         self.evaluate_sampler = Sampler(data, maxlen, batch_size, is_subseq=is_subseq)
         self.chunk_rows = chunk_rows
         self.topk = None
+        self._rows_dev = None
+        if cache is not None and cache.get("n") == len(self.evaluate_sampler.prepared_data):
+            self.evaluate_sampler._packed = cache["packed"]
+            self._rows_dev = cache["dev"]
 
     def evaluate(self, epoch: int, k: int = 0) -> str:                           # util.py:309-327
         """All rows of one pass are ranked on the device in a few large calls.  The rank list is in
         the reference's batch order; the sampler's RNG is consumed as batch_num() sampler() calls.
         k > 0 additionally keeps the top-k item ids per row in ``self.topk`` (the metrics only need ranks)."""
         s = self.evaluate_sampler
-        order = s.epoch_order()
+        order = s.epoch_order(defer_shuffle=True)
         ids, label, n_in = s.packed()
         ranks = []
         tops = []
@@ -298,11 +313,30 @@ class Evaluator:
             from .dist import shard_range
             lo_r, hi_r = shard_range(n_all, self.dp[0], self.dp[1])
             order = order[lo_r:hi_r]
+        # the rows of the pass live on the device (uploaded once per Evaluator: every epoch ranks the same rows in a new
+        # order); a chunk is a device gather by the order indices, the host only launches
+        dev = self.model.device
+        if self._rows_dev is None:
+            self._rows_dev = (torch.from_numpy(np.ascontiguousarray(ids)).to(dev), torch.from_numpy(np.ascontiguousarray(label)).to(dev))
+        ids_d, label_d = self._rows_dev
+        if self.cache is not None:
+            self.cache.update(n=len(s.prepared_data), packed=s.packed(), dev=self._rows_dev)
+        order_d = torch.from_numpy(order).to(dev)
+        guards, spans = [], []
         for lo in range(0, len(order), self.chunk_rows):
             idx = order[lo:lo + self.chunk_rows]
-            r, items, _ = self.model.rank_topk(ids[idx], label[idx], self.max_item, k, n_tokens=int(n_in[idx].sum()))
+            idx_d = order_d[lo:lo + self.chunk_rows]
+            r, items, _ = self.model.rank_topk(ids_d.index_select(0, idx_d), label_d.index_select(0, idx_d), self.max_item, k,
+                                               n_tokens=int(n_in[idx].sum()), guards=guards)
             ranks.append(r)
             tops.append(items)
+            spans.append((lo, idx))
+        s.finish_epoch_order()                               # the wrap reshuffle (same RNG draws), behind the launches
+        for i in self.model.check_guards(guards):            # a candidate band overflowed: that chunk again, exact path
+            lo, idx = spans[i]
+            idx_d = order_d[lo:lo + self.chunk_rows]
+            ranks[i], tops[i], _ = self.model.rank_topk(ids_d.index_select(0, idx_d), label_d.index_select(0, idx_d), self.max_item, k,
+                                                       n_tokens=int(n_in[idx].sum()), force_exact=True)
         if self.dp is not None and self.dp[1] > 1:
             import torch.distributed as dist
             from .dist import shard_range

@@ -520,6 +520,7 @@ def run(args) -> dict:
         best_epoch = 1
         train_time = 0.0
         eval_time, eval_rows = 0.0, 0
+        valid_cache = {}                   # packed validation rows + device copies, shared by the per-epoch Evaluators
         epoch_s, epoch_rows = [], []
         for epoch in range(1, args.num_epochs + 1):
             rows0 = trainer.rows_seen
@@ -548,7 +549,8 @@ def run(args) -> dict:
                 model.variables_prev = model.snapshot_variables()
                 rnd = random.sample(exemplar_subseq, min(len(exemplar_subseq), args.ewc_sample_num))
                 model.compute_fisher(None, rnd, 50, max_item)
-            valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None, dp=dp)
+            valid_evaluator = Evaluator(valid_subseq, True, args.maxlen, args.test_batch, max_item, "valid", model, None, dp=dp,
+                                        cache=valid_cache)
             t0 = time.time()
             info = valid_evaluator.evaluate(epoch)
             eval_time += time.time() - t0                         # evaluate() ends with the ranks on the host

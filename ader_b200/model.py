@@ -302,16 +302,25 @@ class Ader:
                          self.args.dropout_rate if dropout_rate is None else dropout_rate, teacher, sources, tcaps, queue)
 
     # ---- evaluation ---------------------------------------------------------------------------
-    def rank_topk(self, seq, gt, max_item: int, k: int = 20, n_tokens: Optional[int] = None):
+    def rank_topk(self, seq, gt, max_item: int, k: int = 20, n_tokens: Optional[int] = None, guards: Optional[list] = None,
+                  force_exact: bool = False):
         """Rank of the ground-truth item among items 1..max_item (== pred_last[row, gt-1],
-        ADER.py:103 + util.py:325; ties -> lower index first) and the top-k item ids."""
+        ADER.py:103 + util.py:325; ties -> lower index first) and the top-k item ids.
+        guards: None = the two guard words of the call (encoder token overflow, candidate-band overflow of the fused path)
+        are read here (two small host syncs); a list = they are appended as device tensors ``(tokens, band)`` and the CALLER
+        reads them later (``check_guards``) - an evaluation pass then launches all its chunks without a host sync."""
         ids = _to_ids(seq, self.hp.maxlen, self.device)
         gt_t = _to_i32(gt, self.device)
-        rep, _ = self.encode(ids, n_tokens)
-        self._check_overflow()
+        rep, tcap_used = self.encode(ids, n_tokens)
         M = ids.shape[0]
+        tok_flag = None
+        if guards is None:
+            self._check_overflow()
+        else:
+            off = ops.encoder_ws_slot(self.ms, M, tcap_used, -4, 0)
+            tok_flag = self._enc_ws.buf[off:off + 4].view(torch.int32).clone()
         rank = torch.empty(M, dtype=torch.int32, device=self.device)
-        if self.eval_impl == "tc" and self.hp.hidden_units <= 160 and (k <= 0 or 2 * ops.eval_topk_chunks(self.ms, M, max_item) >= k):
+        if not force_exact and self.eval_impl == "tc" and self.hp.hidden_units <= 160 and (k <= 0 or 2 * ops.eval_topk_chunks(self.ms, M, max_item) >= k):
             # tcgen05 scores + exact refinement of the columns inside the certainty bands (ader_eval_rank_tc /
             # ader_eval_rank_topk_tc: identical ranks and top-k lists, the [M, V] scores are never written)
             ws = self._eval_ws.get(ops.eval_rank_tc_ws_bytes(self.ms, M, max_item))
@@ -324,14 +333,31 @@ class Ader:
                 items = torch.empty((M, k), dtype=torch.int32, device=self.device)
                 scores = torch.empty((M, k), dtype=torch.float32, device=self.device)
                 ops.eval_rank_topk_tc(self.ms, self.theta, rep, gt_t, max_item, k, ws, rank, items, scores, over)
+            if guards is not None:
+                guards.append((tok_flag, over))
+                return rank, items, scores
             if int(over.item()) == 0:
                 return rank, items, scores
             self.eval_fallbacks += 1          # a band held more than ADER_EVAL_CAND_CAP columns: exact path for this batch
+        if guards is not None:
+            guards.append((tok_flag, torch.zeros(1, dtype=torch.int32, device=self.device)))
         ws = self._eval_ws.get(ops.eval_ws_bytes(self.ms, M, max_item))
         items = torch.empty((M, max(k, 1)), dtype=torch.int32, device=self.device)
         scores = torch.empty((M, max(k, 1)), dtype=torch.float32, device=self.device)
         ops.eval_rank_topk(self.ms, self.theta, rep, gt_t, max_item, k, ws, rank, items, scores)
         return rank, items, scores
+
+    def check_guards(self, guards) -> list:
+        """One host read of the guard words collected by rank_topk(guards=...): raises on an encoder token overflow, returns
+        the indices of the calls whose candidate band overflowed (the caller re-runs those with force_exact=True)."""
+        if not guards:
+            return []
+        words = torch.stack([torch.cat([t.view(-1)[:1], b.view(-1)[:1]]) for t, b in guards]).cpu().numpy()
+        if self._tight_cap and bool((words[:, 0] != 0).any()):
+            raise ops._lib.AderError("encoder: n_tokens was smaller than the number of real tokens in the batch (tokens dropped)")
+        redo = [int(i) for i in np.nonzero(words[:, 1])[0]]
+        self.eval_fallbacks += len(redo)
+        return redo
 
     def predict(self, sess, seq, item_idx):
         """Reference signature (ADER.py:140-150): full rank matrix ``argsort(argsort(-logits))`` over

@@ -121,6 +121,32 @@ def test_evaluator_metrics_unchanged_by_the_fused_path():
     assert out["exact"][0] == out["tc"][0] and out["exact"][1] == out["tc"][1]
 
 
+def test_evaluator_reruns_a_chunk_whose_band_overflowed():
+    """Evaluator.evaluate launches all chunks without a host sync and reads the guard words once; a chunk whose candidate
+    band overflowed (here: 400 items bit-equal to the ground truth) is ranked again through the exact kernel."""
+    from ader_b200.data import Evaluator
+    import random
+    V, item_num = 900, 1000
+    m, hp, _ = _model(item_num)
+    tab = m.layout.views(m.theta)[0]
+    tab[100:500].copy_(tab[100].expand(400, -1).clone())
+    rng = np.random.RandomState(11)
+    sessions = [list(rng.randint(1, V + 1, rng.randint(2, 9))) for _ in range(300)]
+    for s_ in sessions[:40]:
+        s_[-1] = 300                                                  # ground truth inside the tie group
+    out = {}
+    for impl in ("exact", "tc"):
+        m.eval_impl = impl
+        m.eval_fallbacks = 0
+        random.seed(4)
+        ev = Evaluator(sessions, False, 50, 64, V, "test", m, None, chunk_rows=128)
+        ev.evaluate(1)
+        out[impl] = (list(ev.ranks), m.eval_fallbacks, random.random())
+    assert out["exact"][0] == out["tc"][0]
+    assert out["exact"][1] == 0 and out["tc"][1] >= 1
+    assert out["exact"][2] == out["tc"][2]                            # same RNG draws (deferred wrap reshuffle)
+
+
 @pytest.mark.parametrize("R,V,item_num", [(300, 40135, 43136), (1500, 18661, 25958)])
 def test_fused_topk_equals_exact_topk(R, V, item_num):
     """Top-20 lists (ids and exact fp32 scores) of the two-pass tensor-core path == the exact path, tie order included."""
