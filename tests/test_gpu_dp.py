@@ -62,7 +62,11 @@ def test_peer_memory_dp_equals_full_batch(world, loss_impl, item_num, V):
     batches, V = _batches(steps, V=V, Vp=min(300, V))
     _m = lambda li: _model(li, item_num=item_num)
     ref = _m(loss_impl)
-    ref_losses = [float(ref.train_step(ids, pos, V, 5e-4, 0.0, exemplar_logits=t).item()) for ids, pos, t in batches]
+    ref_losses, th_ref1 = [], None
+    for ids, pos, t in batches:
+        ref_losses.append(float(ref.train_step(ids, pos, V, 5e-4, 0.0, exemplar_logits=t).item()))
+        if th_ref1 is None:
+            th_ref1 = ref.theta.cpu().numpy()
 
     models = [_m(loss_impl) for _ in range(world)]
     comms = local_peer_group(models)
@@ -86,6 +90,8 @@ def test_peer_memory_dp_equals_full_batch(world, loss_impl, item_num, V):
                 part.append(m.train_step(ids[rows], pos[tl:th], V, 5e-4, 0.0, exemplar_logits=teacher[el:eh]).clone())
         torch.cuda.synchronize()
         losses.append(sum(float(p.item()) for p in part))
+        if len(losses) == 1:
+            th1 = models[0].theta.cpu().numpy()
     for c in comms:
         c.check()
     tol = 1e-5 if loss_impl == "exact" else 2e-4
@@ -94,13 +100,19 @@ def test_peer_memory_dp_equals_full_batch(world, loss_impl, item_num, V):
     th = [m.theta.cpu().numpy() for m in models]
     for r in range(1, world):
         assert np.array_equal(th[0], th[r])                  # replicas stay bit-identical (the owner broadcasts its slice)
-    # three Adam steps move weights by ~3 lr; summation order of the gradient differs from the single-replica kernels
-    assert np.abs(th[0] - th_ref).max() < (3e-5 if loss_impl == "exact" else 3e-4)
+    # After ONE step the parameters agree to the summation-order noise of the gradient (Adam normalises, so even noise-only
+    # gradients move a weight by at most lr * |dg| / |g|).  Later steps of the tensor-core path diverge further without any
+    # error in the exchange: the encoder / logits kernels read 16-bit shadows of the weights, a 1e-6 difference of a weight
+    # flips the rounding of its shadow (fp16 ulp 3e-5 at 0.05) for a few percent of the weights, and the next gradients differ
+    # by ~1e-3 relative (measured: scripts/dp_debug.py).  So: tight after one step, within the Adam step bound after three.
+    assert np.abs(th1 - th_ref1).max() < 1e-5
+    assert np.abs(th[0] - th_ref).max() < (3e-5 if loss_impl == "exact" else 3 * 5e-4 * 1.01)
     assert [int(m.adam_state[0].item()) for m in models] == [steps] * world
     # the optimiser state is sharded: a rank only ever touches the slots of its own slice, the union is the reference state
     m_sum = sum(m.adam_m.cpu().numpy() for m in models)
     ref_m = ref.adam_m.cpu().numpy()
-    assert np.abs(m_sum - ref_m).max() <= (1e-5 if loss_impl == "exact" else 1e-2) * max(np.abs(ref_m).max(), 1e-12) + 1e-9
+    # (tensor-core path: the third step's gradients already differ by a few 1e-3 through the 16-bit weight shadows, see above)
+    assert np.abs(m_sum - ref_m).max() <= (1e-5 if loss_impl == "exact" else 5e-2) * max(np.abs(ref_m).max(), 1e-12) + 1e-9
     touched = [(m.adam_v.cpu().numpy() != 0) for m in models]
     assert not np.logical_and(touched[0], touched[1]).any()
 
