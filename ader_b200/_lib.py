@@ -44,7 +44,8 @@ DP_FLAG_WORDS = 64
 class AderDpComm(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("separate_arrive", C.c_int32), ("reserved", C.c_int32),
                 ("theta", C.c_void_p * DP_MAX_RANKS),
-                ("grad", C.c_void_p * DP_MAX_RANKS), ("flags", C.c_void_p * DP_MAX_RANKS)]
+                ("grad", C.c_void_p * DP_MAX_RANKS), ("flags", C.c_void_p * DP_MAX_RANKS),
+                ("mc_theta", C.c_void_p), ("mc_grad", C.c_void_p)]
 
 
 _P = C.c_void_p

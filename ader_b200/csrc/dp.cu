@@ -95,6 +95,8 @@ struct DpArgs {
   long long q_lo, q_hi;       // quads owned by this rank
   float lr, beta1, beta2, eps, ewc_lambda;
   const float *fisher, *theta_star;
+  float* mc_theta;            // NVLS multicast views of theta / grad (k_dp_adam_mc), else NULL
+  const float* mc_grad;
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) {
@@ -178,6 +180,67 @@ __global__ void __launch_bounds__(256) k_dp_adam(DpArgs a) {
   }
 }
 
+// ---- NVLS variant: the NVSwitch sums and broadcasts ------------------------------------------------------------------
+// `mc_grad` / `mc_theta` are multicast addresses bound to every rank's gradient / parameter buffer.  One
+// multimem.ld_reduce.add returns the sum of the quad over all ranks (added inside the switch: this rank receives 16 bytes
+// instead of 16 x world), one multimem.st delivers the new quad to every replica (sent once instead of world times), so the
+// NVLink traffic per rank is 2 x its slice whatever the world size.  The owner still computes and everyone receives the
+// same bits, so replicas stay bit-identical; the order of the in-switch sum is the switch's, not rank order.
+__device__ __forceinline__ float4 mm_ld_sum4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 mm_ld_sum2(const float* p) {
+  float2 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st4(float* p, float a, float b, float c, float d) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mm_st2(float* p, float a, float b) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_dp_adam_mc(DpArgs a) {
+  const long long q = a.q_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.q_hi) return;
+  const float lr_t = __uint_as_float(ld_relaxed_sys(a.flags[a.rank] + F_LR));
+  const int s = q >= a.q0[1] ? 1 : 0;
+  const long long u0 = 2 * (q - a.q0[s]) - a.ph[s];
+  const long long el = a.e0[s] + 2 * u0;
+  const int msk = ((u0 >= 0) ? 1 : 0) | ((u0 + 1 < a.n2[s]) ? 2 : 0);
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (msk == 3) { const float4 t = mm_ld_sum4(a.mc_grad + el); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+  else {
+    const int o = (msk == 2) ? 2 : 0;
+    const float2 t = mm_ld_sum2(a.mc_grad + el + o);
+    g[o] = t.x; g[o + 1] = t.y;
+  }
+  const int lo = (msk & 1) ? 0 : 2, hi = (msk & 2) ? 4 : 2;
+  float th[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool ewc = a.ewc_lambda != 0.f;
+#pragma unroll
+  for (int h = 0; h < 4; h += 2) {
+    if (h < lo || h >= hi) continue;
+    const long long x = el + h;
+    const float2 t2 = *reinterpret_cast<const float2*>(a.theta[a.rank] + x);
+    float2 m2 = *reinterpret_cast<const float2*>(a.m + x);
+    float2 v2 = *reinterpret_cast<const float2*>(a.v + x);
+    float2 f2 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+    if (ewc) { f2 = *reinterpret_cast<const float2*>(a.fisher + x); s2 = *reinterpret_cast<const float2*>(a.theta_star + x); }
+    th[h] = t2.x; th[h + 1] = t2.y;
+    adam_update_elem(g[h], th[h], m2.x, v2.x, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f2.x, s2.x);
+    adam_update_elem(g[h + 1], th[h + 1], m2.y, v2.y, lr_t, a.beta1, a.beta2, a.eps, a.ewc_lambda, f2.y, s2.y);
+    *reinterpret_cast<float2*>(a.m + x) = m2;
+    *reinterpret_cast<float2*>(a.v + x) = v2;
+  }
+  if (msk == 3) mm_st4(a.mc_theta + el, th[0], th[1], th[2], th[3]);
+  else mm_st2(a.mc_theta + el + lo, th[lo], th[lo + 1]);
+}
+
 // B: stream order puts every load / store of k_dp_adam before this kernel (the kernel boundary is the system-wide fence)
 __global__ void k_dp_publish(DpFlags a, int* state) {
   uint32_t* myf = a.flags[a.rank];
@@ -227,6 +290,7 @@ static void dp_preload() {
   cudaFuncGetAttributes(&fa, k_dp_adam<4>);
   cudaFuncGetAttributes(&fa, k_dp_adam<8>);
   cudaFuncGetAttributes(&fa, k_dp_adam<16>);
+  cudaFuncGetAttributes(&fa, k_dp_adam_mc);
   cudaFuncGetAttributes(&fa, k_dp_publish);
   cudaFuncGetAttributes(&fa, k_dp_arrive);
   cudaFuncGetAttributes(&fa, k_dp_wait);
@@ -280,6 +344,9 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
   d.q_hi = q_total * (c->rank + 1) / c->world;
   d.lr = a->lr; d.beta1 = a->beta1; d.beta2 = a->beta2; d.eps = a->eps; d.ewc_lambda = a->ewc_lambda;
   d.fisher = a->fisher; d.theta_star = a->theta_star;
+  d.mc_theta = c->mc_theta; d.mc_grad = c->mc_grad;
+  ADER_CHECK_ARG((c->mc_theta == nullptr) == (c->mc_grad == nullptr), "dp_adam_step: mc_theta and mc_grad go together");
+  ADER_CHECK_ARG(((uintptr_t)c->mc_theta % 16) == 0 && ((uintptr_t)c->mc_grad % 16) == 0, "dp_adam_step: multicast views must be 16-byte aligned");
   ADER_CHECK_ARG(((uintptr_t)adam_m % 16) == 0 && ((uintptr_t)adam_v % 16) == 0, "dp_adam_step: optimiser slots must be 16-byte aligned");
   for (int r = 0; r < c->world; ++r)
     ADER_CHECK_ARG(((uintptr_t)c->theta[r] % 16) == 0 && ((uintptr_t)c->grad[r] % 16) == 0, "dp_adam_step: theta / grad of rank %d must be 16-byte aligned", r);
@@ -290,7 +357,8 @@ extern "C" int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, fl
   for (int r = 0; r < ADER_DP_MAX_RANKS; ++r) fl.flags[r] = d.flags[r];
   cudaStream_t st = (cudaStream_t)stream;
   k_dp_arrive<<<1, 32, 0, st>>>(fl, state, a->lr, a->beta1, a->beta2);
-  if (c->world <= 2) k_dp_adam<2><<<grid, 256, 0, st>>>(d);
+  if (c->mc_theta) k_dp_adam_mc<<<grid, 256, 0, st>>>(d);
+  else if (c->world <= 2) k_dp_adam<2><<<grid, 256, 0, st>>>(d);
   else if (c->world <= 4) k_dp_adam<4><<<grid, 256, 0, st>>>(d);
   else if (c->world <= 8) k_dp_adam<8><<<grid, 256, 0, st>>>(d);
   else k_dp_adam<16><<<grid, 256, 0, st>>>(d);

@@ -91,14 +91,50 @@ class PeerComm:
 
     kind = "p2p"
 
-    def __init__(self, model, rank: int, world: int, peers, flags: torch.Tensor, opened=(), separate_arrive: bool = False):
+    def __init__(self, model, rank: int, world: int, peers, flags: torch.Tensor, opened=(), separate_arrive: bool = False,
+                 mc_theta: int = 0, mc_grad: int = 0):
         from . import ops
         self.rank, self.world = rank, world
         self.flags = flags                                   # keep the local flag block alive
         self._opened = list(opened)                          # IPC mappings to close
         self.comm = ops.dp_comm(rank, world, [p[0] for p in peers], [p[1] for p in peers], [p[2] for p in peers],
-                                separate_arrive=separate_arrive)
+                                separate_arrive=separate_arrive, mc_theta=mc_theta, mc_grad=mc_grad)
         self._ops = ops
+        if mc_theta:
+            self.kind = "nvls"
+
+    @classmethod
+    def from_symmetric_memory(cls, model, group=None):
+        """NVLS form: theta, grad and the flag block of every rank live in ONE torch symmetric-memory allocation per rank
+        (cuMemCreate + NVSwitch multicast object, set up by torch.distributed._symmetric_memory: plumbing).  The update
+        kernel then sums the gradient inside the switch (multimem.ld_reduce) and broadcasts the new parameters with
+        multimem.st (csrc/dp.cu k_dp_adam_mc).  The model's ``theta`` / ``grad`` are re-bound to views of that allocation
+        (same values).  Returns None when the fabric has no multicast support (the caller falls back to CUDA IPC)."""
+        import torch.distributed._symmetric_memory as symm
+        from . import ops
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        total = model.theta.numel()
+        pad = (total + 3) // 4 * 4                            # grad starts 16-byte aligned, same phase as theta
+        words = ops._lib.DP_FLAG_WORDS
+        buf = symm.empty(2 * pad + words, dtype=torch.float32, device=model.device)
+        hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        have = torch.tensor([1.0 if mc else 0.0], device=model.device)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)
+        if float(have.item()) == 0.0:
+            return None
+        buf.zero_()
+        theta, grad = buf[:total], buf[pad:pad + total]
+        flags = buf[2 * pad:2 * pad + words].view(torch.int32)
+        theta.copy_(model.theta)
+        torch.cuda.synchronize(model.device)
+        model.theta, model.grad = theta, grad
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        peers = [(b, b + 4 * pad, b + 8 * pad) for b in bases]
+        dist.barrier(group=group)                             # every replica is initialised before the first step
+        comm = cls(model, rank, world, peers, flags, (), mc_theta=mc, mc_grad=mc + 4 * pad)
+        comm._symm = (buf, hdl)                               # keep the allocation and the mappings alive
+        return comm
 
     @classmethod
     def from_process_group(cls, model, group=None):
@@ -163,14 +199,29 @@ def local_peer_group(models):
     return comms
 
 
+NVLS_MIN_WORLD = 4      # "auto": in-switch reduction from this world size on (below it plain peer loads are faster: measured)
+
+
 def make_comm(model, group=None, backend: str = None):
-    """Pick the data-parallel back end: ADER_B200_DP=p2p|nccl (default p2p, NCCL when the peer mapping fails)."""
-    backend = backend or os.environ.get("ADER_B200_DP", "p2p")
-    if backend == "p2p" and model.device.type == "cuda":
+    """Pick the data-parallel back end: ADER_B200_DP = auto | nvls | p2p | nccl.
+    auto (default): NVLS multicast (PeerComm.from_symmetric_memory) for world >= NVLS_MIN_WORLD when the fabric supports
+    it, else peer loads / stores over CUDA IPC mappings (p2p), else NCCL.  Every decision is collective."""
+    backend = backend or os.environ.get("ADER_B200_DP", "auto")
+    world = dist.get_world_size(group)
+    if backend in ("auto", "nvls", "p2p") and model.device.type == "cuda":
+        want_nvls = backend == "nvls" or (backend == "auto" and world >= NVLS_MIN_WORLD)
         ok = torch.ones(1, device=model.device)
         comm = None
         try:
-            comm = PeerComm.from_process_group(model, group)
+            if want_nvls:
+                try:
+                    comm = PeerComm.from_symmetric_memory(model, group)
+                except Exception as ex:      # noqa: BLE001 -- no symmetric memory / multicast here: plain peer mappings
+                    import sys
+                    sys.stderr.write("[ader_b200] NVLS multicast unavailable on rank %d (%r); peer loads / stores\n" % (dist.get_rank(group), ex))
+                    comm = None
+            if comm is None:
+                comm = PeerComm.from_process_group(model, group)
         except Exception as ex:      # noqa: BLE001 -- e.g. IPC not permitted in this container: every rank must agree
             import sys
             sys.stderr.write("[ader_b200] peer-memory data parallel unavailable on rank %d (%r); using NCCL\n" % (dist.get_rank(group), ex))

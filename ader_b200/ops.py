@@ -207,11 +207,14 @@ def adam_step(ms: AderModel, theta, m, v, grad, state, V: int, lr: float, ewc_la
 
 
 # ---- data parallel over peer memory (csrc/dp.cu) -------------------------------------------------------
-def dp_comm(rank: int, world: int, theta_ptrs, grad_ptrs, flag_ptrs, separate_arrive: bool = False) -> "_lib.AderDpComm":
+def dp_comm(rank: int, world: int, theta_ptrs, grad_ptrs, flag_ptrs, separate_arrive: bool = False,
+            mc_theta: int = 0, mc_grad: int = 0) -> "_lib.AderDpComm":
+    """mc_theta / mc_grad: optional NVLS multicast addresses of the same buffers (0 = peer loads / stores)."""
     c = _lib.AderDpComm()
     c.rank, c.world, c.separate_arrive, c.reserved = rank, world, int(separate_arrive), 0
     for r in range(world):
         c.theta[r], c.grad[r], c.flags[r] = int(theta_ptrs[r]), int(grad_ptrs[r]), int(flag_ptrs[r])
+    c.mc_theta, c.mc_grad = (int(mc_theta) or None), (int(mc_grad) or None)
     return c
 
 

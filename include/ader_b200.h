@@ -251,6 +251,12 @@ typedef struct AderDpComm {
   float*    theta[ADER_DP_MAX_RANKS];
   float*    grad[ADER_DP_MAX_RANKS];
   uint32_t* flags[ADER_DP_MAX_RANKS];
+  /* optional NVLS multicast views of the SAME buffers (NVSwitch multicast object bound to every rank's theta / grad,
+     e.g. torch symmetric memory): when both are set the update kernel sums the gradient inside the switch
+     (multimem.ld_reduce: each rank loads its slice once instead of once per peer) and broadcasts the new parameters with
+     one multimem.st per quad; NULL = peer loads / stores through theta[] / grad[]. */
+  float*    mc_theta;
+  float*    mc_grad;
 } AderDpComm;
 int32_t ader_dp_wait(const AderDpComm* c, void* stream);
 int32_t ader_dp_adam_step(const AderModel* m, const AderDpComm* c, float* adam_m, float* adam_v, int32_t* state,

@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 T0=$(date +%s)
 : > gpurun_out/legs_scale_$N.txt
 leg() { echo "$1 rc=$2 t=$(( $(date +%s) - T0 ))" >> gpurun_out/legs_scale_$N.txt; }
-for be in ${2:-p2p nccl}; do
+for be in ${2:-auto nccl}; do
   ADER_B200_DP=$be timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
     bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/bench_n${N}_$be.json 2> gpurun_out/bench_n${N}_$be.err; leg bench_n${N}_$be $?
 done

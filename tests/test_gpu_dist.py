@@ -44,6 +44,9 @@ def _worker(rank, world, port, out, backend):
         m.update_loss(0.7)
         ids, pos, teacher, V = _batch()
         dp = DataParallel(m, backend=backend)
+        if backend == "nvls" and m.dp.kind != "nvls":
+            out[rank] = "no multicast"                   # fabric without NVLS: nothing to test
+            return
         assert m.dp.kind == backend, "back end %s unavailable (fell back to %s)" % (backend, m.dp.kind)
         loss = dp.train_step(ids, pos, V, 5e-4, 0.0, exemplar_logits=teacher)
         l2 = dp.train_step(ids, pos, V, 5e-4, 0.0, exemplar_logits=teacher)
@@ -55,7 +58,7 @@ def _worker(rank, world, port, out, backend):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("backend", ["p2p", "nccl"])
+@pytest.mark.parametrize("backend", ["p2p", "nvls", "nccl"])
 def test_data_parallel_step_matches_single_gpu(backend):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -64,6 +67,8 @@ def test_data_parallel_step_matches_single_gpu(backend):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out, backend), nprocs=2, join=True)
+    if out[0] == "no multicast":
+        pytest.skip("no NVLS multicast support on this box")
     m = Ader(400, _args(), init_seed=0)
     m.theta.add_(torch.randn(m.theta.shape, generator=torch.Generator().manual_seed(1)).to(m.device) * 0.05)
     m.update_loss(0.7)
@@ -79,7 +84,7 @@ def test_data_parallel_step_matches_single_gpu(backend):
     assert np.array_equal(out[0][1], out[1][1])          # replicas stay bit-identical
 
 
-def _graph_worker(rank, world, port, out):
+def _graph_worker(rank, world, port, out, backend="p2p"):
     import torch.distributed as dist
     from ader_b200.dist import DataParallel, shard_rows
     from ader_b200.model import Ader
@@ -97,8 +102,11 @@ def _graph_worker(rank, world, port, out):
             m = Ader(400, args, device=torch.device("cuda", rank), init_seed=0)
             m.theta.add_(torch.randn(m.theta.shape, generator=torch.Generator().manual_seed(1)).to(m.device) * 0.05)
             m.update_loss(0.7)
-            DataParallel(m, backend="p2p")
-            assert m.dp.kind == "p2p"
+            DataParallel(m, backend=backend)
+            if backend == "nvls" and m.dp.kind != "nvls":
+                out[rank] = "no multicast"
+                return
+            assert m.dp.kind == backend
             m.global_counts = (n_train, n_ex)
             t_dev = torch.from_numpy(teacher).to(m.device)
             trows = np.arange(el, eh, dtype=np.int32)
@@ -117,15 +125,18 @@ def _graph_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_dp_graph_replay_equals_eager_step_across_gpus():
+@pytest.mark.parametrize("backend", ["p2p", "nvls"])
+def test_dp_graph_replay_equals_eager_step_across_gpus(backend):
     """The peer-memory data-parallel step captured as a CUDA graph (what bench.py and the period loop replay) gives the
-    same bits as the eager step, on every rank."""
+    same bits as the eager step, on every rank (peer loads / stores, and the in-switch NVLS form)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_graph_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_graph_worker, args=(2, _free_port(), out, backend), nprocs=2, join=True)
+    if out[0] == "no multicast":
+        pytest.skip("no NVLS multicast support on this box")
     for r in range(2):
         assert np.array_equal(out[r]["eager"], out[r]["graph"])
     assert np.array_equal(out[0]["graph"], out[1]["graph"])
