@@ -120,11 +120,17 @@ def load() -> C.CDLL:
     # build() returns at once when the .so is newer than every source / header (mtime check), so a pulled kernel change
     # can never run against a stale library; a box without nvcc (or a read-only tree) uses the shipped .so as it is
     path = _build.LIB_PATH
-    try:
-        path = _build.build(force=os.environ.get("ADER_B200_REBUILD") == "1")
-    except Exception:
-        if not os.path.exists(path):
-            raise
+    alt = os.environ.get("ADER_B200_LIB")       # debug builds (python -m ader_b200.build --timeline): use that file as it is
+    if alt:
+        if not os.path.exists(alt):
+            raise AderError("ADER_B200_LIB=%s does not exist" % alt)
+        path = alt
+    else:
+        try:
+            path = _build.build(force=os.environ.get("ADER_B200_REBUILD") == "1")
+        except Exception:
+            if not os.path.exists(path):
+                raise
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly

@@ -34,17 +34,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: a second library beside the product one (e.g. variant="tl", defines=["-DADER_TC_TIMELINE"] for
+    the phase-stamp debug build, loaded with ADER_B200_LIB=<path>); the default call builds the product library."""
+    lib_path = LIB_PATH if not variant else os.path.join(LIB_DIR, "libader_b200_%s.so" % variant)
+    if not variant and not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + (".o" if not variant else ".%s.o" % variant))
         cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *os.environ.get("ADER_B200_DEFINES", "").split(),
-               "-c", src, "-o", obj]
+               *defines, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,12 +58,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timeline" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv, variant="tl", defines=["-DADER_TC_TIMELINE"]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -61,6 +61,7 @@ struct BwdWs {
   int *keys[2], *vals[2], *hist;
   float* Dv;             // fused path: per-token softmax-backward row dots
   float* spart; int* scount;   // windowed scatter: partial slots [windows][2][SPAD], arrival counters [windows]
+  uint8_t* touched;            // [v_tab] 1 = an input token of this step carries the item (written by the scatter plan)
   float* g2[8];          // fused path: second set of gO..gQ1 (blocks alternate sets, so the weight-gradient kernel of
                          // block b may still read its set while block b-1's data-gradient kernels write the other)
   size_t bytes;
@@ -78,6 +79,7 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
   for (int i = 0; i < 8; ++i) w.g2[i] = (float*)take(sizeof(float) * (size_t)Tcap * m->d);
   w.spart = (float*)take(sizeof(float) * (size_t)cdiv(Tcap, 16) * 2 * 256);
   w.scount = (int*)take(sizeof(int) * (size_t)cdiv(Tcap, 16));
+  w.touched = (uint8_t*)take(align_up((size_t)m->v_tab, 16));
   w.bytes = o;
   return w;
 }
@@ -269,6 +271,64 @@ __global__ void k_lnf_bwd(const float* __restrict__ d_rep, const float* __restri
   int r = tok_row[t];
   long long o = (long long)t * d;
   if (t != row_off[r + 1] - 1) { for (int c = lane; c < d; c += 32) gx[o + c] = 0.f; return; }
+  ln_row_bwd(d_rep + (long long)r * d, x + o, mean[r], rstd[r], gamma, gx + o, d, lane, false);
+}
+
+// The same with the d_rep reduction of the loss group folded in (fused step): warp t < Tcap is token t as above, but the
+// warp of a row's last token first sums the row's split partials (the left-to-right sum of tc::k_reduce_drep, all loads of
+// a trip in flight together) and writes d_rep[row]; warps Tcap.. cover the rows without tokens (d_rep only).  One launch
+// and one L2 round trip less on the critical chain, bit-identical values.
+__global__ void k_lnf_bwd_drep(const DrepFuse df, float* d_rep, const float* __restrict__ x,
+                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ gamma, const int* __restrict__ tok_row,
+                               const int* __restrict__ row_off, const int* __restrict__ row_len, float* __restrict__ gx,
+                               const int* __restrict__ dT, int M, int Tcap, int d) {
+  pdl_wait(); pdl_go();
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int r; long long o = 0; bool do_ln;
+  if (w < Tcap) {
+    if (w >= *dT) return;
+    r = tok_row[w];
+    o = (long long)w * d;
+    if (w != row_off[r + 1] - 1) { for (int c = lane; c < d; c += 32) gx[o + c] = 0.f; return; }
+    do_ln = true;
+  } else {
+    r = w - Tcap;
+    if (r >= M || row_len[r] != 0) return;
+    do_ln = false;
+  }
+  const size_t cs = (size_t)df.rows_pad * df.kp;
+  const float* p0 = df.part + (size_t)r * df.kp + lane;
+  float s[LN_MAXE];
+#pragma unroll
+  for (int e = 0; e < LN_MAXE; ++e) s[e] = 0.f;
+  int k = 0;
+  for (; k + 8 <= df.n_chunks; k += 8) {          // eight chunks x all columns of the row in flight per trip
+    float v[LN_MAXE][8];
+#pragma unroll
+    for (int e = 0; e < LN_MAXE; ++e)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[e][j] = (lane + 32 * e < d) ? __ldcg(p0 + 32 * e + (size_t)(k + j) * cs) : 0.f;
+#pragma unroll
+    for (int e = 0; e < LN_MAXE; ++e)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[e] += v[e][j];
+  }
+  for (; k < df.n_chunks; ++k) {
+#pragma unroll
+    for (int e = 0; e < LN_MAXE; ++e) if (lane + 32 * e < d) s[e] += __ldcg(p0 + 32 * e + (size_t)k * cs);
+  }
+#pragma unroll
+  for (int e = 0; e < LN_MAXE; ++e) {
+    const int c = lane + 32 * e;
+    if (c < d) {
+      float t = s[e];
+      if (df.u && r >= df.n_train) t -= df.u[(size_t)(r - df.u_row0) * df.kp + c];
+      d_rep[(long long)r * d + c] = t;
+    }
+  }
+  if (!do_ln) return;
+  __threadfence_block();        // the row below is read back by the lanes that wrote it
   ln_row_bwd(d_rep + (long long)r * d, x + o, mean[r], rstd[r], gamma, gx + o, d, lane, false);
 }
 
@@ -656,8 +716,15 @@ __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__
 // ------------------------------------------------------------------------------------------
 constexpr int SORT_TILE = 2048;
 
+// start of the plan: arrival counters and the touched-row flags back to zero (a memset node costs ~10 us in a graph)
+__global__ void k_plan_zero(uint4* __restrict__ touched16, int n16, int* __restrict__ scount, int n_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) touched16[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (i < n_count) scount[i] = 0;
+}
+
 __global__ void __launch_bounds__(256) k_sort_hist(const int* __restrict__ keys, const int* __restrict__ dT,
-                                                   int shift, int ntiles, int* __restrict__ hist) {
+                                                   int shift, int ntiles, int* __restrict__ hist, uint8_t* __restrict__ touched) {
   __shared__ int h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -665,7 +732,11 @@ __global__ void __launch_bounds__(256) k_sort_hist(const int* __restrict__ keys,
   const int base = blockIdx.x * SORT_TILE;
   for (int r = 0; r < SORT_TILE / 256; ++r) {
     int i = base + r * 256 + threadIdx.x;
-    if (i < T) atomicAdd(&h[(keys[i] >> shift) & 255], 1);     // integer atomics: order-independent result
+    if (i < T) {
+      const int key = keys[i];
+      atomicAdd(&h[(key >> shift) & 255], 1);                  // integer atomics: order-independent result
+      if (touched) touched[key] = 1;                           // first pass: rows the scatter will add into
+    }
   }
   __syncthreads();
   hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
@@ -751,46 +822,12 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ ke
 // dependent batches instead of fifteen.
 constexpr int SW = 16;
 constexpr int SPAD = 160 > LN_MAXE * 32 ? 160 : LN_MAXE * 32;      // floats per partial slot
+// A run that is a PIECE of a longer segment (a hot item spanning several windows): rare, and kept out of line -- inlined
+// into the 16-fold unrolled window loop it made the kernel 139 KB of code, most of which was only ever jumped over.
 template <int NEL>
-__global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ keys, const int* __restrict__ vals,
-                                                       const int* __restrict__ dT, const float* __restrict__ gx, int d, float scale,
-                                                       float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter) {
-  const int T = *dT;
-  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  const int p0 = w * SW;
-  if (p0 >= T) return;
-  const int n = min(SW, T - p0);
-  const int key_l = (lane < n) ? keys[p0 + lane] : -1;
-  const int val_l = (lane < n) ? vals[p0 + lane] : 0;
-  const int key_prev = (p0 > 0) ? keys[p0 - 1] : -1;
-  const int key_next = (p0 + n < T) ? keys[p0 + n] : -1;
-  float v[SW][NEL];
-#pragma unroll
-  for (int u = 0; u < SW; ++u) {
-    const int tu = __shfl_sync(0xffffffffu, val_l, u);
-    const long long o = (long long)tu * d;
-#pragma unroll
-    for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; v[u][i] = (u < n && c < d) ? gx[o + c] : 0.f; }
-  }
-  float acc[NEL];
-#pragma unroll
-  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
-  int run_start = 0;
-#pragma unroll
-  for (int u = 0; u < SW; ++u) {
-    const int ku = __shfl_sync(0xffffffffu, key_l, u);
-    const int kn = __shfl_sync(0xffffffffu, key_l, (u + 1) & 31);
-    if (u < n) {                                                   // warp-uniform
-#pragma unroll
-      for (int i = 0; i < NEL; ++i) acc[i] += v[u][i];
-      const bool last_in_window = (u + 1 == n);
-      if (last_in_window || kn != ku) {                            // the run [run_start, u] of item ku ends here
-        const bool cont_after = last_in_window && key_next == ku;
-        const bool cont_before = run_start == 0 && key_prev == ku;
-        if (!cont_after && !cont_before) {
-#pragma unroll
-          for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
-        } else {
+__device__ __noinline__ void scatter_piece(const int* __restrict__ keys, int T, int p0, int n, int w, int lane, int ku, int run_start, int u,
+                                           bool cont_before, bool cont_after, const float (&acc)[NEL], float* __restrict__ gtable, int d,
+                                           float scale, float* __restrict__ part, int* __restrict__ counter) {
           float* mine = part + ((long long)w * 2 + (cont_before ? 0 : 1)) * SPAD;
 #pragma unroll
           for (int i = 0; i < NEL; ++i) mine[lane + 32 * i] = acc[i];
@@ -838,10 +875,86 @@ __global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ k
             for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * tot[i]); }
             if (lane == 0) counter[w1] = 0;                        // ready for the next step
           }
+}
+
+template <int NEL>
+__global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ keys, const int* __restrict__ vals,
+                                                       const int* __restrict__ dT, const float* __restrict__ gx, int d, float scale,
+                                                       float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter) {
+  const int T = *dT;
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int p0 = w * SW;
+  if (p0 >= T) return;
+  const int n = min(SW, T - p0);
+  const int key_l = (lane < n) ? keys[p0 + lane] : -1;
+  const int val_l = (lane < n) ? vals[p0 + lane] : 0;
+  const int key_prev = (p0 > 0) ? keys[p0 - 1] : -1;
+  const int key_next = (p0 + n < T) ? keys[p0 + n] : -1;
+  float v[SW][NEL];
+#pragma unroll
+  for (int u = 0; u < SW; ++u) {
+    const int tu = __shfl_sync(0xffffffffu, val_l, u);
+    const long long o = (long long)tu * d;
+#pragma unroll
+    for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; v[u][i] = (u < n && c < d) ? gx[o + c] : 0.f; }
+  }
+  float acc[NEL];
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+  int run_start = 0;
+#pragma unroll
+  for (int u = 0; u < SW; ++u) {
+    const int ku = __shfl_sync(0xffffffffu, key_l, u);
+    const int kn = __shfl_sync(0xffffffffu, key_l, (u + 1) & 31);
+    if (u < n) {                                                   // warp-uniform
+#pragma unroll
+      for (int i = 0; i < NEL; ++i) acc[i] += v[u][i];
+      const bool last_in_window = (u + 1 == n);
+      if (last_in_window || kn != ku) {                            // the run [run_start, u] of item ku ends here
+        const bool cont_after = last_in_window && key_next == ku;
+        const bool cont_before = run_start == 0 && key_prev == ku;
+        if (!cont_after && !cont_before) {
+#pragma unroll
+          for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
+        } else {
+          scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter);
         }
 #pragma unroll
         for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
         run_start = u + 1;
+      }
+    }
+  }
+}
+
+// Fused step with the split table update (f.split_adam): TF1 Adam on the table rows the scatter added into, one warp per
+// sorted position that starts a segment (= one warp per distinct item of the batch).  The other rows 1..V were updated by
+// k_adam_untouched beside the scatter; same arithmetic (adam_update_elem), so the step's bits do not depend on the split.
+__global__ void __launch_bounds__(256) k_adam_touched(const int* __restrict__ keys, const int* __restrict__ dT, int d, int V,
+                                                      const float* __restrict__ gtable, float* __restrict__ theta, float* __restrict__ am,
+                                                      float* __restrict__ av, const int* __restrict__ state, float beta1, float beta2,
+                                                      float eps, float ewc_lambda, const float* __restrict__ fisher,
+                                                      const float* __restrict__ theta_star) {
+  const int p = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (p >= *dT) return;
+  const int key = keys[p];
+  if ((p > 0 && keys[p - 1] == key) || key < 1 || key > V) return;
+  const float lr_t = __int_as_float(state[1]);
+  const long long o = (long long)key * d;
+  for (int c0 = 0; c0 < d; c0 += 128) {          // four elements per lane in flight
+    float g[4], th[4], m[4], v[4], fi[4], ts[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + lane + 32 * i; const bool ok = c < d;
+      g[i] = ok ? gtable[o + c] : 0.f; th[i] = ok ? theta[o + c] : 0.f; m[i] = ok ? am[o + c] : 0.f; v[i] = ok ? av[o + c] : 0.f;
+      fi[i] = (ok && ewc_lambda != 0.f) ? fisher[o + c] : 0.f; ts[i] = (ok && ewc_lambda != 0.f) ? theta_star[o + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + lane + 32 * i;
+      if (c < d) {
+        adam_update_elem(g[i], th[i], m[i], v[i], lr_t, beta1, beta2, eps, ewc_lambda, fi[i], ts[i]);
+        theta[o + c] = th[i]; am[o + c] = m[i]; av[o + c] = v[i];
       }
     }
   }
@@ -914,12 +1027,13 @@ static int run_scatter_plan(const AderModel* m, const EncWs& w, const BwdWs& g, 
   const int* dT = w.row_off + M;
   const int ntiles = sort_tiles(Tcap);
   const int bits = key_bits(m->v_tab);
-  cudaMemsetAsync(g.scount, 0, sizeof(int) * (size_t)cdiv(Tcap, SW), st);
+  const int n16 = cdiv(m->v_tab, 16), n_count = cdiv(Tcap, SW);
+  k_plan_zero<<<cdiv(n16 > n_count ? n16 : n_count, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(g.touched), n16, g.scount, n_count);
   int cur = 0;
   const int* kin = w.tok_id; const int* vin = nullptr;
   int pass = 0;
   for (int shift = 0; shift < bits; shift += 8, ++pass) {
-    k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist);
+    k_sort_hist<<<ntiles, 256, 0, st>>>(kin, dT, shift, ntiles, g.hist, pass == 0 ? g.touched : nullptr);
     k_sort_scan<<<1, 1024, 0, st>>>(g.hist, 256 * ntiles);
     k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
     kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
@@ -938,6 +1052,18 @@ static int run_scatter_apply(const AderModel* m, const Layout& l, const EncWs& w
   else
     k_scatter_apply<LN_MAXE><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount);
   ADER_CHECK_LAUNCH("scatter apply");
+  return 0;
+}
+// Adam on the touched table rows (behind the scatter, split update)
+static int run_adam_touched(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, int M, int Tcap, const AdamPlan& ap,
+                            cudaStream_t st) {
+  const int fin = (sort_passes(m) - 1) & 1;
+  k_adam_touched<<<cdiv((long long)Tcap * 32, 256), 256, 0, st>>>(g.keys[fin], w.row_off + M, m->d, ap.a.V, ap.grad + l.off_table,
+                                                                 ap.theta + l.off_table, ap.m + l.off_table, ap.v + l.off_table, ap.state,
+                                                                 ap.a.beta1, ap.a.beta2, ap.a.eps, ap.a.ewc_lambda,
+                                                                 ap.a.fisher ? ap.a.fisher + l.off_table : nullptr,
+                                                                 ap.a.theta_star ? ap.a.theta_star + l.off_table : nullptr);
+  ADER_CHECK_LAUNCH("adam table (touched rows)");
   return 0;
 }
 static int run_table_scatter(const AderModel* m, const Layout& l, const EncWs& w, const BwdWs& g, const float* gX,
@@ -1451,6 +1577,7 @@ static void fused_attrs() {
   cudaFuncSetAttribute(fz::k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::FFN_BWD_SMEM);
   cudaFuncSetAttribute(fz::k_qkv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::QKV_BWD_SMEM);
   cudaFuncSetAttribute(fz::k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::WGRAD_SMEM);
+  cudaFuncSetAttribute(fz::k_wgrad2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::WGRAD2_SMEM);
   cudaFuncSetAttribute(fz::k_attn_ln_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * fz::att_rows_cap(64) * fz::KP * 4);
   cudaFuncSetAttribute(fz::k_attn_bwd_s1, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::att_bwd_smem(64, fz::KP));
   cudaFuncSetAttribute(fz::k_attn_ln_fwd_team, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::att_tile_smem(64));
@@ -1570,6 +1697,15 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   return 0;
 }
 
+// weight / LayerNorm-parameter gradient launch: second generation (two 4-warp CTAs per GEMM problem and split, bulk-copied
+// tiles) unless ADER_B200_WGRAD=1
+static void launch_wgrad(const fz::WgradArgs& wa, int splits, cudaStream_t st) {
+  static int gen = -1;
+  if (gen < 0) { const char* e = getenv("ADER_B200_WGRAD"); gen = (e && e[0] == '1') ? 1 : 2; }
+  if (gen == 1) fz::k_wgrad<<<dim3(splits, wa.n_gemm + wa.n_ln), fz::NTHR, fz::WGRAD_SMEM, st>>>(wa);
+  else fz::k_wgrad2<<<dim3(splits, 2 * wa.n_gemm + wa.n_ln), fz::WG2_THR, fz::WGRAD2_SMEM, st>>>(wa);
+}
+
 int ader::enc_scatter_plan_run(const AderModel* m, int M, int Tcap, const void* ws, void* bwd_ws, Fork& f) {
   if (!f.parallel() || !f.has_tok_ready) return 0;
   EncWs w = carve_enc(m, M, Tcap, (char*)ws);
@@ -1581,6 +1717,8 @@ int ader::enc_scatter_plan_run(const AderModel* m, int M, int Tcap, const void* 
   f.plan_done = true;
   return 0;
 }
+
+bool ader::enc_chain_enabled(const AderModel* m) { return chain_ok(m); }
 
 extern "C" int32_t ader_encoder_bwd_tc(const AderModel* m, const float* theta, const int32_t* ids, int32_t M,
                                        int32_t Tcap, const void* ws, void* bwd_ws, const float* d_rep, float* grad,
@@ -1620,11 +1758,22 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   // one launch behind the data-gradient kernel (10 problems x 14 splits = 140 CTAs, one wave)
   const int splits = chained ? CHAIN_SPLITS : SPLITS;
   // final LayerNorm: data gradient on the chain, parameter gradient beside it
-  f.edge(st, f.c);
-  k_ln_param_grad<<<splits, dim3(ln_threads, PG_LANES), 0, f.c>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
-                                                 part(l.off_lnf), part(l.off_lnf + d), PS);
+  const bool drep_here = f.has_drep && !chained;      // the loss group left the d_rep reduction to the kernel below
+  if (f.has_drep && chained) return fail(-3, "encoder_bwd_tc: d_rep partials handed to the chained path");
+  auto ln_params = [&] {
+    f.edge(st, f.c);
+    k_ln_param_grad<<<splits, dim3(ln_threads, PG_LANES), 0, f.c>>>(d_rep, w.xfinal, w.meanf, w.rstdf, dT, M, w.row_len, w.row_off, d,
+                                                   part(l.off_lnf), part(l.off_lnf + d), PS);
+  };
+  if (!drep_here) ln_params();
   fz::ChainBwdArgs ca;
-  if (!chained) {
+  if (drep_here) {
+    launch_chain(k_lnf_bwd_drep, dim3(cdiv((long long)(Tcap + M) * 32, 256)), dim3(256), 0, st, f.pdl, f.drep, const_cast<float*>(d_rep),
+                 (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf, theta + l.off_lnf + d, (const int*)w.tok_row,
+                 (const int*)w.row_off, (const int*)w.row_len, chain[0], dT, M, Tcap, d);
+    ADER_CHECK_LAUNCH("encoder_bwd_tc/final_ln+d_rep");
+    ln_params();
+  } else if (!chained) {
     // directly behind the d_rep reduction on f.main in the fused step (f.pdl is only set there)
     launch_chain(k_lnf_bwd, dim3(ln_grid), dim3(256), 0, st, f.pdl, d_rep, (const float*)w.xfinal, (const float*)w.meanf, (const float*)w.rstdf,
                  theta + l.off_lnf + d, (const int*)w.tok_row, (const int*)w.row_off, chain[0], dT, d);
@@ -1682,15 +1831,15 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     // most of that work is done while the data-gradient chain is still running
     launch_chain(fz::k_ffn_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::FFN_BWD_SMEM, st, f.pdl && !joined, fa);
     f.edge(st, f.wg[0]);
-    fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa[0]);
+    launch_wgrad(wa[0], SPLITS, f.wg[0]);
     if (m->num_heads == 1) launch_chain(fz::k_attn_bwd_s1, dim3(cdiv(Tcap, fz::ATT_TOK)), dim3(256), (size_t)fz::att_bwd_smem(L, d), st, f.pdl, ab);
     else fz::k_attn_bwd_w<<<ln_grid, 256, 0, st>>>(ab);
     f.edge(st, f.wg[1]);
-    fz::k_wgrad<<<dim3(SPLITS, 3), fz::NTHR, fz::WGRAD_SMEM, f.wg[1]>>>(wa[1]);
+    launch_wgrad(wa[1], SPLITS, f.wg[1]);
     launch_chain(fz::k_qkv_bwd, dim3(tile_grid), dim3(fz::NTHR), fz::QKV_BWD_SMEM, st, f.pdl, qb);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/dgrad");
     f.edge(st, f.wg[2]);
-    fz::k_wgrad<<<dim3(SPLITS, 1), fz::NTHR, fz::WGRAD_SMEM, f.wg[2]>>>(wa[2]);
+    launch_wgrad(wa[2], SPLITS, f.wg[2]);
     ADER_CHECK_LAUNCH("encoder_bwd_tc/wgrad");
     if (f.parallel())
       for (int k = 0; k < 3; ++k) { wg_done[b][k] = f.take(); cudaEventRecord(wg_done[b][k], f.wg[k]); }
@@ -1710,7 +1859,7 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
     }
     wa.n_gemm = np; wa.n_ln = 0; wa.dT = dT; wa.d = d; wa.split_stride = PS;
     f.edge(st, f.wg[0]);
-    fz::k_wgrad<<<dim3(splits, np), fz::NTHR, fz::WGRAD_SMEM, f.wg[0]>>>(wa);
+    launch_wgrad(wa, splits, f.wg[0]);
     for (int k = 1; k < 3; ++k) {             // LayerNorm-parameter gradients of the blocks beside it
       f.edge(st, f.wg[k]);
       for (int b = m->num_blocks - 1; b >= 0; --b) {
@@ -1723,8 +1872,34 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   }
   const float* gX0 = chain[ci % 3];          // gradient w.r.t. the (dropout-masked) embedding output
 
+  // Issue order of the tail = launch order of the graph nodes that become ready together when the chain ends: the
+  // latency-bound scatter first, the bulk kernels (table Adam, position-table reduction) behind it -- a 5 000-CTA grid
+  // issued first would sit in front of the scatter's 30 CTAs in the block scheduler.
+  cudaEvent_t chain_end = nullptr;           // the data-gradient chain has produced gX0 (side work below waits for this, not
+  if (f.parallel()) { chain_end = f.take(); cudaEventRecord(chain_end, st); }   // for the scatter issued in front of it)
+  // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
+  if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);
+  // Split table update (f.split_adam): the rows no token touches have their final gradient since the dE kernel, so their
+  // Adam pass (HBM-bound) runs on f.b BESIDE the scatter (latency-bound) once the data-gradient chain has ended -- started
+  // earlier it only slowed the chain kernels down (measured) -- and the touched rows follow the scatter, one warp per item.
+  const bool split = f.adam && f.split_adam && f.plan_done && f.has_table_ready && f.parallel();
+  if (f.plan_done) {
+    cudaStreamWaitEvent(st, f.plan_ready, 0);
+    if (int e = run_scatter_apply(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  } else if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
+  if (f.adam) {                              // ... and the item-table rows here
+    cudaStreamWaitEvent(st, f.adam->prep_ready, 0);
+    if (split) { if (int e = run_adam_touched(m, l, w, g, M, Tcap, *f.adam, st)) return e; }
+    else if (int e = adam_table_part(m, *f.adam, st)) return e;
+  }
+  if (split) {
+    cudaStreamWaitEvent(f.b, chain_end, 0);  // f.b carries the dE kernel: stream order covers the gradient
+    cudaStreamWaitEvent(f.b, f.plan_ready, 0);
+    cudaStreamWaitEvent(f.b, f.adam->prep_ready, 0);
+    if (int e = adam_table_untouched(m, *f.adam, g.touched, f.b)) return e;
+  }
   // position table (ADER.py:41-52) beside the scatter; then all split partials -> dense gradients in fixed order
-  f.edge(st, f.c);
+  if (chain_end) cudaStreamWaitEvent(f.c, chain_end, 0);
   k_pos_grad<<<dim3(L, splits), dim3(ln_threads, PG_LANES), 0, f.c>>>(gX0, w.row_len, w.row_off, M, L, d, 0.f, 0, nullptr, g.partial, PS);
   f.edge(f.c, f.a);
   f.edge(f.wg[1], f.a);
@@ -1738,16 +1913,6 @@ int ader::enc_bwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
                                                            ap.a.theta_star ? ap.a.theta_star + l.off_pos : nullptr);
   } else {
     k_reduce_partials<<<cdiv(PS, 256), 256, 0, f.a>>>(g.partial, PS, splits, 0, PS, grad + l.off_pos);
-  }
-  // item-table scatter (modules.py:127-130): adds to the rows the dE kernel wrote
-  if (f.has_table_ready) cudaStreamWaitEvent(st, f.table_ready, 0);
-  if (f.plan_done) {
-    cudaStreamWaitEvent(st, f.plan_ready, 0);
-    if (int e = run_scatter_apply(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
-  } else if (int e = run_table_scatter(m, l, w, g, gX0, M, Tcap, grad, st)) return e;
-  if (f.adam) {                              // ... and the item-table rows here
-    cudaStreamWaitEvent(st, f.adam->prep_ready, 0);
-    if (int e = adam_table_part(m, *f.adam, st)) return e;
   }
   f.edge(f.a, st);
   ADER_CHECK_LAUNCH("encoder_bwd_tc/embedding");

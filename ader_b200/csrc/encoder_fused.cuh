@@ -1249,7 +1249,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
 // ---- backward: weight / bias / LayerNorm-parameter gradients of one block, ONE launch ------------------
 // dW[c_in][c_out] = sum_t act[t][c_in] * grad[t][c_out] is a [150 x T] x [T x 150] product whose contraction
 // runs over tokens.  TF32 mma.sync.m16n8k8: both operands are read straight from their natural [t][c] fp32
-// layout (cp.async double-buffered token tiles, row stride 168 words -> conflict-free fragment loads), no
+// layout (cp.async token tiles in a ring of WG_NST stages, row stride 168 words -> conflict-free fragment loads), no
 // transposes and no range scaling (8-bit exponent), 10-bit mantissa.  CTA (split, problem) owns a contiguous
 // range of token tiles and a full 160 x 160 fp32 accumulator in registers (8 warps x 5 x 5 mma tiles); the
 // `splits` partials are reduced afterwards in index order (k_reduce_partials) -> deterministic.
@@ -1258,12 +1258,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_qkv_bwd(const __grid_constant__ Qkv
 constexpr int WG_TK = 32;                     // tokens per staged tile
 constexpr int WG_LD = 168;                    // fp32 row stride (168 % 32 == 8)
 constexpr int WG_TILE = WG_TK * WG_LD;        // floats per operand tile
-constexpr size_t WGRAD_SMEM = sizeof(float) * 4 * WG_TILE;   // 2 stages x (act, grad) = 86 016 B
+constexpr int WG_NST = 5;                     // ring depth: a CTA's whole token range (T/21 splits ~ 5 tiles at the reference's
+                                              // batch sizes) is in flight at once; with two stages every tile paid its own
+                                              // L2 round trip.  (229 registers x 256 threads already keep every other CTA
+                                              // of the step off the SM, so the 215 KB cost no co-residency.)
+constexpr size_t WGRAD_SMEM = sizeof(float) * 2 * WG_NST * WG_TILE;   // stages x (act, grad) = 215 040 B
 constexpr int WG_MAXP = 10;                   // problems of one launch (chained path: the 5 matrices of 2 blocks)
 struct WgradProb { const float *act, *grad, *mean, *rstd; float *out0, *out1; };   // GEMM: out0 = pW, out1 = pb; LN: out0 = pbeta, out1 = pgamma
 struct WgradArgs { WgradProb p[WG_MAXP]; int n_gemm, n_ln; const int* dT; int d; long long split_stride; };
 
-__device__ __forceinline__ uint32_t to_tf32(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return r; }
+// fp32 -> tf32, round to nearest with ties away from zero: cvt.rna.tf32.f32 as ONE integer add on the bit pattern (half an
+// ulp of the 10-bit mantissa added to the magnitude; the tensor core ignores the low 13 bits, so they need no masking).
+// Same operand values as the conversion instruction for every finite input, but on the full-rate integer pipe: the 30
+// conversions per 25 mma of a k-step cost as much issue time as the products themselves.
+__device__ __forceinline__ uint32_t to_tf32(float v) { return __float_as_uint(v) + 0x1000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -1278,6 +1286,12 @@ __device__ __forceinline__ void wg_stage(float* __restrict__ dst, const float* _
   }
 }
 
+#ifdef ADER_TC_TIMELINE      // stamps of problem 0 of the last GEMM launch (rows 0..) and the last LayerNorm-only launch (rows 64..)
+#define WG_TL(slot) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    g_fz_tl[7][blockIdx.x + (is_ln ? 64 : 0)][slot] = t_; } } while (0)
+#else
+#define WG_TL(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(16) float wsm[];
   const int T = *a.dT, d = a.d;
@@ -1295,19 +1309,29 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ Wgrad
 #pragma unroll
     for (int j = 0; j < 5; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
   float cs0 = 0.f, cs1 = 0.f;                        // column sums owned by thread tid < 160
-  if (tile_lo < tile_hi) {
-    wg_stage(wsm, pr.act, tile_lo * WG_TK, T, d);
-    wg_stage(wsm + WG_TILE, pr.grad, tile_lo * WG_TK, T, d);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int tile = tile_lo; tile < tile_hi; ++tile) {
-    const int buf = (tile - tile_lo) & 1;
-    if (tile + 1 < tile_hi) {
-      wg_stage(wsm + (buf ^ 1) * 2 * WG_TILE, pr.act, (tile + 1) * WG_TK, T, d);
-      wg_stage(wsm + (buf ^ 1) * 2 * WG_TILE + WG_TILE, pr.grad, (tile + 1) * WG_TK, T, d);
+  WG_TL(0);
+  // prologue: WG_NST - 1 tiles in flight (one commit group per tile, empty groups keep the count uniform)
+#pragma unroll
+  for (int s = 0; s < WG_NST - 1; ++s) {
+    if (tile_lo + s < tile_hi) {
+      wg_stage(wsm + s * 2 * WG_TILE, pr.act, (tile_lo + s) * WG_TK, T, d);
+      wg_stage(wsm + s * 2 * WG_TILE + WG_TILE, pr.grad, (tile_lo + s) * WG_TK, T, d);
     }
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    const int buf = (tile - tile_lo) % WG_NST;
+    {   // refill the stage the previous iteration released (its readers passed the barrier at the end of that iteration)
+      const int nt = tile + WG_NST - 1, nb = (nt - tile_lo) % WG_NST;
+      if (nt < tile_hi) {
+        wg_stage(wsm + nb * 2 * WG_TILE, pr.act, nt * WG_TK, T, d);
+        wg_stage(wsm + nb * 2 * WG_TILE + WG_TILE, pr.grad, nt * WG_TK, T, d);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(WG_NST - 1) : "memory");
     __syncthreads();
+    if (tile - tile_lo < 6) WG_TL(1 + (tile - tile_lo));
     const float* As = wsm + buf * 2 * WG_TILE;
     const float* Bs = As + WG_TILE;
     if (!is_ln) {
@@ -1331,17 +1355,27 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ Wgrad
         for (int r = 0; r < WG_TK; ++r) cs0 += Bs[r * WG_LD + tid];
       }
     } else if (tid < KP) {                            // LayerNorm parameter gradients
+      // rows beyond T were zero-filled by the staging copy (gq = 0 contributes +-0: the sums keep their bits), so the loop
+      // runs over the whole tile and the statistics of eight rows are fetched together instead of one L2 trip per row
       const int t0 = tile * WG_TK;
-      const int rmax = min(WG_TK, T - t0);
-      for (int r = 0; r < rmax; ++r) {
-        const float gq = Bs[r * WG_LD + tid];
-        cs0 += gq;
-        cs1 += gq * ((As[r * WG_LD + tid] - pr.mean[t0 + r]) * pr.rstd[t0 + r]);
+#pragma unroll
+      for (int r8 = 0; r8 < WG_TK; r8 += 8) {
+        float mu[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int t = min(t0 + r8 + j, T - 1); mu[j] = __ldg(pr.mean + t); rs[j] = __ldg(pr.rstd + t); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r8 + j;
+          const float gq = Bs[r * WG_LD + tid];
+          cs0 += gq;
+          cs1 += gq * ((As[r * WG_LD + tid] - mu[j]) * rs[j]);
+        }
       }
     }
     __syncthreads();
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  WG_TL(8);
   const long long so = (long long)blockIdx.x * a.split_stride;
   if (!is_ln) {
 #pragma unroll
@@ -1358,6 +1392,166 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ Wgrad
   } else if (tid < d) {
     pr.out0[so + tid] = cs0;
     pr.out1[so + tid] = cs1;
+  }
+  WG_TL(9);
+}
+
+
+// ---- second generation of the weight-gradient kernel (default; ADER_B200_WGRAD=1 selects k_wgrad above) -----------------
+// Phase stamps of k_wgrad (scripts/wgrad_timeline.py, profiles/r2/wgrad_phase_timeline.txt): 6 us from entry to the first
+// tile (25 600 8-byte cp.async per CTA: issue-bound), 1.35 us per 32-token tile (tensor pipe 0.92), 2.75 us for the
+// fragment-scattered partial stores.  Here
+//   * a tile operand is ONE cp.async.bulk of the contiguous [32 tokens][d] block (19 200 B) completing on an mbarrier, the
+//     whole token range of the CTA in flight from the start;
+//   * shared-memory rows keep the global stride d, and the k slots of a k-step are mapped to tile rows so that the four
+//     rows one fragment load touches are 4 apart (4 * 150 = 24 mod 32 banks): conflict-free without padding.  Summation
+//     over k does not care which token sits in which slot as long as A and B agree;
+//   * a (split, problem) is TWO CTAs of 4 warps, each owning 160 x 80 of the result (the tensor pipe of an SM is saturated by
+//     4 warps with 25 independent accumulators each), so a launch of 3 problems x 21 splits covers 126 SMs instead of 63 and
+//     the per-CTA product time halves;
+//   * partials leave through shared memory as coalesced 8-byte row stores.
+// Same token splits and the same fixed-order reduction afterwards: deterministic; bias and LayerNorm-parameter sums keep
+// their exact order (bit-identical to k_wgrad), the weight products differ in the order of additions inside a k-step only.
+constexpr int WG2_THR = 128;
+constexpr int WG2_NST = 5;
+constexpr int WG2_OPB = WG_TK * KP * 4;                      // bytes of one operand slot (d <= 160)
+constexpr int WG2_STG_LD = 88;                               // staging row stride of the 160 x 80 result block
+constexpr size_t WGRAD2_SMEM = (size_t)WG2_NST * 2 * WG2_OPB + 64;
+static_assert(160 * WG2_STG_LD * 4 <= WG2_NST * 2 * WG2_OPB, "result staging must fit the ring");
+
+__global__ void __launch_bounds__(WG2_THR) k_wgrad2(const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(128) float wsm[];
+  const int T = *a.dT, d = a.d;
+  const int ntiles = (T + WG_TK - 1) / WG_TK;
+  const int chunk = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int tile_lo = blockIdx.x * chunk, tile_hi = min(ntiles, tile_lo + chunk);
+  const int n_my = max(tile_hi - tile_lo, 0);
+  const bool is_ln = (int)blockIdx.y >= 2 * a.n_gemm;
+  const int prob = is_ln ? a.n_gemm + ((int)blockIdx.y - 2 * a.n_gemm) : ((int)blockIdx.y >> 1);
+  const int half = is_ln ? 0 : ((int)blockIdx.y & 1);
+  const WgradProb pr = a.p[prob];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;           // warp block: rows wm*80.., columns half*80 + wn*40..
+  const uint32_t bar0 = smem_u32(reinterpret_cast<char*>(wsm) + (size_t)WG2_NST * 2 * WG2_OPB);
+  const uint32_t op_bytes_full = (uint32_t)(WG_TK * d * 4);
+  auto issue = [&](int li) {                         // thread 0: both operands of local tile li into stage li % NST
+    const int t0 = (tile_lo + li) * WG_TK;
+    const int rv = min(WG_TK, T - t0) & ~1;          // bulk copies move whole 16-byte units: an even number of rows
+    const uint32_t bytes = (uint32_t)(rv * d * 4);
+    const int s = li % WG2_NST;
+    const uint32_t bar = bar0 + 8 * s;
+    mbar_expect_tx(bar, 2 * bytes);
+    if (bytes) {
+      const uint32_t dst = smem_u32(reinterpret_cast<char*>(wsm) + (size_t)s * 2 * WG2_OPB);
+      bulk_g2s(dst, pr.act + (long long)t0 * d, bytes, bar);
+      bulk_g2s(dst + WG2_OPB, pr.grad + (long long)t0 * d, bytes, bar);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < WG2_NST; ++s) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int li = 0; li < n_my && li < WG2_NST; ++li) issue(li);
+  }
+  float acc[5][5][4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
+  float cs0[2] = {0.f, 0.f}, cs1[2] = {0.f, 0.f};    // GEMM: [0] = bias column half*80 + tid (tid < 80); LN: columns tid, tid + 128
+  __syncthreads();                                   // barrier words initialised before anyone waits on them
+  (void)op_bytes_full;
+#pragma unroll 1
+  for (int li = 0; li < n_my; ++li) {
+    const int s = li % WG2_NST;
+    float* As = reinterpret_cast<float*>(reinterpret_cast<char*>(wsm) + (size_t)s * 2 * WG2_OPB);
+    float* Bs = reinterpret_cast<float*>(reinterpret_cast<char*>(As) + WG2_OPB);
+    const int t0 = (tile_lo + li) * WG_TK;
+    const int rv = min(WG_TK, T - t0);
+    if (rv < WG_TK) {                                // last tile of the batch: odd last row by hand, rows beyond T zero
+      const int re = rv & ~1;
+      for (int idx = tid; idx < (WG_TK - re) * d; idx += WG2_THR) {
+        const int r = re + idx / d, c = idx % d;
+        const bool ok = r < rv;
+        As[r * d + c] = ok ? pr.act[(long long)(t0 + r) * d + c] : 0.f;
+        Bs[r * d + c] = ok ? pr.grad[(long long)(t0 + r) * d + c] : 0.f;
+      }
+      __syncthreads();
+    }
+    mbar_wait(bar0 + 8 * s, (uint32_t)(li / WG2_NST) & 1u);
+    if (!is_ln) {
+#pragma unroll
+      for (int ks = 0; ks < WG_TK / 8; ++ks) {
+        // k slot t4 <-> tile row R + 2q + 4*t4, k slot t4 + 4 <-> the row below it (R = 16 * (ks / 2), q = ks % 2)
+        const int row = (ks >> 1) * 16 + (ks & 1) * 2 + 4 * t4;
+        const float* ar = As + row * d + wm * 80 + g;
+        const float* br = Bs + row * d + half * 80 + wn * 40 + g;
+        uint32_t bf[5][2];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { bf[j][0] = to_tf32(br[j * 8]); bf[j][1] = to_tf32(br[d + j * 8]); }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const uint32_t a0 = to_tf32(ar[i * 16]), a1 = to_tf32(ar[i * 16 + 8]);
+          const uint32_t a2 = to_tf32(ar[d + i * 16]), a3 = to_tf32(ar[d + i * 16 + 8]);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+        }
+      }
+      const int c = half * 80 + tid;
+      if (tid < 80 && c < d) {                        // bias gradient: column sums of grad, token order
+#pragma unroll 8
+        for (int r = 0; r < WG_TK; ++r) cs0[0] += Bs[r * d + c];
+      }
+    } else {                                          // LayerNorm parameter gradients (rows beyond T are zero: gq = 0)
+#pragma unroll
+      for (int r8 = 0; r8 < WG_TK; r8 += 8) {
+        float mu[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int t = min(t0 + r8 + j, T - 1); mu[j] = __ldg(pr.mean + t); rs[j] = __ldg(pr.rstd + t); }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = tid + q * WG2_THR;
+          if (c < d) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gq = Bs[(r8 + j) * d + c];
+              cs0[q] += gq;
+              cs1[q] += gq * ((As[(r8 + j) * d + c] - mu[j]) * rs[j]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                  // every reader of stage s is done: refill it
+    if (tid == 0 && li + WG2_NST < n_my) issue(li + WG2_NST);
+  }
+  const long long so = (long long)blockIdx.x * a.split_stride;
+  if (!is_ln) {
+    // 160 x 80 block -> shared memory (the ring is idle: every copy was waited for) -> coalesced 8-byte row stores
+    float* stg = wsm;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int m = wm * 80 + i * 16 + g, n = wn * 40 + j * 8 + 2 * t4;
+        *reinterpret_cast<float2*>(stg + m * WG2_STG_LD + n) = make_float2(acc[i][j][0], acc[i][j][1]);
+        *reinterpret_cast<float2*>(stg + (m + 8) * WG2_STG_LD + n) = make_float2(acc[i][j][2], acc[i][j][3]);
+      }
+    __syncthreads();
+    const int ncol2 = min(80, d - half * 80) / 2;     // float2 columns of this half that exist (d is even)
+    float* out = pr.out0 + so + half * 80;
+    for (int f = tid; f < d * 40; f += WG2_THR) {
+      const int m = f / 40, c2 = f % 40;
+      if (c2 < ncol2) *reinterpret_cast<float2*>(out + (long long)m * d + 2 * c2) = *reinterpret_cast<const float2*>(stg + m * WG2_STG_LD + 2 * c2);
+    }
+    const int c = half * 80 + tid;
+    if (tid < 80 && c < d) pr.out1[so + c] = cs0[0];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = tid + q * WG2_THR;
+      if (c < d) { pr.out0[so + c] = cs0[q]; pr.out1[so + c] = cs1[q]; }
+    }
   }
 }
 

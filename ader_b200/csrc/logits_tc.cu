@@ -858,9 +858,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc2(TcArgs a, const __grid_cons
 }
 
 // fp32 rows -> row-major bf16 [rows_pad][160] (rows >= n_rows and columns >= d are zero): the HBM operand of the tc2 kernels
+// (zero4: four flag words cleared on the way -- a memset node in front of this kernel costs ~10 us in a graph)
 __global__ void k_pack_rows16(const float* __restrict__ src, long long ld, int n_rows, int d, int rows_pad,
-                              __nv_bfloat16* __restrict__ out) {
+                              __nv_bfloat16* __restrict__ out, int* __restrict__ zero4) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (zero4 && idx < 4) zero4[idx] = 0;
   const long long total = (long long)rows_pad * (ROW16 / 8);
   if (idx >= total) return;
   const int kc = (int)(idx % (ROW16 / 8));
@@ -1221,10 +1223,10 @@ static void launch_teacher_u(const AderLossArgs* a, const TcWs& w, const TcArgs&
   launch_reduce_u(a, w, rep, d, st);
 }
 // operand packing of either generation: fp32 rows -> bf16 (T128 tiles, or the row-major matrix the tensor maps describe)
-static void launch_pack(const float* src, long long ld, int n_rows, int d, int n_tiles, uint8_t* out, cudaStream_t st) {
+static void launch_pack(const float* src, long long ld, int n_rows, int d, int n_tiles, uint8_t* out, cudaStream_t st, int* zero4 = nullptr) {
   if (tc_gen() == 2)
     k_pack_rows16<<<cdiv((long long)n_tiles * TILE * (ROW16 / 8), 256), 256, 0, st>>>(src, ld, n_rows, d, n_tiles * TILE,
-                                                                                      reinterpret_cast<__nv_bfloat16*>(out));
+                                                                                      reinterpret_cast<__nv_bfloat16*>(out), zero4);
   else
     k_pack_tiles<<<cdiv((long long)n_tiles * TILE * (KP / 8), 256), 256, 0, st>>>(src, ld, n_rows, d, n_tiles, out);
 }
@@ -1300,8 +1302,8 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
     return 0;
   }
   if (phase_mask & 1) {
-    cudaMemsetAsync(w.err, 0, sizeof(int) * 4, sb);
-    launch_pack(theta + d, d, V, d, nv, w.e_tiles, sb);
+    if (g2) launch_pack(theta + d, d, V, d, nv, w.e_tiles, sb, w.err);       // clears the error words on the way
+    else { cudaMemsetAsync(w.err, 0, sizeof(int) * 4, sb); launch_pack(theta + d, d, V, d, nv, w.e_tiles, sb); }
     if (kd) launch_teacher_tu(a, w, t, 0, sb, g2 ? &mp : nullptr);
     ADER_CHECK_LAUNCH("tc prep");
   }
@@ -1325,8 +1327,13 @@ int ader::loss_tc_run(const AderModel* m, const float* theta, const float* rep, 
   if (d_rep) {
     if (g2) launch_chain(k_tc2<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_tc2(MODE_DREP), st, f.pdl, t, mp.rep, mp.e, mp.pt);
     else launch_chain(k_tc_logits<MODE_DREP>, dim3(nm * nc), dim3(NTHREADS), (size_t)smem_bwd, st, f.pdl, t);
-    launch_chain(k_reduce_drep, dim3(cdiv((long long)M * d, 256)), dim3(256), 0, st, f.pdl, (const float*)w.drep_part, nc, nm * TILE, M, d, d_rep,
-                 (const float*)(kd ? w.u : nullptr), w.x0_t, a->n_train);
+    if (f.fuse_drep) {        // fused step: the final-LayerNorm backward kernel sums the partials (encoder.cu, k_lnf_bwd_drep)
+      f.drep.part = w.drep_part; f.drep.u = kd ? w.u : nullptr; f.drep.n_chunks = nc; f.drep.rows_pad = nm * TILE; f.drep.kp = KP;
+      f.drep.u_row0 = w.x0_t * TILE; f.drep.n_train = a->n_train;
+      f.has_drep = true;
+    } else
+      launch_chain(k_reduce_drep, dim3(cdiv((long long)M * d, 256)), dim3(256), 0, st, f.pdl, (const float*)w.drep_part, nc, nm * TILE, M, d, d_rep,
+                   (const float*)(kd ? w.u : nullptr), w.x0_t, a->n_train);
     ADER_CHECK_LAUNCH("tc d_rep");
   }
   if (grad) {

@@ -69,6 +69,13 @@ static int run_step(const AderModel* m, const float* theta, const int32_t* ids, 
   }
   static const int pdl = env_flag("ADER_B200_PDL", 1);
   f.pdl = pdl != 0;
+  // ADER_B200_SPLIT_ADAM=1: Adam on the table rows no token touches beside the scatter, on the touched rows behind it
+  // (measured slower: the HBM-bound pass slows the latency-bound tail kernels it runs beside, so the default is ONE Adam
+  // launch over the table behind the scatter); ADER_B200_FUSE_DREP=0: the stand-alone d_rep reduction kernel.  All forms
+  // produce the same bits.
+  static const int split_adam = env_flag("ADER_B200_SPLIT_ADAM", 0), fuse_drep = env_flag("ADER_B200_FUSE_DREP", 1);
+  f.split_adam = f.parallel() && adam && split_adam;
+  f.fuse_drep = f.parallel() && fuse_drep && d_rep && !enc_chain_enabled(m);
   // teacher products / table tiles need nothing from the encoder: start them first, beside it
   f.edge(f.main, f.b);
   if (int e = loss_tc_run(m, theta, nullptr, a, loss_ws, nullptr, nullptr, nullptr, grad, f, 1)) return e;
