@@ -62,6 +62,7 @@ struct BwdWs {
   float* Dv;             // fused path: per-token softmax-backward row dots
   float* spart; int* scount;   // windowed scatter: partial slots [windows][2][SPAD], arrival counters [windows]
   uint8_t* touched;            // [v_tab] 1 = an input token of this step carries the item (written by the scatter plan)
+  int2* sbounds;               // [windows] segment head of a window's first run / segment end of its last run (scatter plan)
   float* g2[8];          // fused path: second set of gO..gQ1 (blocks alternate sets, so the weight-gradient kernel of
                          // block b may still read its set while block b-1's data-gradient kernels write the other)
   size_t bytes;
@@ -80,6 +81,7 @@ static BwdWs carve_bwd(const AderModel* m, int M, int Tcap, char* base) {
   w.spart = (float*)take(sizeof(float) * (size_t)cdiv(Tcap, 16) * 2 * 256);
   w.scount = (int*)take(sizeof(int) * (size_t)cdiv(Tcap, 16));
   w.touched = (uint8_t*)take(align_up((size_t)m->v_tab, 16));
+  w.sbounds = (int2*)take(sizeof(int2) * (size_t)cdiv(Tcap, 16));
   w.bytes = o;
   return w;
 }
@@ -656,11 +658,21 @@ __global__ void k_reduce_partials_adam(const float* __restrict__ partial, long l
                                        float ewc_lambda, const float* __restrict__ fisher, const float* __restrict__ theta_star) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += partial[(long long)k * stride + i];
-  gout[i] = s;
   const float lr_t = __int_as_float(state[1]);
-  adam_update_elem(s, theta[i], am[i], av[i], lr_t, beta1, beta2, eps, ewc_lambda, fisher ? fisher[i] : 0.f, theta_star ? theta_star[i] : 0.f);
+  float th = theta[i], m1 = am[i], v1 = av[i];        // in flight with the partials
+  float s = 0.f;
+  int k = 0;
+  for (; k + 8 <= splits; k += 8) {                   // left-to-right sum, eight loads in flight per trip
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = partial[(long long)(k + j) * stride + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; k < splits; ++k) s += partial[(long long)k * stride + i];
+  gout[i] = s;
+  adam_update_elem(s, th, m1, v1, lr_t, beta1, beta2, eps, ewc_lambda, fisher ? fisher[i] : 0.f, theta_star ? theta_star[i] : 0.f);
+  theta[i] = th; am[i] = m1; av[i] = v1;
   if (i == 0) state[0] += 1;
 }
 
@@ -682,6 +694,9 @@ __global__ void k_pos_grad(const float* __restrict__ gx, const int* __restrict__
   const uint64_t seed = seed0 + (d_step ? (uint64_t)(uint32_t)__ldg(d_step) : 0ull);
   // grid (L, splits): CTA (p, s) sums the rows of chunk s that have position p into partial slot s.
   // blockDim = (ceil32(d), PG_LANES): thread (c, k) sums rows lo+k, lo+k+PG_LANES, ...; lanes reduced in fixed order.
+  // (Round 2 tried eight rows per trip and ten positions per CTA with the row lengths fetched once: 23 us and 34 us in the
+  // step against 16-19 us for this form -- the tail kernels run beside the last weight-gradient CTAs, and what a variant
+  // gains in dependent trips it loses to registers / shared memory that no longer fit beside them.)
   __shared__ float part[PG_LANES][256];
   const int p = blockIdx.x, c = threadIdx.x, k = threadIdx.y;
   const int chunk = (M + gridDim.y - 1) / gridDim.y;
@@ -821,31 +836,49 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ ke
 // Every row is therefore a fixed function of the sorted order: deterministic, and a 230-occurrence item costs two
 // dependent batches instead of fifteen.
 constexpr int SW = 16;
+static_assert(SW == 16, "k_seg_bounds (scatter plan) is written for windows of 16 positions");
 constexpr int SPAD = 160 > LN_MAXE * 32 ? 160 : LN_MAXE * 32;      // floats per partial slot
+// Plan: for every window of SW sorted positions, where the segment of its FIRST run starts (if that run continues from the
+// previous window) and where the segment of its LAST run ends (if it continues into the next window).  Warp per window.
+__global__ void __launch_bounds__(256) k_seg_bounds(const int* __restrict__ keys, const int* __restrict__ dT, int2* __restrict__ bounds) {
+  const int T = *dT;
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int p0 = w * 16;
+  if (p0 >= T) return;
+  const int n = min(16, T - p0);
+  const int kf = keys[p0], kl = keys[p0 + n - 1];
+  int head = p0, end = p0 + n;
+  if (p0 > 0 && keys[p0 - 1] == kf) {                            // last position before p0 with another id, + 1
+    for (int base = p0 - 32;; base -= 32) {
+      const int q = base + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, q < 0 || keys[q] != kf);
+      if (m) { head = base + (31 - __clz(m)) + 1; break; }
+    }
+  }
+  if (p0 + n < T && keys[p0 + n] == kl) {                        // segment end (exclusive)
+    for (int base = p0 + n;; base += 32) {
+      const int q = base + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, q >= T || keys[q] != kl);
+      if (m) { end = base + __ffs(m) - 1; break; }
+    }
+  }
+  if (lane == 0) bounds[w] = make_int2(head, end);
+}
+
 // A run that is a PIECE of a longer segment (a hot item spanning several windows): rare, and kept out of line -- inlined
 // into the 16-fold unrolled window loop it made the kernel 139 KB of code, most of which was only ever jumped over.
 template <int NEL>
 __device__ __noinline__ void scatter_piece(const int* __restrict__ keys, int T, int p0, int n, int w, int lane, int ku, int run_start, int u,
                                            bool cont_before, bool cont_after, const float (&acc)[NEL], float* __restrict__ gtable, int d,
-                                           float scale, float* __restrict__ part, int* __restrict__ counter) {
+                                           float scale, float* __restrict__ part, int* __restrict__ counter, const int2* __restrict__ bounds) {
           float* mine = part + ((long long)w * 2 + (cont_before ? 0 : 1)) * SPAD;
 #pragma unroll
           for (int i = 0; i < NEL; ++i) mine[lane + 32 * i] = acc[i];
+          // where the segment starts / ends was worked out by the plan (k_seg_bounds, off the critical path): a hot item of
+          // 230 occurrences used to cost every one of its windows ~8 dependent key loads in each direction here
           int head = p0 + run_start, end = p0 + u + 1;
-          if (cont_before) {                                       // segment head: last position before p0 with another id, + 1
-            for (int base = p0 - 32;; base -= 32) {
-              const int q = base + lane;
-              const unsigned m = __ballot_sync(0xffffffffu, q < 0 || keys[q] != ku);
-              if (m) { head = base + (31 - __clz(m)) + 1; break; }
-            }
-          }
-          if (cont_after) {                                        // segment end (exclusive)
-            for (int base = p0 + n;; base += 32) {
-              const int q = base + lane;
-              const unsigned m = __ballot_sync(0xffffffffu, q >= T || keys[q] != ku);
-              if (m) { end = base + __ffs(m) - 1; break; }
-            }
-          }
+          if (cont_before) head = bounds[w].x;
+          if (cont_after) end = bounds[w].y;
           const int w1 = head / SW, w2 = (end - 1) / SW;
           __threadfence();
           __syncwarp();
@@ -880,7 +913,8 @@ __device__ __noinline__ void scatter_piece(const int* __restrict__ keys, int T, 
 template <int NEL>
 __global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ keys, const int* __restrict__ vals,
                                                        const int* __restrict__ dT, const float* __restrict__ gx, int d, float scale,
-                                                       float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter) {
+                                                       float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter,
+                                                       const int2* __restrict__ bounds) {
   const int T = *dT;
   const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const int p0 = w * SW;
@@ -917,12 +951,75 @@ __global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ k
 #pragma unroll
           for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
         } else {
-          scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter);
+          scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
         }
 #pragma unroll
         for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
         run_start = u + 1;
       }
+    }
+  }
+}
+
+// Shared-memory form of the windowed reduction (opt-in: ADER_B200_SCATTER=2; measured equal to slightly slower in the step:
+// its 40 KB of shared memory do not fit beside the weight-gradient CTAs the tail runs next to).  k_scatter_apply
+// keeps a window's 16 gradient rows in registers, which forces the 16-step run loop to be unrolled: 49 KB of straight-line
+// code that every warp executes exactly once -- the kernel (30 CTAs, on the tail of the step) was bound by instruction
+// fetch, not by its three dependent memory trips.  Here the rows go to shared memory with cp.async (one batch, no register
+// staging) and the run loop is a real loop over the window: a few hundred instructions.  Same sums in the same order.
+constexpr int SW2_WARPS = 4;
+template <int NEL>
+__global__ void __launch_bounds__(SW2_WARPS * 32) k_scatter_apply2(const int* __restrict__ keys, const int* __restrict__ vals,
+                                                                   const int* __restrict__ dT, const float* __restrict__ gx, int d, float scale,
+                                                                   float* __restrict__ gtable, float* __restrict__ part, int* __restrict__ counter,
+                                                       const int2* __restrict__ bounds) {
+  __shared__ float rows[SW2_WARPS][SW][NEL * 32];
+  const int T = *dT;
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int p0 = w * SW;
+  if (p0 >= T) return;
+  float (*my)[NEL * 32] = rows[threadIdx.x >> 5];
+  const int n = min(SW, T - p0);
+  const int key_l = (lane < n) ? keys[p0 + lane] : -1;
+  const int val_l = (lane < n) ? vals[p0 + lane] : 0;
+  const int key_prev = (p0 > 0) ? keys[p0 - 1] : -1;
+  const int key_next = (p0 + n < T) ? keys[p0 + n] : -1;
+#pragma unroll 1
+  for (int u = 0; u < n; ++u) {
+    const long long o = (long long)__shfl_sync(0xffffffffu, val_l, u) * d;
+#pragma unroll
+    for (int i = 0; i < NEL; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = c < d;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&my[u][c])),
+                   "l"(ok ? gx + o + c : gx), "r"(ok ? 4 : 0) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  float acc[NEL];
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+  int run_start = 0;
+#pragma unroll 1
+  for (int u = 0; u < n; ++u) {
+    const int ku = __shfl_sync(0xffffffffu, key_l, u);
+    const int kn = __shfl_sync(0xffffffffu, key_l, (u + 1) & 31);
+#pragma unroll
+    for (int i = 0; i < NEL; ++i) acc[i] += my[u][lane + 32 * i];
+    const bool last_in_window = (u + 1 == n);
+    if (last_in_window || kn != ku) {                              // the run [run_start, u] of item ku ends here
+      const bool cont_after = last_in_window && key_next == ku;
+      const bool cont_before = run_start == 0 && key_prev == ku;
+      if (!cont_after && !cont_before) {
+#pragma unroll
+        for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
+      } else {
+        scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
+      }
+#pragma unroll
+      for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
+      run_start = u + 1;
     }
   }
 }
@@ -1038,6 +1135,7 @@ static int run_scatter_plan(const AderModel* m, const EncWs& w, const BwdWs& g, 
     k_sort_scatter<<<ntiles, 256, 0, st>>>(kin, vin, dT, shift, ntiles, g.hist, pass == 0, g.keys[cur], g.vals[cur]);
     kin = g.keys[cur]; vin = g.vals[cur]; cur ^= 1;
   }
+  k_seg_bounds<<<cdiv((long long)n_count * 32, 256), 256, 0, st>>>(kin, dT, g.sbounds);
   ADER_CHECK_LAUNCH("scatter plan");
   return 0;
 }
@@ -1046,11 +1144,19 @@ static int run_scatter_apply(const AderModel* m, const Layout& l, const EncWs& w
   const int d = m->d;
   const int* dT = w.row_off + M;
   const int fin = (sort_passes(m) - 1) & 1;
+  static int gen = -1;
+  if (gen < 0) { const char* e = getenv("ADER_B200_SCATTER"); gen = (e && e[0] == '2') ? 2 : 1; }
+  if (gen == 2 && d <= 160) {        // rows staged in shared memory, rolled run loop (40 KB static shared memory per CTA): opt-in
+    k_scatter_apply2<5><<<cdiv(cdiv(Tcap, SW), SW2_WARPS), SW2_WARPS * 32, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d),
+                                                                                   grad + l.off_table, g.spart, g.scount, g.sbounds);
+    ADER_CHECK_LAUNCH("scatter apply");
+    return 0;
+  }
   const int grid = cdiv((long long)cdiv(Tcap, SW) * 32, 256);
   if (d <= 160)
-    k_scatter_apply<5><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount);
+    k_scatter_apply<5><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount, g.sbounds);
   else
-    k_scatter_apply<LN_MAXE><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount);
+    k_scatter_apply<LN_MAXE><<<grid, 256, 0, st>>>(g.keys[fin], g.vals[fin], dT, gX, d, sqrtf((float)d), grad + l.off_table, g.spart, g.scount, g.sbounds);
   ADER_CHECK_LAUNCH("scatter apply");
   return 0;
 }

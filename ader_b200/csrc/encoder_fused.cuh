@@ -1402,7 +1402,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ Wgrad
 // tile (25 600 8-byte cp.async per CTA: issue-bound), 1.35 us per 32-token tile (tensor pipe 0.92), 2.75 us for the
 // fragment-scattered partial stores.  Here
 //   * a tile operand is ONE cp.async.bulk of the contiguous [32 tokens][d] block (19 200 B) completing on an mbarrier, the
-//     whole token range of the CTA in flight from the start;
+//     next tile in flight behind the one being multiplied (ring depth: see WG2_NST);
 //   * shared-memory rows keep the global stride d, and the k slots of a k-step are mapped to tile rows so that the four
 //     rows one fragment load touches are 4 apart (4 * 150 = 24 mod 32 banks): conflict-free without padding.  Summation
 //     over k does not care which token sits in which slot as long as A and B agree;
@@ -1413,11 +1413,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad(const __grid_constant__ Wgrad
 // Same token splits and the same fixed-order reduction afterwards: deterministic; bias and LayerNorm-parameter sums keep
 // their exact order (bit-identical to k_wgrad), the weight products differ in the order of additions inside a k-step only.
 constexpr int WG2_THR = 128;
-constexpr int WG2_NST = 5;
+// ring depth (-DADER_WG2_NST=n): measured in the step on one box, 200 graph replays each, two runs per depth
+// (profiles/r2b/wgrad2_ring_depth.txt): 5 stages (205 KB) 0.2807 / 0.2804 ms, 3 stages (123 KB) 0.2799 / 0.2801,
+// 2 stages (82 KB) 0.2789 / 0.2780 (end to end 0.289 against 0.294).  Small but repeatable: the kernel runs beside the
+// data-gradient chain, where a smaller footprint packs better than an earlier first tile
+#ifndef ADER_WG2_NST
+#define ADER_WG2_NST 2
+#endif
+constexpr int WG2_NST = ADER_WG2_NST;
 constexpr int WG2_OPB = WG_TK * KP * 4;                      // bytes of one operand slot (d <= 160)
 constexpr int WG2_STG_LD = 88;                               // staging row stride of the 160 x 80 result block
 constexpr size_t WGRAD2_SMEM = (size_t)WG2_NST * 2 * WG2_OPB + 64;
-static_assert(160 * WG2_STG_LD * 4 <= WG2_NST * 2 * WG2_OPB, "result staging must fit the ring");
+static_assert(160 * WG2_STG_LD * 4 <= WG2_NST * 2 * WG2_OPB, "result staging must fit the ring");    // 56 320 B: two stages suffice
 
 __global__ void __launch_bounds__(WG2_THR) k_wgrad2(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(128) float wsm[];
