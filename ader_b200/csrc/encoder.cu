@@ -136,6 +136,64 @@ __global__ void __launch_bounds__(1024) k_scan_rows(const int* __restrict__ row_
   }
 }
 
+// The three packing kernels above as ONE single-CTA kernel for batches of up to 1024 rows: the id matrix is staged in shared
+// memory with one coalesced pass, lengths / offsets / token lists come from there.  Same integers.  Opt-in
+// (ADER_B200_PACK=1), because it is SLOWER in the step: 0.2818 / 0.2820 ms against 0.2765 / 0.2759 for the three launches
+// (same box, alternating runs) -- one SM pulling 130 KB through its own L2 port and walking 650 rows with 32 warps takes
+// longer than three 3 us kernels spread over the chip, launch gaps included.
+constexpr int PACK1_THR = 1024;
+__global__ void __launch_bounds__(PACK1_THR) k_pack_small(const int* __restrict__ ids, int M, int L, int Tcap, int* __restrict__ row_len,
+                                                          int* __restrict__ row_off, int* __restrict__ tok_row, int* __restrict__ tok_id,
+                                                          int* __restrict__ flags) {
+  extern __shared__ int pk_sm[];
+  int* ids_s = pk_sm;                       // [M * L]
+  int* len_s = ids_s + M * L;               // [1024]
+  int* off_s = len_s + PACK1_THR;           // [1024]
+  __shared__ int warp_sum[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < N_WS_FLAGS; i += PACK1_THR) flags[i] = 0;
+  for (int i = tid; i < M * L; i += PACK1_THR) ids_s[i] = ids[i];
+  __syncthreads();
+  for (int r = wid; r < M; r += PACK1_THR / 32) {        // row lengths: warp per row
+    int c = 0;
+    for (int j = lane; j < L; j += 32) c += (ids_s[r * L + j] != 0);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) { len_s[r] = c; row_len[r] = c; }
+  }
+  __syncthreads();
+  const int v = (tid < M) ? len_s[tid] : 0;              // exclusive scan over the rows (M <= 1024: one element per thread)
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_sum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+    warp_sum[lane] = t;
+  }
+  __syncthreads();
+  const int excl = (wid ? warp_sum[wid - 1] : 0) + x - v;
+  if (tid < M) { off_s[tid] = excl; row_off[tid] = excl; }
+  if (tid == 0) {
+    int T = warp_sum[31];
+    if (T > Tcap) { flags[0] = T; T = Tcap; }            // overflow: checked by the host (ader_b200/model.py)
+    row_off[M] = T;
+  }
+  __syncthreads();
+  for (int r = wid; r < M; r += PACK1_THR / 32) {        // token lists: real tokens are the suffix (util.py:161-169)
+    const int n = len_s[r], off = off_s[r];
+    for (int i = lane; i < n; i += 32) {
+      if (off + i < Tcap) {
+        tok_row[off + i] = r;
+        tok_id[off + i] = ids_s[r * L + (L - n + i)];
+      }
+    }
+  }
+}
+
 __global__ void k_fill_tok(const int* __restrict__ ids, const int* __restrict__ row_len,
                            const int* __restrict__ row_off, int M, int L, int Tcap,
                            int* __restrict__ tok_row, int* __restrict__ tok_id) {
@@ -1067,6 +1125,23 @@ namespace ader {
 // ------------------------------------------------------------------------------------------
 // group entry points
 // ------------------------------------------------------------------------------------------
+// packed token lists of a batch (row_len, row_off, tok_row, tok_id): three small launches; ADER_B200_PACK=1 selects the
+// single-CTA kernel for batches of up to 1024 rows (measured slower, see k_pack_small)
+static void launch_pack_tokens(const int32_t* ids, int M, int L, int Tcap, const EncWs& w, cudaStream_t st) {
+  static int three = -1;
+  if (three < 0) {
+    const char* e = getenv("ADER_B200_PACK"); three = (e && e[0] == '1') ? 0 : 1;
+    cudaFuncSetAttribute(k_pack_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+  }
+  const size_t smem = sizeof(int) * ((size_t)M * L + 2 * PACK1_THR);
+  if (!three && M <= PACK1_THR && smem <= 216 * 1024) {
+    k_pack_small<<<1, PACK1_THR, smem, st>>>(ids, M, L, Tcap, w.row_len, w.row_off, w.tok_row, w.tok_id, w.flags);
+    return;
+  }
+  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len, w.flags);
+  k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
+  k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
+}
 static int run_dense(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
                      int Tcap, const int* dT, int d, bool transW, int relu, const float* resid,
                      const float* relu_mask, int accumulate, float alpha,
@@ -1221,9 +1296,7 @@ extern "C" int32_t ader_encoder_fwd(const AderModel* m, const float* theta, cons
   EncWs w = carve_enc(m, M, Tcap, (char*)ws);
   const int* dT = w.row_off + M;
 
-  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len, w.flags);
-  k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
-  k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
+  launch_pack_tokens(ids, M, L, Tcap, w, st);
   k_embed<<<cdiv((long long)Tcap * d, 256), 256, 0, st>>>(theta + l.off_table, theta + l.off_pos, w.tok_row, w.tok_id,
                                                            w.row_len, w.row_off, dT, d, L, sqrtf((float)d),
                                                            dropout_rate, seed, w.slot[0][0]);
@@ -1745,9 +1818,7 @@ int ader::enc_fwd_tc_run(const AderModel* m, const float* theta, const int32_t* 
   // weight shadows depend on theta only: off the packing chain (joined before the first tile kernel)
   f.edge(st, f.a);
   fz::k_pack_weights<<<dim3(m->num_blocks * 5, fz::KP / fz::PACK_BAND), 256, 0, f.a>>>(theta, l, (fz::op_t*)w.wshadow);
-  k_row_len<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, M, L, w.row_len, w.flags);
-  k_scan_rows<<<1, 1024, 0, st>>>(w.row_len, M, Tcap, w.row_off, w.flags);
-  k_fill_tok<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(ids, w.row_len, w.row_off, M, L, Tcap, w.tok_row, w.tok_id);
+  launch_pack_tokens(ids, M, L, Tcap, w, st);
   ADER_CHECK_LAUNCH("encoder_fwd_tc/pack");
   if (f.parallel()) { f.tok_ready = f.take(); cudaEventRecord(f.tok_ready, st); f.has_tok_ready = true; }
   f.edge(f.a, st);
