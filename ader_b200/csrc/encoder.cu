@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(256) k_seg_bounds(const int* __restrict__ keys
 // A run that is a PIECE of a longer segment (a hot item spanning several windows): rare, and kept out of line -- inlined
 // into the 16-fold unrolled window loop it made the kernel 139 KB of code, most of which was only ever jumped over.
 template <int NEL>
-__device__ __noinline__ void scatter_piece(const int* __restrict__ keys, int T, int p0, int n, int w, int lane, int ku, int run_start, int u,
+__device__ __noinline__ void scatter_piece(int p0, int w, int lane, int ku, int run_start, int u,
                                            bool cont_before, bool cont_after, const float (&acc)[NEL], float* __restrict__ gtable, int d,
                                            float scale, float* __restrict__ part, int* __restrict__ counter, const int2* __restrict__ bounds) {
           float* mine = part + ((long long)w * 2 + (cont_before ? 0 : 1)) * SPAD;
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(256) k_scatter_apply(const int* __restrict__ k
 #pragma unroll
           for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
         } else {
-          scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
+          scatter_piece<NEL>(p0, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
         }
 #pragma unroll
         for (int i = 0; i < NEL; ++i) acc[i] = 0.f;
@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(SW2_WARPS * 32) k_scatter_apply2(const int* __
 #pragma unroll
         for (int i = 0; i < NEL; ++i) { const int c = lane + 32 * i; if (c < d) atomicAdd(gtable + (long long)ku * d + c, scale * acc[i]); }
       } else {
-        scatter_piece<NEL>(keys, T, p0, n, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
+        scatter_piece<NEL>(p0, w, lane, ku, run_start, u, cont_before, cont_after, acc, gtable, d, scale, part, counter, bounds);
       }
 #pragma unroll
       for (int i = 0; i < NEL; ++i) acc[i] = 0.f;

@@ -1441,7 +1441,6 @@ __global__ void __launch_bounds__(WG2_THR) k_wgrad2(const __grid_constant__ Wgra
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp & 1, wn = warp >> 1;           // warp block: rows wm*80.., columns half*80 + wn*40..
   const uint32_t bar0 = smem_u32(reinterpret_cast<char*>(wsm) + (size_t)WG2_NST * 2 * WG2_OPB);
-  const uint32_t op_bytes_full = (uint32_t)(WG_TK * d * 4);
   auto issue = [&](int li) {                         // thread 0: both operands of local tile li into stage li % NST
     const int t0 = (tile_lo + li) * WG_TK;
     const int rv = min(WG_TK, T - t0) & ~1;          // bulk copies move whole 16-byte units: an even number of rows
@@ -1467,7 +1466,6 @@ __global__ void __launch_bounds__(WG2_THR) k_wgrad2(const __grid_constant__ Wgra
     for (int j = 0; j < 5; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
   float cs0[2] = {0.f, 0.f}, cs1[2] = {0.f, 0.f};    // GEMM: [0] = bias column half*80 + tid (tid < 80); LN: columns tid, tid + 128
   __syncthreads();                                   // barrier words initialised before anyone waits on them
-  (void)op_bytes_full;
 #pragma unroll 1
   for (int li = 0; li < n_my; ++li) {
     const int s = li % WG2_NST;
