@@ -673,6 +673,23 @@ def gpu_arm(args):
                 traffic = tr["dram_bytes_per_step"]
         except Exception:
             pass
+        # the kernel that dominates the step BY TIME is not the north-star kernel: the weight-gradient launches (TF32 legacy
+        # mma.sync).  Algorithmic work 2 * T * d * d per matrix, 5 matrices per block; in-pipeline durations from the CUPTI pass
+        # above; peak = the probe-measured mma.sync rate (profiles/r2/hmma_probe.txt: 0.45 m16n8k8 per cycle per SM)
+        dominant = None
+        try:
+            wname = max((k for k in kernels_us if "k_wgrad" in k), key=lambda k: kernels_us[k])
+            t_mean = float(np.mean(ntok[W:W + 10]))
+            wflops = 2.0 * t_mean * 150 * 150 * 5 * 2
+            sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+            wpeak = 0.45 * 2048 * 148 * sm_mhz * 1e6 / 1e12
+            wach = wflops / (kernels_us[wname] * 1e-6) / 1e12
+            dominant = {"kernel": wname + " (all launches of a step, in-pipeline durations)", "bound": "tensor (legacy mma.sync tf32)",
+                        "achieved": wach, "peak": wpeak, "unit": "TFLOP/s", "frac": wach / wpeak,
+                        "us_per_step": kernels_us[wname], "algorithmic_flops_per_step": wflops,
+                        "peak_source": "hmma_probe: 0.45 mma.m16n8k8 per cycle per SM x 148 SMs x sm clock"}
+        except Exception:
+            pass
         big = WL["V"] > 200000        # the CPU restatement materialises [M, V] fp32 logits + a one-hot: 40 GB at 1M items
         cpu_val, cpu_ms, cores, _ = (None, None, None, None) if big else run_cpu(2, 1)
         period = components = cpu_comp = None
@@ -712,6 +729,7 @@ def gpu_arm(args):
                              "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_flops_per_launch": flops,
                              "group_achieved": flops / (loss_group_ms * 1e-3) / 1e12 if loss_group_ms else None},
+                "roofline_step_dominant": dominant,
                 "cpu_baseline": None if big else
                                 {"value": cpu_val, "unit": "sessions/s", "cores": cores, "kind": "port",
                                  "sample": "2 full steps of %d rows after 1 warm-up, torch-CPU fp32 restatement" % M}}

@@ -1,8 +1,8 @@
 """Executable model of the windowed embedding-gradient scatter (ader_b200/csrc/encoder.cu: k_scatter_apply) on CPU.
 
 The CUDA kernel is checked against the oracle on the GPU (tests/test_gpu_parity.py); this file pins the ALGORITHM it
-implements -- window / run / piece bookkeeping, head and end probing, which slot a piece is parked in, who combines the
-pieces and in which order -- on the edge cases a GPU batch rarely hits: segments that end exactly on a window edge,
+implements -- window / run / piece bookkeeping, the segment bounds the plan works out per window (k_seg_bounds: head and
+end probing), which slot a piece is parked in, who combines the pieces and in which order -- on the edge cases a GPU batch rarely hits: segments that end exactly on a window edge,
 windows that lie completely inside one segment, a last window shorter than 16, one token, one item for every token.
 The model walks the sorted (item id, token) pairs exactly like a warp does and must (a) reproduce a plain scatter-add
 up to fp32 re-association, (b) touch every table row exactly once (the kernel's single-contributor reduction), (c) give
@@ -19,6 +19,40 @@ def _stable_sort(ids):
     return ids[order].astype(np.int64), order.astype(np.int64)
 
 
+def seg_bounds_model(keys):
+    """k_seg_bounds (scatter plan, a warp per window): bounds[w] = (head of the segment of the window's FIRST run if that run
+    continues from the previous window, else p0; end (exclusive) of the segment of its LAST run if it continues into the next
+    window, else p0 + n).  Probes in steps of 32 positions like the warp's ballots."""
+    T = len(keys)
+    n_win = (T + SW - 1) // SW
+    bounds = np.zeros((n_win, 2), np.int64)
+    for w in range(n_win):
+        p0 = w * SW
+        n = min(SW, T - p0)
+        kf, kl = keys[p0], keys[p0 + n - 1]
+        head, end = p0, p0 + n
+        if p0 > 0 and keys[p0 - 1] == kf:
+            base = p0 - 32
+            while True:
+                q = np.arange(base, base + 32)
+                diff = (q < 0) | (keys[np.clip(q, 0, T - 1)] != kf)
+                if diff.any():
+                    head = base + int(np.flatnonzero(diff).max()) + 1
+                    break
+                base -= 32
+        if p0 + n < T and keys[p0 + n] == kl:
+            base = p0 + n
+            while True:
+                q = np.arange(base, base + 32)
+                diff = (q >= T) | (keys[np.clip(q, 0, T - 1)] != kl)
+                if diff.any():
+                    end = base + int(np.flatnonzero(diff).min())
+                    break
+                base += 32
+        bounds[w] = (head, end)
+    return bounds
+
+
 def scatter_model(ids, gx, n_rows, scale, window_order=None):
     """Returns (table [n_rows, d] fp32, writes per row, combines per spanning segment head-window)."""
     keys, vals = _stable_sort(np.asarray(ids))
@@ -29,6 +63,7 @@ def scatter_model(ids, gx, n_rows, scale, window_order=None):
     part = np.full((n_win, 2, d), np.nan, np.float32)            # partial slots; NaN = never written
     counter = np.zeros(n_win, np.int64)
     combines = {}
+    bounds = seg_bounds_model(keys)
     windows = list(range(n_win)) if window_order is None else list(window_order)
     for w in windows:                                              # any order: warps run concurrently
         p0 = w * SW
@@ -50,24 +85,10 @@ def scatter_model(ids, gx, n_rows, scale, window_order=None):
                 else:
                     part[w, 0 if cont_before else 1] = acc
                     head, end = p0 + run_start, p0 + u + 1
-                    if cont_before:                                 # probe backwards in steps of 32 like the warp
-                        base = p0 - 32
-                        while True:
-                            q = np.arange(base, base + 32)
-                            diff = (q < 0) | (keys[np.clip(q, 0, T - 1)] != ku)
-                            if diff.any():
-                                head = base + int(np.flatnonzero(diff).max()) + 1
-                                break
-                            base -= 32
+                    if cont_before:                                 # the plan's bounds (k_seg_bounds), not a probe here
+                        head = int(bounds[w, 0])
                     if cont_after:
-                        base = p0 + n
-                        while True:
-                            q = np.arange(base, base + 32)
-                            diff = (q >= T) | (keys[np.clip(q, 0, T - 1)] != ku)
-                            if diff.any():
-                                end = base + int(np.flatnonzero(diff).min())
-                                break
-                            base += 32
+                        end = int(bounds[w, 1])
                     assert keys[head] == ku and (head == 0 or keys[head - 1] != ku)
                     assert keys[end - 1] == ku and (end == T or keys[end] != ku)
                     w1, w2 = head // SW, (end - 1) // SW
@@ -139,3 +160,22 @@ def test_windowed_scatter_random_batches_and_arrival_orders():
             order = rng.permutation(n_win)
             again, _, _ = scatter_model(ids, gx, vmax + 1, 3.0, window_order=order)
             assert np.array_equal(base, again)
+
+
+def test_segment_bounds_of_the_plan():
+    """bounds[w] against a direct computation from the run-length structure of the sorted keys."""
+    rng = np.random.RandomState(11)
+    for trial in range(40):
+        T = int(rng.randint(1, 500))
+        vmax = int(rng.choice([1, 2, 3, 30]))
+        keys = np.sort(rng.randint(1, vmax + 1, T)).astype(np.int64)
+        change = np.flatnonzero(np.diff(keys)) + 1
+        starts = np.concatenate([[0], change]); ends = np.concatenate([change, [T]])
+        seg_of = np.repeat(np.arange(len(starts)), ends - starts)
+        b = seg_bounds_model(keys)
+        for w in range(len(b)):
+            p0 = w * SW; n = min(SW, T - p0)
+            first, last = seg_of[p0], seg_of[p0 + n - 1]
+            want_head = starts[first] if (p0 > 0 and keys[p0 - 1] == keys[p0]) else p0
+            want_end = ends[last] if (p0 + n < T and keys[p0 + n] == keys[p0 + n - 1]) else p0 + n
+            assert (b[w, 0], b[w, 1]) == (want_head, want_end), (trial, w)
