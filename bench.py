@@ -56,6 +56,8 @@ def synth_rows(rng, n, vmax, L=50):
     p = np.array(LEN_HIST[1:], np.float64)
     p /= p.sum()
     lens = rng.choice(np.arange(1, L + 1), size=n, p=p)
+    if WL.get("full_len"):          # SURVEY 8(d) "seq len 50" variant: every slot of every row filled
+        lens = np.full(n, L, dtype=lens.dtype)
     ids = np.zeros((n, L), np.int32)
     # item popularity ~ Zipf-like over 1..vmax (hot rows exercise the scatter)
     u = rng.random_sample((n, L))
@@ -754,11 +756,14 @@ def main():
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="issue the step's launches eagerly")
     ap.add_argument("--no-period", dest="no_period", action="store_true",
                     help="skip the real-period run on the shipped split and the component figures (N = 1 only)")
-    ap.add_argument("--config", default="yoochoose_p4", choices=["yoochoose_p4", "synthetic1m"],
-                    help="workload: BASELINE configs[1] shape (default, the headline) or configs[4] (1M-item vocabulary)")
+    ap.add_argument("--config", default="yoochoose_p4", choices=["yoochoose_p4", "synthetic1m", "synthetic1m_full"],
+                    help="workload: BASELINE configs[1] shape (default, the headline) or configs[4] (1M-item vocabulary; session "
+                         "lengths from the YOOCHOOSE histogram, or _full: all 50 slots of every row filled)")
     args = ap.parse_args()
-    if args.config == "synthetic1m":
+    if args.config.startswith("synthetic1m"):
         WL.update(WL_SYNTH1M)
+        if args.config.endswith("_full"):
+            WL.update(full_len=True, name=WL_SYNTH1M["name"] + ", all 50 slots filled")
     if args.impl == "reference":
         reference_arm(args)
     else:
